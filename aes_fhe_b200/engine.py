@@ -1,0 +1,552 @@
+"""`desilofhe`-compatible CKKS engine facade (host logic only).
+
+This is the drop-in boundary of the hot path: the reference's Python services call
+exactly these members of ``desilofhe.Engine`` (call sites
+/root/reference/engine_context.py:28-85, xor_service.py:59-129, sbox/sbox_service.py:85-138,
+gf_service.py:44-64, new.py:94-146, shiftrows_service.py:30-68).  The facade keeps the
+level / scale bookkeeping, key objects and operand normalisation in Python and hands
+every polynomial operation to a *backend*:
+
+* product: :class:`aes_fhe_b200.backend_cuda.CudaBackend` -- hand-written sm_100a
+  kernels behind the C-ABI in ``include/aesfhe_b200.h``.  It is the only backend this
+  package ships and the default; constructing an Engine without the built CUDA library
+  or without a GPU raises.
+* tests / CPU baseline only: ``oracle.refmod.RefBackend`` is injected explicitly by
+  ``tests/`` and ``bench.py`` to obtain the bit-exact residues the kernels must match.
+
+Ciphertext layout: ``polys`` is ``[npoly, level+1, N]`` 64-bit residues in the NTT
+(evaluation) domain, bit-reversed spectrum order, canonical [0, q).
+"""
+from __future__ import annotations
+
+from fractions import Fraction
+from typing import Any, Dict, List, Optional, Sequence
+
+import numpy as np
+
+from . import encoding
+from .params import CKKSParams, make_params, sqrt_minus_one
+
+_SIGMA = 3.2
+
+
+class Plaintext:
+    """Level-agnostic plaintext: slot values plus a per-level cache of encodings.
+
+    The reference encodes a plaintext once (``engine.encode``) and then multiplies it
+    into ciphertexts at many different levels (/root/reference/xor_service.py:184-196,
+    :283-285), so the residues are produced lazily for the level they are used at.
+    """
+
+    def __init__(self, engine: "Engine", values: np.ndarray):
+        self.engine = engine
+        v = np.asarray(values)
+        if v.ndim == 0:
+            v = v.reshape(1)
+        self.values = v.astype(np.complex128 if np.iscomplexobj(v) else np.float64).ravel()
+        self.const = encoding.as_constant(self.values) if self.values.size == engine.slot_count else None
+        self._cache: Dict[int, Any] = {}
+
+    def at_level(self, level: int):
+        h = self._cache.get(level)
+        if h is None:
+            eng = self.engine
+            coeffs = encoding.encode_i64(self.values, eng.params.scale(level), eng.params.log_n)
+            h = eng.backend.from_i64(coeffs, level + 1, False)
+            self._cache[level] = h
+        return h
+
+
+class Ciphertext:
+    def __init__(self, engine: "Engine", polys, level: int, zero: bool = False):
+        self.engine = engine
+        self.polys = polys
+        self._level = level
+        self.zero = zero
+
+    @property
+    def level(self) -> int:
+        """Remaining multiplicative levels (the reference compares it with 8:
+        /root/reference/xor_service.py:274-277)."""
+        return self._level
+
+    @property
+    def npoly(self) -> int:
+        return self.engine.backend.npoly(self.polys)
+
+    def __repr__(self):
+        return f"Ciphertext(level={self._level}, npoly={self.npoly})"
+
+
+class SecretKey:
+    def __init__(self, coeffs: np.ndarray, ntt_full):
+        self.coeffs = coeffs          # int64 ternary, length N
+        self.ntt = ntt_full           # [1, n_q+n_p, N]
+
+
+class PublicKey:
+    def __init__(self, polys):
+        self.polys = polys            # [2, n_q, N]
+
+
+class SwitchKey:
+    """Hybrid key-switching key  [dnum, 2, n_q+n_p, N]."""
+
+    def __init__(self, data, galois: Optional[int] = None):
+        self.data = data
+        self.galois = galois
+
+
+class RelinearizationKey(SwitchKey):
+    pass
+
+
+class ConjugationKey(SwitchKey):
+    pass
+
+
+class FixedRotationKey(SwitchKey):
+    def __init__(self, data, galois, delta):
+        super().__init__(data, galois)
+        self.delta = delta
+
+
+class RotationKey:
+    """Power-of-two rotation keys (+-2^k); arbitrary deltas are composed in NAF form."""
+
+    def __init__(self, keys: Dict[int, FixedRotationKey]):
+        self.keys = keys
+
+
+class BootstrapKey:
+    """Placeholder: bootstrapping is not built yet."""
+
+    def __init__(self, small: bool):
+        self.small = small
+
+
+def _naf_steps(delta: int, slot_count: int) -> List[int]:
+    """Signed power-of-two decomposition of a rotation amount (shortest of +-)."""
+    d = delta % slot_count
+    if d > slot_count // 2:
+        d -= slot_count
+    steps, k, x = [], 0, abs(d)
+    sign = 1 if d >= 0 else -1
+    while x:
+        if x & 1:
+            digit = 2 - (x & 3)          # +1 or -1
+            steps.append(sign * digit * (1 << k))
+            x -= digit
+        x >>= 1
+        k += 1
+    return steps
+
+
+class Engine:
+    """Same three constructor signatures as ``desilofhe.Engine``
+    (/root/reference/engine_context.py:28-56)."""
+
+    def __init__(self, *args, mode: str = 'cpu', use_bootstrap: bool = False,
+                 use_multiparty: bool = False, thread_count: int = 0, device_id: int = 0,
+                 max_level: Optional[int] = None, log_coeff_count: Optional[int] = None,
+                 special_prime_count: Optional[int] = None, seed: int = 0,
+                 _backend=None, _params: Optional[CKKSParams] = None):
+        args = list(args)
+        # positional forms: Engine(mode) | Engine(max_level, mode) | Engine(log_n, K, mode)
+        if len(args) >= 1 and isinstance(args[0], str):
+            mode = args.pop(0)
+        ints = [a for a in args if isinstance(a, (int, np.integer))]
+        strs = [a for a in args if isinstance(a, str)]
+        if strs:
+            mode = strs[0]
+        if len(ints) == 1 and max_level is None:
+            max_level = int(ints[0])
+        elif len(ints) >= 2:
+            log_coeff_count, special_prime_count = int(ints[0]), int(ints[1])
+        if use_multiparty:
+            raise NotImplementedError("multiparty CKKS is outside the hot path (SURVEY.md section 8)")
+        if mode not in ('cpu', 'parallel', 'gpu'):
+            raise ValueError(f"unknown mode {mode!r}")
+        self.mode = mode
+        self.use_bootstrap = bool(use_bootstrap)
+        self.thread_count = thread_count
+        self.device_id = device_id
+
+        if _params is not None:
+            params = _params
+        elif log_coeff_count is not None:
+            log_n = int(log_coeff_count)
+            k = int(special_prime_count or 0)
+            # depth the modulus budget allows at this ring size (about 27*2^(log_n-10) bits)
+            budget = 27 * (1 << (log_n - 10)) + 16
+            lvl = max(1, min(30, (budget - 60 - 60 * max(k, 1)) // 40))
+            params = make_params(log_n, lvl, special_count=k)
+        else:
+            params = make_params(16, int(max_level) if max_level is not None else 30)
+        self.params = params
+        self.slot_count = params.slot_count
+        self.max_level = params.max_level
+
+        if _backend is None:
+            from .backend_cuda import CudaBackend      # raises if the CUDA library / GPU is missing
+            _backend = CudaBackend(params, device_id=device_id)
+        elif isinstance(_backend, type):
+            _backend = _backend(params)
+        self.backend = _backend
+        self._rng = np.random.Generator(np.random.PCG64(seed))
+        # per-limb sqrt(-1) (NTT image of X^(N/2))
+        self._imag = [sqrt_minus_one(params, l) for l in range(len(params.moduli))]
+        self.op_counts: Dict[str, int] = {}
+
+    # ------------------------------------------------------------------ utils
+    def _count(self, name: str, k: int = 1):
+        self.op_counts[name] = self.op_counts.get(name, 0) + k
+
+    def _sample_ternary(self) -> np.ndarray:
+        return self._rng.integers(-1, 2, size=self.params.n, dtype=np.int64)
+
+    def _sample_error(self) -> np.ndarray:
+        return np.rint(self._rng.normal(0.0, _SIGMA, size=self.params.n)).astype(np.int64)
+
+    def _sample_uniform(self, limb_ids: Sequence[int]) -> np.ndarray:
+        out = np.empty((len(limb_ids), self.params.n), dtype=np.uint64)
+        for r, l in enumerate(limb_ids):
+            out[r] = self._rng.integers(0, self.params.moduli[l], size=self.params.n, dtype=np.uint64)
+        return out
+
+    def _const_residues(self, re: int, im: int, n_q_active: int):
+        """(c_plus, c_minus) per active limb for the polynomial re + im*X^(N/2)."""
+        cp, cm = [], []
+        for l in range(n_q_active):
+            q = self.params.moduli[l]
+            t = (im % q) * self._imag[l] % q
+            cp.append((re + t) % q)
+            cm.append((re - t) % q)
+        return cp, cm
+
+    # ------------------------------------------------------------------ keys
+    def create_secret_key(self) -> SecretKey:
+        s = self._sample_ternary()
+        return SecretKey(s, self.backend.from_i64(s, self.params.n_q, True))
+
+    def create_public_key(self, sk: SecretKey) -> PublicKey:
+        be, P = self.backend, self.params
+        nq = P.n_q
+        a = be.from_numpy(self._sample_uniform(range(nq))[None])
+        e = be.from_i64(self._sample_error(), nq, False)
+        s = be.take_limbs(sk.ntt, nq, False)
+        b = be.sub(e, be.mul(a, s, nq, 0), nq, 0)
+        return PublicKey(be.concat([b, a]))
+
+    def _make_switch_key(self, sk: SecretKey, s_from) -> Any:
+        """KSK for s_from -> s.  s_from: [1, n_q+n_p, N] NTT."""
+        be, P = self.backend, self.params
+        nq, npp = P.n_q, P.n_p
+        tot = nq + npp
+        ids = list(range(tot))
+        p_prod = 1
+        for p in P.p:
+            p_prod *= p
+        parts = []
+        for j in range(P.dnum):
+            lo, hi = j * P.alpha, min((j + 1) * P.alpha, nq)
+            a = be.from_numpy(self._sample_uniform(ids)[None])
+            e = be.from_i64(self._sample_error(), nq, True)
+            b = be.sub(e, be.mul(a, sk.ntt, nq, npp), nq, npp)
+            # + (P mod q_i) * s_from on the digit's own limbs
+            fac = [(p_prod % P.moduli[l]) if lo <= l < hi else 0 for l in ids]
+            b = be.add(b, be.mul_scalar(s_from, fac, nq, npp), nq, npp)
+            parts.append(be.concat([b, a]))
+        return be.stack(parts)
+
+    def create_relinearization_key(self, sk: SecretKey) -> RelinearizationKey:
+        P = self.params
+        s2 = self.backend.mul(sk.ntt, sk.ntt, P.n_q, P.n_p)
+        return RelinearizationKey(self._make_switch_key(sk, s2))
+
+    def _galois_key(self, sk: SecretKey, g: int):
+        P = self.params
+        sg = self.backend.automorphism(sk.ntt, g, P.n_q, P.n_p)
+        return self._make_switch_key(sk, sg)
+
+    def create_conjugation_key(self, sk: SecretKey) -> ConjugationKey:
+        g = self.params.galois_conj
+        return ConjugationKey(self._galois_key(sk, g), g)
+
+    def create_fixed_rotation_key(self, sk: SecretKey, delta: int) -> FixedRotationKey:
+        g = self.params.galois_for_rotation(int(delta))
+        return FixedRotationKey(self._galois_key(sk, g), g, int(delta))
+
+    def create_rotation_key(self, sk: SecretKey, steps: Optional[Sequence[int]] = None) -> RotationKey:
+        """All +-2^k steps by default (the reference passes only ``sk``:
+        /root/reference/engine_context.py:66); ``steps`` restricts the set."""
+        if steps is None:
+            steps = []
+            k = 1
+            while k < self.slot_count:
+                steps += [k, -k]
+                k <<= 1
+        return RotationKey({int(d): self.create_fixed_rotation_key(sk, int(d)) for d in steps})
+
+    def create_small_bootstrap_key(self, sk: SecretKey) -> BootstrapKey:
+        return BootstrapKey(small=True)
+
+    def create_bootstrap_key(self, sk: SecretKey) -> BootstrapKey:
+        return BootstrapKey(small=False)
+
+    # ------------------------------------------------------------------ encode / encrypt / decrypt
+    def encode(self, values) -> Plaintext:
+        v = np.asarray(values)
+        if v.size > self.slot_count:
+            raise ValueError(f"encode: {v.size} values exceed slot_count={self.slot_count}")
+        return Plaintext(self, v)
+
+    def encrypt(self, data, public_key: PublicKey, level: Optional[int] = None) -> Ciphertext:
+        be, P = self.backend, self.params
+        if isinstance(data, Plaintext):
+            data = data.values
+        lvl = P.max_level if level is None else int(level)
+        nq = lvl + 1
+        m = be.from_i64(encoding.encode_i64(np.asarray(data), P.scale(lvl), P.log_n), nq, False)
+        v = be.from_i64(self._sample_ternary(), nq, False)
+        e0 = be.from_i64(self._sample_error(), nq, False)
+        e1 = be.from_i64(self._sample_error(), nq, False)
+        pk = public_key.polys if nq == P.n_q else be.take_limbs(public_key.polys, nq, False)
+        vb = be.mul(pk, v, nq, 0)                      # [2,nq,N] * [1,nq,N]
+        c = be.add(vb, be.concat([be.add(e0, m, nq, 0), e1]), nq, 0)
+        self._count('encrypt')
+        return Ciphertext(self, c, lvl)
+
+    def decrypt_to_plaintext_coeffs(self, ct: Ciphertext, sk: SecretKey) -> np.ndarray:
+        """Centred coefficient vector (float64) of c0 + c1 s (+ c2 s^2)."""
+        be = self.backend
+        use = min(2, ct.level + 1)
+        c = be.take_limbs(ct.polys, use, False)
+        s = be.take_limbs(sk.ntt, use, False)
+        acc = be.add(be.select_poly(c, 0), be.mul(be.select_poly(c, 1), s, use, 0), use, 0)
+        if ct.npoly == 3:
+            s2 = be.mul(s, s, use, 0)
+            acc = be.add(acc, be.mul(be.select_poly(c, 2), s2, use, 0), use, 0)
+        acc = be.intt(acc, use, 0)
+        return be.crt_centered(acc, use)
+
+    def decrypt(self, ct: Ciphertext, sk: SecretKey) -> np.ndarray:
+        m = self.decrypt_to_plaintext_coeffs(ct, sk)
+        self._count('decrypt')
+        return encoding.coeffs_to_slots(m, self.params.log_n) / self.params.scale(ct.level)
+
+    # ------------------------------------------------------------------ level management
+    def _rescale(self, ct: Ciphertext) -> Ciphertext:
+        if ct.level == 0:
+            raise RuntimeError("cannot rescale: ciphertext is at level 0 (no multiplicative depth left)")
+        self._count('rescale')
+        return Ciphertext(self, self.backend.rescale(ct.polys, ct.level + 1), ct.level - 1)
+
+    def _mul_int_const(self, ct: Ciphertext, re: int, im: int) -> Ciphertext:
+        nq = ct.level + 1
+        cp, cm = self._const_residues(re, im, nq)
+        return Ciphertext(self, self.backend.mul_const(ct.polys, cp, cm, nq), ct.level)
+
+    def level_down(self, ct: Ciphertext, target: int) -> Ciphertext:
+        """Bring ``ct`` to ``target`` (< ct.level) *and* onto that level's scale."""
+        if target == ct.level:
+            return ct
+        if target > ct.level:
+            raise RuntimeError("cannot raise the level of a ciphertext without bootstrapping")
+        P = self.params
+        if ct.zero:
+            return self._zero(target, ct.npoly)
+        polys = ct.polys
+        if ct.level > target + 1:
+            polys = self.backend.take_limbs(polys, target + 2, False)
+        c = P.delta[target] * P.moduli[target + 1] / P.delta[ct.level]
+        tmp = self._mul_int_const(Ciphertext(self, polys, target + 1), int(round(c)), 0)
+        self._count('level_adjust')
+        return self._rescale(tmp)
+
+    def _align(self, a: Ciphertext, b: Ciphertext):
+        if a.level > b.level:
+            a = self.level_down(a, b.level)
+        elif b.level > a.level:
+            b = self.level_down(b, a.level)
+        return a, b
+
+    def _zero(self, level: int, npoly: int = 2) -> Ciphertext:
+        return Ciphertext(self, self.backend.zeros(npoly, level + 1, False), level, zero=True)
+
+    # ------------------------------------------------------------------ arithmetic
+    def add(self, a, b):
+        if isinstance(a, Ciphertext) and isinstance(b, Ciphertext):
+            a, b = self._align(a, b)
+            if a.zero and a.npoly <= b.npoly:
+                return b
+            if b.zero and b.npoly <= a.npoly:
+                return a
+            if a.npoly != b.npoly:
+                a, b = self._pad_poly(a, b)
+            nq = a.level + 1
+            self._count('add_ct')
+            return Ciphertext(self, self.backend.add(a.polys, b.polys, nq, 0), a.level)
+        if isinstance(b, Ciphertext):
+            a, b = b, a
+        if not isinstance(a, Ciphertext):
+            raise TypeError("add: at least one operand must be a Ciphertext")
+        if isinstance(b, Plaintext):
+            if b.const is not None:
+                return self.add_plain(a, b.const)
+            self._count('add_pt')
+            return Ciphertext(self, self.backend.add_poly0(a.polys, b.at_level(a.level), a.level + 1), a.level)
+        return self.add_plain(a, b)
+
+    def _pad_poly(self, a: Ciphertext, b: Ciphertext):
+        be = self.backend
+        if a.npoly < b.npoly:
+            a = Ciphertext(self, be.concat([a.polys, be.zeros(b.npoly - a.npoly, a.level + 1, False)]), a.level)
+        else:
+            b = Ciphertext(self, be.concat([b.polys, be.zeros(a.npoly - b.npoly, b.level + 1, False)]), b.level)
+        return a, b
+
+    def add_plain(self, ct: Ciphertext, value) -> Ciphertext:
+        re, im = encoding.const_i64(complex(value), self.params.delta[ct.level])
+        nq = ct.level + 1
+        cp, cm = self._const_residues(re, im, nq)
+        self._count('add_const')
+        return Ciphertext(self, self.backend.add_const(ct.polys, cp, cm, nq), ct.level)
+
+    def subtract(self, a: Ciphertext, b: Ciphertext) -> Ciphertext:
+        a, b = self._align(a, b)
+        if a.npoly != b.npoly:
+            a, b = self._pad_poly(a, b)
+        return Ciphertext(self, self.backend.sub(a.polys, b.polys, a.level + 1, 0), a.level)
+
+    def negate(self, a: Ciphertext) -> Ciphertext:
+        return Ciphertext(self, self.backend.neg(a.polys, a.level + 1, 0), a.level, a.zero)
+
+    def multiply(self, a, b, relin_key: Optional[RelinearizationKey] = None):
+        if isinstance(a, Ciphertext) and isinstance(b, Ciphertext):
+            return self._mul_ct(a, b, relin_key)
+        if isinstance(b, Ciphertext):
+            a, b = b, a
+        if not isinstance(a, Ciphertext):
+            raise TypeError("multiply: at least one operand must be a Ciphertext")
+        if isinstance(b, Plaintext):
+            if b.const is not None:
+                return self._mul_scalar(a, b.const)
+            if a.level == 0:
+                raise RuntimeError("multiply: no multiplicative depth left")
+            if a.zero:
+                return self._zero(a.level - 1, a.npoly)
+            self._count('mul_pt')
+            prod = self.backend.mul(a.polys, b.at_level(a.level), a.level + 1, 0)
+            return self._rescale(Ciphertext(self, prod, a.level))
+        return self._mul_scalar(a, b)
+
+    def _mul_scalar(self, ct: Ciphertext, value) -> Ciphertext:
+        """ct x complex constant, rescaled (the reference uses ``multiply(ct, 0.0)`` as
+        its "zero ciphertext": /root/reference/xor_service.py:282)."""
+        if ct.level == 0:
+            raise RuntimeError("multiply: no multiplicative depth left")
+        v = complex(value)
+        if v == 0 or ct.zero:
+            return self._zero(ct.level - 1, ct.npoly)
+        re, im = encoding.const_i64(v, self.params.delta[ct.level])
+        self._count('mul_const')
+        return self._rescale(self._mul_int_const(ct, re, im))
+
+    def _mul_ct(self, a: Ciphertext, b: Ciphertext, rlk: Optional[RelinearizationKey]) -> Ciphertext:
+        a, b = self._align(a, b)
+        if a.npoly != 2 or b.npoly != 2:
+            raise RuntimeError("multiply: operands must have 2 polynomials (relinearize first)")
+        if a.level == 0:
+            raise RuntimeError("multiply: no multiplicative depth left")
+        if a.zero or b.zero:
+            return self._zero(a.level - 1, 2 if rlk is not None else 3)
+        nq = a.level + 1
+        self._count('mul_ct')
+        d = self.backend.tensor(a.polys, b.polys, nq)
+        ct3 = Ciphertext(self, d, a.level)
+        if rlk is not None:
+            ct3 = self._relin(ct3, rlk)
+        return self._rescale(ct3)
+
+    def square(self, a: Ciphertext, relin_key=None) -> Ciphertext:
+        return self._mul_ct(a, a, relin_key)
+
+    def _relin(self, ct3: Ciphertext, rlk: SwitchKey) -> Ciphertext:
+        be = self.backend
+        nq = ct3.level + 1
+        self._count('keyswitch_relin')
+        ks = be.keyswitch(be.select_poly(ct3.polys, 2), rlk.data, nq)
+        return Ciphertext(self, be.add(be.take_polys(ct3.polys, 2), ks, nq, 0), ct3.level)
+
+    def relinearize(self, ct: Ciphertext, relin_key: RelinearizationKey) -> Ciphertext:
+        if ct.npoly != 3:
+            # message pinned by /root/reference/xor_service.py:112-118
+            raise RuntimeError("relinearize: ciphertext should have 3 polynomials, "
+                               f"but it has {ct.npoly}")
+        if ct.zero:
+            return self._zero(ct.level, 2)
+        return self._relin(ct, relin_key)
+
+    def rescale(self, ct: Ciphertext) -> Ciphertext:
+        """Public alias; every multiply in this engine already rescales."""
+        return self._rescale(ct)
+
+    # ------------------------------------------------------------------ powers
+    def make_power_basis(self, ct: Ciphertext, degree: int, relin_key) -> List[Ciphertext]:
+        """[ct^1, ..., ct^degree]; ct^k sits ceil(log2 k) levels below ct
+        (/root/reference/xor_service.py:86, sbox/sbox_service.py:93)."""
+        degree = int(degree)
+        if degree < 1:
+            return []
+        pw: List[Optional[Ciphertext]] = [None] * (degree + 1)
+        pw[1] = ct
+        for k in range(2, degree + 1):
+            hi = (k + 1) // 2
+            lo = k // 2
+            pw[k] = self._mul_ct(pw[hi], pw[lo], relin_key)
+        return pw[1:]
+
+    # ------------------------------------------------------------------ automorphisms
+    def _apply_galois(self, ct: Ciphertext, key: SwitchKey) -> Ciphertext:
+        be = self.backend
+        if ct.npoly != 2:
+            raise RuntimeError("rotate/conjugate: ciphertext must have 2 polynomials")
+        nq = ct.level + 1
+        rot = be.automorphism(ct.polys, key.galois, nq, 0)
+        ks = be.keyswitch(be.select_poly(rot, 1), key.data, nq)
+        self._count('keyswitch_galois')
+        return Ciphertext(self, be.add_poly0(ks, be.select_poly(rot, 0), nq), ct.level)
+
+    def conjugate(self, ct: Ciphertext, conj_key: ConjugationKey) -> Ciphertext:
+        if ct.zero:
+            return ct
+        return self._apply_galois(ct, conj_key)
+
+    def rotate(self, ct: Ciphertext, rot_key, delta: Optional[int] = None) -> Ciphertext:
+        """``out = np.roll(in, delta)`` (/root/reference/test/test_engine_rot.py:32-40)."""
+        if isinstance(rot_key, FixedRotationKey):
+            if delta is not None and int(delta) % self.slot_count != rot_key.delta % self.slot_count:
+                raise ValueError("fixed rotation key was generated for a different delta")
+            return ct if ct.zero else self._apply_galois(ct, rot_key)
+        if delta is None:
+            raise TypeError("rotate(ct, rotation_key, delta): delta is required")
+        d = int(delta) % self.slot_count
+        if d == 0 or ct.zero:
+            return ct
+        if d in rot_key.keys:
+            return self._apply_galois(ct, rot_key.keys[d])
+        if d - self.slot_count in rot_key.keys:
+            return self._apply_galois(ct, rot_key.keys[d - self.slot_count])
+        out = ct
+        for step in _naf_steps(d, self.slot_count):
+            key = rot_key.keys.get(step) or rot_key.keys.get(step % self.slot_count)
+            if key is None:
+                raise RuntimeError(f"rotation key lacks step {step} needed for delta {delta}")
+            out = self._apply_galois(out, key)
+        return out
+
+    # ------------------------------------------------------------------ bootstrap
+    def bootstrap(self, ct: Ciphertext, relin_key, conj_key, boot_key) -> Ciphertext:
+        raise NotImplementedError(
+            "bootstrapping is row (f)-1 of SURVEY.md section 8 and is not built in this round")

@@ -1,0 +1,236 @@
+"""ctypes binding of oracle/refmod.cpp + the `RefBackend` adapter.
+
+TEST INFRASTRUCTURE ONLY (see the header of refmod.cpp).  `RefBackend` implements the
+backend interface of ``aes_fhe_b200.engine.Engine`` on NumPy ``uint64`` arrays so the same
+facade (level/scale bookkeeping) can be driven by the CPU restatement; tests compare its
+residues bit-for-bit with the CUDA backend's, and bench.py times it as the CPU baseline.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+from pathlib import Path
+from typing import List, Sequence
+
+import numpy as np
+
+_HERE = Path(__file__).resolve().parent
+_LIB = None
+
+
+def build(force: bool = False) -> Path:
+    so = _HERE / "librefmod.so"
+    src = _HERE / "refmod.cpp"
+    if force or not so.exists() or (src.exists() and so.stat().st_mtime < src.stat().st_mtime):
+        subprocess.check_call(["make", "-C", str(_HERE), "-s"] + (["-B"] if force else []))
+    return so
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        _LIB = C.CDLL(str(build()))
+        _LIB.ref_ctx_create.restype = C.c_void_p
+        _LIB.ref_ctx_threads.restype = C.c_int
+        _LIB.ref_ctx_threads.argtypes = [C.c_void_p]
+    return _LIB
+
+
+def _p(a: np.ndarray):
+    return C.c_void_p(a.ctypes.data)
+
+
+class RefBackend:
+    name = "refmod-cpu"
+
+    def __init__(self, params, threads: int = 0):
+        self.params = params
+        self.n = params.n
+        L = lib()
+        mod = np.array(params.moduli, dtype=np.uint64)
+        psi = np.array(params.psi, dtype=np.uint64)
+        self._ctx = C.c_void_p(L.ref_ctx_create(params.log_n, params.n_q, params.n_p, params.alpha,
+                                                _p(mod), _p(psi), int(threads)))
+        self.threads = L.ref_ctx_threads(self._ctx)
+        self._L = L
+
+    def __del__(self):
+        try:
+            self._L.ref_ctx_destroy(self._ctx)
+        except Exception:
+            pass
+
+    # ---- layout helpers
+    def _ids(self, nq: int, np_: int, npoly: int = 1) -> np.ndarray:
+        ids = list(range(nq)) + [self.params.n_q + k for k in range(np_)]
+        return np.array(ids * npoly, dtype=np.int32)
+
+    def npoly(self, h) -> int:
+        return h.shape[0]
+
+    def from_numpy(self, a: np.ndarray):
+        return np.ascontiguousarray(a, dtype=np.uint64)
+
+    def to_numpy(self, h) -> np.ndarray:
+        return np.array(h, dtype=np.uint64, copy=True)
+
+    def zeros(self, npoly: int, nq: int, with_p: bool):
+        return np.zeros((npoly, nq + (self.params.n_p if with_p else 0), self.n), dtype=np.uint64)
+
+    def take_limbs(self, h, nq: int, with_p: bool):
+        if with_p:
+            K = self.params.n_p
+            return np.ascontiguousarray(np.concatenate([h[:, :nq], h[:, h.shape[1] - K:]], axis=1))
+        return np.ascontiguousarray(h[:, :nq])
+
+    def select_poly(self, h, i: int):
+        return h[i:i + 1]
+
+    def take_polys(self, h, k: int):
+        return h[:k]
+
+    def concat(self, hs: List):
+        return np.ascontiguousarray(np.concatenate(hs, axis=0))
+
+    def stack(self, hs: List):
+        return np.ascontiguousarray(np.stack(hs, axis=0))
+
+    # ---- transforms
+    def ntt(self, h, nq: int, np_: int):
+        out = np.array(h, copy=True)
+        ids = self._ids(nq, np_, out.shape[0])
+        self._L.ref_ntt(self._ctx, _p(out), _p(ids), C.c_int(len(ids)))
+        return out
+
+    def intt(self, h, nq: int, np_: int):
+        out = np.array(h, copy=True)
+        ids = self._ids(nq, np_, out.shape[0])
+        self._L.ref_intt(self._ctx, _p(out), _p(ids), C.c_int(len(ids)))
+        return out
+
+    def from_i64(self, coeffs: np.ndarray, nq: int, with_p: bool):
+        np_ = self.params.n_p if with_p else 0
+        ids = self._ids(nq, np_)
+        out = np.empty((1, len(ids), self.n), dtype=np.uint64)
+        c = np.ascontiguousarray(coeffs, dtype=np.int64)
+        self._L.ref_from_i64(self._ctx, _p(out), _p(c), _p(ids), C.c_int(len(ids)))
+        self._L.ref_ntt(self._ctx, _p(out), _p(ids), C.c_int(len(ids)))
+        return out
+
+    # ---- elementwise
+    def _bin(self, fn, a, b, nq, np_):
+        npoly = max(a.shape[0], b.shape[0])
+        a = np.ascontiguousarray(np.broadcast_to(a, (npoly,) + a.shape[1:]))
+        b = np.ascontiguousarray(np.broadcast_to(b, (npoly,) + b.shape[1:]))
+        out = np.empty_like(a)
+        ids = self._ids(nq, np_, npoly)
+        fn(self._ctx, _p(out), _p(a), _p(b), _p(ids), C.c_int(len(ids)))
+        return out
+
+    def add(self, a, b, nq, np_):
+        return self._bin(self._L.ref_add, a, b, nq, np_)
+
+    def sub(self, a, b, nq, np_):
+        return self._bin(self._L.ref_sub, a, b, nq, np_)
+
+    def mul(self, a, b, nq, np_):
+        return self._bin(self._L.ref_mul, a, b, nq, np_)
+
+    def neg(self, a, nq, np_):
+        a = np.ascontiguousarray(a)
+        out = np.empty_like(a)
+        ids = self._ids(nq, np_, a.shape[0])
+        self._L.ref_neg(self._ctx, _p(out), _p(a), _p(ids), C.c_int(len(ids)))
+        return out
+
+    def mul_scalar(self, a, fac: Sequence[int], nq, np_):
+        a = np.ascontiguousarray(a)
+        npoly = a.shape[0]
+        f = np.array(list(fac) * npoly, dtype=np.uint64)
+        out = np.empty_like(a)
+        ids = self._ids(nq, np_, npoly)
+        self._L.ref_mul_const(self._ctx, _p(out), _p(a), _p(f), _p(f), _p(ids), C.c_int(len(ids)))
+        return out
+
+    def mul_const(self, a, cp, cm, nq):
+        a = np.ascontiguousarray(a)
+        npoly = a.shape[0]
+        fp = np.array(list(cp) * npoly, dtype=np.uint64)
+        fm = np.array(list(cm) * npoly, dtype=np.uint64)
+        out = np.empty_like(a)
+        ids = self._ids(nq, 0, npoly)
+        self._L.ref_mul_const(self._ctx, _p(out), _p(a), _p(fp), _p(fm), _p(ids), C.c_int(len(ids)))
+        return out
+
+    def add_const(self, a, cp, cm, nq):
+        out = np.array(a, copy=True)
+        fp = np.array(list(cp), dtype=np.uint64)
+        fm = np.array(list(cm), dtype=np.uint64)
+        ids = self._ids(nq, 0, 1)
+        p0 = np.ascontiguousarray(out[0])
+        self._L.ref_add_const(self._ctx, _p(p0), _p(p0), _p(fp), _p(fm), _p(ids), C.c_int(len(ids)))
+        out[0] = p0
+        return out
+
+    def add_poly0(self, a, p, nq):
+        out = np.array(a, copy=True)
+        out[0:1] = self.add(out[0:1], p, nq, 0)
+        return out
+
+    def tensor(self, a, b, nq):
+        a0, a1, b0, b1 = a[0:1], a[1:2], b[0:1], b[1:2]
+        d0 = self.mul(a0, b0, nq, 0)
+        d1 = self.add(self.mul(a0, b1, nq, 0), self.mul(a1, b0, nq, 0), nq, 0)
+        d2 = self.mul(a1, b1, nq, 0)
+        return self.concat([d0, d1, d2])
+
+    # ---- structural
+    def rescale(self, h, nq):
+        h = np.ascontiguousarray(h)
+        out = np.empty((h.shape[0], nq - 1, self.n), dtype=np.uint64)
+        for i in range(h.shape[0]):
+            o = np.empty((nq - 1, self.n), dtype=np.uint64)
+            self._L.ref_rescale(self._ctx, _p(o), _p(np.ascontiguousarray(h[i])), C.c_int(nq))
+            out[i] = o
+        return out
+
+    def automorphism(self, h, g: int, nq, np_):
+        h = np.ascontiguousarray(h)
+        out = np.empty_like(h)
+        self._L.ref_automorphism(self._ctx, _p(out), _p(h), C.c_uint64(int(g)), C.c_int(h.shape[0] * h.shape[1]))
+        return out
+
+    def modup(self, d, nq):
+        P = self.params
+        beta = P.digits_at(nq)
+        ext = np.empty((beta, nq + P.n_p, self.n), dtype=np.uint64)
+        self._L.ref_modup(self._ctx, _p(ext), _p(np.ascontiguousarray(d)), C.c_int(nq))
+        return ext
+
+    def ks_inner(self, ext, ksk, nq):
+        acc = np.empty((2, nq + self.params.n_p, self.n), dtype=np.uint64)
+        self._L.ref_ks_inner(self._ctx, _p(acc), _p(ext), _p(np.ascontiguousarray(ksk)), C.c_int(nq))
+        return acc
+
+    def moddown(self, acc, nq):
+        acc = np.ascontiguousarray(acc)
+        out = np.empty((acc.shape[0], nq, self.n), dtype=np.uint64)
+        self._L.ref_moddown(self._ctx, _p(out), _p(acc), C.c_int(nq), C.c_int(acc.shape[0]))
+        return out
+
+    def keyswitch(self, d, ksk, nq):
+        return self.moddown(self.ks_inner(self.modup(d, nq), ksk, nq), nq)
+
+    def crt_centered(self, h, use: int) -> np.ndarray:
+        h = np.ascontiguousarray(h)
+        out = np.empty(self.n, dtype=np.float64)
+        if use >= 2:
+            self._L.ref_crt2_centered(self._ctx, _p(out), _p(np.ascontiguousarray(h[0, 0])),
+                                      _p(np.ascontiguousarray(h[0, 1])))
+        else:
+            self._L.ref_crt1_centered(self._ctx, _p(out), _p(np.ascontiguousarray(h[0, 0])))
+        return out
+
+    def synchronize(self):
+        pass
