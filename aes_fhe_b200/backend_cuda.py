@@ -1,0 +1,235 @@
+"""CUDA backend of the engine facade: torch owns device memory and the stream, every
+operation is one call through the C ABI (include/aesfhe_b200.h) into hand-written sm_100a
+kernels.  No CPU path: without the built library or without a GPU the constructor raises.
+
+Handles are ``torch.int64`` tensors ``[npoly, limbs, N]`` (bit pattern = unsigned residue).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Sequence
+
+import numpy as np
+import torch
+
+from . import _capi
+
+
+class CudaBackend:
+    name = "cuda-sm100a"
+
+    def __init__(self, params, device_id: int = 0, _lib_path=None, _device: str | None = None):
+        self.params = params
+        self.n = params.n
+        self.lib = _capi.load(_lib_path)
+        if _device is None:
+            if not torch.cuda.is_available():
+                raise _capi.FheError("CUDA device required: this engine has no CPU fallback")
+            self.device = torch.device("cuda", device_id)
+        else:
+            # tests/emu only: the g++ -DFHE_EMU build of the same kernels on host memory
+            self.device = torch.device(_device)
+        self.is_cuda = self.device.type == "cuda"
+        mod = np.array(params.moduli, dtype=np.uint64)
+        psi = np.array(params.psi, dtype=np.uint64)
+        h = C.c_void_p()
+        rc = self.lib.fhe_ctx_create(C.byref(h), params.log_n, params.n_q, params.n_p, params.alpha,
+                                     mod.ctypes.data, psi.ctypes.data, device_id if self.is_cuda else 0)
+        _capi.check(self.lib, rc, "fhe_ctx_create")
+        self.ctx = h
+        self._K = params.n_p
+
+    def __del__(self):
+        try:
+            if getattr(self, "ctx", None):
+                self.lib.fhe_ctx_destroy(self.ctx)
+                self.ctx = None
+        except Exception:
+            pass
+
+    # ---- plumbing
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream) if self.is_cuda else C.c_void_p(0)
+
+    def _empty(self, *shape):
+        return torch.empty(shape, dtype=torch.int64, device=self.device)
+
+    def _call(self, name, *args):
+        _capi.check(self.lib, getattr(self.lib, name)(self.ctx, self._stream(), *args), name)
+
+    @staticmethod
+    def _ptr(t: torch.Tensor):
+        return C.c_void_p(t.data_ptr())
+
+    def synchronize(self):
+        if self.is_cuda:
+            torch.cuda.synchronize(self.device)
+
+    def launch_count(self) -> int:
+        return int(self.lib.fhe_launch_count())
+
+    # ---- layout helpers
+    def npoly(self, h) -> int:
+        return h.shape[0]
+
+    def from_numpy(self, a: np.ndarray):
+        a = np.ascontiguousarray(a, dtype=np.uint64)
+        return torch.from_numpy(a.view(np.int64)).to(self.device)
+
+    def to_numpy(self, h) -> np.ndarray:
+        return h.detach().cpu().contiguous().numpy().view(np.uint64).copy()
+
+    def zeros(self, npoly: int, nq: int, with_p: bool):
+        return torch.zeros((npoly, nq + (self._K if with_p else 0), self.n), dtype=torch.int64, device=self.device)
+
+    def take_limbs(self, h, nq: int, with_p: bool):
+        if with_p:
+            return torch.cat([h[:, :nq], h[:, h.shape[1] - self._K:]], dim=1).contiguous()
+        return h[:, :nq].contiguous()
+
+    def select_poly(self, h, i: int):
+        return h[i:i + 1]
+
+    def take_polys(self, h, k: int):
+        return h[:k]
+
+    def concat(self, hs: List):
+        return torch.cat(hs, dim=0)
+
+    def stack(self, hs: List):
+        return torch.stack(hs, dim=0)
+
+    # ---- transforms
+    def ntt(self, h, nq: int, np_: int):
+        out = h.clone()
+        self._call("fhe_ntt_fwd", self._ptr(out), out.shape[0], nq, np_)
+        return out
+
+    def intt(self, h, nq: int, np_: int):
+        out = h.clone()
+        self._call("fhe_ntt_inv", self._ptr(out), out.shape[0], nq, np_)
+        return out
+
+    def from_i64(self, coeffs: np.ndarray, nq: int, with_p: bool):
+        np_ = self._K if with_p else 0
+        c = torch.from_numpy(np.ascontiguousarray(coeffs, dtype=np.int64)).to(self.device)
+        out = self._empty(1, nq + np_, self.n)
+        self._call("fhe_from_i64", self._ptr(out), self._ptr(c), nq, np_)
+        self._call("fhe_ntt_fwd", self._ptr(out), 1, nq, np_)
+        return out
+
+    # ---- elementwise
+    def _bin(self, name, a, b, nq, np_):
+        if a.shape[0] < b.shape[0]:
+            if name == "fhe_sub":
+                a = a.expand(b.shape[0], -1, -1).contiguous()
+            else:
+                a, b = b, a
+        a = a.contiguous()
+        b = b.contiguous()
+        out = torch.empty_like(a)
+        self._call(name, self._ptr(out), self._ptr(a), self._ptr(b), a.shape[0], b.shape[0], nq, np_)
+        return out
+
+    def add(self, a, b, nq, np_):
+        return self._bin("fhe_add", a, b, nq, np_)
+
+    def sub(self, a, b, nq, np_):
+        return self._bin("fhe_sub", a, b, nq, np_)
+
+    def mul(self, a, b, nq, np_):
+        return self._bin("fhe_mul", a, b, nq, np_)
+
+    def neg(self, a, nq, np_):
+        a = a.contiguous()
+        out = torch.empty_like(a)
+        self._call("fhe_neg", self._ptr(out), self._ptr(a), a.shape[0], nq, np_)
+        return out
+
+    def _consts(self, cp: Sequence[int], cm: Sequence[int]):
+        a = np.array([int(v) for v in cp], dtype=np.uint64)
+        b = np.array([int(v) for v in cm], dtype=np.uint64)
+        return a, b
+
+    def mul_scalar(self, a, fac: Sequence[int], nq, np_):
+        a = a.contiguous()
+        f, _ = self._consts(fac, fac)
+        out = torch.empty_like(a)
+        self._call("fhe_mul_const", self._ptr(out), self._ptr(a), f.ctypes.data, f.ctypes.data, a.shape[0], nq, np_)
+        return out
+
+    def mul_const(self, a, cp, cm, nq):
+        a = a.contiguous()
+        fp, fm = self._consts(cp, cm)
+        out = torch.empty_like(a)
+        self._call("fhe_mul_const", self._ptr(out), self._ptr(a), fp.ctypes.data, fm.ctypes.data, a.shape[0], nq, 0)
+        return out
+
+    def add_const(self, a, cp, cm, nq):
+        out = a.clone()
+        fp, fm = self._consts(cp, cm)
+        self._call("fhe_add_const", self._ptr(out), self._ptr(out), fp.ctypes.data, fm.ctypes.data, 1, nq, 0)
+        return out
+
+    def add_poly0(self, a, p, nq):
+        out = a.clone()
+        p = p.contiguous()
+        self._call("fhe_add", self._ptr(out), self._ptr(out), self._ptr(p), 1, 1, nq, 0)
+        return out
+
+    def tensor(self, a, b, nq):
+        a = a.contiguous()
+        b = b.contiguous()
+        out = self._empty(3, nq, self.n)
+        self._call("fhe_tensor", self._ptr(out), self._ptr(a), self._ptr(b), nq)
+        return out
+
+    # ---- structural
+    def rescale(self, h, nq):
+        h = h.contiguous()
+        out = self._empty(h.shape[0], nq - 1, self.n)
+        self._call("fhe_rescale", self._ptr(out), self._ptr(h), h.shape[0], nq)
+        return out
+
+    def automorphism(self, h, g: int, nq, np_):
+        h = h.contiguous()
+        out = torch.empty_like(h)
+        self._call("fhe_automorphism", self._ptr(out), self._ptr(h), C.c_uint64(int(g)), h.shape[0] * h.shape[1])
+        return out
+
+    def modup(self, d, nq):
+        d = d.contiguous()
+        beta = self.params.digits_at(nq)
+        ext = self._empty(beta, nq + self._K, self.n)
+        self._call("fhe_modup", self._ptr(ext), self._ptr(d), nq)
+        # a digit's own limbs are read from d by the inner product; mirror them here so the
+        # tensor is comparable with the oracle's ModUp output
+        a = self.params.alpha
+        for j in range(beta):
+            lo, hi = j * a, min((j + 1) * a, nq)
+            ext[j, lo:hi] = d.reshape(-1, self.n)[lo:hi]
+        return ext
+
+    def ks_inner(self, ext, d, ksk, nq):
+        acc = self._empty(2, nq + self._K, self.n)
+        self._call("fhe_ks_inner", self._ptr(acc), self._ptr(ext.contiguous()), self._ptr(d.contiguous()),
+                   self._ptr(ksk), nq)
+        return acc
+
+    def moddown(self, acc, nq):
+        acc = acc.clone()
+        out = self._empty(acc.shape[0], nq, self.n)
+        self._call("fhe_moddown", self._ptr(out), self._ptr(acc), nq, acc.shape[0])
+        return out
+
+    def keyswitch(self, d, ksk, nq):
+        d = d.contiguous()
+        out = self._empty(2, nq, self.n)
+        self._call("fhe_keyswitch", self._ptr(out), self._ptr(d), self._ptr(ksk), nq)
+        return out
+
+    def crt_centered(self, h, use: int) -> np.ndarray:
+        h = h.contiguous()
+        out = torch.empty(self.n, dtype=torch.float64, device=self.device)
+        self._call("fhe_crt_centered", self._ptr(out), self._ptr(h), use)
+        return out.cpu().numpy()

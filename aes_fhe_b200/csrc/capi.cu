@@ -1,0 +1,501 @@
+// capi.cu -- context (device tables) and the extern "C" entry points declared in
+// include/aesfhe_b200.h.  Host code here only builds small integer tables and sequences
+// kernel launches on the caller's stream.
+#include "kernels.cuh"
+#include "../../include/aesfhe_b200.h"
+
+#include <algorithm>
+#include <atomic>
+#include <cstring>
+#include <cstdio>
+#include <string>
+#include <vector>
+
+typedef unsigned __int128 u128;
+
+static thread_local std::string g_err;
+static std::atomic<uint64_t> g_launches(0);
+
+namespace {
+
+// ------------------------------------------------------------------ host modular helpers
+inline u64 h_mul(u64 a, u64 b, u64 q) { return (u64)((u128)a * b % q); }
+inline u64 h_pow(u64 b, u64 e, u64 q) {
+    u64 r = 1; b %= q;
+    while (e) { if (e & 1) r = h_mul(r, b, q); b = h_mul(b, b, q); e >>= 1; }
+    return r;
+}
+inline u64 h_inv(u64 a, u64 q) { return h_pow(a, q - 2, q); }
+inline ShoupConst h_shoup(u64 w, u64 q) {
+    ShoupConst s; s.w = w; s.ws = (u64)(((u128)w << 64) / q); return s;
+}
+inline Modulus h_modulus(u64 q) {
+    Modulus m; m.q = q;
+    u128 hi = ((u128)1 << 64) / q, rem = ((u128)1 << 64) % q;
+    u128 lo = (rem << 64) / q;
+    u128 mu = (hi << 64) + lo;
+    m.mu_hi = (u64)(mu >> 64); m.mu_lo = (u64)mu;
+    return m;
+}
+inline u32 h_brev(u32 x, int bits) {
+    u32 r = 0;
+    for (int i = 0; i < bits; ++i) { r = (r << 1) | (x & 1); x >>= 1; }
+    return r;
+}
+
+template <class T>
+T* to_device(const std::vector<T>& v) {
+    T* d = nullptr;
+    if (cudaMalloc((void**)&d, sizeof(T) * (v.size() ? v.size() : 1)) != cudaSuccess) return nullptr;
+    cudaMemcpy(d, v.data(), sizeof(T) * v.size(), cudaMemcpyHostToDevice);
+    return d;
+}
+
+}  // namespace
+
+struct fhe_ctx {
+    int log_n, n, n_q, n_p, alpha, tot, device;
+    std::vector<u64> q;                       // all moduli
+    DevTables T;
+    // per active-limb-count tables, index nq (1..n_q)
+    std::vector<BConvTable*> modup_tables;    // device array of beta(nq) tables
+    std::vector<int> modup_beta;
+    std::vector<ShoupConst*> modup_scale;     // [nq][2] iNTT final constants incl. (Q_j/q_i)^-1
+    std::vector<BConvTable*> moddown_table;   // one table
+    std::vector<ShoupConst*> rescale_c;       // [nq-1] q_{nq-1}^-1 mod q_i
+    ShoupConst* moddown_scale = nullptr;      // [4*n_p][2]
+    ShoupConst* pinv = nullptr;               // [n_q]  P^-1 mod q_i
+    u64 q0inv_mod_q1 = 0;
+    std::vector<void*> owned;
+    // scratch arena
+    u64* scratch = nullptr;
+    size_t scratch_words = 0;
+
+    u64 id_mod(int t, int nq) const { return q[t < nq ? t : n_q + (t - nq)]; }
+    int id_of(int t, int nq) const { return t < nq ? t : n_q + (t - nq); }
+};
+
+namespace {
+
+u64* arena(fhe_ctx* c, size_t words) {
+    if (words > c->scratch_words) {
+        if (c->scratch) { cudaDeviceSynchronize(); cudaFree(c->scratch); }
+        c->scratch = nullptr;
+        if (cudaMalloc((void**)&c->scratch, words * sizeof(u64)) != cudaSuccess) { c->scratch_words = 0; return nullptr; }
+        c->scratch_words = words;
+    }
+    return c->scratch;
+}
+
+int fail(const char* what) {
+    g_err = what;
+    return -1;
+}
+int check(const char* where) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        g_err = std::string(where) + ": " + cudaGetErrorString(e);
+        return -2;
+    }
+    return 0;
+}
+
+template <typename... KArgs, typename... Args>
+inline void launch(void (*k)(KArgs...), dim3 g, dim3 b, cudaStream_t s, Args&&... args) {
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    fhe_launch(k, g, b, 0, s, std::forward<Args>(args)...);
+}
+
+RowMap make_map(const fhe_ctx* c, int rows_per_poly, int j0, int nq, int skip_alpha = 0) {
+    RowMap m;
+    m.rows_per_poly = rows_per_poly; m.j0 = j0; m.nq = nq; m.p_base = c->n_q; m.skip_alpha = skip_alpha;
+    m.log_n = c->log_n;
+    return m;
+}
+
+bool bad_shape(const fhe_ctx* c, int nq, int np) {
+    return !c || nq < 1 || nq > c->n_q || (np != 0 && np != c->n_p);
+}
+
+// product of q[ids] except index `skip` (position in ids), reduced mod m
+u64 prod_except(const fhe_ctx* c, const std::vector<int>& ids, int skip, u64 m) {
+    u64 r = 1 % m;
+    for (size_t i = 0; i < ids.size(); ++i)
+        if ((int)i != skip) r = h_mul(r, c->q[ids[i]] % m, m);
+    return r;
+}
+
+void build_level_tables(fhe_ctx* c) {
+    const int n_q = c->n_q, K = c->n_p, alpha = c->alpha;
+    c->modup_tables.assign(n_q + 1, nullptr);
+    c->modup_beta.assign(n_q + 1, 0);
+    c->modup_scale.assign(n_q + 1, nullptr);
+    c->moddown_table.assign(n_q + 1, nullptr);
+    c->rescale_c.assign(n_q + 1, nullptr);
+
+    std::vector<u64> ninv(c->tot), w1ninv(c->tot);
+    {
+        // psi^-bitrev(1) = psi^-(N/2)
+        std::vector<ShoupConst> fin(2 * (size_t)c->tot);
+        cudaMemcpy(fin.data(), c->T.inv_final, sizeof(ShoupConst) * fin.size(), cudaMemcpyDeviceToHost);
+        for (int l = 0; l < c->tot; ++l) { ninv[l] = fin[2 * l].w; w1ninv[l] = fin[2 * l + 1].w; }
+    }
+    std::vector<int> pids(K);
+    for (int k = 0; k < K; ++k) pids[k] = n_q + k;
+
+    for (int nq = 1; nq <= n_q; ++nq) {
+        const int beta = (nq + alpha - 1) / alpha, ne = nq + K;
+        c->modup_beta[nq] = beta;
+        std::vector<BConvTable> tabs(beta);
+        std::vector<ShoupConst> scale(2 * (size_t)nq);
+        for (int j = 0; j < beta; ++j) {
+            BConvTable& tb = tabs[j];
+            std::memset(&tb, 0, sizeof(tb));
+            const int lo = j * alpha, hi = std::min(lo + alpha, nq);
+            std::vector<int> src;
+            for (int i = lo; i < hi; ++i) src.push_back(i);
+            tb.ns = (int)src.size();
+            for (int k = 0; k < tb.ns; ++k) {
+                tb.src_mod[k] = src[k]; tb.src_slot[k] = src[k];
+                const u64 qk = c->q[src[k]];
+                const u64 inv = h_inv(prod_except(c, src, k, qk), qk);
+                scale[2 * (size_t)src[k]] = h_shoup(h_mul(ninv[src[k]], inv, qk), qk);
+                scale[2 * (size_t)src[k] + 1] = h_shoup(h_mul(w1ninv[src[k]], inv, qk), qk);
+            }
+            int nt = 0;
+            for (int t = 0; t < ne; ++t) {
+                if (t >= lo && t < hi) continue;
+                const int id = c->id_of(t, nq);
+                const u64 m = c->q[id];
+                tb.dst_mod[nt] = id; tb.dst_slot[nt] = t;
+                for (int k = 0; k < tb.ns; ++k) tb.f[k][nt] = prod_except(c, src, k, m);
+                tb.qmod[nt] = prod_except(c, src, -1, m);
+                ++nt;
+            }
+            tb.nt = nt;
+        }
+        c->modup_tables[nq] = to_device(tabs);
+        c->modup_scale[nq] = to_device(scale);
+        c->owned.push_back(c->modup_tables[nq]); c->owned.push_back(c->modup_scale[nq]);
+
+        if (K > 0) {
+            std::vector<BConvTable> td(1);
+            BConvTable& tb = td[0];
+            std::memset(&tb, 0, sizeof(tb));
+            tb.ns = K; tb.nt = nq;
+            for (int k = 0; k < K; ++k) { tb.src_mod[k] = pids[k]; tb.src_slot[k] = k; }
+            for (int i = 0; i < nq; ++i) {
+                const u64 m = c->q[i];
+                tb.dst_mod[i] = i; tb.dst_slot[i] = i;
+                for (int k = 0; k < K; ++k) tb.f[k][i] = prod_except(c, pids, k, m);
+                tb.qmod[i] = prod_except(c, pids, -1, m);
+            }
+            c->moddown_table[nq] = to_device(td);
+            c->owned.push_back(c->moddown_table[nq]);
+        }
+        if (nq >= 2) {
+            std::vector<ShoupConst> rc(nq - 1);
+            const u64 ql = c->q[nq - 1];
+            for (int i = 0; i < nq - 1; ++i) rc[i] = h_shoup(h_inv(ql % c->q[i], c->q[i]), c->q[i]);
+            c->rescale_c[nq] = to_device(rc);
+            c->owned.push_back(c->rescale_c[nq]);
+        }
+    }
+    if (K > 0) {
+        // iNTT final constants for the special limbs, replicated for up to 4 polys
+        std::vector<ShoupConst> ms(2 * (size_t)K * 4);
+        for (int rep = 0; rep < 4; ++rep)
+            for (int k = 0; k < K; ++k) {
+                const u64 pk = c->q[pids[k]];
+                const u64 inv = h_inv(prod_except(c, pids, k, pk), pk);
+                ms[2 * ((size_t)rep * K + k)] = h_shoup(h_mul(ninv[pids[k]], inv, pk), pk);
+                ms[2 * ((size_t)rep * K + k) + 1] = h_shoup(h_mul(w1ninv[pids[k]], inv, pk), pk);
+            }
+        c->moddown_scale = to_device(ms);
+        c->owned.push_back(c->moddown_scale);
+        std::vector<ShoupConst> pv(n_q);
+        for (int i = 0; i < n_q; ++i) pv[i] = h_shoup(h_inv(prod_except(c, pids, -1, c->q[i]), c->q[i]), c->q[i]);
+        c->pinv = to_device(pv);
+        c->owned.push_back(c->pinv);
+    }
+    if (n_q >= 2) c->q0inv_mod_q1 = h_inv(c->q[0] % c->q[1], c->q[1]);
+}
+
+template <int NS>
+void launch_bconv_ns(fhe_ctx* c, cudaStream_t s, int groups, const BConvTable* tabs, int n_tabs, u64* dst,
+                     long long dst_stride, const u64* src, long long src_stride) {
+    launch(k_bconv<NS>, dim3(c->n / 256, groups), dim3(256), s, c->T, tabs, n_tabs, dst, dst_stride, src, src_stride);
+}
+void launch_bconv(fhe_ctx* c, cudaStream_t s, int ns_max, int groups, const BConvTable* tabs, int n_tabs, u64* dst,
+                  long long dst_stride, const u64* src, long long src_stride) {
+#define FHE_BCONV_CASE(NS) case NS: launch_bconv_ns<NS>(c, s, groups, tabs, n_tabs, dst, dst_stride, src, src_stride); break;
+    switch (ns_max) {
+        FHE_BCONV_CASE(1) FHE_BCONV_CASE(2) FHE_BCONV_CASE(3) FHE_BCONV_CASE(4)
+        FHE_BCONV_CASE(5) FHE_BCONV_CASE(6) FHE_BCONV_CASE(7) FHE_BCONV_CASE(8)
+        FHE_BCONV_CASE(9) FHE_BCONV_CASE(10) FHE_BCONV_CASE(11) FHE_BCONV_CASE(12)
+        FHE_BCONV_CASE(13) FHE_BCONV_CASE(14) FHE_BCONV_CASE(15)
+        default: launch_bconv_ns<16>(c, s, groups, tabs, n_tabs, dst, dst_stride, src, src_stride); break;
+    }
+#undef FHE_BCONV_CASE
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* fhe_last_error(void) { return g_err.c_str(); }
+uint64_t fhe_launch_count(void) { return g_launches.load(); }
+
+int fhe_ctx_create(fhe_ctx** out, int log_n, int n_q, int n_p, int alpha, const uint64_t* moduli,
+                   const uint64_t* psi, int device) {
+    if (!out || !moduli || !psi) return fail("fhe_ctx_create: null argument");
+    if (log_n < 12 || log_n > 16) return fail("fhe_ctx_create: log_n must be in [12,16]");
+    if (n_q < 1 || n_p < 0 || n_q + n_p > FHE_MAX_LIMBS || n_q + n_p > FHE_MAX_DST)
+        return fail("fhe_ctx_create: too many limbs");
+    if (alpha < 1 || alpha > FHE_MAX_SRC || n_p > FHE_MAX_SRC) return fail("fhe_ctx_create: digit size out of range");
+    if (cudaSetDevice(device) != cudaSuccess) return fail("fhe_ctx_create: cudaSetDevice failed");
+    fhe_ctx* c = new fhe_ctx;
+    c->log_n = log_n; c->n = 1 << log_n; c->n_q = n_q; c->n_p = n_p; c->alpha = alpha; c->tot = n_q + n_p;
+    c->device = device;
+    const int n = c->n, tot = c->tot;
+    c->q.assign(moduli, moduli + tot);
+    std::vector<Modulus> mods(tot);
+    std::vector<ShoupConst> twf((size_t)tot * n), twi((size_t)tot * n), fin(2 * (size_t)tot);
+    for (int l = 0; l < tot; ++l) {
+        const u64 q = (u64)moduli[l];
+        if (q >= (1ull << 61) || (q - 1) % (2ull * n) != 0) { delete c; return fail("fhe_ctx_create: modulus must be < 2^61 and = 1 mod 2N"); }
+        if (h_pow(psi[l], n, q) != q - 1) { delete c; return fail("fhe_ctx_create: psi is not a primitive 2N-th root"); }
+        mods[l] = h_modulus(q);
+        const u64 ipsi = h_inv(psi[l], q);
+        std::vector<u64> pw(n), ipw(n);
+        pw[0] = 1; ipw[0] = 1;
+        for (int k = 1; k < n; ++k) { pw[k] = h_mul(pw[k - 1], psi[l], q); ipw[k] = h_mul(ipw[k - 1], ipsi, q); }
+        for (int k = 0; k < n; ++k) {
+            const u32 r = h_brev((u32)k, log_n);
+            twf[(size_t)l * n + k] = h_shoup(pw[r], q);
+            twi[(size_t)l * n + k] = h_shoup(ipw[r], q);
+        }
+        const u64 ninv = h_inv((u64)n % q, q);
+        fin[2 * (size_t)l] = h_shoup(ninv, q);
+        fin[2 * (size_t)l + 1] = h_shoup(h_mul(ninv, twi[(size_t)l * n + 1].w, q), q);
+    }
+    Modulus* d_mod = to_device(mods);
+    ShoupConst* d_twf = to_device(twf);
+    ShoupConst* d_twi = to_device(twi);
+    ShoupConst* d_fin = to_device(fin);
+    if (!d_mod || !d_twf || !d_twi || !d_fin) { delete c; return fail("fhe_ctx_create: device allocation failed"); }
+    c->owned = {d_mod, d_twf, d_twi, d_fin};
+    c->T.mod = d_mod; c->T.tw_fwd = d_twf; c->T.tw_inv = d_twi; c->T.inv_final = d_fin;
+    c->T.log_n = log_n; c->T.n_q = n_q; c->T.n_p = n_p;
+    build_level_tables(c);
+    *out = c;
+    return check("fhe_ctx_create");
+}
+
+void fhe_ctx_destroy(fhe_ctx* c) {
+    if (!c) return;
+    cudaDeviceSynchronize();
+    for (void* p : c->owned) cudaFree(p);
+    if (c->scratch) cudaFree(c->scratch);
+    delete c;
+}
+
+int fhe_ntt_fwd(fhe_ctx* c, void* stream, uint64_t* data, int npoly, int nq, int np) {
+    if (bad_shape(c, nq, np) || npoly < 1) return fail("fhe_ntt_fwd: bad shape");
+    const int rpp = nq + np;
+    RowMap m = make_map(c, rpp, 0, nq);
+    const long long ps = (long long)rpp * c->n;
+    LoadPlain ld; ld.src = (const u64*)data; ld.poly_stride = ps;
+    StorePlain st; st.dst = (u64*)data; st.poly_stride = ps;
+    ntt_forward(c->T, m, npoly * rpp, ld, (u64*)data, ps, st, (cudaStream_t)stream);
+    g_launches.fetch_add(2);
+    return check("fhe_ntt_fwd");
+}
+
+int fhe_ntt_inv(fhe_ctx* c, void* stream, uint64_t* data, int npoly, int nq, int np) {
+    if (bad_shape(c, nq, np) || npoly < 1) return fail("fhe_ntt_inv: bad shape");
+    const int rpp = nq + np;
+    RowMap m = make_map(c, rpp, 0, nq);
+    const long long ps = (long long)rpp * c->n;
+    LoadPlain ld; ld.src = (const u64*)data; ld.poly_stride = ps;
+    StorePlain st; st.dst = (u64*)data; st.poly_stride = ps;
+    ntt_inverse(c->T, m, npoly * rpp, ld, (u64*)data, ps, st, nullptr, (cudaStream_t)stream);
+    g_launches.fetch_add(2);
+    return check("fhe_ntt_inv");
+}
+
+static int binary(int op, fhe_ctx* c, void* stream, uint64_t* out, const uint64_t* a, const uint64_t* b,
+                  int npoly, int npoly_b, int nq, int np) {
+    if (bad_shape(c, nq, np) || npoly < 1 || (npoly_b != npoly && npoly_b != 1)) return fail("fhe_add/sub/mul: bad shape");
+    const int rpp = nq + np;
+    RowMap m = make_map(c, rpp, 0, nq);
+    const long long ps = (long long)rpp * c->n;
+    const long long bs = npoly_b == 1 && npoly > 1 ? 0 : ps;
+    dim3 grid(c->n / 256, npoly * rpp), block(256);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (op == 0) launch(k_binary<0>, grid, block, s, c->T, m, (u64*)out, (const u64*)a, (const u64*)b, ps, ps, bs);
+    else if (op == 1) launch(k_binary<1>, grid, block, s, c->T, m, (u64*)out, (const u64*)a, (const u64*)b, ps, ps, bs);
+    else launch(k_binary<2>, grid, block, s, c->T, m, (u64*)out, (const u64*)a, (const u64*)b, ps, ps, bs);
+    return check("fhe_binary");
+}
+int fhe_add(fhe_ctx* c, void* s, uint64_t* o, const uint64_t* a, const uint64_t* b, int npoly, int npoly_b, int nq, int np) {
+    return binary(0, c, s, o, a, b, npoly, npoly_b, nq, np);
+}
+int fhe_sub(fhe_ctx* c, void* s, uint64_t* o, const uint64_t* a, const uint64_t* b, int npoly, int npoly_b, int nq, int np) {
+    return binary(1, c, s, o, a, b, npoly, npoly_b, nq, np);
+}
+int fhe_mul(fhe_ctx* c, void* s, uint64_t* o, const uint64_t* a, const uint64_t* b, int npoly, int npoly_b, int nq, int np) {
+    return binary(2, c, s, o, a, b, npoly, npoly_b, nq, np);
+}
+
+int fhe_neg(fhe_ctx* c, void* stream, uint64_t* out, const uint64_t* a, int npoly, int nq, int np) {
+    if (bad_shape(c, nq, np) || npoly < 1) return fail("fhe_neg: bad shape");
+    const int rpp = nq + np;
+    launch(k_neg, dim3(c->n / 256, npoly * rpp), dim3(256), (cudaStream_t)stream, c->T, make_map(c, rpp, 0, nq),
+           (u64*)out, (const u64*)a);
+    return check("fhe_neg");
+}
+
+int fhe_tensor(fhe_ctx* c, void* stream, uint64_t* out, const uint64_t* a, const uint64_t* b, int nq) {
+    if (bad_shape(c, nq, 0)) return fail("fhe_tensor: bad shape");
+    launch(k_tensor, dim3(c->n / 256, nq), dim3(256), (cudaStream_t)stream, c->T, nq, (u64*)out, (const u64*)a,
+           (const u64*)b);
+    return check("fhe_tensor");
+}
+
+static int constop(int add, fhe_ctx* c, void* stream, uint64_t* out, const uint64_t* a, const uint64_t* c1,
+                   const uint64_t* c2, int npoly, int nq, int np) {
+    if (bad_shape(c, nq, np) || npoly < 1 || !c1 || !c2) return fail("fhe_mul_const/add_const: bad shape");
+    const int rpp = nq + np;
+    LimbConsts k;
+    for (int j = 0; j < rpp; ++j) { k.a[j] = c1[j]; k.b[j] = c2[j]; }
+    dim3 grid(c->n / 256, npoly * rpp), block(256);
+    RowMap m = make_map(c, rpp, 0, nq);
+    if (add) launch(k_const<1>, grid, block, (cudaStream_t)stream, c->T, m, (u64*)out, (const u64*)a, k);
+    else launch(k_const<0>, grid, block, (cudaStream_t)stream, c->T, m, (u64*)out, (const u64*)a, k);
+    return check("fhe_const");
+}
+int fhe_mul_const(fhe_ctx* c, void* s, uint64_t* o, const uint64_t* a, const uint64_t* c1, const uint64_t* c2,
+                  int npoly, int nq, int np) { return constop(0, c, s, o, a, c1, c2, npoly, nq, np); }
+int fhe_add_const(fhe_ctx* c, void* s, uint64_t* o, const uint64_t* a, const uint64_t* c1, const uint64_t* c2,
+                  int npoly, int nq, int np) { return constop(1, c, s, o, a, c1, c2, npoly, nq, np); }
+
+int fhe_rescale(fhe_ctx* c, void* stream, uint64_t* out, const uint64_t* in, int npoly, int nq) {
+    if (bad_shape(c, nq, 0) || nq < 2 || npoly < 1) return fail("fhe_rescale: bad shape");
+    cudaStream_t s = (cudaStream_t)stream;
+    const int n = c->n;
+    u64* last = arena(c, (size_t)npoly * n);
+    if (!last) return fail("fhe_rescale: scratch allocation failed");
+    // 1) dropped limb -> coefficient domain
+    {
+        RowMap m = make_map(c, 1, nq - 1, nq);
+        LoadPlain ld; ld.src = (const u64*)in + (size_t)(nq - 1) * n; ld.poly_stride = (long long)nq * n;
+        StorePlain st; st.dst = last; st.poly_stride = n;
+        ntt_inverse(c->T, m, npoly, ld, last, n, st, nullptr, s);
+    }
+    // 2) per remaining limb: NTT(centred remainder), out = (in - it) * q_last^-1
+    {
+        const int rpp = nq - 1;
+        RowMap m = make_map(c, rpp, 0, nq);
+        LoadCentered ld; ld.last = last; ld.q_last = c->q[nq - 1];
+        StoreSubMul st; st.out = (u64*)out; st.out_poly_stride = (long long)rpp * n;
+        st.in = (const u64*)in; st.in_poly_stride = (long long)nq * n; st.c = c->rescale_c[nq];
+        ntt_forward(c->T, m, npoly * rpp, ld, (u64*)out, (long long)rpp * n, st, s);
+    }
+    g_launches.fetch_add(4);
+    return check("fhe_rescale");
+}
+
+int fhe_automorphism(fhe_ctx* c, void* stream, uint64_t* out, const uint64_t* in, uint64_t galois, int nrows) {
+    if (!c || nrows < 1 || !(galois & 1)) return fail("fhe_automorphism: bad arguments");
+    launch(k_automorphism, dim3(c->n / 256, nrows), dim3(256), (cudaStream_t)stream, c->log_n, (u64*)out,
+           (const u64*)in, (u64)galois);
+    return check("fhe_automorphism");
+}
+
+int fhe_modup(fhe_ctx* c, void* stream, uint64_t* ext, const uint64_t* d, int nq) {
+    if (bad_shape(c, nq, 0) || c->n_p == 0) return fail("fhe_modup: bad shape");
+    cudaStream_t s = (cudaStream_t)stream;
+    const int n = c->n, ne = nq + c->n_p, beta = c->modup_beta[nq];
+    u64* y = arena(c, (size_t)nq * n);
+    if (!y) return fail("fhe_modup: scratch allocation failed");
+    {   // iNTT with the (Q_j/q_i)^-1 factor folded into the final stage
+        RowMap m = make_map(c, nq, 0, nq);
+        LoadPlain ld; ld.src = (const u64*)d; ld.poly_stride = (long long)nq * n;
+        StorePlain st; st.dst = y; st.poly_stride = (long long)nq * n;
+        ntt_inverse(c->T, m, nq, ld, y, (long long)nq * n, st, c->modup_scale[nq], s);
+    }
+    launch_bconv(c, s, std::min(c->alpha, nq), beta, c->modup_tables[nq], beta, (u64*)ext, (long long)ne * n, y, 0);
+    {   // NTT of every converted row (a digit's own limbs are skipped)
+        RowMap m = make_map(c, ne, 0, nq, c->alpha);
+        LoadPlain ld; ld.src = (const u64*)ext; ld.poly_stride = (long long)ne * n;
+        StorePlain st; st.dst = (u64*)ext; st.poly_stride = (long long)ne * n;
+        ntt_forward(c->T, m, beta * ne, ld, (u64*)ext, (long long)ne * n, st, s);
+    }
+    g_launches.fetch_add(4);
+    return check("fhe_modup");
+}
+
+int fhe_ks_inner(fhe_ctx* c, void* stream, uint64_t* acc, const uint64_t* ext, const uint64_t* d,
+                 const uint64_t* ksk, int nq) {
+    if (bad_shape(c, nq, 0) || c->n_p == 0) return fail("fhe_ks_inner: bad shape");
+    launch(k_ks_inner, dim3(c->n / 256, nq + c->n_p), dim3(256), (cudaStream_t)stream, c->T, nq, c->alpha,
+           c->modup_beta[nq], (u64*)acc, (const u64*)ext, (const u64*)d, (const u64*)ksk);
+    return check("fhe_ks_inner");
+}
+
+int fhe_moddown(fhe_ctx* c, void* stream, uint64_t* out, uint64_t* acc, int nq, int npoly) {
+    if (bad_shape(c, nq, 0) || c->n_p == 0 || npoly < 1 || npoly > 4) return fail("fhe_moddown: bad shape");
+    cudaStream_t s = (cudaStream_t)stream;
+    const int n = c->n, K = c->n_p, ne = nq + K;
+    u64* accp = (u64*)acc + (size_t)nq * n;
+    {   // special limbs -> coefficient domain, times (P/p_k)^-1, in place
+        RowMap m = make_map(c, K, nq, nq);
+        LoadPlain ld; ld.src = accp; ld.poly_stride = (long long)ne * n;
+        StorePlain st; st.dst = accp; st.poly_stride = (long long)ne * n;
+        ntt_inverse(c->T, m, npoly * K, ld, accp, (long long)ne * n, st, c->moddown_scale, s);
+    }
+    // P -> q_i conversion written straight into `out` (coefficient domain) ...
+    launch_bconv(c, s, K, npoly, c->moddown_table[nq], 1, (u64*)out, (long long)nq * n, accp, (long long)ne * n);
+    {   // ... then NTT it in place and finish: out = (acc - it) * P^-1
+        RowMap m = make_map(c, nq, 0, nq);
+        LoadPlain ld; ld.src = (const u64*)out; ld.poly_stride = (long long)nq * n;
+        StoreSubMul st; st.out = (u64*)out; st.out_poly_stride = (long long)nq * n;
+        st.in = (const u64*)acc; st.in_poly_stride = (long long)ne * n; st.c = c->pinv;
+        ntt_forward(c->T, m, npoly * nq, ld, (u64*)out, (long long)nq * n, st, s);
+    }
+    g_launches.fetch_add(4);
+    return check("fhe_moddown");
+}
+
+int fhe_keyswitch(fhe_ctx* c, void* stream, uint64_t* out, const uint64_t* d, const uint64_t* ksk, int nq) {
+    if (bad_shape(c, nq, 0) || c->n_p == 0) return fail("fhe_keyswitch: bad shape");
+    const int n = c->n, ne = nq + c->n_p, beta = c->modup_beta[nq];
+    // arena layout: [y : nq][ext : beta*ne][acc : 2*ne]   (fhe_modup uses the first nq rows)
+    const size_t words = ((size_t)nq + (size_t)beta * ne + 2 * (size_t)ne) * n;
+    u64* base = arena(c, words);
+    if (!base) return fail("fhe_keyswitch: scratch allocation failed");
+    u64* ext = base + (size_t)nq * n;
+    u64* acc = ext + (size_t)beta * ne * n;
+    int rc;
+    if ((rc = fhe_modup(c, stream, (uint64_t*)ext, d, nq))) return rc;
+    if ((rc = fhe_ks_inner(c, stream, (uint64_t*)acc, (const uint64_t*)ext, d, ksk, nq))) return rc;
+    return fhe_moddown(c, stream, out, (uint64_t*)acc, nq, 2);
+}
+
+int fhe_from_i64(fhe_ctx* c, void* stream, uint64_t* out, const int64_t* coeffs, int nq, int np) {
+    if (bad_shape(c, nq, np)) return fail("fhe_from_i64: bad shape");
+    const int rpp = nq + np;
+    launch(k_from_i64, dim3(c->n / 256, rpp), dim3(256), (cudaStream_t)stream, c->T, make_map(c, rpp, 0, nq),
+           (u64*)out, (const long long*)coeffs);
+    return check("fhe_from_i64");
+}
+
+int fhe_crt_centered(fhe_ctx* c, void* stream, double* out, const uint64_t* x, int limbs) {
+    if (!c || limbs < 1 || limbs > 2 || limbs > c->n_q) return fail("fhe_crt_centered: bad shape");
+    launch(k_crt_centered, dim3(c->n / 256), dim3(256), (cudaStream_t)stream, c->T, out, (const u64*)x, limbs,
+           c->q0inv_mod_q1);
+    return check("fhe_crt_centered");
+}
+
+}  // extern "C"

@@ -1,0 +1,219 @@
+// kernels.cuh -- streaming (HBM-bound) kernels around the NTT: ciphertext arithmetic,
+// Galois permutation, hybrid key-switch phases (base conversion, key inner product) and
+// the fused load/store functors used by rescale and ModDown.
+//
+// Layout convention: a "poly block" is [rows_per_poly][N] u64, blocks are contiguous unless
+// a stride is given.  One thread handles one coefficient index of one row (or of all rows
+// when a contraction over limbs is involved); consecutive threads touch consecutive
+// addresses, so every access is a full 128-byte line per half-warp.
+#pragma once
+#include "ntt.cuh"
+
+#define FHE_MAX_SRC 16      // max limbs in one base-conversion source basis (alpha, K)
+#define FHE_MAX_DST 48      // max target limbs of one base conversion
+#define FHE_MAX_LIMBS 48
+
+struct LimbConsts {          // per-limb-slot constants passed by value
+    u64 a[FHE_MAX_LIMBS];
+    u64 b[FHE_MAX_LIMBS];
+};
+
+// ---------------------------------------------------------------- elementwise
+// op: 0 add, 1 sub, 2 mul      b is broadcast over polys when b_poly_stride == 0
+template <int OP>
+__global__ void __launch_bounds__(256) k_binary(DevTables T, RowMap map, u64* out, const u64* a, const u64* b,
+                                                long long o_poly_stride, long long a_poly_stride, long long b_poly_stride) {
+    const int row = blockIdx.y;
+    const int mid = map.mod_id(row);
+    const Modulus M = T.mod[mid];
+    const u32 idx = blockIdx.x * 256 + threadIdx.x;
+    const int poly = row / map.rows_per_poly, j = row % map.rows_per_poly;
+    const size_t lo = ((size_t)j << map.log_n) + idx;
+    const u64 x = a[(size_t)poly * a_poly_stride + lo];
+    const u64 y = b[(size_t)poly * b_poly_stride + lo];
+    u64 r;
+    if (OP == 0) r = add_mod(x, y, M.q);
+    else if (OP == 1) r = sub_mod(x, y, M.q);
+    else r = mul_mod(x, y, M);
+    out[(size_t)poly * o_poly_stride + lo] = r;
+}
+
+__global__ void __launch_bounds__(256) k_neg(DevTables T, RowMap map, u64* out, const u64* a) {
+    const int row = blockIdx.y;
+    const Modulus M = T.mod[map.mod_id(row)];
+    const size_t o = ((size_t)row << map.log_n) + blockIdx.x * 256 + threadIdx.x;
+    out[o] = neg_mod(a[o], M.q);
+}
+
+// d0 = a0 b0, d1 = a0 b1 + a1 b0, d2 = a1 b1      rows: nq limbs
+__global__ void __launch_bounds__(256) k_tensor(DevTables T, int nq, u64* d, const u64* a, const u64* b) {
+    const int j = blockIdx.y;
+    const Modulus M = T.mod[j];
+    const size_t n = (size_t)1 << T.log_n;
+    const size_t o = (size_t)j * n + blockIdx.x * 256 + threadIdx.x;
+    const size_t ps = (size_t)nq * n;
+    const u64 a0 = a[o], a1 = a[o + ps], b0 = b[o], b1 = b[o + ps];
+    d[o] = mul_mod(a0, b0, M);
+    u128t acc = mul_wide(a0, b1);
+    acc_wide(acc, a1, b0);
+    d[o + ps] = barrett_reduce(acc, M);
+    d[o + 2 * ps] = mul_mod(a1, b1, M);
+}
+
+// out = a * (first half of spectrum ? c.a[j] : c.b[j])   (complex constant, see encoding.py)
+// ADD != 0: out = a + constant instead.
+template <int ADD>
+__global__ void __launch_bounds__(256) k_const(DevTables T, RowMap map, u64* out, const u64* a, LimbConsts c) {
+    const int row = blockIdx.y;
+    const int mid = map.mod_id(row);
+    const Modulus M = T.mod[mid];
+    const u32 idx = blockIdx.x * 256 + threadIdx.x;
+    const int j = row % map.rows_per_poly;
+    const u64 k = (idx >> (map.log_n - 1)) ? c.b[j] : c.a[j];
+    const size_t o = ((size_t)row << map.log_n) + idx;
+    out[o] = ADD ? add_mod(a[o], k, M.q) : mul_mod(a[o], k, M);
+}
+
+// NTT-domain automorphism X -> X^g on bit-reversed spectra: out[p] = in[perm(p)]
+__global__ void __launch_bounds__(256) k_automorphism(int log_n, u64* out, const u64* in, u64 g) {
+    const u32 p = blockIdx.x * 256 + threadIdx.x;
+    const size_t ro = (size_t)blockIdx.y << log_n;
+    const u32 k = brev32(p) >> (32 - log_n);
+    const u32 mask = (2u << log_n) - 1;
+    const u32 kk = (u32)((g * (u64)(2 * k + 1)) & mask) >> 1;
+    const u32 src = brev32(kk) >> (32 - log_n);
+    out[ro + p] = in[ro + src];
+}
+
+// signed coefficients -> residues of every row's modulus
+__global__ void __launch_bounds__(256) k_from_i64(DevTables T, RowMap map, u64* out, const long long* coeffs) {
+    const int row = blockIdx.y;
+    const Modulus M = T.mod[map.mod_id(row)];
+    const u32 idx = blockIdx.x * 256 + threadIdx.x;
+    const long long v = coeffs[idx];
+    u64 r;
+    if (v >= 0) r = reduce_u64((u64)v, M);
+    else r = neg_mod(reduce_u64((u64)(-v), M), M.q);
+    out[((size_t)row << map.log_n) + idx] = r;
+}
+
+// centred CRT of limbs (0,1) (or limb 0 alone) to double
+__global__ void __launch_bounds__(256) k_crt_centered(DevTables T, double* out, const u64* x, int limbs, u64 q0inv_mod_q1) {
+    const u32 idx = blockIdx.x * 256 + threadIdx.x;
+    const Modulus M0 = T.mod[0];
+    const u64 x0 = x[idx];
+    if (limbs < 2) {
+        out[idx] = x0 > (M0.q >> 1) ? -(double)(M0.q - x0) : (double)x0;
+        return;
+    }
+    const Modulus M1 = T.mod[1];
+    const u64 x1 = x[((size_t)1 << T.log_n) + idx];
+    const u64 t = mul_mod(sub_mod(x1, reduce_u64(x0, M1), M1.q), q0inv_mod_q1, M1);
+    // v = x0 + q0 * t  in [0, q0 q1);  compare with Q/2 and negate in 128 bits
+    u128t v = mul_wide(M0.q, t);
+    v.lo += x0; v.hi += (v.lo < x0);
+    u128t Q = mul_wide(M0.q, M1.q);
+    u128t h; h.lo = (Q.lo >> 1) | (Q.hi << 63); h.hi = Q.hi >> 1;
+    const bool neg = v.hi > h.hi || (v.hi == h.hi && v.lo > h.lo);
+    if (neg) { u128t w; w.lo = Q.lo - v.lo; w.hi = Q.hi - v.hi - (Q.lo < v.lo); v = w; }
+    const double d = (double)v.hi * 18446744073709551616.0 + (double)v.lo;
+    out[idx] = neg ? -d : d;
+}
+
+// ---------------------------------------------------------------- base conversion
+// One table per source basis.  Output value for target t:
+//     sum_k y_k * f[k][t]  -  #{k : y_k > q_k/2} * qmod[t]      (mod m_t)
+// where y_k (already multiplied by (Q/q_k)^-1 mod q_k by the preceding iNTT) is the k-th
+// source row.  Centred digits make the conversion error zero-mean (see oracle/refmod.cpp).
+struct BConvTable {
+    int ns, nt;
+    int src_mod[FHE_MAX_SRC];
+    int src_slot[FHE_MAX_SRC];      // row slot of source k inside the source group
+    int dst_mod[FHE_MAX_DST];
+    int dst_slot[FHE_MAX_DST];      // row slot of target t inside the destination group
+    u64 f[FHE_MAX_SRC][FHE_MAX_DST];
+    u64 qmod[FHE_MAX_DST];
+};
+
+// grid: (N/256, groups).  group g uses table g % n_tables.  NS_MAX bounds every table's ns.
+template <int NS_MAX>
+__global__ void __launch_bounds__(256) k_bconv(DevTables T, const BConvTable* tables, int n_tables,
+                                               u64* dst, long long dst_group_stride,
+                                               const u64* src, long long src_group_stride) {
+    const int g = blockIdx.y;
+    const BConvTable& tb = tables[g % n_tables];
+    const u32 idx = blockIdx.x * 256 + threadIdx.x;
+    const int log_n = T.log_n;
+    const u64* s = src + (size_t)g * src_group_stride + idx;
+    u64* d = dst + (size_t)g * dst_group_stride + idx;
+    u64 y[NS_MAX];
+    u64 neg = 0;
+    const int ns = tb.ns;
+#pragma unroll
+    for (int k = 0; k < NS_MAX; ++k) {
+        if (k < ns) {
+            y[k] = s[(size_t)tb.src_slot[k] << log_n];
+            neg += y[k] > (T.mod[tb.src_mod[k]].q >> 1);
+        } else y[k] = 0;
+    }
+    for (int t = 0; t < tb.nt; ++t) {
+        const Modulus M = T.mod[tb.dst_mod[t]];
+        u128t acc; acc.lo = 0; acc.hi = 0;
+#pragma unroll
+        for (int k = 0; k < NS_MAX; ++k)
+            if (k < ns) acc_wide(acc, y[k], tb.f[k][t]);
+        u64 r = barrett_reduce(acc, M);
+        r = sub_mod(r, mul_mod(neg, tb.qmod[t], M), M.q);
+        d[(size_t)tb.dst_slot[t] << log_n] = r;
+    }
+}
+
+// ---------------------------------------------------------------- key inner product
+// acc[c][t] = sum_j e_j[t] * ksk[j][c][id(t)],  e_j[t] = d[t] if t in digit j else ext[j][t]
+// grid: (N/256, nq + n_p)      ksk: [dnum][2][n_q_total + n_p][N]
+__global__ void __launch_bounds__(256) k_ks_inner(DevTables T, int nq, int alpha, int beta,
+                                                  u64* acc, const u64* ext, const u64* d, const u64* ksk) {
+    const int t = blockIdx.y;
+    const int ne = nq + T.n_p;
+    const int id = t < nq ? t : T.n_q + (t - nq);
+    const Modulus M = T.mod[id];
+    const int log_n = T.log_n;
+    const u32 idx = blockIdx.x * 256 + threadIdx.x;
+    const size_t tot = (size_t)(T.n_q + T.n_p);
+    u128t a0; a0.lo = 0; a0.hi = 0;
+    u128t a1 = a0;
+    for (int j = 0; j < beta; ++j) {
+        const bool own = t < nq && t >= j * alpha && t < (j + 1) * alpha;
+        const u64 e = own ? d[((size_t)t << log_n) + idx] : ext[(((size_t)j * ne + t) << log_n) + idx];
+        const u64* k0 = ksk + ((((size_t)j * 2) * tot + id) << log_n) + idx;
+        acc_wide(a0, e, k0[0]);
+        acc_wide(a1, e, k0[tot << log_n]);
+    }
+    acc[((size_t)t << log_n) + idx] = barrett_reduce(a0, M);
+    acc[((size_t)(ne + t) << log_n) + idx] = barrett_reduce(a1, M);
+}
+
+// ---------------------------------------------------------------- fused NTT functors
+// rescale: load the centred remainder of the dropped limb, reduced into the row's modulus
+struct LoadCentered {
+    const u64* last;            // [npoly][N] coefficient-domain rows of the dropped limb
+    u64 q_last;
+    FHE_D u64 operator()(const RowMap& map, int row, u32 idx, int, const Modulus& M) const {
+        const u64 v = last[((size_t)(row / map.rows_per_poly) << map.log_n) + idx];
+        if (v > (q_last >> 1)) return neg_mod(reduce_u64(q_last - v, M), M.q);
+        return reduce_u64(v, M);
+    }
+};
+// rescale / ModDown epilogue: out = (in - ntt_value) * c[j]
+struct StoreSubMul {
+    u64* out; long long out_poly_stride;
+    const u64* in; long long in_poly_stride;
+    const ShoupConst* c;        // per limb slot j
+    FHE_D void operator()(const RowMap& map, int row, u32 idx, u64 v, int, const Modulus& M) const {
+        const int poly = row / map.rows_per_poly, j = row % map.rows_per_poly;
+        const size_t lo = ((size_t)j << map.log_n) + idx;
+        const u64 x = in[(size_t)poly * in_poly_stride + lo];
+        const ShoupConst k = c[j];
+        out[(size_t)poly * out_poly_stride + lo] = mul_shoup(sub_mod(x, v, M.q), k.w, k.ws, M.q);
+    }
+};

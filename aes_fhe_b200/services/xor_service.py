@@ -1,0 +1,222 @@
+"""4-bit XOR LUT service (AddRoundKey primitive).  Mirror of /root/reference/xor_service.py:
+XORConfig (:16-33), EngineWrapper (:36-129), ZetaEncoder (:132-145), CoefficientCache
+(:148-196), FullXORCache (:199-224), XORService (:227-552).
+
+``XORService.xor_cipher`` reproduces the reference's operation sequence exactly (two power
+bases to degree 8 + conjugates, 64 relinearised products, 64 constant multiplications);
+``xor_cipher_fused`` evaluates the same polynomial with lazy relinearisation (2 key switches
+after the bases instead of 64) -- same slots within CKKS noise, different residues.
+"""
+from __future__ import annotations
+
+from pathlib import Path
+from typing import Any, Dict, Optional, Sequence, Tuple
+
+import numpy as np
+
+from ..engine import Ciphertext, Engine
+from . import lut
+from .engine_context import EngineContext
+
+
+class XORConfig:
+    """Accepts the reference's five parameters plus the extra paths its tests pass
+    (test/test_xor_service.py:17-26 -- SURVEY defect D1)."""
+
+    def __init__(self, coeffs_path: Optional[Path] = None, max_level: int = 33, mode: str = "parallel",
+                 thread_count: int = 8, device_id: int = 0, nibble_hi_path: Optional[Path] = None,
+                 nibble_lo_path: Optional[Path] = None, mul_coeffs_path: Optional[Path] = None):
+        self.coeffs_path = Path(coeffs_path) if coeffs_path is not None else lut.ensure_default_files()["xor"]
+        self.max_level = max_level
+        self.mode = mode
+        self.thread_count = thread_count
+        self.device_id = device_id
+        self.nibble_hi_path = nibble_hi_path
+        self.nibble_lo_path = nibble_lo_path
+        self.mul_path = mul_coeffs_path
+
+
+class EngineWrapper:
+    def __init__(self, config: XORConfig, _engine_kwargs: Optional[dict] = None,
+                 rotation_steps: Optional[Sequence[int]] = None):
+        ctx = EngineContext(signature=1, use_bootstrap=True, max_level=config.max_level, mode=config.mode,
+                            thread_count=config.thread_count, device_id=config.device_id,
+                            _engine_kwargs=_engine_kwargs, rotation_steps=rotation_steps)
+        self.ctx = ctx
+        self.engine: Engine = ctx.engine
+        self.public_key = ctx.public_key
+        self.secret_key = ctx.secret_key
+        self.relin_key = ctx.relinearization_key
+        self.conj_key = ctx.conjugation_key
+        self.rot_key = ctx.rotation_key
+        self.boot_key = ctx.bootstrap_key
+
+    def encrypt(self, data: np.ndarray):
+        return self.engine.encrypt(data, self.public_key)
+
+    def decrypt(self, ct) -> np.ndarray:
+        return self.engine.decrypt(ct, self.secret_key)
+
+    def encode(self, vec: np.ndarray):
+        return self.engine.encode(vec)
+
+    def multiply(self, a, b, relin_key=None):
+        if isinstance(a, Ciphertext) and isinstance(b, Ciphertext):
+            return self.engine.multiply(a, b, relin_key or self.relin_key)
+        return self.engine.multiply(a, b)
+
+    def add(self, a, b):
+        return self.engine.add(a, b)
+
+    def add_plain(self, ct, val):
+        return self.engine.add_plain(ct, val)
+
+    def make_power_basis(self, ct, degree: int):
+        return self.engine.make_power_basis(ct, degree, self.relin_key)
+
+    def conjugate(self, ct):
+        return self.engine.conjugate(ct, self.conj_key)
+
+    def multiply_plain(self, ct, val):
+        if np.isscalar(val):
+            return self.engine.multiply(ct, val)
+        return self.engine.multiply(ct, self.engine.encode(np.array(val, dtype=np.complex128)))
+
+    def rotate(self, ct, steps: int):
+        return self.engine.rotate(ct, self.rot_key, steps)
+
+    def relinearize(self, ct, relin_key=None):
+        try:
+            return self.engine.relinearize(ct, relin_key or self.relin_key)
+        except RuntimeError as e:
+            if "should have 3 polynomials" in str(e):
+                return ct
+            raise
+
+    def bootstrap(self, ct):
+        return self.engine.bootstrap(ct, self.relin_key, self.conj_key, self.boot_key)
+
+
+class ZetaEncoder:
+    """x -> exp(-2*pi*i*x/m) and back (xor_service.py:132-145).  The cast to int64 keeps
+    uint8 inputs working with modulus 256 on NumPy 2 (SURVEY defect D4)."""
+
+    @staticmethod
+    def to_zeta(arr: np.ndarray, modulus: int = 16) -> np.ndarray:
+        a = np.asarray(arr).astype(np.int64) % modulus
+        return np.exp(-2j * np.pi * a / modulus)
+
+    @staticmethod
+    def from_zeta(z_arr: np.ndarray, modulus: int = 16) -> np.ndarray:
+        k = (-np.angle(z_arr) * modulus) / (2 * np.pi)
+        return np.mod(np.rint(k), modulus).astype(np.uint8)
+
+
+class CoefficientCache:
+    def __init__(self, path: Path):
+        self.path = Path(path)
+        self._coeffs: Optional[Dict[Any, complex]] = None
+        self._plain_cache: Dict[int, Dict[Any, object]] = {}
+
+    def load_coeffs(self) -> Dict[Any, complex]:
+        if self._coeffs is None:
+            self._coeffs = lut.load_entries(self.path)
+        return self._coeffs
+
+    def get_plaintext_coeffs(self, engine_wrapper: EngineWrapper) -> Dict[Any, object]:
+        sc = engine_wrapper.engine.slot_count
+        if sc not in self._plain_cache:
+            self._plain_cache[sc] = {key: engine_wrapper.encode(np.full(sc, val, dtype=np.complex128))
+                                     for key, val in self.load_coeffs().items()}
+        return self._plain_cache[sc]
+
+
+class FullXORCache(CoefficientCache):
+    """256x256 two-input LUT (xor_service.py:199-224); same loader, 4-field entries."""
+
+
+class XORService:
+    def __init__(self, engine_wrapper: EngineWrapper, coeff_cache: CoefficientCache,
+                 nibble_hi_path: Optional[CoefficientCache] = None,
+                 nibble_lo_path: Optional[CoefficientCache] = None,
+                 full_xor_cache: Optional[FullXORCache] = None):
+        self.eng_wrap = engine_wrapper
+        self.coeff_cache = coeff_cache
+        self.nibble_hi_cache = nibble_hi_path
+        self.nibble_lo_cache = nibble_lo_path
+        self.full_xor_cache = full_xor_cache
+
+    @property
+    def eng(self) -> EngineWrapper:
+        return self.eng_wrap
+
+    # -- power basis t^0..t^15 of a zeta_16-valued ciphertext (xor_service.py:245-254)
+    def _build_power_basis(self, ct) -> Dict[int, object]:
+        eng = self.eng_wrap
+        pos = eng.make_power_basis(ct, 8)
+        basis = {0: eng.add_plain(ct, 1.0)}
+        for k, c in enumerate(pos, 1):
+            basis[k] = c
+        for k in range(1, 8):
+            basis[16 - k] = eng.conjugate(pos[k - 1])      # |t| = 1  =>  t^(16-k) = conj(t^k)
+        return basis
+
+    def xor_cipher(self, enc_a, enc_b):
+        """zeta_16^a, zeta_16^b -> zeta_16^(a xor b): sum over the 64 odd-odd monomials
+        (xor_service.py:271-286), reference operation order."""
+        eng = self.eng_wrap
+        if enc_a.level < 8:
+            enc_a = eng.bootstrap(enc_a)
+        if enc_b.level < 8:
+            enc_b = eng.bootstrap(enc_b)
+        bx = self._build_power_basis(enc_a)
+        by = self._build_power_basis(enc_b)
+        pts = self.coeff_cache.get_plaintext_coeffs(eng)
+        res = eng.multiply(enc_a, 0.0)
+        for (i, j), pt in pts.items():
+            term = eng.multiply(bx[i], by[j], eng.relin_key)
+            res = eng.add(res, eng.multiply(term, pt))
+        return res
+
+    def xor_cipher_fused(self, enc_a, enc_b):
+        """Same polynomial, restructured for the GPU: inner sums over j are constant
+        multiplications (no key switch), the 8 outer products are accumulated as degree-2
+        ciphertexts and relinearised once.  5 levels, 14 + 14 + 1 key switches."""
+        from ..fused import bivariate_lut
+        coeffs = np.zeros((16, 16), dtype=np.complex128)
+        for (i, j), c in self.coeff_cache.load_coeffs().items():
+            coeffs[i, j] = c
+        return bivariate_lut(self.eng_wrap, enc_a, enc_b, [coeffs])[0]
+
+    def xor(self, a_int: np.ndarray, b_int: np.ndarray) -> np.ndarray:
+        enc_a = self.eng_wrap.encrypt(ZetaEncoder.to_zeta(a_int))
+        enc_b = self.eng_wrap.encrypt(ZetaEncoder.to_zeta(b_int))
+        return ZetaEncoder.from_zeta(self.eng_wrap.decrypt(self.xor_cipher(enc_a, enc_b)))
+
+    def recombine_nibbles(self, hi_ct, lo_ct):
+        """zeta_16^hi, zeta_16^lo -> zeta_256^(16 hi + lo)?  The reference raises the hi
+        ciphertext to the 16th power and multiplies (xor_service.py:256-269); kept as is."""
+        hi16 = self.eng_wrap.make_power_basis(hi_ct, 16)[15]
+        return self.eng_wrap.multiply(hi16, lo_ct)
+
+    def xor_cipher_full(self, enc_a, enc_b):
+        """8-bit XOR through the 256x256 LUT (xor_service.py:288-307)."""
+        if self.full_xor_cache is None:
+            raise AttributeError("XORService was constructed without full_xor_cache")
+        eng = self.eng_wrap
+        pos = eng.make_power_basis(enc_a, 128)
+        posb = eng.make_power_basis(enc_b, 128)
+        ba = {k: pos[k - 1] for k in range(1, 129)}
+        bb = {k: posb[k - 1] for k in range(1, 129)}
+        for k in range(129, 256):
+            ba[k] = eng.conjugate(pos[256 - k - 1])
+            bb[k] = eng.conjugate(posb[256 - k - 1])
+        res = eng.multiply(enc_a, 0.0)
+        for (i, j), pt in self.full_xor_cache.get_plaintext_coeffs(eng).items():
+            res = eng.add(res, eng.multiply(eng.multiply(ba[i], bb[j], eng.relin_key), pt))
+        return res
+
+    def xor256(self, a_int, b_int):
+        enc_a = self.eng_wrap.encrypt(ZetaEncoder.to_zeta(a_int, modulus=256))
+        enc_b = self.eng_wrap.encrypt(ZetaEncoder.to_zeta(b_int, modulus=256))
+        return ZetaEncoder.from_zeta(self.eng_wrap.decrypt(self.xor_cipher_full(enc_a, enc_b)), modulus=256)

@@ -1,0 +1,107 @@
+/* aesfhe_b200.h -- C ABI of the B200 CKKS evaluation backend (libaesfhe_b200.so).
+ *
+ * This is the drop-in boundary below the reference's Python services.  The reference
+ * (songhayeong/aes-fhe) reaches its ciphertext arithmetic only through the Python API of
+ * the third-party module `desilofhe` (Engine / Ciphertext / Plaintext; import sites
+ * engine_context.py:6, xor_service.py:12,69, gf_service.py:7, new.py:6).  A maintainer
+ * binds these entry points with ctypes; every function below names the
+ * `desilofhe.Engine` member(s) whose arithmetic it replaces and the reference call sites.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; all data pointers are DEVICE pointers to 64-bit residues
+ *     unless stated otherwise; `stream` is a cudaStream_t passed as void*.
+ *   - a polynomial block is [nq + np][N] u64: the first nq active q-limbs (moduli 0..nq-1)
+ *     followed by np special limbs (np is 0 or the context's n_p); blocks of one call are
+ *     contiguous: [npoly][nq + np][N].  Residues are canonical [0,q), NTT domain
+ *     (bit-reversed spectrum) unless a function says "coefficient domain".
+ *   - return value 0 = ok; negative = error, text via fhe_last_error().  No function
+ *     synchronises the stream; nothing is allocated per call except when the context's
+ *     scratch arena has to grow (first call at a new size).
+ */
+#ifndef AESFHE_B200_H
+#define AESFHE_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct fhe_ctx fhe_ctx;
+
+/* Engine(...) construction (engine_context.py:32-56): builds twiddle / base-conversion
+ * tables on `device` for the RNS chain `moduli` = q_0..q_{n_q-1}, p_0..p_{n_p-1} with
+ * primitive 2N-th roots `psi` (host arrays of n_q + n_p entries); alpha = q-limbs per
+ * key-switch digit. */
+int fhe_ctx_create(fhe_ctx** out, int log_n, int n_q, int n_p, int alpha,
+                   const uint64_t* moduli, const uint64_t* psi, int device);
+void fhe_ctx_destroy(fhe_ctx* ctx);
+const char* fhe_last_error(void);
+/* number of kernels this library has launched since load (bench.py's gpu_launches) */
+uint64_t fhe_launch_count(void);
+
+/* Forward / inverse negacyclic NTT, in place.  Used by encode/encrypt/decrypt
+ * (xor_service.py:59-66) and inside every multiply / rotate / conjugate. */
+int fhe_ntt_fwd(fhe_ctx* ctx, void* stream, uint64_t* data, int npoly, int nq, int np);
+int fhe_ntt_inv(fhe_ctx* ctx, void* stream, uint64_t* data, int npoly, int nq, int np);
+
+/* Engine.add(ct, ct) / subtract / pointwise products (xor_service.py:76,
+ * sbox/sbox_service.py:105,112,129,136).  b is broadcast over polys when npoly_b == 1. */
+int fhe_add(fhe_ctx* ctx, void* stream, uint64_t* out, const uint64_t* a, const uint64_t* b,
+            int npoly, int npoly_b, int nq, int np);
+int fhe_sub(fhe_ctx* ctx, void* stream, uint64_t* out, const uint64_t* a, const uint64_t* b,
+            int npoly, int npoly_b, int nq, int np);
+int fhe_mul(fhe_ctx* ctx, void* stream, uint64_t* out, const uint64_t* a, const uint64_t* b,
+            int npoly, int npoly_b, int nq, int np);
+int fhe_neg(fhe_ctx* ctx, void* stream, uint64_t* out, const uint64_t* a, int npoly, int nq, int np);
+
+/* Engine.multiply(ct, ct) tensor step (xor_service.py:71, sbox/sbox_service.py:114):
+ * out[3][nq][N] = (a0 b0, a0 b1 + a1 b0, a1 b1). */
+int fhe_tensor(fhe_ctx* ctx, void* stream, uint64_t* out, const uint64_t* a, const uint64_t* b, int nq);
+
+/* Engine.multiply(ct, float|const Plaintext) / add_plain (xor_service.py:78-83,98,282-285;
+ * sbox/sbox_service.py:124-136): multiply (or add) by the encoding of a complex constant,
+ * given per limb slot as host arrays c_first[j], c_second[j] (value on the first / second
+ * half of the bit-reversed spectrum). */
+int fhe_mul_const(fhe_ctx* ctx, void* stream, uint64_t* out, const uint64_t* a,
+                  const uint64_t* c_first, const uint64_t* c_second, int npoly, int nq, int np);
+int fhe_add_const(fhe_ctx* ctx, void* stream, uint64_t* out, const uint64_t* a,
+                  const uint64_t* c_first, const uint64_t* c_second, int npoly, int nq, int np);
+
+/* Rescale after every multiply: [npoly][nq][N] -> [npoly][nq-1][N], division by q_{nq-1}
+ * rounded to nearest. */
+int fhe_rescale(fhe_ctx* ctx, void* stream, uint64_t* out, const uint64_t* in, int npoly, int nq);
+
+/* Engine.rotate / conjugate permutation part (xor_service.py:89,105): X -> X^galois on
+ * `nrows` NTT-domain rows. */
+int fhe_automorphism(fhe_ctx* ctx, void* stream, uint64_t* out, const uint64_t* in,
+                     uint64_t galois, int nrows);
+
+/* Hybrid key switching (Engine.relinearize, the relin inside multiply(ct,ct,rlk),
+ * rotate, conjugate).  ksk: [dnum][2][n_q + n_p][N] over the full chain.
+ *   fhe_keyswitch : d[nq][N] -> out[2][nq][N]          (= moddown(inner(modup(d))))
+ * The three phases are exported for hoisted rotations and for phase-level parity tests:
+ *   fhe_modup    : d[nq][N] -> ext[beta][nq+n_p][N]   (rows of a digit's own limbs are left
+ *                                                      untouched; inner reads them from d)
+ *   fhe_ks_inner : (ext, d, ksk) -> acc[2][nq+n_p][N]
+ *   fhe_moddown  : acc[npoly][nq+n_p][N] -> out[npoly][nq][N]   (acc's special limbs are
+ *                                                      overwritten with scratch data) */
+int fhe_keyswitch(fhe_ctx* ctx, void* stream, uint64_t* out, const uint64_t* d,
+                  const uint64_t* ksk, int nq);
+int fhe_modup(fhe_ctx* ctx, void* stream, uint64_t* ext, const uint64_t* d, int nq);
+int fhe_ks_inner(fhe_ctx* ctx, void* stream, uint64_t* acc, const uint64_t* ext,
+                 const uint64_t* d, const uint64_t* ksk, int nq);
+int fhe_moddown(fhe_ctx* ctx, void* stream, uint64_t* out, uint64_t* acc, int nq, int npoly);
+
+/* Engine.encode / encrypt residue step (xor_service.py:59-66): signed 64-bit coefficients
+ * (device) -> coefficient-domain residues of a [nq + np][N] block. */
+int fhe_from_i64(fhe_ctx* ctx, void* stream, uint64_t* out, const int64_t* coeffs, int nq, int np);
+
+/* Engine.decrypt tail (xor_service.py:62-63): centred CRT of coefficient-domain limbs
+ * 0..limbs-1 (limbs = 1 or 2) of x to doubles. */
+int fhe_crt_centered(fhe_ctx* ctx, void* stream, double* out, const uint64_t* x, int limbs);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,110 @@
+"""Shared bit-exact parity checks: a CUDA-source backend (the real GPU build, or the host
+simulation of the same kernels) against the CPU oracle, through the C ABI."""
+import numpy as np
+
+from conftest import rand_poly
+
+
+def check_primitives(P, gb, rb, seed=1):
+    rng = np.random.default_rng(seed)
+    nq, K = P.n_q, P.n_p
+    up = gb.from_numpy
+    a = rand_poly(P, rng, 2, nq, True)
+    assert np.array_equal(gb.to_numpy(gb.ntt(up(a), nq, K)), rb.ntt(a, nq, K)), "ntt"
+    assert np.array_equal(gb.to_numpy(gb.intt(up(a), nq, K)), rb.intt(a, nq, K)), "intt"
+    assert np.array_equal(gb.to_numpy(gb.intt(gb.ntt(up(a), nq, K), nq, K)), a), "ntt round trip"
+    b = rand_poly(P, rng, 2, nq, False)
+    c = rand_poly(P, rng, 2, nq, False)
+    c1 = rand_poly(P, rng, 1, nq, False)
+    for name in ("add", "sub", "mul"):
+        assert np.array_equal(gb.to_numpy(getattr(gb, name)(up(b), up(c), nq, 0)), getattr(rb, name)(b, c, nq, 0)), name
+    assert np.array_equal(gb.to_numpy(gb.mul(up(b), up(c1), nq, 0)), rb.mul(b, c1, nq, 0)), "mul broadcast"
+    assert np.array_equal(gb.to_numpy(gb.neg(up(b), nq, 0)), rb.neg(b, nq, 0)), "neg"
+    assert np.array_equal(gb.to_numpy(gb.tensor(up(b), up(c), nq)), rb.tensor(b, c, nq)), "tensor"
+    for g in (5, 2 * P.n - 1, pow(5, 7, 2 * P.n), pow(5, P.slot_count - 3, 2 * P.n)):
+        assert np.array_equal(gb.to_numpy(gb.automorphism(up(b), g, nq, 0)), rb.automorphism(b, g, nq, 0)), f"auto {g}"
+    co = rng.integers(-2 ** 55, 2 ** 55, size=P.n, dtype=np.int64)
+    co[:4] = [0, -1, 1, -(2 ** 62)]
+    assert np.array_equal(gb.to_numpy(gb.from_i64(co, nq, True)), rb.from_i64(co, nq, True)), "from_i64"
+    cp = [int(rng.integers(0, P.moduli[l])) for l in range(nq)]
+    cm = [int(rng.integers(0, P.moduli[l])) for l in range(nq)]
+    assert np.array_equal(gb.to_numpy(gb.mul_const(up(b), cp, cm, nq)), rb.mul_const(b, cp, cm, nq)), "mul_const"
+    assert np.array_equal(gb.to_numpy(gb.add_const(up(b), cp, cm, nq)), rb.add_const(b, cp, cm, nq)), "add_const"
+    assert np.array_equal(gb.to_numpy(gb.add_poly0(up(b), up(c1), nq)), rb.add_poly0(b, c1, nq)), "add_poly0"
+    x = rand_poly(P, rng, 1, 2, False)
+    assert np.array_equal(gb.crt_centered(up(x), 2), rb.crt_centered(x, 2)), "crt2"
+    assert np.array_equal(gb.crt_centered(up(x), 1), rb.crt_centered(x, 1)), "crt1"
+
+
+def check_rescale(P, gb, rb, seed=2):
+    rng = np.random.default_rng(seed)
+    for nq in sorted({P.n_q, max(2, P.n_q - 3), 2}):
+        for npoly in (2, 3):
+            b = rand_poly(P, rng, npoly, nq, False)
+            # edge values around the centring threshold of the dropped limb
+            ql = P.moduli[nq - 1]
+            b[0, nq - 1, :4] = [0, ql >> 1, (ql >> 1) + 1, ql - 1]
+            assert np.array_equal(gb.to_numpy(gb.rescale(gb.from_numpy(b), nq)), rb.rescale(b, nq)), f"rescale nq={nq}"
+
+
+def check_keyswitch(P, gb, rb, levels=None, seed=3):
+    rng = np.random.default_rng(seed)
+    ksk = np.stack([rand_poly(P, rng, 2, P.n_q, True) for _ in range(P.dnum)])
+    gk = gb.from_numpy(ksk)
+    if levels is None:
+        levels = sorted({P.n_q, P.n_q - 1, P.alpha, P.alpha + 1, 1, 2})
+    for nq in levels:
+        if nq < 1 or nq > P.n_q:
+            continue
+        d = rand_poly(P, rng, 1, nq, False)
+        ge, re_ = gb.modup(gb.from_numpy(d), nq), rb.modup(d, nq)
+        assert np.array_equal(gb.to_numpy(ge), re_), f"modup nq={nq}"
+        ga, ra = gb.ks_inner(ge, gb.from_numpy(d), gk, nq), rb.ks_inner(re_, ksk, nq)
+        assert np.array_equal(gb.to_numpy(ga), ra), f"ks_inner nq={nq}"
+        gm, rm = gb.moddown(ga, nq), rb.moddown(ra, nq)
+        assert np.array_equal(gb.to_numpy(gm), rm), f"moddown nq={nq}"
+        assert np.array_equal(gb.to_numpy(gb.keyswitch(gb.from_numpy(d), gk, nq)), rm), f"keyswitch nq={nq}"
+
+
+def check_engine_ops(eg, er, slot_tol=1e-5):
+    """Same seed => same keys and ciphertexts; every engine op must give identical residues."""
+    def same(cg, cr, what):
+        assert cg.level == cr.level, what
+        assert np.array_equal(eg.backend.to_numpy(cg.polys), er.backend.to_numpy(cr.polys)), what
+
+    keys = []
+    for e in (eg, er):
+        sk = e.create_secret_key()
+        keys.append(dict(sk=sk, pk=e.create_public_key(sk), rlk=e.create_relinearization_key(sk),
+                         cj=e.create_conjugation_key(sk), rot=e.create_rotation_key(sk, steps=[1, -1, -2, 4])))
+    kg, kr = keys
+    assert np.array_equal(eg.backend.to_numpy(kg['rlk'].data), er.backend.to_numpy(kr['rlk'].data)), "rlk"
+    sc = eg.slot_count
+    rng = np.random.default_rng(11)
+    v = np.exp(-2j * np.pi * rng.integers(0, 16, sc) / 16)
+    w = rng.random(sc) - 0.5
+    cg, cr = eg.encrypt(v, kg['pk']), er.encrypt(v, kr['pk'])
+    same(cg, cr, "encrypt")
+    dg, dr = eg.encrypt(w, kg['pk']), er.encrypt(w, kr['pk'])
+    assert np.allclose(eg.decrypt(cg, kg['sk']), v, atol=1e-6)
+    assert np.array_equal(eg.decrypt(cg, kg['sk']), er.decrypt(cr, kr['sk'])), "decrypt"
+    m_g, m_r = eg.multiply(cg, dg, kg['rlk']), er.multiply(cr, dr, kr['rlk'])
+    same(m_g, m_r, "multiply relin")
+    assert np.allclose(eg.decrypt(m_g, kg['sk']), v * w, atol=slot_tol)
+    same(eg.multiply(cg, dg), er.multiply(cr, dr), "multiply no relin (3 polys)")
+    same(eg.relinearize(eg.multiply(cg, dg), kg['rlk']), er.relinearize(er.multiply(cr, dr), kr['rlk']), "relinearize")
+    same(eg.multiply(cg, 0.25 - 0.5j), er.multiply(cr, 0.25 - 0.5j), "multiply const")
+    pt_g, pt_r = eg.encode(w), er.encode(w)
+    same(eg.multiply(cg, pt_g), er.multiply(cr, pt_r), "multiply plaintext")
+    same(eg.add(cg, pt_g), er.add(cr, pt_r), "add plaintext")
+    same(eg.add(m_g, cg), er.add(m_r, cr), "add mixed level")
+    same(eg.add_plain(cg, 1.0), er.add_plain(cr, 1.0), "add_plain")
+    same(eg.conjugate(cg, kg['cj']), er.conjugate(cr, kr['cj']), "conjugate")
+    for delta in (1, -2, 3, 5, -1):
+        rg, rr = eg.rotate(cg, kg['rot'], delta), er.rotate(cr, kr['rot'], delta)
+        same(rg, rr, f"rotate {delta}")
+        assert np.allclose(eg.decrypt(rg, kg['sk']), np.roll(v, delta), atol=slot_tol), f"rotate {delta} = np.roll"
+    pg, pr = eg.make_power_basis(cg, 5, kg['rlk']), er.make_power_basis(cr, 5, kr['rlk'])
+    for k, (x, y) in enumerate(zip(pg, pr), 1):
+        same(x, y, f"power {k}")
+        assert np.allclose(eg.decrypt(x, kg['sk']), v ** k, atol=slot_tol)

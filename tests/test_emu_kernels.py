@@ -1,0 +1,41 @@
+"""The CUDA kernel sources, compiled for the host simulator (csrc/compat.h, -DFHE_EMU), must
+match the CPU oracle bit for bit through the C ABI.  Runs without a GPU; the same checks run
+on the real sm_100a build in test_gpu_parity.py."""
+import pytest
+
+import kernel_parity as kp
+from aes_fhe_b200.backend_cuda import CudaBackend
+from aes_fhe_b200.params import make_params
+from conftest import make_engines
+
+
+def _emu(P, emu_lib):
+    return CudaBackend(P, _lib_path=emu_lib, _device="cpu")
+
+
+@pytest.mark.parametrize("log_n,lvl", [(12, 5), (13, 4), (14, 2)])
+def test_primitives(log_n, lvl, emu_lib, ref_backend_cls):
+    P = make_params(log_n, lvl)
+    kp.check_primitives(P, _emu(P, emu_lib), ref_backend_cls(P))
+
+
+def test_primitives_full_ring(emu_lib, ref_backend_cls):
+    P = make_params(16, 2)
+    kp.check_primitives(P, _emu(P, emu_lib), ref_backend_cls(P))
+
+
+def test_rescale(emu_lib, ref_backend_cls):
+    P = make_params(12, 6)
+    kp.check_rescale(P, _emu(P, emu_lib), ref_backend_cls(P))
+
+
+@pytest.mark.parametrize("log_n,lvl,dnum", [(12, 6, 4), (12, 7, 3), (13, 4, 2)])
+def test_keyswitch_phases(log_n, lvl, dnum, emu_lib, ref_backend_cls):
+    P = make_params(log_n, lvl, dnum=dnum)
+    kp.check_keyswitch(P, _emu(P, emu_lib), ref_backend_cls(P))
+
+
+def test_engine_ops(emu_lib, ref_backend_cls):
+    P = make_params(12, 6)
+    eg, er = make_engines(P, ref_backend_cls, _emu(P, emu_lib))
+    kp.check_engine_ops(eg, er)

@@ -1,0 +1,80 @@
+"""Parity tests proper: the sm_100a build on a real B200, through the C ABI, against the CPU
+oracle on the same seeded inputs -- bit-exact residues, then slot / byte level checks."""
+import numpy as np
+import pytest
+import torch
+
+import kernel_parity as kp
+from aes_fhe_b200.params import make_params
+from conftest import make_engines
+
+pytestmark = pytest.mark.gpu
+
+
+def _gpu(P):
+    from aes_fhe_b200.backend_cuda import CudaBackend
+    assert torch.cuda.is_available(), "these tests need the B200"
+    return CudaBackend(P)
+
+
+@pytest.mark.parametrize("log_n,lvl", [(12, 5), (13, 4), (14, 3), (15, 3), (16, 4)])
+def test_primitives_small_chain(log_n, lvl, ref_backend_cls, cuda_lib):
+    P = make_params(log_n, lvl)
+    kp.check_primitives(P, _gpu(P), ref_backend_cls(P))
+
+
+def test_primitives_full_parameters(ref_backend_cls, cuda_lib):
+    P = make_params(16, 30)          # N = 2^16, 31 + 6 limbs: the BASELINE configuration
+    kp.check_primitives(P, _gpu(P), ref_backend_cls(P))
+
+
+def test_rescale(ref_backend_cls, cuda_lib):
+    for P in (make_params(12, 6), make_params(16, 30)):
+        kp.check_rescale(P, _gpu(P), ref_backend_cls(P))
+
+
+@pytest.mark.parametrize("log_n,lvl,dnum", [(12, 6, 4), (12, 7, 3), (13, 4, 2), (14, 9, 1)])
+def test_keyswitch_phases_small(log_n, lvl, dnum, ref_backend_cls, cuda_lib):
+    P = make_params(log_n, lvl, dnum=dnum)
+    kp.check_keyswitch(P, _gpu(P), ref_backend_cls(P))
+
+
+def test_keyswitch_full_parameters(ref_backend_cls, cuda_lib):
+    P = make_params(16, 30)
+    kp.check_keyswitch(P, _gpu(P), ref_backend_cls(P), levels=[31, 30, 25, 17, 16, 9, 8, 2, 1])
+
+
+@pytest.mark.parametrize("log_n,lvl", [(12, 6), (14, 6)])
+def test_engine_ops(log_n, lvl, ref_backend_cls, cuda_lib):
+    P = make_params(log_n, lvl)
+    eg, er = make_engines(P, ref_backend_cls, _gpu(P))
+    kp.check_engine_ops(eg, er)
+
+
+def test_engine_ops_full_ring(ref_backend_cls, cuda_lib):
+    P = make_params(16, 8)
+    eg, er = make_engines(P, ref_backend_cls, _gpu(P))
+    kp.check_engine_ops(eg, er)
+
+
+def test_linearity_property_full_size(cuda_lib):
+    """Size-independent property at the BASELINE size: NTT(a) + NTT(b) == NTT(a + b) and the
+    transform inverts, on 2 x 37 limbs of N = 2^16."""
+    P = make_params(16, 30)
+    gb = _gpu(P)
+    rng = np.random.default_rng(5)
+    from conftest import rand_poly
+    a = gb.from_numpy(rand_poly(P, rng, 2, P.n_q, True))
+    b = gb.from_numpy(rand_poly(P, rng, 2, P.n_q, True))
+    nq, K = P.n_q, P.n_p
+    lhs = gb.add(gb.ntt(a, nq, K), gb.ntt(b, nq, K), nq, K)
+    rhs = gb.ntt(gb.add(a, b, nq, K), nq, K)
+    assert torch.equal(lhs, rhs)
+    assert torch.equal(gb.intt(gb.ntt(a, nq, K), nq, K), a)
+    # negacyclic convolution theorem against the oracle-free schoolbook on a sparse operand
+    x = np.zeros(P.n, dtype=np.int64); x[1] = 1                      # X
+    y = rng.integers(-5, 6, P.n).astype(np.int64)
+    px, py = gb.from_i64(x, nq, False), gb.from_i64(y, nq, False)
+    prod = gb.intt(gb.mul(px, py, nq, 0), nq, 0)
+    shifted = np.roll(y, 1); shifted[0] = -shifted[0]                # X * y  (mod X^N + 1)
+    assert torch.equal(prod, gb.intt(gb.from_i64(shifted, nq, False), nq, 0))

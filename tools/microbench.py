@@ -1,0 +1,104 @@
+"""Per-kernel timings on the B200 (CUDA events on the launching stream, L2 flushed between
+timed iterations).  Prints one JSON line per measurement; `achieved_gbs` uses the
+ALGORITHMIC bytes of SURVEY.md section 8(d)."""
+import json
+import sys
+import time
+from pathlib import Path
+
+import numpy as np
+import torch
+
+sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
+from aes_fhe_b200.backend_cuda import CudaBackend
+from aes_fhe_b200.params import make_params
+
+
+def timeit(fn, iters=10, warmup=3, flush=None):
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(iters):
+        if flush is not None:
+            flush.zero_()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record(); fn(); e.record()
+        torch.cuda.synchronize()
+        ts.append(s.elapsed_time(e) * 1e3)       # us
+    ts.sort()
+    return ts[len(ts) // 2], ts[0]
+
+
+def main():
+    peak = 6455.9
+    try:
+        peak = json.load(open(Path(__file__).resolve().parent.parent / "MEASURED_PEAKS.json"))["hbm_gbs"]
+    except Exception:
+        pass
+    P = make_params(16, 30)
+    gb = CudaBackend(P)
+    n, K = P.n, P.n_p
+    limb = n * 8
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")   # > 126 MB L2
+    rng = np.random.default_rng(0)
+
+    def rnd(*shape):
+        return torch.randint(0, 2 ** 39, shape, dtype=torch.int64, device="cuda")
+
+    out = []
+
+    def rec(name, us_med, us_min, alg_bytes, **kw):
+        r = dict(kernel=name, us=round(us_med, 2), us_min=round(us_min, 2), algorithmic_MB=round(alg_bytes / 1e6, 2),
+                 achieved_gbs=round(alg_bytes / us_med / 1e3, 1), frac_of_measured_peak=round(alg_bytes / us_med / 1e3 / peak, 3), **kw)
+        out.append(r)
+        print(json.dumps(r), flush=True)
+
+    # copy roofline reference (torch's own copy kernel) on the same buffers
+    a = rnd(8, 37, n); b = torch.empty_like(a)
+    m, mn = timeit(lambda: b.copy_(a), flush=flush)
+    rec("torch_copy_ref", m, mn, 2 * a.numel() * 8)
+
+    for rows in (37, 2 * 37, 8 * 37):
+        x = rnd(rows // 37, 37, n)
+        m, mn = timeit(lambda: gb._call("fhe_ntt_fwd", gb._ptr(x), x.shape[0], 31, K), flush=flush)
+        rec("ntt_fwd", m, mn, 2 * rows * limb, rows=rows)
+        m, mn = timeit(lambda: gb._call("fhe_ntt_inv", gb._ptr(x), x.shape[0], 31, K), flush=flush)
+        rec("ntt_inv", m, mn, 2 * rows * limb, rows=rows)
+
+    for nq in (31, 21, 11):
+        x = rnd(2, nq, n); y = rnd(2, nq, n); o = torch.empty_like(x)
+        m, mn = timeit(lambda: gb._call("fhe_add", gb._ptr(o), gb._ptr(x), gb._ptr(y), 2, 2, nq, 0), flush=flush)
+        rec("add_ct", m, mn, 6 * nq * limb, nq=nq)
+        m, mn = timeit(lambda: gb._call("fhe_mul", gb._ptr(o), gb._ptr(x), gb._ptr(y), 2, 2, nq, 0), flush=flush)
+        rec("mul_pointwise", m, mn, 6 * nq * limb, nq=nq)
+        o3 = torch.empty(3, nq, n, dtype=torch.int64, device="cuda")
+        m, mn = timeit(lambda: gb._call("fhe_tensor", gb._ptr(o3), gb._ptr(x), gb._ptr(y), nq), flush=flush)
+        rec("tensor", m, mn, 7 * nq * limb, nq=nq)
+        r = torch.empty(2, nq - 1, n, dtype=torch.int64, device="cuda")
+        m, mn = timeit(lambda: gb._call("fhe_rescale", gb._ptr(r), gb._ptr(x), 2, nq), flush=flush)
+        rec("rescale", m, mn, (2 * nq + 2 * (nq - 1)) * limb, nq=nq)
+        import ctypes as C
+        m, mn = timeit(lambda: gb._call("fhe_automorphism", gb._ptr(o), gb._ptr(x), C.c_uint64(5), 2 * nq), flush=flush)
+        rec("automorphism", m, mn, 4 * nq * limb, nq=nq)
+        # key switch
+        ksk = rnd(P.dnum, 2, 37, n)
+        d = rnd(1, nq, n); ko = torch.empty(2, nq, n, dtype=torch.int64, device="cuda")
+        beta = P.digits_at(nq)
+        alg = (2 * beta * (nq + K) + 3 * nq) * limb
+        m, mn = timeit(lambda: gb._call("fhe_keyswitch", gb._ptr(ko), gb._ptr(d), gb._ptr(ksk), nq), flush=flush)
+        rec("keyswitch", m, mn, alg, nq=nq, beta=beta)
+        ext = torch.empty(beta, nq + K, n, dtype=torch.int64, device="cuda")
+        acc = torch.empty(2, nq + K, n, dtype=torch.int64, device="cuda")
+        m, mn = timeit(lambda: gb._call("fhe_modup", gb._ptr(ext), gb._ptr(d), nq), flush=flush)
+        rec("ks.modup", m, mn, (nq + beta * (nq + K)) * limb, nq=nq)
+        m, mn = timeit(lambda: gb._call("fhe_ks_inner", gb._ptr(acc), gb._ptr(ext), gb._ptr(d), gb._ptr(ksk), nq), flush=flush)
+        rec("ks.inner", m, mn, (3 * beta * (nq + K) + 2 * (nq + K)) * limb, nq=nq)
+        m, mn = timeit(lambda: gb._call("fhe_moddown", gb._ptr(ko), gb._ptr(acc), nq, 2), flush=flush)
+        rec("ks.moddown", m, mn, (2 * (nq + K) + 2 * nq) * limb, nq=nq)
+    Path("gpurun_out").mkdir(exist_ok=True)
+    json.dump(out, open("gpurun_out/microbench.json", "w"), indent=1)
+
+
+if __name__ == "__main__":
+    main()
