@@ -24,21 +24,21 @@ SIGNATURES = {
     "fhe_launch_count": [],
     "fhe_ntt_fwd": [_P, _P, _P, _I, _I, _I],
     "fhe_ntt_inv": [_P, _P, _P, _I, _I, _I],
-    "fhe_add": [_P, _P, _P, _P, _P, _I, _I, _I, _I],
-    "fhe_sub": [_P, _P, _P, _P, _P, _I, _I, _I, _I],
-    "fhe_mul": [_P, _P, _P, _P, _P, _I, _I, _I, _I],
+    "fhe_add": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I],
+    "fhe_sub": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I],
+    "fhe_mul": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I],
     "fhe_neg": [_P, _P, _P, _P, _I, _I, _I],
-    "fhe_tensor": [_P, _P, _P, _P, _P, _I],
+    "fhe_tensor": [_P, _P, _P, _P, _P, _I, _I],
     "fhe_mul_const": [_P, _P, _P, _P, _P, _P, _I, _I, _I],
     "fhe_add_const": [_P, _P, _P, _P, _P, _P, _I, _I, _I],
     "fhe_rescale": [_P, _P, _P, _P, _I, _I],
     "fhe_automorphism": [_P, _P, _P, _P, _U64, _I],
-    "fhe_keyswitch": [_P, _P, _P, _P, _P, _I],
-    "fhe_modup": [_P, _P, _P, _P, _I],
-    "fhe_ks_inner": [_P, _P, _P, _P, _P, _P, _I],
+    "fhe_keyswitch": [_P, _P, _P, _P, _P, _I, _I],
+    "fhe_modup": [_P, _P, _P, _P, _I, _I],
+    "fhe_ks_inner": [_P, _P, _P, _P, _P, _P, _I, _I],
     "fhe_moddown": [_P, _P, _P, _P, _I, _I],
-    "fhe_from_i64": [_P, _P, _P, _P, _I, _I],
-    "fhe_crt_centered": [_P, _P, _P, _P, _I],
+    "fhe_from_i64": [_P, _P, _P, _P, _I, _I, _I],
+    "fhe_crt_centered": [_P, _P, _P, _P, _I, _I],
 }
 _RESTYPES = {"fhe_ctx_destroy": None, "fhe_last_error": C.c_char_p, "fhe_launch_count": _U64}
 

@@ -2,7 +2,9 @@
 operation is one call through the C ABI (include/aesfhe_b200.h) into hand-written sm_100a
 kernels.  No CPU path: without the built library or without a GPU the constructor raises.
 
-Handles are ``torch.int64`` tensors ``[npoly, limbs, N]`` (bit pattern = unsigned residue).
+Handles are ``torch.int64`` tensors ``[npoly, batch, limbs, N]`` (bit pattern = unsigned
+residue): ``batch`` independent ciphertexts travel through every operation together, which
+is what fills the 148 SMs and lets one pass over a key-switching key serve the whole batch.
 """
 from __future__ import annotations
 
@@ -72,6 +74,9 @@ class CudaBackend:
     def npoly(self, h) -> int:
         return h.shape[0]
 
+    def batch(self, h) -> int:
+        return h.shape[1]
+
     def from_numpy(self, a: np.ndarray):
         a = np.ascontiguousarray(a, dtype=np.uint64)
         return torch.from_numpy(a.view(np.int64)).to(self.device)
@@ -79,13 +84,14 @@ class CudaBackend:
     def to_numpy(self, h) -> np.ndarray:
         return h.detach().cpu().contiguous().numpy().view(np.uint64).copy()
 
-    def zeros(self, npoly: int, nq: int, with_p: bool):
-        return torch.zeros((npoly, nq + (self._K if with_p else 0), self.n), dtype=torch.int64, device=self.device)
+    def zeros(self, npoly: int, batch: int, nq: int, with_p: bool):
+        return torch.zeros((npoly, batch, nq + (self._K if with_p else 0), self.n), dtype=torch.int64,
+                           device=self.device)
 
     def take_limbs(self, h, nq: int, with_p: bool):
         if with_p:
-            return torch.cat([h[:, :nq], h[:, h.shape[1] - self._K:]], dim=1).contiguous()
-        return h[:, :nq].contiguous()
+            return torch.cat([h[:, :, :nq], h[:, :, h.shape[2] - self._K:]], dim=2).contiguous()
+        return h[:, :, :nq].contiguous()
 
     def select_poly(self, h, i: int):
         return h[i:i + 1]
@@ -99,36 +105,46 @@ class CudaBackend:
     def stack(self, hs: List):
         return torch.stack(hs, dim=0)
 
+    def expand_batch(self, h, batch: int):
+        return h if h.shape[1] == batch else h.expand(-1, batch, -1, -1).contiguous()
+
     # ---- transforms
     def ntt(self, h, nq: int, np_: int):
         out = h.clone()
-        self._call("fhe_ntt_fwd", self._ptr(out), out.shape[0], nq, np_)
+        self._call("fhe_ntt_fwd", self._ptr(out), out.shape[0] * out.shape[1], nq, np_)
         return out
 
     def intt(self, h, nq: int, np_: int):
         out = h.clone()
-        self._call("fhe_ntt_inv", self._ptr(out), out.shape[0], nq, np_)
+        self._call("fhe_ntt_inv", self._ptr(out), out.shape[0] * out.shape[1], nq, np_)
         return out
 
     def from_i64(self, coeffs: np.ndarray, nq: int, with_p: bool):
+        """coeffs: int64 [N] or [batch, N] -> NTT-domain [1, batch, limbs, N]."""
         np_ = self._K if with_p else 0
-        c = torch.from_numpy(np.ascontiguousarray(coeffs, dtype=np.int64)).to(self.device)
-        out = self._empty(1, nq + np_, self.n)
-        self._call("fhe_from_i64", self._ptr(out), self._ptr(c), nq, np_)
-        self._call("fhe_ntt_fwd", self._ptr(out), 1, nq, np_)
+        c = np.ascontiguousarray(coeffs, dtype=np.int64).reshape(-1, self.n)
+        b = c.shape[0]
+        cd = torch.from_numpy(c).to(self.device)
+        out = self._empty(1, b, nq + np_, self.n)
+        self._call("fhe_from_i64", self._ptr(out), self._ptr(cd), nq, np_, b)
+        self._call("fhe_ntt_fwd", self._ptr(out), b, nq, np_)
         return out
 
-    # ---- elementwise
+    # ---- elementwise.  a: [p, B, L, N]; b: [p or 1, B or 1, L, N] -- broadcasts are strides
+    # inside the kernel, nothing is replicated.  If `a` is the smaller operand the roles swap
+    # (add / mul commute); sub materialises.
     def _bin(self, name, a, b, nq, np_):
-        if a.shape[0] < b.shape[0]:
-            if name == "fhe_sub":
-                a = a.expand(b.shape[0], -1, -1).contiguous()
-            else:
+        full = (max(a.shape[0], b.shape[0]), max(a.shape[1], b.shape[1]))
+        if tuple(a.shape[:2]) != full:
+            if name != "fhe_sub" and tuple(b.shape[:2]) == full:
                 a, b = b, a
+            else:
+                a = a.expand(full[0], full[1], -1, -1)
         a = a.contiguous()
         b = b.contiguous()
         out = torch.empty_like(a)
-        self._call(name, self._ptr(out), self._ptr(a), self._ptr(b), a.shape[0], b.shape[0], nq, np_)
+        self._call(name, self._ptr(out), self._ptr(a), self._ptr(b), a.shape[0], a.shape[1], b.shape[0], b.shape[1],
+                   nq, np_)
         return out
 
     def add(self, a, b, nq, np_):
@@ -143,7 +159,7 @@ class CudaBackend:
     def neg(self, a, nq, np_):
         a = a.contiguous()
         out = torch.empty_like(a)
-        self._call("fhe_neg", self._ptr(out), self._ptr(a), a.shape[0], nq, np_)
+        self._call("fhe_neg", self._ptr(out), self._ptr(a), a.shape[0] * a.shape[1], nq, np_)
         return out
 
     def _consts(self, cp: Sequence[int], cm: Sequence[int]):
@@ -155,81 +171,91 @@ class CudaBackend:
         a = a.contiguous()
         f, _ = self._consts(fac, fac)
         out = torch.empty_like(a)
-        self._call("fhe_mul_const", self._ptr(out), self._ptr(a), f.ctypes.data, f.ctypes.data, a.shape[0], nq, np_)
+        self._call("fhe_mul_const", self._ptr(out), self._ptr(a), f.ctypes.data, f.ctypes.data,
+                   a.shape[0] * a.shape[1], nq, np_)
         return out
 
     def mul_const(self, a, cp, cm, nq):
         a = a.contiguous()
         fp, fm = self._consts(cp, cm)
         out = torch.empty_like(a)
-        self._call("fhe_mul_const", self._ptr(out), self._ptr(a), fp.ctypes.data, fm.ctypes.data, a.shape[0], nq, 0)
+        self._call("fhe_mul_const", self._ptr(out), self._ptr(a), fp.ctypes.data, fm.ctypes.data,
+                   a.shape[0] * a.shape[1], nq, 0)
         return out
 
     def add_const(self, a, cp, cm, nq):
+        """constant added to polynomial 0 of every ciphertext of the batch"""
         out = a.clone()
         fp, fm = self._consts(cp, cm)
-        self._call("fhe_add_const", self._ptr(out), self._ptr(out), fp.ctypes.data, fm.ctypes.data, 1, nq, 0)
+        self._call("fhe_add_const", self._ptr(out), self._ptr(out), fp.ctypes.data, fm.ctypes.data, a.shape[1], nq, 0)
         return out
 
     def add_poly0(self, a, p, nq):
         out = a.clone()
-        p = p.contiguous()
-        self._call("fhe_add", self._ptr(out), self._ptr(out), self._ptr(p), 1, 1, nq, 0)
+        p = self.expand_batch(p, a.shape[1]).contiguous()
+        self._call("fhe_add", self._ptr(out), self._ptr(out), self._ptr(p), 1, a.shape[1], 1, a.shape[1], nq, 0)
         return out
 
     def tensor(self, a, b, nq):
-        a = a.contiguous()
-        b = b.contiguous()
-        out = self._empty(3, nq, self.n)
-        self._call("fhe_tensor", self._ptr(out), self._ptr(a), self._ptr(b), nq)
+        bt = max(a.shape[1], b.shape[1])
+        a = self.expand_batch(a, bt).contiguous()
+        b = self.expand_batch(b, bt).contiguous()
+        out = self._empty(3, bt, nq, self.n)
+        self._call("fhe_tensor", self._ptr(out), self._ptr(a), self._ptr(b), nq, bt)
         return out
 
     # ---- structural
     def rescale(self, h, nq):
         h = h.contiguous()
-        out = self._empty(h.shape[0], nq - 1, self.n)
-        self._call("fhe_rescale", self._ptr(out), self._ptr(h), h.shape[0], nq)
+        out = self._empty(h.shape[0], h.shape[1], nq - 1, self.n)
+        self._call("fhe_rescale", self._ptr(out), self._ptr(h), h.shape[0] * h.shape[1], nq)
         return out
 
     def automorphism(self, h, g: int, nq, np_):
         h = h.contiguous()
         out = torch.empty_like(h)
-        self._call("fhe_automorphism", self._ptr(out), self._ptr(h), C.c_uint64(int(g)), h.shape[0] * h.shape[1])
+        self._call("fhe_automorphism", self._ptr(out), self._ptr(h), C.c_uint64(int(g)),
+                   h.shape[0] * h.shape[1] * h.shape[2])
         return out
 
     def modup(self, d, nq):
+        """d [1, B, nq, N] -> ext [B, beta, nq+K, N] (own-digit rows mirrored from d so the
+        tensor is comparable with the oracle's ModUp output)."""
         d = d.contiguous()
+        bt = d.shape[1]
         beta = self.params.digits_at(nq)
-        ext = self._empty(beta, nq + self._K, self.n)
-        self._call("fhe_modup", self._ptr(ext), self._ptr(d), nq)
-        # a digit's own limbs are read from d by the inner product; mirror them here so the
-        # tensor is comparable with the oracle's ModUp output
+        ext = self._empty(bt, beta, nq + self._K, self.n)
+        self._call("fhe_modup", self._ptr(ext), self._ptr(d), nq, bt)
         a = self.params.alpha
         for j in range(beta):
             lo, hi = j * a, min((j + 1) * a, nq)
-            ext[j, lo:hi] = d.reshape(-1, self.n)[lo:hi]
+            ext[:, j, lo:hi] = d[0, :, lo:hi]
         return ext
 
     def ks_inner(self, ext, d, ksk, nq):
-        acc = self._empty(2, nq + self._K, self.n)
+        bt = d.shape[1]
+        acc = self._empty(2, bt, nq + self._K, self.n)
         self._call("fhe_ks_inner", self._ptr(acc), self._ptr(ext.contiguous()), self._ptr(d.contiguous()),
-                   self._ptr(ksk), nq)
+                   self._ptr(ksk), nq, bt)
         return acc
 
     def moddown(self, acc, nq):
         acc = acc.clone()
-        out = self._empty(acc.shape[0], nq, self.n)
-        self._call("fhe_moddown", self._ptr(out), self._ptr(acc), nq, acc.shape[0])
+        out = self._empty(acc.shape[0], acc.shape[1], nq, self.n)
+        self._call("fhe_moddown", self._ptr(out), self._ptr(acc), nq, acc.shape[0] * acc.shape[1])
         return out
 
     def keyswitch(self, d, ksk, nq):
         d = d.contiguous()
-        out = self._empty(2, nq, self.n)
-        self._call("fhe_keyswitch", self._ptr(out), self._ptr(d), self._ptr(ksk), nq)
+        bt = d.shape[1]
+        out = self._empty(2, bt, nq, self.n)
+        self._call("fhe_keyswitch", self._ptr(out), self._ptr(d), self._ptr(ksk), nq, bt)
         return out
 
     def crt_centered(self, h, use: int) -> np.ndarray:
+        """h [1, B, use, N] coefficient domain -> float64 [B, N]"""
         h = h.contiguous()
-        out = torch.empty(self.n, dtype=torch.float64, device=self.device)
-        self._call("fhe_crt_centered", self._ptr(out), self._ptr(h), use)
+        bt = h.shape[1]
+        out = torch.empty((bt, self.n), dtype=torch.float64, device=self.device)
+        self._call("fhe_crt_centered", self._ptr(out), self._ptr(h), use, bt)
         return out.cpu().numpy()

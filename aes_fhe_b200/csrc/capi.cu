@@ -63,7 +63,7 @@ struct fhe_ctx {
     std::vector<ShoupConst*> modup_scale;     // [nq][2] iNTT final constants incl. (Q_j/q_i)^-1
     std::vector<BConvTable*> moddown_table;   // one table
     std::vector<ShoupConst*> rescale_c;       // [nq-1] q_{nq-1}^-1 mod q_i
-    ShoupConst* moddown_scale = nullptr;      // [4*n_p][2]
+    ShoupConst* moddown_scale = nullptr;      // [n_p][2]
     ShoupConst* pinv = nullptr;               // [n_q]  P^-1 mod q_i
     u64 q0inv_mod_q1 = 0;
     std::vector<void*> owned;
@@ -109,6 +109,7 @@ inline void launch(void (*k)(KArgs...), dim3 g, dim3 b, cudaStream_t s, Args&&..
 RowMap make_map(const fhe_ctx* c, int rows_per_poly, int j0, int nq, int skip_alpha = 0) {
     RowMap m;
     m.rows_per_poly = rows_per_poly; m.j0 = j0; m.nq = nq; m.p_base = c->n_q; m.skip_alpha = skip_alpha;
+    m.digits = skip_alpha > 0 ? (nq + skip_alpha - 1) / skip_alpha : 1;
     m.log_n = c->log_n;
     return m;
 }
@@ -203,14 +204,13 @@ void build_level_tables(fhe_ctx* c) {
     }
     if (K > 0) {
         // iNTT final constants for the special limbs, replicated for up to 4 polys
-        std::vector<ShoupConst> ms(2 * (size_t)K * 4);
-        for (int rep = 0; rep < 4; ++rep)
-            for (int k = 0; k < K; ++k) {
-                const u64 pk = c->q[pids[k]];
-                const u64 inv = h_inv(prod_except(c, pids, k, pk), pk);
-                ms[2 * ((size_t)rep * K + k)] = h_shoup(h_mul(ninv[pids[k]], inv, pk), pk);
-                ms[2 * ((size_t)rep * K + k) + 1] = h_shoup(h_mul(w1ninv[pids[k]], inv, pk), pk);
-            }
+        std::vector<ShoupConst> ms(2 * (size_t)K);
+        for (int k = 0; k < K; ++k) {
+            const u64 pk = c->q[pids[k]];
+            const u64 inv = h_inv(prod_except(c, pids, k, pk), pk);
+            ms[2 * (size_t)k] = h_shoup(h_mul(ninv[pids[k]], inv, pk), pk);
+            ms[2 * (size_t)k + 1] = h_shoup(h_mul(w1ninv[pids[k]], inv, pk), pk);
+        }
         c->moddown_scale = to_device(ms);
         c->owned.push_back(c->moddown_scale);
         std::vector<ShoupConst> pv(n_q);
@@ -325,28 +325,30 @@ int fhe_ntt_inv(fhe_ctx* c, void* stream, uint64_t* data, int npoly, int nq, int
 }
 
 static int binary(int op, fhe_ctx* c, void* stream, uint64_t* out, const uint64_t* a, const uint64_t* b,
-                  int npoly, int npoly_b, int nq, int np) {
-    if (bad_shape(c, nq, np) || npoly < 1 || (npoly_b != npoly && npoly_b != 1)) return fail("fhe_add/sub/mul: bad shape");
+                  int npoly, int batch, int b_npoly, int b_batch, int nq, int np) {
+    if (bad_shape(c, nq, np) || npoly < 1 || batch < 1 || (b_npoly != npoly && b_npoly != 1) ||
+        (b_batch != batch && b_batch != 1))
+        return fail("fhe_add/sub/mul: bad shape");
     const int rpp = nq + np;
     RowMap m = make_map(c, rpp, 0, nq);
-    const long long ps = (long long)rpp * c->n;
-    const long long bs = npoly_b == 1 && npoly > 1 ? 0 : ps;
-    dim3 grid(c->n / 256, npoly * rpp), block(256);
+    const long long blk = (long long)rpp * c->n;
+    Strides so, sa, sb;
+    so.poly = sa.poly = blk * batch; so.batch = sa.batch = blk;
+    sb.batch = b_batch == 1 ? 0 : blk;
+    sb.poly = b_npoly == 1 ? 0 : blk * b_batch;
+    dim3 grid(c->n / 256, npoly * batch * rpp), block(256);
     cudaStream_t s = (cudaStream_t)stream;
-    if (op == 0) launch(k_binary<0>, grid, block, s, c->T, m, (u64*)out, (const u64*)a, (const u64*)b, ps, ps, bs);
-    else if (op == 1) launch(k_binary<1>, grid, block, s, c->T, m, (u64*)out, (const u64*)a, (const u64*)b, ps, ps, bs);
-    else launch(k_binary<2>, grid, block, s, c->T, m, (u64*)out, (const u64*)a, (const u64*)b, ps, ps, bs);
+    if (op == 0) launch(k_binary<0>, grid, block, s, c->T, m, batch, (u64*)out, (const u64*)a, (const u64*)b, so, sa, sb);
+    else if (op == 1) launch(k_binary<1>, grid, block, s, c->T, m, batch, (u64*)out, (const u64*)a, (const u64*)b, so, sa, sb);
+    else launch(k_binary<2>, grid, block, s, c->T, m, batch, (u64*)out, (const u64*)a, (const u64*)b, so, sa, sb);
     return check("fhe_binary");
 }
-int fhe_add(fhe_ctx* c, void* s, uint64_t* o, const uint64_t* a, const uint64_t* b, int npoly, int npoly_b, int nq, int np) {
-    return binary(0, c, s, o, a, b, npoly, npoly_b, nq, np);
-}
-int fhe_sub(fhe_ctx* c, void* s, uint64_t* o, const uint64_t* a, const uint64_t* b, int npoly, int npoly_b, int nq, int np) {
-    return binary(1, c, s, o, a, b, npoly, npoly_b, nq, np);
-}
-int fhe_mul(fhe_ctx* c, void* s, uint64_t* o, const uint64_t* a, const uint64_t* b, int npoly, int npoly_b, int nq, int np) {
-    return binary(2, c, s, o, a, b, npoly, npoly_b, nq, np);
-}
+int fhe_add(fhe_ctx* c, void* s, uint64_t* o, const uint64_t* a, const uint64_t* b, int npoly, int batch, int b_npoly,
+            int b_batch, int nq, int np) { return binary(0, c, s, o, a, b, npoly, batch, b_npoly, b_batch, nq, np); }
+int fhe_sub(fhe_ctx* c, void* s, uint64_t* o, const uint64_t* a, const uint64_t* b, int npoly, int batch, int b_npoly,
+            int b_batch, int nq, int np) { return binary(1, c, s, o, a, b, npoly, batch, b_npoly, b_batch, nq, np); }
+int fhe_mul(fhe_ctx* c, void* s, uint64_t* o, const uint64_t* a, const uint64_t* b, int npoly, int batch, int b_npoly,
+            int b_batch, int nq, int np) { return binary(2, c, s, o, a, b, npoly, batch, b_npoly, b_batch, nq, np); }
 
 int fhe_neg(fhe_ctx* c, void* stream, uint64_t* out, const uint64_t* a, int npoly, int nq, int np) {
     if (bad_shape(c, nq, np) || npoly < 1) return fail("fhe_neg: bad shape");
@@ -356,10 +358,10 @@ int fhe_neg(fhe_ctx* c, void* stream, uint64_t* out, const uint64_t* a, int npol
     return check("fhe_neg");
 }
 
-int fhe_tensor(fhe_ctx* c, void* stream, uint64_t* out, const uint64_t* a, const uint64_t* b, int nq) {
-    if (bad_shape(c, nq, 0)) return fail("fhe_tensor: bad shape");
-    launch(k_tensor, dim3(c->n / 256, nq), dim3(256), (cudaStream_t)stream, c->T, nq, (u64*)out, (const u64*)a,
-           (const u64*)b);
+int fhe_tensor(fhe_ctx* c, void* stream, uint64_t* out, const uint64_t* a, const uint64_t* b, int nq, int batch) {
+    if (bad_shape(c, nq, 0) || batch < 1) return fail("fhe_tensor: bad shape");
+    launch(k_tensor, dim3(c->n / 256, batch * nq), dim3(256), (cudaStream_t)stream, c->T, nq, (u64*)out, (const u64*)a,
+           (const u64*)b, (long long)batch * nq * c->n);
     return check("fhe_tensor");
 }
 
@@ -413,39 +415,41 @@ int fhe_automorphism(fhe_ctx* c, void* stream, uint64_t* out, const uint64_t* in
     return check("fhe_automorphism");
 }
 
-int fhe_modup(fhe_ctx* c, void* stream, uint64_t* ext, const uint64_t* d, int nq) {
-    if (bad_shape(c, nq, 0) || c->n_p == 0) return fail("fhe_modup: bad shape");
+int fhe_modup(fhe_ctx* c, void* stream, uint64_t* ext, const uint64_t* d, int nq, int batch) {
+    if (bad_shape(c, nq, 0) || c->n_p == 0 || batch < 1) return fail("fhe_modup: bad shape");
     cudaStream_t s = (cudaStream_t)stream;
     const int n = c->n, ne = nq + c->n_p, beta = c->modup_beta[nq];
-    u64* y = arena(c, (size_t)nq * n);
+    u64* y = arena(c, (size_t)batch * nq * n);
     if (!y) return fail("fhe_modup: scratch allocation failed");
     {   // iNTT with the (Q_j/q_i)^-1 factor folded into the final stage
         RowMap m = make_map(c, nq, 0, nq);
         LoadPlain ld; ld.src = (const u64*)d; ld.poly_stride = (long long)nq * n;
         StorePlain st; st.dst = y; st.poly_stride = (long long)nq * n;
-        ntt_inverse(c->T, m, nq, ld, y, (long long)nq * n, st, c->modup_scale[nq], s);
+        ntt_inverse(c->T, m, batch * nq, ld, y, (long long)nq * n, st, c->modup_scale[nq], s);
     }
-    launch_bconv(c, s, std::min(c->alpha, nq), beta, c->modup_tables[nq], beta, (u64*)ext, (long long)ne * n, y, 0);
+    launch_bconv(c, s, std::min(c->alpha, nq), batch * beta, c->modup_tables[nq], beta, (u64*)ext, (long long)ne * n, y,
+                 (long long)nq * n);
     {   // NTT of every converted row (a digit's own limbs are skipped)
         RowMap m = make_map(c, ne, 0, nq, c->alpha);
         LoadPlain ld; ld.src = (const u64*)ext; ld.poly_stride = (long long)ne * n;
         StorePlain st; st.dst = (u64*)ext; st.poly_stride = (long long)ne * n;
-        ntt_forward(c->T, m, beta * ne, ld, (u64*)ext, (long long)ne * n, st, s);
+        ntt_forward(c->T, m, batch * beta * ne, ld, (u64*)ext, (long long)ne * n, st, s);
     }
     g_launches.fetch_add(4);
     return check("fhe_modup");
 }
 
 int fhe_ks_inner(fhe_ctx* c, void* stream, uint64_t* acc, const uint64_t* ext, const uint64_t* d,
-                 const uint64_t* ksk, int nq) {
-    if (bad_shape(c, nq, 0) || c->n_p == 0) return fail("fhe_ks_inner: bad shape");
+                 const uint64_t* ksk, int nq, int batch) {
+    if (bad_shape(c, nq, 0) || c->n_p == 0 || batch < 1 || c->modup_beta[nq] > FHE_MAX_BETA)
+        return fail("fhe_ks_inner: bad shape");
     launch(k_ks_inner, dim3(c->n / 256, nq + c->n_p), dim3(256), (cudaStream_t)stream, c->T, nq, c->alpha,
-           c->modup_beta[nq], (u64*)acc, (const u64*)ext, (const u64*)d, (const u64*)ksk);
+           c->modup_beta[nq], batch, (u64*)acc, (const u64*)ext, (const u64*)d, (const u64*)ksk);
     return check("fhe_ks_inner");
 }
 
 int fhe_moddown(fhe_ctx* c, void* stream, uint64_t* out, uint64_t* acc, int nq, int npoly) {
-    if (bad_shape(c, nq, 0) || c->n_p == 0 || npoly < 1 || npoly > 4) return fail("fhe_moddown: bad shape");
+    if (bad_shape(c, nq, 0) || c->n_p == 0 || npoly < 1) return fail("fhe_moddown: bad shape");
     cudaStream_t s = (cudaStream_t)stream;
     const int n = c->n, K = c->n_p, ne = nq + K;
     u64* accp = (u64*)acc + (size_t)nq * n;
@@ -468,32 +472,32 @@ int fhe_moddown(fhe_ctx* c, void* stream, uint64_t* out, uint64_t* acc, int nq, 
     return check("fhe_moddown");
 }
 
-int fhe_keyswitch(fhe_ctx* c, void* stream, uint64_t* out, const uint64_t* d, const uint64_t* ksk, int nq) {
-    if (bad_shape(c, nq, 0) || c->n_p == 0) return fail("fhe_keyswitch: bad shape");
+int fhe_keyswitch(fhe_ctx* c, void* stream, uint64_t* out, const uint64_t* d, const uint64_t* ksk, int nq, int batch) {
+    if (bad_shape(c, nq, 0) || c->n_p == 0 || batch < 1) return fail("fhe_keyswitch: bad shape");
     const int n = c->n, ne = nq + c->n_p, beta = c->modup_beta[nq];
-    // arena layout: [y : nq][ext : beta*ne][acc : 2*ne]   (fhe_modup uses the first nq rows)
-    const size_t words = ((size_t)nq + (size_t)beta * ne + 2 * (size_t)ne) * n;
+    // arena layout: [y : B*nq][ext : B*beta*ne][acc : 2*B*ne]   (fhe_modup uses the first B*nq rows)
+    const size_t words = ((size_t)batch * nq + (size_t)batch * beta * ne + 2 * (size_t)batch * ne) * n;
     u64* base = arena(c, words);
     if (!base) return fail("fhe_keyswitch: scratch allocation failed");
-    u64* ext = base + (size_t)nq * n;
-    u64* acc = ext + (size_t)beta * ne * n;
+    u64* ext = base + (size_t)batch * nq * n;
+    u64* acc = ext + (size_t)batch * beta * ne * n;
     int rc;
-    if ((rc = fhe_modup(c, stream, (uint64_t*)ext, d, nq))) return rc;
-    if ((rc = fhe_ks_inner(c, stream, (uint64_t*)acc, (const uint64_t*)ext, d, ksk, nq))) return rc;
-    return fhe_moddown(c, stream, out, (uint64_t*)acc, nq, 2);
+    if ((rc = fhe_modup(c, stream, (uint64_t*)ext, d, nq, batch))) return rc;
+    if ((rc = fhe_ks_inner(c, stream, (uint64_t*)acc, (const uint64_t*)ext, d, ksk, nq, batch))) return rc;
+    return fhe_moddown(c, stream, out, (uint64_t*)acc, nq, 2 * batch);
 }
 
-int fhe_from_i64(fhe_ctx* c, void* stream, uint64_t* out, const int64_t* coeffs, int nq, int np) {
-    if (bad_shape(c, nq, np)) return fail("fhe_from_i64: bad shape");
+int fhe_from_i64(fhe_ctx* c, void* stream, uint64_t* out, const int64_t* coeffs, int nq, int np, int batch) {
+    if (bad_shape(c, nq, np) || batch < 1) return fail("fhe_from_i64: bad shape");
     const int rpp = nq + np;
-    launch(k_from_i64, dim3(c->n / 256, rpp), dim3(256), (cudaStream_t)stream, c->T, make_map(c, rpp, 0, nq),
+    launch(k_from_i64, dim3(c->n / 256, batch * rpp), dim3(256), (cudaStream_t)stream, c->T, make_map(c, rpp, 0, nq),
            (u64*)out, (const long long*)coeffs);
     return check("fhe_from_i64");
 }
 
-int fhe_crt_centered(fhe_ctx* c, void* stream, double* out, const uint64_t* x, int limbs) {
-    if (!c || limbs < 1 || limbs > 2 || limbs > c->n_q) return fail("fhe_crt_centered: bad shape");
-    launch(k_crt_centered, dim3(c->n / 256), dim3(256), (cudaStream_t)stream, c->T, out, (const u64*)x, limbs,
+int fhe_crt_centered(fhe_ctx* c, void* stream, double* out, const uint64_t* x, int limbs, int batch) {
+    if (!c || limbs < 1 || limbs > 2 || limbs > c->n_q || batch < 1) return fail("fhe_crt_centered: bad shape");
+    launch(k_crt_centered, dim3(c->n / 256, batch), dim3(256), (cudaStream_t)stream, c->T, out, (const u64*)x, limbs,
            c->q0inv_mod_q1);
     return check("fhe_crt_centered");
 }

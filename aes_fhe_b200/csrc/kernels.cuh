@@ -19,23 +19,26 @@ struct LimbConsts {          // per-limb-slot constants passed by value
 };
 
 // ---------------------------------------------------------------- elementwise
-// op: 0 add, 1 sub, 2 mul      b is broadcast over polys when b_poly_stride == 0
+// op: 0 add, 1 sub, 2 mul.  Rows are [poly][batch][limb]; each operand has its own poly and
+// batch strides (0 = broadcast), so plaintexts / keys are never replicated in memory.
+struct Strides { long long poly, batch; };
 template <int OP>
-__global__ void __launch_bounds__(256) k_binary(DevTables T, RowMap map, u64* out, const u64* a, const u64* b,
-                                                long long o_poly_stride, long long a_poly_stride, long long b_poly_stride) {
+__global__ void __launch_bounds__(256) k_binary(DevTables T, RowMap map, int batch, u64* out, const u64* a, const u64* b,
+                                                Strides so, Strides sa, Strides sb) {
     const int row = blockIdx.y;
     const int mid = map.mod_id(row);
     const Modulus M = T.mod[mid];
     const u32 idx = blockIdx.x * 256 + threadIdx.x;
-    const int poly = row / map.rows_per_poly, j = row % map.rows_per_poly;
+    const int blk = row / map.rows_per_poly, j = row % map.rows_per_poly;
+    const size_t poly = blk / batch, bt = blk % batch;
     const size_t lo = ((size_t)j << map.log_n) + idx;
-    const u64 x = a[(size_t)poly * a_poly_stride + lo];
-    const u64 y = b[(size_t)poly * b_poly_stride + lo];
+    const u64 x = a[poly * sa.poly + bt * sa.batch + lo];
+    const u64 y = b[poly * sb.poly + bt * sb.batch + lo];
     u64 r;
     if (OP == 0) r = add_mod(x, y, M.q);
     else if (OP == 1) r = sub_mod(x, y, M.q);
     else r = mul_mod(x, y, M);
-    out[(size_t)poly * o_poly_stride + lo] = r;
+    out[poly * so.poly + bt * so.batch + lo] = r;
 }
 
 __global__ void __launch_bounds__(256) k_neg(DevTables T, RowMap map, u64* out, const u64* a) {
@@ -45,13 +48,12 @@ __global__ void __launch_bounds__(256) k_neg(DevTables T, RowMap map, u64* out, 
     out[o] = neg_mod(a[o], M.q);
 }
 
-// d0 = a0 b0, d1 = a0 b1 + a1 b0, d2 = a1 b1      rows: nq limbs
-__global__ void __launch_bounds__(256) k_tensor(DevTables T, int nq, u64* d, const u64* a, const u64* b) {
-    const int j = blockIdx.y;
+// d0 = a0 b0, d1 = a0 b1 + a1 b0, d2 = a1 b1      rows: batch * nq limbs, poly stride ps
+__global__ void __launch_bounds__(256) k_tensor(DevTables T, int nq, u64* d, const u64* a, const u64* b, long long ps) {
+    const int j = blockIdx.y % nq;
     const Modulus M = T.mod[j];
     const size_t n = (size_t)1 << T.log_n;
-    const size_t o = (size_t)j * n + blockIdx.x * 256 + threadIdx.x;
-    const size_t ps = (size_t)nq * n;
+    const size_t o = (size_t)blockIdx.y * n + blockIdx.x * 256 + threadIdx.x;
     const u64 a0 = a[o], a1 = a[o + ps], b0 = b[o], b1 = b[o + ps];
     d[o] = mul_mod(a0, b0, M);
     u128t acc = mul_wide(a0, b1);
@@ -85,22 +87,24 @@ __global__ void __launch_bounds__(256) k_automorphism(int log_n, u64* out, const
     out[ro + p] = in[ro + src];
 }
 
-// signed coefficients -> residues of every row's modulus
+// signed coefficients [batch][N] -> residues of every row's modulus, rows [batch][limbs]
 __global__ void __launch_bounds__(256) k_from_i64(DevTables T, RowMap map, u64* out, const long long* coeffs) {
     const int row = blockIdx.y;
     const Modulus M = T.mod[map.mod_id(row)];
     const u32 idx = blockIdx.x * 256 + threadIdx.x;
-    const long long v = coeffs[idx];
+    const long long v = coeffs[((size_t)(row / map.rows_per_poly) << map.log_n) + idx];
     u64 r;
     if (v >= 0) r = reduce_u64((u64)v, M);
     else r = neg_mod(reduce_u64((u64)(-v), M), M.q);
     out[((size_t)row << map.log_n) + idx] = r;
 }
 
-// centred CRT of limbs (0,1) (or limb 0 alone) to double
+// centred CRT of limbs (0,1) (or limb 0 alone) to double; x: [batch][limbs][N], out [batch][N]
 __global__ void __launch_bounds__(256) k_crt_centered(DevTables T, double* out, const u64* x, int limbs, u64 q0inv_mod_q1) {
     const u32 idx = blockIdx.x * 256 + threadIdx.x;
     const Modulus M0 = T.mod[0];
+    x += ((size_t)blockIdx.y * limbs) << T.log_n;
+    out += (size_t)blockIdx.y << T.log_n;
     const u64 x0 = x[idx];
     if (limbs < 2) {
         out[idx] = x0 > (M0.q >> 1) ? -(double)(M0.q - x0) : (double)x0;
@@ -135,16 +139,18 @@ struct BConvTable {
     u64 qmod[FHE_MAX_DST];
 };
 
-// grid: (N/256, groups).  group g uses table g % n_tables.  NS_MAX bounds every table's ns.
+// grid: (N/256, groups).  group g uses table g % n_tables and the source block g / n_tables
+// (ModUp: groups = batch x digits, all digits of one ciphertext read the same source block;
+//  ModDown: one table, groups = polys).  NS_MAX bounds every table's ns.
 template <int NS_MAX>
 __global__ void __launch_bounds__(256) k_bconv(DevTables T, const BConvTable* tables, int n_tables,
                                                u64* dst, long long dst_group_stride,
-                                               const u64* src, long long src_group_stride) {
+                                               const u64* src, long long src_block_stride) {
     const int g = blockIdx.y;
     const BConvTable& tb = tables[g % n_tables];
     const u32 idx = blockIdx.x * 256 + threadIdx.x;
     const int log_n = T.log_n;
-    const u64* s = src + (size_t)g * src_group_stride + idx;
+    const u64* s = src + (size_t)(g / n_tables) * src_block_stride + idx;
     u64* d = dst + (size_t)g * dst_group_stride + idx;
     u64 y[NS_MAX];
     u64 neg = 0;
@@ -169,9 +175,12 @@ __global__ void __launch_bounds__(256) k_bconv(DevTables T, const BConvTable* ta
 }
 
 // ---------------------------------------------------------------- key inner product
-// acc[c][t] = sum_j e_j[t] * ksk[j][c][id(t)],  e_j[t] = d[t] if t in digit j else ext[j][t]
-// grid: (N/256, nq + n_p)      ksk: [dnum][2][n_q_total + n_p][N]
-__global__ void __launch_bounds__(256) k_ks_inner(DevTables T, int nq, int alpha, int beta,
+// acc[c][b][t] = sum_j e_bj[t] * ksk[j][c][id(t)],  e_bj[t] = d[b][t] if t in digit j else ext[b][j][t]
+// grid: (N/256, nq + n_p).  One thread owns (t, idx) for EVERY ciphertext of the batch, so each
+// key word is read from HBM once per batch.      ksk: [dnum][2][n_q_total + n_p][N]
+// ext: [batch][beta][ne][N], d: [batch][nq][N], acc: [2][batch][ne][N]
+#define FHE_MAX_BETA 8
+__global__ void __launch_bounds__(256) k_ks_inner(DevTables T, int nq, int alpha, int beta, int batch,
                                                   u64* acc, const u64* ext, const u64* d, const u64* ksk) {
     const int t = blockIdx.y;
     const int ne = nq + T.n_p;
@@ -180,17 +189,31 @@ __global__ void __launch_bounds__(256) k_ks_inner(DevTables T, int nq, int alpha
     const int log_n = T.log_n;
     const u32 idx = blockIdx.x * 256 + threadIdx.x;
     const size_t tot = (size_t)(T.n_q + T.n_p);
-    u128t a0; a0.lo = 0; a0.hi = 0;
-    u128t a1 = a0;
-    for (int j = 0; j < beta; ++j) {
-        const bool own = t < nq && t >= j * alpha && t < (j + 1) * alpha;
-        const u64 e = own ? d[((size_t)t << log_n) + idx] : ext[(((size_t)j * ne + t) << log_n) + idx];
-        const u64* k0 = ksk + ((((size_t)j * 2) * tot + id) << log_n) + idx;
-        acc_wide(a0, e, k0[0]);
-        acc_wide(a1, e, k0[tot << log_n]);
+    u64 k0[FHE_MAX_BETA], k1[FHE_MAX_BETA];
+#pragma unroll
+    for (int j = 0; j < FHE_MAX_BETA; ++j) {
+        if (j < beta) {
+            const u64* kp = ksk + ((((size_t)j * 2) * tot + id) << log_n) + idx;
+            k0[j] = kp[0];
+            k1[j] = kp[tot << log_n];
+        } else { k0[j] = 0; k1[j] = 0; }
     }
-    acc[((size_t)t << log_n) + idx] = barrett_reduce(a0, M);
-    acc[((size_t)(ne + t) << log_n) + idx] = barrett_reduce(a1, M);
+    const int own = t < nq ? t / alpha : -1;
+    for (int b = 0; b < batch; ++b) {
+        u128t a0; a0.lo = 0; a0.hi = 0;
+        u128t a1 = a0;
+#pragma unroll
+        for (int j = 0; j < FHE_MAX_BETA; ++j) {
+            if (j < beta) {
+                const u64 e = j == own ? d[(((size_t)b * nq + t) << log_n) + idx]
+                                       : ext[((((size_t)b * beta + j) * ne + t) << log_n) + idx];
+                acc_wide(a0, e, k0[j]);
+                acc_wide(a1, e, k1[j]);
+            }
+        }
+        acc[(((size_t)b * ne + t) << log_n) + idx] = barrett_reduce(a0, M);
+        acc[((((size_t)batch + b) * ne + t) << log_n) + idx] = barrett_reduce(a1, M);
+    }
 }
 
 // ---------------------------------------------------------------- fused NTT functors

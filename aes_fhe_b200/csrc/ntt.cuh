@@ -26,7 +26,7 @@ struct DevTables {
 
 // Which modulus a row belongs to, and where it lives.  Rows are grouped in "polys" of
 // rows_per_poly limbs; limb slot j = j0 + row % rows_per_poly maps to modulus j (< nq) or
-// p_base + (j - nq).  skip_alpha > 0 marks the ModUp layout [digit][nq + n_p]: the rows of a
+// p_base + (j - nq).  skip_alpha > 0 marks the ModUp layout [batch][digit][nq + n_p]: the rows of a
 // digit's own limbs are not transformed.
 struct RowMap {
     int rows_per_poly;
@@ -34,11 +34,12 @@ struct RowMap {
     int nq;
     int p_base;
     int skip_alpha;
+    int digits;                    // beta, when skip_alpha > 0 (rows are [batch][digit][nq + n_p])
     int log_n;
     FHE_D int mod_id(int row) const {
         int j = j0 + row % rows_per_poly;
         if (skip_alpha > 0) {
-            int lo = (row / rows_per_poly) * skip_alpha;
+            int lo = ((row / rows_per_poly) % digits) * skip_alpha;
             if (j >= lo && j < lo + skip_alpha && j < nq) return -1;
         }
         return j < nq ? j : p_base + (j - nq);
@@ -237,7 +238,8 @@ __global__ void __launch_bounds__(256) ntt_inv_pass_b(DevTables T, RowMap map, L
 }
 
 // pass A' : stages log_n-8 .. 1 (row strides 1..R/2); the final stage carries the scaling
-// constants scale[row] = {c * N^-1, c * psi^-bitrev(1) * N^-1} (c = 1 when scale == nullptr).
+// constants scale[row % rows_per_poly] = {c * N^-1, c * psi^-bitrev(1) * N^-1} (c = 1 when
+// scale == nullptr).
 template <int LOG_R, class LoadOp, class StoreOp>
 __global__ void __launch_bounds__(256) ntt_inv_pass_a(DevTables T, RowMap map, LoadOp ld, StoreOp st,
                                                       const ShoupConst* scale) {
@@ -250,7 +252,7 @@ __global__ void __launch_bounds__(256) ntt_inv_pass_a(DevTables T, RowMap map, L
     const u64 q = M.q, two_q = 2 * M.q;
     const int log_n = T.log_n;
     const ShoupConst* tw = T.tw_inv + ((size_t)mid << log_n);
-    const ShoupConst* fin = scale ? scale + 2 * (size_t)row : T.inv_final + 2 * (size_t)mid;
+    const ShoupConst* fin = scale ? scale + 2 * (size_t)(row % map.rows_per_poly) : T.inv_final + 2 * (size_t)mid;
     const ShoupConst fin0 = fin[0], fin1 = fin[1];
     const int tid = threadIdx.x, cc = tid % COLS, g = tid / COLS;
     const u32 c = blockIdx.x * COLS + cc;

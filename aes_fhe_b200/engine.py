@@ -14,8 +14,10 @@ every polynomial operation to a *backend*:
 * tests / CPU baseline only: ``oracle.refmod.RefBackend`` is injected explicitly by
   ``tests/`` and ``bench.py`` to obtain the bit-exact residues the kernels must match.
 
-Ciphertext layout: ``polys`` is ``[npoly, level+1, N]`` 64-bit residues in the NTT
-(evaluation) domain, bit-reversed spectrum order, canonical [0, q).
+Ciphertext layout: ``polys`` is ``[npoly, batch, level+1, N]`` 64-bit residues in the NTT
+(evaluation) domain, bit-reversed spectrum order, canonical [0, q).  ``batch`` independent
+ciphertexts (each packing slot_count/16 AES blocks) move through every operation together;
+the reference's one-ciphertext calls are the batch = 1 case.
 """
 from __future__ import annotations
 
@@ -74,23 +76,27 @@ class Ciphertext:
     def npoly(self) -> int:
         return self.engine.backend.npoly(self.polys)
 
+    @property
+    def batch(self) -> int:
+        return self.engine.backend.batch(self.polys)
+
     def __repr__(self):
-        return f"Ciphertext(level={self._level}, npoly={self.npoly})"
+        return f"Ciphertext(level={self._level}, npoly={self.npoly}, batch={self.batch})"
 
 
 class SecretKey:
     def __init__(self, coeffs: np.ndarray, ntt_full):
         self.coeffs = coeffs          # int64 ternary, length N
-        self.ntt = ntt_full           # [1, n_q+n_p, N]
+        self.ntt = ntt_full           # [1, 1, n_q+n_p, N]
 
 
 class PublicKey:
     def __init__(self, polys):
-        self.polys = polys            # [2, n_q, N]
+        self.polys = polys            # [2, 1, n_q, N]
 
 
 class SwitchKey:
-    """Hybrid key-switching key  [dnum, 2, n_q+n_p, N]."""
+    """Hybrid key-switching key  [dnum, 2, 1, n_q+n_p, N]."""
 
     def __init__(self, data, galois: Optional[int] = None):
         self.data = data
@@ -202,16 +208,17 @@ class Engine:
     def _count(self, name: str, k: int = 1):
         self.op_counts[name] = self.op_counts.get(name, 0) + k
 
-    def _sample_ternary(self) -> np.ndarray:
-        return self._rng.integers(-1, 2, size=self.params.n, dtype=np.int64)
+    def _sample_ternary(self, batch: int = 1) -> np.ndarray:
+        return self._rng.integers(-1, 2, size=(batch, self.params.n), dtype=np.int64)
 
-    def _sample_error(self) -> np.ndarray:
-        return np.rint(self._rng.normal(0.0, _SIGMA, size=self.params.n)).astype(np.int64)
+    def _sample_error(self, batch: int = 1) -> np.ndarray:
+        return np.rint(self._rng.normal(0.0, _SIGMA, size=(batch, self.params.n))).astype(np.int64)
 
     def _sample_uniform(self, limb_ids: Sequence[int]) -> np.ndarray:
-        out = np.empty((len(limb_ids), self.params.n), dtype=np.uint64)
+        """[1, 1, len(limb_ids), N] uniform residues"""
+        out = np.empty((1, 1, len(limb_ids), self.params.n), dtype=np.uint64)
         for r, l in enumerate(limb_ids):
-            out[r] = self._rng.integers(0, self.params.moduli[l], size=self.params.n, dtype=np.uint64)
+            out[0, 0, r] = self._rng.integers(0, self.params.moduli[l], size=self.params.n, dtype=np.uint64)
         return out
 
     def _const_residues(self, re: int, im: int, n_q_active: int):
@@ -232,14 +239,14 @@ class Engine:
     def create_public_key(self, sk: SecretKey) -> PublicKey:
         be, P = self.backend, self.params
         nq = P.n_q
-        a = be.from_numpy(self._sample_uniform(range(nq))[None])
+        a = be.from_numpy(self._sample_uniform(range(nq)))
         e = be.from_i64(self._sample_error(), nq, False)
         s = be.take_limbs(sk.ntt, nq, False)
         b = be.sub(e, be.mul(a, s, nq, 0), nq, 0)
         return PublicKey(be.concat([b, a]))
 
     def _make_switch_key(self, sk: SecretKey, s_from) -> Any:
-        """KSK for s_from -> s.  s_from: [1, n_q+n_p, N] NTT."""
+        """KSK for s_from -> s.  s_from: [1, 1, n_q+n_p, N] NTT."""
         be, P = self.backend, self.params
         nq, npp = P.n_q, P.n_p
         tot = nq + npp
@@ -250,7 +257,7 @@ class Engine:
         parts = []
         for j in range(P.dnum):
             lo, hi = j * P.alpha, min((j + 1) * P.alpha, nq)
-            a = be.from_numpy(self._sample_uniform(ids)[None])
+            a = be.from_numpy(self._sample_uniform(ids))
             e = be.from_i64(self._sample_error(), nq, True)
             b = be.sub(e, be.mul(a, sk.ntt, nq, npp), nq, npp)
             # + (P mod q_i) * s_from on the digit's own limbs
@@ -302,23 +309,28 @@ class Engine:
         return Plaintext(self, v)
 
     def encrypt(self, data, public_key: PublicKey, level: Optional[int] = None) -> Ciphertext:
+        """1-D data -> one ciphertext; 2-D data [B, <= slot_count] -> a batch of B ciphertexts."""
         be, P = self.backend, self.params
         if isinstance(data, Plaintext):
             data = data.values
+        data = np.asarray(data)
+        rows = data.reshape(1, -1) if data.ndim <= 1 else data
+        bt = rows.shape[0]
         lvl = P.max_level if level is None else int(level)
         nq = lvl + 1
-        m = be.from_i64(encoding.encode_i64(np.asarray(data), P.scale(lvl), P.log_n), nq, False)
-        v = be.from_i64(self._sample_ternary(), nq, False)
-        e0 = be.from_i64(self._sample_error(), nq, False)
-        e1 = be.from_i64(self._sample_error(), nq, False)
+        coeffs = np.stack([encoding.encode_i64(r, P.scale(lvl), P.log_n) for r in rows])
+        m = be.from_i64(coeffs, nq, False)
+        v = be.from_i64(self._sample_ternary(bt), nq, False)
+        e0 = be.from_i64(self._sample_error(bt), nq, False)
+        e1 = be.from_i64(self._sample_error(bt), nq, False)
         pk = public_key.polys if nq == P.n_q else be.take_limbs(public_key.polys, nq, False)
-        vb = be.mul(pk, v, nq, 0)                      # [2,nq,N] * [1,nq,N]
+        vb = be.mul(pk, v, nq, 0)                      # [2,1,nq,N] * [1,B,nq,N]
         c = be.add(vb, be.concat([be.add(e0, m, nq, 0), e1]), nq, 0)
-        self._count('encrypt')
+        self._count('encrypt', bt)
         return Ciphertext(self, c, lvl)
 
     def decrypt_to_plaintext_coeffs(self, ct: Ciphertext, sk: SecretKey) -> np.ndarray:
-        """Centred coefficient vector (float64) of c0 + c1 s (+ c2 s^2)."""
+        """Centred coefficient vectors (float64 [batch, N]) of c0 + c1 s (+ c2 s^2)."""
         be = self.backend
         use = min(2, ct.level + 1)
         c = be.take_limbs(ct.polys, use, False)
@@ -332,8 +344,10 @@ class Engine:
 
     def decrypt(self, ct: Ciphertext, sk: SecretKey) -> np.ndarray:
         m = self.decrypt_to_plaintext_coeffs(ct, sk)
-        self._count('decrypt')
-        return encoding.coeffs_to_slots(m, self.params.log_n) / self.params.scale(ct.level)
+        self._count('decrypt', m.shape[0])
+        scale = self.params.scale(ct.level)
+        out = np.stack([encoding.coeffs_to_slots(r, self.params.log_n) for r in m]) / scale
+        return out[0] if out.shape[0] == 1 else out
 
     # ------------------------------------------------------------------ level management
     def _rescale(self, ct: Ciphertext) -> Ciphertext:
@@ -355,7 +369,7 @@ class Engine:
             raise RuntimeError("cannot raise the level of a ciphertext without bootstrapping")
         P = self.params
         if ct.zero:
-            return self._zero(target, ct.npoly)
+            return self._zero(target, ct.npoly, ct.batch)
         polys = ct.polys
         if ct.level > target + 1:
             polys = self.backend.take_limbs(polys, target + 2, False)
@@ -371,8 +385,8 @@ class Engine:
             b = self.level_down(b, a.level)
         return a, b
 
-    def _zero(self, level: int, npoly: int = 2) -> Ciphertext:
-        return Ciphertext(self, self.backend.zeros(npoly, level + 1, False), level, zero=True)
+    def _zero(self, level: int, npoly: int = 2, batch: int = 1) -> Ciphertext:
+        return Ciphertext(self, self.backend.zeros(npoly, batch, level + 1, False), level, zero=True)
 
     # ------------------------------------------------------------------ arithmetic
     def add(self, a, b):
@@ -401,9 +415,9 @@ class Engine:
     def _pad_poly(self, a: Ciphertext, b: Ciphertext):
         be = self.backend
         if a.npoly < b.npoly:
-            a = Ciphertext(self, be.concat([a.polys, be.zeros(b.npoly - a.npoly, a.level + 1, False)]), a.level)
+            a = Ciphertext(self, be.concat([a.polys, be.zeros(b.npoly - a.npoly, a.batch, a.level + 1, False)]), a.level)
         else:
-            b = Ciphertext(self, be.concat([b.polys, be.zeros(a.npoly - b.npoly, b.level + 1, False)]), b.level)
+            b = Ciphertext(self, be.concat([b.polys, be.zeros(a.npoly - b.npoly, b.batch, b.level + 1, False)]), b.level)
         return a, b
 
     def add_plain(self, ct: Ciphertext, value) -> Ciphertext:
@@ -435,7 +449,7 @@ class Engine:
             if a.level == 0:
                 raise RuntimeError("multiply: no multiplicative depth left")
             if a.zero:
-                return self._zero(a.level - 1, a.npoly)
+                return self._zero(a.level - 1, a.npoly, a.batch)
             self._count('mul_pt')
             prod = self.backend.mul(a.polys, b.at_level(a.level), a.level + 1, 0)
             return self._rescale(Ciphertext(self, prod, a.level))
@@ -448,7 +462,7 @@ class Engine:
             raise RuntimeError("multiply: no multiplicative depth left")
         v = complex(value)
         if v == 0 or ct.zero:
-            return self._zero(ct.level - 1, ct.npoly)
+            return self._zero(ct.level - 1, ct.npoly, ct.batch)
         re, im = encoding.const_i64(v, self.params.delta[ct.level])
         self._count('mul_const')
         return self._rescale(self._mul_int_const(ct, re, im))
@@ -460,7 +474,7 @@ class Engine:
         if a.level == 0:
             raise RuntimeError("multiply: no multiplicative depth left")
         if a.zero or b.zero:
-            return self._zero(a.level - 1, 2 if rlk is not None else 3)
+            return self._zero(a.level - 1, 2 if rlk is not None else 3, max(a.batch, b.batch))
         nq = a.level + 1
         self._count('mul_ct')
         d = self.backend.tensor(a.polys, b.polys, nq)
@@ -485,7 +499,7 @@ class Engine:
             raise RuntimeError("relinearize: ciphertext should have 3 polynomials, "
                                f"but it has {ct.npoly}")
         if ct.zero:
-            return self._zero(ct.level, 2)
+            return self._zero(ct.level, 2, ct.batch)
         return self._relin(ct, relin_key)
 
     def rescale(self, ct: Ciphertext) -> Ciphertext:

@@ -52,6 +52,7 @@ def bivariate_lut(eng_wrap, ct_x, ct_y, coeff_mats: Sequence[np.ndarray],
     if lo < 2:
         raise RuntimeError("bivariate_lut: not enough levels left")
     nq = lo + 1
+    bt = max(ct_x.batch, ct_y.batch)
     # scale of the accumulated products before the two closing rescales
     target = P.delta[lo - 2] * P.moduli[lo] * P.moduli[lo - 1]
     xs = {i: (be.take_limbs(c.polys, nq, False) if c.level > lo else c.polys) for i, c in bx.items()}
@@ -59,7 +60,7 @@ def bivariate_lut(eng_wrap, ct_x, ct_y, coeff_mats: Sequence[np.ndarray],
     outs = []
     for C in coeff_mats:
         C = np.asarray(C, dtype=np.complex128)
-        acc = be.zeros(3, nq, False)
+        acc = be.zeros(3, bt, nq, False)
         for i in range(16):
             row = C[i]
             if not np.any(np.abs(row) > 1e-13):
@@ -74,7 +75,7 @@ def bivariate_lut(eng_wrap, ct_x, ct_y, coeff_mats: Sequence[np.ndarray],
                 term = be.mul_const(ys[j], cp, cm, nq)
                 inner = term if inner is None else be.add(inner, term, nq, 0)
             if inner is None:
-                inner = be.zeros(2, nq, False)
+                inner = be.zeros(2, bt, nq, False)
             if abs(row[0]) > 1e-13:
                 cp, cm = _const_to_residues(eng, row[0], s_in, nq)
                 inner = be.add_const(inner, cp, cm, nq)

@@ -46,18 +46,20 @@ int fhe_ntt_fwd(fhe_ctx* ctx, void* stream, uint64_t* data, int npoly, int nq, i
 int fhe_ntt_inv(fhe_ctx* ctx, void* stream, uint64_t* data, int npoly, int nq, int np);
 
 /* Engine.add(ct, ct) / subtract / pointwise products (xor_service.py:76,
- * sbox/sbox_service.py:105,112,129,136).  b is broadcast over polys when npoly_b == 1. */
+ * sbox/sbox_service.py:105,112,129,136).  out, a: [npoly][batch][nq+np][N];
+ * b: [b_npoly][b_batch][nq+np][N] with b_npoly in {npoly, 1} and b_batch in {batch, 1}
+ * (1 = broadcast: plaintext masks and keys are shared by the polys / the batch). */
 int fhe_add(fhe_ctx* ctx, void* stream, uint64_t* out, const uint64_t* a, const uint64_t* b,
-            int npoly, int npoly_b, int nq, int np);
+            int npoly, int batch, int b_npoly, int b_batch, int nq, int np);
 int fhe_sub(fhe_ctx* ctx, void* stream, uint64_t* out, const uint64_t* a, const uint64_t* b,
-            int npoly, int npoly_b, int nq, int np);
+            int npoly, int batch, int b_npoly, int b_batch, int nq, int np);
 int fhe_mul(fhe_ctx* ctx, void* stream, uint64_t* out, const uint64_t* a, const uint64_t* b,
-            int npoly, int npoly_b, int nq, int np);
+            int npoly, int batch, int b_npoly, int b_batch, int nq, int np);
 int fhe_neg(fhe_ctx* ctx, void* stream, uint64_t* out, const uint64_t* a, int npoly, int nq, int np);
 
 /* Engine.multiply(ct, ct) tensor step (xor_service.py:71, sbox/sbox_service.py:114):
- * out[3][nq][N] = (a0 b0, a0 b1 + a1 b0, a1 b1). */
-int fhe_tensor(fhe_ctx* ctx, void* stream, uint64_t* out, const uint64_t* a, const uint64_t* b, int nq);
+ * out[3][batch][nq][N] = (a0 b0, a0 b1 + a1 b0, a1 b1) for a, b = [2][batch][nq][N]. */
+int fhe_tensor(fhe_ctx* ctx, void* stream, uint64_t* out, const uint64_t* a, const uint64_t* b, int nq, int batch);
 
 /* Engine.multiply(ct, float|const Plaintext) / add_plain (xor_service.py:78-83,98,282-285;
  * sbox/sbox_service.py:124-136): multiply (or add) by the encoding of a complex constant,
@@ -79,27 +81,28 @@ int fhe_automorphism(fhe_ctx* ctx, void* stream, uint64_t* out, const uint64_t* 
 
 /* Hybrid key switching (Engine.relinearize, the relin inside multiply(ct,ct,rlk),
  * rotate, conjugate).  ksk: [dnum][2][n_q + n_p][N] over the full chain.
- *   fhe_keyswitch : d[nq][N] -> out[2][nq][N]          (= moddown(inner(modup(d))))
+ * A batch of `batch` independent ciphertexts shares one pass over the key.
+ *   fhe_keyswitch : d[batch][nq][N] -> out[2][batch][nq][N]   (= moddown(inner(modup(d))))
  * The three phases are exported for hoisted rotations and for phase-level parity tests:
- *   fhe_modup    : d[nq][N] -> ext[beta][nq+n_p][N]   (rows of a digit's own limbs are left
- *                                                      untouched; inner reads them from d)
- *   fhe_ks_inner : (ext, d, ksk) -> acc[2][nq+n_p][N]
+ *   fhe_modup    : d[batch][nq][N] -> ext[batch][beta][nq+n_p][N]   (rows of a digit's own
+ *                  limbs are left untouched; the inner product reads them from d)
+ *   fhe_ks_inner : (ext, d, ksk) -> acc[2][batch][nq+n_p][N]
  *   fhe_moddown  : acc[npoly][nq+n_p][N] -> out[npoly][nq][N]   (acc's special limbs are
- *                                                      overwritten with scratch data) */
+ *                  overwritten with scratch data) */
 int fhe_keyswitch(fhe_ctx* ctx, void* stream, uint64_t* out, const uint64_t* d,
-                  const uint64_t* ksk, int nq);
-int fhe_modup(fhe_ctx* ctx, void* stream, uint64_t* ext, const uint64_t* d, int nq);
+                  const uint64_t* ksk, int nq, int batch);
+int fhe_modup(fhe_ctx* ctx, void* stream, uint64_t* ext, const uint64_t* d, int nq, int batch);
 int fhe_ks_inner(fhe_ctx* ctx, void* stream, uint64_t* acc, const uint64_t* ext,
-                 const uint64_t* d, const uint64_t* ksk, int nq);
+                 const uint64_t* d, const uint64_t* ksk, int nq, int batch);
 int fhe_moddown(fhe_ctx* ctx, void* stream, uint64_t* out, uint64_t* acc, int nq, int npoly);
 
 /* Engine.encode / encrypt residue step (xor_service.py:59-66): signed 64-bit coefficients
- * (device) -> coefficient-domain residues of a [nq + np][N] block. */
-int fhe_from_i64(fhe_ctx* ctx, void* stream, uint64_t* out, const int64_t* coeffs, int nq, int np);
+ * coeffs[batch][N] (device) -> coefficient-domain residues out[batch][nq + np][N]. */
+int fhe_from_i64(fhe_ctx* ctx, void* stream, uint64_t* out, const int64_t* coeffs, int nq, int np, int batch);
 
 /* Engine.decrypt tail (xor_service.py:62-63): centred CRT of coefficient-domain limbs
- * 0..limbs-1 (limbs = 1 or 2) of x to doubles. */
-int fhe_crt_centered(fhe_ctx* ctx, void* stream, double* out, const uint64_t* x, int limbs);
+ * 0..limbs-1 (limbs = 1 or 2) of x[batch][limbs][N] to doubles out[batch][N]. */
+int fhe_crt_centered(fhe_ctx* ctx, void* stream, double* out, const uint64_t* x, int limbs, int batch);
 
 #ifdef __cplusplus
 }

@@ -61,13 +61,16 @@ class RefBackend:
         except Exception:
             pass
 
-    # ---- layout helpers
-    def _ids(self, nq: int, np_: int, npoly: int = 1) -> np.ndarray:
+    # ---- layout helpers.  Handles are uint64 arrays [npoly, batch, limbs, N].
+    def _ids(self, nq: int, np_: int, reps: int = 1) -> np.ndarray:
         ids = list(range(nq)) + [self.params.n_q + k for k in range(np_)]
-        return np.array(ids * npoly, dtype=np.int32)
+        return np.array(ids * reps, dtype=np.int32)
 
     def npoly(self, h) -> int:
         return h.shape[0]
+
+    def batch(self, h) -> int:
+        return h.shape[1]
 
     def from_numpy(self, a: np.ndarray):
         return np.ascontiguousarray(a, dtype=np.uint64)
@@ -75,14 +78,14 @@ class RefBackend:
     def to_numpy(self, h) -> np.ndarray:
         return np.array(h, dtype=np.uint64, copy=True)
 
-    def zeros(self, npoly: int, nq: int, with_p: bool):
-        return np.zeros((npoly, nq + (self.params.n_p if with_p else 0), self.n), dtype=np.uint64)
+    def zeros(self, npoly: int, batch: int, nq: int, with_p: bool):
+        return np.zeros((npoly, batch, nq + (self.params.n_p if with_p else 0), self.n), dtype=np.uint64)
 
     def take_limbs(self, h, nq: int, with_p: bool):
         if with_p:
             K = self.params.n_p
-            return np.ascontiguousarray(np.concatenate([h[:, :nq], h[:, h.shape[1] - K:]], axis=1))
-        return np.ascontiguousarray(h[:, :nq])
+            return np.ascontiguousarray(np.concatenate([h[:, :, :nq], h[:, :, h.shape[2] - K:]], axis=2))
+        return np.ascontiguousarray(h[:, :, :nq])
 
     def select_poly(self, h, i: int):
         return h[i:i + 1]
@@ -96,35 +99,42 @@ class RefBackend:
     def stack(self, hs: List):
         return np.ascontiguousarray(np.stack(hs, axis=0))
 
+    def expand_batch(self, h, batch: int):
+        return h if h.shape[1] == batch else np.ascontiguousarray(np.broadcast_to(h, (h.shape[0], batch) + h.shape[2:]))
+
     # ---- transforms
     def ntt(self, h, nq: int, np_: int):
         out = np.array(h, copy=True)
-        ids = self._ids(nq, np_, out.shape[0])
+        ids = self._ids(nq, np_, out.shape[0] * out.shape[1])
         self._L.ref_ntt(self._ctx, _p(out), _p(ids), C.c_int(len(ids)))
         return out
 
     def intt(self, h, nq: int, np_: int):
         out = np.array(h, copy=True)
-        ids = self._ids(nq, np_, out.shape[0])
+        ids = self._ids(nq, np_, out.shape[0] * out.shape[1])
         self._L.ref_intt(self._ctx, _p(out), _p(ids), C.c_int(len(ids)))
         return out
 
     def from_i64(self, coeffs: np.ndarray, nq: int, with_p: bool):
         np_ = self.params.n_p if with_p else 0
         ids = self._ids(nq, np_)
-        out = np.empty((1, len(ids), self.n), dtype=np.uint64)
-        c = np.ascontiguousarray(coeffs, dtype=np.int64)
-        self._L.ref_from_i64(self._ctx, _p(out), _p(c), _p(ids), C.c_int(len(ids)))
-        self._L.ref_ntt(self._ctx, _p(out), _p(ids), C.c_int(len(ids)))
+        c = np.ascontiguousarray(coeffs, dtype=np.int64).reshape(-1, self.n)
+        out = np.empty((1, c.shape[0], len(ids), self.n), dtype=np.uint64)
+        for b in range(c.shape[0]):
+            o = np.empty((len(ids), self.n), dtype=np.uint64)
+            cb = np.ascontiguousarray(c[b])
+            self._L.ref_from_i64(self._ctx, _p(o), _p(cb), _p(ids), C.c_int(len(ids)))
+            self._L.ref_ntt(self._ctx, _p(o), _p(ids), C.c_int(len(ids)))
+            out[0, b] = o
         return out
 
     # ---- elementwise
     def _bin(self, fn, a, b, nq, np_):
-        npoly = max(a.shape[0], b.shape[0])
-        a = np.ascontiguousarray(np.broadcast_to(a, (npoly,) + a.shape[1:]))
-        b = np.ascontiguousarray(np.broadcast_to(b, (npoly,) + b.shape[1:]))
+        shape = (max(a.shape[0], b.shape[0]), max(a.shape[1], b.shape[1])) + a.shape[2:]
+        a = np.ascontiguousarray(np.broadcast_to(a, shape))
+        b = np.ascontiguousarray(np.broadcast_to(b, shape))
         out = np.empty_like(a)
-        ids = self._ids(nq, np_, npoly)
+        ids = self._ids(nq, np_, shape[0] * shape[1])
         fn(self._ctx, _p(out), _p(a), _p(b), _p(ids), C.c_int(len(ids)))
         return out
 
@@ -140,37 +150,29 @@ class RefBackend:
     def neg(self, a, nq, np_):
         a = np.ascontiguousarray(a)
         out = np.empty_like(a)
-        ids = self._ids(nq, np_, a.shape[0])
+        ids = self._ids(nq, np_, a.shape[0] * a.shape[1])
         self._L.ref_neg(self._ctx, _p(out), _p(a), _p(ids), C.c_int(len(ids)))
         return out
 
-    def mul_scalar(self, a, fac: Sequence[int], nq, np_):
+    def _constop(self, fn, a, cp, cm, nq, np_):
         a = np.ascontiguousarray(a)
-        npoly = a.shape[0]
-        f = np.array(list(fac) * npoly, dtype=np.uint64)
+        reps = a.shape[0] * a.shape[1]
+        fp = np.array([int(v) for v in cp] * reps, dtype=np.uint64)
+        fm = np.array([int(v) for v in cm] * reps, dtype=np.uint64)
         out = np.empty_like(a)
-        ids = self._ids(nq, np_, npoly)
-        self._L.ref_mul_const(self._ctx, _p(out), _p(a), _p(f), _p(f), _p(ids), C.c_int(len(ids)))
+        ids = self._ids(nq, np_, reps)
+        fn(self._ctx, _p(out), _p(a), _p(fp), _p(fm), _p(ids), C.c_int(len(ids)))
         return out
 
+    def mul_scalar(self, a, fac: Sequence[int], nq, np_):
+        return self._constop(self._L.ref_mul_const, a, fac, fac, nq, np_)
+
     def mul_const(self, a, cp, cm, nq):
-        a = np.ascontiguousarray(a)
-        npoly = a.shape[0]
-        fp = np.array(list(cp) * npoly, dtype=np.uint64)
-        fm = np.array(list(cm) * npoly, dtype=np.uint64)
-        out = np.empty_like(a)
-        ids = self._ids(nq, 0, npoly)
-        self._L.ref_mul_const(self._ctx, _p(out), _p(a), _p(fp), _p(fm), _p(ids), C.c_int(len(ids)))
-        return out
+        return self._constop(self._L.ref_mul_const, a, cp, cm, nq, 0)
 
     def add_const(self, a, cp, cm, nq):
         out = np.array(a, copy=True)
-        fp = np.array(list(cp), dtype=np.uint64)
-        fm = np.array(list(cm), dtype=np.uint64)
-        ids = self._ids(nq, 0, 1)
-        p0 = np.ascontiguousarray(out[0])
-        self._L.ref_add_const(self._ctx, _p(p0), _p(p0), _p(fp), _p(fm), _p(ids), C.c_int(len(ids)))
-        out[0] = p0
+        out[0:1] = self._constop(self._L.ref_add_const, out[0:1], cp, cm, nq, 0)
         return out
 
     def add_poly0(self, a, p, nq):
@@ -188,48 +190,64 @@ class RefBackend:
     # ---- structural
     def rescale(self, h, nq):
         h = np.ascontiguousarray(h)
-        out = np.empty((h.shape[0], nq - 1, self.n), dtype=np.uint64)
+        out = np.empty(h.shape[:2] + (nq - 1, self.n), dtype=np.uint64)
         for i in range(h.shape[0]):
-            o = np.empty((nq - 1, self.n), dtype=np.uint64)
-            self._L.ref_rescale(self._ctx, _p(o), _p(np.ascontiguousarray(h[i])), C.c_int(nq))
-            out[i] = o
+            for b in range(h.shape[1]):
+                o = np.empty((nq - 1, self.n), dtype=np.uint64)
+                self._L.ref_rescale(self._ctx, _p(o), _p(np.ascontiguousarray(h[i, b])), C.c_int(nq))
+                out[i, b] = o
         return out
 
     def automorphism(self, h, g: int, nq, np_):
         h = np.ascontiguousarray(h)
         out = np.empty_like(h)
-        self._L.ref_automorphism(self._ctx, _p(out), _p(h), C.c_uint64(int(g)), C.c_int(h.shape[0] * h.shape[1]))
+        self._L.ref_automorphism(self._ctx, _p(out), _p(h), C.c_uint64(int(g)),
+                                 C.c_int(h.shape[0] * h.shape[1] * h.shape[2]))
         return out
 
     def modup(self, d, nq):
+        """d [1, B, nq, N] -> ext [B, beta, nq+K, N]"""
         P = self.params
         beta = P.digits_at(nq)
-        ext = np.empty((beta, nq + P.n_p, self.n), dtype=np.uint64)
-        self._L.ref_modup(self._ctx, _p(ext), _p(np.ascontiguousarray(d)), C.c_int(nq))
+        ext = np.empty((d.shape[1], beta, nq + P.n_p, self.n), dtype=np.uint64)
+        for b in range(d.shape[1]):
+            e = np.empty((beta, nq + P.n_p, self.n), dtype=np.uint64)
+            self._L.ref_modup(self._ctx, _p(e), _p(np.ascontiguousarray(d[0, b])), C.c_int(nq))
+            ext[b] = e
         return ext
 
-    def ks_inner(self, ext, ksk, nq):
-        acc = np.empty((2, nq + self.params.n_p, self.n), dtype=np.uint64)
-        self._L.ref_ks_inner(self._ctx, _p(acc), _p(ext), _p(np.ascontiguousarray(ksk)), C.c_int(nq))
+    def ks_inner(self, ext, d, ksk, nq):
+        """-> acc [2, B, nq+K, N]"""
+        ksk = np.ascontiguousarray(ksk)
+        acc = np.empty((2, ext.shape[0], nq + self.params.n_p, self.n), dtype=np.uint64)
+        for b in range(ext.shape[0]):
+            a = np.empty((2, nq + self.params.n_p, self.n), dtype=np.uint64)
+            self._L.ref_ks_inner(self._ctx, _p(a), _p(np.ascontiguousarray(ext[b])), _p(ksk), C.c_int(nq))
+            acc[:, b] = a
         return acc
 
     def moddown(self, acc, nq):
         acc = np.ascontiguousarray(acc)
-        out = np.empty((acc.shape[0], nq, self.n), dtype=np.uint64)
-        self._L.ref_moddown(self._ctx, _p(out), _p(acc), C.c_int(nq), C.c_int(acc.shape[0]))
-        return out
+        flat = acc.reshape(-1, acc.shape[2], self.n)
+        out = np.empty((flat.shape[0], nq, self.n), dtype=np.uint64)
+        self._L.ref_moddown(self._ctx, _p(out), _p(flat), C.c_int(nq), C.c_int(flat.shape[0]))
+        return out.reshape(acc.shape[0], acc.shape[1], nq, self.n)
 
     def keyswitch(self, d, ksk, nq):
-        return self.moddown(self.ks_inner(self.modup(d, nq), ksk, nq), nq)
+        return self.moddown(self.ks_inner(self.modup(d, nq), d, ksk, nq), nq)
 
     def crt_centered(self, h, use: int) -> np.ndarray:
+        """h [1, B, use, N] -> float64 [B, N]"""
         h = np.ascontiguousarray(h)
-        out = np.empty(self.n, dtype=np.float64)
-        if use >= 2:
-            self._L.ref_crt2_centered(self._ctx, _p(out), _p(np.ascontiguousarray(h[0, 0])),
-                                      _p(np.ascontiguousarray(h[0, 1])))
-        else:
-            self._L.ref_crt1_centered(self._ctx, _p(out), _p(np.ascontiguousarray(h[0, 0])))
+        out = np.empty((h.shape[1], self.n), dtype=np.float64)
+        for b in range(h.shape[1]):
+            o = np.empty(self.n, dtype=np.float64)
+            if use >= 2:
+                self._L.ref_crt2_centered(self._ctx, _p(o), _p(np.ascontiguousarray(h[0, b, 0])),
+                                          _p(np.ascontiguousarray(h[0, b, 1])))
+            else:
+                self._L.ref_crt1_centered(self._ctx, _p(o), _p(np.ascontiguousarray(h[0, b, 0])))
+            out[b] = o
         return out
 
     def synchronize(self):

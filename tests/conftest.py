@@ -37,12 +37,14 @@ def cuda_lib():
     return b.build_cuda()
 
 
-def rand_poly(params, rng, npoly, nq, with_p):
+def rand_poly(params, rng, npoly, nq, with_p, batch=1):
+    """uniform residues [npoly, batch, limbs, N]"""
     ids = list(range(nq)) + ([params.n_q + k for k in range(params.n_p)] if with_p else [])
-    a = np.empty((npoly, len(ids), params.n), dtype=np.uint64)
+    a = np.empty((npoly, batch, len(ids), params.n), dtype=np.uint64)
     for p in range(npoly):
-        for r, l in enumerate(ids):
-            a[p, r] = rng.integers(0, params.moduli[l], size=params.n, dtype=np.uint64)
+        for b in range(batch):
+            for r, l in enumerate(ids):
+                a[p, b, r] = rng.integers(0, params.moduli[l], size=params.n, dtype=np.uint64)
     return a
 
 

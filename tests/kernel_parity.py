@@ -13,37 +13,44 @@ def check_primitives(P, gb, rb, seed=1):
     assert np.array_equal(gb.to_numpy(gb.ntt(up(a), nq, K)), rb.ntt(a, nq, K)), "ntt"
     assert np.array_equal(gb.to_numpy(gb.intt(up(a), nq, K)), rb.intt(a, nq, K)), "intt"
     assert np.array_equal(gb.to_numpy(gb.intt(gb.ntt(up(a), nq, K), nq, K)), a), "ntt round trip"
-    b = rand_poly(P, rng, 2, nq, False)
-    c = rand_poly(P, rng, 2, nq, False)
-    c1 = rand_poly(P, rng, 1, nq, False)
+    b = rand_poly(P, rng, 2, nq, False, batch=2)
+    c = rand_poly(P, rng, 2, nq, False, batch=2)
+    c1 = rand_poly(P, rng, 1, nq, False, batch=2)
+    c11 = rand_poly(P, rng, 1, nq, False, batch=1)
+    c21 = rand_poly(P, rng, 2, nq, False, batch=1)
     for name in ("add", "sub", "mul"):
         assert np.array_equal(gb.to_numpy(getattr(gb, name)(up(b), up(c), nq, 0)), getattr(rb, name)(b, c, nq, 0)), name
-    assert np.array_equal(gb.to_numpy(gb.mul(up(b), up(c1), nq, 0)), rb.mul(b, c1, nq, 0)), "mul broadcast"
+        for other, tag in ((c1, "poly"), (c11, "poly+batch"), (c21, "batch")):
+            assert np.array_equal(gb.to_numpy(getattr(gb, name)(up(b), up(other), nq, 0)),
+                                  getattr(rb, name)(b, other, nq, 0)), f"{name} broadcast {tag}"
+    assert np.array_equal(gb.to_numpy(gb.mul(up(c21), up(c1), nq, 0)), rb.mul(c21, c1, nq, 0)), "mul cross broadcast"
+    assert np.array_equal(gb.to_numpy(gb.sub(up(c11), up(b), nq, 0)), rb.sub(c11, b, nq, 0)), "sub small - big"
     assert np.array_equal(gb.to_numpy(gb.neg(up(b), nq, 0)), rb.neg(b, nq, 0)), "neg"
     assert np.array_equal(gb.to_numpy(gb.tensor(up(b), up(c), nq)), rb.tensor(b, c, nq)), "tensor"
     for g in (5, 2 * P.n - 1, pow(5, 7, 2 * P.n), pow(5, P.slot_count - 3, 2 * P.n)):
         assert np.array_equal(gb.to_numpy(gb.automorphism(up(b), g, nq, 0)), rb.automorphism(b, g, nq, 0)), f"auto {g}"
-    co = rng.integers(-2 ** 55, 2 ** 55, size=P.n, dtype=np.int64)
-    co[:4] = [0, -1, 1, -(2 ** 62)]
+    co = rng.integers(-2 ** 55, 2 ** 55, size=(2, P.n), dtype=np.int64)
+    co[0, :4] = [0, -1, 1, -(2 ** 62)]
     assert np.array_equal(gb.to_numpy(gb.from_i64(co, nq, True)), rb.from_i64(co, nq, True)), "from_i64"
     cp = [int(rng.integers(0, P.moduli[l])) for l in range(nq)]
     cm = [int(rng.integers(0, P.moduli[l])) for l in range(nq)]
     assert np.array_equal(gb.to_numpy(gb.mul_const(up(b), cp, cm, nq)), rb.mul_const(b, cp, cm, nq)), "mul_const"
     assert np.array_equal(gb.to_numpy(gb.add_const(up(b), cp, cm, nq)), rb.add_const(b, cp, cm, nq)), "add_const"
     assert np.array_equal(gb.to_numpy(gb.add_poly0(up(b), up(c1), nq)), rb.add_poly0(b, c1, nq)), "add_poly0"
-    x = rand_poly(P, rng, 1, 2, False)
+    x = rand_poly(P, rng, 1, 2, False, batch=3)
     assert np.array_equal(gb.crt_centered(up(x), 2), rb.crt_centered(x, 2)), "crt2"
-    assert np.array_equal(gb.crt_centered(up(x), 1), rb.crt_centered(x, 1)), "crt1"
+    x1 = np.ascontiguousarray(x[:, :, :1])
+    assert np.array_equal(gb.crt_centered(up(x1), 1), rb.crt_centered(x1, 1)), "crt1"
 
 
 def check_rescale(P, gb, rb, seed=2):
     rng = np.random.default_rng(seed)
     for nq in sorted({P.n_q, max(2, P.n_q - 3), 2}):
-        for npoly in (2, 3):
-            b = rand_poly(P, rng, npoly, nq, False)
+        for npoly, batch in ((2, 1), (3, 2)):
+            b = rand_poly(P, rng, npoly, nq, False, batch=batch)
             # edge values around the centring threshold of the dropped limb
             ql = P.moduli[nq - 1]
-            b[0, nq - 1, :4] = [0, ql >> 1, (ql >> 1) + 1, ql - 1]
+            b[0, 0, nq - 1, :4] = [0, ql >> 1, (ql >> 1) + 1, ql - 1]
             assert np.array_equal(gb.to_numpy(gb.rescale(gb.from_numpy(b), nq)), rb.rescale(b, nq)), f"rescale nq={nq}"
 
 
@@ -53,13 +60,13 @@ def check_keyswitch(P, gb, rb, levels=None, seed=3):
     gk = gb.from_numpy(ksk)
     if levels is None:
         levels = sorted({P.n_q, P.n_q - 1, P.alpha, P.alpha + 1, 1, 2})
-    for nq in levels:
+    for it, nq in enumerate(levels):
         if nq < 1 or nq > P.n_q:
             continue
-        d = rand_poly(P, rng, 1, nq, False)
+        d = rand_poly(P, rng, 1, nq, False, batch=1 + it % 3)
         ge, re_ = gb.modup(gb.from_numpy(d), nq), rb.modup(d, nq)
         assert np.array_equal(gb.to_numpy(ge), re_), f"modup nq={nq}"
-        ga, ra = gb.ks_inner(ge, gb.from_numpy(d), gk, nq), rb.ks_inner(re_, ksk, nq)
+        ga, ra = gb.ks_inner(ge, gb.from_numpy(d), gk, nq), rb.ks_inner(re_, d, ksk, nq)
         assert np.array_equal(gb.to_numpy(ga), ra), f"ks_inner nq={nq}"
         gm, rm = gb.moddown(ga, nq), rb.moddown(ra, nq)
         assert np.array_equal(gb.to_numpy(gm), rm), f"moddown nq={nq}"
@@ -104,6 +111,19 @@ def check_engine_ops(eg, er, slot_tol=1e-5):
         rg, rr = eg.rotate(cg, kg['rot'], delta), er.rotate(cr, kr['rot'], delta)
         same(rg, rr, f"rotate {delta}")
         assert np.allclose(eg.decrypt(rg, kg['sk']), np.roll(v, delta), atol=slot_tol), f"rotate {delta} = np.roll"
+    # a batch of 3 ciphertexts goes through the same calls in lockstep
+    vb = np.exp(-2j * np.pi * rng.integers(0, 16, (3, sc)) / 16)
+    bg, br = eg.encrypt(vb, kg['pk']), er.encrypt(vb, kr['pk'])
+    same(bg, br, "encrypt batch")
+    assert bg.batch == 3
+    sq_g, sq_r = eg.multiply(bg, bg, kg['rlk']), er.multiply(br, br, kr['rlk'])
+    same(sq_g, sq_r, "batched multiply relin")
+    assert np.allclose(eg.decrypt(sq_g, kg['sk']), vb * vb, atol=slot_tol)
+    same(eg.multiply(bg, cg, kg['rlk']), er.multiply(br, cr, kr['rlk']), "batch x single multiply")
+    same(eg.multiply(bg, pt_g), er.multiply(br, pt_r), "batch multiply plaintext")
+    same(eg.add(bg, pt_g), er.add(br, pt_r), "batch add plaintext")
+    same(eg.rotate(bg, kg['rot'], -2), er.rotate(br, kr['rot'], -2), "batch rotate")
+    same(eg.conjugate(bg, kg['cj']), er.conjugate(br, kr['cj']), "batch conjugate")
     pg, pr = eg.make_power_basis(cg, 5, kg['rlk']), er.make_power_basis(cr, 5, kr['rlk'])
     for k, (x, y) in enumerate(zip(pg, pr), 1):
         same(x, y, f"power {k}")

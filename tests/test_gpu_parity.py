@@ -64,8 +64,8 @@ def test_linearity_property_full_size(cuda_lib):
     gb = _gpu(P)
     rng = np.random.default_rng(5)
     from conftest import rand_poly
-    a = gb.from_numpy(rand_poly(P, rng, 2, P.n_q, True))
-    b = gb.from_numpy(rand_poly(P, rng, 2, P.n_q, True))
+    a = gb.from_numpy(rand_poly(P, rng, 2, P.n_q, True, batch=2))
+    b = gb.from_numpy(rand_poly(P, rng, 2, P.n_q, True, batch=2))
     nq, K = P.n_q, P.n_p
     lhs = gb.add(gb.ntt(a, nq, K), gb.ntt(b, nq, K), nq, K)
     rhs = gb.ntt(gb.add(a, b, nq, K), nq, K)

@@ -68,12 +68,12 @@ def main():
 
     for nq in (31, 21, 11):
         x = rnd(2, nq, n); y = rnd(2, nq, n); o = torch.empty_like(x)
-        m, mn = timeit(lambda: gb._call("fhe_add", gb._ptr(o), gb._ptr(x), gb._ptr(y), 2, 2, nq, 0), flush=flush)
+        m, mn = timeit(lambda: gb._call("fhe_add", gb._ptr(o), gb._ptr(x), gb._ptr(y), 2, 1, 2, 1, nq, 0), flush=flush)
         rec("add_ct", m, mn, 6 * nq * limb, nq=nq)
-        m, mn = timeit(lambda: gb._call("fhe_mul", gb._ptr(o), gb._ptr(x), gb._ptr(y), 2, 2, nq, 0), flush=flush)
+        m, mn = timeit(lambda: gb._call("fhe_mul", gb._ptr(o), gb._ptr(x), gb._ptr(y), 2, 1, 2, 1, nq, 0), flush=flush)
         rec("mul_pointwise", m, mn, 6 * nq * limb, nq=nq)
         o3 = torch.empty(3, nq, n, dtype=torch.int64, device="cuda")
-        m, mn = timeit(lambda: gb._call("fhe_tensor", gb._ptr(o3), gb._ptr(x), gb._ptr(y), nq), flush=flush)
+        m, mn = timeit(lambda: gb._call("fhe_tensor", gb._ptr(o3), gb._ptr(x), gb._ptr(y), nq, 1), flush=flush)
         rec("tensor", m, mn, 7 * nq * limb, nq=nq)
         r = torch.empty(2, nq - 1, n, dtype=torch.int64, device="cuda")
         m, mn = timeit(lambda: gb._call("fhe_rescale", gb._ptr(r), gb._ptr(x), 2, nq), flush=flush)
@@ -81,21 +81,22 @@ def main():
         import ctypes as C
         m, mn = timeit(lambda: gb._call("fhe_automorphism", gb._ptr(o), gb._ptr(x), C.c_uint64(5), 2 * nq), flush=flush)
         rec("automorphism", m, mn, 4 * nq * limb, nq=nq)
-        # key switch
+        # key switch, batch of B ciphertexts sharing one pass over the key
         ksk = rnd(P.dnum, 2, 37, n)
-        d = rnd(1, nq, n); ko = torch.empty(2, nq, n, dtype=torch.int64, device="cuda")
         beta = P.digits_at(nq)
-        alg = (2 * beta * (nq + K) + 3 * nq) * limb
-        m, mn = timeit(lambda: gb._call("fhe_keyswitch", gb._ptr(ko), gb._ptr(d), gb._ptr(ksk), nq), flush=flush)
-        rec("keyswitch", m, mn, alg, nq=nq, beta=beta)
-        ext = torch.empty(beta, nq + K, n, dtype=torch.int64, device="cuda")
-        acc = torch.empty(2, nq + K, n, dtype=torch.int64, device="cuda")
-        m, mn = timeit(lambda: gb._call("fhe_modup", gb._ptr(ext), gb._ptr(d), nq), flush=flush)
-        rec("ks.modup", m, mn, (nq + beta * (nq + K)) * limb, nq=nq)
-        m, mn = timeit(lambda: gb._call("fhe_ks_inner", gb._ptr(acc), gb._ptr(ext), gb._ptr(d), gb._ptr(ksk), nq), flush=flush)
-        rec("ks.inner", m, mn, (3 * beta * (nq + K) + 2 * (nq + K)) * limb, nq=nq)
-        m, mn = timeit(lambda: gb._call("fhe_moddown", gb._ptr(ko), gb._ptr(acc), nq, 2), flush=flush)
-        rec("ks.moddown", m, mn, (2 * (nq + K) + 2 * nq) * limb, nq=nq)
+        for B in (1, 4, 8):
+            d = rnd(B, nq, n); ko = torch.empty(2, B, nq, n, dtype=torch.int64, device="cuda")
+            alg = (2 * beta * (nq + K) + 3 * nq * B) * limb
+            m_, mn = timeit(lambda: gb._call("fhe_keyswitch", gb._ptr(ko), gb._ptr(d), gb._ptr(ksk), nq, B), flush=flush)
+            rec("keyswitch", m_, mn, alg, nq=nq, beta=beta, batch=B, us_per_ct=round(m_ / B, 1))
+            ext = torch.empty(B, beta, nq + K, n, dtype=torch.int64, device="cuda")
+            acc = torch.empty(2, B, nq + K, n, dtype=torch.int64, device="cuda")
+            m_, mn = timeit(lambda: gb._call("fhe_modup", gb._ptr(ext), gb._ptr(d), nq, B), flush=flush)
+            rec("ks.modup", m_, mn, B * (nq + beta * (nq + K)) * limb, nq=nq, batch=B)
+            m_, mn = timeit(lambda: gb._call("fhe_ks_inner", gb._ptr(acc), gb._ptr(ext), gb._ptr(d), gb._ptr(ksk), nq, B), flush=flush)
+            rec("ks.inner", m_, mn, (2 * beta * (nq + K) + B * (beta * (nq + K) + 2 * (nq + K))) * limb, nq=nq, batch=B)
+            m_, mn = timeit(lambda: gb._call("fhe_moddown", gb._ptr(ko), gb._ptr(acc), nq, 2 * B), flush=flush)
+            rec("ks.moddown", m_, mn, B * (2 * (nq + K) + 2 * nq) * limb, nq=nq, batch=B)
     Path("gpurun_out").mkdir(exist_ok=True)
     json.dump(out, open("gpurun_out/microbench.json", "w"), indent=1)
 
