@@ -46,7 +46,7 @@ def build_emu(force: bool = False) -> Path:
     deps = _deps() + [emu_dir / "emu_runtime.cpp"]
     if not force and not _stale(out, deps):
         return out
-    cmd = ["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-DFHE_EMU", "-pthread", f"-I{CSRC}",
+    cmd = ["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-DFHE_EMU", "-ffp-contract=off", "-pthread", f"-I{CSRC}",
            "-x", "c++"] + [str(CSRC / s) for s in SOURCES] + [str(emu_dir / "emu_runtime.cpp"), "-o", str(out)]
     subprocess.check_call(cmd)
     return out

@@ -26,11 +26,11 @@ inline u64 h_pow(u64 b, u64 e, u64 q) {
     return r;
 }
 inline u64 h_inv(u64 a, u64 q) { return h_pow(a, q - 2, q); }
-inline ShoupConst h_shoup(u64 w, u64 q) {
-    ShoupConst s; s.w = w; s.ws = (u64)(((u128)w << 64) / q); return s;
+inline ConstF h_shoup(u64 w, u64 q) {
+    ConstF s; s.w = (double)w; s.wq = (double)((long double)w / (long double)q); return s;
 }
 inline Modulus h_modulus(u64 q) {
-    Modulus m; m.q = q;
+    Modulus m; m.q = q; m.qd = (double)q; m.qinv = (double)(1.0L / (long double)q);
     u128 hi = ((u128)1 << 64) / q, rem = ((u128)1 << 64) % q;
     u128 lo = (rem << 64) / q;
     u128 mu = (hi << 64) + lo;
@@ -60,11 +60,11 @@ struct fhe_ctx {
     // per active-limb-count tables, index nq (1..n_q)
     std::vector<BConvTable*> modup_tables;    // device array of beta(nq) tables
     std::vector<int> modup_beta;
-    std::vector<ShoupConst*> modup_scale;     // [nq][2] iNTT final constants incl. (Q_j/q_i)^-1
+    std::vector<ConstF*> modup_scale;     // [nq][2] iNTT final constants incl. (Q_j/q_i)^-1
     std::vector<BConvTable*> moddown_table;   // one table
-    std::vector<ShoupConst*> rescale_c;       // [nq-1] q_{nq-1}^-1 mod q_i
-    ShoupConst* moddown_scale = nullptr;      // [n_p][2]
-    ShoupConst* pinv = nullptr;               // [n_q]  P^-1 mod q_i
+    std::vector<ConstF*> rescale_c;       // [nq-1] q_{nq-1}^-1 mod q_i
+    ConstF* moddown_scale = nullptr;      // [n_p][2]
+    ConstF* pinv = nullptr;               // [n_q]  P^-1 mod q_i
     u64 q0inv_mod_q1 = 0;
     std::vector<void*> owned;
     // scratch arena
@@ -137,9 +137,9 @@ void build_level_tables(fhe_ctx* c) {
     std::vector<u64> ninv(c->tot), w1ninv(c->tot);
     {
         // psi^-bitrev(1) = psi^-(N/2)
-        std::vector<ShoupConst> fin(2 * (size_t)c->tot);
-        cudaMemcpy(fin.data(), c->T.inv_final, sizeof(ShoupConst) * fin.size(), cudaMemcpyDeviceToHost);
-        for (int l = 0; l < c->tot; ++l) { ninv[l] = fin[2 * l].w; w1ninv[l] = fin[2 * l + 1].w; }
+        std::vector<ConstF> fin(2 * (size_t)c->tot);
+        cudaMemcpy(fin.data(), c->T.inv_final, sizeof(ConstF) * fin.size(), cudaMemcpyDeviceToHost);
+        for (int l = 0; l < c->tot; ++l) { ninv[l] = (u64)fin[2 * l].w; w1ninv[l] = (u64)fin[2 * l + 1].w; }
     }
     std::vector<int> pids(K);
     for (int k = 0; k < K; ++k) pids[k] = n_q + k;
@@ -148,7 +148,7 @@ void build_level_tables(fhe_ctx* c) {
         const int beta = (nq + alpha - 1) / alpha, ne = nq + K;
         c->modup_beta[nq] = beta;
         std::vector<BConvTable> tabs(beta);
-        std::vector<ShoupConst> scale(2 * (size_t)nq);
+        std::vector<ConstF> scale(2 * (size_t)nq);
         for (int j = 0; j < beta; ++j) {
             BConvTable& tb = tabs[j];
             std::memset(&tb, 0, sizeof(tb));
@@ -169,8 +169,7 @@ void build_level_tables(fhe_ctx* c) {
                 const int id = c->id_of(t, nq);
                 const u64 m = c->q[id];
                 tb.dst_mod[nt] = id; tb.dst_slot[nt] = t;
-                for (int k = 0; k < tb.ns; ++k) tb.f[k][nt] = prod_except(c, src, k, m);
-                tb.qmod[nt] = prod_except(c, src, -1, m);
+                for (int k = 0; k < tb.ns; ++k) tb.f[nt][k] = h_shoup(prod_except(c, src, k, m), m);
                 ++nt;
             }
             tb.nt = nt;
@@ -188,14 +187,13 @@ void build_level_tables(fhe_ctx* c) {
             for (int i = 0; i < nq; ++i) {
                 const u64 m = c->q[i];
                 tb.dst_mod[i] = i; tb.dst_slot[i] = i;
-                for (int k = 0; k < K; ++k) tb.f[k][i] = prod_except(c, pids, k, m);
-                tb.qmod[i] = prod_except(c, pids, -1, m);
+                for (int k = 0; k < K; ++k) tb.f[i][k] = h_shoup(prod_except(c, pids, k, m), m);
             }
             c->moddown_table[nq] = to_device(td);
             c->owned.push_back(c->moddown_table[nq]);
         }
         if (nq >= 2) {
-            std::vector<ShoupConst> rc(nq - 1);
+            std::vector<ConstF> rc(nq - 1);
             const u64 ql = c->q[nq - 1];
             for (int i = 0; i < nq - 1; ++i) rc[i] = h_shoup(h_inv(ql % c->q[i], c->q[i]), c->q[i]);
             c->rescale_c[nq] = to_device(rc);
@@ -204,7 +202,7 @@ void build_level_tables(fhe_ctx* c) {
     }
     if (K > 0) {
         // iNTT final constants for the special limbs, replicated for up to 4 polys
-        std::vector<ShoupConst> ms(2 * (size_t)K);
+        std::vector<ConstF> ms(2 * (size_t)K);
         for (int k = 0; k < K; ++k) {
             const u64 pk = c->q[pids[k]];
             const u64 inv = h_inv(prod_except(c, pids, k, pk), pk);
@@ -213,7 +211,7 @@ void build_level_tables(fhe_ctx* c) {
         }
         c->moddown_scale = to_device(ms);
         c->owned.push_back(c->moddown_scale);
-        std::vector<ShoupConst> pv(n_q);
+        std::vector<ConstF> pv(n_q);
         for (int i = 0; i < n_q; ++i) pv[i] = h_shoup(h_inv(prod_except(c, pids, -1, c->q[i]), c->q[i]), c->q[i]);
         c->pinv = to_device(pv);
         c->owned.push_back(c->pinv);
@@ -260,10 +258,11 @@ int fhe_ctx_create(fhe_ctx** out, int log_n, int n_q, int n_p, int alpha, const 
     const int n = c->n, tot = c->tot;
     c->q.assign(moduli, moduli + tot);
     std::vector<Modulus> mods(tot);
-    std::vector<ShoupConst> twf((size_t)tot * n), twi((size_t)tot * n), fin(2 * (size_t)tot);
+    std::vector<double> twf((size_t)tot * n), twi((size_t)tot * n);
+    std::vector<ConstF> fin(2 * (size_t)tot);
     for (int l = 0; l < tot; ++l) {
         const u64 q = (u64)moduli[l];
-        if (q >= (1ull << 61) || (q - 1) % (2ull * n) != 0) { delete c; return fail("fhe_ctx_create: modulus must be < 2^61 and = 1 mod 2N"); }
+        if (q >= (1ull << 45) || (q - 1) % (2ull * n) != 0) { delete c; return fail("fhe_ctx_create: modulus must be < 2^45 and = 1 mod 2N"); }
         if (h_pow(psi[l], n, q) != q - 1) { delete c; return fail("fhe_ctx_create: psi is not a primitive 2N-th root"); }
         mods[l] = h_modulus(q);
         const u64 ipsi = h_inv(psi[l], q);
@@ -272,17 +271,17 @@ int fhe_ctx_create(fhe_ctx** out, int log_n, int n_q, int n_p, int alpha, const 
         for (int k = 1; k < n; ++k) { pw[k] = h_mul(pw[k - 1], psi[l], q); ipw[k] = h_mul(ipw[k - 1], ipsi, q); }
         for (int k = 0; k < n; ++k) {
             const u32 r = h_brev((u32)k, log_n);
-            twf[(size_t)l * n + k] = h_shoup(pw[r], q);
-            twi[(size_t)l * n + k] = h_shoup(ipw[r], q);
+            twf[(size_t)l * n + k] = (double)pw[r];
+            twi[(size_t)l * n + k] = (double)ipw[r];
         }
         const u64 ninv = h_inv((u64)n % q, q);
         fin[2 * (size_t)l] = h_shoup(ninv, q);
-        fin[2 * (size_t)l + 1] = h_shoup(h_mul(ninv, twi[(size_t)l * n + 1].w, q), q);
+        fin[2 * (size_t)l + 1] = h_shoup(h_mul(ninv, ipw[h_brev(1u, log_n)], q), q);
     }
     Modulus* d_mod = to_device(mods);
-    ShoupConst* d_twf = to_device(twf);
-    ShoupConst* d_twi = to_device(twi);
-    ShoupConst* d_fin = to_device(fin);
+    double* d_twf = to_device(twf);
+    double* d_twi = to_device(twi);
+    ConstF* d_fin = to_device(fin);
     if (!d_mod || !d_twf || !d_twi || !d_fin) { delete c; return fail("fhe_ctx_create: device allocation failed"); }
     c->owned = {d_mod, d_twf, d_twi, d_fin};
     c->T.mod = d_mod; c->T.tw_fwd = d_twf; c->T.tw_inv = d_twi; c->T.inv_final = d_fin;

@@ -37,7 +37,7 @@ __global__ void __launch_bounds__(256) k_binary(DevTables T, RowMap map, int bat
     u64 r;
     if (OP == 0) r = add_mod(x, y, M.q);
     else if (OP == 1) r = sub_mod(x, y, M.q);
-    else r = mul_mod(x, y, M);
+    else r = f_to_u64(canon(mulmod_var(u64_to_f(x), u64_to_f(y), M.qd, M.qinv), M.qd));
     out[poly * so.poly + bt * so.batch + lo] = r;
 }
 
@@ -54,12 +54,12 @@ __global__ void __launch_bounds__(256) k_tensor(DevTables T, int nq, u64* d, con
     const Modulus M = T.mod[j];
     const size_t n = (size_t)1 << T.log_n;
     const size_t o = (size_t)blockIdx.y * n + blockIdx.x * 256 + threadIdx.x;
-    const u64 a0 = a[o], a1 = a[o + ps], b0 = b[o], b1 = b[o + ps];
-    d[o] = mul_mod(a0, b0, M);
-    u128t acc = mul_wide(a0, b1);
-    acc_wide(acc, a1, b0);
-    d[o + ps] = barrett_reduce(acc, M);
-    d[o + 2 * ps] = mul_mod(a1, b1, M);
+    const double q = M.qd, qi = M.qinv;
+    const double a0 = u64_to_f(a[o]), a1 = u64_to_f(a[o + ps]), b0 = u64_to_f(b[o]), b1 = u64_to_f(b[o + ps]);
+    d[o] = f_to_u64(canon(mulmod_var(a0, b0, q, qi), q));
+    const double m = d_add(mulmod_var(a0, b1, q, qi), mulmod_var(a1, b0, q, qi));      // (-1.1q, 1.1q)
+    d[o + ps] = f_to_u64(reduce_canon(m, q, qi));
+    d[o + 2 * ps] = f_to_u64(canon(mulmod_var(a1, b1, q, qi), q));
 }
 
 // out = a * (first half of spectrum ? c.a[j] : c.b[j])   (complex constant, see encoding.py)
@@ -73,7 +73,7 @@ __global__ void __launch_bounds__(256) k_const(DevTables T, RowMap map, u64* out
     const int j = row % map.rows_per_poly;
     const u64 k = (idx >> (map.log_n - 1)) ? c.b[j] : c.a[j];
     const size_t o = ((size_t)row << map.log_n) + idx;
-    out[o] = ADD ? add_mod(a[o], k, M.q) : mul_mod(a[o], k, M);
+    out[o] = ADD ? add_mod(a[o], k, M.q) : f_to_u64(canon(mulmod_var(u64_to_f(a[o]), u64_to_f(k), M.qd, M.qinv), M.qd));
 }
 
 // NTT-domain automorphism X -> X^g on bit-reversed spectra: out[p] = in[perm(p)]
@@ -126,51 +126,59 @@ __global__ void __launch_bounds__(256) k_crt_centered(DevTables T, double* out, 
 
 // ---------------------------------------------------------------- base conversion
 // One table per source basis.  Output value for target t:
-//     sum_k y_k * f[k][t]  -  #{k : y_k > q_k/2} * qmod[t]      (mod m_t)
+//     sum_k yc_k * f[k][t]   (mod m_t),     yc_k = centred representative of y_k mod q_k
 // where y_k (already multiplied by (Q/q_k)^-1 mod q_k by the preceding iNTT) is the k-th
-// source row.  Centred digits make the conversion error zero-mean (see oracle/refmod.cpp).
+// source row.  Using the centred digit (-q_k/2, q_k/2] is the same as subtracting
+// #{k : y_k > q_k/2} * Q, and makes the conversion error zero-mean (see oracle/refmod.cpp).
 struct BConvTable {
     int ns, nt;
     int src_mod[FHE_MAX_SRC];
-    int src_slot[FHE_MAX_SRC];      // row slot of source k inside the source group
+    int src_slot[FHE_MAX_SRC];      // row slot of source k inside the source block
     int dst_mod[FHE_MAX_DST];
     int dst_slot[FHE_MAX_DST];      // row slot of target t inside the destination group
-    u64 f[FHE_MAX_SRC][FHE_MAX_DST];
-    u64 qmod[FHE_MAX_DST];
+    ConstF f[FHE_MAX_DST][FHE_MAX_SRC];   // (Q/q_k) mod m_t prepared for mulmod_const
 };
 
 // grid: (N/256, groups).  group g uses table g % n_tables and the source block g / n_tables
 // (ModUp: groups = batch x digits, all digits of one ciphertext read the same source block;
-//  ModDown: one table, groups = polys).  NS_MAX bounds every table's ns.
+//  ModDown: one table, groups = polys).  NS_MAX bounds every table's ns.  The constants of the
+// table are staged in shared memory once per CTA.
 template <int NS_MAX>
 __global__ void __launch_bounds__(256) k_bconv(DevTables T, const BConvTable* tables, int n_tables,
                                                u64* dst, long long dst_group_stride,
                                                const u64* src, long long src_block_stride) {
+    FHE_SHARED ConstF sf[FHE_MAX_DST * NS_MAX];
+    FHE_SHARED double sq[FHE_MAX_DST], sqi[FHE_MAX_DST];
+    FHE_SHARED int sslot[FHE_MAX_DST];
     const int g = blockIdx.y;
     const BConvTable& tb = tables[g % n_tables];
+    const int ns = tb.ns, nt = tb.nt;
+    for (int i = threadIdx.x; i < nt * NS_MAX; i += 256) sf[i] = tb.f[i / NS_MAX][i % NS_MAX];
+    for (int t = threadIdx.x; t < nt; t += 256) {
+        const Modulus M = T.mod[tb.dst_mod[t]];
+        sq[t] = M.qd; sqi[t] = M.qinv; sslot[t] = tb.dst_slot[t];
+    }
     const u32 idx = blockIdx.x * 256 + threadIdx.x;
     const int log_n = T.log_n;
     const u64* s = src + (size_t)(g / n_tables) * src_block_stride + idx;
     u64* d = dst + (size_t)g * dst_group_stride + idx;
-    u64 y[NS_MAX];
-    u64 neg = 0;
-    const int ns = tb.ns;
+    double y[NS_MAX];
 #pragma unroll
     for (int k = 0; k < NS_MAX; ++k) {
         if (k < ns) {
-            y[k] = s[(size_t)tb.src_slot[k] << log_n];
-            neg += y[k] > (T.mod[tb.src_mod[k]].q >> 1);
-        } else y[k] = 0;
+            const u64 v = s[(size_t)tb.src_slot[k] << log_n];
+            const u64 qk = T.mod[tb.src_mod[k]].q;
+            y[k] = v > (qk >> 1) ? d_add(u64_to_f(v), -u64_to_f(qk)) : u64_to_f(v);
+        } else y[k] = 0.0;
     }
-    for (int t = 0; t < tb.nt; ++t) {
-        const Modulus M = T.mod[tb.dst_mod[t]];
-        u128t acc; acc.lo = 0; acc.hi = 0;
+    __syncthreads();
+    for (int t = 0; t < nt; ++t) {
+        const double q = sq[t];
+        double acc = 0.0;
 #pragma unroll
         for (int k = 0; k < NS_MAX; ++k)
-            if (k < ns) acc_wide(acc, y[k], tb.f[k][t]);
-        u64 r = barrett_reduce(acc, M);
-        r = sub_mod(r, mul_mod(neg, tb.qmod[t], M), M.q);
-        d[(size_t)tb.dst_slot[t] << log_n] = r;
+            if (k < ns) acc = d_add(acc, mulmod_const(y[k], sf[t * NS_MAX + k], q));
+        d[(size_t)sslot[t] << log_n] = f_to_u64(reduce_canon(acc, q, sqi[t]));
     }
 }
 
@@ -186,57 +194,56 @@ __global__ void __launch_bounds__(256) k_ks_inner(DevTables T, int nq, int alpha
     const int ne = nq + T.n_p;
     const int id = t < nq ? t : T.n_q + (t - nq);
     const Modulus M = T.mod[id];
+    const double q = M.qd, qi = M.qinv;
     const int log_n = T.log_n;
     const u32 idx = blockIdx.x * 256 + threadIdx.x;
     const size_t tot = (size_t)(T.n_q + T.n_p);
-    u64 k0[FHE_MAX_BETA], k1[FHE_MAX_BETA];
+    double k0[FHE_MAX_BETA], k1[FHE_MAX_BETA];
 #pragma unroll
     for (int j = 0; j < FHE_MAX_BETA; ++j) {
         if (j < beta) {
             const u64* kp = ksk + ((((size_t)j * 2) * tot + id) << log_n) + idx;
-            k0[j] = kp[0];
-            k1[j] = kp[tot << log_n];
-        } else { k0[j] = 0; k1[j] = 0; }
+            k0[j] = u64_to_f(kp[0]);
+            k1[j] = u64_to_f(kp[tot << log_n]);
+        } else { k0[j] = 0.0; k1[j] = 0.0; }
     }
     const int own = t < nq ? t / alpha : -1;
     for (int b = 0; b < batch; ++b) {
-        u128t a0; a0.lo = 0; a0.hi = 0;
-        u128t a1 = a0;
+        double a0 = 0.0, a1 = 0.0;
 #pragma unroll
         for (int j = 0; j < FHE_MAX_BETA; ++j) {
             if (j < beta) {
-                const u64 e = j == own ? d[(((size_t)b * nq + t) << log_n) + idx]
-                                       : ext[((((size_t)b * beta + j) * ne + t) << log_n) + idx];
-                acc_wide(a0, e, k0[j]);
-                acc_wide(a1, e, k1[j]);
+                const double e = u64_to_f(j == own ? d[(((size_t)b * nq + t) << log_n) + idx]
+                                                   : ext[((((size_t)b * beta + j) * ne + t) << log_n) + idx]);
+                a0 = d_add(a0, mulmod_var(e, k0[j], q, qi));
+                a1 = d_add(a1, mulmod_var(e, k1[j], q, qi));
             }
         }
-        acc[(((size_t)b * ne + t) << log_n) + idx] = barrett_reduce(a0, M);
-        acc[((((size_t)batch + b) * ne + t) << log_n) + idx] = barrett_reduce(a1, M);
+        acc[(((size_t)b * ne + t) << log_n) + idx] = f_to_u64(reduce_canon(a0, q, qi));
+        acc[((((size_t)batch + b) * ne + t) << log_n) + idx] = f_to_u64(reduce_canon(a1, q, qi));
     }
 }
 
 // ---------------------------------------------------------------- fused NTT functors
-// rescale: load the centred remainder of the dropped limb, reduced into the row's modulus
+// rescale: load the centred remainder of the dropped limb.  |r| <= q_last/2 < 2^44 is a valid
+// lazy NTT input for any row modulus, so no reduction is needed here.
 struct LoadCentered {
     const u64* last;            // [npoly][N] coefficient-domain rows of the dropped limb
     u64 q_last;
-    FHE_D u64 operator()(const RowMap& map, int row, u32 idx, int, const Modulus& M) const {
+    FHE_D double operator()(const RowMap& map, int row, u32 idx, int, const Modulus&) const {
         const u64 v = last[((size_t)(row / map.rows_per_poly) << map.log_n) + idx];
-        if (v > (q_last >> 1)) return neg_mod(reduce_u64(q_last - v, M), M.q);
-        return reduce_u64(v, M);
+        return v > (q_last >> 1) ? d_add(u64_to_f(v), -u64_to_f(q_last)) : u64_to_f(v);
     }
 };
 // rescale / ModDown epilogue: out = (in - ntt_value) * c[j]
 struct StoreSubMul {
     u64* out; long long out_poly_stride;
     const u64* in; long long in_poly_stride;
-    const ShoupConst* c;        // per limb slot j
-    FHE_D void operator()(const RowMap& map, int row, u32 idx, u64 v, int, const Modulus& M) const {
+    const ConstF* c;            // per limb slot j
+    FHE_D void operator()(const RowMap& map, int row, u32 idx, double v, int, const Modulus& M) const {
         const int poly = row / map.rows_per_poly, j = row % map.rows_per_poly;
         const size_t lo = ((size_t)j << map.log_n) + idx;
-        const u64 x = in[(size_t)poly * in_poly_stride + lo];
-        const ShoupConst k = c[j];
-        out[(size_t)poly * out_poly_stride + lo] = mul_shoup(sub_mod(x, v, M.q), k.w, k.ws, M.q);
+        const double x = u64_to_f(in[(size_t)poly * in_poly_stride + lo]);
+        out[(size_t)poly * out_poly_stride + lo] = f_to_u64(canon(mulmod_const(d_add(x, -v), c[j], M.qd), M.qd));
     }
 };

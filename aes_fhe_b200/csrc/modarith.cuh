@@ -1,65 +1,93 @@
-// modarith.cuh -- 64-bit modular arithmetic for moduli q < 2^62.
+// modarith.cuh -- modular arithmetic for moduli q < 2^45, carried out on the FP64 pipe.
 //
-// * Shoup multiplication by a constant w with companion w' = floor(w 2^64 / q): used for
-//   every NTT twiddle and every per-limb constant (1 mul.hi + 2 mul.lo).
-// * Harvey lazy butterflies keep values in [0,4q) (forward) / [0,2q) (inverse).
-// * Barrett reduction of a 128-bit value with mu = floor(2^128/q) for variable x variable
-//   products and for the 128-bit accumulators of the base-conversion / key inner products.
+// Why FP64: measured on B200 (tools/ubench/pipes.cu) the SM retires 63 DFMA/DMUL/DADD per
+// clock but only 21 IMAD.WIDE (32x32->64) and 6.8 mul.hi.u64, so a 64-bit Shoup/Barrett
+// product costs about three times as many issue cycles as the same product done with
+// error-free double arithmetic.  All residues are integers below 2^45, every intermediate
+// value stays an exactly representable integer (|x| < 2^50), and the results are the same
+// canonical residues an integer implementation produces -- bit-exact with oracle/refmod.cpp.
+//
+//   mulmod by a constant w (Shoup style, wq = RN(w/q) precomputed):
+//       qe = rint(x * wq)                  (one FMA against the 1.5*2^52 magic constant)
+//       p  = RN(x * w),  plo = fma(x, w, -p)           (exact product as p + plo)
+//       r  = fma(-qe, q, p) + plo          (both steps exact)      |r| <= q (1/2 + |x| 2^-53)
+//   six FP64 operations; a Cooley-Tukey butterfly is eight.  Values are kept signed and lazy:
+//   a forward transform never needs a correction (|x| grows by < 0.63 q per stage).
+//
+// A few cold paths (reducing 63-bit encoder coefficients, CRT decode) still use integer Barrett.
 #pragma once
 #include "compat.h"
 
 struct Modulus {
     u64 q;
-    u64 mu_hi, mu_lo;     // floor(2^128 / q)
+    u64 mu_hi, mu_lo;     // floor(2^128 / q)      (integer Barrett, cold paths)
+    double qd, qinv;      // (double) q, RN(1/q)
 };
 
-struct ShoupConst {
-    u64 w, ws;            // w in [0,q),  ws = floor(w * 2^64 / q)
+struct ConstF {           // a constant c in [0,q) prepared for mulmod_const
+    double w, wq;         // (double) c, RN(c / q)
 };
 
+#define FHE_MAGIC 6755399441055744.0      /* 1.5 * 2^52 */
+#define FHE_TWO52 4503599627370496.0      /* 2^52 */
+
+#ifndef FHE_EMU
+FHE_D double d_fma(double a, double b, double c) { return __fma_rn(a, b, c); }
+FHE_D double d_mul(double a, double b) { return __dmul_rn(a, b); }
+FHE_D double d_add(double a, double b) { return __dadd_rn(a, b); }
+FHE_D double bits_to_f(u64 b) { return __longlong_as_double((long long)b); }
+FHE_D u64 f_to_bits(double d) { return (u64)__double_as_longlong(d); }
+#else
+#include <cmath>
+#include <cstring>
+inline double d_fma(double a, double b, double c) { return std::fma(a, b, c); }
+inline double d_mul(double a, double b) { volatile double r = a * b; return r; }
+inline double d_add(double a, double b) { volatile double r = a + b; return r; }
+inline double bits_to_f(u64 b) { double d; std::memcpy(&d, &b, 8); return d; }
+inline u64 f_to_bits(double d) { u64 b; std::memcpy(&b, &d, 8); return b; }
+#endif
+
+// exact u64 (< 2^52) <-> double without conversion instructions
+FHE_D double u64_to_f(u64 x) { return d_add(bits_to_f(0x4330000000000000ull | x), -FHE_TWO52); }
+FHE_D u64 f_to_u64(double r) { return f_to_bits(d_add(r, FHE_TWO52)) & 0x000FFFFFFFFFFFFFull; }
+
+// rint(x * c) for |x * c| < 2^51
+FHE_D double round_quot(double x, double c) { return d_add(d_fma(x, c, FHE_MAGIC), -FHE_MAGIC); }
+
+// x * w mod q, signed result with |r| <= q (1/2 + |x| 2^-53); needs |x| < 2^50
+FHE_D double mulmod_const(double x, const ConstF w, double q) {
+    const double qe = round_quot(x, w.wq);
+    const double p = d_mul(x, w.w);
+    const double plo = d_fma(x, w.w, -p);
+    return d_add(d_fma(-qe, q, p), plo);
+}
+// a * b mod q for |a|, |b| < 2^47 (so that |a b| / q < 2^51); |r| <= 0.51 q
+FHE_D double mulmod_var(double a, double b, double q, double qinv) {
+    const double p = d_mul(a, b);
+    const double plo = d_fma(a, b, -p);
+    const double qe = round_quot(p, qinv);
+    return d_add(d_fma(-qe, q, p), plo);
+}
+// symmetric reduction of a lazy value, |x| < 2^51  ->  |r| <= q/2 (+1)
+FHE_D double reduce_sym(double x, double q, double qinv) { return d_fma(-round_quot(x, qinv), q, x); }
+// (-q, q) -> [0, q)
+FHE_D double canon(double r, double q) { return r < 0.0 ? d_add(r, q) : r; }
+FHE_D double reduce_canon(double x, double q, double qinv) { return canon(reduce_sym(x, q, qinv), q); }
+
+// ---- integer helpers (canonical add/sub are pure ALU work; Barrett only on cold paths)
 FHE_HD u64 add_mod(u64 a, u64 b, u64 q) { u64 s = a + b; return s >= q ? s - q : s; }
 FHE_HD u64 sub_mod(u64 a, u64 b, u64 q) { return a >= b ? a - b : a + q - b; }
 FHE_HD u64 neg_mod(u64 a, u64 q) { return a ? q - a : 0; }
 
-// x*w mod q in [0,2q) for ANY 64-bit x.
-FHE_D u64 mul_shoup_lazy(u64 x, u64 w, u64 ws, u64 q) {
-    u64 hi = umulhi64(x, ws);
-    return x * w - hi * q;
-}
-// canonical result
-FHE_D u64 mul_shoup(u64 x, u64 w, u64 ws, u64 q) {
-    u64 r = mul_shoup_lazy(x, w, ws, q);
-    return r >= q ? r - q : r;
-}
-
-// 128-bit helpers -------------------------------------------------------------------
 struct u128t { u64 lo, hi; };
-
-FHE_D u128t mul_wide(u64 a, u64 b) {
-    u128t r; r.lo = a * b; r.hi = umulhi64(a, b); return r;
-}
-FHE_D void acc_wide(u128t& acc, u64 a, u64 b) {
-    u64 lo = a * b, hi = umulhi64(a, b);
-    acc.lo += lo;
-    acc.hi += hi + (acc.lo < lo ? 1ull : 0ull);
-}
-// z mod q for any 128-bit z with z < q * 2^64  (always true for our accumulators: <= 16
-// products of a 62-bit by a 62-bit value is < 2^128 but we additionally keep z.hi < q by
-// construction: see callers).  Result canonical.
+FHE_D u128t mul_wide(u64 a, u64 b) { u128t r; r.lo = a * b; r.hi = umulhi64(a, b); return r; }
 FHE_D u64 barrett_reduce(u128t z, const Modulus& m) {
-    // t ~= floor(z * mu / 2^128), under-estimated by at most 4
     u64 t = umulhi64(z.hi, m.mu_lo) + umulhi64(z.lo, m.mu_hi) + z.hi * m.mu_hi;
     u64 r = z.lo - t * m.q;
-    // r < 5q < 2^64
     if (r >= 2 * m.q) r -= 2 * m.q;
     if (r >= 2 * m.q) r -= 2 * m.q;
     if (r >= m.q) r -= m.q;
     return r;
 }
 FHE_D u64 mul_mod(u64 a, u64 b, const Modulus& m) { return barrett_reduce(mul_wide(a, b), m); }
-
-// value v < 2^64 reduced mod q (q may be much smaller than v)
-FHE_D u64 reduce_u64(u64 v, const Modulus& m) {
-    u128t z; z.lo = v; z.hi = 0;
-    return barrett_reduce(z, m);
-}
+FHE_D u64 reduce_u64(u64 v, const Modulus& m) { u128t z; z.lo = v; z.hi = 0; return barrett_reduce(z, m); }

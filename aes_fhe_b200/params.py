@@ -27,8 +27,10 @@ from typing import List, Tuple
 
 import numpy as np
 
-BASE_BITS = 60
-SPECIAL_BITS = 60
+# every modulus is < 2^45: the kernels do their modular arithmetic exactly on the FP64 pipe
+# (csrc/modarith.cuh), which needs all lazy intermediates below 2^50
+BASE_BITS = 45
+SPECIAL_BITS = 45
 DEFAULT_SCALE_BITS = 40
 DEFAULT_DNUM = 4
 

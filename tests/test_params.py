@@ -11,7 +11,7 @@ def test_chain_is_ntt_friendly_and_distinct(log_n, lvl):
     P = make_params(log_n, lvl)
     assert len(set(P.moduli)) == len(P.moduli)
     for q, psi in zip(P.moduli, P.psi):
-        assert is_prime(q) and q % (2 * P.n) == 1 and q < (1 << 61)
+        assert is_prime(q) and q % (2 * P.n) == 1 and q < (1 << 45)
         assert pow(psi, P.n, q) == q - 1            # primitive 2N-th root
     assert P.n_q == lvl + 1 and P.n_p >= 1
 

@@ -44,7 +44,7 @@ def main():
     rng = np.random.default_rng(0)
 
     def rnd(*shape):
-        return torch.randint(0, 2 ** 39, shape, dtype=torch.int64, device="cuda")
+        return torch.randint(0, 2 ** 39, shape, dtype=torch.int64, device="cuda")   # valid residues of every modulus
 
     out = []
 
@@ -55,12 +55,13 @@ def main():
         print(json.dumps(r), flush=True)
 
     # copy roofline reference (torch's own copy kernel) on the same buffers
-    a = rnd(8, 37, n); b = torch.empty_like(a)
+    tot = P.n_q + K
+    a = rnd(8, tot, n); b = torch.empty_like(a)
     m, mn = timeit(lambda: b.copy_(a), flush=flush)
     rec("torch_copy_ref", m, mn, 2 * a.numel() * 8)
 
-    for rows in (37, 2 * 37, 8 * 37):
-        x = rnd(rows // 37, 37, n)
+    for rows in (tot, 2 * tot, 8 * tot, 32 * tot):
+        x = rnd(rows // tot, tot, n)
         m, mn = timeit(lambda: gb._call("fhe_ntt_fwd", gb._ptr(x), x.shape[0], 31, K), flush=flush)
         rec("ntt_fwd", m, mn, 2 * rows * limb, rows=rows)
         m, mn = timeit(lambda: gb._call("fhe_ntt_inv", gb._ptr(x), x.shape[0], 31, K), flush=flush)
@@ -82,7 +83,7 @@ def main():
         m, mn = timeit(lambda: gb._call("fhe_automorphism", gb._ptr(o), gb._ptr(x), C.c_uint64(5), 2 * nq), flush=flush)
         rec("automorphism", m, mn, 4 * nq * limb, nq=nq)
         # key switch, batch of B ciphertexts sharing one pass over the key
-        ksk = rnd(P.dnum, 2, 37, n)
+        ksk = rnd(P.dnum, 2, tot, n)
         beta = P.digits_at(nq)
         for B in (1, 4, 8):
             d = rnd(B, nq, n); ko = torch.empty(2, B, nq, n, dtype=torch.int64, device="cuda")
