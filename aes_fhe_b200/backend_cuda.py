@@ -252,6 +252,65 @@ class CudaBackend:
         self._call("fhe_keyswitch", self._ptr(out), self._ptr(d), self._ptr(ksk), nq, bt)
         return out
 
+    # ---- fused LUT evaluation pieces
+    def prepare_lincomb(self, const_res, c0_res, nq: int):
+        """const_res[m][t] = (c_first[nq], c_second[nq]) residues; c0_res[m] likewise or None.
+        Returns device tables for fhe_lincomb: (c, RN(c/q)) pairs as doubles."""
+        from fractions import Fraction
+        M, T = len(const_res), len(const_res[0])
+        q = self.params.moduli
+        tab = np.zeros((M, T, nq, 2, 2), dtype=np.float64)
+        for m in range(M):
+            for t in range(T):
+                for h in range(2):
+                    for j in range(nq):
+                        c = int(const_res[m][t][h][j])
+                        tab[m, t, j, h, 0] = float(c)
+                        tab[m, t, j, h, 1] = float(Fraction(c, q[j]))
+        dev = torch.from_numpy(tab).to(self.device)
+        c0 = None
+        if c0_res is not None:
+            a = np.zeros((M, nq, 2), dtype=np.uint64)
+            for m in range(M):
+                for h in range(2):
+                    a[m, :, h] = np.array([int(v) for v in c0_res[m][h]], dtype=np.uint64)
+            c0 = torch.from_numpy(a.view(np.int64)).to(self.device)
+        return dict(consts=dev, c0=c0, M=M, T=T, nq=nq)
+
+    def lincomb(self, inputs: List, prep) -> List:
+        M, T, nq = prep["M"], prep["T"], prep["nq"]
+        assert len(inputs) == T
+        inputs = [x.contiguous() for x in inputs]
+        bt = inputs[0].shape[1]
+        ptrs = (C.c_void_p * T)(*[x.data_ptr() for x in inputs])
+        nqs = (C.c_int * T)(*[x.shape[2] for x in inputs])
+        out = self._empty(M, 2, bt, nq, self.n)
+        self._call("fhe_lincomb", self._ptr(out), ptrs, nqs, self._ptr(prep["consts"]),
+                   self._ptr(prep["c0"]) if prep["c0"] is not None else None, M, T, nq, bt)
+        return [out[m] for m in range(M)]
+
+    def tensor_acc(self, acc, a_list: List, b_list: List, nq: int):
+        """acc [3,B,nq,N] (or None) += sum_g a_g (x) b_g ; a_g may carry more limbs than nq."""
+        G = len(a_list)
+        a_list = [x.contiguous() for x in a_list]
+        bt = b_list[0].shape[1]
+        bcat = torch.stack([x.contiguous() for x in b_list], dim=0) if G > 1 or not b_list[0].is_contiguous() \
+            else b_list[0].unsqueeze(0)
+        bcat = bcat.contiguous()
+        accumulate = 1
+        if acc is None:
+            acc = self._empty(3, bt, nq, self.n)
+            accumulate = 0
+        done = 0
+        while done < G:
+            g = min(16, G - done)
+            ptrs = (C.c_void_p * g)(*[x.data_ptr() for x in a_list[done:done + g]])
+            nqs = (C.c_int * g)(*[x.shape[2] for x in a_list[done:done + g]])
+            self._call("fhe_tensor_acc", self._ptr(acc), ptrs, nqs, self._ptr(bcat[done]), g, nq, bt, accumulate)
+            accumulate = 1
+            done += g
+        return acc
+
     def crt_centered(self, h, use: int) -> np.ndarray:
         """h [1, B, use, N] coefficient domain -> float64 [B, N]"""
         h = h.contiguous()

@@ -381,6 +381,44 @@ int fhe_mul_const(fhe_ctx* c, void* s, uint64_t* o, const uint64_t* a, const uin
 int fhe_add_const(fhe_ctx* c, void* s, uint64_t* o, const uint64_t* a, const uint64_t* c1, const uint64_t* c2,
                   int npoly, int nq, int np) { return constop(1, c, s, o, a, c1, c2, npoly, nq, np); }
 
+int fhe_lincomb(fhe_ctx* c, void* stream, uint64_t* out, const uint64_t* const* in, const int* in_nq,
+                const double* consts, const uint64_t* c0, int M, int T, int nq, int batch) {
+    if (bad_shape(c, nq, 0) || batch < 1 || M < 1 || T < 1 || T > FHE_LC_MAX_T || !in || !in_nq || !consts)
+        return fail("fhe_lincomb: bad shape");
+    LinCombIn li;
+    for (int t = 0; t < FHE_LC_MAX_T; ++t) {
+        const int nt = t < T ? in_nq[t] : nq;
+        if (t < T && nt < nq) return fail("fhe_lincomb: input has fewer limbs than the output");
+        li.ptr[t] = t < T ? (const u64*)in[t] : nullptr;
+        li.batch_stride[t] = (long long)nt * c->n;
+        li.poly_stride[t] = (long long)batch * nt * c->n;
+    }
+    dim3 grid(c->n / 256, 2 * batch * nq), block(256);
+    cudaStream_t s = (cudaStream_t)stream;
+    const ConstF* cf = (const ConstF*)consts;
+    if (T <= 4) launch(k_lincomb<4>, grid, block, s, c->T, nq, batch, M, T, li, cf, (const u64*)c0, (u64*)out);
+    else if (T <= 8) launch(k_lincomb<8>, grid, block, s, c->T, nq, batch, M, T, li, cf, (const u64*)c0, (u64*)out);
+    else launch(k_lincomb<16>, grid, block, s, c->T, nq, batch, M, T, li, cf, (const u64*)c0, (u64*)out);
+    return check("fhe_lincomb");
+}
+
+int fhe_tensor_acc(fhe_ctx* c, void* stream, uint64_t* acc, const uint64_t* const* a, const int* a_nq,
+                   const uint64_t* b, int G, int nq, int batch, int accumulate) {
+    if (bad_shape(c, nq, 0) || batch < 1 || G < 1 || G > FHE_LC_MAX_T || !a || !a_nq || !b)
+        return fail("fhe_tensor_acc: bad shape");
+    TensorAccIn ti;
+    for (int g = 0; g < FHE_LC_MAX_T; ++g) {
+        const int ng = g < G ? a_nq[g] : nq;
+        if (g < G && ng < nq) return fail("fhe_tensor_acc: operand has fewer limbs than the accumulator");
+        ti.a[g] = g < G ? (const u64*)a[g] : nullptr;
+        ti.a_batch_stride[g] = (long long)ng * c->n;
+        ti.a_poly_stride[g] = (long long)batch * ng * c->n;
+    }
+    launch(k_tensor_acc, dim3(c->n / 256, batch * nq), dim3(256), (cudaStream_t)stream, c->T, nq, batch, G, ti,
+           (const u64*)b, (u64*)acc, accumulate);
+    return check("fhe_tensor_acc");
+}
+
 int fhe_rescale(fhe_ctx* c, void* stream, uint64_t* out, const uint64_t* in, int npoly, int nq) {
     if (bad_shape(c, nq, 0) || nq < 2 || npoly < 1) return fail("fhe_rescale: bad shape");
     cudaStream_t s = (cudaStream_t)stream;

@@ -124,6 +124,88 @@ __global__ void __launch_bounds__(256) k_crt_centered(DevTables T, double* out, 
     out[idx] = neg ? -d : d;
 }
 
+// ---------------------------------------------------------------- LUT inner sums (K7)
+// out_m = sum_t c[m][t] (.) in_t  (+ c0[m] on polynomial 0),   m < M, t < T <= 16
+// The reference encodes every LUT coefficient as a full-slot constant plaintext and does one
+// multiply + rescale + add per term (xor_service.py:283-285, sbox_service.py:124-136).  A
+// constant a+bi is the 2-term polynomial a + b X^(N/2), whose NTT image takes one value on the
+// first half of the bit-reversed spectrum and another on the second half -- so the whole
+// inner sum is an elementwise weighted sum.  Each input ciphertext is read ONCE and all M
+// outputs are produced from registers; no rescale happens here (the constants already carry
+// the scale that makes the later product land on the level's scale).
+#define FHE_LC_MAX_T 16
+struct LinCombIn {
+    const u64* ptr[FHE_LC_MAX_T];        // in_t : [2][batch][nq_t][N]
+    long long poly_stride[FHE_LC_MAX_T];
+    long long batch_stride[FHE_LC_MAX_T];
+};
+// consts: [M][T][nq][2] ConstF (first / second half of the spectrum); c0: [M][nq][2] u64 or null
+// grid: (N/256, 2 * batch * nq)
+template <int T_MAX>
+__global__ void __launch_bounds__(256) k_lincomb(DevTables Tb, int nq, int batch, int M, int T, LinCombIn in,
+                                                 const ConstF* consts, const u64* c0, u64* out) {
+    const int row = blockIdx.y;
+    const int j = row % nq, b = (row / nq) % batch, poly = row / (nq * batch);
+    const Modulus Mo = Tb.mod[j];
+    const double q = Mo.qd, qi = Mo.qinv;
+    const u32 idx = blockIdx.x * 256 + threadIdx.x;
+    const int half = idx >> (Tb.log_n - 1);
+    const size_t lo = ((size_t)j << Tb.log_n) + idx;
+    double x[T_MAX];
+#pragma unroll
+    for (int t = 0; t < T_MAX; ++t)
+        x[t] = t < T ? u64_to_f(in.ptr[t][(size_t)poly * in.poly_stride[t] + (size_t)b * in.batch_stride[t] + lo]) : 0.0;
+    const size_t out_ct = (size_t)2 * batch * nq << Tb.log_n;
+    u64* o = out + (((size_t)poly * batch + b) * nq << Tb.log_n) + lo;
+    for (int m = 0; m < M; ++m) {
+        const ConstF* cm = consts + (((size_t)m * T) * nq + j) * 2 + half;
+        double acc = 0.0;
+#pragma unroll
+        for (int t = 0; t < T_MAX; ++t)
+            if (t < T) acc = d_add(acc, mulmod_const(x[t], cm[(size_t)t * nq * 2], q));
+        double r = reduce_canon(acc, q, qi);
+        if (c0 != nullptr && poly == 0) {
+            r = d_add(r, u64_to_f(c0[((size_t)m * nq + j) * 2 + half]));
+            r = r >= q ? d_add(r, -q) : r;
+        }
+        o[(size_t)m * out_ct] = f_to_u64(r);
+    }
+}
+
+// acc3 (+)= a (x) b  : accumulate the three tensor components of G products in one pass.
+//   a_g : [2][batch][nq_a][N]  (first nq limbs used),  b : G x [2][batch][nq][N] contiguous
+//   acc : [3][batch][nq][N]    grid: (N/256, batch * nq)
+struct TensorAccIn {
+    const u64* a[FHE_LC_MAX_T];
+    long long a_poly_stride[FHE_LC_MAX_T];
+    long long a_batch_stride[FHE_LC_MAX_T];
+};
+__global__ void __launch_bounds__(256) k_tensor_acc(DevTables Tb, int nq, int batch, int G, TensorAccIn in,
+                                                    const u64* bsrc, u64* acc, int accumulate) {
+    const int row = blockIdx.y;
+    const int j = row % nq, b = row / nq;
+    const Modulus Mo = Tb.mod[j];
+    const double q = Mo.qd, qi = Mo.qinv;
+    const u32 idx = blockIdx.x * 256 + threadIdx.x;
+    const size_t lo = ((size_t)j << Tb.log_n) + idx;
+    const size_t ps = (size_t)batch * nq << Tb.log_n;            // poly stride of b_g and acc
+    const size_t bo = ((size_t)b * nq << Tb.log_n) + lo;
+    double d0 = 0.0, d1 = 0.0, d2 = 0.0;
+    if (accumulate) { d0 = u64_to_f(acc[bo]); d1 = u64_to_f(acc[bo + ps]); d2 = u64_to_f(acc[bo + 2 * ps]); }
+    for (int g = 0; g < G; ++g) {
+        const u64* ap = in.a[g] + (size_t)b * in.a_batch_stride[g] + lo;
+        const double a0 = u64_to_f(ap[0]), a1 = u64_to_f(ap[in.a_poly_stride[g]]);
+        const u64* bp = bsrc + (size_t)g * 2 * ps + bo;
+        const double b0 = u64_to_f(bp[0]), b1 = u64_to_f(bp[ps]);
+        d0 = d_add(d0, mulmod_var(a0, b0, q, qi));
+        d1 = d_add(d1, d_add(mulmod_var(a0, b1, q, qi), mulmod_var(a1, b0, q, qi)));
+        d2 = d_add(d2, mulmod_var(a1, b1, q, qi));
+    }
+    acc[bo] = f_to_u64(reduce_canon(d0, q, qi));
+    acc[bo + ps] = f_to_u64(reduce_canon(d1, q, qi));
+    acc[bo + 2 * ps] = f_to_u64(reduce_canon(d2, q, qi));
+}
+
 // ---------------------------------------------------------------- base conversion
 // One table per source basis.  Output value for target t:
 //     sum_k yc_k * f[k][t]   (mod m_t),     yc_k = centred representative of y_k mod q_k

@@ -1,26 +1,32 @@
-"""Service-level evaluation schedules (the K8 row of SURVEY.md section 2.2): bivariate
-16x16 LUT polynomials in two zeta_16-valued ciphertexts, with lazy relinearisation.
+"""Service-level evaluation schedules (rows K7/K8 of SURVEY.md section 2.2): LUT polynomials
+evaluated with baby-step/giant-step structure, constant-only inner sums and lazy
+relinearisation.  Everything is batched: the ciphertext operands may carry any batch size.
 
-    f(x, y) = sum_i x^i * ( sum_j c_ij y^j )
+    univariate (Paterson-Stockmeyer):  p(t)    = sum_m  (t^B)^m * ( sum_j c[B m + j] t^j )
+    bivariate 16x16:                   f(x, y) = sum_i  x^i     * ( sum_j c[i][j]  y^j )
 
-* the inner sums are pure constant multiplications (no key switch);
-* the level / scale alignment of every operand is folded into the constants, so no
-  operand is rescaled on its own;
-* the 15 outer products of one output are accumulated as a 3-polynomial ciphertext and
-  relinearised once, then rescaled twice.
+* the inner sums are pure constant multiplications -- one pass of ``fhe_lincomb`` reads every
+  power once and writes all inner sums of all outputs; the level / scale alignment of every
+  operand is folded into the constants, so nothing is rescaled on its own;
+* the outer products of one output are accumulated as a 3-polynomial ciphertext
+  (``fhe_tensor_acc``) and relinearised ONCE, then rescaled twice.
 
-Depth: 3 (power basis) + 2 = 5 levels, the same as the reference's ``xor_cipher``
-(/root/reference/xor_service.py:271-286), with 1 relinearisation per output instead of one
-per monomial.  Several outputs (the six S-box / 2S / 3S nibble planes) share the bases.
+Depth: baby basis + giant basis + 2.  For the reference's degree-255 S-box pair
+(/root/reference/sbox/sbox_service.py:116-138: 254 relinearisations, 10 levels) that is
+4 + 4 + 2 (+1 for hi x lo) = 11 levels and 15 + 14 + 2 + 1 = 32 key switches; for the 4-bit XOR
+(/root/reference/xor_service.py:271-286: 92 key switches, 5 levels) 5 levels and 29 key switches.
+Same slot values within CKKS noise; residues differ from the reference operation order.
 """
 from __future__ import annotations
 
 from fractions import Fraction
-from typing import Dict, List, Sequence
+from typing import Dict, List, Optional, Sequence
 
 import numpy as np
 
 from .engine import Ciphertext
+
+_EPS = 1e-13
 
 
 def power_basis_16(eng_wrap, ct) -> Dict[int, Ciphertext]:
@@ -33,57 +39,101 @@ def power_basis_16(eng_wrap, ct) -> Dict[int, Ciphertext]:
     return basis
 
 
-def _const_to_residues(eng, value: complex, scale: Fraction, nq: int):
+def _const_pair(eng, value: complex, scale: Fraction, nq: int):
     re = int(round(Fraction(float(value.real)) * scale))
     im = int(round(Fraction(float(value.imag)) * scale))
     return eng._const_residues(re, im, nq)
 
 
-def bivariate_lut(eng_wrap, ct_x, ct_y, coeff_mats: Sequence[np.ndarray],
-                  bx: Dict[int, Ciphertext] | None = None,
-                  by: Dict[int, Ciphertext] | None = None) -> List[Ciphertext]:
-    eng = eng_wrap.engine
+def _outer_sum(eng, relin_key, outer: Dict[int, Ciphertext], inner_basis: Dict[int, Ciphertext],
+               coeff_mats: Sequence[np.ndarray], cache_key) -> List[Ciphertext]:
+    """sum_i outer[i] * (sum_j C[i][j] inner_basis[j]),  i = 0 meaning the constant 1 (same for
+    j = 0).  ``coeff_mats`` is a list of (n_outer+1) x (n_inner+1) complex matrices; all outputs
+    share the two bases.  Returns one ciphertext per matrix, two levels below the lowest
+    operand."""
     be, P = eng.backend, eng.params
+    lo = min([c.level for c in outer.values()] + [c.level for c in inner_basis.values()])
+    if lo < 2:
+        raise RuntimeError("LUT evaluation: not enough levels left")
+    nq = lo + 1
+    target = P.delta[lo - 2] * P.moduli[lo] * P.moduli[lo - 1]     # scale before the two rescales
+    n_out = len(coeff_mats)
+    i_list = sorted(outer)                       # outer powers actually present
+    j_list = sorted(inner_basis)
+    rows = [(m, i) for m in range(n_out) for i in [0] + i_list
+            if np.any(np.abs(np.asarray(coeff_mats[m])[i]) > _EPS)]
+
+    cache = eng.__dict__.setdefault("_lut_cache", {})
+    key = (cache_key, lo, tuple(outer[i].level for i in i_list), tuple(inner_basis[j].level for j in j_list))
+    prep = cache.get(key)
+    if prep is None:
+        const_res, c0_res = [], []
+        for (m, i) in rows:
+            C = np.asarray(coeff_mats[m], dtype=np.complex128)
+            s_in = target if i == 0 else target / P.delta[outer[i].level]
+            const_res.append([_const_pair(eng, C[i, j], s_in / P.delta[inner_basis[j].level], nq) for j in j_list])
+            c0_res.append(_const_pair(eng, C[i, 0], s_in, nq))
+        prep = be.prepare_lincomb(const_res, c0_res, nq)
+        cache[key] = prep
+    inner = be.lincomb([inner_basis[j].polys for j in j_list], prep)      # one pass, all inner sums
+
+    outs = []
+    for m in range(n_out):
+        a_list, b_list, acc = [], [], None
+        zero_term = None
+        for r, (mm, i) in enumerate(rows):
+            if mm != m:
+                continue
+            if i == 0:
+                zero_term = inner[r]
+            else:
+                a_list.append(outer[i].polys)
+                b_list.append(inner[r])
+        bt = inner[0].shape[1] if hasattr(inner[0], "shape") else 1
+        if a_list:
+            acc = be.tensor_acc(None, a_list, b_list, nq)
+        else:
+            acc = be.zeros(3, bt, nq, False)
+        if zero_term is not None:
+            acc = be.concat([be.add(be.take_polys(acc, 2), zero_term, nq, 0), be.select_poly(acc, 2)])
+        ct2 = eng._relin(Ciphertext(eng, acc, lo), relin_key)
+        outs.append(eng._rescale(eng._rescale(ct2)))
+    return outs
+
+
+def bivariate_lut(eng_wrap, ct_x, ct_y, coeff_mats: Sequence[np.ndarray],
+                  bx: Optional[Dict[int, Ciphertext]] = None,
+                  by: Optional[Dict[int, Ciphertext]] = None, cache_key="biv") -> List[Ciphertext]:
+    """f_m(x, y) = sum_ij C_m[i][j] x^i y^j for 16x16 coefficient matrices (zeta_16 inputs)."""
+    eng = eng_wrap.engine
     if bx is None:
         bx = power_basis_16(eng_wrap, ct_x)
     if by is None:
         by = power_basis_16(eng_wrap, ct_y)
-    lo = min(min(c.level for c in bx.values()), min(c.level for c in by.values()))
-    if lo < 2:
-        raise RuntimeError("bivariate_lut: not enough levels left")
-    nq = lo + 1
-    bt = max(ct_x.batch, ct_y.batch)
-    # scale of the accumulated products before the two closing rescales
-    target = P.delta[lo - 2] * P.moduli[lo] * P.moduli[lo - 1]
-    xs = {i: (be.take_limbs(c.polys, nq, False) if c.level > lo else c.polys) for i, c in bx.items()}
-    ys = {j: (be.take_limbs(c.polys, nq, False) if c.level > lo else c.polys) for j, c in by.items()}
-    outs = []
-    for C in coeff_mats:
-        C = np.asarray(C, dtype=np.complex128)
-        acc = be.zeros(3, bt, nq, False)
-        for i in range(16):
-            row = C[i]
-            if not np.any(np.abs(row) > 1e-13):
-                continue
-            # scale the inner sum must carry so that x^i * inner sits at `target`
-            s_in = target if i == 0 else target / P.delta[bx[i].level]
-            inner = None
-            for j in range(1, 16):
-                if abs(row[j]) <= 1e-13:
-                    continue
-                cp, cm = _const_to_residues(eng, row[j], s_in / P.delta[by[j].level], nq)
-                term = be.mul_const(ys[j], cp, cm, nq)
-                inner = term if inner is None else be.add(inner, term, nq, 0)
-            if inner is None:
-                inner = be.zeros(2, bt, nq, False)
-            if abs(row[0]) > 1e-13:
-                cp, cm = _const_to_residues(eng, row[0], s_in, nq)
-                inner = be.add_const(inner, cp, cm, nq)
-            if i == 0:
-                acc = be.concat([be.add(be.take_polys(acc, 2), inner, nq, 0), be.select_poly(acc, 2)])
-            else:
-                acc = be.add(acc, be.tensor(xs[i], inner, nq), nq, 0)
-        ct3 = Ciphertext(eng, acc, lo)
-        ct2 = eng._relin(ct3, eng_wrap.relin_key)
-        outs.append(eng._rescale(eng._rescale(ct2)))
-    return outs
+    used_i = [i for i in range(1, 16) if any(np.any(np.abs(np.asarray(C)[i]) > _EPS) for C in coeff_mats)]
+    used_j = [j for j in range(1, 16) if any(np.any(np.abs(np.asarray(C)[:, j]) > _EPS) for C in coeff_mats)]
+    outer = {i: bx[i] for i in used_i}
+    inner = {j: by[j] for j in used_j}
+    return _outer_sum(eng, eng_wrap.relin_key, outer, inner, coeff_mats, (cache_key, len(coeff_mats)))
+
+
+def poly_eval_bsgs(engine, relin_key, ct, coeff_vecs: Sequence[np.ndarray], baby: int = 16,
+                   cache_key="ps") -> List[Ciphertext]:
+    """Paterson-Stockmeyer evaluation of several polynomials of degree < baby^2 on one
+    ciphertext, sharing the baby basis t^1..t^baby and the giant basis (t^baby)^1..(baby-1)."""
+    deg = max(len(c) for c in coeff_vecs) - 1
+    n_giant = deg // baby                                     # highest giant power needed
+    pw = engine.make_power_basis(ct, baby, relin_key)         # t^1 .. t^baby
+    babies = {j: pw[j - 1] for j in range(1, baby)}
+    giants: Dict[int, Ciphertext] = {}
+    if n_giant >= 1:
+        gp = engine.make_power_basis(pw[baby - 1], n_giant, relin_key)
+        giants = {m: gp[m - 1] for m in range(1, n_giant + 1)}
+    mats = []
+    for c in coeff_vecs:
+        c = np.asarray(c, dtype=np.complex128)
+        M = np.zeros((n_giant + 1, baby), dtype=np.complex128)
+        for k, v in enumerate(c):
+            M[k // baby, k % baby] = v
+        mats.append(M)
+    return _outer_sum(engine, relin_key, giants, babies, mats, (cache_key, len(mats), baby))

@@ -1,0 +1,320 @@
+#!/usr/bin/env python
+"""Benchmark of the homomorphic-AES hot path on B200 ("Measurement").
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--batch B]
+
+Workload (BASELINE.json configs[1]): SubBytes on 2K-block-packed ciphertexts -- the function of
+the reference's ``SBoxService.sub_bytes_array`` (zeta_256^x -> zeta_256^S(x) through the
+sbox_hi / sbox_lo degree-255 LUT polynomials and their product;
+/root/reference/sbox/sbox_service.py:116-138) at N = 2^16, max_level = 22
+(test/test_sbox_service.py:19), on a batch of B ciphertexts per GPU; one ciphertext packs
+slot_count/16 = 2048 AES blocks.  Both arms evaluate it with the baby-step/giant-step
+Paterson-Stockmeyer schedule of aes_fhe_b200/fused.py (32 key switches); the reference's own
+operation order (255 key switches) is timed once and reported as `reference_order`.
+
+A "step" is one pass of that path over one batch.  `value` = AES blocks per second with the
+input ciphertexts resident in HBM; `e2e` = the same through the public API from host buffers
+(encode + encrypt + H2D, SubBytes, decrypt + D2H + decode inside the timed region).
+Ciphertext batches shard across ranks with no data-path collective (weak scaling); NCCL is
+used once to broadcast the evaluation key and once to gather result checksums.
+
+`--impl reference` times the same operation sequence on the CPU oracle (oracle/refmod.cpp,
+OpenMP over all host cores): the reference's own arithmetic lives in the closed `desilofhe`
+wheel, so the oracle port is the CPU arm (cpu_baseline.kind = "port").
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+METRIC = "homomorphic AES blocks/sec (SubBytes stage, 2048 blocks per ciphertext)"
+UNIT = "blocks/s"
+MAX_LEVEL = 22
+LOG_N = 16
+
+
+def _peak_gbs():
+    try:
+        return json.load(open(ROOT / "MEASURED_PEAKS.json"))["hbm_gbs"], "measured"
+    except Exception:
+        return 6650.0, "fallback"
+
+
+def _inputs(slot_count: int, batch: int, seed: int) -> np.ndarray:
+    """test_sbox_array_simd's input (tile(arange(256))) for ciphertext 0, seeded uniform bytes
+    for the others (test/test_sbox_service.py:55-66)."""
+    rng = np.random.default_rng(seed)
+    rows = [np.tile(np.arange(256, dtype=np.uint8), slot_count // 256 + 1)[:slot_count]]
+    for _ in range(batch - 1):
+        rows.append(rng.integers(0, 256, slot_count, dtype=np.uint8))
+    return np.stack(rows)
+
+
+def _make_service(backend=None, seed=1):
+    from aes_fhe_b200.params import make_params
+    from aes_fhe_b200.services.engine_context import EngineContext
+    from aes_fhe_b200.services.sbox_service import SBoxService
+    kw = dict(_params=make_params(LOG_N, MAX_LEVEL), seed=seed)
+    if backend is not None:
+        kw["_backend"] = backend
+    ctx = EngineContext(signature=2, max_level=MAX_LEVEL, mode="parallel", _engine_kwargs=kw, rotation_steps=[])
+    return ctx, SBoxService(ctx)
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock / throttle reasons during the timed region (nvidia-smi's numbers via NVML)."""
+
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index = index
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._halt = threading.Event()
+
+    def run(self):
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            names = {nv.nvmlClocksThrottleReasonHwSlowdown: "hw_slowdown",
+                     nv.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
+                     nv.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown",
+                     nv.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap"}
+            while not self._halt.is_set():
+                self.samples.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+                time.sleep(0.1)
+        except Exception as e:  # pragma: no cover
+            self.reasons.add(f"nvml_unavailable:{type(e).__name__}")
+
+    def stop(self):
+        self._halt.set()
+        self.join(timeout=2)
+        med = float(np.median(self.samples)) if self.samples else None
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+
+
+# --------------------------------------------------------------------------- CPU arm
+def cpu_arm(threads: int = 0):
+    """One full pass of the same schedule (sub_bytes_array_bsgs, 32 key switches) on ONE
+    ciphertext (2048 blocks) on the CPU oracle, N = 2^16, max_level 22, all host cores."""
+    from oracle.refmod import RefBackend, build
+    build()
+    from aes_fhe_b200.params import make_params
+    from aes_fhe_b200.services.xor_service import ZetaEncoder
+    from aes_fhe_b200.services.sbox_service import AES_SBOX
+    P = make_params(LOG_N, MAX_LEVEL)
+    be = RefBackend(P, threads=threads)
+    ctx, svc = _make_service(backend=be)
+    eng = ctx.engine
+    x = _inputs(eng.slot_count, 1, 0)[0]
+    ct = ctx.encrypt(ZetaEncoder.to_zeta(x, 256))
+    t0 = time.perf_counter()
+    out = svc.sub_bytes_array_bsgs(ct)
+    full = time.perf_counter() - t0
+    got = ZetaEncoder.from_zeta(ctx.decrypt(out), 256)
+    assert np.array_equal(got, np.array(AES_SBOX, dtype=np.uint8)[x])
+    blocks = eng.slot_count // 16
+    return {"value": blocks / full, "unit": UNIT, "cores": be.threads, "kind": "port",
+            "sample": f"one ciphertext ({blocks} blocks), full sub_bytes_array_bsgs at N=2^16, L=22: {full:.2f}s "
+                      f"on {be.threads} threads (oracle/refmod.cpp)"}, full
+
+
+# --------------------------------------------------------------------------- main
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=4, help="ciphertexts per GPU per step")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--reference-order", action="store_true",
+                    help="also time the reference's own 255-key-switch operation order")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    config = {"workload": "configs[1]: SubBytes (sbox_hi/sbox_lo degree-255 zeta_256 LUT pair, BSGS schedule) on "
+                          "2048-block ciphertexts, N=2^16, max_level=22",
+              "batch_ciphertexts_per_gpu": args.batch, "blocks_per_ciphertext": (1 << (LOG_N - 1)) // 16,
+              "l2": "working set per step (GBs of power-basis ciphertexts) exceeds the 126 MB L2",
+              "sharding": "independent ciphertext batches per rank, no data-path collective"}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        times = []
+        for _ in range(max(1, min(args.steps, 3))):
+            cb, full = cpu_arm()
+            times.append(full)
+        full = float(np.median(times))
+        blocks = (1 << (LOG_N - 1)) // 16
+        v = blocks / full
+        cb["value"] = v
+        print(json.dumps({"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus,
+                          "steps": args.steps, "warmup": args.warmup, "ms_per_step": full * 1e3,
+                          "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64-exact-int",
+                          "data": "synthetic", "config": config, "cpu_baseline": cb,
+                          "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return
+
+    import torch
+    import torch.distributed as dist
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    from aes_fhe_b200.services.xor_service import ZetaEncoder
+    from aes_fhe_b200.services.sbox_service import AES_SBOX
+    import aes_fhe_b200.backend_cuda as bc
+
+    ctx, svc = _make_service(seed=1)
+    eng = ctx.engine
+    be = eng.backend
+    if world > 1:
+        # evaluation key comes from rank 0 over NCCL/NVLink (every rank derived the same key from
+        # the shared seed; the broadcast is the deployment path and must be a no-op on the bits)
+        rlk = svc.rlk.data
+        before = rlk.clone() if rank else None
+        dist.broadcast(rlk, src=0)
+        if rank:
+            assert torch.equal(before, rlk)
+    sc = eng.slot_count
+    sbox = np.array(AES_SBOX, dtype=np.uint8)
+    data = _inputs(sc, args.batch, seed=rank)
+    zeta = ZetaEncoder.to_zeta(data, 256)
+    ct_in = eng.encrypt(zeta, ctx.public_key)
+
+    def step():
+        return svc.sub_bytes_array_bsgs(ct_in)
+
+    def e2e_step():
+        pinned = torch.from_numpy(np.ascontiguousarray(zeta.view(np.float64))).pin_memory()
+        z = pinned.numpy().view(np.complex128)
+        out = svc.sub_bytes_array_bsgs(eng.encrypt(z, ctx.public_key))
+        dec = eng.decrypt(out, ctx.secret_key)
+        return ZetaEncoder.from_zeta(dec, 256)
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    # correctness of what is being timed (also the first warm-up)
+    out = step()
+    got = ZetaEncoder.from_zeta(np.atleast_2d(eng.decrypt(out, ctx.secret_key)), 256)
+    assert np.array_equal(got, sbox[data]), "SubBytes output differs from the AES S-box"
+    for _ in range(max(0, args.warmup - 1)):
+        step()
+
+    sampler = ClockSampler(local)
+    sampler.start()
+    sync_all()
+    l0 = be.launch_count()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    ev[0].record()
+    for _ in range(args.steps):
+        step()
+    ev[1].record()
+    sync_all()
+    launches = be.launch_count() - l0
+    ms = ev[0].elapsed_time(ev[1]) / args.steps
+    clocks = sampler.stop()
+
+    # end-to-end through the public API from host buffers
+    e2e_step()
+    sync_all()
+    t0 = time.perf_counter()
+    for _ in range(max(1, args.steps // 2)):
+        res = e2e_step()
+    torch.cuda.synchronize()
+    e2e_ms = (time.perf_counter() - t0) / max(1, args.steps // 2) * 1e3
+    assert np.array_equal(np.atleast_2d(res), sbox[data])
+
+    # dominant kernel: the forward NTT (pass A + pass B), timed alone on this stream at the row
+    # count one key-switch ModUp of this batch launches
+    nq = MAX_LEVEL + 1
+    P = eng.params
+    rows = args.batch * P.digits_at(nq) * (nq + P.n_p)
+    x = torch.randint(0, 2 ** 39, (rows // (nq + P.n_p), nq + P.n_p, P.n), dtype=torch.int64, device="cuda")
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    for _ in range(3):
+        be._call("fhe_ntt_fwd", be._ptr(x), x.shape[0], nq, P.n_p)
+    kt = []
+    for _ in range(10):
+        flush.zero_()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); be._call("fhe_ntt_fwd", be._ptr(x), x.shape[0], nq, P.n_p); b.record()
+        torch.cuda.synchronize()
+        kt.append(a.elapsed_time(b))
+    k_ms = float(np.median(kt))
+    alg_bytes = 2 * rows * P.n * 8                      # read once + write once per limb
+    peak, peak_kind = _peak_gbs()
+    achieved = alg_bytes / (k_ms * 1e-3) / 1e9
+    traffic = None
+    try:
+        traffic = json.load(open(ROOT / "profiles" / "ntt_traffic.json"))["dram_bytes_per_row"] * rows
+    except Exception:
+        pass
+
+    t = torch.tensor([ms, e2e_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        chk = torch.tensor([int(got.astype(np.uint64).sum())], dtype=torch.int64, device="cuda")
+        gathered = [torch.zeros_like(chk) for _ in range(world)]
+        dist.all_gather(gathered, chk)
+    ms, e2e_ms = float(t[0]), float(t[1])
+    blocks = world * args.batch * (sc // 16)
+    value = blocks / (ms * 1e-3)
+    e2e_value = blocks / (e2e_ms * 1e-3)
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f64-exact-int", "data": "synthetic", "config": config,
+                "clocks": clocks, "gpu_launches": int(launches),
+                "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms,
+                        "h2d_bytes_per_step": int(4 * args.batch * P.n * 8),
+                        "d2h_bytes_per_step": int(args.batch * P.n * 8)},
+                "roofline": {"bound": "hbm", "kernel": "ntt_fwd (pass A + pass B)", "rows_per_launch": rows,
+                             "achieved": achieved, "peak": peak, "peak_kind": peak_kind, "unit": "GB/s",
+                             "frac": achieved / peak, "traffic": traffic,
+                             "note": "compute-bound on the FP64 pipe, see profiles/"},
+                "ms_per_ciphertext": ms / args.batch,
+                "keyswitches_per_ciphertext": 32}
+        if args.reference_order:
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            svc.sub_bytes_array(ct_in)
+            a.record(); o2 = svc.sub_bytes_array(ct_in); b.record()
+            torch.cuda.synchronize()
+            ok = np.array_equal(ZetaEncoder.from_zeta(np.atleast_2d(eng.decrypt(o2, ctx.secret_key)), 256), sbox[data])
+            line["reference_order"] = {"ms_per_step": a.elapsed_time(b), "keyswitches_per_ciphertext": 255,
+                                       "blocks_per_s": blocks / (a.elapsed_time(b) * 1e-3), "bytes_ok": bool(ok)}
+        if not args.no_cpu_baseline and world == 1:
+            try:
+                line["cpu_baseline"], _ = cpu_arm()
+            except Exception as e:  # pragma: no cover
+                line["cpu_baseline"] = {"unavailable": repr(e)}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

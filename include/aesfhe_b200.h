@@ -70,6 +70,23 @@ int fhe_mul_const(fhe_ctx* ctx, void* stream, uint64_t* out, const uint64_t* a,
 int fhe_add_const(fhe_ctx* ctx, void* stream, uint64_t* out, const uint64_t* a,
                   const uint64_t* c_first, const uint64_t* c_second, int npoly, int nq, int np);
 
+/* LUT inner sums (the multiply(term, pt) + add loops of xor_service.py:283-285 and
+ * sbox/sbox_service.py:124-136, batched): out_m = sum_t c[m][t] (.) in_t (+ c0[m] on poly 0).
+ *   in[t]   : T (<= 16) device pointers to ciphertexts [2][batch][in_nq[t]][N], in_nq[t] >= nq
+ *             (host array of pointers; higher-level inputs are read on their first nq limbs)
+ *   consts  : device, [M][T][nq][2] pairs (c, RN(c/q_j)) of doubles -- the constant's residue on
+ *             the first / second half of the bit-reversed spectrum
+ *   c0      : device, [M][nq][2] residues added to polynomial 0, or NULL
+ *   out     : M ciphertexts [2][batch][nq][N], contiguous.  No rescale is performed. */
+int fhe_lincomb(fhe_ctx* ctx, void* stream, uint64_t* out, const uint64_t* const* in, const int* in_nq,
+                const double* consts, const uint64_t* c0, int M, int T, int nq, int batch);
+
+/* Lazy-relinearised products: acc[3][batch][nq][N] (+)= sum_g a_g (x) b_g for G <= 16 products;
+ * a[g] are ciphertexts [2][batch][a_nq[g]][N] (host array of device pointers), b is G
+ * contiguous ciphertexts [2][batch][nq][N].  One fhe_keyswitch then relinearises the sum. */
+int fhe_tensor_acc(fhe_ctx* ctx, void* stream, uint64_t* acc, const uint64_t* const* a, const int* a_nq,
+                   const uint64_t* b, int G, int nq, int batch, int accumulate);
+
 /* Rescale after every multiply: [npoly][nq][N] -> [npoly][nq-1][N], division by q_{nq-1}
  * rounded to nearest. */
 int fhe_rescale(fhe_ctx* ctx, void* stream, uint64_t* out, const uint64_t* in, int npoly, int nq);

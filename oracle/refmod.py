@@ -236,6 +236,31 @@ class RefBackend:
     def keyswitch(self, d, ksk, nq):
         return self.moddown(self.ks_inner(self.modup(d, nq), d, ksk, nq), nq)
 
+    # ---- fused LUT evaluation pieces, restated with the plain primitives
+    def prepare_lincomb(self, const_res, c0_res, nq: int):
+        return dict(const_res=const_res, c0_res=c0_res, nq=nq, M=len(const_res), T=len(const_res[0]))
+
+    def lincomb(self, inputs: List, prep) -> List:
+        nq = prep["nq"]
+        outs = []
+        for m in range(prep["M"]):
+            acc = None
+            for t, x in enumerate(inputs):
+                cp, cm = prep["const_res"][m][t]
+                term = self.mul_const(np.ascontiguousarray(x[:, :, :nq]), cp, cm, nq)
+                acc = term if acc is None else self.add(acc, term, nq, 0)
+            if prep["c0_res"] is not None:
+                cp, cm = prep["c0_res"][m]
+                acc = self.add_const(acc, cp, cm, nq)
+            outs.append(acc)
+        return outs
+
+    def tensor_acc(self, acc, a_list: List, b_list: List, nq: int):
+        for a, b in zip(a_list, b_list):
+            t = self.tensor(np.ascontiguousarray(a[:, :, :nq]), b, nq)
+            acc = t if acc is None else self.add(acc, t, nq, 0)
+        return acc
+
     def crt_centered(self, h, use: int) -> np.ndarray:
         """h [1, B, use, N] -> float64 [B, N]"""
         h = np.ascontiguousarray(h)

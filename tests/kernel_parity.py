@@ -128,3 +128,36 @@ def check_engine_ops(eg, er, slot_tol=1e-5):
     for k, (x, y) in enumerate(zip(pg, pr), 1):
         same(x, y, f"power {k}")
         assert np.allclose(eg.decrypt(x, kg['sk']), v ** k, atol=slot_tol)
+
+
+def check_fused_services(P, gpu_backend, ref_backend, batch=2):
+    """BSGS S-box and fused 4-bit XOR through fhe_lincomb / fhe_tensor_acc: residues identical
+    on both backends, decoded values equal to the AES S-box / a ^ b."""
+    from aes_fhe_b200.services.engine_context import EngineContext
+    from aes_fhe_b200.services.sbox_service import SBoxService, AES_SBOX
+    from aes_fhe_b200.services.xor_service import (XORService, EngineWrapper, XORConfig, CoefficientCache,
+                                                   ZetaEncoder)
+    outs = []
+    for be in (gpu_backend, ref_backend):
+        ctx = EngineContext(signature=2, max_level=P.max_level,
+                            _engine_kwargs=dict(_params=P, _backend=be, seed=5), rotation_steps=[])
+        svc = SBoxService(ctx)
+        sc = ctx.engine.slot_count
+        rng = np.random.default_rng(3)
+        x = rng.integers(0, 256, (batch, sc), dtype=np.uint8)
+        x[0, :256] = np.arange(256)
+        out = svc.sub_bytes_array_bsgs(ctx.encrypt(ZetaEncoder.to_zeta(x, 256)))
+        dec = ZetaEncoder.from_zeta(np.atleast_2d(ctx.decrypt(out)), 256)
+        assert np.array_equal(dec, np.array(AES_SBOX, dtype=np.uint8)[x]), "S-box bytes"
+        w = EngineWrapper.__new__(EngineWrapper)
+        w.ctx, w.engine = ctx, ctx.engine
+        w.public_key, w.secret_key, w.relin_key = ctx.public_key, ctx.secret_key, ctx.relinearization_key
+        w.conj_key, w.rot_key, w.boot_key = ctx.conjugation_key, ctx.rotation_key, ctx.bootstrap_key
+        xs = XORService(w, CoefficientCache(XORConfig().coeffs_path))
+        a = rng.integers(0, 16, (batch, sc), dtype=np.uint8)
+        b = rng.integers(0, 16, (batch, sc), dtype=np.uint8)
+        r = xs.xor_cipher_fused(w.encrypt(ZetaEncoder.to_zeta(a)), w.encrypt(ZetaEncoder.to_zeta(b)))
+        assert np.array_equal(ZetaEncoder.from_zeta(np.atleast_2d(w.decrypt(r))), a ^ b), "xor nibbles"
+        outs.append((be.to_numpy(out.polys), be.to_numpy(r.polys)))
+    assert np.array_equal(outs[0][0], outs[1][0]), "BSGS S-box residues"
+    assert np.array_equal(outs[0][1], outs[1][1]), "fused XOR residues"

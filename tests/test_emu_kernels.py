@@ -39,3 +39,8 @@ def test_engine_ops(emu_lib, ref_backend_cls):
     P = make_params(12, 6)
     eg, er = make_engines(P, ref_backend_cls, _emu(P, emu_lib))
     kp.check_engine_ops(eg, er)
+
+
+def test_fused_lut_services(emu_lib, ref_backend_cls):
+    P = make_params(12, 13)
+    kp.check_fused_services(P, _emu(P, emu_lib), ref_backend_cls(P), batch=2)

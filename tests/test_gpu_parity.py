@@ -78,3 +78,9 @@ def test_linearity_property_full_size(cuda_lib):
     prod = gb.intt(gb.mul(px, py, nq, 0), nq, 0)
     shifted = np.roll(y, 1); shifted[0] = -shifted[0]                # X * y  (mod X^N + 1)
     assert torch.equal(prod, gb.intt(gb.from_i64(shifted, nq, False), nq, 0))
+
+
+@pytest.mark.parametrize("log_n,batch", [(12, 2), (14, 3)])
+def test_fused_lut_services(log_n, batch, ref_backend_cls, cuda_lib):
+    P = make_params(log_n, 13)
+    kp.check_fused_services(P, _gpu(P), ref_backend_cls(P), batch=batch)
