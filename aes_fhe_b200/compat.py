@@ -1,0 +1,40 @@
+"""Drop-in shim: makes ``import desilofhe`` resolve to this package's Engine / Ciphertext /
+Plaintext, so the reference's unmodified files (engine_context.py:6, xor_service.py:12,69,
+gf_service.py:7, new.py:6) run on the B200 backend.
+
+    import aes_fhe_b200.compat as compat
+    compat.install()                       # sys.modules['desilofhe'] = shim
+    compat.mount_reference('/path/to/aes-fhe')   # also importable as package `aes_xor_fhe`
+
+``install(engine_cls=...)`` lets tests substitute an Engine subclass (e.g. one that injects
+the CPU oracle backend or a smaller ring)."""
+from __future__ import annotations
+
+import importlib.util
+import sys
+import types
+from pathlib import Path
+
+from . import engine as _engine
+
+
+def install(engine_cls=None) -> types.ModuleType:
+    m = types.ModuleType("desilofhe")
+    m.Engine = engine_cls or _engine.Engine
+    m.Ciphertext = _engine.Ciphertext
+    m.Plaintext = _engine.Plaintext
+    m.__doc__ = "aes_fhe_b200 shim of the desilofhe API surface used by songhayeong/aes-fhe"
+    sys.modules["desilofhe"] = m
+    return m
+
+
+def mount_reference(path) -> None:
+    """The reference mixes flat imports (new.py:4-5) with `aes_xor_fhe.`-prefixed ones
+    (gf_service.py:9-10, every test): expose the directory both ways."""
+    path = str(Path(path).resolve())
+    if path not in sys.path:
+        sys.path.insert(0, path)
+    if "aes_xor_fhe" not in sys.modules:
+        pkg = types.ModuleType("aes_xor_fhe")
+        pkg.__path__ = [path]
+        sys.modules["aes_xor_fhe"] = pkg

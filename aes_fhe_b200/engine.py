@@ -455,6 +455,21 @@ class Engine:
             return self._rescale(Ciphertext(self, prod, a.level))
         return self._mul_scalar(a, b)
 
+    def multiply_plain_sum(self, cts: Sequence[Ciphertext], pts: Sequence[Plaintext]) -> Ciphertext:
+        """sum_i ct_i (.) pt_i with ONE rescale (the rotate-mask-add pattern of
+        /root/reference/shiftrows_service.py:41-50 without a rescale per mask)."""
+        lvl = min(c.level for c in cts)
+        if lvl == 0:
+            raise RuntimeError("multiply: no multiplicative depth left")
+        be = self.backend
+        acc = None
+        for ct, pt in zip(cts, pts):
+            ct = self.level_down(ct, lvl)
+            prod = be.mul(ct.polys, pt.at_level(lvl), lvl + 1, 0)
+            acc = prod if acc is None else be.add(acc, prod, lvl + 1, 0)
+            self._count('mul_pt')
+        return self._rescale(Ciphertext(self, acc, lvl))
+
     def _mul_scalar(self, ct: Ciphertext, value) -> Ciphertext:
         """ct x complex constant, rescaled (the reference uses ``multiply(ct, 0.0)`` as
         its "zero ciphertext": /root/reference/xor_service.py:282)."""
