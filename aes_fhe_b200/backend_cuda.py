@@ -290,13 +290,13 @@ class CudaBackend:
         return [out[m] for m in range(M)]
 
     def tensor_acc(self, acc, a_list: List, b_list: List, nq: int):
-        """acc [3,B,nq,N] (or None) += sum_g a_g (x) b_g ; a_g may carry more limbs than nq."""
+        """acc [3,B,nq,N] (or None) += sum_g a_g (x) b_g ; a_g may carry more limbs than nq and
+        either side may be a single ciphertext broadcast over the batch."""
         G = len(a_list)
         a_list = [x.contiguous() for x in a_list]
-        bt = b_list[0].shape[1]
-        bcat = torch.stack([x.contiguous() for x in b_list], dim=0) if G > 1 or not b_list[0].is_contiguous() \
-            else b_list[0].unsqueeze(0)
-        bcat = bcat.contiguous()
+        b_batch = b_list[0].shape[1]
+        bt = max(b_batch, max(x.shape[1] for x in a_list))
+        bcat = torch.stack([x.contiguous() for x in b_list], dim=0).contiguous()
         accumulate = 1
         if acc is None:
             acc = self._empty(3, bt, nq, self.n)
@@ -306,7 +306,9 @@ class CudaBackend:
             g = min(16, G - done)
             ptrs = (C.c_void_p * g)(*[x.data_ptr() for x in a_list[done:done + g]])
             nqs = (C.c_int * g)(*[x.shape[2] for x in a_list[done:done + g]])
-            self._call("fhe_tensor_acc", self._ptr(acc), ptrs, nqs, self._ptr(bcat[done]), g, nq, bt, accumulate)
+            abs_ = (C.c_int * g)(*[x.shape[1] for x in a_list[done:done + g]])
+            self._call("fhe_tensor_acc", self._ptr(acc), ptrs, nqs, abs_, self._ptr(bcat[done]), b_batch, g, nq, bt,
+                       accumulate)
             accumulate = 1
             done += g
         return acc

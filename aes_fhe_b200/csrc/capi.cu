@@ -403,19 +403,22 @@ int fhe_lincomb(fhe_ctx* c, void* stream, uint64_t* out, const uint64_t* const* 
 }
 
 int fhe_tensor_acc(fhe_ctx* c, void* stream, uint64_t* acc, const uint64_t* const* a, const int* a_nq,
-                   const uint64_t* b, int G, int nq, int batch, int accumulate) {
-    if (bad_shape(c, nq, 0) || batch < 1 || G < 1 || G > FHE_LC_MAX_T || !a || !a_nq || !b)
+                   const int* a_batch, const uint64_t* b, int b_batch, int G, int nq, int batch, int accumulate) {
+    if (bad_shape(c, nq, 0) || batch < 1 || G < 1 || G > FHE_LC_MAX_T || !a || !a_nq || !a_batch || !b ||
+        (b_batch != batch && b_batch != 1))
         return fail("fhe_tensor_acc: bad shape");
     TensorAccIn ti;
     for (int g = 0; g < FHE_LC_MAX_T; ++g) {
         const int ng = g < G ? a_nq[g] : nq;
         if (g < G && ng < nq) return fail("fhe_tensor_acc: operand has fewer limbs than the accumulator");
+        const int ab = g < G ? a_batch[g] : batch;
+        if (ab != batch && ab != 1) return fail("fhe_tensor_acc: operand batch must be 1 or the accumulator's");
         ti.a[g] = g < G ? (const u64*)a[g] : nullptr;
-        ti.a_batch_stride[g] = (long long)ng * c->n;
-        ti.a_poly_stride[g] = (long long)batch * ng * c->n;
+        ti.a_batch_stride[g] = ab == 1 ? 0 : (long long)ng * c->n;
+        ti.a_poly_stride[g] = (long long)ab * ng * c->n;
     }
     launch(k_tensor_acc, dim3(c->n / 256, batch * nq), dim3(256), (cudaStream_t)stream, c->T, nq, batch, G, ti,
-           (const u64*)b, (u64*)acc, accumulate);
+           (const u64*)b, b_batch, (u64*)acc, accumulate);
     return check("fhe_tensor_acc");
 }
 

@@ -89,13 +89,13 @@ def _outer_sum(eng, relin_key, outer: Dict[int, Ciphertext], inner_basis: Dict[i
             else:
                 a_list.append(outer[i].polys)
                 b_list.append(inner[r])
-        bt = inner[0].shape[1] if hasattr(inner[0], "shape") else 1
+        bt = max([inner[0].shape[1]] + [c.batch for c in outer.values()])
         if a_list:
             acc = be.tensor_acc(None, a_list, b_list, nq)
         else:
             acc = be.zeros(3, bt, nq, False)
         if zero_term is not None:
-            acc = be.concat([be.add(be.take_polys(acc, 2), zero_term, nq, 0), be.select_poly(acc, 2)])
+            acc = be.concat([be.add(be.take_polys(acc, 2), be.expand_batch(zero_term, bt), nq, 0), be.select_poly(acc, 2)])
         ct2 = eng._relin(Ciphertext(eng, acc, lo), relin_key)
         outs.append(eng._rescale(eng._rescale(ct2)))
     return outs

@@ -227,10 +227,12 @@ def main():
     sync_all()
     l0 = be.launch_count()
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    torch.cuda.nvtx.range_push("timed_region")
     ev[0].record()
     for _ in range(args.steps):
         step()
     ev[1].record()
+    torch.cuda.nvtx.range_pop()
     sync_all()
     launches = be.launch_count() - l0
     ms = ev[0].elapsed_time(ev[1]) / args.steps

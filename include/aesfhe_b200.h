@@ -82,10 +82,12 @@ int fhe_lincomb(fhe_ctx* ctx, void* stream, uint64_t* out, const uint64_t* const
                 const double* consts, const uint64_t* c0, int M, int T, int nq, int batch);
 
 /* Lazy-relinearised products: acc[3][batch][nq][N] (+)= sum_g a_g (x) b_g for G <= 16 products;
- * a[g] are ciphertexts [2][batch][a_nq[g]][N] (host array of device pointers), b is G
- * contiguous ciphertexts [2][batch][nq][N].  One fhe_keyswitch then relinearises the sum. */
+ * a[g] are ciphertexts [2][a_batch[g]][a_nq[g]][N] (host array of device pointers), b is G
+ * contiguous ciphertexts [2][b_batch][nq][N]; a_batch[g] and b_batch are `batch` or 1 (a
+ * single ciphertext, e.g. an encrypted round key, broadcast over the batch).  One
+ * fhe_keyswitch then relinearises the sum. */
 int fhe_tensor_acc(fhe_ctx* ctx, void* stream, uint64_t* acc, const uint64_t* const* a, const int* a_nq,
-                   const uint64_t* b, int G, int nq, int batch, int accumulate);
+                   const int* a_batch, const uint64_t* b, int b_batch, int G, int nq, int batch, int accumulate);
 
 /* Rescale after every multiply: [npoly][nq][N] -> [npoly][nq-1][N], division by q_{nq-1}
  * rounded to nearest. */
