@@ -188,11 +188,11 @@ def main():
     if world > 1:
         # evaluation key comes from rank 0 over NCCL/NVLink (every rank derived the same key from
         # the shared seed; the broadcast is the deployment path and must be a no-op on the bits)
-        rlk = svc.rlk.data
-        before = rlk.clone() if rank else None
-        dist.broadcast(rlk, src=0)
+        from aes_fhe_b200.sharding import broadcast_handle
+        before = svc.rlk.data.clone() if rank else None
+        svc.rlk.data = broadcast_handle(be, svc.rlk.data, src=0)
         if rank:
-            assert torch.equal(before, rlk)
+            assert torch.equal(before, svc.rlk.data)
     sc = eng.slot_count
     sbox = np.array(AES_SBOX, dtype=np.uint8)
     data = _inputs(sc, args.batch, seed=rank)
