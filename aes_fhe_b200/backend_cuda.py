@@ -313,6 +313,46 @@ class CudaBackend:
             done += g
         return acc
 
+    # ---- device-side encode / decode / sampling (throughput path; the default host path keeps
+    # GPU and oracle ciphertexts bit-identical for the parity tests)
+    def _enc_tables(self):
+        t = getattr(self, "_enc_tab", None)
+        if t is None:
+            from . import encoding
+            k_pos, k_neg, twist = encoding._tables(self.params.log_n)
+            t = (torch.from_numpy(k_pos).to(self.device), torch.from_numpy(k_neg).to(self.device),
+                 torch.from_numpy(twist).to(self.device))
+            self._enc_tab = t
+        return t
+
+    def encode_device(self, values: torch.Tensor, scale: float):
+        """complex128 [B, slots] (device) -> NTT-domain plaintext [1, B, nq?]: returns int64 coefficients [B, N]"""
+        k_pos, k_neg, twist = self._enc_tables()
+        bt = values.shape[0]
+        spec = torch.empty((bt, self.n), dtype=torch.complex128, device=self.device)
+        spec[:, k_pos] = values
+        spec[:, k_neg] = values.conj()
+        m = (torch.fft.fft(spec, dim=1) * twist.conj() / self.n).real * scale
+        return torch.round(m).to(torch.int64)
+
+    def from_i64_device(self, coeffs: torch.Tensor, nq: int, with_p: bool):
+        np_ = self._K if with_p else 0
+        coeffs = coeffs.contiguous()
+        out = self._empty(1, coeffs.shape[0], nq + np_, self.n)
+        self._call("fhe_from_i64", self._ptr(out), self._ptr(coeffs), nq, np_, coeffs.shape[0])
+        self._call("fhe_ntt_fwd", self._ptr(out), coeffs.shape[0], nq, np_)
+        return out
+
+    def decode_device(self, h, use: int, scale: float) -> torch.Tensor:
+        """coefficient-domain [1, B, use, N] -> complex128 slots [B, slots] on the device"""
+        k_pos, _, twist = self._enc_tables()
+        h = h.contiguous()
+        bt = h.shape[1]
+        m = torch.empty((bt, self.n), dtype=torch.float64, device=self.device)
+        self._call("fhe_crt_centered", self._ptr(m), self._ptr(h), use, bt)
+        spec = torch.fft.ifft(m * twist, dim=1) * self.n
+        return spec[:, k_pos] / scale
+
     def crt_centered(self, h, use: int) -> np.ndarray:
         """h [1, B, use, N] coefficient domain -> float64 [B, N]"""
         h = h.contiguous()

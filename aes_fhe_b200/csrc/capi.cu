@@ -111,6 +111,7 @@ RowMap make_map(const fhe_ctx* c, int rows_per_poly, int j0, int nq, int skip_al
     m.rows_per_poly = rows_per_poly; m.j0 = j0; m.nq = nq; m.p_base = c->n_q; m.skip_alpha = skip_alpha;
     m.digits = skip_alpha > 0 ? (nq + skip_alpha - 1) / skip_alpha : 1;
     m.log_n = c->log_n;
+    m.n_blocks = 1;
     return m;
 }
 

@@ -39,6 +39,9 @@ struct RowMap {
     int skip_alpha;
     int digits;                    // beta, when skip_alpha > 0
     int log_n;
+    int n_blocks;                  // rows / rows_per_poly: launch order is limb-major, block-minor,
+                                   // so the CTAs sharing one twiddle table are co-resident (L2 reuse)
+    FHE_D int launch_row(int y) const { return (y % n_blocks) * rows_per_poly + y / n_blocks; }
     FHE_D int mod_id(int row) const {
         int j = j0 + row % rows_per_poly;
         if (skip_alpha > 0) {
@@ -182,7 +185,7 @@ template <int LOG_R, class LoadOp>
 __global__ void __launch_bounds__(256) ntt_fwd_pass_a(DevTables T, RowMap map, LoadOp ld, StoreRaw st) {
     constexpr int R = 1 << LOG_R, G = R / 16, COLS = 256 / G, LEV1 = LOG_R - 4;
     FHE_SHARED double sm[4096];
-    const int row = blockIdx.y;
+    const int row = map.launch_row(blockIdx.y);
     const int mid = map.mod_id(row);
     if (mid < 0) return;
     const Modulus M = T.mod[mid];
@@ -214,7 +217,7 @@ __global__ void __launch_bounds__(256) ntt_fwd_pass_a(DevTables T, RowMap map, L
 template <class StoreOp>
 __global__ void __launch_bounds__(256) ntt_fwd_pass_b(DevTables T, RowMap map, LoadRaw ld, StoreOp st) {
     FHE_SHARED double sm[4096 + 256];
-    const int row = blockIdx.y;
+    const int row = map.launch_row(blockIdx.y);
     const int mid = map.mod_id(row);
     if (mid < 0) return;
     const Modulus M = T.mod[mid];
@@ -248,7 +251,7 @@ __global__ void __launch_bounds__(256) ntt_fwd_pass_b(DevTables T, RowMap map, L
 template <class LoadOp>
 __global__ void __launch_bounds__(256) ntt_inv_pass_b(DevTables T, RowMap map, LoadOp ld, StoreRaw st) {
     FHE_SHARED double sm[4096 + 256];
-    const int row = blockIdx.y;
+    const int row = map.launch_row(blockIdx.y);
     const int mid = map.mod_id(row);
     if (mid < 0) return;
     const Modulus M = T.mod[mid];
@@ -285,7 +288,7 @@ __global__ void __launch_bounds__(256) ntt_inv_pass_a(DevTables T, RowMap map, L
                                                       const ConstF* scale) {
     constexpr int R = 1 << LOG_R, G = R / 16, COLS = 256 / G, LEV1 = LOG_R - 4;
     FHE_SHARED double sm[4096];
-    const int row = blockIdx.y;
+    const int row = map.launch_row(blockIdx.y);
     const int mid = map.mod_id(row);
     if (mid < 0) return;
     const Modulus M = T.mod[mid];
@@ -320,12 +323,13 @@ __global__ void __launch_bounds__(256) ntt_inv_pass_a(DevTables T, RowMap map, L
 // `work` ([.., work_stride] layout) receives the lazy intermediate between the two passes; it
 // may alias the destination, or the source for in-place use.
 template <class LoadOp, class StoreOp>
-inline void ntt_forward(const DevTables& T, const RowMap& map, int rows, LoadOp ld, u64* work,
+inline void ntt_forward(const DevTables& T, const RowMap& map_in, int rows, LoadOp ld, u64* work,
                         long long work_stride, StoreOp st, cudaStream_t s) {
     const int log_r = T.log_n - 8;
     dim3 grid(1u << (log_r - 4), rows), block(256);
     StoreRaw sp; sp.dst = work; sp.poly_stride = work_stride;
     LoadRaw lp; lp.src = work; lp.poly_stride = work_stride;
+    RowMap map = map_in; map.n_blocks = rows / map.rows_per_poly;
     switch (log_r) {
         case 4: fhe_launch(ntt_fwd_pass_a<4, LoadOp>, grid, block, 0, s, T, map, ld, sp); break;
         case 5: fhe_launch(ntt_fwd_pass_a<5, LoadOp>, grid, block, 0, s, T, map, ld, sp); break;
@@ -337,12 +341,13 @@ inline void ntt_forward(const DevTables& T, const RowMap& map, int rows, LoadOp 
 }
 
 template <class LoadOp, class StoreOp>
-inline void ntt_inverse(const DevTables& T, const RowMap& map, int rows, LoadOp ld, u64* work,
+inline void ntt_inverse(const DevTables& T, const RowMap& map_in, int rows, LoadOp ld, u64* work,
                         long long work_stride, StoreOp st, const ConstF* scale, cudaStream_t s) {
     const int log_r = T.log_n - 8;
     dim3 grid(1u << (log_r - 4), rows), block(256);
     StoreRaw sp; sp.dst = work; sp.poly_stride = work_stride;
     LoadRaw lp; lp.src = work; lp.poly_stride = work_stride;
+    RowMap map = map_in; map.n_blocks = rows / map.rows_per_poly;
     fhe_launch(ntt_inv_pass_b<LoadOp>, grid, block, 0, s, T, map, ld, sp);
     switch (log_r) {
         case 4: fhe_launch(ntt_inv_pass_a<4, StoreOp>, grid, block, 0, s, T, map, lp, st, scale); break;

@@ -155,7 +155,7 @@ class Engine:
     def __init__(self, *args, mode: str = 'cpu', use_bootstrap: bool = False,
                  use_multiparty: bool = False, thread_count: int = 0, device_id: int = 0,
                  max_level: Optional[int] = None, log_coeff_count: Optional[int] = None,
-                 special_prime_count: Optional[int] = None, seed: int = 0,
+                 special_prime_count: Optional[int] = None, seed: int = 0, device_codec: bool = False,
                  _backend=None, _params: Optional[CKKSParams] = None):
         args = list(args)
         # positional forms: Engine(mode) | Engine(max_level, mode) | Engine(log_n, K, mode)
@@ -174,6 +174,9 @@ class Engine:
         if mode not in ('cpu', 'parallel', 'gpu'):
             raise ValueError(f"unknown mode {mode!r}")
         self.mode = mode
+        # device_codec: encode / sample / decode on the GPU (throughput path).  Off by default so
+        # that ciphertexts are reproducible bit for bit from the host RNG (parity tests).
+        self.device_codec = bool(device_codec)
         self.use_bootstrap = bool(use_bootstrap)
         self.thread_count = thread_count
         self.device_id = device_id
@@ -313,11 +316,13 @@ class Engine:
         be, P = self.backend, self.params
         if isinstance(data, Plaintext):
             data = data.values
+        lvl = P.max_level if level is None else int(level)
+        nq = lvl + 1
+        if self.device_codec and hasattr(be, "encode_device"):
+            return self._encrypt_device(data, public_key, lvl)
         data = np.asarray(data)
         rows = data.reshape(1, -1) if data.ndim <= 1 else data
         bt = rows.shape[0]
-        lvl = P.max_level if level is None else int(level)
-        nq = lvl + 1
         coeffs = np.stack([encoding.encode_i64(r, P.scale(lvl), P.log_n) for r in rows])
         m = be.from_i64(coeffs, nq, False)
         v = be.from_i64(self._sample_ternary(bt), nq, False)
@@ -328,6 +333,52 @@ class Engine:
         c = be.add(vb, be.concat([be.add(e0, m, nq, 0), e1]), nq, 0)
         self._count('encrypt', bt)
         return Ciphertext(self, c, lvl)
+
+    def _encrypt_device(self, data, public_key: PublicKey, lvl: int) -> Ciphertext:
+        """Throughput path: canonical embedding (cuFFT through torch), rounding and the
+        ternary / Gaussian sampling all on the device; one H2D copy of the slot values."""
+        import torch
+        be, P = self.backend, self.params
+        nq = lvl + 1
+        x = data if isinstance(data, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(np.asarray(data, dtype=np.complex128)))
+        x = x.reshape(1, -1) if x.ndim <= 1 else x
+        x = x.to(be.device, non_blocking=True)
+        bt = x.shape[0]
+        if x.shape[1] < self.slot_count:
+            x = torch.nn.functional.pad(x, (0, self.slot_count - x.shape[1]))
+        m = be.from_i64_device(be.encode_device(x, P.scale(lvl)), nq, False)
+        g = self._torch_gen()
+        v = be.from_i64_device(torch.randint(-1, 2, (bt, P.n), generator=g, device=be.device, dtype=torch.int64), nq, False)
+        e = torch.round(torch.randn((2, bt, P.n), generator=g, device=be.device, dtype=torch.float64) * _SIGMA).to(torch.int64)
+        e0 = be.from_i64_device(e[0], nq, False)
+        e1 = be.from_i64_device(e[1], nq, False)
+        pk = public_key.polys if nq == P.n_q else be.take_limbs(public_key.polys, nq, False)
+        vb = be.mul(pk, v, nq, 0)
+        c = be.add(vb, be.concat([be.add(e0, m, nq, 0), e1]), nq, 0)
+        self._count('encrypt', bt)
+        return Ciphertext(self, c, lvl)
+
+    def _torch_gen(self):
+        g = getattr(self, "_tgen", None)
+        if g is None:
+            import torch
+            g = torch.Generator(device=self.backend.device)
+            g.manual_seed(int(self._rng.integers(0, 2 ** 62)))
+            self._tgen = g
+        return g
+
+    def decrypt_device(self, ct: Ciphertext, sk: SecretKey):
+        """Slots as a complex128 torch tensor [batch, slot_count] on the device."""
+        be = self.backend
+        use = min(2, ct.level + 1)
+        c = be.take_limbs(ct.polys, use, False)
+        s = be.take_limbs(sk.ntt, use, False)
+        acc = be.add(be.select_poly(c, 0), be.mul(be.select_poly(c, 1), s, use, 0), use, 0)
+        if ct.npoly == 3:
+            acc = be.add(acc, be.mul(be.select_poly(c, 2), be.mul(s, s, use, 0), use, 0), use, 0)
+        acc = be.intt(acc, use, 0)
+        self._count('decrypt', ct.batch)
+        return be.decode_device(acc, use, self.params.scale(ct.level))
 
     def decrypt_to_plaintext_coeffs(self, ct: Ciphertext, sk: SecretKey) -> np.ndarray:
         """Centred coefficient vectors (float64 [batch, N]) of c0 + c1 s (+ c2 s^2)."""
@@ -343,6 +394,9 @@ class Engine:
         return be.crt_centered(acc, use)
 
     def decrypt(self, ct: Ciphertext, sk: SecretKey) -> np.ndarray:
+        if self.device_codec and hasattr(self.backend, "decode_device"):
+            out = self.decrypt_device(ct, sk).cpu().numpy()
+            return out[0] if out.shape[0] == 1 else out
         m = self.decrypt_to_plaintext_coeffs(ct, sk)
         self._count('decrypt', m.shape[0])
         scale = self.params.scale(ct.level)

@@ -133,6 +133,47 @@ def cpu_arm(threads: int = 0):
                       f"on {be.threads} threads (oracle/refmod.cpp)"}, full
 
 
+def full_round_probe(batch: int):
+    """configs[3]: AddRoundKey_0 + one full AES round (SubBytes, ShiftRows, MixColumns,
+    AddRoundKey) on `batch` ciphertexts of 2048 blocks at N = 2^16, L = 30; FIPS-197 App. B is
+    block 0 and the decoded bytes of every block are checked against plain AES."""
+    import torch
+    from aes_fhe_b200.params import make_params
+    from aes_fhe_b200.services.aes_round import AESRoundService
+    from aes_fhe_b200.services.key_expansion import expand_key
+    from aes_fhe_b200.services.xor_service import XORService, EngineWrapper, XORConfig, CoefficientCache
+    from oracle import aes_plain as A
+    cfg = XORConfig()
+    w = EngineWrapper(cfg, _engine_kwargs=dict(_params=make_params(LOG_N, 30), seed=2), rotation_steps=[])
+    svc = AESRoundService(w, XORService(w, CoefficientCache(cfg.coeffs_path)))
+    key = bytes.fromhex("2b7e151628aed2a6abf7158809cf4f3c")
+    rks = expand_key(key)
+    rng = np.random.default_rng(7)
+    blocks = [rng.integers(0, 256, (svc.B, 16), dtype=np.uint8) for _ in range(batch)]
+    blocks[0][0] = np.frombuffer(bytes.fromhex("3243f6a8885a308d313198a2e0370734"), np.uint8)
+    st = svc.encrypt_state(blocks)
+    k0, k1 = svc.encrypt_round_key(rks[0]), svc.encrypt_round_key(rks[1])
+
+    def one():
+        return svc.round(svc.add_round_key(st, k0), k1)
+
+    r1 = one()                                     # warm-up: builds rotation keys, LUT tables
+    torch.cuda.synchronize()
+    c0 = dict(w.engine.op_counts)
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record(); r1 = one(); b.record()
+    torch.cuda.synchronize()
+    ms = a.elapsed_time(b)
+    ks = sum(v - c0.get(k, 0) for k, v in w.engine.op_counts.items() if k.startswith("keyswitch"))
+    got = svc.decrypt_state(r1)
+    ok = np.array_equal(got, A.round_fn(np.stack(blocks) ^ rks[0], rks[1]))
+    fips = got.reshape(-1, 16)[0].tobytes().hex() == "a49c7ff2689f352b6b5bea43026a5049"
+    nblk = batch * svc.B
+    return {"workload": "configs[3]: AddRoundKey_0 + full round 1, N=2^16, L=30", "batch": batch, "ms": ms,
+            "blocks_per_s": nblk / (ms * 1e-3), "keyswitches_per_ciphertext_pair": int(ks),
+            "levels_used": 30 - r1[0].level, "bytes_equal_plain_aes": bool(ok), "fips197_appendix_b_round2_input": bool(fips)}
+
+
 # --------------------------------------------------------------------------- main
 def main():
     ap = argparse.ArgumentParser()
@@ -142,6 +183,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=4, help="ciphertexts per GPU per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-full-round", action="store_true",
+                    help="skip the extra measurement of one full AES round (configs[3])")
     ap.add_argument("--reference-order", action="store_true",
                     help="also time the reference's own 255-key-switch operation order")
     args = ap.parse_args()
@@ -202,11 +245,15 @@ def main():
     def step():
         return svc.sub_bytes_array_bsgs(ct_in)
 
+    pinned = torch.from_numpy(zeta).pin_memory()             # host input buffer of the user
+
     def e2e_step():
-        pinned = torch.from_numpy(np.ascontiguousarray(zeta.view(np.float64))).pin_memory()
-        z = pinned.numpy().view(np.complex128)
-        out = svc.sub_bytes_array_bsgs(eng.encrypt(z, ctx.public_key))
-        dec = eng.decrypt(out, ctx.secret_key)
+        eng.device_codec = True                                  # encode / sample / decode on the GPU
+        try:
+            out = svc.sub_bytes_array_bsgs(eng.encrypt(pinned, ctx.public_key))      # H2D inside
+            dec = eng.decrypt(out, ctx.secret_key)                                   # D2H inside
+        finally:
+            eng.device_codec = False
         return ZetaEncoder.from_zeta(dec, 256)
 
     def sync_all():
@@ -291,14 +338,19 @@ def main():
                 "vs_baseline": None, "dtype": "f64-exact-int", "data": "synthetic", "config": config,
                 "clocks": clocks, "gpu_launches": int(launches),
                 "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms,
-                        "h2d_bytes_per_step": int(4 * args.batch * P.n * 8),
-                        "d2h_bytes_per_step": int(args.batch * P.n * 8)},
+                        "h2d_bytes_per_step": int(zeta.nbytes),
+                        "d2h_bytes_per_step": int(zeta.nbytes)},
                 "roofline": {"bound": "hbm", "kernel": "ntt_fwd (pass A + pass B)", "rows_per_launch": rows,
                              "achieved": achieved, "peak": peak, "peak_kind": peak_kind, "unit": "GB/s",
                              "frac": achieved / peak, "traffic": traffic,
                              "note": "compute-bound on the FP64 pipe, see profiles/"},
                 "ms_per_ciphertext": ms / args.batch,
                 "keyswitches_per_ciphertext": 32}
+        if not args.no_full_round and world == 1:
+            try:
+                line["full_round"] = full_round_probe(min(args.batch, 4))
+            except Exception as e:  # pragma: no cover
+                line["full_round"] = {"unavailable": repr(e)}
         if args.reference_order:
             torch.cuda.synchronize()
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
