@@ -193,11 +193,48 @@ class XORService:
         enc_b = self.eng_wrap.encrypt(ZetaEncoder.to_zeta(b_int))
         return ZetaEncoder.from_zeta(self.eng_wrap.decrypt(self.xor_cipher(enc_a, enc_b)))
 
+    # -- byte <-> nibble bridge.  The reference's versions (xor_service.py:256-269,
+    #    :434-547) depend on nibble_{hi,lo}_coeffs.json, which decode wrongly for 240 of 256 inputs
+    #    (defect D5), and raise zeta_16^hi to the 16th power (= 1).  Same names and argument
+    #    meaning, LUTs regenerated from the definition:
+    #       zeta_256^x -> zeta_16^(x>>4)   degree-255 LUT (Paterson-Stockmeyer)
+    #       zeta_256^x -> zeta_16^(x&15)   = (zeta_256^x)^16, no LUT needed
+    #       zeta_16^lo -> zeta_256^lo      degree-15 LUT;  zeta_256^(16 hi) = zeta_16^hi as is
+    def extract_nibbles(self, enc_vec):
+        from ..fused import poly_eval_bsgs
+        eng = self.eng_wrap
+        x = np.arange(256)
+        hi = poly_eval_bsgs(eng.engine, eng.relin_key, enc_vec, [lut.lut_coeffs_1d(x >> 4, 256, 16)], baby=16,
+                            cache_key="nib_hi")[0]
+        lo = eng.make_power_basis(enc_vec, 16)[15]
+        return hi, lo
+
     def recombine_nibbles(self, hi_ct, lo_ct):
-        """zeta_16^hi, zeta_16^lo -> zeta_256^(16 hi + lo)?  The reference raises the hi
-        ciphertext to the 16th power and multiplies (xor_service.py:256-269); kept as is."""
-        hi16 = self.eng_wrap.make_power_basis(hi_ct, 16)[15]
-        return self.eng_wrap.multiply(hi16, lo_ct)
+        """zeta_16^hi, zeta_16^lo -> zeta_256^(16 hi + lo)"""
+        from ..fused import poly_eval_bsgs
+        eng = self.eng_wrap
+        lo256 = poly_eval_bsgs(eng.engine, eng.relin_key, lo_ct, [lut.lut_coeffs_1d(np.arange(16), 16, 256)],
+                               baby=4, cache_key="nib_lo_up")[0]
+        return eng.multiply(hi_ct, lo256, eng.relin_key)
+
+    def add_round_key(self, enc_state, round_key: np.ndarray):
+        """Byte-domain AddRoundKey on a zeta_256 state (xor_service.py:499-547): encrypt the key,
+        split both into nibbles, XOR per nibble, recombine.  (The reference's debug decryptions
+        in the middle of this function are not reproduced.)"""
+        eng = self.eng_wrap
+        zrk = ZetaEncoder.to_zeta(np.asarray(round_key), modulus=256)
+        sc = eng.engine.slot_count
+        if zrk.shape[-1] < sc:
+            pad = [(0, 0)] * (zrk.ndim - 1) + [(0, sc - zrk.shape[-1])]
+            zrk = np.pad(zrk, pad, constant_values=1.0)
+        enc_key = eng.encrypt(zrk)
+        s_hi, s_lo = self.extract_nibbles(enc_state)
+        k_hi, k_lo = self.extract_nibbles(enc_key)
+        return self.recombine_nibbles(self.xor_cipher_fused(s_hi, k_hi), self.xor_cipher_fused(s_lo, k_lo))
+
+    def add_round_key_full(self, enc_state, round_key: np.ndarray):
+        enc_key = self.eng_wrap.encrypt(ZetaEncoder.to_zeta(np.asarray(round_key), modulus=256))
+        return self.xor_cipher_full(enc_state, enc_key)
 
     def xor_cipher_full(self, enc_a, enc_b):
         """8-bit XOR through the 256x256 LUT (xor_service.py:288-307)."""

@@ -1,0 +1,136 @@
+"""Operation-sequence parity (level A): a service evaluated on the real
+engine (CPU oracle backend here, B200 in the gpu tests) must give the slot values the same
+service gives on the plain-complex PlainEngine, within the CKKS bound; and the mirrors must do
+what the reference files do when both run on PlainEngine."""
+import sys
+import types
+
+import numpy as np
+import pytest
+
+from aes_fhe_b200 import compat
+from aes_fhe_b200.params import make_params
+from aes_fhe_b200.services import lut
+from aes_fhe_b200.services.xor_service import (XORService, EngineWrapper, XORConfig, CoefficientCache, ZetaEncoder)
+from conftest import REFERENCE
+from oracle import plain_engine
+
+
+def _wrap(P, backend, steps=()):
+    cfg = XORConfig()
+    w = EngineWrapper(cfg, _engine_kwargs=dict(_params=P, _backend=backend, seed=21), rotation_steps=list(steps))
+    return w, XORService(w, CoefficientCache(cfg.coeffs_path))
+
+
+def test_byte_nibble_bridge_and_byte_domain_add_round_key(ref_backend_cls):
+    P = make_params(12, 24)
+    w, xs = _wrap(P, ref_backend_cls(P))
+    sc = w.engine.slot_count
+    rng = np.random.default_rng(4)
+    x = rng.integers(0, 256, sc, dtype=np.uint8)
+    x[:256] = np.arange(256)
+    ct = w.encrypt(ZetaEncoder.to_zeta(x, 256))
+    hi, lo = xs.extract_nibbles(ct)
+    assert np.array_equal(ZetaEncoder.from_zeta(w.decrypt(hi)), x >> 4)
+    assert np.array_equal(ZetaEncoder.from_zeta(w.decrypt(lo)), x & 15)
+    back = xs.recombine_nibbles(hi, lo)
+    assert np.array_equal(ZetaEncoder.from_zeta(w.decrypt(back), 256), x)
+    key = rng.integers(0, 256, sc, dtype=np.uint8)
+    out = xs.add_round_key(ct, key)                       # test_add_round_key_simd scenario
+    assert np.array_equal(ZetaEncoder.from_zeta(w.decrypt(out), 256), x ^ key)
+
+
+def test_gf_service_mul2_mul3(ref_backend_cls):
+    from aes_fhe_b200.services.gf_service import GFService, gf_tables
+    P = make_params(12, 12)
+    w, xs = _wrap(P, ref_backend_cls(P))
+    gf = GFService(w, xs)
+    sc = w.engine.slot_count
+    x = np.tile(np.arange(256, dtype=np.uint8), sc // 256 + 1)[:sc]
+    ct = w.encrypt(ZetaEncoder.to_zeta(x, 256))
+    t2, t3 = gf_tables()
+    for fn, tab in ((gf.mul2_bsgs, t2), (gf.mul3_bsgs, t3)):
+        hi, lo = fn(ct)
+        assert np.array_equal(ZetaEncoder.from_zeta(w.decrypt(hi)), tab[x] >> 4)
+        assert np.array_equal(ZetaEncoder.from_zeta(w.decrypt(lo), 256), tab[x] & 15)
+    # reference operation order (make_power_basis(255) + 255 constant products) on 2S hi
+    hi_ref = gf._eval_1d_lut(ct, gf._plain("coeffs2_hi"))
+    assert np.array_equal(ZetaEncoder.from_zeta(w.decrypt(hi_ref)), t2[x] >> 4)
+
+
+def test_packed_shiftrows_is_exact_and_16slot_form_matches_plain(ref_backend_cls):
+    from aes_fhe_b200.services.shiftrows_service import AESFHEShiftRows
+    from oracle import aes_plain as A
+    P = make_params(12, 4)
+    B = P.slot_count // 16
+    steps = [s * B for s in (4, 8, 12, -4, -8, -12)] + [4, 8, 12, -4, -8, -12]
+    w, xs = _wrap(P, ref_backend_cls(P), steps=steps)
+    rng = np.random.default_rng(9)
+    blocks = rng.integers(0, 16, (B, 16), dtype=np.uint8)
+    flat = blocks.T.reshape(-1)                                        # slot = byte*B + block
+    packed = AESFHEShiftRows(w, xs, packed=True)
+    ct = w.encrypt(ZetaEncoder.to_zeta(flat))
+    out = ZetaEncoder.from_zeta(w.decrypt(packed.shift_rows(ct))).reshape(16, B).T
+    assert np.array_equal(out, A.shift_rows(blocks))
+    inv = ZetaEncoder.from_zeta(w.decrypt(packed.inverse_shift_rows(packed.shift_rows(ct)))).reshape(16, B).T
+    assert np.array_equal(inv, blocks)
+    # the reference's 16-slot form: same arithmetic as a plain-complex evaluation
+    plain = AESFHEShiftRows(_plain_wrapper(P.slot_count), None)
+    real = AESFHEShiftRows(w, xs)
+    v = ZetaEncoder.to_zeta(np.arange(16, dtype=np.uint8))
+    want = plain.eng.decrypt(plain.shift_rows(plain.eng.encrypt(v)))
+    got = w.decrypt(real.shift_rows(w.encrypt(v)))
+    assert np.abs(got - want).max() < 1e-5
+
+
+def _plain_wrapper(slot_count, max_level=30):
+    """An EngineWrapper-shaped object over PlainEngine."""
+    from aes_fhe_b200.services.xor_service import EngineWrapper
+    from aes_fhe_b200.engine import Ciphertext
+    eng = plain_engine.Engine(slot_count=slot_count, max_level=max_level)
+    w = EngineWrapper.__new__(EngineWrapper)
+    w.engine = eng
+    w.public_key, w.secret_key, w.relin_key = "pk", "sk", "rlk"
+    w.conj_key, w.rot_key, w.boot_key = "cjk", "rot", "bk"
+    w.multiply = types.MethodType(
+        lambda self, a, b, relin_key=None: self.engine.multiply(a, b, (relin_key or self.relin_key)
+                                                                if isinstance(a, plain_engine.Ciphertext) and isinstance(b, plain_engine.Ciphertext) else None), w)
+    return w
+
+
+def test_mixrow_operation_sequence_on_plain_engine_matches_reference():
+    """MixRow.merged_shift_mix_fhe (config 3's named function) needs ~43 levels; on PlainEngine
+    the mirror must reproduce the reference file's slots exactly."""
+    from aes_fhe_b200.services.shift_mix_zeta import MixRow
+    w = _plain_wrapper(32768)
+    xs = XORService(w, CoefficientCache(XORConfig().coeffs_path))
+    state = np.random.default_rng(2025).integers(0, 256, (4, 4), dtype=np.uint8)   # test_shift_mix_fhe.py:96-97
+    mine = MixRow(xs, w).merged_shift_mix_fhe(state)
+    assert w.engine.op_counts["bootstrap"] >= 1
+    if not REFERENCE.exists():
+        pytest.skip("reference tree not mounted")
+    m = types.ModuleType("desilofhe")
+    m.Engine, m.Ciphertext, m.Plaintext = plain_engine.Engine, plain_engine.Ciphertext, plain_engine.Plaintext
+    saved = {k: sys.modules.get(k) for k in list(sys.modules) if k == "desilofhe" or k.startswith("aes_xor_fhe")}
+    for k in list(saved):
+        sys.modules.pop(k, None)
+    sys.modules["desilofhe"] = m
+    try:
+        compat.mount_reference(REFERENCE)
+        import importlib
+        rxs = importlib.import_module("aes_xor_fhe.xor_service")
+        rmz = importlib.import_module("aes_xor_fhe.shift_mix_zeta")
+        rw = rxs.EngineWrapper.__new__(rxs.EngineWrapper)
+        rw.engine = plain_engine.Engine(slot_count=32768, max_level=30)
+        rw.public_key, rw.secret_key, rw.relin_key = "pk", "sk", "rlk"
+        rw.conj_key, rw.rot_key, rw.boot_key = "cjk", "rot", "bk"
+        rsvc = rxs.XORService(rw, rxs.CoefficientCache(REFERENCE / "xor_mono_coeffs.json"))
+        theirs = rmz.MixRow(rsvc, rw).merged_shift_mix_fhe(state)
+        assert np.abs(mine.v - theirs.v).max() < 1e-9
+        assert rw.engine.op_counts == w.engine.op_counts
+    finally:
+        for k in [k for k in sys.modules if k == "desilofhe" or k.startswith("aes_xor_fhe")]:
+            sys.modules.pop(k, None)
+        for k, v in saved.items():
+            if v is not None:
+                sys.modules[k] = v
