@@ -34,6 +34,7 @@ SIGNATURES = {
     "fhe_lincomb": [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I],
     "fhe_tensor_acc": [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I],
     "fhe_rescale": [_P, _P, _P, _P, _I, _I],
+    "fhe_mod_raise": [_P, _P, _P, _P, _I, _I],
     "fhe_automorphism": [_P, _P, _P, _P, _U64, _I],
     "fhe_keyswitch": [_P, _P, _P, _P, _P, _I, _I],
     "fhe_modup": [_P, _P, _P, _P, _I, _I],

@@ -105,6 +105,20 @@ class CudaBackend:
     def stack(self, hs: List):
         return torch.stack(hs, dim=0)
 
+    def concat_batch(self, hs: List):
+        return torch.cat(hs, dim=1)
+
+    def split_batch(self, h, sizes: Sequence[int]):
+        return [x.contiguous() for x in torch.split(h, list(sizes), dim=1)]
+
+    def mod_raise(self, h, nq_out: int):
+        """[p, B, 1, N] at level 0 (NTT) -> [p, B, nq_out, N]: centred lift of the coefficients
+        from q_0 to the first nq_out moduli (the overflow polynomial q_0 * I comes with it)."""
+        h = h.contiguous()
+        out = self._empty(h.shape[0], h.shape[1], nq_out, self.n)
+        self._call("fhe_mod_raise", self._ptr(out), self._ptr(h), h.shape[0] * h.shape[1], nq_out)
+        return out
+
     def expand_batch(self, h, batch: int):
         return h if h.shape[1] == batch else h.expand(-1, batch, -1, -1).contiguous()
 

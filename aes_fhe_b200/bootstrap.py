@@ -1,0 +1,260 @@
+"""CKKS bootstrapping for the full-slot ring (row f-1 of SURVEY.md section 8; the reference
+calls ``engine.bootstrap(ct, rlk, conj_key, boot_key)`` from xor_service.py:120-129, :274-277
+and mixcolumns_service.py:72-75).
+
+Pipeline (Cheon-Han-Kim-Kim-Song 2018, Han-Ki 2020 double-angle variant):
+
+  0. bring the ciphertext to level 0 with the message scaled so that q_0 / |m| >= 32
+  1. ModRaise (``fhe_mod_raise``): plaintext becomes m + q_0 * I, |I| <= K (sparse secret)
+  2. CoeffToSlot: the inverse special FFT as `groups` BSGS linear transforms; slots then hold
+     the coefficients (a_k + i b_k) / (2 K_n) in bit-reversed order (never undone: EvalMod is
+     slot-wise and SlotToCoeff consumes the same order)
+  3. real / imaginary parts via one conjugation (multiplication by -i is the monomial
+     X^(N/2): free), stacked on the batch axis so EvalMod runs once
+  4. EvalMod: alpha_0 cos(2 pi (K_n y - 1/4) / 2^r) by a degree-22 polynomial (Paterson-
+     Stockmeyer), then r double-angle steps c <- c^2 - alpha_{i+1}; the constants alpha_i fold
+     the factor rho / 2 pi so the result is the message coefficient itself
+  5. SlotToCoeff: the forward special FFT, `groups` BSGS linear transforms.
+
+Only the first CoeffToSlot matrix sees a non-standard scale (the raised ciphertext has scale
+q_0); its plaintext diagonals are encoded at Delta_{L-1} q_L / q_0 so that everything
+afterwards sits on the engine's per-level scales.  Depth: 1 + groups + 6 + r + groups
+(= 19 for groups = 3, r = 6).
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Tuple
+
+import numpy as np
+from numpy.polynomial import chebyshev as _cheb
+
+from .engine import BootstrapKey, Ciphertext, FixedRotationKey, Plaintext
+
+RHO_TARGET = 32.0         # q_0 / (scaled message): the message is divided by RHO_TARGET * Delta_0 / q_0
+K_NORM = 33               # |I| <= 32 for hamming weight <= 192 (8 sigma)
+DOUBLE_ANGLES = 6
+POLY_DEGREE = 22
+
+
+# --------------------------------------------------------------------------- matrices
+def _fft_layers(n: int):
+    """Butterfly layers of the special FFT U[j,k] = zeta_j^k (zeta_j = xi^(5^j), xi a primitive
+    4n-th root): U = L_last ... L_1 BitRev.  A layer is {rotation d: diagonal}, meaning
+    out[p] = sum_d diag_d[p] * in[(p + d) % n]."""
+    M = 4 * n
+    rot = [pow(5, j, M) for j in range(n)]
+    ksi = np.exp(2j * np.pi * np.arange(M) / M)
+    layers, inv_layers = [], []
+    ln = 2
+    while ln <= n:
+        lenh, lenq = ln // 2, ln * 4
+        j = np.arange(lenh)
+        w = ksi[(np.array(rot[:lenh]) % lenq) * (M // lenq)]
+        first = (np.arange(n) % ln) < lenh
+        wfull = np.tile(np.concatenate([w, w]), n // ln)
+        d0 = np.where(first, 1.0, -wfull).astype(np.complex128)
+        dp = np.where(first, wfull, 0.0).astype(np.complex128)
+        dm = np.where(first, 0.0, 1.0).astype(np.complex128)
+        i0 = np.where(first, 0.5, -0.5 / wfull).astype(np.complex128)
+        ip = np.where(first, 0.5, 0.0).astype(np.complex128)
+        im = np.where(first, 0.0, 0.5 / wfull).astype(np.complex128)
+        if lenh == n - lenh:
+            layers.append({0: d0, lenh: dp + dm})
+            inv_layers.append({0: i0, lenh: ip + im})
+        else:
+            layers.append({0: d0, lenh: dp, n - lenh: dm})
+            inv_layers.append({0: i0, lenh: ip, n - lenh: im})
+        ln *= 2
+    return layers, inv_layers
+
+
+def _mat_mul(A: Dict[int, np.ndarray], B: Dict[int, np.ndarray], n: int) -> Dict[int, np.ndarray]:
+    """A * B (B applied first) in diagonal form."""
+    C: Dict[int, np.ndarray] = {}
+    for a, va in A.items():
+        for b, vb in B.items():
+            d = (a + b) % n
+            t = va * np.roll(vb, -a)
+            C[d] = C[d] + t if d in C else t
+    return {d: v for d, v in C.items() if np.abs(v).max() > 1e-15}
+
+
+def _group(mats: List[Dict[int, np.ndarray]], groups: int, n: int) -> List[Dict[int, np.ndarray]]:
+    """mats are applied in list order; merge them into `groups` consecutive products."""
+    k = len(mats)
+    groups = min(groups, k)
+    sizes = [k // groups + (1 if i < k % groups else 0) for i in range(groups)]
+    out, pos = [], 0
+    for s in sizes:
+        G = mats[pos]
+        for m in mats[pos + 1:pos + s]:
+            G = _mat_mul(m, G, n)
+        out.append(G)
+        pos += s
+    return out
+
+
+def _bsgs_split(rots: List[int], n: int):
+    """d = g + b with b in [0, bm): returns (bm, {g: [(b, d), ...]})."""
+    nz = [d for d in rots if d]
+    stride = n
+    for d in nz:
+        stride = np.gcd(stride, d)
+    stride = int(stride) if nz else 1
+    n1 = 1
+    while n1 * n1 < len(rots):
+        n1 *= 2
+    bm = stride * n1
+    plan: Dict[int, List[Tuple[int, int]]] = {}
+    for d in rots:
+        b = d % bm
+        plan.setdefault((d - b) % n, []).append((b, d))
+    return bm, plan
+
+
+def _evalmod_design(rho: float):
+    """monomial coefficients of alpha_0 cos(2 pi (K_n y - 1/4) / 2^r) on y in [-1, 1] and the
+    constants alpha_1..alpha_r of the double-angle steps c <- c^2 - alpha."""
+    r = DOUBLE_ANGLES
+    A = 2 * np.pi * K_NORM / 2 ** r
+    phi = 2 * np.pi * 0.25 / 2 ** r
+    alphas = [rho / (2 * np.pi)]
+    for _ in range(r):
+        alphas.append(np.sqrt(2 * alphas[-1]))
+    alphas = alphas[::-1]                       # alphas[0] scales the base polynomial
+    cheb = _cheb.chebinterpolate(lambda y: alphas[0] * np.cos(A * y - phi), POLY_DEGREE)
+    return _cheb.cheb2poly(cheb), alphas
+
+
+# --------------------------------------------------------------------------- key
+class _Plan:
+    pass
+
+
+def make_bootstrap_key(engine, sk, groups: int = 3) -> BootstrapKey:
+    """Lazy: the (large) set of Galois keys and encoded matrices is built on first use.  The
+    key object keeps a reference to the secret key for that purpose, like the reference's
+    EngineContext keeps every key in one process (engine_context.py:62-73)."""
+    bk = BootstrapKey(small=False)
+    bk._sk = sk
+    bk._groups = groups
+    return bk
+
+
+def _materialise(engine, bk: BootstrapKey):
+    if bk.plan is not None:
+        return bk.plan
+    P = engine.params
+    n = engine.slot_count
+    L = P.max_level
+    groups = bk._groups
+    depth = 1 + groups + 6 + DOUBLE_ANGLES + groups        # extra rescale of the first matrix + the rest
+    if L < depth + 1:
+        raise RuntimeError(f"bootstrapping needs max_level >= {depth + 1}, engine has {L}")
+    layers, inv_layers = _fft_layers(n)
+    # CoeffToSlot: L_1^-1 ... L_last^-1 with L_last^-1 applied first; fold 1 / (2 K_n)
+    cts = _group(list(reversed(inv_layers)), groups, n)
+    cts[0] = {d: v / (2.0 * K_NORM) for d, v in cts[0].items()}
+    stc = _group(layers, groups, n)
+    plan = _Plan()
+    plan.depth = depth
+    plan.rot_keys: Dict[int, FixedRotationKey] = {}
+    plan.cts, plan.stc = [], []
+
+    def prepare(mat, scale_fn=None):
+        bm, split = _bsgs_split(sorted(mat), n)
+        entry = dict(bm=bm, giants={})
+        for g, items in split.items():
+            lst = []
+            for b, d in items:
+                # inner sum is rotated by g afterwards, so the diagonal is pre-rotated the other way
+                lst.append((b, Plaintext(engine, np.roll(mat[d], g), scale_fn=scale_fn)))
+                if b and b not in plan.rot_keys:
+                    plan.rot_keys[b] = engine.create_fixed_rotation_key(bk._sk, -b)
+            entry["giants"][g] = lst
+            if g and g not in plan.rot_keys:
+                plan.rot_keys[g] = engine.create_fixed_rotation_key(bk._sk, -g)
+        return entry
+
+    # first matrix: two rescales, plaintext scale ~ Delta * q / q_0 * q: rounding of the diagonals
+    # must be far below 2^-40 because the raised ciphertext's slots are ~ sqrt(n) * |I| large
+    first_scale = lambda lvl: P.delta[lvl - 2] * P.moduli[lvl] * P.moduli[lvl - 1] / P.moduli[0]      # noqa: E731
+    for gi, m in enumerate(cts):
+        plan.cts.append(prepare(m, first_scale if gi == 0 else None))
+    for m in stc:
+        plan.stc.append(prepare(m))
+    plan.shift = max(1.0, RHO_TARGET * float(P.delta[0]) / P.moduli[0])        # message divisor
+    plan.rho = plan.shift * float(P.moduli[0] / P.delta[0])
+    plan.poly, plan.alphas = _evalmod_design(plan.rho)
+    bk.plan = plan
+    return plan
+
+
+# --------------------------------------------------------------------------- evaluation
+def _linear_transform(engine, ct: Ciphertext, entry) -> Ciphertext:
+    """sum_d diag_d (.) roll(x, -d) with baby-step / giant-step rotations; one level."""
+    plan_keys = entry["_keys"]
+    babies: Dict[int, Ciphertext] = {0: ct}
+    out = None
+    for g, items in entry["giants"].items():
+        cts, pts = [], []
+        for b, pt in items:
+            if b not in babies:
+                babies[b] = engine.rotate(ct, plan_keys[b])
+            cts.append(babies[b])
+            pts.append(pt)
+        inner = engine.multiply_plain_sum(cts, pts)
+        if g:
+            inner = engine.rotate(inner, plan_keys[g])
+        out = inner if out is None else engine.add(out, inner)
+    return out
+
+
+def bootstrap(engine, ct: Ciphertext, relin_key, conj_key, boot_key: BootstrapKey) -> Ciphertext:
+    if getattr(boot_key, "small", False) or not hasattr(boot_key, "_sk"):
+        raise RuntimeError("bootstrap needs the key from create_bootstrap_key")
+    if ct.npoly != 2:
+        raise RuntimeError("bootstrap: ciphertext must have 2 polynomials")
+    plan = _materialise(engine, boot_key)
+    for e in plan.cts + plan.stc:
+        e["_keys"] = plan.rot_keys
+    be, P = engine.backend, engine.params
+    L = P.max_level
+    engine._count("bootstrap")
+
+    # 0. level 0, message / 2^5
+    if ct.level == 0:
+        raise RuntimeError("bootstrap: call before the ciphertext reaches level 0")
+    x = ct if ct.level == 1 else Ciphertext(engine, be.take_limbs(ct.polys, 2, False), 1)
+    from fractions import Fraction
+    c = P.delta[0] * P.moduli[1] / (P.delta[ct.level] * Fraction(plan.shift))
+    x = engine._rescale(engine._mul_int_const(x, int(round(c)), 0))                  # level 0
+
+    # 1. ModRaise: declared scale q_0, values = eps * msg_coeff + I
+    raised = Ciphertext(engine, be.mod_raise(x.polys, L + 1), L)
+
+    # 2. CoeffToSlot (first matrix absorbs the q_0 scale)
+    t = engine._rescale(_linear_transform(engine, raised, plan.cts[0]))     # second rescale: scale is standard from here
+    for entry in plan.cts[1:]:
+        t = _linear_transform(engine, t, entry)
+
+    # 3. real and imaginary parts, stacked on the batch axis
+    tc = engine.conjugate(t, conj_key)
+    re = engine.add(t, tc)
+    im = engine.multiply_by_i(engine.subtract(t, tc), -1)
+    bt = t.batch
+    y = Ciphertext(engine, be.concat_batch([re.polys, im.polys]), t.level)
+
+    # 4. EvalMod
+    from .fused import poly_eval_bsgs
+    cpoly = poly_eval_bsgs(engine, relin_key, y, [plan.poly], baby=8, cache_key="evalmod")[0]
+    for i in range(DOUBLE_ANGLES):
+        cpoly = engine.add_plain(engine.multiply(cpoly, cpoly, relin_key), -plan.alphas[i + 1])
+    re_p, im_p = be.split_batch(cpoly.polys, [bt, bt])
+    u = engine.add(Ciphertext(engine, re_p, cpoly.level),
+                   engine.multiply_by_i(Ciphertext(engine, im_p, cpoly.level), 1))
+
+    # 5. SlotToCoeff
+    for entry in plan.stc:
+        u = _linear_transform(engine, u, entry)
+    return u

@@ -449,6 +449,28 @@ int fhe_rescale(fhe_ctx* c, void* stream, uint64_t* out, const uint64_t* in, int
     return check("fhe_rescale");
 }
 
+int fhe_mod_raise(fhe_ctx* c, void* stream, uint64_t* out, const uint64_t* in, int npoly, int nq_out) {
+    if (bad_shape(c, nq_out, 0) || npoly < 1) return fail("fhe_mod_raise: bad shape");
+    cudaStream_t s = (cudaStream_t)stream;
+    const int n = c->n;
+    u64* coef = arena(c, (size_t)npoly * n);
+    if (!coef) return fail("fhe_mod_raise: scratch allocation failed");
+    {   // level-0 rows -> coefficient domain
+        RowMap m = make_map(c, 1, 0, 1);
+        LoadPlain ld; ld.src = (const u64*)in; ld.poly_stride = n;
+        StorePlain st; st.dst = coef; st.poly_stride = n;
+        ntt_inverse(c->T, m, npoly, ld, coef, n, st, nullptr, s);
+    }
+    {   // centred lift into every target modulus, fused into the forward transform's load
+        RowMap m = make_map(c, nq_out, 0, nq_out);
+        LoadCentered ld; ld.last = coef; ld.q_last = c->q[0];
+        StorePlain st; st.dst = (u64*)out; st.poly_stride = (long long)nq_out * n;
+        ntt_forward(c->T, m, npoly * nq_out, ld, (u64*)out, (long long)nq_out * n, st, s);
+    }
+    g_launches.fetch_add(4);
+    return check("fhe_mod_raise");
+}
+
 int fhe_automorphism(fhe_ctx* c, void* stream, uint64_t* out, const uint64_t* in, uint64_t galois, int nrows) {
     if (!c || nrows < 1 || !(galois & 1)) return fail("fhe_automorphism: bad arguments");
     launch(k_automorphism, dim3(c->n / 256, nrows), dim3(256), (cudaStream_t)stream, c->log_n, (u64*)out,

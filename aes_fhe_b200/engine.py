@@ -40,8 +40,9 @@ class Plaintext:
     :283-285), so the residues are produced lazily for the level they are used at.
     """
 
-    def __init__(self, engine: "Engine", values: np.ndarray):
+    def __init__(self, engine: "Engine", values: np.ndarray, scale_fn=None):
         self.engine = engine
+        self.scale_fn = scale_fn            # level -> scale override (bootstrapping's first matrix)
         v = np.asarray(values)
         if v.ndim == 0:
             v = v.reshape(1)
@@ -53,8 +54,20 @@ class Plaintext:
         h = self._cache.get(level)
         if h is None:
             eng = self.engine
-            coeffs = encoding.encode_i64(self.values, eng.params.scale(level), eng.params.log_n)
-            h = eng.backend.from_i64(coeffs, level + 1, False)
+            scale = eng.params.scale(level) if self.scale_fn is None else float(self.scale_fn(level))
+            if scale < 2.0 ** 58:
+                coeffs = encoding.encode_i64(self.values, scale, eng.params.log_n)
+                h = eng.backend.from_i64(coeffs, level + 1, False)
+            else:
+                # very high scale (first bootstrapping matrix): coefficient = hi * 2^40 + lo, both
+                # exact in int64, recombined on the residues
+                m = encoding.slots_to_coeffs(self.values, eng.params.log_n) * (scale / 2.0 ** 40)
+                hi = np.floor(m)
+                lo = np.rint((m - hi) * 2.0 ** 40)
+                be, nq = eng.backend, level + 1
+                fac = [(1 << 40) % eng.params.moduli[l] for l in range(nq)]
+                h = be.add(be.mul_scalar(be.from_i64(hi.astype(np.int64), nq, False), fac, nq, 0),
+                           be.from_i64(lo.astype(np.int64), nq, False), nq, 0)
             self._cache[level] = h
         return h
 
@@ -125,10 +138,13 @@ class RotationKey:
 
 
 class BootstrapKey:
-    """Placeholder: bootstrapping is not built yet."""
+    """Bootstrapping key: Galois keys for the rotations of CoeffToSlot / SlotToCoeff plus the
+    encoded matrices (filled by aes_fhe_b200.bootstrap.make_bootstrap_key).  The "small"
+    variant of the reference API (engine_context.py:72) is an empty token."""
 
     def __init__(self, small: bool):
         self.small = small
+        self.plan = None
 
 
 def _naf_steps(delta: int, slot_count: int) -> List[int]:
@@ -156,6 +172,7 @@ class Engine:
                  use_multiparty: bool = False, thread_count: int = 0, device_id: int = 0,
                  max_level: Optional[int] = None, log_coeff_count: Optional[int] = None,
                  special_prime_count: Optional[int] = None, seed: int = 0, device_codec: bool = False,
+                 secret_hamming_weight: Optional[int] = None, scale_bits: Optional[int] = None,
                  _backend=None, _params: Optional[CKKSParams] = None):
         args = list(args)
         # positional forms: Engine(mode) | Engine(max_level, mode) | Engine(log_n, K, mode)
@@ -191,8 +208,17 @@ class Engine:
             lvl = max(1, min(30, (budget - 60 - 60 * max(k, 1)) // 40))
             params = make_params(log_n, lvl, special_count=k)
         else:
-            params = make_params(16, int(max_level) if max_level is not None else 30)
+            # a bootstrappable engine works at the largest scale the < 2^45 moduli allow: every
+            # operation is 16x more precise, which is what bootstrapping at N = 2^16 needs
+            sb = scale_bits if scale_bits is not None else (44 if use_bootstrap else 40)
+            params = make_params(16, int(max_level) if max_level is not None else 30, scale_bits=sb)
         self.params = params
+        # sparse ternary secret (bootstrappable-CKKS practice, e.g. h = 192 at N = 2^16): bounds the
+        # overflow polynomial of ModRaise and shrinks every rounding-noise term from sqrt(2N/3)
+        # to sqrt(h)
+        if secret_hamming_weight is None:
+            secret_hamming_weight = min(192, params.n // 8)
+        self.secret_hamming_weight = int(secret_hamming_weight)
         self.slot_count = params.slot_count
         self.max_level = params.max_level
 
@@ -236,7 +262,10 @@ class Engine:
 
     # ------------------------------------------------------------------ keys
     def create_secret_key(self) -> SecretKey:
-        s = self._sample_ternary()
+        n, h = self.params.n, self.secret_hamming_weight
+        s = np.zeros((1, n), dtype=np.int64)
+        pos = self._rng.choice(n, size=h, replace=False)
+        s[0, pos] = self._rng.integers(0, 2, size=h, dtype=np.int64) * 2 - 1
         return SecretKey(s, self.backend.from_i64(s, self.params.n_q, True))
 
     def create_public_key(self, sk: SecretKey) -> PublicKey:
@@ -297,12 +326,6 @@ class Engine:
                 steps += [k, -k]
                 k <<= 1
         return RotationKey({int(d): self.create_fixed_rotation_key(sk, int(d)) for d in steps})
-
-    def create_small_bootstrap_key(self, sk: SecretKey) -> BootstrapKey:
-        return BootstrapKey(small=True)
-
-    def create_bootstrap_key(self, sk: SecretKey) -> BootstrapKey:
-        return BootstrapKey(small=False)
 
     # ------------------------------------------------------------------ encode / encrypt / decrypt
     def encode(self, values) -> Plaintext:
@@ -629,7 +652,21 @@ class Engine:
             out = self._apply_galois(out, key)
         return out
 
+    def multiply_by_i(self, ct: Ciphertext, sign: int = 1) -> Ciphertext:
+        """ct * (+-i): multiplication by the monomial +-X^(N/2) -- exact, no level, no rescale."""
+        nq = ct.level + 1
+        cp, cm = self._const_residues(0, 1 if sign >= 0 else -1, nq)
+        return Ciphertext(self, self.backend.mul_const(ct.polys, cp, cm, nq), ct.level, ct.zero)
+
     # ------------------------------------------------------------------ bootstrap
+    def create_bootstrap_key(self, sk: SecretKey):
+        from .bootstrap import make_bootstrap_key
+        return make_bootstrap_key(self, sk)
+
+    def create_small_bootstrap_key(self, sk: SecretKey):
+        return BootstrapKey(small=True)
+
     def bootstrap(self, ct: Ciphertext, relin_key, conj_key, boot_key) -> Ciphertext:
-        raise NotImplementedError(
-            "bootstrapping is row (f)-1 of SURVEY.md section 8 and is not built in this round")
+        """Refresh the level of a ciphertext (xor_service.py:120-129, :274-277)."""
+        from .bootstrap import bootstrap
+        return bootstrap(self, ct, relin_key, conj_key, boot_key)

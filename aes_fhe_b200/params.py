@@ -180,6 +180,8 @@ def make_params(log_n: int = 16, max_level: int = 30, special_count: int = 0,
     """
     if not (10 <= log_n <= 16):
         raise ValueError("log_coeff_count must be in [10, 16]")
+    if not (30 <= scale_bits <= 44):
+        raise ValueError("scale_bits must be in [30, 44] (every modulus has to stay below 2^45)")
     if max_level < 1:
         raise ValueError("max_level must be >= 1")
     n = 1 << log_n
@@ -207,14 +209,20 @@ def make_params(log_n: int = 16, max_level: int = 30, special_count: int = 0,
 
     if special_count <= 0:
         alpha = -(-n_q // max(1, dnum))
-        # largest digit: the one holding q_0
-        digit_bits = BASE_BITS + (alpha - 1) * scale_bits if alpha >= 1 else BASE_BITS
-        special_count = -(-(digit_bits + 1) // (SPECIAL_BITS - 1))
+        # smallest K whose special modulus exceeds the largest digit (the one holding q_0)
+        digit = 1
+        for m in q[:alpha]:
+            digit *= m
+        cand = _primes_below(1 << SPECIAL_BITS, two_n, 48, exclude={q0} | used)
+        special_count, prod = 0, 1
+        while prod <= digit:
+            prod *= cand[special_count]
+            special_count += 1
     else:
         # K given (signature 3): largest alpha whose digit still fits under P
         p_bits = special_count * (SPECIAL_BITS - 1)
         alpha = max(1, min(n_q, 1 + (p_bits - BASE_BITS - 1) // scale_bits))
-    p = _primes_below(1 << SPECIAL_BITS, two_n, special_count, exclude={q0})
+    p = _primes_below(1 << SPECIAL_BITS, two_n, special_count, exclude={q0} | used)
     moduli = tuple(q) + tuple(p)
     psi = tuple(primitive_2n_root(m, two_n) for m in moduli)
     # limit denominators: the exact value is kept, floats are derived on demand

@@ -93,6 +93,11 @@ int fhe_tensor_acc(fhe_ctx* ctx, void* stream, uint64_t* acc, const uint64_t* co
  * rounded to nearest. */
 int fhe_rescale(fhe_ctx* ctx, void* stream, uint64_t* out, const uint64_t* in, int npoly, int nq);
 
+/* Engine.bootstrap, first step (xor_service.py:120-129): ModRaise.  in[npoly][1][N] (level 0)
+ * -> out[npoly][nq_out][N]: the centred representative of every coefficient mod q_0, reduced
+ * into the first nq_out moduli (the plaintext becomes m + q_0 * I with a small integer I). */
+int fhe_mod_raise(fhe_ctx* ctx, void* stream, uint64_t* out, const uint64_t* in, int npoly, int nq_out);
+
 /* Engine.rotate / conjugate permutation part (xor_service.py:89,105): X -> X^galois on
  * `nrows` NTT-domain rows. */
 int fhe_automorphism(fhe_ctx* ctx, void* stream, uint64_t* out, const uint64_t* in,

@@ -99,6 +99,26 @@ class RefBackend:
     def stack(self, hs: List):
         return np.ascontiguousarray(np.stack(hs, axis=0))
 
+    def concat_batch(self, hs: List):
+        return np.ascontiguousarray(np.concatenate(hs, axis=1))
+
+    def split_batch(self, h, sizes: Sequence[int]):
+        out, o = [], 0
+        for s in sizes:
+            out.append(np.ascontiguousarray(h[:, o:o + s]))
+            o += s
+        return out
+
+    def mod_raise(self, h, nq_out: int):
+        coef = self.intt(h, 1, 0)                                   # [p, B, 1, N] coefficients mod q0
+        q0 = self.params.moduli[0]
+        c = coef[:, :, 0, :].astype(np.int64)
+        c = np.where(c > (q0 >> 1), c - q0, c)                      # centred lift
+        out = np.empty(h.shape[:2] + (nq_out, self.n), dtype=np.uint64)
+        for p in range(h.shape[0]):
+            out[p:p + 1] = self.from_i64(c[p], nq_out, False)
+        return out
+
     def expand_batch(self, h, batch: int):
         return h if h.shape[1] == batch else np.ascontiguousarray(np.broadcast_to(h, (h.shape[0], batch) + h.shape[2:]))
 

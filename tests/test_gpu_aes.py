@@ -41,3 +41,49 @@ def test_sbox_reference_order_and_bsgs_full_size(cuda_lib):
         dec = ctx.decrypt(fn(ct))
         assert np.abs(dec - ZetaEncoder.to_zeta(exp, 256)).max() < 1e-3
         assert np.array_equal(ZetaEncoder.from_zeta(dec, 256), exp)
+
+
+def test_bootstrap_full_size(cuda_lib):
+    """Bootstrapping at N = 2^16 (2^15 slots), 44-bit scale, batch of 2 ciphertexts."""
+    import time
+    from aes_fhe_b200.engine import Engine
+    P = make_params(16, 30, scale_bits=44)
+    eng = Engine(_params=P, seed=5)
+    sk = eng.create_secret_key(); pk = eng.create_public_key(sk)
+    rlk = eng.create_relinearization_key(sk); cj = eng.create_conjugation_key(sk)
+    bk = eng.create_bootstrap_key(sk)
+    rng = np.random.default_rng(0)
+    v = np.exp(-2j * np.pi * rng.integers(0, 16, (2, eng.slot_count)) / 16)
+    ct = eng.encrypt(v, pk, level=2)
+    t0 = time.time(); out = eng.bootstrap(ct, rlk, cj, bk); torch.cuda.synchronize(); t_first = time.time() - t0
+    t0 = time.time(); out = eng.bootstrap(ct, rlk, cj, bk); torch.cuda.synchronize(); t_warm = time.time() - t0
+    d = eng.decrypt(out, sk)
+    err = np.abs(d - v).max()
+    print(f"bootstrap N=2^16 batch 2: first {t_first:.1f}s (keys + matrices), warm {t_warm*1e3:.0f} ms, level {out.level}, max err {err:.2e}")
+    assert out.level == 11 and out.batch == 2
+    assert err < 5e-3
+    from aes_fhe_b200.services.xor_service import ZetaEncoder
+    assert np.array_equal(ZetaEncoder.from_zeta(d), ZetaEncoder.from_zeta(v))
+
+
+def test_mixrow_named_function_runs_with_bootstrapping(cuda_lib):
+    """config 3's named function, MixRow.merged_shift_mix_fhe (shift_mix_zeta.py:14-69): 23 XOR
+    LUTs, 24 rotations, bootstraps whenever an operand is below level 8.  Operation-sequence
+    parity: slots must match the plain-complex evaluation of the same sequence."""
+    import types
+    from aes_fhe_b200.services.shift_mix_zeta import MixRow
+    from aes_fhe_b200.services.xor_service import XORService, EngineWrapper, XORConfig, CoefficientCache, ZetaEncoder
+    from test_services_plain_and_oracle import _plain_wrapper
+    cfg = XORConfig()
+    w = EngineWrapper(cfg, _engine_kwargs=dict(seed=3), rotation_steps=[-1, -2, -3, -5, -10, -15])
+    assert w.engine.params.scale_bits == 44 and w.engine.max_level == 30
+    xs = XORService(w, CoefficientCache(cfg.coeffs_path))
+    state = np.random.default_rng(2025).integers(0, 256, (4, 4), dtype=np.uint8)
+    out = MixRow(xs, w).merged_shift_mix_fhe(state)
+    got = w.decrypt(out)[:16]
+    pw = _plain_wrapper(32768)
+    want = MixRow(XORService(pw, CoefficientCache(cfg.coeffs_path)), pw).merged_shift_mix_fhe(state).v[:16]
+    err = np.abs(got - want).max()
+    print("MixRow op counts", w.engine.op_counts, "max slot err vs plain evaluation", err)
+    assert w.engine.op_counts["bootstrap"] >= 4
+    assert np.array_equal(ZetaEncoder.from_zeta(got), ZetaEncoder.from_zeta(want))
