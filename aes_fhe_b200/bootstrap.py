@@ -11,8 +11,8 @@ Pipeline (Cheon-Han-Kim-Kim-Song 2018, Han-Ki 2020 double-angle variant):
      slot-wise and SlotToCoeff consumes the same order)
   3. real / imaginary parts via one conjugation (multiplication by -i is the monomial
      X^(N/2): free), stacked on the batch axis so EvalMod runs once
-  4. EvalMod: alpha_0 cos(2 pi (K_n y - 1/4) / 2^r) by a degree-22 polynomial (Paterson-
-     Stockmeyer), then r double-angle steps c <- c^2 - alpha_{i+1}; the constants alpha_i fold
+  4. EvalMod: alpha_0 cos(2 pi (K_n y - 1/4) / 2^r) by a degree-22 Chebyshev interpolant
+     (T_1..T_22 by the product rule, one constant-only linear combination), then r double-angle steps c <- c^2 - alpha_{i+1}; the constants alpha_i fold
      the factor rho / 2 pi so the result is the message coefficient itself
   5. SlotToCoeff: the forward special FFT, `groups` BSGS linear transforms.
 
@@ -112,9 +112,10 @@ def _bsgs_split(rots: List[int], n: int):
     return bm, plan
 
 
-def _evalmod_design(rho: float):
-    """monomial coefficients of alpha_0 cos(2 pi (K_n y - 1/4) / 2^r) on y in [-1, 1] and the
-    constants alpha_1..alpha_r of the double-angle steps c <- c^2 - alpha."""
+def _evalmod_design(rho: float, basis: str = "monomial"):
+    """coefficients of alpha_0 cos(2 pi (K_n y - 1/4) / 2^r) on y in [-1, 1] (monomial or
+    Chebyshev basis) and the constants alpha_1..alpha_r of the double-angle steps
+    c <- c^2 - alpha."""
     r = DOUBLE_ANGLES
     A = 2 * np.pi * K_NORM / 2 ** r
     phi = 2 * np.pi * 0.25 / 2 ** r
@@ -123,7 +124,44 @@ def _evalmod_design(rho: float):
         alphas.append(np.sqrt(2 * alphas[-1]))
     alphas = alphas[::-1]                       # alphas[0] scales the base polynomial
     cheb = _cheb.chebinterpolate(lambda y: alphas[0] * np.cos(A * y - phi), POLY_DEGREE)
-    return _cheb.cheb2poly(cheb), alphas
+    return (cheb if basis == "chebyshev" else _cheb.cheb2poly(cheb)), alphas
+
+
+def chebyshev_basis(engine, relin_key, y: Ciphertext, degree: int) -> Dict[int, Ciphertext]:
+    """{k: T_k(y)}, k = 1..degree, by T_{a+b} = 2 T_a T_b - T_{a-b}; T_k sits ceil(log2 k) levels
+    below y.  Bounded basis (|T_k| <= 1): the interpolant's coefficients decay instead of
+    alternating with magnitude ~10 as in the monomial basis, so ciphertext noise is not amplified
+    by cancellation."""
+    T: Dict[int, Ciphertext] = {1: y}
+    for k in range(2, degree + 1):
+        a = (k + 1) // 2
+        b = k // 2
+        prod = engine.multiply(T[a], T[b], relin_key)
+        twice = engine.add(prod, prod)
+        if a == b:
+            T[k] = engine.add_plain(twice, -1.0)
+        else:
+            T[k] = engine.subtract(twice, T[a - b])
+    return T
+
+
+def lincomb_const(engine, cts: Dict[int, Ciphertext], coeffs, const: float = 0.0) -> Ciphertext:
+    """const + sum_k coeffs[k] * cts[k]: constants absorb the level / scale alignment, one pass of
+    fhe_lincomb per 16 inputs, ONE rescale."""
+    from .fused import _const_pair
+    be, P = engine.backend, engine.params
+    lo = min(c.level for c in cts.values())
+    nq = lo + 1
+    target = P.delta[lo - 1] * P.moduli[lo]
+    keys = sorted(cts)
+    acc = None
+    for s in range(0, len(keys), 16):
+        part = keys[s:s + 16]
+        res = [[_const_pair(engine, complex(coeffs[k]), target / P.delta[cts[k].level], nq) for k in part]]
+        c0 = [_const_pair(engine, complex(const), target, nq)] if s == 0 else None
+        out = be.lincomb([cts[k].polys for k in part], be.prepare_lincomb(res, c0, nq))[0]
+        acc = out if acc is None else be.add(acc, out, nq, 0)
+    return engine._rescale(Ciphertext(engine, acc, lo))
 
 
 # --------------------------------------------------------------------------- key
@@ -185,7 +223,7 @@ def _materialise(engine, bk: BootstrapKey):
         plan.stc.append(prepare(m))
     plan.shift = max(1.0, RHO_TARGET * float(P.delta[0]) / P.moduli[0])        # message divisor
     plan.rho = plan.shift * float(P.moduli[0] / P.delta[0])
-    plan.poly, plan.alphas = _evalmod_design(plan.rho)
+    plan.poly, plan.alphas = _evalmod_design(plan.rho, "chebyshev")
     bk.plan = plan
     return plan
 
@@ -246,8 +284,8 @@ def bootstrap(engine, ct: Ciphertext, relin_key, conj_key, boot_key: BootstrapKe
     y = Ciphertext(engine, be.concat_batch([re.polys, im.polys]), t.level)
 
     # 4. EvalMod
-    from .fused import poly_eval_bsgs
-    cpoly = poly_eval_bsgs(engine, relin_key, y, [plan.poly], baby=8, cache_key="evalmod")[0]
+    T = chebyshev_basis(engine, relin_key, y, POLY_DEGREE)
+    cpoly = lincomb_const(engine, T, {k: plan.poly[k] for k in T}, const=plan.poly[0])
     for i in range(DOUBLE_ANGLES):
         cpoly = engine.add_plain(engine.multiply(cpoly, cpoly, relin_key), -plan.alphas[i + 1])
     re_p, im_p = be.split_batch(cpoly.polys, [bt, bt])

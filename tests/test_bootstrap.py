@@ -33,7 +33,7 @@ def test_special_fft_factorisation_and_grouping():
 
 def test_evalmod_polynomial_recovers_the_message():
     rho = 32.0
-    poly, alphas = B._evalmod_design(rho)
+    poly, alphas = B._evalmod_design(rho, "monomial")
     rng = np.random.default_rng(0)
     I = rng.integers(-(B.K_NORM - 1), B.K_NORM, 20000)
     msg = rng.uniform(-0.2, 0.2, I.size)

@@ -86,4 +86,7 @@ def test_mixrow_named_function_runs_with_bootstrapping(cuda_lib):
     err = np.abs(got - want).max()
     print("MixRow op counts", w.engine.op_counts, "max slot err vs plain evaluation", err)
     assert w.engine.op_counts["bootstrap"] >= 4
-    assert np.array_equal(ZetaEncoder.from_zeta(got), ZetaEncoder.from_zeta(want))
+    # north_star check 2: decrypted slots within the CKKS bound of the plain-complex evaluation
+    # (the sequence itself collapses to 0 in every slot -- SURVEY defect D8 -- so decoded
+    # integers carry no information here)
+    assert err < 1e-3
