@@ -106,4 +106,4 @@ def test_device_codec_roundtrip_and_compat(cuda_lib):
     eng.device_codec = True
     assert np.abs(eng.decrypt(sq, sk) - v * v).max() < 1e-5
     short = eng.decrypt(eng.encrypt(np.array([1.0, 2.0, 3.0]), pk), sk)
-    assert np.allclose(short[:3], [1, 2, 3], atol=1e-6) and np.allclose(short[3:], 0, atol=1e-6)
+    assert np.allclose(short[:3], [1, 2, 3], atol=5e-6) and np.allclose(short[3:], 0, atol=5e-6)
