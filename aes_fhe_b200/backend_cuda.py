@@ -259,6 +259,14 @@ class CudaBackend:
         self._call("fhe_moddown", self._ptr(out), self._ptr(acc), nq, acc.shape[0] * acc.shape[1])
         return out
 
+    def relin_rescale(self, d3, ksk, nq):
+        """[3,B,nq,N] tensor product -> [2,B,nq-1,N]: relinearise + rescale with one ModDown."""
+        d3 = d3.contiguous()
+        bt = d3.shape[1]
+        out = self._empty(2, bt, nq - 1, self.n)
+        self._call("fhe_relin_rescale", self._ptr(out), self._ptr(d3), self._ptr(ksk), nq, bt)
+        return out
+
     def keyswitch(self, d, ksk, nq):
         d = d.contiguous()
         bt = d.shape[1]

@@ -15,6 +15,7 @@ SOURCES = ["capi.cu"]
 HEADERS = ["compat.h", "modarith.cuh", "ntt.cuh", "kernels.cuh"]
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+              "-DFHE_PASSA_MINB=4", "-DFHE_PASSB_MINB=4",
               "-Xcompiler", "-fPIC", "-shared"]
 
 

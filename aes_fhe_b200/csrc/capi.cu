@@ -63,6 +63,11 @@ struct fhe_ctx {
     std::vector<ConstF*> modup_scale;     // [nq][2] iNTT final constants incl. (Q_j/q_i)^-1
     std::vector<BConvTable*> moddown_table;   // one table
     std::vector<ConstF*> rescale_c;       // [nq-1] q_{nq-1}^-1 mod q_i
+    // merged ModDown + rescale (divide by P * q_{nq-1}): sources = {q_{nq-1}} U P
+    std::vector<BConvTable*> mdrs_table;  // one table, nt = nq-1
+    std::vector<ConstF*> mdrs_scale;      // [K+1][2] iNTT final constants incl. (P q_last / m_k)^-1
+    std::vector<ConstF*> mdrs_inv;        // [nq-1] (P q_last)^-1 mod q_i
+    ConstF* p_mod_q = nullptr;            // [n_q]  P mod q_i
     ConstF* moddown_scale = nullptr;      // [n_p][2]
     ConstF* pinv = nullptr;               // [n_q]  P^-1 mod q_i
     u64 q0inv_mod_q1 = 0;
@@ -134,6 +139,9 @@ void build_level_tables(fhe_ctx* c) {
     c->modup_scale.assign(n_q + 1, nullptr);
     c->moddown_table.assign(n_q + 1, nullptr);
     c->rescale_c.assign(n_q + 1, nullptr);
+    c->mdrs_table.assign(n_q + 1, nullptr);
+    c->mdrs_scale.assign(n_q + 1, nullptr);
+    c->mdrs_inv.assign(n_q + 1, nullptr);
 
     std::vector<u64> ninv(c->tot), w1ninv(c->tot);
     {
@@ -193,6 +201,34 @@ void build_level_tables(fhe_ctx* c) {
             c->moddown_table[nq] = to_device(td);
             c->owned.push_back(c->moddown_table[nq]);
         }
+        if (nq >= 2 && K > 0) {
+            std::vector<int> sids;
+            sids.push_back(nq - 1);
+            for (int k = 0; k < K; ++k) sids.push_back(pids[k]);
+            const int ns = K + 1;
+            std::vector<BConvTable> td(1);
+            BConvTable& tb = td[0];
+            std::memset(&tb, 0, sizeof(tb));
+            tb.ns = ns; tb.nt = nq - 1;
+            std::vector<ConstF> sc(2 * (size_t)ns), inv(nq - 1);
+            for (int k = 0; k < ns; ++k) {
+                tb.src_mod[k] = sids[k]; tb.src_slot[k] = k;
+                const u64 mk = c->q[sids[k]];
+                const u64 iv = h_inv(prod_except(c, sids, k, mk), mk);
+                sc[2 * (size_t)k] = h_shoup(h_mul(ninv[sids[k]], iv, mk), mk);
+                sc[2 * (size_t)k + 1] = h_shoup(h_mul(w1ninv[sids[k]], iv, mk), mk);
+            }
+            for (int i = 0; i < nq - 1; ++i) {
+                const u64 m = c->q[i];
+                tb.dst_mod[i] = i; tb.dst_slot[i] = i;
+                for (int k = 0; k < ns; ++k) tb.f[i][k] = h_shoup(prod_except(c, sids, k, m), m);
+                inv[i] = h_shoup(h_inv(prod_except(c, sids, -1, m), m), m);
+            }
+            c->mdrs_table[nq] = to_device(td);
+            c->mdrs_scale[nq] = to_device(sc);
+            c->mdrs_inv[nq] = to_device(inv);
+            c->owned.push_back(c->mdrs_table[nq]); c->owned.push_back(c->mdrs_scale[nq]); c->owned.push_back(c->mdrs_inv[nq]);
+        }
         if (nq >= 2) {
             std::vector<ConstF> rc(nq - 1);
             const u64 ql = c->q[nq - 1];
@@ -216,6 +252,10 @@ void build_level_tables(fhe_ctx* c) {
         for (int i = 0; i < n_q; ++i) pv[i] = h_shoup(h_inv(prod_except(c, pids, -1, c->q[i]), c->q[i]), c->q[i]);
         c->pinv = to_device(pv);
         c->owned.push_back(c->pinv);
+        std::vector<ConstF> pm(n_q);
+        for (int i = 0; i < n_q; ++i) pm[i] = h_shoup(prod_except(c, pids, -1, c->q[i]), c->q[i]);
+        c->p_mod_q = to_device(pm);
+        c->owned.push_back(c->p_mod_q);
     }
     if (n_q >= 2) c->q0inv_mod_q1 = h_inv(c->q[0] % c->q[1], c->q[1]);
 }
@@ -397,9 +437,12 @@ int fhe_lincomb(fhe_ctx* c, void* stream, uint64_t* out, const uint64_t* const* 
     dim3 grid(c->n / 256, 2 * batch * nq), block(256);
     cudaStream_t s = (cudaStream_t)stream;
     const ConstF* cf = (const ConstF*)consts;
-    if (T <= 4) launch(k_lincomb<4>, grid, block, s, c->T, nq, batch, M, T, li, cf, (const u64*)c0, (u64*)out);
-    else if (T <= 8) launch(k_lincomb<8>, grid, block, s, c->T, nq, batch, M, T, li, cf, (const u64*)c0, (u64*)out);
-    else launch(k_lincomb<16>, grid, block, s, c->T, nq, batch, M, T, li, cf, (const u64*)c0, (u64*)out);
+    const size_t smem = (size_t)M * T * sizeof(ConstF);
+    if (smem > 48 * 1024) return fail("fhe_lincomb: M * T too large for the shared-memory constant tile");
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    if (T <= 4) fhe_launch(k_lincomb<4>, grid, block, smem, s, c->T, nq, batch, M, T, li, cf, (const u64*)c0, (u64*)out);
+    else if (T <= 8) fhe_launch(k_lincomb<8>, grid, block, smem, s, c->T, nq, batch, M, T, li, cf, (const u64*)c0, (u64*)out);
+    else fhe_launch(k_lincomb<16>, grid, block, smem, s, c->T, nq, batch, M, T, li, cf, (const u64*)c0, (u64*)out);
     return check("fhe_lincomb");
 }
 
@@ -506,9 +549,47 @@ int fhe_ks_inner(fhe_ctx* c, void* stream, uint64_t* acc, const uint64_t* ext, c
                  const uint64_t* ksk, int nq, int batch) {
     if (bad_shape(c, nq, 0) || c->n_p == 0 || batch < 1 || c->modup_beta[nq] > FHE_MAX_BETA)
         return fail("fhe_ks_inner: bad shape");
-    launch(k_ks_inner, dim3(c->n / 256, nq + c->n_p), dim3(256), (cudaStream_t)stream, c->T, nq, c->alpha,
-           c->modup_beta[nq], batch, (u64*)acc, (const u64*)ext, (const u64*)d, (const u64*)ksk);
+    launch(k_ks_inner, dim3(c->n / 512, nq + c->n_p), dim3(256), (cudaStream_t)stream, c->T, nq, c->alpha,
+           c->modup_beta[nq], batch, (u64*)acc, (const u64*)ext, (const u64*)d, (const u64*)ksk,
+           (const u64*)nullptr, (const ConstF*)nullptr);
     return check("fhe_ks_inner");
+}
+
+int fhe_relin_rescale(fhe_ctx* c, void* stream, uint64_t* out, const uint64_t* d3, const uint64_t* rlk, int nq,
+                      int batch) {
+    if (bad_shape(c, nq, 0) || nq < 2 || c->n_p == 0 || batch < 1 || c->modup_beta[nq] > FHE_MAX_BETA)
+        return fail("fhe_relin_rescale: bad shape");
+    cudaStream_t s = (cudaStream_t)stream;
+    const int n = c->n, K = c->n_p, ne = nq + K, beta = c->modup_beta[nq], no = nq - 1;
+    const size_t words = ((size_t)batch * nq + (size_t)batch * beta * ne + 2 * (size_t)batch * ne) * n;
+    u64* base = arena(c, words);
+    if (!base) return fail("fhe_relin_rescale: scratch allocation failed");
+    u64* ext = base + (size_t)batch * nq * n;
+    u64* acc = ext + (size_t)batch * beta * ne * n;
+    const u64* d2 = (const u64*)d3 + 2 * (size_t)batch * nq * n;
+    int rc;
+    if ((rc = fhe_modup(c, stream, (uint64_t*)ext, (const uint64_t*)d2, nq, batch))) return rc;
+    // inner product with the key, plus P * (d0, d1) on the q-limbs
+    launch(k_ks_inner, dim3(n / 512, ne), dim3(256), s, c->T, nq, c->alpha, beta, batch, acc, (const u64*)ext, d2,
+           (const u64*)rlk, (const u64*)d3, (const ConstF*)c->p_mod_q);
+    const int npoly = 2 * batch;
+    u64* accs = acc + (size_t)no * n;                       // rows q_{nq-1}, p_0 .. p_{K-1} are contiguous
+    {
+        RowMap m = make_map(c, K + 1, no, nq);
+        LoadPlain ld; ld.src = accs; ld.poly_stride = (long long)ne * n;
+        StorePlain st; st.dst = accs; st.poly_stride = (long long)ne * n;
+        ntt_inverse(c->T, m, npoly * (K + 1), ld, accs, (long long)ne * n, st, c->mdrs_scale[nq], s);
+    }
+    launch_bconv(c, s, K + 1, npoly, c->mdrs_table[nq], 1, (u64*)out, (long long)no * n, accs, (long long)ne * n);
+    {
+        RowMap m = make_map(c, no, 0, nq);
+        LoadPlain ld; ld.src = (const u64*)out; ld.poly_stride = (long long)no * n;
+        StoreSubMul st; st.out = (u64*)out; st.out_poly_stride = (long long)no * n;
+        st.in = acc; st.in_poly_stride = (long long)ne * n; st.c = c->mdrs_inv[nq];
+        ntt_forward(c->T, m, npoly * no, ld, (u64*)out, (long long)no * n, st, s);
+    }
+    g_launches.fetch_add(4);
+    return check("fhe_relin_rescale");
 }
 
 int fhe_moddown(fhe_ctx* c, void* stream, uint64_t* out, uint64_t* acc, int nq, int npoly) {

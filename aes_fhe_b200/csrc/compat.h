@@ -21,6 +21,7 @@ typedef unsigned int u32;
 #define FHE_HD __host__ __device__ __forceinline__
 #define FHE_D __device__ __forceinline__
 #define FHE_SHARED __shared__
+#define FHE_DYN_SHARED(type, name) extern __shared__ __align__(16) unsigned char name##_raw[]; type* name = reinterpret_cast<type*>(name##_raw)
 
 template <typename... KArgs, typename... Args>
 inline void fhe_launch(void (*k)(KArgs...), dim3 g, dim3 b, size_t smem, cudaStream_t s, Args&&... args) {
@@ -45,6 +46,9 @@ FHE_D u32 brev32(u32 x) { return __brev(x); }
 #define FHE_HD inline
 #define FHE_D inline
 #define FHE_SHARED static thread_local
+#define FHE_DYN_SHARED(type, name) type* name = reinterpret_cast<type*>(fhe_emu_dyn_smem())
+char* fhe_emu_dyn_smem();
+void fhe_emu_set_dyn_smem(size_t bytes);
 
 struct dim3 {
     unsigned x, y, z;
@@ -75,7 +79,8 @@ inline const char* cudaGetErrorString(cudaError_t) { return "emu"; }
 void fhe_emu_launch(dim3 g, dim3 b, const std::function<void()>& body);
 
 template <typename... KArgs, typename... Args>
-inline void fhe_launch(void (*k)(KArgs...), dim3 g, dim3 b, size_t, cudaStream_t, Args&&... args) {
+inline void fhe_launch(void (*k)(KArgs...), dim3 g, dim3 b, size_t smem, cudaStream_t, Args&&... args) {
+    fhe_emu_set_dyn_smem(smem);
     fhe_emu_launch(g, b, [=]() { k(args...); });
 }
 

@@ -144,25 +144,29 @@ struct LinCombIn {
 template <int T_MAX>
 __global__ void __launch_bounds__(256) k_lincomb(DevTables Tb, int nq, int batch, int M, int T, LinCombIn in,
                                                  const ConstF* consts, const u64* c0, u64* out) {
+    FHE_DYN_SHARED(ConstF, s_c);                                  // [M][T] constants of this (limb, half)
     const int row = blockIdx.y;
     const int j = row % nq, b = (row / nq) % batch, poly = row / (nq * batch);
     const Modulus Mo = Tb.mod[j];
     const double q = Mo.qd, qi = Mo.qinv;
     const u32 idx = blockIdx.x * 256 + threadIdx.x;
-    const int half = idx >> (Tb.log_n - 1);
+    const int half = (blockIdx.x * 256) >> (Tb.log_n - 1);        // uniform over the CTA
+    for (int i = threadIdx.x; i < M * T; i += 256)
+        s_c[i] = consts[((size_t)i * nq + j) * 2 + half];
     const size_t lo = ((size_t)j << Tb.log_n) + idx;
     double x[T_MAX];
 #pragma unroll
     for (int t = 0; t < T_MAX; ++t)
         x[t] = t < T ? u64_to_f(in.ptr[t][(size_t)poly * in.poly_stride[t] + (size_t)b * in.batch_stride[t] + lo]) : 0.0;
+    __syncthreads();
     const size_t out_ct = (size_t)2 * batch * nq << Tb.log_n;
     u64* o = out + (((size_t)poly * batch + b) * nq << Tb.log_n) + lo;
     for (int m = 0; m < M; ++m) {
-        const ConstF* cm = consts + (((size_t)m * T) * nq + j) * 2 + half;
+        const ConstF* cm = s_c + m * T;
         double acc = 0.0;
 #pragma unroll
         for (int t = 0; t < T_MAX; ++t)
-            if (t < T) acc = d_add(acc, mulmod_const(x[t], cm[(size_t)t * nq * 2], q));
+            if (t < T) acc = d_add(acc, mulmod_const(x[t], cm[t], q));
         double r = reduce_canon(acc, q, qi);
         if (c0 != nullptr && poly == 0) {
             r = d_add(r, u64_to_f(c0[((size_t)m * nq + j) * 2 + half]));
@@ -272,39 +276,74 @@ __global__ void __launch_bounds__(256) k_bconv(DevTables T, const BConvTable* ta
 // key word is read from HBM once per batch.      ksk: [dnum][2][n_q_total + n_p][N]
 // ext: [batch][beta][ne][N], d: [batch][nq][N], acc: [2][batch][ne][N]
 #define FHE_MAX_BETA 8
+struct U2 { u64 x, y; };
+FHE_D U2 ld2(const u64* p) {
+#ifndef FHE_EMU
+    const ulonglong2 v = __ldg(reinterpret_cast<const ulonglong2*>(p));
+    U2 r; r.x = v.x; r.y = v.y; return r;
+#else
+    U2 r; r.x = p[0]; r.y = p[1]; return r;
+#endif
+}
+FHE_D void st2(u64* p, u64 a, u64 b) {
+#ifndef FHE_EMU
+    *reinterpret_cast<ulonglong2*>(p) = make_ulonglong2(a, b);
+#else
+    p[0] = a; p[1] = b;
+#endif
+}
+// grid: (N/512, nq + n_p); every thread owns two consecutive coefficients (16-byte accesses)
 __global__ void __launch_bounds__(256) k_ks_inner(DevTables T, int nq, int alpha, int beta, int batch,
-                                                  u64* acc, const u64* ext, const u64* d, const u64* ksk) {
+                                                  u64* acc, const u64* ext, const u64* d, const u64* ksk,
+                                                  const u64* lift, const ConstF* lift_c) {
     const int t = blockIdx.y;
     const int ne = nq + T.n_p;
     const int id = t < nq ? t : T.n_q + (t - nq);
     const Modulus M = T.mod[id];
     const double q = M.qd, qi = M.qinv;
     const int log_n = T.log_n;
-    const u32 idx = blockIdx.x * 256 + threadIdx.x;
+    const u32 idx = (blockIdx.x * 256 + threadIdx.x) * 2;
     const size_t tot = (size_t)(T.n_q + T.n_p);
-    double k0[FHE_MAX_BETA], k1[FHE_MAX_BETA];
+    double k0[FHE_MAX_BETA][2], k1[FHE_MAX_BETA][2];
 #pragma unroll
     for (int j = 0; j < FHE_MAX_BETA; ++j) {
         if (j < beta) {
             const u64* kp = ksk + ((((size_t)j * 2) * tot + id) << log_n) + idx;
-            k0[j] = u64_to_f(kp[0]);
-            k1[j] = u64_to_f(kp[tot << log_n]);
-        } else { k0[j] = 0.0; k1[j] = 0.0; }
+            const U2 a = ld2(kp), b = ld2(kp + (tot << log_n));
+            k0[j][0] = u64_to_f(a.x); k0[j][1] = u64_to_f(a.y);
+            k1[j][0] = u64_to_f(b.x); k1[j][1] = u64_to_f(b.y);
+        } else { k0[j][0] = k0[j][1] = k1[j][0] = k1[j][1] = 0.0; }
     }
     const int own = t < nq ? t / alpha : -1;
     for (int b = 0; b < batch; ++b) {
-        double a0 = 0.0, a1 = 0.0;
+        double a0[2] = {0.0, 0.0}, a1[2] = {0.0, 0.0};
 #pragma unroll
         for (int j = 0; j < FHE_MAX_BETA; ++j) {
             if (j < beta) {
-                const double e = u64_to_f(j == own ? d[(((size_t)b * nq + t) << log_n) + idx]
-                                                   : ext[((((size_t)b * beta + j) * ne + t) << log_n) + idx]);
-                a0 = d_add(a0, mulmod_var(e, k0[j], q, qi));
-                a1 = d_add(a1, mulmod_var(e, k1[j], q, qi));
+                const U2 e = ld2(j == own ? d + (((size_t)b * nq + t) << log_n) + idx
+                                          : ext + ((((size_t)b * beta + j) * ne + t) << log_n) + idx);
+                const double e0 = u64_to_f(e.x), e1 = u64_to_f(e.y);
+                a0[0] = d_add(a0[0], mulmod_var(e0, k0[j][0], q, qi));
+                a0[1] = d_add(a0[1], mulmod_var(e1, k0[j][1], q, qi));
+                a1[0] = d_add(a1[0], mulmod_var(e0, k1[j][0], q, qi));
+                a1[1] = d_add(a1[1], mulmod_var(e1, k1[j][1], q, qi));
             }
         }
-        acc[(((size_t)b * ne + t) << log_n) + idx] = f_to_u64(reduce_canon(a0, q, qi));
-        acc[((((size_t)batch + b) * ne + t) << log_n) + idx] = f_to_u64(reduce_canon(a1, q, qi));
+        if (lift != nullptr && t < nq) {
+            // fused relinearise + rescale: add P * (d0, d1) so the sum can be divided by P q_last at once
+            const ConstF pc = lift_c[t];
+            const size_t ps = (size_t)batch * nq << log_n;
+            const U2 l0 = ld2(lift + (((size_t)b * nq + t) << log_n) + idx);
+            const U2 l1 = ld2(lift + ps + (((size_t)b * nq + t) << log_n) + idx);
+            a0[0] = d_add(a0[0], mulmod_const(u64_to_f(l0.x), pc, q));
+            a0[1] = d_add(a0[1], mulmod_const(u64_to_f(l0.y), pc, q));
+            a1[0] = d_add(a1[0], mulmod_const(u64_to_f(l1.x), pc, q));
+            a1[1] = d_add(a1[1], mulmod_const(u64_to_f(l1.y), pc, q));
+        }
+        st2(acc + (((size_t)b * ne + t) << log_n) + idx,
+            f_to_u64(reduce_canon(a0[0], q, qi)), f_to_u64(reduce_canon(a0[1], q, qi)));
+        st2(acc + ((((size_t)batch + b) * ne + t) << log_n) + idx,
+            f_to_u64(reduce_canon(a1[0], q, qi)), f_to_u64(reduce_canon(a1[1], q, qi)));
     }
 }
 

@@ -18,6 +18,13 @@
 #pragma once
 #include "modarith.cuh"
 
+#ifndef FHE_PASSA_MINB
+#define FHE_PASSA_MINB 1
+#endif
+#ifndef FHE_PASSB_MINB
+#define FHE_PASSB_MINB 1
+#endif
+
 struct DevTables {
     const Modulus* mod;            // [n_q + n_p]
     const double* tw_fwd;          // [n_q + n_p][N]   psi^bitrev(k)   (w only: w/q = w * RN(1/q)
@@ -182,7 +189,7 @@ struct StoreRaw {
 
 // ------------------------------------------------------------------ forward kernels
 template <int LOG_R, class LoadOp>
-__global__ void __launch_bounds__(256) ntt_fwd_pass_a(DevTables T, RowMap map, LoadOp ld, StoreRaw st) {
+__global__ void __launch_bounds__(256, FHE_PASSA_MINB) ntt_fwd_pass_a(DevTables T, RowMap map, LoadOp ld, StoreRaw st) {
     constexpr int R = 1 << LOG_R, G = R / 16, COLS = 256 / G, LEV1 = LOG_R - 4;
     FHE_SHARED double sm[4096];
     const int row = map.launch_row(blockIdx.y);
@@ -215,7 +222,7 @@ __global__ void __launch_bounds__(256) ntt_fwd_pass_a(DevTables T, RowMap map, L
 }
 
 template <class StoreOp>
-__global__ void __launch_bounds__(256) ntt_fwd_pass_b(DevTables T, RowMap map, LoadRaw ld, StoreOp st) {
+__global__ void __launch_bounds__(256, FHE_PASSB_MINB) ntt_fwd_pass_b(DevTables T, RowMap map, LoadRaw ld, StoreOp st) {
     FHE_SHARED double sm[4096 + 256];
     const int row = map.launch_row(blockIdx.y);
     const int mid = map.mod_id(row);
@@ -249,7 +256,7 @@ __global__ void __launch_bounds__(256) ntt_fwd_pass_b(DevTables T, RowMap map, L
 // ------------------------------------------------------------------ inverse kernels
 // pass B' : stages log_n .. log_n-7 (strides 1..128) on 16 contiguous rows of 256.
 template <class LoadOp>
-__global__ void __launch_bounds__(256) ntt_inv_pass_b(DevTables T, RowMap map, LoadOp ld, StoreRaw st) {
+__global__ void __launch_bounds__(256, FHE_PASSB_MINB) ntt_inv_pass_b(DevTables T, RowMap map, LoadOp ld, StoreRaw st) {
     FHE_SHARED double sm[4096 + 256];
     const int row = map.launch_row(blockIdx.y);
     const int mid = map.mod_id(row);
@@ -284,7 +291,7 @@ __global__ void __launch_bounds__(256) ntt_inv_pass_b(DevTables T, RowMap map, L
 // constants scale[row % rows_per_poly] = {c * N^-1, c * psi^-bitrev(1) * N^-1} (c = 1 when
 // scale == nullptr).
 template <int LOG_R, class StoreOp>
-__global__ void __launch_bounds__(256) ntt_inv_pass_a(DevTables T, RowMap map, LoadRaw ld, StoreOp st,
+__global__ void __launch_bounds__(256, FHE_PASSA_MINB) ntt_inv_pass_a(DevTables T, RowMap map, LoadRaw ld, StoreOp st,
                                                       const ConstF* scale) {
     constexpr int R = 1 << LOG_R, G = R / 16, COLS = 256 / G, LEV1 = LOG_R - 4;
     FHE_SHARED double sm[4096];

@@ -570,10 +570,12 @@ class Engine:
         nq = a.level + 1
         self._count('mul_ct')
         d = self.backend.tensor(a.polys, b.polys, nq)
-        ct3 = Ciphertext(self, d, a.level)
         if rlk is not None:
-            ct3 = self._relin(ct3, rlk)
-        return self._rescale(ct3)
+            # relinearise and rescale together: one ModDown by P * q_l instead of ModDown + rescale
+            self._count('keyswitch_relin')
+            self._count('rescale')
+            return Ciphertext(self, self.backend.relin_rescale(d, rlk.data, nq), a.level - 1)
+        return self._rescale(Ciphertext(self, d, a.level))
 
     def square(self, a: Ciphertext, relin_key=None) -> Ciphertext:
         return self._mul_ct(a, a, relin_key)

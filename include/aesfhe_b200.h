@@ -120,6 +120,13 @@ int fhe_ks_inner(fhe_ctx* ctx, void* stream, uint64_t* acc, const uint64_t* ext,
                  const uint64_t* d, const uint64_t* ksk, int nq, int batch);
 int fhe_moddown(fhe_ctx* ctx, void* stream, uint64_t* out, uint64_t* acc, int nq, int npoly);
 
+/* Engine.multiply(ct, ct, rlk) tail (xor_service.py:71): relinearise and rescale in one step.
+ * d3[3][batch][nq][N] (tensor product) -> out[2][batch][nq-1][N] =
+ * round(((d0, d1) * P + <ModUp(d2), rlk>) / (P * q_{nq-1})): the ModDown by P and the rescale by
+ * q_{nq-1} share one base conversion and one set of NTTs. */
+int fhe_relin_rescale(fhe_ctx* ctx, void* stream, uint64_t* out, const uint64_t* d3, const uint64_t* rlk,
+                      int nq, int batch);
+
 /* Engine.encode / encrypt residue step (xor_service.py:59-66): signed 64-bit coefficients
  * coeffs[batch][N] (device) -> coefficient-domain residues out[batch][nq + np][N]. */
 int fhe_from_i64(fhe_ctx* ctx, void* stream, uint64_t* out, const int64_t* coeffs, int nq, int np, int batch);

@@ -388,33 +388,42 @@ void ref_ks_inner(void* h, u64* acc, const u64* ext, const u64* ksk, int n_q_act
     }
 }
 
-// ModDown: acc [n_polys, n_q_active + n_p, N] (NTT) -> out [n_polys, n_q_active, N] (NTT)
-void ref_moddown(void* h, u64* out, const u64* acc, int n_q_active, int n_polys) {
+// ModDown: acc [n_polys, n_q_active + n_p, N] (NTT) -> out [n_polys, n_out, N] (NTT).
+// drop_last_q = 0: divide by P (n_out = n_q_active).  drop_last_q = 1: divide by P * q_last in
+// one step (n_out = n_q_active - 1) -- key switching and the rescale that follows it, merged.
+void ref_moddown_ex(void* h, u64* out, const u64* acc, int n_q_active, int n_polys, int drop_last_q) {
     Ctx& c = *(Ctx*)h;
     int n = c.n, K = c.n_p, na = n_q_active, ne = na + K;
-    std::vector<int> pids(K), qids(na);
-    for (int k = 0; k < K; ++k) pids[k] = c.n_q + k;
-    for (int i = 0; i < na; ++i) qids[i] = i;
+    int n_out = drop_last_q ? na - 1 : na;
+    std::vector<int> sids, qids(n_out);
+    if (drop_last_q) sids.push_back(na - 1);
+    for (int k = 0; k < K; ++k) sids.push_back(c.n_q + k);
+    for (int i = 0; i < n_out; ++i) qids[i] = i;
+    int ns = (int)sids.size();
     for (int pl = 0; pl < n_polys; ++pl) {
         const u64* a = acc + (size_t)pl * ne * n;
-        std::vector<u64> pc(a + (size_t)na * n, a + (size_t)ne * n);
-        ref_intt(h, pc.data(), pids.data(), K);
-        std::vector<const u64*> in; for (int k = 0; k < K; ++k) in.push_back(pc.data() + (size_t)k * n);
-        std::vector<u64> w((size_t)na * n);
-        std::vector<u64*> outp; for (int i = 0; i < na; ++i) outp.push_back(w.data() + (size_t)i * n);
-        base_convert(c, pids, in.data(), qids, outp.data());
-        ref_ntt(h, w.data(), qids.data(), na);
+        const u64* first = a + (size_t)(drop_last_q ? na - 1 : na) * n;     // source rows are contiguous
+        std::vector<u64> pc(first, first + (size_t)ns * n);
+        ref_intt(h, pc.data(), sids.data(), ns);
+        std::vector<const u64*> in; for (int k = 0; k < ns; ++k) in.push_back(pc.data() + (size_t)k * n);
+        std::vector<u64> w((size_t)n_out * n);
+        std::vector<u64*> outp; for (int i = 0; i < n_out; ++i) outp.push_back(w.data() + (size_t)i * n);
+        base_convert(c, sids, in.data(), qids, outp.data());
+        ref_ntt(h, w.data(), qids.data(), n_out);
         #pragma omp parallel for num_threads(c.threads)
-        for (int i = 0; i < na; ++i) {
+        for (int i = 0; i < n_out; ++i) {
             const Mod& m = c.mod[i];
             u64 pinv = 1;
-            for (int k = 0; k < K; ++k) pinv = mulmod(pinv, c.mod[pids[k]].q % m.q, m);
+            for (int k = 0; k < ns; ++k) pinv = mulmod(pinv, c.mod[sids[k]].q % m.q, m);
             pinv = invmod(pinv, m);
             size_t o = (size_t)i * n;
-            u64* dst = out + (size_t)pl * na * n;
+            u64* dst = out + (size_t)pl * n_out * n;
             for (int j = 0; j < n; ++j) dst[o + j] = mulmod(submod(a[o + j], w[o + j], m.q), pinv, m);
         }
     }
+}
+void ref_moddown(void* h, u64* out, const u64* acc, int n_q_active, int n_polys) {
+    ref_moddown_ex(h, out, acc, n_q_active, n_polys, 0);
 }
 
 // 2-limb CRT of coefficient-domain rows (limbs 0 and 1) to centred doubles.

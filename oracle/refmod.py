@@ -253,6 +253,21 @@ class RefBackend:
         self._L.ref_moddown(self._ctx, _p(out), _p(flat), C.c_int(nq), C.c_int(flat.shape[0]))
         return out.reshape(acc.shape[0], acc.shape[1], nq, self.n)
 
+    def relin_rescale(self, d3, ksk, nq):
+        """(d0, d1) + KS(d2), divided by P * q_{nq-1} in one step: [3,B,nq,N] -> [2,B,nq-1,N]."""
+        P = self.params
+        acc = self.ks_inner(self.modup(d3[2:3], nq), d3[2:3], ksk, nq)           # [2, B, nq+K, N]
+        pprod = 1
+        for p in P.p:
+            pprod *= p
+        lift = self.mul_scalar(np.ascontiguousarray(d3[0:2]), [pprod % P.moduli[l] for l in range(nq)], nq, 0)
+        acc = np.array(acc, copy=True)
+        acc[:, :, :nq] = self.add(np.ascontiguousarray(acc[:, :, :nq]), lift, nq, 0)
+        flat = np.ascontiguousarray(acc).reshape(-1, acc.shape[2], self.n)
+        out = np.empty((flat.shape[0], nq - 1, self.n), dtype=np.uint64)
+        self._L.ref_moddown_ex(self._ctx, _p(out), _p(flat), C.c_int(nq), C.c_int(flat.shape[0]), C.c_int(1))
+        return out.reshape(2, acc.shape[1], nq - 1, self.n)
+
     def keyswitch(self, d, ksk, nq):
         return self.moddown(self.ks_inner(self.modup(d, nq), d, ksk, nq), nq)
 

@@ -13,6 +13,15 @@
 
 thread_local dim3 threadIdx, blockIdx, blockDim, gridDim;
 
+// dynamic shared memory: one buffer per host worker thread (= per running block)
+static size_t g_dyn_bytes = 0;
+void fhe_emu_set_dyn_smem(size_t bytes) { g_dyn_bytes = bytes; }
+char* fhe_emu_dyn_smem() {
+    static thread_local std::vector<char> buf;
+    if (buf.size() < g_dyn_bytes + 16) buf.resize(g_dyn_bytes + 16);
+    return buf.data();
+}
+
 namespace {
 constexpr size_t kStack = 128 * 1024;
 
