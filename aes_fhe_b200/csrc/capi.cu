@@ -278,6 +278,15 @@ void launch_bconv(fhe_ctx* c, cudaStream_t s, int ns_max, int groups, const BCon
 #undef FHE_BCONV_CASE
 }
 
+void launch_ks_inner(fhe_ctx* c, cudaStream_t s, int nq, int batch, u64* acc, const u64* ext, const u64* d,
+                     const u64* ksk, const u64* lift, const ConstF* lift_c) {
+    const int beta = c->modup_beta[nq];
+    dim3 grid(c->n / 512, nq + c->n_p), block(256);
+    if (beta <= 2) launch(k_ks_inner<2>, grid, block, s, c->T, nq, c->alpha, beta, batch, acc, ext, d, ksk, lift, lift_c);
+    else if (beta <= 4) launch(k_ks_inner<4>, grid, block, s, c->T, nq, c->alpha, beta, batch, acc, ext, d, ksk, lift, lift_c);
+    else launch(k_ks_inner<8>, grid, block, s, c->T, nq, c->alpha, beta, batch, acc, ext, d, ksk, lift, lift_c);
+}
+
 }  // namespace
 
 extern "C" {
@@ -549,9 +558,8 @@ int fhe_ks_inner(fhe_ctx* c, void* stream, uint64_t* acc, const uint64_t* ext, c
                  const uint64_t* ksk, int nq, int batch) {
     if (bad_shape(c, nq, 0) || c->n_p == 0 || batch < 1 || c->modup_beta[nq] > FHE_MAX_BETA)
         return fail("fhe_ks_inner: bad shape");
-    launch(k_ks_inner, dim3(c->n / 512, nq + c->n_p), dim3(256), (cudaStream_t)stream, c->T, nq, c->alpha,
-           c->modup_beta[nq], batch, (u64*)acc, (const u64*)ext, (const u64*)d, (const u64*)ksk,
-           (const u64*)nullptr, (const ConstF*)nullptr);
+    launch_ks_inner(c, (cudaStream_t)stream, nq, batch, (u64*)acc, (const u64*)ext, (const u64*)d, (const u64*)ksk,
+                    nullptr, nullptr);
     return check("fhe_ks_inner");
 }
 
@@ -570,8 +578,7 @@ int fhe_relin_rescale(fhe_ctx* c, void* stream, uint64_t* out, const uint64_t* d
     int rc;
     if ((rc = fhe_modup(c, stream, (uint64_t*)ext, (const uint64_t*)d2, nq, batch))) return rc;
     // inner product with the key, plus P * (d0, d1) on the q-limbs
-    launch(k_ks_inner, dim3(n / 512, ne), dim3(256), s, c->T, nq, c->alpha, beta, batch, acc, (const u64*)ext, d2,
-           (const u64*)rlk, (const u64*)d3, (const ConstF*)c->p_mod_q);
+    launch_ks_inner(c, s, nq, batch, acc, (const u64*)ext, d2, (const u64*)rlk, (const u64*)d3, c->p_mod_q);
     const int npoly = 2 * batch;
     u64* accs = acc + (size_t)no * n;                       // rows q_{nq-1}, p_0 .. p_{K-1} are contiguous
     {

@@ -293,7 +293,8 @@ FHE_D void st2(u64* p, u64 a, u64 b) {
 #endif
 }
 // grid: (N/512, nq + n_p); every thread owns two consecutive coefficients (16-byte accesses)
-__global__ void __launch_bounds__(256) k_ks_inner(DevTables T, int nq, int alpha, int beta, int batch,
+template <int BMAX>
+__global__ void __launch_bounds__(256, (BMAX <= 4 ? 3 : 2)) k_ks_inner(DevTables T, int nq, int alpha, int beta, int batch,
                                                   u64* acc, const u64* ext, const u64* d, const u64* ksk,
                                                   const u64* lift, const ConstF* lift_c) {
     const int t = blockIdx.y;
@@ -304,9 +305,9 @@ __global__ void __launch_bounds__(256) k_ks_inner(DevTables T, int nq, int alpha
     const int log_n = T.log_n;
     const u32 idx = (blockIdx.x * 256 + threadIdx.x) * 2;
     const size_t tot = (size_t)(T.n_q + T.n_p);
-    double k0[FHE_MAX_BETA][2], k1[FHE_MAX_BETA][2];
+    double k0[BMAX][2], k1[BMAX][2];
 #pragma unroll
-    for (int j = 0; j < FHE_MAX_BETA; ++j) {
+    for (int j = 0; j < BMAX; ++j) {
         if (j < beta) {
             const u64* kp = ksk + ((((size_t)j * 2) * tot + id) << log_n) + idx;
             const U2 a = ld2(kp), b = ld2(kp + (tot << log_n));
@@ -318,7 +319,7 @@ __global__ void __launch_bounds__(256) k_ks_inner(DevTables T, int nq, int alpha
     for (int b = 0; b < batch; ++b) {
         double a0[2] = {0.0, 0.0}, a1[2] = {0.0, 0.0};
 #pragma unroll
-        for (int j = 0; j < FHE_MAX_BETA; ++j) {
+        for (int j = 0; j < BMAX; ++j) {
             if (j < beta) {
                 const U2 e = ld2(j == own ? d + (((size_t)b * nq + t) << log_n) + idx
                                           : ext + ((((size_t)b * beta + j) * ne + t) << log_n) + idx);
