@@ -22,6 +22,8 @@ SIGNATURES = {
     "fhe_ctx_destroy": [_P],
     "fhe_last_error": [],
     "fhe_launch_count": [],
+    "fhe_set_ntt_fused": [_P, _I],
+    "fhe_ntt_fused_status": [_P],
     "fhe_ntt_fwd": [_P, _P, _P, _I, _I, _I],
     "fhe_ntt_inv": [_P, _P, _P, _I, _I, _I],
     "fhe_add": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I],

@@ -7,6 +7,7 @@
 #include <algorithm>
 #include <atomic>
 #include <cstring>
+#include <cstdlib>
 #include <cstdio>
 #include <string>
 #include <vector>
@@ -75,6 +76,9 @@ struct fhe_ctx {
     // scratch arena
     u64* scratch = nullptr;
     size_t scratch_words = 0;
+    // single-launch NTT (ntt_fused.cuh): L2-resident scratch limbs + group counters
+    FusedHost fz;
+    bool fz_calibrate = false;      // calibration still to be done when the fused path is first enabled
 
     u64 id_mod(int t, int nq) const { return q[t < nq ? t : n_q + (t - nq)]; }
     int id_of(int t, int nq) const { return t < nq ? t : n_q + (t - nq); }
@@ -109,6 +113,16 @@ template <typename... KArgs, typename... Args>
 inline void launch(void (*k)(KArgs...), dim3 g, dim3 b, cudaStream_t s, Args&&... args) {
     g_launches.fetch_add(1, std::memory_order_relaxed);
     fhe_launch(k, g, b, 0, s, std::forward<Args>(args)...);
+}
+
+template <class LoadOp, class StoreOp>
+inline void ntt_fwd(fhe_ctx* c, const RowMap& m, int rows, LoadOp ld, u64* work, long long ws, StoreOp st, cudaStream_t s) {
+    g_launches.fetch_add(ntt_forward_auto(c->T, c->fz, m, rows, ld, work, ws, st, s), std::memory_order_relaxed);
+}
+template <class LoadOp, class StoreOp>
+inline void ntt_inv(fhe_ctx* c, const RowMap& m, int rows, LoadOp ld, u64* work, long long ws, StoreOp st,
+                    const ConstF* scale, cudaStream_t s) {
+    g_launches.fetch_add(ntt_inverse_auto(c->T, c->fz, m, rows, ld, work, ws, st, scale, s), std::memory_order_relaxed);
 }
 
 RowMap make_map(const fhe_ctx* c, int rows_per_poly, int j0, int nq, int skip_alpha = 0) {
@@ -287,6 +301,50 @@ void launch_ks_inner(fhe_ctx* c, cudaStream_t s, int nq, int batch, u64* acc, co
     else launch(k_ks_inner<8>, grid, block, s, c->T, nq, c->alpha, beta, batch, acc, ext, d, ksk, lift, lift_c);
 }
 
+#ifndef FHE_EMU
+// The warp scheduler favours the CTAs that have been resident longest, so the groups of the
+// persistent fused-NTT grid run at different speeds depending on the residency slot their CTAs
+// occupy.  Measure it once (12 rows per group, equal split, wall time per group) and let
+// fused_fill_ctl hand out row ranges proportional to the measured speeds.
+void fused_calibrate(fhe_ctx* c) {
+    FusedHost& fz = c->fz;
+    const int groups = fused_full_groups(c->log_n, fz);
+    if (groups < 2 || groups > FHE_FUSED_MAX_WGROUPS) return;
+    const int per = 32, rows = groups * per;
+    u64* buf = nullptr;
+    if (cudaMalloc((void**)&buf, sizeof(u64) * (size_t)rows * c->n) != cudaSuccess) { cudaGetLastError(); return; }
+    cudaMemset(buf, 0, sizeof(u64) * (size_t)rows * c->n);
+    RowMap m = make_map(c, 1, 0, 1);
+    LoadPlain ld; ld.src = buf; ld.poly_stride = c->n;
+    StorePlain st; st.dst = buf; st.poly_stride = c->n;
+    fz.calibrating = 1; fz.cal_groups = 0;
+    std::vector<unsigned long long> t(groups);
+    std::vector<int> start(groups + 1);
+    // Fixed-point iteration: speeds interact (a late-slot group runs faster once the early-slot
+    // groups have finished), so re-measure with the current split until the groups finish together.
+    for (int it = 0; it < 6; ++it) {
+        FusedCtl probe; fused_fill_ctl(probe, fz, groups, rows);
+        for (int g = 0; g <= groups; ++g) start[g] = probe.weighted ? probe.start[g] : std::min(rows, g * per);
+        bool ok = true;
+        for (int rep = 0; rep < 2 && ok; ++rep) {
+            cudaMemset(fz.gtime, 0, sizeof(unsigned long long) * FHE_FUSED_MAX_WGROUPS);
+            ok = ntt_forward_auto(c->T, fz, m, rows, ld, buf, c->n, st, 0) == 1 && cudaDeviceSynchronize() == cudaSuccess;
+        }
+        if (ok) ok = cudaMemcpy(t.data(), fz.gtime, sizeof(unsigned long long) * groups, cudaMemcpyDeviceToHost) == cudaSuccess;
+        for (int g = 0; g < groups && ok; ++g) if (t[g] == 0 || start[g + 1] <= start[g]) ok = false;
+        if (!ok) { cudaGetLastError(); fz.cal_groups = 0; break; }
+        // speed of a group = rows it was given / time it took (normalised); damped update
+        std::vector<double> sp(groups);
+        double tot = 0;
+        for (int g = 0; g < groups; ++g) { sp[g] = (double)(start[g + 1] - start[g]) / (double)t[g]; tot += sp[g]; }
+        for (int g = 0; g < groups; ++g) fz.weight[g] = fz.cal_groups ? 0.5 * fz.weight[g] + 0.5 * sp[g] / tot : sp[g] / tot;
+        fz.cal_groups = groups;
+    }
+    fz.calibrating = 0;
+    cudaFree(buf);
+}
+#endif
+
 }  // namespace
 
 extern "C" {
@@ -337,8 +395,82 @@ int fhe_ctx_create(fhe_ctx** out, int log_n, int n_q, int n_p, int alpha, const 
     c->T.mod = d_mod; c->T.tw_fwd = d_twf; c->T.tw_inv = d_twi; c->T.inv_final = d_fin;
     c->T.log_n = log_n; c->T.n_q = n_q; c->T.n_p = n_p;
     build_level_tables(c);
+    {   // single-launch NTT resources (ntt_fused.cuh); FHE_NTT_FUSED=0 keeps the two-pass kernels
+#ifndef FHE_EMU
+        int sms = 0;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+        int coop = 0;
+        cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device);
+#else
+        const int sms = 4, coop = 1;
+#endif
+        const int gs = std::max(1, n / FHE_FUSED_TILE);
+        FusedHost& fz = c->fz;
+        fz.sm_count = sms;
+        fz.max_groups = std::max(1, sms * FHE_FUSED_MAX_OCC / gs);
+        if (const char* fl = std::getenv("FHE_FUSED_FLAGS")) fz.flags = std::atoi(fl);
+        // resources are always there; the fused path is opt-in (FHE_NTT_FUSED=1 or fhe_set_ntt_fused):
+        // on B200 it halves the DRAM traffic of a transform but does not yet beat the two-pass
+        // kernels in wall time (profiles/r01_fused_ntt.md)
+        const char* env = std::getenv("FHE_NTT_FUSED");
+        fz.enabled = 0;
+        if (coop && sms > 0) {
+            if (cudaMalloc((void**)&fz.scratch, sizeof(u64) * 2 * (size_t)fz.max_groups * n) != cudaSuccess ||
+                cudaMalloc((void**)&fz.ctr, sizeof(unsigned) * (32 * fz.max_groups + 1)) != cudaSuccess) {
+                delete c; return fail("fhe_ctx_create: fused-NTT scratch allocation failed");
+            }
+            cudaMemset(fz.ctr, 0, sizeof(unsigned) * (32 * fz.max_groups + 1));
+            c->owned.push_back(fz.scratch); c->owned.push_back(fz.ctr);
+            if (cudaMalloc((void**)&fz.gtime, sizeof(unsigned long long) * FHE_FUSED_MAX_WGROUPS) == cudaSuccess)
+                c->owned.push_back(fz.gtime);
+#ifdef FHE_FUSED_PROFILE
+            cudaMalloc((void**)&fz.prof, 64 + 32 * 2048); cudaMemset(fz.prof, 0, 64 + 32 * 2048); c->owned.push_back(fz.prof);
+#endif
+#ifdef FHE_EMU
+            fz.enabled = !(env && env[0] == '0');      // the host simulator always exercises the fused kernels
+#else
+            fz.enabled = (env && env[0] == '1') ? 1 : 0;
+#endif
+        }
+    }
+#ifndef FHE_EMU
+    {
+        const char* cal = std::getenv("FHE_FUSED_CALIBRATE");
+        c->fz_calibrate = !(cal && cal[0] == '0');
+        if (c->fz.enabled && c->fz.gtime && c->fz_calibrate) { fused_calibrate(c); c->fz_calibrate = false; }
+    }
+#endif
     *out = c;
     return check("fhe_ctx_create");
+}
+
+int fhe_set_ntt_fused(fhe_ctx* c, int enabled) {
+    if (!c) return fail("fhe_set_ntt_fused: null context");
+    if (enabled && !c->fz.scratch) return fail("fhe_set_ntt_fused: context was created without fused-NTT resources");
+    c->fz.enabled = enabled ? 1 : 0;
+#ifndef FHE_EMU
+    if (enabled && c->fz_calibrate && c->fz.gtime) { c->fz_calibrate = false; fused_calibrate(c); c->fz.enabled = 1; }
+#endif
+    return 0;
+}
+
+#ifdef FHE_FUSED_PROFILE
+extern "C" int fhe_fused_profile(fhe_ctx* c, unsigned long long* out8) {
+    cudaDeviceSynchronize();
+    cudaMemcpy(out8, c->fz.prof, 64 + 32 * 2048, cudaMemcpyDeviceToHost);
+    cudaMemset(c->fz.prof, 0, 64 + 32 * 2048);
+    return 0;
+}
+#endif
+
+int fhe_ntt_fused_status(fhe_ctx* c) {
+    if (!c) return fail("fhe_ntt_fused_status: null context");
+    if (!c->fz.ctr) return 0;
+    unsigned flag = 0;
+    if (cudaMemcpy(&flag, c->fz.ctr + 32 * c->fz.max_groups, sizeof(unsigned), cudaMemcpyDeviceToHost) != cudaSuccess)
+        return check("fhe_ntt_fused_status");
+    if (flag) return fail("fused NTT: a group barrier timed out (CTAs of a group were not co-resident)");
+    return 0;
 }
 
 void fhe_ctx_destroy(fhe_ctx* c) {
@@ -356,8 +488,7 @@ int fhe_ntt_fwd(fhe_ctx* c, void* stream, uint64_t* data, int npoly, int nq, int
     const long long ps = (long long)rpp * c->n;
     LoadPlain ld; ld.src = (const u64*)data; ld.poly_stride = ps;
     StorePlain st; st.dst = (u64*)data; st.poly_stride = ps;
-    ntt_forward(c->T, m, npoly * rpp, ld, (u64*)data, ps, st, (cudaStream_t)stream);
-    g_launches.fetch_add(2);
+    ntt_fwd(c, m, npoly * rpp, ld, (u64*)data, ps, st, (cudaStream_t)stream);
     return check("fhe_ntt_fwd");
 }
 
@@ -368,8 +499,7 @@ int fhe_ntt_inv(fhe_ctx* c, void* stream, uint64_t* data, int npoly, int nq, int
     const long long ps = (long long)rpp * c->n;
     LoadPlain ld; ld.src = (const u64*)data; ld.poly_stride = ps;
     StorePlain st; st.dst = (u64*)data; st.poly_stride = ps;
-    ntt_inverse(c->T, m, npoly * rpp, ld, (u64*)data, ps, st, nullptr, (cudaStream_t)stream);
-    g_launches.fetch_add(2);
+    ntt_inv(c, m, npoly * rpp, ld, (u64*)data, ps, st, nullptr, (cudaStream_t)stream);
     return check("fhe_ntt_inv");
 }
 
@@ -486,7 +616,7 @@ int fhe_rescale(fhe_ctx* c, void* stream, uint64_t* out, const uint64_t* in, int
         RowMap m = make_map(c, 1, nq - 1, nq);
         LoadPlain ld; ld.src = (const u64*)in + (size_t)(nq - 1) * n; ld.poly_stride = (long long)nq * n;
         StorePlain st; st.dst = last; st.poly_stride = n;
-        ntt_inverse(c->T, m, npoly, ld, last, n, st, nullptr, s);
+        ntt_inv(c, m, npoly, ld, last, n, st, nullptr, s);
     }
     // 2) per remaining limb: NTT(centred remainder), out = (in - it) * q_last^-1
     {
@@ -495,9 +625,8 @@ int fhe_rescale(fhe_ctx* c, void* stream, uint64_t* out, const uint64_t* in, int
         LoadCentered ld; ld.last = last; ld.q_last = c->q[nq - 1];
         StoreSubMul st; st.out = (u64*)out; st.out_poly_stride = (long long)rpp * n;
         st.in = (const u64*)in; st.in_poly_stride = (long long)nq * n; st.c = c->rescale_c[nq];
-        ntt_forward(c->T, m, npoly * rpp, ld, (u64*)out, (long long)rpp * n, st, s);
+        ntt_fwd(c, m, npoly * rpp, ld, (u64*)out, (long long)rpp * n, st, s);
     }
-    g_launches.fetch_add(4);
     return check("fhe_rescale");
 }
 
@@ -511,15 +640,14 @@ int fhe_mod_raise(fhe_ctx* c, void* stream, uint64_t* out, const uint64_t* in, i
         RowMap m = make_map(c, 1, 0, 1);
         LoadPlain ld; ld.src = (const u64*)in; ld.poly_stride = n;
         StorePlain st; st.dst = coef; st.poly_stride = n;
-        ntt_inverse(c->T, m, npoly, ld, coef, n, st, nullptr, s);
+        ntt_inv(c, m, npoly, ld, coef, n, st, nullptr, s);
     }
     {   // centred lift into every target modulus, fused into the forward transform's load
         RowMap m = make_map(c, nq_out, 0, nq_out);
         LoadCentered ld; ld.last = coef; ld.q_last = c->q[0];
         StorePlain st; st.dst = (u64*)out; st.poly_stride = (long long)nq_out * n;
-        ntt_forward(c->T, m, npoly * nq_out, ld, (u64*)out, (long long)nq_out * n, st, s);
+        ntt_fwd(c, m, npoly * nq_out, ld, (u64*)out, (long long)nq_out * n, st, s);
     }
-    g_launches.fetch_add(4);
     return check("fhe_mod_raise");
 }
 
@@ -540,7 +668,7 @@ int fhe_modup(fhe_ctx* c, void* stream, uint64_t* ext, const uint64_t* d, int nq
         RowMap m = make_map(c, nq, 0, nq);
         LoadPlain ld; ld.src = (const u64*)d; ld.poly_stride = (long long)nq * n;
         StorePlain st; st.dst = y; st.poly_stride = (long long)nq * n;
-        ntt_inverse(c->T, m, batch * nq, ld, y, (long long)nq * n, st, c->modup_scale[nq], s);
+        ntt_inv(c, m, batch * nq, ld, y, (long long)nq * n, st, c->modup_scale[nq], s);
     }
     launch_bconv(c, s, std::min(c->alpha, nq), batch * beta, c->modup_tables[nq], beta, (u64*)ext, (long long)ne * n, y,
                  (long long)nq * n);
@@ -548,9 +676,8 @@ int fhe_modup(fhe_ctx* c, void* stream, uint64_t* ext, const uint64_t* d, int nq
         RowMap m = make_map(c, ne, 0, nq, c->alpha);
         LoadPlain ld; ld.src = (const u64*)ext; ld.poly_stride = (long long)ne * n;
         StorePlain st; st.dst = (u64*)ext; st.poly_stride = (long long)ne * n;
-        ntt_forward(c->T, m, batch * beta * ne, ld, (u64*)ext, (long long)ne * n, st, s);
+        ntt_fwd(c, m, batch * beta * ne, ld, (u64*)ext, (long long)ne * n, st, s);
     }
-    g_launches.fetch_add(4);
     return check("fhe_modup");
 }
 
@@ -585,7 +712,7 @@ int fhe_relin_rescale(fhe_ctx* c, void* stream, uint64_t* out, const uint64_t* d
         RowMap m = make_map(c, K + 1, no, nq);
         LoadPlain ld; ld.src = accs; ld.poly_stride = (long long)ne * n;
         StorePlain st; st.dst = accs; st.poly_stride = (long long)ne * n;
-        ntt_inverse(c->T, m, npoly * (K + 1), ld, accs, (long long)ne * n, st, c->mdrs_scale[nq], s);
+        ntt_inv(c, m, npoly * (K + 1), ld, accs, (long long)ne * n, st, c->mdrs_scale[nq], s);
     }
     launch_bconv(c, s, K + 1, npoly, c->mdrs_table[nq], 1, (u64*)out, (long long)no * n, accs, (long long)ne * n);
     {
@@ -593,9 +720,8 @@ int fhe_relin_rescale(fhe_ctx* c, void* stream, uint64_t* out, const uint64_t* d
         LoadPlain ld; ld.src = (const u64*)out; ld.poly_stride = (long long)no * n;
         StoreSubMul st; st.out = (u64*)out; st.out_poly_stride = (long long)no * n;
         st.in = acc; st.in_poly_stride = (long long)ne * n; st.c = c->mdrs_inv[nq];
-        ntt_forward(c->T, m, npoly * no, ld, (u64*)out, (long long)no * n, st, s);
+        ntt_fwd(c, m, npoly * no, ld, (u64*)out, (long long)no * n, st, s);
     }
-    g_launches.fetch_add(4);
     return check("fhe_relin_rescale");
 }
 
@@ -608,7 +734,7 @@ int fhe_moddown(fhe_ctx* c, void* stream, uint64_t* out, uint64_t* acc, int nq, 
         RowMap m = make_map(c, K, nq, nq);
         LoadPlain ld; ld.src = accp; ld.poly_stride = (long long)ne * n;
         StorePlain st; st.dst = accp; st.poly_stride = (long long)ne * n;
-        ntt_inverse(c->T, m, npoly * K, ld, accp, (long long)ne * n, st, c->moddown_scale, s);
+        ntt_inv(c, m, npoly * K, ld, accp, (long long)ne * n, st, c->moddown_scale, s);
     }
     // P -> q_i conversion written straight into `out` (coefficient domain) ...
     launch_bconv(c, s, K, npoly, c->moddown_table[nq], 1, (u64*)out, (long long)nq * n, accp, (long long)ne * n);
@@ -617,9 +743,8 @@ int fhe_moddown(fhe_ctx* c, void* stream, uint64_t* out, uint64_t* acc, int nq, 
         LoadPlain ld; ld.src = (const u64*)out; ld.poly_stride = (long long)nq * n;
         StoreSubMul st; st.out = (u64*)out; st.out_poly_stride = (long long)nq * n;
         st.in = (const u64*)acc; st.in_poly_stride = (long long)ne * n; st.c = c->pinv;
-        ntt_forward(c->T, m, npoly * nq, ld, (u64*)out, (long long)nq * n, st, s);
+        ntt_fwd(c, m, npoly * nq, ld, (u64*)out, (long long)nq * n, st, s);
     }
-    g_launches.fetch_add(4);
     return check("fhe_moddown");
 }
 

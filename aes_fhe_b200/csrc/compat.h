@@ -68,6 +68,7 @@ inline cudaError_t cudaMalloc(void** p, size_t n) { *p = std::malloc(n ? n : 1);
 inline cudaError_t cudaFree(void* p) { std::free(p); return 0; }
 inline cudaError_t cudaMemcpy(void* d, const void* s, size_t n, cudaMemcpyKind) { std::memcpy(d, s, n); return 0; }
 inline cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, cudaMemcpyKind, cudaStream_t) { std::memmove(d, s, n); return 0; }
+inline cudaError_t cudaMemset(void* d, int v, size_t n) { std::memset(d, v, n); return 0; }
 inline cudaError_t cudaMemsetAsync(void* d, int v, size_t n, cudaStream_t) { std::memset(d, v, n); return 0; }
 inline cudaError_t cudaGetLastError() { return 0; }
 inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return 0; }

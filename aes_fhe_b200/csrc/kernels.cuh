@@ -7,7 +7,7 @@
 // when a contraction over limbs is involved); consecutive threads touch consecutive
 // addresses, so every access is a full 128-byte line per half-warp.
 #pragma once
-#include "ntt.cuh"
+#include "ntt_fused.cuh"
 
 #define FHE_MAX_SRC 16      // max limbs in one base-conversion source basis (alpha, K)
 #define FHE_MAX_DST 48      // max target limbs of one base conversion
@@ -354,9 +354,13 @@ __global__ void __launch_bounds__(256, (BMAX <= 4 ? 3 : 2)) k_ks_inner(DevTables
 struct LoadCentered {
     const u64* last;            // [npoly][N] coefficient-domain rows of the dropped limb
     u64 q_last;
-    FHE_D double operator()(const RowMap& map, int row, u32 idx, int, const Modulus&) const {
-        const u64 v = last[((size_t)(row / map.rows_per_poly) << map.log_n) + idx];
+    FHE_D double operator()(const RowMap& map, RowRef row, int idx, int, const Modulus&) const {
+        const u64 v = last[((size_t)row.blk << map.log_n) + idx];
         return v > (q_last >> 1) ? d_add(u64_to_f(v), -u64_to_f(q_last)) : u64_to_f(v);
+    }
+    FHE_D void prefetch(const RowMap& map, RowRef row, int idx, int count) const {
+        const u64* p = last + ((size_t)row.blk << map.log_n) + idx;
+        for (int k = 0; k < count; k += 16) prefetch_l2(p + k);
     }
 };
 // rescale / ModDown epilogue: out = (in - ntt_value) * c[j]
@@ -364,8 +368,8 @@ struct StoreSubMul {
     u64* out; long long out_poly_stride;
     const u64* in; long long in_poly_stride;
     const ConstF* c;            // per limb slot j
-    FHE_D void operator()(const RowMap& map, int row, u32 idx, double v, int, const Modulus& M) const {
-        const int poly = row / map.rows_per_poly, j = row % map.rows_per_poly;
+    FHE_D void operator()(const RowMap& map, RowRef row, int idx, double v, int, const Modulus& M) const {
+        const int poly = row.blk, j = row.j;
         const size_t lo = ((size_t)j << map.log_n) + idx;
         const double x = u64_to_f(in[(size_t)poly * in_poly_stride + lo]);
         out[(size_t)poly * out_poly_stride + lo] = f_to_u64(canon(mulmod_const(d_add(x, -v), c[j], M.qd), M.qd));

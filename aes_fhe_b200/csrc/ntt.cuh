@@ -38,6 +38,7 @@ struct DevTables {
 // slot j = j0 + row % rows_per_poly maps to modulus j (< nq) or p_base + (j - nq).
 // skip_alpha > 0 marks the ModUp layout [batch][digit][nq + n_p]: the rows of a digit's own
 // limbs are not transformed.
+struct RowRef { int blk, j; };     // row = blk * rows_per_poly + j: poly block and limb slot
 struct RowMap {
     int rows_per_poly;
     int j0;
@@ -49,6 +50,16 @@ struct RowMap {
     int n_blocks;                  // rows / rows_per_poly: launch order is limb-major, block-minor,
                                    // so the CTAs sharing one twiddle table are co-resident (L2 reuse)
     FHE_D int launch_row(int y) const { return (y % n_blocks) * rows_per_poly + y / n_blocks; }
+    FHE_D RowRef ref(int row) const { RowRef r; r.blk = row / rows_per_poly; r.j = row - r.blk * rows_per_poly; return r; }
+    // the same classification from (limb slot j, digit index of the block); no divisions
+    FHE_D int mod_id_of(int j_slot, int dig) const {
+        const int j = j0 + j_slot;
+        if (skip_alpha > 0) {
+            const int lo = dig * skip_alpha;
+            if (j >= lo && j < lo + skip_alpha && j < nq) return -1;
+        }
+        return j < nq ? j : p_base + (j - nq);
+    }
     FHE_D int mod_id(int row) const {
         int j = j0 + row % rows_per_poly;
         if (skip_alpha > 0) {
@@ -72,6 +83,13 @@ FHE_D void gs_bfly(double& a, double& b, const ConstF w, double q) {
     b = mulmod_const(d, w, q);
 }
 
+FHE_D void prefetch_l2(const void* p) {
+#ifndef FHE_EMU
+    asm volatile("prefetch.global.L2 [%0];" :: "l"(p));
+#else
+    (void)p;
+#endif
+}
 FHE_D ConstF mk_tw(double w, double qinv) { ConstF r; r.w = w; r.wq = d_mul(w, qinv); return r; }
 FHE_D double ld_d(const double* p) {
 #ifndef FHE_EMU
@@ -159,30 +177,35 @@ FHE_D int pad16(int a) { return a + (a >> 4); }
 // A LoadOp returns the element as a (small, signed) double; a StoreOp receives the canonical
 // value in [0, q) as a double.  Each functor carries its own poly stride so source, scratch
 // and destination may have different layouts.
-FHE_D size_t row_off(const RowMap& map, int row, long long poly_stride) {
-    return (size_t)(row / map.rows_per_poly) * (size_t)poly_stride + ((size_t)(row % map.rows_per_poly) << map.log_n);
+FHE_D size_t row_off(const RowMap& map, RowRef row, long long poly_stride) {
+    return (size_t)row.blk * (size_t)poly_stride + ((size_t)row.j << map.log_n);
 }
 struct LoadPlain {          // canonical residues
     const u64* src; long long poly_stride;
-    FHE_D double operator()(const RowMap& map, int row, u32 idx, int, const Modulus&) const {
+    FHE_D double operator()(const RowMap& map, RowRef row, int idx, int, const Modulus&) const {
         return u64_to_f(src[row_off(map, row, poly_stride) + idx]);
+    }
+    // hint: `count` consecutive elements starting at idx will be loaded soon (fused NTT, L2 prefetch)
+    FHE_D void prefetch(const RowMap& map, RowRef row, int idx, int count) const {
+        const u64* p = src + row_off(map, row, poly_stride) + idx;
+        for (int k = 0; k < count; k += 16) prefetch_l2(p + k);
     }
 };
 struct StorePlain {
     u64* dst; long long poly_stride;
-    FHE_D void operator()(const RowMap& map, int row, u32 idx, double v, int, const Modulus&) const {
+    FHE_D void operator()(const RowMap& map, RowRef row, int idx, double v, int, const Modulus&) const {
         dst[row_off(map, row, poly_stride) + idx] = f_to_u64(v);
     }
 };
 struct LoadRaw {            // lazy doubles written by the other pass
     const u64* src; long long poly_stride;
-    FHE_D double operator()(const RowMap& map, int row, u32 idx, int, const Modulus&) const {
+    FHE_D double operator()(const RowMap& map, RowRef row, int idx, int, const Modulus&) const {
         return bits_to_f(src[row_off(map, row, poly_stride) + idx]);
     }
 };
 struct StoreRaw {
     u64* dst; long long poly_stride;
-    FHE_D void operator()(const RowMap& map, int row, u32 idx, double v, int, const Modulus&) const {
+    FHE_D void operator()(const RowMap& map, RowRef row, int idx, double v, int, const Modulus&) const {
         dst[row_off(map, row, poly_stride) + idx] = f_to_bits(v);
     }
 };
@@ -195,6 +218,7 @@ __global__ void __launch_bounds__(256, FHE_PASSA_MINB) ntt_fwd_pass_a(DevTables 
     const int row = map.launch_row(blockIdx.y);
     const int mid = map.mod_id(row);
     if (mid < 0) return;
+    const RowRef rref = map.ref(row);
     const Modulus M = T.mod[mid];
     const double q = M.qd;
     const int log_n = T.log_n;
@@ -205,7 +229,7 @@ __global__ void __launch_bounds__(256, FHE_PASSA_MINB) ntt_fwd_pass_a(DevTables 
     double x[16];
     if (LEV1 > 0) {
 #pragma unroll
-        for (int i = 0; i < 16; ++i) x[i] = ld(map, row, (u32)((g + G * i) << 8) + c, mid, M);
+        for (int i = 0; i < 16; ++i) x[i] = ld(map, rref, (u32)((g + G * i) << 8) + c, mid, M);
         ct_radix16<(16 >> (LEV1 > 0 ? LEV1 : 1))>(x, 1, [&](int S, int, int i) { return mk_tw(ld_d(tw + tw_index(S, (u32)((g + G * i) << 8) + c, log_n)), qinv); }, q);
 #pragma unroll
         for (int i = 0; i < 16; ++i) sm[(g + G * i) * COLS + cc] = x[i];
@@ -214,11 +238,11 @@ __global__ void __launch_bounds__(256, FHE_PASSA_MINB) ntt_fwd_pass_a(DevTables 
         for (int i = 0; i < 16; ++i) x[i] = sm[(16 * g + i) * COLS + cc];
     } else {
 #pragma unroll
-        for (int i = 0; i < 16; ++i) x[i] = ld(map, row, (u32)((16 * g + i) << 8) + c, mid, M);
+        for (int i = 0; i < 16; ++i) x[i] = ld(map, rref, (u32)((16 * g + i) << 8) + c, mid, M);
     }
     ct_radix16<1>(x, LEV1 + 1, [&](int S, int, int i) { return mk_tw(ld_d(tw + tw_index(S, (u32)((16 * g + i) << 8) + c, log_n)), qinv); }, q);
 #pragma unroll
-    for (int i = 0; i < 16; ++i) st(map, row, (u32)((16 * g + i) << 8) + c, x[i], mid, M);
+    for (int i = 0; i < 16; ++i) st(map, rref, (u32)((16 * g + i) << 8) + c, x[i], mid, M);
 }
 
 template <class StoreOp>
@@ -227,6 +251,7 @@ __global__ void __launch_bounds__(256, FHE_PASSB_MINB) ntt_fwd_pass_b(DevTables 
     const int row = map.launch_row(blockIdx.y);
     const int mid = map.mod_id(row);
     if (mid < 0) return;
+    const RowRef rref = map.ref(row);
     const Modulus M = T.mod[mid];
     const double q = M.qd;
     const int log_n = T.log_n;
@@ -236,7 +261,7 @@ __global__ void __launch_bounds__(256, FHE_PASSB_MINB) ntt_fwd_pass_b(DevTables 
     const u32 base = (u32)(blockIdx.x * 16 + rr) << 8;
     double x[16];
 #pragma unroll
-    for (int i = 0; i < 16; ++i) x[i] = ld(map, row, base + l16 + 16 * i, mid, M);
+    for (int i = 0; i < 16; ++i) x[i] = ld(map, rref, base + l16 + 16 * i, mid, M);
     const Tw15 t2 = ld_tw15(tw, base + 16 * l16, log_n);          // issued early, used in round 2
     ct_radix16<1>(x, log_n - 7, [&](int S, int, int i) { return mk_tw(ld_d(tw + tw_index(S, base + l16 + 16 * i, log_n)), qinv); }, q);
 #pragma unroll
@@ -250,7 +275,7 @@ __global__ void __launch_bounds__(256, FHE_PASSB_MINB) ntt_fwd_pass_b(DevTables 
     for (int i = 0; i < 16; ++i) sm[pad16(rr * 256 + 16 * l16 + i)] = reduce_canon(x[i], q, M.qinv);
     __syncthreads();
 #pragma unroll
-    for (int i = 0; i < 16; ++i) st(map, row, base + l16 + 16 * i, sm[pad16(rr * 256 + l16 + 16 * i)], mid, M);
+    for (int i = 0; i < 16; ++i) st(map, rref, base + l16 + 16 * i, sm[pad16(rr * 256 + l16 + 16 * i)], mid, M);
 }
 
 // ------------------------------------------------------------------ inverse kernels
@@ -261,6 +286,7 @@ __global__ void __launch_bounds__(256, FHE_PASSB_MINB) ntt_inv_pass_b(DevTables 
     const int row = map.launch_row(blockIdx.y);
     const int mid = map.mod_id(row);
     if (mid < 0) return;
+    const RowRef rref = map.ref(row);
     const Modulus M = T.mod[mid];
     const double q = M.qd, qinv = M.qinv;
     const int log_n = T.log_n;
@@ -271,7 +297,7 @@ __global__ void __launch_bounds__(256, FHE_PASSB_MINB) ntt_inv_pass_b(DevTables 
     ConstF dummy; dummy.w = 0; dummy.wq = 0;
     const Tw15 t1 = ld_tw15(tw, base + 16 * l16, log_n);
 #pragma unroll
-    for (int i = 0; i < 16; ++i) sm[pad16(rr * 256 + l16 + 16 * i)] = ld(map, row, base + l16 + 16 * i, mid, M);
+    for (int i = 0; i < 16; ++i) sm[pad16(rr * 256 + l16 + 16 * i)] = ld(map, rref, base + l16 + 16 * i, mid, M);
     __syncthreads();
 #pragma unroll
     for (int i = 0; i < 16; ++i) x[i] = sm[pad16(rr * 256 + 16 * l16 + i)];
@@ -284,7 +310,7 @@ __global__ void __launch_bounds__(256, FHE_PASSB_MINB) ntt_inv_pass_b(DevTables 
     for (int i = 0; i < 16; ++i) x[i] = sm[pad16(rr * 256 + l16 + 16 * i)];
     gs_radix16<1, false>(x, log_n - 4, [&](int S, int, int i) { return mk_tw(ld_d(tw + tw_index(S, base + l16 + 16 * i, log_n)), qinv); }, q, dummy, dummy);
 #pragma unroll
-    for (int i = 0; i < 16; ++i) st(map, row, base + l16 + 16 * i, reduce_sym(x[i], q, qinv), mid, M);
+    for (int i = 0; i < 16; ++i) st(map, rref, base + l16 + 16 * i, reduce_sym(x[i], q, qinv), mid, M);
 }
 
 // pass A' : stages log_n-8 .. 1 (row strides 1..R/2); the final stage carries the scaling
@@ -298,17 +324,18 @@ __global__ void __launch_bounds__(256, FHE_PASSA_MINB) ntt_inv_pass_a(DevTables 
     const int row = map.launch_row(blockIdx.y);
     const int mid = map.mod_id(row);
     if (mid < 0) return;
+    const RowRef rref = map.ref(row);
     const Modulus M = T.mod[mid];
     const double q = M.qd, qinv = M.qinv;
     const int log_n = T.log_n;
     const double* tw = T.tw_inv + ((size_t)mid << log_n);
-    const ConstF* fin = scale ? scale + 2 * (size_t)(row % map.rows_per_poly) : T.inv_final + 2 * (size_t)mid;
+    const ConstF* fin = scale ? scale + 2 * (size_t)rref.j : T.inv_final + 2 * (size_t)mid;
     const ConstF fin0 = fin[0], fin1 = fin[1];
     const int tid = threadIdx.x, cc = tid % COLS, g = tid / COLS;
     const u32 c = blockIdx.x * COLS + cc;
     double x[16];
 #pragma unroll
-    for (int i = 0; i < 16; ++i) x[i] = ld(map, row, (u32)((16 * g + i) << 8) + c, mid, M);
+    for (int i = 0; i < 16; ++i) x[i] = ld(map, rref, (u32)((16 * g + i) << 8) + c, mid, M);
     if (LEV1 > 0) {
         gs_radix16<1, false>(x, LOG_R, [&](int S, int, int i) { return mk_tw(ld_d(tw + tw_index(S, (u32)((16 * g + i) << 8) + c, log_n)), qinv); }, q, fin0, fin1);
 #pragma unroll
@@ -318,11 +345,11 @@ __global__ void __launch_bounds__(256, FHE_PASSA_MINB) ntt_inv_pass_a(DevTables 
         for (int i = 0; i < 16; ++i) x[i] = sm[(g + G * i) * COLS + cc];
         gs_radix16<(16 >> (LEV1 > 0 ? LEV1 : 1)), true>(x, LEV1, [&](int S, int, int i) { return mk_tw(ld_d(tw + tw_index(S, (u32)((g + G * i) << 8) + c, log_n)), qinv); }, q, fin0, fin1);
 #pragma unroll
-        for (int i = 0; i < 16; ++i) st(map, row, (u32)((g + G * i) << 8) + c, x[i], mid, M);
+        for (int i = 0; i < 16; ++i) st(map, rref, (u32)((g + G * i) << 8) + c, x[i], mid, M);
     } else {
         gs_radix16<1, true>(x, LOG_R, [&](int S, int, int i) { return mk_tw(ld_d(tw + tw_index(S, (u32)((16 * g + i) << 8) + c, log_n)), qinv); }, q, fin0, fin1);
 #pragma unroll
-        for (int i = 0; i < 16; ++i) st(map, row, (u32)((16 * g + i) << 8) + c, x[i], mid, M);
+        for (int i = 0; i < 16; ++i) st(map, rref, (u32)((16 * g + i) << 8) + c, x[i], mid, M);
     }
 }
 

@@ -40,6 +40,15 @@ const char* fhe_last_error(void);
 /* number of kernels this library has launched since load (bench.py's gpu_launches) */
 uint64_t fhe_launch_count(void);
 
+/* NTT variant used by every entry point below.  Default: the two-pass kernels (csrc/ntt.cuh).
+ * fhe_set_ntt_fused(ctx, 1) (or env FHE_NTT_FUSED=1 at context creation) selects the single-launch
+ * persistent cooperative kernel (csrc/ntt_fused.cuh: each limb read from HBM once and written
+ * once); the first enable runs a short calibration of the group speeds.  Results are
+ * bit-identical.  fhe_ntt_fused_status synchronises the device and returns non-zero if a
+ * hand-over of the fused kernel ever timed out (it never hangs). */
+int fhe_set_ntt_fused(fhe_ctx* ctx, int enabled);
+int fhe_ntt_fused_status(fhe_ctx* ctx);
+
 /* Forward / inverse negacyclic NTT, in place.  Used by encode/encrypt/decrypt
  * (xor_service.py:59-66) and inside every multiply / rotate / conjugate. */
 int fhe_ntt_fwd(fhe_ctx* ctx, void* stream, uint64_t* data, int npoly, int nq, int np);

@@ -100,3 +100,19 @@ void fhe_emu_launch(dim3 g, dim3 b, const std::function<void()>& body) {
     for (int i = 0; i < nthreads; ++i) pool.emplace_back(worker);
     for (auto& t : pool) t.join();
 }
+
+// Persistent kernels whose blocks wait for each other (csrc/ntt_fused.cuh) need every block
+// running at once: one host thread per block.
+void fhe_emu_launch_coresident(dim3 g, dim3 b, const std::function<void()>& body) {
+    const long nblocks = (long)g.x * g.y * g.z;
+    std::vector<std::thread> pool;
+    for (long i = 0; i < nblocks; ++i)
+        pool.emplace_back([&, i]() {
+            BlockRunner runner;
+            gridDim = g;
+            blockDim = b;
+            blockIdx = dim3((unsigned)(i % g.x), (unsigned)((i / g.x) % g.y), (unsigned)(i / ((long)g.x * g.y)));
+            run_block(runner, b, body);
+        });
+    for (auto& t : pool) t.join();
+}

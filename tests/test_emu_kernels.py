@@ -9,14 +9,20 @@ from aes_fhe_b200.params import make_params
 from conftest import make_engines
 
 
-def _emu(P, emu_lib):
-    return CudaBackend(P, _lib_path=emu_lib, _device="cpu")
+def _emu(P, emu_lib, fused=1):
+    """fused=1: the single-launch NTT (csrc/ntt_fused.cuh, the simulator's default); 0: the two-pass kernels."""
+    b = CudaBackend(P, _lib_path=emu_lib, _device="cpu")
+    assert b.lib.fhe_set_ntt_fused(b.ctx, fused) == 0
+    return b
 
 
+@pytest.mark.parametrize("fused", [1, 0])
 @pytest.mark.parametrize("log_n,lvl", [(12, 5), (13, 4), (14, 2)])
-def test_primitives(log_n, lvl, emu_lib, ref_backend_cls):
+def test_primitives(log_n, lvl, fused, emu_lib, ref_backend_cls):
     P = make_params(log_n, lvl)
-    kp.check_primitives(P, _emu(P, emu_lib), ref_backend_cls(P))
+    b = _emu(P, emu_lib, fused)
+    kp.check_primitives(P, b, ref_backend_cls(P))
+    assert b.lib.fhe_ntt_fused_status(b.ctx) == 0
 
 
 def test_primitives_full_ring(emu_lib, ref_backend_cls):
@@ -24,15 +30,17 @@ def test_primitives_full_ring(emu_lib, ref_backend_cls):
     kp.check_primitives(P, _emu(P, emu_lib), ref_backend_cls(P))
 
 
-def test_rescale(emu_lib, ref_backend_cls):
+@pytest.mark.parametrize("fused", [1, 0])
+def test_rescale(fused, emu_lib, ref_backend_cls):
     P = make_params(12, 6)
-    kp.check_rescale(P, _emu(P, emu_lib), ref_backend_cls(P))
+    kp.check_rescale(P, _emu(P, emu_lib, fused), ref_backend_cls(P))
 
 
+@pytest.mark.parametrize("fused", [1, 0])
 @pytest.mark.parametrize("log_n,lvl,dnum", [(12, 6, 4), (12, 7, 3), (13, 4, 2)])
-def test_keyswitch_phases(log_n, lvl, dnum, emu_lib, ref_backend_cls):
+def test_keyswitch_phases(log_n, lvl, dnum, fused, emu_lib, ref_backend_cls):
     P = make_params(log_n, lvl, dnum=dnum)
-    kp.check_keyswitch(P, _emu(P, emu_lib), ref_backend_cls(P))
+    kp.check_keyswitch(P, _emu(P, emu_lib, fused), ref_backend_cls(P))
 
 
 def test_engine_ops(emu_lib, ref_backend_cls):

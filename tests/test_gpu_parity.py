@@ -107,3 +107,32 @@ def test_device_codec_roundtrip_and_compat(cuda_lib):
     assert np.abs(eng.decrypt(sq, sk) - v * v).max() < 1e-5
     short = eng.decrypt(eng.encrypt(np.array([1.0, 2.0, 3.0]), pk), sk)
     assert np.allclose(short[:3], [1, 2, 3], atol=5e-6) and np.allclose(short[3:], 0, atol=5e-6)
+
+
+def test_fused_ntt_equals_two_pass_at_scale(ref_backend_cls, cuda_lib):
+    """The single-launch NTT (csrc/ntt_fused.cuh: persistent groups, L2-resident scratch, group
+    barriers) against the two-pass kernels on far more rows than there are groups, including the
+    fused load/store functors (rescale, key switch, mod-raise); no barrier may have timed out."""
+    from conftest import rand_poly
+    P = make_params(16, 30)
+    gb = _gpu(P)
+    rng = np.random.default_rng(11)
+    nq, K = P.n_q, P.n_p
+    a = gb.from_numpy(rand_poly(P, rng, 2, nq, True, batch=12))            # 24 x 39 = 936 rows
+    d = gb.from_numpy(rand_poly(P, rng, 1, 25, False, batch=5))
+    ksk = gb.from_numpy(np.stack([rand_poly(P, rng, 2, nq, True) for _ in range(P.dnum)]))
+    r = gb.from_numpy(rand_poly(P, rng, 3, 17, False, batch=3))
+    outs = []
+    for fused in (1, 0):
+        assert gb.lib.fhe_set_ntt_fused(gb.ctx, fused) == 0
+        f = gb.ntt(a, nq, K)
+        outs.append([f, gb.intt(a, nq, K), gb.intt(f, nq, K), gb.keyswitch(d, ksk, 25), gb.rescale(r, 17),
+                     gb.mod_raise(r[:, :, :1].contiguous(), 9)])
+    assert gb.lib.fhe_ntt_fused_status(gb.ctx) == 0
+    for x, y in zip(*outs):
+        assert torch.equal(x, y)
+    assert torch.equal(outs[0][2], a)
+    # one row against the oracle
+    one = rand_poly(P, rng, 1, nq, True)
+    assert gb.lib.fhe_set_ntt_fused(gb.ctx, 1) == 0
+    assert np.array_equal(gb.to_numpy(gb.ntt(gb.from_numpy(one), nq, K)), ref_backend_cls(P).ntt(one, nq, K))

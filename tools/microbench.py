@@ -62,12 +62,18 @@ def main():
     m, mn = timeit(lambda: b.copy_(a), flush=flush)
     rec("torch_copy_ref", m, mn, 2 * a.numel() * 8)
 
-    for rows in (tot, 2 * tot, 8 * tot, 32 * tot):
-        x = rnd(rows // tot, tot, n)
-        m, mn = timeit(lambda: gb._call("fhe_ntt_fwd", gb._ptr(x), x.shape[0], 31, K), flush=flush)
-        rec("ntt_fwd", m, mn, 2 * rows * limb, rows=rows)
-        m, mn = timeit(lambda: gb._call("fhe_ntt_inv", gb._ptr(x), x.shape[0], 31, K), flush=flush)
-        rec("ntt_inv", m, mn, 2 * rows * limb, rows=rows)
+    for fused in (0, 1):
+        gb.lib.fhe_set_ntt_fused(gb.ctx, fused)
+        tag = "fused" if fused else "two_pass"
+        for rows in (tot, 2 * tot, 8 * tot, 32 * tot):
+            x = rnd(rows // tot, tot, n)
+            m, mn = timeit(lambda: gb._call("fhe_ntt_fwd", gb._ptr(x), x.shape[0], 31, K), flush=flush)
+            rec("ntt_fwd." + tag, m, mn, 2 * rows * limb, rows=rows)
+            m, mn = timeit(lambda: gb._call("fhe_ntt_inv", gb._ptr(x), x.shape[0], 31, K), flush=flush)
+            rec("ntt_inv." + tag, m, mn, 2 * rows * limb, rows=rows)
+    assert gb.lib.fhe_ntt_fused_status(gb.ctx) == 0, "fused NTT barrier timed out"
+    if os.environ.get("FHE_NTT_FUSED") == "0":
+        gb.lib.fhe_set_ntt_fused(gb.ctx, 0)
 
     for nq in (() if only_ntt else (31, 21, 11)):
         x = rnd(2, nq, n); y = rnd(2, nq, n); o = torch.empty_like(x)
