@@ -60,14 +60,15 @@ def _inputs(slot_count: int, batch: int, seed: int) -> np.ndarray:
     return np.stack(rows)
 
 
-def _make_service(backend=None, seed=1):
+def _make_service(backend=None, seed=1, device_id=0):
     from aes_fhe_b200.params import make_params
     from aes_fhe_b200.services.engine_context import EngineContext
     from aes_fhe_b200.services.sbox_service import SBoxService
     kw = dict(_params=make_params(LOG_N, MAX_LEVEL), seed=seed)
     if backend is not None:
         kw["_backend"] = backend
-    ctx = EngineContext(signature=2, max_level=MAX_LEVEL, mode="parallel", _engine_kwargs=kw, rotation_steps=[])
+    ctx = EngineContext(signature=2, max_level=MAX_LEVEL, mode="parallel", device_id=device_id, _engine_kwargs=kw,
+                        rotation_steps=[])
     return ctx, SBoxService(ctx)
 
 
@@ -225,7 +226,7 @@ def main():
     from aes_fhe_b200.services.sbox_service import AES_SBOX
     import aes_fhe_b200.backend_cuda as bc
 
-    ctx, svc = _make_service(seed=1)
+    ctx, svc = _make_service(seed=1, device_id=local)
     eng = ctx.engine
     be = eng.backend
     if world > 1:
