@@ -276,6 +276,13 @@ __global__ void __launch_bounds__(256) k_bconv(DevTables T, const BConvTable* ta
 // key word is read from HBM once per batch.      ksk: [dnum][2][n_q_total + n_p][N]
 // ext: [batch][beta][ne][N], d: [batch][nq][N], acc: [2][batch][ne][N]
 #define FHE_MAX_BETA 8
+FHE_D u64 ld_u64(const u64* p) {
+#ifndef FHE_EMU
+    return __ldg(p);
+#else
+    return *p;
+#endif
+}
 struct U2 { u64 x, y; };
 FHE_D U2 ld2(const u64* p) {
 #ifndef FHE_EMU
@@ -292,8 +299,11 @@ FHE_D void st2(u64* p, u64 a, u64 b) {
     p[0] = a; p[1] = b;
 #endif
 }
-// grid: (N/512, nq + n_p); every thread owns two consecutive coefficients (16-byte accesses)
-template <int BMAX>
+// grid: (N/256, nq + n_p).  A thread owns one coefficient of one limb for the whole batch: the key
+// words are read once (2 * beta doubles in registers), then the batch is walked UNR ciphertexts at
+// a time with all UNR * (beta + 2) loads issued before the first multiply -- the kernel is
+// HBM-bound and what matters is the number of bytes in flight per SM (Little's law: ~150 KB).
+template <int BMAX, int UNR>
 __global__ void __launch_bounds__(256, (BMAX <= 4 ? 3 : 2)) k_ks_inner(DevTables T, int nq, int alpha, int beta, int batch,
                                                   u64* acc, const u64* ext, const u64* d, const u64* ksk,
                                                   const u64* lift, const ConstF* lift_c) {
@@ -303,48 +313,63 @@ __global__ void __launch_bounds__(256, (BMAX <= 4 ? 3 : 2)) k_ks_inner(DevTables
     const Modulus M = T.mod[id];
     const double q = M.qd, qi = M.qinv;
     const int log_n = T.log_n;
-    const u32 idx = (blockIdx.x * 256 + threadIdx.x) * 2;
+    const int idx = blockIdx.x * 256 + threadIdx.x;
     const size_t tot = (size_t)(T.n_q + T.n_p);
-    double k0[BMAX][2], k1[BMAX][2];
+    double k0[BMAX], k1[BMAX];
 #pragma unroll
     for (int j = 0; j < BMAX; ++j) {
         if (j < beta) {
             const u64* kp = ksk + ((((size_t)j * 2) * tot + id) << log_n) + idx;
-            const U2 a = ld2(kp), b = ld2(kp + (tot << log_n));
-            k0[j][0] = u64_to_f(a.x); k0[j][1] = u64_to_f(a.y);
-            k1[j][0] = u64_to_f(b.x); k1[j][1] = u64_to_f(b.y);
-        } else { k0[j][0] = k0[j][1] = k1[j][0] = k1[j][1] = 0.0; }
+            k0[j] = u64_to_f(ld_u64(kp)); k1[j] = u64_to_f(ld_u64(kp + (tot << log_n)));
+        } else { k0[j] = k1[j] = 0.0; }
     }
     const int own = t < nq ? t / alpha : -1;
-    for (int b = 0; b < batch; ++b) {
-        double a0[2] = {0.0, 0.0}, a1[2] = {0.0, 0.0};
+    const bool has_lift = lift != nullptr && t < nq;
+    const size_t ps = (size_t)batch * nq << log_n;
+    ConstF pc; pc.w = 0; pc.wq = 0;
+    if (has_lift) pc = lift_c[t];
+    const u64* dp = d + ((size_t)t << log_n) + idx;                 // + b * nq * N
+    const u64* ep = ext + ((size_t)t << log_n) + idx;               // + (b * beta + j) * ne * N
+    const u64* lp = has_lift ? lift + ((size_t)t << log_n) + idx : nullptr;
+    for (int b0 = 0; b0 < batch; b0 += UNR) {
+        u64 e[UNR][BMAX], l0[UNR], l1[UNR];
 #pragma unroll
-        for (int j = 0; j < BMAX; ++j) {
-            if (j < beta) {
-                const U2 e = ld2(j == own ? d + (((size_t)b * nq + t) << log_n) + idx
-                                          : ext + ((((size_t)b * beta + j) * ne + t) << log_n) + idx);
-                const double e0 = u64_to_f(e.x), e1 = u64_to_f(e.y);
-                a0[0] = d_add(a0[0], mulmod_var(e0, k0[j][0], q, qi));
-                a0[1] = d_add(a0[1], mulmod_var(e1, k0[j][1], q, qi));
-                a1[0] = d_add(a1[0], mulmod_var(e0, k1[j][0], q, qi));
-                a1[1] = d_add(a1[1], mulmod_var(e1, k1[j][1], q, qi));
+        for (int u = 0; u < UNR; ++u) {
+            const int b = b0 + u;
+            if (b < batch) {
+#pragma unroll
+                for (int j = 0; j < BMAX; ++j)
+                    if (j < beta)
+                        e[u][j] = ld_u64(j == own ? dp + (((size_t)b * nq) << log_n)
+                                                  : ep + ((((size_t)b * beta + j) * ne) << log_n));
+                if (has_lift) {
+                    l0[u] = ld_u64(lp + (((size_t)b * nq) << log_n));
+                    l1[u] = ld_u64(lp + ps + (((size_t)b * nq) << log_n));
+                }
             }
         }
-        if (lift != nullptr && t < nq) {
-            // fused relinearise + rescale: add P * (d0, d1) so the sum can be divided by P q_last at once
-            const ConstF pc = lift_c[t];
-            const size_t ps = (size_t)batch * nq << log_n;
-            const U2 l0 = ld2(lift + (((size_t)b * nq + t) << log_n) + idx);
-            const U2 l1 = ld2(lift + ps + (((size_t)b * nq + t) << log_n) + idx);
-            a0[0] = d_add(a0[0], mulmod_const(u64_to_f(l0.x), pc, q));
-            a0[1] = d_add(a0[1], mulmod_const(u64_to_f(l0.y), pc, q));
-            a1[0] = d_add(a1[0], mulmod_const(u64_to_f(l1.x), pc, q));
-            a1[1] = d_add(a1[1], mulmod_const(u64_to_f(l1.y), pc, q));
+#pragma unroll
+        for (int u = 0; u < UNR; ++u) {
+            const int b = b0 + u;
+            if (b < batch) {
+                double a0 = 0.0, a1 = 0.0;
+#pragma unroll
+                for (int j = 0; j < BMAX; ++j) {
+                    if (j < beta) {
+                        const double ev = u64_to_f(e[u][j]);
+                        a0 = d_add(a0, mulmod_var(ev, k0[j], q, qi));
+                        a1 = d_add(a1, mulmod_var(ev, k1[j], q, qi));
+                    }
+                }
+                if (has_lift) {
+                    // fused relinearise + rescale: add P * (d0, d1) so the sum can be divided by P q_last at once
+                    a0 = d_add(a0, mulmod_const(u64_to_f(l0[u]), pc, q));
+                    a1 = d_add(a1, mulmod_const(u64_to_f(l1[u]), pc, q));
+                }
+                acc[(((size_t)b * ne + t) << log_n) + idx] = f_to_u64(reduce_canon(a0, q, qi));
+                acc[((((size_t)batch + b) * ne + t) << log_n) + idx] = f_to_u64(reduce_canon(a1, q, qi));
+            }
         }
-        st2(acc + (((size_t)b * ne + t) << log_n) + idx,
-            f_to_u64(reduce_canon(a0[0], q, qi)), f_to_u64(reduce_canon(a0[1], q, qi)));
-        st2(acc + ((((size_t)batch + b) * ne + t) << log_n) + idx,
-            f_to_u64(reduce_canon(a1[0], q, qi)), f_to_u64(reduce_canon(a1[1], q, qi)));
     }
 }
 
