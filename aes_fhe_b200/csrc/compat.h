@@ -43,6 +43,7 @@ FHE_D u32 brev32(u32 x) { return __brev(x); }
 #define __forceinline__ inline
 #define __restrict__
 #define __launch_bounds__(...)
+#define __align__(n) __attribute__((aligned(n)))
 #define FHE_HD inline
 #define FHE_D inline
 #define FHE_SHARED static thread_local

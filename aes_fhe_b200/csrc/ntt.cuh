@@ -210,146 +210,230 @@ struct StoreRaw {
     }
 };
 
-// ------------------------------------------------------------------ forward kernels
+// ------------------------------------------------------------------ two-pass kernels
+// Grid: (tiles, n_blocks, rows_per_poly) -- blockIdx.y is the poly block, blockIdx.z the limb slot,
+// so no division is needed to find the row; launch order is limb-major (z outermost), which
+// keeps the CTAs sharing one twiddle table co-resident (L2 reuse).  LOG_N, the tile shape and
+// the stage are compile-time, indices are signed ints: after unrolling every access is
+// `base register + immediate`.
+//
+// Twiddle index algebra (element e, stage S, LOG_N = LOG_R + 8): tw_index = 2^(S-1) + (e >> (LOG_N-S+1)).
+//   column pass, first round  (S = 1..LEV1, registers hold rows g + G i):   2^(S-1) + (i >> (5-S))          (thread-independent)
+//   column pass, second round (S = LEV1+t, rows 16 g + i):                  2^(S-1) + (g << (t-1)) + (i >> (5-t))
+//   row pass (S = LOG_R+s, 256-element row `grow`, local element e):        2^(S-1) + (grow << (s-1)) + (e >> (9-s))
+FHE_D int ntt_dig(const RowMap& map, int blk) { return map.skip_alpha > 0 ? blk % map.digits : 0; }
+
+#ifndef FHE_EMU
+FHE_D void ntt_sync_warp() { __syncwarp(); }
+#else
+inline void ntt_sync_warp() { __syncthreads(); }       // control flow is CTA-uniform: equivalent
+#endif
+// 16 contiguous doubles <-> registers with 16-byte shared-memory accesses
+FHE_D void lds16(double (&x)[16], const double* p) {
+#ifndef FHE_EMU
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { const double2 v = reinterpret_cast<const double2*>(p)[i]; x[2 * i] = v.x; x[2 * i + 1] = v.y; }
+#else
+    for (int i = 0; i < 16; ++i) x[i] = p[i];
+#endif
+}
+FHE_D void sts16(double* p, const double (&x)[16]) {
+#ifndef FHE_EMU
+#pragma unroll
+    for (int i = 0; i < 8; ++i) reinterpret_cast<double2*>(p)[i] = make_double2(x[2 * i], x[2 * i + 1]);
+#else
+    for (int i = 0; i < 16; ++i) p[i] = x[i];
+#endif
+}
+#define FHE_ROW_STRIDE 288     /* a 256-element row as 16 blocks of 16 (+2 pad): LDS.128, conflict-free both ways */
+
+template <int LOG_R>
+FHE_D double tw_col_r1(const double* tw, int S, int i) { return ld_d(tw + (1 << (S - 1)) + (i >> (5 - S))); }
+template <int LOG_R>
+FHE_D double tw_col_r2(const double* tw, int g, int S, int i) {
+    constexpr int LEV1 = LOG_R - 4;
+    const int t = S - LEV1;
+    return ld_d(tw + (1 << (S - 1)) + (g << (t - 1)) + (i >> (5 - t)));
+}
+// the 15 twiddles of the last four stages for the 16 contiguous elements of block `blk16` of the limb
+template <int LOG_N>
+FHE_D Tw15 ld_tw15c(const double* tw, int blk16) {
+    Tw15 t;
+    constexpr int n16 = 1 << (LOG_N - 4);
+    t.w[0] = ld_d(tw + n16 + blk16);
+#ifndef FHE_EMU
+    const double2 a = __ldg(reinterpret_cast<const double2*>(tw + 2 * n16) + blk16);
+    t.w[1] = a.x; t.w[2] = a.y;
+    const double2* p4 = reinterpret_cast<const double2*>(tw + 4 * n16) + 2 * blk16;
+    const double2 b0 = __ldg(p4), b1 = __ldg(p4 + 1);
+    t.w[3] = b0.x; t.w[4] = b0.y; t.w[5] = b1.x; t.w[6] = b1.y;
+    const double2* p8 = reinterpret_cast<const double2*>(tw + 8 * n16) + 4 * blk16;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { const double2 c = __ldg(p8 + j); t.w[7 + 2 * j] = c.x; t.w[8 + 2 * j] = c.y; }
+#else
+    for (int j = 0; j < 2; ++j) t.w[1 + j] = tw[2 * (n16 + blk16) + j];
+    for (int j = 0; j < 4; ++j) t.w[3 + j] = tw[4 * (n16 + blk16) + j];
+    for (int j = 0; j < 8; ++j) t.w[7 + j] = tw[8 * (n16 + blk16) + j];
+#endif
+    return t;
+}
+
+// ------------------------------------------------------------------ forward
 template <int LOG_R, class LoadOp>
 __global__ void __launch_bounds__(256, FHE_PASSA_MINB) ntt_fwd_pass_a(DevTables T, RowMap map, LoadOp ld, StoreRaw st) {
-    constexpr int R = 1 << LOG_R, G = R / 16, COLS = 256 / G, LEV1 = LOG_R - 4;
+    constexpr int R = 1 << LOG_R, G = R / 16, COLS = 256 / G, LEV1 = LOG_R - 4, LOG_N = LOG_R + 8;
     FHE_SHARED double sm[4096];
-    const int row = map.launch_row(blockIdx.y);
-    const int mid = map.mod_id(row);
+    RowRef rref; rref.blk = blockIdx.y; rref.j = blockIdx.z;
+    const int mid = map.mod_id_of(rref.j, ntt_dig(map, rref.blk));
     if (mid < 0) return;
-    const RowRef rref = map.ref(row);
-    const Modulus M = T.mod[mid];
-    const double q = M.qd;
-    const int log_n = T.log_n;
-    const double* tw = T.tw_fwd + ((size_t)mid << log_n);
-    const double qinv = M.qinv;
-    const int tid = threadIdx.x, cc = tid % COLS, g = tid / COLS;
-    const u32 c = blockIdx.x * COLS + cc;
-    double x[16];
-    if (LEV1 > 0) {
-#pragma unroll
-        for (int i = 0; i < 16; ++i) x[i] = ld(map, rref, (u32)((g + G * i) << 8) + c, mid, M);
-        ct_radix16<(16 >> (LEV1 > 0 ? LEV1 : 1))>(x, 1, [&](int S, int, int i) { return mk_tw(ld_d(tw + tw_index(S, (u32)((g + G * i) << 8) + c, log_n)), qinv); }, q);
-#pragma unroll
-        for (int i = 0; i < 16; ++i) sm[(g + G * i) * COLS + cc] = x[i];
-        __syncthreads();
-#pragma unroll
-        for (int i = 0; i < 16; ++i) x[i] = sm[(16 * g + i) * COLS + cc];
-    } else {
-#pragma unroll
-        for (int i = 0; i < 16; ++i) x[i] = ld(map, rref, (u32)((16 * g + i) << 8) + c, mid, M);
-    }
-    ct_radix16<1>(x, LEV1 + 1, [&](int S, int, int i) { return mk_tw(ld_d(tw + tw_index(S, (u32)((16 * g + i) << 8) + c, log_n)), qinv); }, q);
-#pragma unroll
-    for (int i = 0; i < 16; ++i) st(map, rref, (u32)((16 * g + i) << 8) + c, x[i], mid, M);
-}
-
-template <class StoreOp>
-__global__ void __launch_bounds__(256, FHE_PASSB_MINB) ntt_fwd_pass_b(DevTables T, RowMap map, LoadRaw ld, StoreOp st) {
-    FHE_SHARED double sm[4096 + 256];
-    const int row = map.launch_row(blockIdx.y);
-    const int mid = map.mod_id(row);
-    if (mid < 0) return;
-    const RowRef rref = map.ref(row);
-    const Modulus M = T.mod[mid];
-    const double q = M.qd;
-    const int log_n = T.log_n;
-    const double* tw = T.tw_fwd + ((size_t)mid << log_n);
-    const double qinv = M.qinv;
-    const int tid = threadIdx.x, l16 = tid & 15, rr = tid >> 4;
-    const u32 base = (u32)(blockIdx.x * 16 + rr) << 8;
-    double x[16];
-#pragma unroll
-    for (int i = 0; i < 16; ++i) x[i] = ld(map, rref, base + l16 + 16 * i, mid, M);
-    const Tw15 t2 = ld_tw15(tw, base + 16 * l16, log_n);          // issued early, used in round 2
-    ct_radix16<1>(x, log_n - 7, [&](int S, int, int i) { return mk_tw(ld_d(tw + tw_index(S, base + l16 + 16 * i, log_n)), qinv); }, q);
-#pragma unroll
-    for (int i = 0; i < 16; ++i) sm[pad16(rr * 256 + l16 + 16 * i)] = x[i];
-    __syncthreads();
-#pragma unroll
-    for (int i = 0; i < 16; ++i) x[i] = sm[pad16(rr * 256 + 16 * l16 + i)];
-    ct_radix16<1>(x, log_n - 3, [&](int, int half, int i) { return mk_tw(t2.w[8 / half - 1 + i / (2 * half)], qinv); }, q);
-    __syncthreads();
-#pragma unroll
-    for (int i = 0; i < 16; ++i) sm[pad16(rr * 256 + 16 * l16 + i)] = reduce_canon(x[i], q, M.qinv);
-    __syncthreads();
-#pragma unroll
-    for (int i = 0; i < 16; ++i) st(map, rref, base + l16 + 16 * i, sm[pad16(rr * 256 + l16 + 16 * i)], mid, M);
-}
-
-// ------------------------------------------------------------------ inverse kernels
-// pass B' : stages log_n .. log_n-7 (strides 1..128) on 16 contiguous rows of 256.
-template <class LoadOp>
-__global__ void __launch_bounds__(256, FHE_PASSB_MINB) ntt_inv_pass_b(DevTables T, RowMap map, LoadOp ld, StoreRaw st) {
-    FHE_SHARED double sm[4096 + 256];
-    const int row = map.launch_row(blockIdx.y);
-    const int mid = map.mod_id(row);
-    if (mid < 0) return;
-    const RowRef rref = map.ref(row);
     const Modulus M = T.mod[mid];
     const double q = M.qd, qinv = M.qinv;
-    const int log_n = T.log_n;
-    const double* tw = T.tw_inv + ((size_t)mid << log_n);
-    const int tid = threadIdx.x, l16 = tid & 15, rr = tid >> 4;
-    const u32 base = (u32)(blockIdx.x * 16 + rr) << 8;
+    const double* tw = T.tw_fwd + ((size_t)mid << LOG_N);
+    const int tid = threadIdx.x, cc = tid % COLS, g = tid / COLS;
+    const int c = blockIdx.x * COLS + cc;
     double x[16];
-    ConstF dummy; dummy.w = 0; dummy.wq = 0;
-    const Tw15 t1 = ld_tw15(tw, base + 16 * l16, log_n);
+    if (LEV1 > 0) {
+        const int e0 = (g << 8) + c;
 #pragma unroll
-    for (int i = 0; i < 16; ++i) sm[pad16(rr * 256 + l16 + 16 * i)] = ld(map, rref, base + l16 + 16 * i, mid, M);
-    __syncthreads();
+        for (int i = 0; i < 16; ++i) x[i] = ld(map, rref, e0 + i * (G << 8), mid, M);
+        ct_radix16<(16 >> (LEV1 > 0 ? LEV1 : 1))>(x, 1, [&](int S, int, int i) { return mk_tw(tw_col_r1<LOG_R>(tw, S, i), qinv); }, q);
+        double* smw = sm + g * COLS + cc;
 #pragma unroll
-    for (int i = 0; i < 16; ++i) x[i] = sm[pad16(rr * 256 + 16 * l16 + i)];
-    gs_radix16<1, false>(x, log_n, [&](int, int half, int i) { return mk_tw(t1.w[8 / half - 1 + i / (2 * half)], qinv); }, q, dummy, dummy);
-    __syncthreads();
+        for (int i = 0; i < 16; ++i) smw[i * (G * COLS)] = x[i];
+        __syncthreads();
+        const double* smr = sm + 16 * g * COLS + cc;
 #pragma unroll
-    for (int i = 0; i < 16; ++i) sm[pad16(rr * 256 + 16 * l16 + i)] = reduce_sym(x[i], q, qinv);
-    __syncthreads();
+        for (int i = 0; i < 16; ++i) x[i] = smr[i * COLS];
+    } else {
+        const int e0 = (g << 12) + c;
 #pragma unroll
-    for (int i = 0; i < 16; ++i) x[i] = sm[pad16(rr * 256 + l16 + 16 * i)];
-    gs_radix16<1, false>(x, log_n - 4, [&](int S, int, int i) { return mk_tw(ld_d(tw + tw_index(S, base + l16 + 16 * i, log_n)), qinv); }, q, dummy, dummy);
+        for (int i = 0; i < 16; ++i) x[i] = ld(map, rref, e0 + (i << 8), mid, M);
+    }
+    ct_radix16<1>(x, LEV1 + 1, [&](int S, int, int i) { return mk_tw(tw_col_r2<LOG_R>(tw, g, S, i), qinv); }, q);
+    const int o0 = (g << 12) + c;
 #pragma unroll
-    for (int i = 0; i < 16; ++i) st(map, rref, base + l16 + 16 * i, reduce_sym(x[i], q, qinv), mid, M);
+    for (int i = 0; i < 16; ++i) st(map, rref, o0 + (i << 8), x[i], mid, M);
 }
 
-// pass A' : stages log_n-8 .. 1 (row strides 1..R/2); the final stage carries the scaling
-// constants scale[row % rows_per_poly] = {c * N^-1, c * psi^-bitrev(1) * N^-1} (c = 1 when
-// scale == nullptr).
+template <int LOG_N, class StoreOp>
+__global__ void __launch_bounds__(256, FHE_PASSB_MINB) ntt_fwd_pass_b(DevTables T, RowMap map, LoadRaw ld, StoreOp st) {
+    constexpr int LOG_R = LOG_N - 8, RS = FHE_ROW_STRIDE;
+    FHE_SHARED __align__(16) double sm[16 * RS];
+    RowRef rref; rref.blk = blockIdx.y; rref.j = blockIdx.z;
+    const int mid = map.mod_id_of(rref.j, ntt_dig(map, rref.blk));
+    if (mid < 0) return;
+    const Modulus M = T.mod[mid];
+    const double q = M.qd, qinv = M.qinv;
+    const double* tw = T.tw_fwd + ((size_t)mid << LOG_N);
+    const int tid = threadIdx.x, l16 = tid & 15, rr = tid >> 4;
+    const int grow = blockIdx.x * 16 + rr;                    // 256-element row of the limb
+    const int rbase = (grow << 8) + l16;
+    double* smS = sm + rr * RS + l16;                         // strided view    [18 * i]
+    double* smC = sm + rr * RS + 18 * l16;                    // contiguous view [i]
+    double x[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) x[i] = ld(map, rref, rbase + 16 * i, mid, M);
+    const Tw15 t2 = ld_tw15c<LOG_N>(tw, grow * 16 + l16);     // issued early, used in round 2
+    {
+        const double* t1 = tw + (1 << LOG_R) + grow, *t2p = tw + (2 << LOG_R) + 2 * grow,
+                    *t3 = tw + (4 << LOG_R) + 4 * grow, *t4 = tw + (8 << LOG_R) + 8 * grow;
+        ct_radix16<1>(x, 1, [&](int s, int, int i) {
+            return mk_tw(ld_d(s == 1 ? t1 : s == 2 ? t2p + (i >> 3) : s == 3 ? t3 + (i >> 2) : t4 + (i >> 1)), qinv); }, q);
+    }
+#pragma unroll
+    for (int i = 0; i < 16; ++i) smS[18 * i] = x[i];
+    ntt_sync_warp();                                          // a row is owned by 16 lanes of one warp
+    lds16(x, smC);
+    ct_radix16<1>(x, 5, [&](int, int half, int i) { return mk_tw(t2.w[8 / half - 1 + i / (2 * half)], qinv); }, q);
+    ntt_sync_warp();
+#pragma unroll
+    for (int i = 0; i < 16; ++i) x[i] = reduce_canon(x[i], q, qinv);
+    sts16(smC, x);
+    ntt_sync_warp();
+#pragma unroll
+    for (int i = 0; i < 16; ++i) st(map, rref, rbase + 16 * i, smS[18 * i], mid, M);
+}
+
+// ------------------------------------------------------------------ inverse
+// pass B' : stages LOG_N .. LOG_N-7 (strides 1..128) on 16 contiguous rows of 256.
+template <int LOG_N, class LoadOp>
+__global__ void __launch_bounds__(256, FHE_PASSB_MINB) ntt_inv_pass_b(DevTables T, RowMap map, LoadOp ld, StoreRaw st) {
+    constexpr int LOG_R = LOG_N - 8, RS = FHE_ROW_STRIDE;
+    FHE_SHARED __align__(16) double sm[16 * RS];
+    RowRef rref; rref.blk = blockIdx.y; rref.j = blockIdx.z;
+    const int mid = map.mod_id_of(rref.j, ntt_dig(map, rref.blk));
+    if (mid < 0) return;
+    const Modulus M = T.mod[mid];
+    const double q = M.qd, qinv = M.qinv;
+    const double* tw = T.tw_inv + ((size_t)mid << LOG_N);
+    const int tid = threadIdx.x, l16 = tid & 15, rr = tid >> 4;
+    const int grow = blockIdx.x * 16 + rr;
+    const int rbase = (grow << 8) + l16;
+    double* smS = sm + rr * RS + l16;
+    double* smC = sm + rr * RS + 18 * l16;
+    double x[16];
+    ConstF dummy; dummy.w = 0; dummy.wq = 0;
+    const Tw15 t1 = ld_tw15c<LOG_N>(tw, grow * 16 + l16);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) smS[18 * i] = ld(map, rref, rbase + 16 * i, mid, M);
+    ntt_sync_warp();
+    lds16(x, smC);
+    gs_radix16<1, false>(x, 8, [&](int, int half, int i) { return mk_tw(t1.w[8 / half - 1 + i / (2 * half)], qinv); }, q, dummy, dummy);
+    ntt_sync_warp();
+#pragma unroll
+    for (int i = 0; i < 16; ++i) x[i] = reduce_sym(x[i], q, qinv);
+    sts16(smC, x);
+    ntt_sync_warp();
+#pragma unroll
+    for (int i = 0; i < 16; ++i) x[i] = smS[18 * i];
+    {
+        const double* t1p = tw + (1 << LOG_R) + grow, *t2p = tw + (2 << LOG_R) + 2 * grow,
+                    *t3 = tw + (4 << LOG_R) + 4 * grow, *t4 = tw + (8 << LOG_R) + 8 * grow;
+        gs_radix16<1, false>(x, 4, [&](int s, int, int i) {
+            return mk_tw(ld_d(s == 1 ? t1p : s == 2 ? t2p + (i >> 3) : s == 3 ? t3 + (i >> 2) : t4 + (i >> 1)), qinv); }, q, dummy, dummy);
+    }
+#pragma unroll
+    for (int i = 0; i < 16; ++i) st(map, rref, rbase + 16 * i, reduce_sym(x[i], q, qinv), mid, M);
+}
+
+// pass A' : stages LOG_R .. 1 (row strides 1..R/2); the final stage carries the scaling
+// constants scale[limb slot] = {c * N^-1, c * psi^-bitrev(1) * N^-1} (c = 1 when scale == nullptr).
 template <int LOG_R, class StoreOp>
 __global__ void __launch_bounds__(256, FHE_PASSA_MINB) ntt_inv_pass_a(DevTables T, RowMap map, LoadRaw ld, StoreOp st,
                                                       const ConstF* scale) {
-    constexpr int R = 1 << LOG_R, G = R / 16, COLS = 256 / G, LEV1 = LOG_R - 4;
+    constexpr int R = 1 << LOG_R, G = R / 16, COLS = 256 / G, LEV1 = LOG_R - 4, LOG_N = LOG_R + 8;
     FHE_SHARED double sm[4096];
-    const int row = map.launch_row(blockIdx.y);
-    const int mid = map.mod_id(row);
+    RowRef rref; rref.blk = blockIdx.y; rref.j = blockIdx.z;
+    const int mid = map.mod_id_of(rref.j, ntt_dig(map, rref.blk));
     if (mid < 0) return;
-    const RowRef rref = map.ref(row);
     const Modulus M = T.mod[mid];
     const double q = M.qd, qinv = M.qinv;
-    const int log_n = T.log_n;
-    const double* tw = T.tw_inv + ((size_t)mid << log_n);
+    const double* tw = T.tw_inv + ((size_t)mid << LOG_N);
     const ConstF* fin = scale ? scale + 2 * (size_t)rref.j : T.inv_final + 2 * (size_t)mid;
     const ConstF fin0 = fin[0], fin1 = fin[1];
     const int tid = threadIdx.x, cc = tid % COLS, g = tid / COLS;
-    const u32 c = blockIdx.x * COLS + cc;
+    const int c = blockIdx.x * COLS + cc;
     double x[16];
+    const int e1 = (g << 12) + c;
 #pragma unroll
-    for (int i = 0; i < 16; ++i) x[i] = ld(map, rref, (u32)((16 * g + i) << 8) + c, mid, M);
+    for (int i = 0; i < 16; ++i) x[i] = ld(map, rref, e1 + (i << 8), mid, M);
     if (LEV1 > 0) {
-        gs_radix16<1, false>(x, LOG_R, [&](int S, int, int i) { return mk_tw(ld_d(tw + tw_index(S, (u32)((16 * g + i) << 8) + c, log_n)), qinv); }, q, fin0, fin1);
+        gs_radix16<1, false>(x, LOG_R, [&](int S, int, int i) { return mk_tw(tw_col_r2<LOG_R>(tw, g, S, i), qinv); }, q, fin0, fin1);
+        double* smw = sm + 16 * g * COLS + cc;
 #pragma unroll
-        for (int i = 0; i < 16; ++i) sm[(16 * g + i) * COLS + cc] = reduce_sym(x[i], q, qinv);
+        for (int i = 0; i < 16; ++i) smw[i * COLS] = reduce_sym(x[i], q, qinv);
         __syncthreads();
+        const double* smr = sm + g * COLS + cc;
 #pragma unroll
-        for (int i = 0; i < 16; ++i) x[i] = sm[(g + G * i) * COLS + cc];
-        gs_radix16<(16 >> (LEV1 > 0 ? LEV1 : 1)), true>(x, LEV1, [&](int S, int, int i) { return mk_tw(ld_d(tw + tw_index(S, (u32)((g + G * i) << 8) + c, log_n)), qinv); }, q, fin0, fin1);
+        for (int i = 0; i < 16; ++i) x[i] = smr[i * (G * COLS)];
+        gs_radix16<(16 >> (LEV1 > 0 ? LEV1 : 1)), true>(x, LEV1, [&](int S, int, int i) { return mk_tw(tw_col_r1<LOG_R>(tw, S, i), qinv); }, q, fin0, fin1);
+        const int e0 = (g << 8) + c;
 #pragma unroll
-        for (int i = 0; i < 16; ++i) st(map, rref, (u32)((g + G * i) << 8) + c, x[i], mid, M);
+        for (int i = 0; i < 16; ++i) st(map, rref, e0 + i * (G << 8), x[i], mid, M);
     } else {
-        gs_radix16<1, true>(x, LOG_R, [&](int S, int, int i) { return mk_tw(ld_d(tw + tw_index(S, (u32)((16 * g + i) << 8) + c, log_n)), qinv); }, q, fin0, fin1);
+        gs_radix16<1, true>(x, LOG_R, [&](int S, int, int i) { return mk_tw(tw_col_r2<LOG_R>(tw, g, S, i), qinv); }, q, fin0, fin1);
 #pragma unroll
-        for (int i = 0; i < 16; ++i) st(map, rref, (u32)((16 * g + i) << 8) + c, x[i], mid, M);
+        for (int i = 0; i < 16; ++i) st(map, rref, e1 + (i << 8), x[i], mid, M);
     }
 }
 
@@ -360,34 +444,42 @@ template <class LoadOp, class StoreOp>
 inline void ntt_forward(const DevTables& T, const RowMap& map_in, int rows, LoadOp ld, u64* work,
                         long long work_stride, StoreOp st, cudaStream_t s) {
     const int log_r = T.log_n - 8;
-    dim3 grid(1u << (log_r - 4), rows), block(256);
+    RowMap map = map_in; map.n_blocks = rows / map.rows_per_poly;
+    dim3 grid(1u << (log_r - 4), map.n_blocks, map.rows_per_poly), block(256);
     StoreRaw sp; sp.dst = work; sp.poly_stride = work_stride;
     LoadRaw lp; lp.src = work; lp.poly_stride = work_stride;
-    RowMap map = map_in; map.n_blocks = rows / map.rows_per_poly;
     switch (log_r) {
-        case 4: fhe_launch(ntt_fwd_pass_a<4, LoadOp>, grid, block, 0, s, T, map, ld, sp); break;
-        case 5: fhe_launch(ntt_fwd_pass_a<5, LoadOp>, grid, block, 0, s, T, map, ld, sp); break;
-        case 6: fhe_launch(ntt_fwd_pass_a<6, LoadOp>, grid, block, 0, s, T, map, ld, sp); break;
-        case 7: fhe_launch(ntt_fwd_pass_a<7, LoadOp>, grid, block, 0, s, T, map, ld, sp); break;
-        default: fhe_launch(ntt_fwd_pass_a<8, LoadOp>, grid, block, 0, s, T, map, ld, sp); break;
+        case 4: fhe_launch(ntt_fwd_pass_a<4, LoadOp>, grid, block, 0, s, T, map, ld, sp);
+                fhe_launch(ntt_fwd_pass_b<12, StoreOp>, grid, block, 0, s, T, map, lp, st); break;
+        case 5: fhe_launch(ntt_fwd_pass_a<5, LoadOp>, grid, block, 0, s, T, map, ld, sp);
+                fhe_launch(ntt_fwd_pass_b<13, StoreOp>, grid, block, 0, s, T, map, lp, st); break;
+        case 6: fhe_launch(ntt_fwd_pass_a<6, LoadOp>, grid, block, 0, s, T, map, ld, sp);
+                fhe_launch(ntt_fwd_pass_b<14, StoreOp>, grid, block, 0, s, T, map, lp, st); break;
+        case 7: fhe_launch(ntt_fwd_pass_a<7, LoadOp>, grid, block, 0, s, T, map, ld, sp);
+                fhe_launch(ntt_fwd_pass_b<15, StoreOp>, grid, block, 0, s, T, map, lp, st); break;
+        default: fhe_launch(ntt_fwd_pass_a<8, LoadOp>, grid, block, 0, s, T, map, ld, sp);
+                 fhe_launch(ntt_fwd_pass_b<16, StoreOp>, grid, block, 0, s, T, map, lp, st); break;
     }
-    fhe_launch(ntt_fwd_pass_b<StoreOp>, grid, block, 0, s, T, map, lp, st);
 }
 
 template <class LoadOp, class StoreOp>
 inline void ntt_inverse(const DevTables& T, const RowMap& map_in, int rows, LoadOp ld, u64* work,
                         long long work_stride, StoreOp st, const ConstF* scale, cudaStream_t s) {
     const int log_r = T.log_n - 8;
-    dim3 grid(1u << (log_r - 4), rows), block(256);
+    RowMap map = map_in; map.n_blocks = rows / map.rows_per_poly;
+    dim3 grid(1u << (log_r - 4), map.n_blocks, map.rows_per_poly), block(256);
     StoreRaw sp; sp.dst = work; sp.poly_stride = work_stride;
     LoadRaw lp; lp.src = work; lp.poly_stride = work_stride;
-    RowMap map = map_in; map.n_blocks = rows / map.rows_per_poly;
-    fhe_launch(ntt_inv_pass_b<LoadOp>, grid, block, 0, s, T, map, ld, sp);
     switch (log_r) {
-        case 4: fhe_launch(ntt_inv_pass_a<4, StoreOp>, grid, block, 0, s, T, map, lp, st, scale); break;
-        case 5: fhe_launch(ntt_inv_pass_a<5, StoreOp>, grid, block, 0, s, T, map, lp, st, scale); break;
-        case 6: fhe_launch(ntt_inv_pass_a<6, StoreOp>, grid, block, 0, s, T, map, lp, st, scale); break;
-        case 7: fhe_launch(ntt_inv_pass_a<7, StoreOp>, grid, block, 0, s, T, map, lp, st, scale); break;
-        default: fhe_launch(ntt_inv_pass_a<8, StoreOp>, grid, block, 0, s, T, map, lp, st, scale); break;
+        case 4: fhe_launch(ntt_inv_pass_b<12, LoadOp>, grid, block, 0, s, T, map, ld, sp);
+                fhe_launch(ntt_inv_pass_a<4, StoreOp>, grid, block, 0, s, T, map, lp, st, scale); break;
+        case 5: fhe_launch(ntt_inv_pass_b<13, LoadOp>, grid, block, 0, s, T, map, ld, sp);
+                fhe_launch(ntt_inv_pass_a<5, StoreOp>, grid, block, 0, s, T, map, lp, st, scale); break;
+        case 6: fhe_launch(ntt_inv_pass_b<14, LoadOp>, grid, block, 0, s, T, map, ld, sp);
+                fhe_launch(ntt_inv_pass_a<6, StoreOp>, grid, block, 0, s, T, map, lp, st, scale); break;
+        case 7: fhe_launch(ntt_inv_pass_b<15, LoadOp>, grid, block, 0, s, T, map, ld, sp);
+                fhe_launch(ntt_inv_pass_a<7, StoreOp>, grid, block, 0, s, T, map, lp, st, scale); break;
+        default: fhe_launch(ntt_inv_pass_b<16, LoadOp>, grid, block, 0, s, T, map, ld, sp);
+                 fhe_launch(ntt_inv_pass_a<8, StoreOp>, grid, block, 0, s, T, map, lp, st, scale); break;
     }
 }

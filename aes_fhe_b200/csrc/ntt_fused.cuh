@@ -152,24 +152,6 @@ FHE_D double lds_tw_lo(const double* s_tw, int s, int e) {
     return s_tw[FHE_FUSED_ROWS * ((1 << (s - 1)) - 1) + (e >> (9 - s))];
 }
 
-// 16 contiguous doubles <-> registers with 16-byte shared-memory accesses
-FHE_D void lds16(double (&x)[16], const double* p) {
-#ifndef FHE_EMU
-#pragma unroll
-    for (int i = 0; i < 8; ++i) { const double2 v = reinterpret_cast<const double2*>(p)[i]; x[2 * i] = v.x; x[2 * i + 1] = v.y; }
-#else
-    for (int i = 0; i < 16; ++i) x[i] = p[i];
-#endif
-}
-FHE_D void sts16(double* p, const double (&x)[16]) {
-#ifndef FHE_EMU
-#pragma unroll
-    for (int i = 0; i < 8; ++i) reinterpret_cast<double2*>(p)[i] = make_double2(x[2 * i], x[2 * i + 1]);
-#else
-    for (int i = 0; i < 16; ++i) p[i] = x[i];
-#endif
-}
-
 // Schedule of one CTA over the rows r_0, r_1, ... of its group (software-pipelined by one
 // phase so that a hand-over is almost never waited on):
 //      A(r_0);  for k = 0, 1, ...:  A(r_{k+1});  wait "all A(r_k) stored";  B(r_k)
