@@ -12,7 +12,7 @@ PKG = Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
 ROOT = PKG.parent
 SOURCES = ["capi.cu"]
-HEADERS = ["compat.h", "modarith.cuh", "ntt.cuh", "ntt_fused.cuh", "kernels.cuh"]
+HEADERS = ["compat.h", "modarith.cuh", "ntt.cuh", "ntt_chained.cuh", "ntt_fused.cuh", "kernels.cuh"]
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-DFHE_PASSA_MINB=4", "-DFHE_PASSB_MINB=4",

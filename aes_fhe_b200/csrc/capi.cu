@@ -426,6 +426,12 @@ int fhe_ctx_create(fhe_ctx** out, int log_n, int n_q, int n_p, int alpha, const 
 #ifdef FHE_FUSED_PROFILE
             cudaMalloc((void**)&fz.prof, 64 + 32 * 2048); cudaMemset(fz.prof, 0, 64 + 32 * 2048); c->owned.push_back(fz.prof);
 #endif
+            if (cudaMalloc((void**)&fz.chain.ctr, sizeof(unsigned) * (FHE_CHAIN_MAX_CHUNKS + 2)) == cudaSuccess) {
+                cudaMemset(fz.chain.ctr, 0, sizeof(unsigned) * (FHE_CHAIN_MAX_CHUNKS + 2));
+                c->owned.push_back(fz.chain.ctr);
+                if (const char* cr = std::getenv("FHE_CHAIN_ROWS")) fz.chain.chunk_rows = std::max(1, std::atoi(cr));
+                fz.chain.enabled = (env && env[0] == '2') ? 1 : 0;
+            }
 #ifdef FHE_EMU
             fz.enabled = !(env && env[0] == '0');      // the host simulator always exercises the fused kernels
 #else
@@ -447,6 +453,8 @@ int fhe_ctx_create(fhe_ctx** out, int log_n, int n_q, int n_p, int alpha, const 
 int fhe_set_ntt_fused(fhe_ctx* c, int enabled) {
     if (!c) return fail("fhe_set_ntt_fused: null context");
     if (enabled && !c->fz.scratch) return fail("fhe_set_ntt_fused: context was created without fused-NTT resources");
+    c->fz.chain.enabled = (enabled == 2 && c->fz.chain.ctr) ? 1 : 0;
+    if (enabled == 2) { c->fz.enabled = 0; return c->fz.chain.enabled ? 0 : fail("fhe_set_ntt_fused: chained NTT unavailable"); }
     c->fz.enabled = enabled ? 1 : 0;
 #ifndef FHE_EMU
     if (enabled && c->fz_calibrate && c->fz.gtime) { c->fz_calibrate = false; fused_calibrate(c); c->fz.enabled = 1; }
@@ -470,6 +478,11 @@ int fhe_ntt_fused_status(fhe_ctx* c) {
     if (cudaMemcpy(&flag, c->fz.ctr + 32 * c->fz.max_groups, sizeof(unsigned), cudaMemcpyDeviceToHost) != cudaSuccess)
         return check("fhe_ntt_fused_status");
     if (flag) return fail("fused NTT: a group barrier timed out (CTAs of a group were not co-resident)");
+    if (c->fz.chain.ctr) {
+        if (cudaMemcpy(&flag, c->fz.chain.ctr + 1 + FHE_CHAIN_MAX_CHUNKS, sizeof(unsigned), cudaMemcpyDeviceToHost) != cudaSuccess)
+            return check("fhe_ntt_fused_status");
+        if (flag) return fail("chained NTT: a second-pass CTA timed out waiting for its chunk");
+    }
     return 0;
 }
 

@@ -279,18 +279,15 @@ FHE_D Tw15 ld_tw15c(const double* tw, int blk16) {
 }
 
 // ------------------------------------------------------------------ forward
-template <int LOG_R, class LoadOp>
-__global__ void __launch_bounds__(256, FHE_PASSA_MINB) ntt_fwd_pass_a(DevTables T, RowMap map, LoadOp ld, StoreRaw st) {
+template <int LOG_R, class LoadOp, class StoreOp>
+FHE_D void fwd_pass_a_body(const DevTables& T, const RowMap& map, RowRef rref, int mid, int tile, const LoadOp& ld,
+                           const StoreOp& st, double* sm) {
     constexpr int R = 1 << LOG_R, G = R / 16, COLS = 256 / G, LEV1 = LOG_R - 4, LOG_N = LOG_R + 8;
-    FHE_SHARED double sm[4096];
-    RowRef rref; rref.blk = blockIdx.y; rref.j = blockIdx.z;
-    const int mid = map.mod_id_of(rref.j, ntt_dig(map, rref.blk));
-    if (mid < 0) return;
     const Modulus M = T.mod[mid];
     const double q = M.qd, qinv = M.qinv;
     const double* tw = T.tw_fwd + ((size_t)mid << LOG_N);
     const int tid = threadIdx.x, cc = tid % COLS, g = tid / COLS;
-    const int c = blockIdx.x * COLS + cc;
+    const int c = tile * COLS + cc;
     double x[16];
     if (LEV1 > 0) {
         const int e0 = (g << 8) + c;
@@ -314,19 +311,24 @@ __global__ void __launch_bounds__(256, FHE_PASSA_MINB) ntt_fwd_pass_a(DevTables 
 #pragma unroll
     for (int i = 0; i < 16; ++i) st(map, rref, o0 + (i << 8), x[i], mid, M);
 }
-
-template <int LOG_N, class StoreOp>
-__global__ void __launch_bounds__(256, FHE_PASSB_MINB) ntt_fwd_pass_b(DevTables T, RowMap map, LoadRaw ld, StoreOp st) {
-    constexpr int LOG_R = LOG_N - 8, RS = FHE_ROW_STRIDE;
-    FHE_SHARED __align__(16) double sm[16 * RS];
+template <int LOG_R, class LoadOp>
+__global__ void __launch_bounds__(256, FHE_PASSA_MINB) ntt_fwd_pass_a(DevTables T, RowMap map, LoadOp ld, StoreRaw st) {
+    FHE_SHARED double sm[4096];
     RowRef rref; rref.blk = blockIdx.y; rref.j = blockIdx.z;
     const int mid = map.mod_id_of(rref.j, ntt_dig(map, rref.blk));
     if (mid < 0) return;
+    fwd_pass_a_body<LOG_R>(T, map, rref, mid, blockIdx.x, ld, st, sm);
+}
+
+template <int LOG_N, class LoadOp, class StoreOp>
+FHE_D void fwd_pass_b_body(const DevTables& T, const RowMap& map, RowRef rref, int mid, int tile, const LoadOp& ld,
+                           const StoreOp& st, double* sm) {
+    constexpr int LOG_R = LOG_N - 8, RS = FHE_ROW_STRIDE;
     const Modulus M = T.mod[mid];
     const double q = M.qd, qinv = M.qinv;
     const double* tw = T.tw_fwd + ((size_t)mid << LOG_N);
     const int tid = threadIdx.x, l16 = tid & 15, rr = tid >> 4;
-    const int grow = blockIdx.x * 16 + rr;                    // 256-element row of the limb
+    const int grow = tile * 16 + rr;                          // 256-element row of the limb
     const int rbase = (grow << 8) + l16;
     double* smS = sm + rr * RS + l16;                         // strided view    [18 * i]
     double* smC = sm + rr * RS + 18 * l16;                    // contiguous view [i]
@@ -353,21 +355,26 @@ __global__ void __launch_bounds__(256, FHE_PASSB_MINB) ntt_fwd_pass_b(DevTables 
 #pragma unroll
     for (int i = 0; i < 16; ++i) st(map, rref, rbase + 16 * i, smS[18 * i], mid, M);
 }
-
-// ------------------------------------------------------------------ inverse
-// pass B' : stages LOG_N .. LOG_N-7 (strides 1..128) on 16 contiguous rows of 256.
-template <int LOG_N, class LoadOp>
-__global__ void __launch_bounds__(256, FHE_PASSB_MINB) ntt_inv_pass_b(DevTables T, RowMap map, LoadOp ld, StoreRaw st) {
-    constexpr int LOG_R = LOG_N - 8, RS = FHE_ROW_STRIDE;
-    FHE_SHARED __align__(16) double sm[16 * RS];
+template <int LOG_N, class StoreOp>
+__global__ void __launch_bounds__(256, FHE_PASSB_MINB) ntt_fwd_pass_b(DevTables T, RowMap map, LoadRaw ld, StoreOp st) {
+    FHE_SHARED __align__(16) double sm[16 * FHE_ROW_STRIDE];
     RowRef rref; rref.blk = blockIdx.y; rref.j = blockIdx.z;
     const int mid = map.mod_id_of(rref.j, ntt_dig(map, rref.blk));
     if (mid < 0) return;
+    fwd_pass_b_body<LOG_N>(T, map, rref, mid, blockIdx.x, ld, st, sm);
+}
+
+// ------------------------------------------------------------------ inverse
+// pass B' : stages LOG_N .. LOG_N-7 (strides 1..128) on 16 contiguous rows of 256.
+template <int LOG_N, class LoadOp, class StoreOp>
+FHE_D void inv_pass_b_body(const DevTables& T, const RowMap& map, RowRef rref, int mid, int tile, const LoadOp& ld,
+                           const StoreOp& st, double* sm) {
+    constexpr int LOG_R = LOG_N - 8, RS = FHE_ROW_STRIDE;
     const Modulus M = T.mod[mid];
     const double q = M.qd, qinv = M.qinv;
     const double* tw = T.tw_inv + ((size_t)mid << LOG_N);
     const int tid = threadIdx.x, l16 = tid & 15, rr = tid >> 4;
-    const int grow = blockIdx.x * 16 + rr;
+    const int grow = tile * 16 + rr;
     const int rbase = (grow << 8) + l16;
     double* smS = sm + rr * RS + l16;
     double* smC = sm + rr * RS + 18 * l16;
@@ -395,24 +402,28 @@ __global__ void __launch_bounds__(256, FHE_PASSB_MINB) ntt_inv_pass_b(DevTables 
 #pragma unroll
     for (int i = 0; i < 16; ++i) st(map, rref, rbase + 16 * i, reduce_sym(x[i], q, qinv), mid, M);
 }
-
-// pass A' : stages LOG_R .. 1 (row strides 1..R/2); the final stage carries the scaling
-// constants scale[limb slot] = {c * N^-1, c * psi^-bitrev(1) * N^-1} (c = 1 when scale == nullptr).
-template <int LOG_R, class StoreOp>
-__global__ void __launch_bounds__(256, FHE_PASSA_MINB) ntt_inv_pass_a(DevTables T, RowMap map, LoadRaw ld, StoreOp st,
-                                                      const ConstF* scale) {
-    constexpr int R = 1 << LOG_R, G = R / 16, COLS = 256 / G, LEV1 = LOG_R - 4, LOG_N = LOG_R + 8;
-    FHE_SHARED double sm[4096];
+template <int LOG_N, class LoadOp>
+__global__ void __launch_bounds__(256, FHE_PASSB_MINB) ntt_inv_pass_b(DevTables T, RowMap map, LoadOp ld, StoreRaw st) {
+    FHE_SHARED __align__(16) double sm[16 * FHE_ROW_STRIDE];
     RowRef rref; rref.blk = blockIdx.y; rref.j = blockIdx.z;
     const int mid = map.mod_id_of(rref.j, ntt_dig(map, rref.blk));
     if (mid < 0) return;
+    inv_pass_b_body<LOG_N>(T, map, rref, mid, blockIdx.x, ld, st, sm);
+}
+
+// pass A' : stages LOG_R .. 1 (row strides 1..R/2); the final stage carries the scaling
+// constants scale[limb slot] = {c * N^-1, c * psi^-bitrev(1) * N^-1} (c = 1 when scale == nullptr).
+template <int LOG_R, class LoadOp, class StoreOp>
+FHE_D void inv_pass_a_body(const DevTables& T, const RowMap& map, RowRef rref, int mid, int tile, const LoadOp& ld,
+                           const StoreOp& st, const ConstF* scale, double* sm) {
+    constexpr int R = 1 << LOG_R, G = R / 16, COLS = 256 / G, LEV1 = LOG_R - 4, LOG_N = LOG_R + 8;
     const Modulus M = T.mod[mid];
     const double q = M.qd, qinv = M.qinv;
     const double* tw = T.tw_inv + ((size_t)mid << LOG_N);
     const ConstF* fin = scale ? scale + 2 * (size_t)rref.j : T.inv_final + 2 * (size_t)mid;
     const ConstF fin0 = fin[0], fin1 = fin[1];
     const int tid = threadIdx.x, cc = tid % COLS, g = tid / COLS;
-    const int c = blockIdx.x * COLS + cc;
+    const int c = tile * COLS + cc;
     double x[16];
     const int e1 = (g << 12) + c;
 #pragma unroll
@@ -435,6 +446,15 @@ __global__ void __launch_bounds__(256, FHE_PASSA_MINB) ntt_inv_pass_a(DevTables 
 #pragma unroll
         for (int i = 0; i < 16; ++i) st(map, rref, e1 + (i << 8), x[i], mid, M);
     }
+}
+template <int LOG_R, class StoreOp>
+__global__ void __launch_bounds__(256, FHE_PASSA_MINB) ntt_inv_pass_a(DevTables T, RowMap map, LoadRaw ld, StoreOp st,
+                                                      const ConstF* scale) {
+    FHE_SHARED double sm[4096];
+    RowRef rref; rref.blk = blockIdx.y; rref.j = blockIdx.z;
+    const int mid = map.mod_id_of(rref.j, ntt_dig(map, rref.blk));
+    if (mid < 0) return;
+    inv_pass_a_body<LOG_R>(T, map, rref, mid, blockIdx.x, ld, st, scale, sm);
 }
 
 // ------------------------------------------------------------------ host launchers

@@ -25,6 +25,7 @@
 // canonical output is bit-identical to the two-pass kernels and to the oracle.
 #pragma once
 #include "ntt.cuh"
+#include "ntt_chained.cuh"
 
 #ifndef FHE_FUSED_TPB
 #define FHE_FUSED_TPB 128
@@ -520,6 +521,7 @@ struct FusedHost {
     int cal_groups = 0;
     unsigned long long* gtime = nullptr;      // [FHE_FUSED_MAX_WGROUPS] device, filled while calibrating
     int calibrating = 0;
+    ChainHost chain;                          // the chained single-launch variant (ntt_chained.cuh)
 };
 
 #ifndef FHE_EMU
@@ -613,6 +615,7 @@ inline bool ntt_inverse_fused(const DevTables& T, const FusedHost& fz, const Row
 template <class LoadOp, class StoreOp>
 inline int ntt_forward_auto(const DevTables& T, const FusedHost& fz, const RowMap& map_in, int rows, LoadOp ld,
                             u64* work, long long work_stride, StoreOp st, cudaStream_t s) {
+    if (fz.chain.enabled && ntt_forward_chained(T, fz.chain, map_in, rows, ld, work, work_stride, st, s)) return 1;
     if (fz.enabled) {
         RowMap map = map_in; map.n_blocks = rows / map.rows_per_poly;
         bool ok = false;
@@ -631,6 +634,7 @@ inline int ntt_forward_auto(const DevTables& T, const FusedHost& fz, const RowMa
 template <class LoadOp, class StoreOp>
 inline int ntt_inverse_auto(const DevTables& T, const FusedHost& fz, const RowMap& map_in, int rows, LoadOp ld,
                             u64* work, long long work_stride, StoreOp st, const ConstF* scale, cudaStream_t s) {
+    if (fz.chain.enabled && ntt_inverse_chained(T, fz.chain, map_in, rows, ld, work, work_stride, st, scale, s)) return 1;
     if (fz.enabled) {
         RowMap map = map_in; map.n_blocks = rows / map.rows_per_poly;
         bool ok = false;

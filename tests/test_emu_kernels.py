@@ -10,13 +10,14 @@ from conftest import make_engines
 
 
 def _emu(P, emu_lib, fused=1):
-    """fused=1: the single-launch NTT (csrc/ntt_fused.cuh, the simulator's default); 0: the two-pass kernels."""
+    """NTT variant: 1 = persistent single-launch (csrc/ntt_fused.cuh, the simulator default), 0 = two-pass
+    (csrc/ntt.cuh), 2 = chained single-launch (csrc/ntt_chained.cuh)."""
     b = CudaBackend(P, _lib_path=emu_lib, _device="cpu")
     assert b.lib.fhe_set_ntt_fused(b.ctx, fused) == 0
     return b
 
 
-@pytest.mark.parametrize("fused", [1, 0])
+@pytest.mark.parametrize("fused", [1, 0, 2])
 @pytest.mark.parametrize("log_n,lvl", [(12, 5), (13, 4), (14, 2)])
 def test_primitives(log_n, lvl, fused, emu_lib, ref_backend_cls):
     P = make_params(log_n, lvl)
@@ -30,13 +31,13 @@ def test_primitives_full_ring(emu_lib, ref_backend_cls):
     kp.check_primitives(P, _emu(P, emu_lib), ref_backend_cls(P))
 
 
-@pytest.mark.parametrize("fused", [1, 0])
+@pytest.mark.parametrize("fused", [1, 0, 2])
 def test_rescale(fused, emu_lib, ref_backend_cls):
     P = make_params(12, 6)
     kp.check_rescale(P, _emu(P, emu_lib, fused), ref_backend_cls(P))
 
 
-@pytest.mark.parametrize("fused", [1, 0])
+@pytest.mark.parametrize("fused", [1, 0, 2])
 @pytest.mark.parametrize("log_n,lvl,dnum", [(12, 6, 4), (12, 7, 3), (13, 4, 2)])
 def test_keyswitch_phases(log_n, lvl, dnum, fused, emu_lib, ref_backend_cls):
     P = make_params(log_n, lvl, dnum=dnum)

@@ -123,14 +123,14 @@ def test_fused_ntt_equals_two_pass_at_scale(ref_backend_cls, cuda_lib):
     ksk = gb.from_numpy(np.stack([rand_poly(P, rng, 2, nq, True) for _ in range(P.dnum)]))
     r = gb.from_numpy(rand_poly(P, rng, 3, 17, False, batch=3))
     outs = []
-    for fused in (1, 0):
+    for fused in (1, 2, 0):        # persistent single-launch, chained single-launch, two-pass
         assert gb.lib.fhe_set_ntt_fused(gb.ctx, fused) == 0
         f = gb.ntt(a, nq, K)
         outs.append([f, gb.intt(a, nq, K), gb.intt(f, nq, K), gb.keyswitch(d, ksk, 25), gb.rescale(r, 17),
                      gb.mod_raise(r[:, :, :1].contiguous(), 9)])
     assert gb.lib.fhe_ntt_fused_status(gb.ctx) == 0
-    for x, y in zip(*outs):
-        assert torch.equal(x, y)
+    for x, y, z in zip(*outs):
+        assert torch.equal(x, z) and torch.equal(y, z)
     assert torch.equal(outs[0][2], a)
     # one row against the oracle
     one = rand_poly(P, rng, 1, nq, True)

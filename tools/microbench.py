@@ -70,10 +70,11 @@ def main():
     m, mn = timeit(lambda: b.copy_(a), flush=flush)
     rec("torch_copy_ref", m, mn, 2 * a.numel() * 8)
 
-    for fused in ((0, 1) if has_fused else (0,)):
+    modes = [int(m) for m in os.environ.get("FHE_NTT_MODES", "0,2,1").split(",")] if has_fused else [0]
+    for fused in modes:
         if has_fused:
             gb.lib.fhe_set_ntt_fused(gb.ctx, fused)
-        tag = "fused" if fused else "two_pass"
+        tag = {0: "two_pass", 1: "fused", 2: "chained"}[fused]
         for rows in (tot, 2 * tot, 8 * tot, 32 * tot):
             x = rnd(rows // tot, tot, n)
             m, mn = timeit(lambda: gb._call("fhe_ntt_fwd", gb._ptr(x), x.shape[0], 31, K), flush=flush)
@@ -82,7 +83,7 @@ def main():
             rec("ntt_inv." + tag, m, mn, 2 * rows * limb, rows=rows)
     if has_fused:
         assert gb.lib.fhe_ntt_fused_status(gb.ctx) == 0, "fused NTT barrier timed out"
-        gb.lib.fhe_set_ntt_fused(gb.ctx, 1 if os.environ.get("FHE_NTT_FUSED") == "1" else 0)
+        gb.lib.fhe_set_ntt_fused(gb.ctx, int(os.environ.get("FHE_NTT_FUSED", "0")))
 
     for nq in (() if only_ntt else (31, 21, 11)):
         x = rnd(2, nq, n); y = rnd(2, nq, n); o = torch.empty_like(x)
