@@ -344,7 +344,8 @@ def main():
                 "roofline": {"bound": "hbm", "kernel": "ntt_fwd (pass A + pass B)", "rows_per_launch": rows,
                              "achieved": achieved, "peak": peak, "peak_kind": peak_kind, "unit": "GB/s",
                              "frac": achieved / peak, "traffic": traffic,
-                             "note": "compute-bound on the FP64 pipe, see profiles/"},
+                             "note": "FP64-pipe bound: 8 FP64 ops per butterfly, pipe at 70-82 % (profiles/r01_ncu_twopass_v2.md); "
+                                     "traffic = ncu dram bytes of both passes"},
                 "ms_per_ciphertext": ms / args.batch,
                 "keyswitches_per_ciphertext": 32}
         if not args.no_full_round and world == 1:
