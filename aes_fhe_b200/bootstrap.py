@@ -169,13 +169,14 @@ class _Plan:
     pass
 
 
-def make_bootstrap_key(engine, sk, groups: int = 3) -> BootstrapKey:
+def make_bootstrap_key(engine, sk, groups: int = 3, groups_stc: Optional[int] = None) -> BootstrapKey:
     """Lazy: the (large) set of Galois keys and encoded matrices is built on first use.  The
     key object keeps a reference to the secret key for that purpose, like the reference's
     EngineContext keeps every key in one process (engine_context.py:62-73)."""
     bk = BootstrapKey(small=False)
     bk._sk = sk
-    bk._groups = groups
+    bk._groups = groups                                            # CoeffToSlot matrices
+    bk._groups_stc = groups if groups_stc is None else groups_stc   # SlotToCoeff matrices (fewer = one level back)
     return bk
 
 
@@ -186,14 +187,15 @@ def _materialise(engine, bk: BootstrapKey):
     n = engine.slot_count
     L = P.max_level
     groups = bk._groups
-    depth = 1 + groups + 6 + DOUBLE_ANGLES + groups        # extra rescale of the first matrix + the rest
+    groups_stc = getattr(bk, "_groups_stc", groups)
+    depth = 1 + groups + 6 + DOUBLE_ANGLES + groups_stc    # extra rescale of the first matrix + the rest
     if L < depth + 1:
         raise RuntimeError(f"bootstrapping needs max_level >= {depth + 1}, engine has {L}")
     layers, inv_layers = _fft_layers(n)
     # CoeffToSlot: L_1^-1 ... L_last^-1 with L_last^-1 applied first; fold 1 / (2 K_n)
     cts = _group(list(reversed(inv_layers)), groups, n)
     cts[0] = {d: v / (2.0 * K_NORM) for d, v in cts[0].items()}
-    stc = _group(layers, groups, n)
+    stc = _group(layers, groups_stc, n)
     plan = _Plan()
     plan.depth = depth
     plan.rot_keys: Dict[int, FixedRotationKey] = {}

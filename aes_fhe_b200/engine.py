@@ -661,9 +661,12 @@ class Engine:
         return Ciphertext(self, self.backend.mul_const(ct.polys, cp, cm, nq), ct.level, ct.zero)
 
     # ------------------------------------------------------------------ bootstrap
-    def create_bootstrap_key(self, sk: SecretKey):
+    def create_bootstrap_key(self, sk: SecretKey, groups: int = 3, groups_stc: Optional[int] = None):
+        """engine_context.py:73.  `groups` / `groups_stc`: number of BSGS linear transforms of
+        CoeffToSlot / SlotToCoeff (depth = 13 + groups + groups_stc; fewer = more levels left, more
+        rotations)."""
         from .bootstrap import make_bootstrap_key
-        return make_bootstrap_key(self, sk)
+        return make_bootstrap_key(self, sk, groups, groups_stc)
 
     def create_small_bootstrap_key(self, sk: SecretKey):
         return BootstrapKey(small=True)
