@@ -175,6 +175,42 @@ def full_round_probe(batch: int):
             "levels_used": 30 - r1[0].level, "bytes_equal_plain_aes": bool(ok), "fips197_appendix_b_round2_input": bool(fips)}
 
 
+def aes128_probe(batch: int):
+    """configs[4]: full AES-128 (ten rounds, clear key schedule, refresh = bootstrap + clean-up after
+    every LUT layer; aes_fhe_b200/services/aes128.py) on `batch` ciphertexts of 2048 blocks, N = 2^16,
+    L = 30.  Timed on the second run (keys, matrices and LUT tables exist); every decoded block is
+    checked against plain AES, block 0 is FIPS-197 Appendix B."""
+    import torch
+    from aes_fhe_b200.services.aes128 import AES128Service
+    from aes_fhe_b200.services.xor_service import XORService, EngineWrapper, XORConfig, CoefficientCache
+    from oracle import aes_plain as A
+    cfg = XORConfig()
+    w = EngineWrapper(cfg, _engine_kwargs=dict(seed=3), rotation_steps=[])
+    svc = AES128Service(w, XORService(w, CoefficientCache(cfg.coeffs_path)))
+    key = bytes.fromhex("2b7e151628aed2a6abf7158809cf4f3c")
+    rng = np.random.default_rng(9)
+    blocks = [rng.integers(0, 256, (svc.B, 16), dtype=np.uint8) for _ in range(batch)]
+    blocks[0][0] = np.frombuffer(bytes.fromhex("3243f6a8885a308d313198a2e0370734"), np.uint8)
+    st = svc.encrypt_state(blocks)
+    svc.encrypt_blocks(st, key)                               # warm-up: builds every key / matrix / table
+    torch.cuda.synchronize()
+    c0, r0 = dict(w.engine.op_counts), svc.refreshes
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record(); out = svc.encrypt_blocks(st, key); b.record()
+    torch.cuda.synchronize()
+    ms = a.elapsed_time(b)
+    got = svc.decrypt_state(out).reshape(batch, svc.B, 16)
+    want = np.stack([A.encrypt_blocks(bl, key) for bl in blocks])
+    ks = sum(v - c0.get(k, 0) for k, v in w.engine.op_counts.items() if k.startswith("keyswitch"))
+    nblk = batch * svc.B
+    return {"workload": "configs[4]: AES-128, 10 rounds, N=2^16, L=30, refresh after every LUT layer", "batch": batch,
+            "ms": ms, "ms_per_round": ms / 10, "blocks_per_s": nblk / (ms * 1e-3),
+            "bootstrap_calls": int(w.engine.op_counts["bootstrap"] - c0.get("bootstrap", 0)),
+            "ciphertexts_refreshed_per_batch_element": int((svc.refreshes - r0) // batch),
+            "keyswitches": int(ks), "bytes_equal_plain_aes": bool(np.array_equal(got, want)),
+            "fips197_appendix_b_ciphertext": bool(got[0, 0].tobytes().hex() == "3925841d02dc09fbdc118597196a0b32")}
+
+
 # --------------------------------------------------------------------------- main
 def main():
     ap = argparse.ArgumentParser()
@@ -186,6 +222,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-full-round", action="store_true",
                     help="skip the extra measurement of one full AES round (configs[3])")
+    ap.add_argument("--no-aes128", action="store_true",
+                    help="skip the extra measurement of full AES-128 (configs[4], ten rounds with bootstrapping)")
     ap.add_argument("--reference-order", action="store_true",
                     help="also time the reference's own 255-key-switch operation order")
     args = ap.parse_args()
@@ -353,6 +391,11 @@ def main():
                 line["full_round"] = full_round_probe(min(args.batch, 4))
             except Exception as e:  # pragma: no cover
                 line["full_round"] = {"unavailable": repr(e)}
+        if not args.no_aes128 and world == 1:
+            try:
+                line["aes128"] = aes128_probe(min(args.batch, 2))
+            except Exception as e:  # pragma: no cover
+                line["aes128"] = {"unavailable": repr(e)}
         if args.reference_order:
             torch.cuda.synchronize()
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

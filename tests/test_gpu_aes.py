@@ -90,3 +90,34 @@ def test_mixrow_named_function_runs_with_bootstrapping(cuda_lib):
     # (the sequence itself collapses to 0 in every slot -- SURVEY defect D8 -- so decoded
     # integers carry no information here)
     assert err < 1e-3
+
+
+def test_aes128_ten_rounds_full_size(cuda_lib):
+    """BASELINE config 5 on the B200: AES-128, ten rounds, N = 2^16 (2048 blocks per ciphertext),
+    refresh (bootstrap + clean-up) after every LUT layer.  Decoded ciphertext bytes of all 2048
+    blocks must equal plain AES; block 0 is FIPS-197 Appendix B, block 1 uses the Appendix C.1
+    plaintext under the Appendix B key."""
+    import time
+    from aes_fhe_b200.services.aes128 import AES128Service
+    from aes_fhe_b200.services.xor_service import XORService, EngineWrapper, XORConfig, CoefficientCache
+    from oracle import aes_plain as A
+    cfg = XORConfig()
+    w = EngineWrapper(cfg, _engine_kwargs=dict(seed=4), rotation_steps=[])
+    assert w.engine.params.log_n == 16 and w.engine.max_level == 30
+    svc = AES128Service(w, XORService(w, CoefficientCache(cfg.coeffs_path)))
+    key = bytes.fromhex("2b7e151628aed2a6abf7158809cf4f3c")
+    rng = np.random.default_rng(11)
+    blocks = rng.integers(0, 256, (svc.B, 16), dtype=np.uint8)
+    blocks[0] = np.frombuffer(bytes.fromhex("3243f6a8885a308d313198a2e0370734"), np.uint8)
+    blocks[1] = np.frombuffer(bytes.fromhex("00112233445566778899aabbccddeeff"), np.uint8)
+    t0 = time.time()
+    out = svc.encrypt_blocks(svc.encrypt_state(blocks), key)
+    torch.cuda.synchronize()
+    dt = time.time() - t0
+    got = svc.decrypt_state(out)
+    want = A.encrypt_blocks(blocks, key)
+    bad = int((got != want).any(axis=1).sum())
+    print(f"AES-128 x {svc.B} blocks: {dt:.1f}s first run (keys, matrices, tables included), "
+          f"{w.engine.op_counts['bootstrap']} bootstrap calls, {svc.refreshes} ciphertexts refreshed, wrong blocks {bad}")
+    assert got[0].tobytes().hex() == "3925841d02dc09fbdc118597196a0b32"
+    assert bad == 0
