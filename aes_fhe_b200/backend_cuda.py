@@ -259,6 +259,12 @@ class CudaBackend:
         self._call("fhe_moddown", self._ptr(out), self._ptr(acc), nq, acc.shape[0] * acc.shape[1])
         return out
 
+    def moddown_inplace(self, acc, nq):
+        """as moddown, but the caller's acc (a temporary) is used as scratch"""
+        out = self._empty(acc.shape[0], acc.shape[1], nq, self.n)
+        self._call("fhe_moddown", self._ptr(out), self._ptr(acc), nq, acc.shape[0] * acc.shape[1])
+        return out
+
     def relin_rescale(self, d3, ksk, nq):
         """[3,B,nq,N] tensor product -> [2,B,nq-1,N]: relinearise + rescale with one ModDown."""
         d3 = d3.contiguous()
@@ -310,6 +316,37 @@ class CudaBackend:
         self._call("fhe_lincomb", self._ptr(out), ptrs, nqs, self._ptr(prep["consts"]),
                    self._ptr(prep["c0"]) if prep["c0"] is not None else None, M, T, nq, bt)
         return [out[m] for m in range(M)]
+
+    def mul_plain_sum(self, a_list: List, p_list: List, nq: int):
+        """sum_t a_t (.) p_t in one pass per 16 terms; a_t [2,B,>=nq,N], p_t [1,1,nq,N] -> [2,B,nq,N]."""
+        a_list = [x.contiguous() for x in a_list]
+        p_list = [x.contiguous() for x in p_list]
+        bt = a_list[0].shape[1]
+        out = self._empty(2, bt, nq, self.n)
+        done, T = 0, len(a_list)
+        while done < T:
+            g = min(16, T - done)
+            ap = (C.c_void_p * g)(*[x.data_ptr() for x in a_list[done:done + g]])
+            an = (C.c_int * g)(*[x.shape[2] for x in a_list[done:done + g]])
+            pp = (C.c_void_p * g)(*[x.data_ptr() for x in p_list[done:done + g]])
+            self._call("fhe_mul_plain_sum", self._ptr(out), ap, an, pp, g, nq, bt, 1 if done else 0)
+            done += g
+        return out
+
+    def automorphism_rows(self, h, g: int):
+        """X -> X^g on every row of an arbitrary [.., N] tensor (hoisted rotations act on ModUp output)."""
+        h = h.contiguous()
+        out = torch.empty_like(h)
+        self._call("fhe_automorphism", self._ptr(out), self._ptr(h), C.c_uint64(int(g)), h.numel() // self.n)
+        return out
+
+    def modup_raw(self, d, nq):
+        """fhe_modup without mirroring the digits' own rows (they are read from d by ks_inner)."""
+        d = d.contiguous()
+        bt = d.shape[1]
+        ext = self._empty(bt, self.params.digits_at(nq), nq + self._K, self.n)
+        self._call("fhe_modup", self._ptr(ext), self._ptr(d), nq, bt)
+        return ext
 
     def tensor_acc(self, acc, a_list: List, b_list: List, nq: int):
         """acc [3,B,nq,N] (or None) += sum_g a_g (x) b_g ; a_g may carry more limbs than nq and

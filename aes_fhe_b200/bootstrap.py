@@ -235,6 +235,9 @@ def _linear_transform(engine, ct: Ciphertext, entry) -> Ciphertext:
     """sum_d diag_d (.) roll(x, -d) with baby-step / giant-step rotations; one level."""
     plan_keys = entry["_keys"]
     babies: Dict[int, Ciphertext] = {0: ct}
+    need = sorted({b for items in entry["giants"].values() for b, _ in items if b})
+    for b, r in zip(need, engine.rotate_hoisted(ct, [plan_keys[b] for b in need])):      # one ModUp for all baby steps
+        babies[b] = r
     out = None
     for g, items in entry["giants"].items():
         cts, pts = [], []

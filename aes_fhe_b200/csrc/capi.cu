@@ -598,6 +598,27 @@ int fhe_lincomb(fhe_ctx* c, void* stream, uint64_t* out, const uint64_t* const* 
     return check("fhe_lincomb");
 }
 
+int fhe_mul_plain_sum(fhe_ctx* c, void* stream, uint64_t* out, const uint64_t* const* a, const int* a_nq,
+                      const uint64_t* const* p, int T, int nq, int batch, int accumulate) {
+    if (bad_shape(c, nq, 0) || batch < 1 || T < 1 || T > FHE_LC_MAX_T || !a || !a_nq || !p)
+        return fail("fhe_mul_plain_sum: bad shape");
+    PlainSumIn in;
+    for (int t = 0; t < FHE_LC_MAX_T; ++t) {
+        const int nt = t < T ? a_nq[t] : nq;
+        if (t < T && nt < nq) return fail("fhe_mul_plain_sum: operand has fewer limbs than the output");
+        in.a[t] = t < T ? (const u64*)a[t] : nullptr;
+        in.p[t] = t < T ? (const u64*)p[t] : nullptr;
+        in.a_batch_stride[t] = (long long)nt * c->n;
+        in.a_poly_stride[t] = (long long)batch * nt * c->n;
+    }
+    dim3 grid(c->n / 256, nq), block(256);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (T <= 4) launch(k_mul_plain_sum<4>, grid, block, s, c->T, nq, batch, T, in, (u64*)out, accumulate);
+    else if (T <= 8) launch(k_mul_plain_sum<8>, grid, block, s, c->T, nq, batch, T, in, (u64*)out, accumulate);
+    else launch(k_mul_plain_sum<16>, grid, block, s, c->T, nq, batch, T, in, (u64*)out, accumulate);
+    return check("fhe_mul_plain_sum");
+}
+
 int fhe_tensor_acc(fhe_ctx* c, void* stream, uint64_t* acc, const uint64_t* const* a, const int* a_nq,
                    const int* a_batch, const uint64_t* b, int b_batch, int G, int nq, int batch, int accumulate) {
     if (bad_shape(c, nq, 0) || batch < 1 || G < 1 || G > FHE_LC_MAX_T || !a || !a_nq || !a_batch || !b ||

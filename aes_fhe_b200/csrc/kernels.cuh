@@ -13,6 +13,14 @@
 #define FHE_MAX_DST 48      // max target limbs of one base conversion
 #define FHE_MAX_LIMBS 48
 
+FHE_D u64 ld_u64(const u64* p) {
+#ifndef FHE_EMU
+    return __ldg(p);
+#else
+    return *p;
+#endif
+}
+
 struct LimbConsts {          // per-limb-slot constants passed by value
     u64 a[FHE_MAX_LIMBS];
     u64 b[FHE_MAX_LIMBS];
@@ -212,6 +220,43 @@ __global__ void __launch_bounds__(256) k_tensor_acc(DevTables Tb, int nq, int ba
     acc[bo + 2 * ps] = f_to_u64(reduce_canon(d2, q, qi));
 }
 
+// out (+)= sum_t a_t (.) p_t : the rotate-mask-add / diagonal-matrix pattern (shiftrows_service.py:41-50
+// and the BSGS linear transforms of bootstrapping) in ONE pass.  p_t are plaintexts [nq][N] shared by
+// both polynomials and the whole batch: a thread owns (limb, index), keeps its T plaintext words in
+// registers and walks (poly, batch) with all T ciphertext loads of an iteration in flight.
+//   a_t : [2][batch][nq_t >= nq][N],  out : [2][batch][nq][N]      grid: (N/256, nq)
+struct PlainSumIn {
+    const u64* a[FHE_LC_MAX_T];
+    long long a_poly_stride[FHE_LC_MAX_T];
+    long long a_batch_stride[FHE_LC_MAX_T];
+    const u64* p[FHE_LC_MAX_T];
+};
+template <int T_MAX>
+__global__ void __launch_bounds__(256, 2) k_mul_plain_sum(DevTables Tb, int nq, int batch, int T, PlainSumIn in, u64* out,
+                                                           int accumulate) {
+    const int j = blockIdx.y;
+    const Modulus Mo = Tb.mod[j];
+    const double q = Mo.qd, qi = Mo.qinv;
+    const size_t lo = ((size_t)j << Tb.log_n) + blockIdx.x * 256 + threadIdx.x;
+    double p[T_MAX];
+#pragma unroll
+    for (int t = 0; t < T_MAX; ++t) p[t] = t < T ? u64_to_f(ld_u64(in.p[t] + lo)) : 0.0;
+    const size_t ops = (size_t)batch * nq << Tb.log_n, obs = (size_t)nq << Tb.log_n;
+    for (int poly = 0; poly < 2; ++poly)
+        for (int b = 0; b < batch; ++b) {
+            u64 a[T_MAX];
+#pragma unroll
+            for (int t = 0; t < T_MAX; ++t)
+                if (t < T) a[t] = ld_u64(in.a[t] + (size_t)poly * in.a_poly_stride[t] + (size_t)b * in.a_batch_stride[t] + lo);
+            u64* o = out + (size_t)poly * ops + (size_t)b * obs + lo;
+            double acc = accumulate ? u64_to_f(*o) : 0.0;
+#pragma unroll
+            for (int t = 0; t < T_MAX; ++t)
+                if (t < T) acc = d_add(acc, mulmod_var(u64_to_f(a[t]), p[t], q, qi));
+            *o = f_to_u64(reduce_canon(acc, q, qi));
+        }
+}
+
 // ---------------------------------------------------------------- base conversion
 // One table per source basis.  Output value for target t:
 //     sum_k yc_k * f[k][t]   (mod m_t),     yc_k = centred representative of y_k mod q_k
@@ -276,13 +321,6 @@ __global__ void __launch_bounds__(256) k_bconv(DevTables T, const BConvTable* ta
 // key word is read from HBM once per batch.      ksk: [dnum][2][n_q_total + n_p][N]
 // ext: [batch][beta][ne][N], d: [batch][nq][N], acc: [2][batch][ne][N]
 #define FHE_MAX_BETA 8
-FHE_D u64 ld_u64(const u64* p) {
-#ifndef FHE_EMU
-    return __ldg(p);
-#else
-    return *p;
-#endif
-}
 struct U2 { u64 x, y; };
 FHE_D U2 ld2(const u64* p) {
 #ifndef FHE_EMU

@@ -32,6 +32,10 @@ from .params import CKKSParams, make_params, sqrt_minus_one
 _SIGMA = 3.2
 
 
+import os as _os
+_NO_FUSE = _os.environ.get("FHE_NO_HOIST") == "1"      # A/B switch: separate rotations, mul + add per mask
+
+
 class Plaintext:
     """Level-agnostic plaintext: slot values plus a per-level cache of encodings.
 
@@ -539,13 +543,38 @@ class Engine:
         if lvl == 0:
             raise RuntimeError("multiply: no multiplicative depth left")
         be = self.backend
+        self._count('mul_pt', len(cts))
+        if hasattr(be, "mul_plain_sum") and not _NO_FUSE and all(c.batch == cts[0].batch and c.npoly == 2 for c in cts):
+            # one fused pass (fhe_mul_plain_sum): every operand read once, the sum written once
+            acc = be.mul_plain_sum([self.level_down(c, lvl).polys for c in cts], [p.at_level(lvl) for p in pts], lvl + 1)
+            return self._rescale(Ciphertext(self, acc, lvl))
         acc = None
         for ct, pt in zip(cts, pts):
             ct = self.level_down(ct, lvl)
             prod = be.mul(ct.polys, pt.at_level(lvl), lvl + 1, 0)
             acc = prod if acc is None else be.add(acc, prod, lvl + 1, 0)
-            self._count('mul_pt')
         return self._rescale(Ciphertext(self, acc, lvl))
+
+    def rotate_hoisted(self, ct: Ciphertext, keys: Sequence[FixedRotationKey]) -> List[Ciphertext]:
+        """Several rotations of ONE ciphertext sharing a single ModUp (the base extension commutes
+        with the Galois automorphism bit for bit: centred digits are odd functions and the
+        automorphism only permutes and negates coefficients), so every rotation after the first
+        costs an automorphism, the key inner product and the ModDown only."""
+        be = self.backend
+        if ct.zero or not keys:
+            return [ct for _ in keys]
+        if not hasattr(be, "modup_raw") or len(keys) < 2 or _NO_FUSE:
+            return [self._apply_galois(ct, k) for k in keys]
+        nq = ct.level + 1
+        ext = be.modup_raw(be.select_poly(ct.polys, 1), nq)
+        outs = []
+        for key in keys:
+            rot = be.automorphism(ct.polys, key.galois, nq, 0)
+            acc = be.ks_inner(be.automorphism_rows(ext, key.galois), be.select_poly(rot, 1), key.data, nq)
+            ks = be.moddown_inplace(acc, nq) if hasattr(be, "moddown_inplace") else be.moddown(acc, nq)
+            self._count('keyswitch_galois')
+            outs.append(Ciphertext(self, be.add_poly0(ks, be.select_poly(rot, 0), nq), ct.level))
+        return outs
 
     def _mul_scalar(self, ct: Ciphertext, value) -> Ciphertext:
         """ct x complex constant, rescaled (the reference uses ``multiply(ct, 0.0)`` as

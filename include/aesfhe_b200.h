@@ -90,6 +90,13 @@ int fhe_add_const(fhe_ctx* ctx, void* stream, uint64_t* out, const uint64_t* a,
 int fhe_lincomb(fhe_ctx* ctx, void* stream, uint64_t* out, const uint64_t* const* in, const int* in_nq,
                 const double* consts, const uint64_t* c0, int M, int T, int nq, int batch);
 
+/* Rotate-mask-add and diagonal-matrix sums (shiftrows_service.py:41-50; the linear transforms of
+ * Engine.bootstrap): out[2][batch][nq][N] (+)= sum_t a_t (.) p_t for T <= 16 terms in one pass.
+ * a[t]: ciphertexts [2][batch][a_nq[t] >= nq][N] (host array of device pointers), p[t]: plaintexts
+ * [nq][N] (NTT domain) shared by both polynomials and the batch.  No rescale is performed. */
+int fhe_mul_plain_sum(fhe_ctx* ctx, void* stream, uint64_t* out, const uint64_t* const* a, const int* a_nq,
+                      const uint64_t* const* p, int T, int nq, int batch, int accumulate);
+
 /* Lazy-relinearised products: acc[3][batch][nq][N] (+)= sum_g a_g (x) b_g for G <= 16 products;
  * a[g] are ciphertexts [2][a_batch[g]][a_nq[g]][N] (host array of device pointers), b is G
  * contiguous ciphertexts [2][b_batch][nq][N]; a_batch[g] and b_batch are `batch` or 1 (a

@@ -124,6 +124,18 @@ def check_engine_ops(eg, er, slot_tol=1e-5):
     same(eg.add(bg, pt_g), er.add(br, pt_r), "batch add plaintext")
     same(eg.rotate(bg, kg['rot'], -2), er.rotate(br, kr['rot'], -2), "batch rotate")
     same(eg.conjugate(bg, kg['cj']), er.conjugate(br, kr['cj']), "batch conjugate")
+    # hoisted rotations (one ModUp shared) are bit-identical to separate rotations and to the oracle
+    fk_g = [eg.create_fixed_rotation_key(kg['sk'], d) for d in (1, -3, 7)]
+    fk_r = [er.create_fixed_rotation_key(kr['sk'], d) for d in (1, -3, 7)]
+    for hg, k_g, k_r in zip(eg.rotate_hoisted(bg, fk_g), fk_g, fk_r):
+        assert np.array_equal(eg.backend.to_numpy(hg.polys), eg.backend.to_numpy(eg.rotate(bg, k_g).polys)), "hoisted == separate rotation"
+        same(hg, er.rotate(br, k_r), "hoisted rotation vs oracle")
+    # rotate-mask-add in one fused pass (fhe_mul_plain_sum) against the oracle's mul + add sequence
+    pts_g = [eg.encode(rng.random(sc) - 0.5) for _ in range(3)]
+    cts_g = [bg, eg.rotate(bg, kg['rot'], 1), sq_g]
+    cts_r = [br, er.rotate(br, kr['rot'], 1), sq_r]
+    pts_r = [er.encode(p.values) for p in pts_g]
+    same(eg.multiply_plain_sum(cts_g, pts_g), er.multiply_plain_sum(cts_r, pts_r), "multiply_plain_sum")
     pg, pr = eg.make_power_basis(cg, 5, kg['rlk']), er.make_power_basis(cr, 5, kr['rlk'])
     for k, (x, y) in enumerate(zip(pg, pr), 1):
         same(x, y, f"power {k}")
