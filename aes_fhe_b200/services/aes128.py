@@ -98,8 +98,7 @@ class AES128Service(AESRoundService):
             for nib in ("hi", "lo"):
                 t0 = self._gather(planes["2S_" + nib], 0)
                 t1 = self._gather(planes["3S_" + nib], 1)
-                t2 = self._gather(planes["S_" + nib], 2)
-                t3 = self._gather(planes["S_" + nib], 3)
+                t2, t3 = self._gather_many(planes["S_" + nib], [2, 3])
                 layer1 += [self._xor(t0, t1), self._xor(t2, t3)]
             a_hi, b_hi, a_lo, b_lo = self.ensure(layer1, L + 1)
             s_hi, s_lo = self.ensure([self._xor(a_hi, b_hi), self._xor(a_lo, b_lo)], L + (0 if final else 1))

@@ -16,7 +16,7 @@ in new.py:199-216.
 """
 from __future__ import annotations
 
-from typing import Dict, List, Optional, Tuple
+from typing import Dict, List, Optional, Sequence, Tuple
 
 import numpy as np
 
@@ -132,18 +132,38 @@ class AESRoundService:
             self._masks[rows] = pt
         return pt
 
-    def _gather(self, plane, k: int):
-        """T_k[r, c] = plane[(r+k)%4, (c + (r+k)%4) % 4] as rotate-mask-add.
-        source byte position of target i = 4c + r is i + (5 r' - r), r' = (r+k) % 4."""
+    def _rot_key(self, offset: int):
+        key = self._rot_keys.get(offset)
+        if key is None:
+            key = self.engine.create_fixed_rotation_key(self.eng.secret_key, -offset * self.B)
+            self._rot_keys[offset] = key
+        return key
+
+    @staticmethod
+    def _gather_plan(k: int) -> Dict[int, List[int]]:
+        """T_k[r, c] = plane[(r+k)%4, (c + (r+k)%4) % 4]: source byte position of target i = 4c + r is
+        i + (5 r' - r), r' = (r+k) % 4.  Returns {rotation offset: rows it serves}."""
         by_off: Dict[int, List[int]] = {}
         for r in range(4):
             rp = (r + k) % 4
             by_off.setdefault((5 * rp - r) % 16, []).append(r)
-        cts, pts = [], []
-        for off, rows in sorted(by_off.items()):
-            cts.append(self._rot(plane, off))
-            pts.append(self._mask(tuple(rows)))
-        return self.engine.multiply_plain_sum(cts, pts)
+        return by_off
+
+    def _gather_many(self, plane, ks: Sequence[int]):
+        """rotate-mask-add gathers T_k of one plane for several k: all rotations of the plane share
+        one ModUp (Engine.rotate_hoisted), each gather is one fused multiply-accumulate."""
+        plans = {k: self._gather_plan(k) for k in ks}
+        offs = sorted({o for p in plans.values() for o in p if o})
+        rots = dict(zip(offs, self.engine.rotate_hoisted(plane, [self._rot_key(o) for o in offs])))
+        rots[0] = plane
+        out = []
+        for k in ks:
+            items = sorted(plans[k].items())
+            out.append(self.engine.multiply_plain_sum([rots[o] for o, _ in items], [self._mask(tuple(r)) for _, r in items]))
+        return out
+
+    def _gather(self, plane, k: int):
+        return self._gather_many(plane, [k])[0]
 
     def shift_rows(self, state):
         """ShiftRows alone (k = 0 gather), the corrected form of shiftrows_service.shift_rows."""
@@ -154,8 +174,7 @@ class AESRoundService:
         for nib in ("hi", "lo"):
             t0 = self._gather(planes["2S_" + nib], 0)
             t1 = self._gather(planes["3S_" + nib], 1)
-            t2 = self._gather(planes["S_" + nib], 2)
-            t3 = self._gather(planes["S_" + nib], 3)
+            t2, t3 = self._gather_many(planes["S_" + nib], [2, 3])
             out.append(self._xor(self._xor(t0, t1), self._xor(t2, t3)))
         return out[0], out[1]
 

@@ -393,7 +393,7 @@ def main():
                 line["full_round"] = {"unavailable": repr(e)}
         if not args.no_aes128 and world == 1:
             try:
-                line["aes128"] = aes128_probe(min(args.batch, 2))
+                line["aes128"] = aes128_probe(min(args.batch, 4))
             except Exception as e:  # pragma: no cover
                 line["aes128"] = {"unavailable": repr(e)}
         if args.reference_order:

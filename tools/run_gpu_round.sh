@@ -1,8 +1,3 @@
 set -x
 mkdir -p gpurun_out
-timeout 1500 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
-timeout 1500 python bench.py --steps 3 --warmup 3 > gpurun_out/bench_r1.json 2> gpurun_out/bench_r1.err; tail -3 gpurun_out/bench_r1.err; python - <<'PY'
-import json
-d=json.load(open('gpurun_out/bench_r1.json'))
-for k in ('value','ms_per_step','gpu_launches','e2e','roofline','full_round','aes128','cpu_baseline','clocks'): print(k, d.get(k))
-PY
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 2500 --csv --log-file gpurun_out/launches_r1c.csv python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-full-round --no-aes128 > gpurun_out/ncu_list.log 2>&1; tail -1 gpurun_out/ncu_list.log | cut -c1-200
