@@ -12,14 +12,14 @@ Pipeline (Cheon-Han-Kim-Kim-Song 2018, Han-Ki 2020 double-angle variant):
   3. real / imaginary parts via one conjugation (multiplication by -i is the monomial
      X^(N/2): free), stacked on the batch axis so EvalMod runs once
   4. EvalMod: alpha_0 cos(2 pi (K_n y - 1/4) / 2^r) by a degree-22 Chebyshev interpolant
-     (T_1..T_22 by the product rule, one constant-only linear combination), then r double-angle steps c <- c^2 - alpha_{i+1}; the constants alpha_i fold
+     (Paterson-Stockmeyer in the Chebyshev basis: 10 products, depth 5), then r double-angle steps c <- c^2 - alpha_{i+1}; the constants alpha_i fold
      the factor rho / 2 pi so the result is the message coefficient itself
   5. SlotToCoeff: the forward special FFT, `groups` BSGS linear transforms.
 
 Only the first CoeffToSlot matrix sees a non-standard scale (the raised ciphertext has scale
 q_0); its plaintext diagonals are encoded at Delta_{L-1} q_L / q_0 so that everything
-afterwards sits on the engine's per-level scales.  Depth: 1 + groups + 6 + r + groups
-(= 19 for groups = 3, r = 6).
+afterwards sits on the engine's per-level scales.  Depth: 1 + groups + 5 + r + groups
+(= 18 for groups = 3, r = 6).
 """
 from __future__ import annotations
 
@@ -145,6 +145,59 @@ def chebyshev_basis(engine, relin_key, y: Ciphertext, degree: int) -> Dict[int, 
     return T
 
 
+def chebyshev_eval_ps(engine, relin_key, y: Ciphertext, coeffs, baby: int = 4) -> Ciphertext:
+    """sum_k coeffs[k] T_k(y) with the Paterson-Stockmeyer recursion in the Chebyshev basis:
+    p = q * T_n + r with T_k = 2 T_n T_(k-n) - T_(2n-k) for n < k < 2n, n = baby * 2^j.  The leaves
+    (degree < baby) are constant-only linear combinations of T_1..T_(baby-1).  Degree 22 costs
+    10 ciphertext products (T_2, T_3, T_4, T_8, T_16 and five recombinations) instead of the 21 of
+    the full basis, at the same depth (6)."""
+    c = [float(v) for v in coeffs]
+    while len(c) > 1 and abs(c[-1]) < 1e-300:
+        c.pop()
+    deg = len(c) - 1
+    T: Dict[int, Ciphertext] = {1: y}
+
+    def double_minus(prod, sub):          # 2 * prod - sub  (sub: ciphertext or the constant 1)
+        twice = engine.add(prod, prod)
+        return engine.add_plain(twice, -1.0) if sub is None else engine.subtract(twice, sub)
+
+    for k in range(2, baby + 1):
+        a, b = (k + 1) // 2, k // 2
+        T[k] = double_minus(engine.multiply(T[a], T[b], relin_key), None if a == b else T[a - b])
+    n = baby
+    while 2 * n <= deg:
+        T[2 * n] = double_minus(engine.multiply(T[n], T[n], relin_key), None)
+        n *= 2
+
+    def leaf(cc):
+        terms = {k: cc[k] for k in range(1, len(cc)) if abs(cc[k]) > 0.0}
+        if not terms:
+            return float(cc[0])
+        return lincomb_const(engine, {k: T[k] for k in terms}, terms, const=cc[0])
+
+    def ev(cc):
+        d = len(cc) - 1
+        if d < baby:
+            return leaf(cc)
+        n = baby
+        while 2 * n <= d:
+            n *= 2
+        q = [0.0] * (d - n + 1)
+        r = list(cc[:n])
+        q[0] = cc[n]
+        for k in range(n + 1, d + 1):
+            q[k - n] += 2.0 * cc[k]
+            r[2 * n - k] -= cc[k]
+        qv, rv = ev(q), ev(r)
+        prod = engine.multiply(T[n], qv) if isinstance(qv, float) else engine.multiply(qv, T[n], relin_key)
+        return engine.add_plain(prod, rv) if isinstance(rv, float) else engine.add(prod, rv)
+
+    out = ev(c)
+    if isinstance(out, float):
+        raise ValueError("chebyshev_eval_ps: constant polynomial")
+    return out
+
+
 def lincomb_const(engine, cts: Dict[int, Ciphertext], coeffs, const: float = 0.0) -> Ciphertext:
     """const + sum_k coeffs[k] * cts[k]: constants absorb the level / scale alignment, one pass of
     fhe_lincomb per 16 inputs, ONE rescale."""
@@ -188,7 +241,7 @@ def _materialise(engine, bk: BootstrapKey):
     L = P.max_level
     groups = bk._groups
     groups_stc = getattr(bk, "_groups_stc", groups)
-    depth = 1 + groups + 6 + DOUBLE_ANGLES + groups_stc    # extra rescale of the first matrix + the rest
+    depth = 1 + groups + 5 + DOUBLE_ANGLES + groups_stc    # extra rescale of the first matrix, EvalMod polynomial (5), the rest
     if L < depth + 1:
         raise RuntimeError(f"bootstrapping needs max_level >= {depth + 1}, engine has {L}")
     layers, inv_layers = _fft_layers(n)
@@ -289,8 +342,7 @@ def bootstrap(engine, ct: Ciphertext, relin_key, conj_key, boot_key: BootstrapKe
     y = Ciphertext(engine, be.concat_batch([re.polys, im.polys]), t.level)
 
     # 4. EvalMod
-    T = chebyshev_basis(engine, relin_key, y, POLY_DEGREE)
-    cpoly = lincomb_const(engine, T, {k: plan.poly[k] for k in T}, const=plan.poly[0])
+    cpoly = chebyshev_eval_ps(engine, relin_key, y, plan.poly)
     for i in range(DOUBLE_ANGLES):
         cpoly = engine.add_plain(engine.multiply(cpoly, cpoly, relin_key), -plan.alphas[i + 1])
     re_p, im_p = be.split_batch(cpoly.polys, [bt, bt])

@@ -13,8 +13,8 @@ layers without correction would leave the decode margin of zeta_16 (0.196).  So 
 
 The clean-up polynomial is the unique degree-17 polynomial with f(z) = z and f'(z) = 0 on the
 sixteen 16th roots of unity: an input z (1 + e) comes out as z (1 - 8.5 e^2).  It costs five
-levels (x^2, x^4, x^8, x^16, then x^16 * (-x / 16) + 17 x / 16).  With CoeffToSlot in 3 and
-SlotToCoeff in 2 transforms a bootstrap uses 18 of the 30 levels: 12 left, 7 after the clean-up,
+levels (x^2, x^4, x^8, x^16, then x^16 * (-x / 16) + 17 x / 16).  A bootstrap (CoeffToSlot and
+SlotToCoeff in 3 transforms each) uses 18 of the 30 levels: 12 left, 7 after the clean-up,
 enough for one layer (gather + LUT = 6) with one level to spare for the next bootstrap.  A
 simulation of the error dynamics (Gaussian refresh noise of 7e-4 rms, 131 072 slots, ten rounds)
 stays at 3e-3 before and 6e-5 after each clean-up; without the clean-up the first round fails.
@@ -39,7 +39,7 @@ class AES128Service(AESRoundService):
     LUT_LEVELS = 5              # power bases (3) + product + two rescales folded into one more
     CLEAN_LEVELS = 5
 
-    def __init__(self, eng_wrap, xor_svc, boot_groups=(3, 2)):
+    def __init__(self, eng_wrap, xor_svc, boot_groups=(3, 3)):
         super().__init__(eng_wrap, xor_svc)
         self.boot_key = self.engine.create_bootstrap_key(eng_wrap.secret_key, boot_groups[0], boot_groups[1])
         self.refreshes = 0          # ciphertexts refreshed (bootstrap + clean-up)

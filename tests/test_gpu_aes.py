@@ -60,7 +60,7 @@ def test_bootstrap_full_size(cuda_lib):
     d = eng.decrypt(out, sk)
     err = np.abs(d - v).max()
     print(f"bootstrap N=2^16 batch 2: first {t_first:.1f}s (keys + matrices), warm {t_warm*1e3:.0f} ms, level {out.level}, max err {err:.2e}")
-    assert out.level == 11 and out.batch == 2
+    assert out.level == 12 and out.batch == 2
     assert err < 5e-3
     from aes_fhe_b200.services.xor_service import ZetaEncoder
     assert np.array_equal(ZetaEncoder.from_zeta(d), ZetaEncoder.from_zeta(v))

@@ -1,3 +1,4 @@
 set -x
 mkdir -p gpurun_out
-timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 2500 --csv --log-file gpurun_out/launches_r1c.csv python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-full-round --no-aes128 > gpurun_out/ncu_list.log 2>&1; tail -1 gpurun_out/ncu_list.log | cut -c1-200
+timeout 1500 python -m pytest tests/test_gpu_aes.py -m gpu -x -q -s 2>&1 | grep -v Warning | tail -8
+timeout 600 python tools/boot_phases.py 12 2>&1 | grep -v Warning | tail -10
