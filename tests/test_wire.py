@@ -1,0 +1,48 @@
+"""Wire format: round trips on the CPU oracle, rejection of foreign / damaged data."""
+import numpy as np
+import pytest
+
+from aes_fhe_b200 import wire
+from aes_fhe_b200.engine import Engine
+from aes_fhe_b200.params import make_params
+
+
+def _engine(ref_backend_cls, lvl=5, seed=4):
+    P = make_params(12, lvl)
+    return Engine(_params=P, _backend=ref_backend_cls(P), seed=seed)
+
+
+def test_round_trip_of_ciphertexts_and_evaluation_keys(ref_backend_cls):
+    owner = _engine(ref_backend_cls)
+    sk = owner.create_secret_key(); pk = owner.create_public_key(sk)
+    rlk = owner.create_relinearization_key(sk); cj = owner.create_conjugation_key(sk)
+    rk = owner.create_fixed_rotation_key(sk, 3)
+    server = _engine(ref_backend_cls, seed=99)                       # another process: same parameters, no secret key
+    pk2, rlk2, cj2, rk2 = (wire.loads(server, wire.dumps(owner, k)) for k in (pk, rlk, cj, rk))
+    assert rk2.delta == 3 and rk2.galois == rk.galois
+    rng = np.random.default_rng(0)
+    v = np.exp(-2j * np.pi * rng.integers(0, 16, (2, owner.slot_count)) / 16)
+    ct = wire.loads(server, wire.dumps(owner, owner.encrypt(v, pk)))
+    assert ct.level == 5 and ct.batch == 2
+    out = server.rotate(server.conjugate(server.multiply(ct, ct, rlk2), cj2), rk2)
+    back = wire.loads(owner, wire.dumps(server, out))
+    assert np.abs(owner.decrypt(back, sk) - np.roll(np.conj(v * v), 3, axis=-1)).max() < 1e-5
+    # a client encrypts with the shipped public key
+    assert np.abs(owner.decrypt(server.encrypt(v[0], pk2), sk) - v[0]).max() < 1e-5
+
+
+def test_rejects_foreign_parameters_damage_and_secret_keys(ref_backend_cls):
+    a, b = _engine(ref_backend_cls, 5), _engine(ref_backend_cls, 4)
+    sk = a.create_secret_key(); pk = a.create_public_key(sk)
+    blob = wire.dumps(a, a.encrypt(np.ones(8), pk))
+    with pytest.raises(wire.WireError, match="different parameter set"):
+        wire.loads(b, blob)
+    with pytest.raises(wire.WireError, match="bad magic"):
+        wire.loads(a, b"XXXXXXXX" + blob[8:])
+    with pytest.raises(wire.WireError, match="payload size"):
+        wire.loads(a, blob[:-8])
+    bad = bytearray(blob); bad[-1] = 0xFF                              # top byte of the last residue: >= modulus
+    with pytest.raises(wire.WireError, match="out of range"):
+        wire.loads(a, bytes(bad))
+    with pytest.raises(wire.WireError, match="not serialisable"):
+        wire.dumps(a, sk)
