@@ -41,6 +41,17 @@ def build_cuda(force: bool = False, verbose: bool = False) -> Path:
     return out
 
 
+def build_profile_variant() -> Path:
+    """csrc/variants/libprof.so: the product sources with -DFHE_FUSED_PROFILE (cycle counters inside the
+    persistent fused NTT), used by tools/fused_prof.py only."""
+    out = CSRC / "variants" / "libprof.so"
+    out.parent.mkdir(exist_ok=True)
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    subprocess.check_call([nvcc] + NVCC_FLAGS + ["-DFHE_FUSED_PROFILE", "-ccbin", "g++", "-o", str(out)] +
+                          [str(CSRC / s) for s in SOURCES], cwd=str(CSRC))
+    return out
+
+
 def build_emu(force: bool = False) -> Path:
     emu_dir = ROOT / "tests" / "emu"
     out = emu_dir / "libaesfhe_emu.so"

@@ -1,4 +1,5 @@
-"""Where a CTA of the fused NTT spends its cycles (FHE_FUSED_PROFILE build, csrc/variants/libprof.so)."""
+"""Where a CTA of the fused NTT spends its cycles (FHE_FUSED_PROFILE build, csrc/variants/libprof.so:
+`python -c "from aes_fhe_b200.build import build_profile_variant as b; b()"` before `gpurun`)."""
 import ctypes as C
 import sys
 from pathlib import Path
