@@ -52,7 +52,18 @@ FHE_D double u64_to_f(u64 x) { return d_add(bits_to_f(0x4330000000000000ull | x)
 FHE_D u64 f_to_u64(double r) { return f_to_bits(d_add(r, FHE_TWO52)) & 0x000FFFFFFFFFFFFFull; }
 
 // rint(x * c) for |x * c| < 2^51
+#ifdef FHE_RINT_QUOT
+// variant: DMUL + FRND.F64 -- the round-to-integer issues on the conversion pipe (16 lanes/clk/SM,
+// tools/ubench/frnd.cu) instead of a second FP64-pipe operation.  The quotient may differ by one from
+// the single-rounding form in rare near-tie cases, which only changes the lazy representative.
+#ifndef FHE_EMU
+FHE_D double round_quot(double x, double c) { return rint(d_mul(x, c)); }
+#else
+inline double round_quot(double x, double c) { return std::rint(d_mul(x, c)); }
+#endif
+#else
 FHE_D double round_quot(double x, double c) { return d_add(d_fma(x, c, FHE_MAGIC), -FHE_MAGIC); }
+#endif
 
 // x * w mod q, signed result with |r| <= q (1/2 + |x| 2^-53); needs |x| < 2^50
 FHE_D double mulmod_const(double x, const ConstF w, double q) {

@@ -407,6 +407,39 @@ class Engine:
         self._count('decrypt', ct.batch)
         return be.decode_device(acc, use, self.params.scale(ct.level))
 
+    # ---- byte-level codec on the device (the reference's ZetaEncoder.to_zeta / from_zeta around
+    #      encrypt / decrypt: xor_service.py:132-145, 318-328), so a step moves bytes, not complex128
+    def encrypt_zeta(self, values, public_key: PublicKey, modulus: int = 16, level: Optional[int] = None) -> Ciphertext:
+        """uint8 values [<= slot_count] or [B, <= slot_count] -> ciphertext(s) of zeta_m^x = exp(-2 pi i x / m);
+        one H2D copy of the bytes, everything else on the device.  Same result as
+        ``encrypt(ZetaEncoder.to_zeta(values, modulus), pk)`` up to the encryption randomness."""
+        import torch
+        be = self.backend
+        if not hasattr(be, "encode_device"):
+            ang = -2.0 * np.pi * (np.asarray(values).astype(np.int64) % modulus) / modulus
+            return self.encrypt(np.exp(1j * ang), public_key, level)
+        x = values if isinstance(values, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(np.asarray(values, dtype=np.uint8)))
+        x = x.reshape(1, -1) if x.ndim <= 1 else x
+        x = x.to(be.device, non_blocking=True)
+        n_in = x.shape[1]
+        ang = (x.to(torch.float64) % modulus) * (-2.0 * np.pi / modulus)
+        z = torch.complex(torch.cos(ang), torch.sin(ang))
+        if n_in < self.slot_count:
+            z = torch.nn.functional.pad(z, (0, self.slot_count - n_in))            # zero-padded, like encrypt()
+        return self._encrypt_device(z, public_key, self.params.max_level if level is None else int(level))
+
+    def decrypt_zeta(self, ct: Ciphertext, sk: SecretKey, modulus: int = 16) -> np.ndarray:
+        """decrypt + ZetaEncoder.from_zeta on the device: uint8 [slot_count] or [B, slot_count]."""
+        import torch
+        if not hasattr(self.backend, "decode_device"):
+            z = np.atleast_2d(self.decrypt(ct, sk))
+            out = (np.rint(-np.angle(z) * modulus / (2 * np.pi)).astype(np.int64) % modulus).astype(np.uint8)
+        else:
+            z = self.decrypt_device(ct, sk)
+            k = torch.round(torch.angle(z) * (-modulus / (2.0 * np.pi))).to(torch.int64) % modulus
+            out = k.to(torch.uint8).cpu().numpy()
+        return out[0] if out.shape[0] == 1 else out
+
     def decrypt_to_plaintext_coeffs(self, ct: Ciphertext, sk: SecretKey) -> np.ndarray:
         """Centred coefficient vectors (float64 [batch, N]) of c0 + c1 s (+ c2 s^2)."""
         be = self.backend

@@ -105,6 +105,11 @@ def test_device_codec_roundtrip_and_compat(cuda_lib):
     sq = eng.multiply(ct, ct, rlk)
     eng.device_codec = True
     assert np.abs(eng.decrypt(sq, sk) - v * v).max() < 1e-5
+    # byte-level codec on the device: zeta_256 encode + encrypt, decrypt + decode, ragged input zero-padded
+    x = rng.integers(0, 256, (3, eng.slot_count), dtype=np.uint8)
+    assert np.array_equal(eng.decrypt_zeta(eng.encrypt_zeta(x, pk, 256), sk, 256), x)
+    assert np.abs(eng.decrypt(eng.encrypt_zeta(x[0, :100], pk, 16), sk)[:100] - np.exp(-2j * np.pi * (x[0, :100] % 16) / 16)).max() < 5e-6
+    assert np.abs(eng.decrypt(eng.encrypt_zeta(x[0, :100], pk, 16), sk)[100:]).max() < 5e-6
     short = eng.decrypt(eng.encrypt(np.array([1.0, 2.0, 3.0]), pk), sk)
     assert np.allclose(short[:3], [1, 2, 3], atol=5e-6) and np.allclose(short[3:], 0, atol=5e-6)
 

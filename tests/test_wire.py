@@ -46,3 +46,16 @@ def test_rejects_foreign_parameters_damage_and_secret_keys(ref_backend_cls):
         wire.loads(a, bytes(bad))
     with pytest.raises(wire.WireError, match="not serialisable"):
         wire.dumps(a, sk)
+
+
+def test_byte_codec_fallback_matches_zeta_encoder(ref_backend_cls):
+    """Engine.encrypt_zeta / decrypt_zeta (device codec on the GPU) on a backend without a device codec:
+    same values as ZetaEncoder.to_zeta + encrypt / decrypt + from_zeta (xor_service.py:132-145)."""
+    from aes_fhe_b200.services.xor_service import ZetaEncoder
+    eng = _engine(ref_backend_cls)
+    sk = eng.create_secret_key(); pk = eng.create_public_key(sk)
+    x = np.random.default_rng(2).integers(0, 256, (2, eng.slot_count), dtype=np.uint8)
+    ct = eng.encrypt_zeta(x, pk, 256)
+    assert np.array_equal(ZetaEncoder.from_zeta(eng.decrypt(ct, sk), 256), x)
+    assert np.array_equal(eng.decrypt_zeta(ct, sk, 256), x)
+    assert np.array_equal(eng.decrypt_zeta(eng.encrypt_zeta(x[0, :10] % 16, pk), sk)[:10], x[0, :10] % 16)
