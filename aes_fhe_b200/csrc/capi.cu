@@ -277,7 +277,7 @@ void build_level_tables(fhe_ctx* c) {
 template <int NS>
 void launch_bconv_ns(fhe_ctx* c, cudaStream_t s, int groups, const BConvTable* tabs, int n_tabs, u64* dst,
                      long long dst_stride, const u64* src, long long src_stride) {
-    launch(k_bconv<NS>, dim3(c->n / 256, groups), dim3(256), s, c->T, tabs, n_tabs, dst, dst_stride, src, src_stride);
+    launch(k_bconv<NS>, dim3(c->n / 512, groups), dim3(256), s, c->T, tabs, n_tabs, dst, dst_stride, src, src_stride);
 }
 void launch_bconv(fhe_ctx* c, cudaStream_t s, int ns_max, int groups, const BConvTable* tabs, int n_tabs, u64* dst,
                   long long dst_stride, const u64* src, long long src_stride) {
@@ -586,7 +586,7 @@ int fhe_lincomb(fhe_ctx* c, void* stream, uint64_t* out, const uint64_t* const* 
         li.batch_stride[t] = (long long)nt * c->n;
         li.poly_stride[t] = (long long)batch * nt * c->n;
     }
-    dim3 grid(c->n / 256, 2 * batch * nq), block(256);
+    dim3 grid(c->n / 512, 2 * batch * nq), block(256);
     cudaStream_t s = (cudaStream_t)stream;
     const ConstF* cf = (const ConstF*)consts;
     const size_t smem = (size_t)M * T * sizeof(ConstF);

@@ -148,7 +148,8 @@ struct LinCombIn {
     long long batch_stride[FHE_LC_MAX_T];
 };
 // consts: [M][T][nq][2] ConstF (first / second half of the spectrum); c0: [M][nq][2] u64 or null
-// grid: (N/256, 2 * batch * nq)
+// grid: (N/512, 2 * batch * nq): a thread owns two coefficients 256 apart (same half of the
+// spectrum), so each constant fetched from shared memory feeds two modular products.
 template <int T_MAX>
 __global__ void __launch_bounds__(256) k_lincomb(DevTables Tb, int nq, int batch, int M, int T, LinCombIn in,
                                                  const ConstF* consts, const u64* c0, u64* out) {
@@ -157,30 +158,40 @@ __global__ void __launch_bounds__(256) k_lincomb(DevTables Tb, int nq, int batch
     const int j = row % nq, b = (row / nq) % batch, poly = row / (nq * batch);
     const Modulus Mo = Tb.mod[j];
     const double q = Mo.qd, qi = Mo.qinv;
-    const u32 idx = blockIdx.x * 256 + threadIdx.x;
-    const int half = (blockIdx.x * 256) >> (Tb.log_n - 1);        // uniform over the CTA
+    const u32 idx = blockIdx.x * 512 + threadIdx.x;
+    const int half = (blockIdx.x * 512) >> (Tb.log_n - 1);        // uniform over the CTA
     for (int i = threadIdx.x; i < M * T; i += 256)
         s_c[i] = consts[((size_t)i * nq + j) * 2 + half];
     const size_t lo = ((size_t)j << Tb.log_n) + idx;
-    double x[T_MAX];
+    double x0[T_MAX], x1[T_MAX];
 #pragma unroll
-    for (int t = 0; t < T_MAX; ++t)
-        x[t] = t < T ? u64_to_f(in.ptr[t][(size_t)poly * in.poly_stride[t] + (size_t)b * in.batch_stride[t] + lo]) : 0.0;
+    for (int t = 0; t < T_MAX; ++t) {
+        if (t < T) {
+            const u64* p = in.ptr[t] + (size_t)poly * in.poly_stride[t] + (size_t)b * in.batch_stride[t] + lo;
+            x0[t] = u64_to_f(p[0]); x1[t] = u64_to_f(p[256]);
+        } else { x0[t] = 0.0; x1[t] = 0.0; }
+    }
     __syncthreads();
     const size_t out_ct = (size_t)2 * batch * nq << Tb.log_n;
     u64* o = out + (((size_t)poly * batch + b) * nq << Tb.log_n) + lo;
     for (int m = 0; m < M; ++m) {
         const ConstF* cm = s_c + m * T;
-        double acc = 0.0;
+        double a0 = 0.0, a1 = 0.0;
 #pragma unroll
         for (int t = 0; t < T_MAX; ++t)
-            if (t < T) acc = d_add(acc, mulmod_const(x[t], cm[t], q));
-        double r = reduce_canon(acc, q, qi);
+            if (t < T) {
+                const ConstF c = cm[t];
+                a0 = d_add(a0, mulmod_const(x0[t], c, q));
+                a1 = d_add(a1, mulmod_const(x1[t], c, q));
+            }
+        double r0 = reduce_canon(a0, q, qi), r1 = reduce_canon(a1, q, qi);
         if (c0 != nullptr && poly == 0) {
-            r = d_add(r, u64_to_f(c0[((size_t)m * nq + j) * 2 + half]));
-            r = r >= q ? d_add(r, -q) : r;
+            const double k = u64_to_f(c0[((size_t)m * nq + j) * 2 + half]);
+            r0 = d_add(r0, k); r0 = r0 >= q ? d_add(r0, -q) : r0;
+            r1 = d_add(r1, k); r1 = r1 >= q ? d_add(r1, -q) : r1;
         }
-        o[(size_t)m * out_ct] = f_to_u64(r);
+        o[(size_t)m * out_ct] = f_to_u64(r0);
+        o[(size_t)m * out_ct + 256] = f_to_u64(r1);
     }
 }
 
@@ -276,6 +287,9 @@ struct BConvTable {
 // (ModUp: groups = batch x digits, all digits of one ciphertext read the same source block;
 //  ModDown: one table, groups = polys).  NS_MAX bounds every table's ns.  The constants of the
 // table are staged in shared memory once per CTA.
+// Every thread converts TWO coefficients (idx and idx + N/2): each constant fetched from shared
+// memory feeds two modular products, which halves the non-FP64 instructions per FP64 instruction
+// (the kernel is FP64-pipe bound and was co-limited by issue slots).   grid: (N/512, groups)
 template <int NS_MAX>
 __global__ void __launch_bounds__(256) k_bconv(DevTables T, const BConvTable* tables, int n_tables,
                                                u64* dst, long long dst_group_stride,
@@ -291,27 +305,37 @@ __global__ void __launch_bounds__(256) k_bconv(DevTables T, const BConvTable* ta
         const Modulus M = T.mod[tb.dst_mod[t]];
         sq[t] = M.qd; sqi[t] = M.qinv; sslot[t] = tb.dst_slot[t];
     }
-    const u32 idx = blockIdx.x * 256 + threadIdx.x;
     const int log_n = T.log_n;
+    const u32 idx = blockIdx.x * 256 + threadIdx.x;
+    const u32 half = 1u << (log_n - 1);
     const u64* s = src + (size_t)(g / n_tables) * src_block_stride + idx;
     u64* d = dst + (size_t)g * dst_group_stride + idx;
-    double y[NS_MAX];
+    double y0[NS_MAX], y1[NS_MAX];
 #pragma unroll
     for (int k = 0; k < NS_MAX; ++k) {
         if (k < ns) {
-            const u64 v = s[(size_t)tb.src_slot[k] << log_n];
+            const u64* sp = s + ((size_t)tb.src_slot[k] << log_n);
+            const u64 v0 = sp[0], v1 = sp[half];
             const u64 qk = T.mod[tb.src_mod[k]].q;
-            y[k] = v > (qk >> 1) ? d_add(u64_to_f(v), -u64_to_f(qk)) : u64_to_f(v);
-        } else y[k] = 0.0;
+            const double qkd = u64_to_f(qk);
+            y0[k] = v0 > (qk >> 1) ? d_add(u64_to_f(v0), -qkd) : u64_to_f(v0);
+            y1[k] = v1 > (qk >> 1) ? d_add(u64_to_f(v1), -qkd) : u64_to_f(v1);
+        } else { y0[k] = 0.0; y1[k] = 0.0; }
     }
     __syncthreads();
     for (int t = 0; t < nt; ++t) {
         const double q = sq[t];
-        double acc = 0.0;
+        double a0 = 0.0, a1 = 0.0;
 #pragma unroll
         for (int k = 0; k < NS_MAX; ++k)
-            if (k < ns) acc = d_add(acc, mulmod_const(y[k], sf[t * NS_MAX + k], q));
-        d[(size_t)sslot[t] << log_n] = f_to_u64(reduce_canon(acc, q, sqi[t]));
+            if (k < ns) {
+                const ConstF c = sf[t * NS_MAX + k];
+                a0 = d_add(a0, mulmod_const(y0[k], c, q));
+                a1 = d_add(a1, mulmod_const(y1[k], c, q));
+            }
+        u64* dp = d + ((size_t)sslot[t] << log_n);
+        dp[0] = f_to_u64(reduce_canon(a0, q, sqi[t]));
+        dp[half] = f_to_u64(reduce_canon(a1, q, sqi[t]));
     }
 }
 
