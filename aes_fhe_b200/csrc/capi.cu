@@ -409,9 +409,8 @@ int fhe_ctx_create(fhe_ctx** out, int log_n, int n_q, int n_p, int alpha, const 
         fz.sm_count = sms;
         fz.max_groups = std::max(1, sms * FHE_FUSED_MAX_OCC / gs);
         if (const char* fl = std::getenv("FHE_FUSED_FLAGS")) fz.flags = std::atoi(fl);
-        // resources are always there; the fused path is opt-in (FHE_NTT_FUSED=1 or fhe_set_ntt_fused):
-        // on B200 it halves the DRAM traffic of a transform but does not yet beat the two-pass
-        // kernels in wall time (profiles/r01_fused_ntt.md)
+        // resources are always there; mode 1 (persistent groups) is opt-in (FHE_NTT_FUSED=1 or
+        // fhe_set_ntt_fused): it is slower than the other two on small launches (profiles/r01_fused_ntt.md)
         const char* env = std::getenv("FHE_NTT_FUSED");
         fz.enabled = 0;
         if (coop && sms > 0) {
@@ -430,7 +429,9 @@ int fhe_ctx_create(fhe_ctx** out, int log_n, int n_q, int n_p, int alpha, const 
                 cudaMemset(fz.chain.ctr, 0, sizeof(unsigned) * (FHE_CHAIN_MAX_CHUNKS + 2));
                 c->owned.push_back(fz.chain.ctr);
                 if (const char* cr = std::getenv("FHE_CHAIN_ROWS")) fz.chain.chunk_rows = std::max(1, std::atoi(cr));
-                fz.chain.enabled = (env && env[0] == '2') ? 1 : 0;
+                // default: the chained single-launch transform (same wall time as two launches on B200, half
+                // the DRAM traffic, a third fewer launches); FHE_NTT_FUSED=0 selects the two-pass kernels
+                fz.chain.enabled = (!env || env[0] == '2') ? 1 : 0;
             }
 #ifdef FHE_EMU
             fz.enabled = !(env && env[0] == '0');      // the host simulator always exercises the fused kernels

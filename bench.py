@@ -331,8 +331,8 @@ def main():
     e2e_ms = (time.perf_counter() - t0) / max(1, args.steps // 2) * 1e3
     assert np.array_equal(np.atleast_2d(res), sbox[data])
 
-    # dominant kernel: the forward NTT (pass A + pass B), timed alone on this stream at the row
-    # count one key-switch ModUp of this batch launches
+    # dominant kernel: the forward NTT (both passes, one chained launch), timed alone on this stream at
+    # the row count one key-switch ModUp of this batch launches
     nq = MAX_LEVEL + 1
     P = eng.params
     rows = args.batch * P.digits_at(nq) * (nq + P.n_p)
@@ -376,11 +376,11 @@ def main():
                 "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms,
                         "h2d_bytes_per_step": int(data.nbytes),
                         "d2h_bytes_per_step": int(data.nbytes)},
-                "roofline": {"bound": "hbm", "kernel": "ntt_fwd (pass A + pass B)", "rows_per_launch": rows,
+                "roofline": {"bound": "hbm", "kernel": "ntt_fwd_chained (both radix passes in one launch)", "rows_per_launch": rows,
                              "achieved": achieved, "peak": peak, "peak_kind": peak_kind, "unit": "GB/s",
                              "frac": achieved / peak, "traffic": traffic,
-                             "note": "FP64-pipe bound: 8 FP64 ops per butterfly, pipe at 70-82 % (profiles/r01_ncu_twopass_v2.md); "
-                                     "traffic = ncu dram bytes of both passes"},
+                             "note": "FP64-pipe bound: 8 FP64 ops per butterfly, pipe at 70 % (profiles/r01_ncu_chained.md); "
+                                     "traffic = ncu dram bytes of the launch"},
                 "ms_per_ciphertext": ms / args.batch,
                 "keyswitches_per_ciphertext": 32}
         if not args.no_full_round and world == 1:

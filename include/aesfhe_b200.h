@@ -40,12 +40,14 @@ const char* fhe_last_error(void);
 /* number of kernels this library has launched since load (bench.py's gpu_launches) */
 uint64_t fhe_launch_count(void);
 
-/* NTT variant used by every entry point below.  Default: the two-pass kernels (csrc/ntt.cuh).
- * fhe_set_ntt_fused(ctx, 1) (or env FHE_NTT_FUSED=1 at context creation) selects the single-launch
- * persistent cooperative kernel (csrc/ntt_fused.cuh: each limb read from HBM once and written
- * once); the first enable runs a short calibration of the group speeds.  Results are
- * bit-identical.  fhe_ntt_fused_status synchronises the device and returns non-zero if a
- * hand-over of the fused kernel ever timed out (it never hangs). */
+/* NTT variant used by every entry point below (results are bit-identical):
+ *   2 (default)  csrc/ntt_chained.cuh -- both passes in ONE launch, ticket-ordered so that the lazy
+ *                intermediate is consumed from L2 (1.2 MB of DRAM traffic per limb instead of 2.0);
+ *   0            csrc/ntt.cuh -- two launches per transform;
+ *   1            csrc/ntt_fused.cuh -- persistent cooperative kernel (first enable calibrates the groups).
+ * fhe_set_ntt_fused(ctx, mode), or env FHE_NTT_FUSED=mode at context creation.
+ * fhe_ntt_fused_status synchronises the device and returns non-zero if a hand-over wait of modes 1 / 2
+ * ever timed out (they never hang). */
 int fhe_set_ntt_fused(fhe_ctx* ctx, int enabled);
 int fhe_ntt_fused_status(fhe_ctx* ctx);
 
