@@ -9,8 +9,9 @@ sbox_hi / sbox_lo degree-255 LUT polynomials and their product;
 /root/reference/sbox/sbox_service.py:116-138) at N = 2^16, max_level = 22
 (test/test_sbox_service.py:19), on a batch of B ciphertexts per GPU; one ciphertext packs
 slot_count/16 = 2048 AES blocks.  Both arms evaluate it with the baby-step/giant-step
-Paterson-Stockmeyer schedule of aes_fhe_b200/fused.py (32 key switches); the reference's own
-operation order (255 key switches) is timed once and reported as `reference_order`.
+Paterson-Stockmeyer schedule of aes_fhe_b200/fused.py on the product polynomial hi * lo folded by
+conjugate symmetry (SBoxService.sub_bytes_array_bsgs: 25 key switches, 9 levels); the reference's
+own operation order (255 key switches) is timed with --reference-order.
 
 A "step" is one pass of that path over one batch.  `value` = AES blocks per second with the
 input ciphertexts resident in HBM; `e2e` = the same through the public API from host buffers
@@ -110,7 +111,7 @@ class ClockSampler(threading.Thread):
 
 # --------------------------------------------------------------------------- CPU arm
 def cpu_arm(threads: int = 0):
-    """One full pass of the same schedule (sub_bytes_array_bsgs, 32 key switches) on ONE
+    """One full pass of the same schedule (sub_bytes_array_bsgs, 25 key switches) on ONE
     ciphertext (2048 blocks) on the CPU oracle, N = 2^16, max_level 22, all host cores."""
     from oracle.refmod import RefBackend, build
     build()
@@ -231,7 +232,7 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
-    config = {"workload": "configs[1]: SubBytes (sbox_hi/sbox_lo degree-255 zeta_256 LUT pair, BSGS schedule) on "
+    config = {"workload": "configs[1]: SubBytes (sbox_hi x sbox_lo degree-255 zeta_256 LUT polynomials, BSGS schedule) on "
                           "2048-block ciphertexts, N=2^16, max_level=22",
               "batch_ciphertexts_per_gpu": args.batch, "blocks_per_ciphertext": (1 << (LOG_N - 1)) // 16,
               "l2": "working set per step (GBs of power-basis ciphertexts) exceeds the 126 MB L2",
@@ -382,7 +383,7 @@ def main():
                              "note": "FP64-pipe bound: 8 FP64 ops per butterfly, pipe at 70 % (profiles/r01_ncu_chained.md); "
                                      "traffic = ncu dram bytes of the launch"},
                 "ms_per_ciphertext": ms / args.batch,
-                "keyswitches_per_ciphertext": 32}
+                "keyswitches_per_ciphertext": 25}
         if not args.no_full_round and world == 1:
             try:
                 line["full_round"] = full_round_probe(min(args.batch, 4))

@@ -112,10 +112,12 @@ def test_sbox_all_256_bytes_both_schedules(ref_backend_cls):
     x = np.tile(np.arange(256, dtype=np.uint8), sc // 256 + 1)[:sc]
     ct = ctx.encrypt(ZetaEncoder.to_zeta(x, 256))
     exp = np.array(AES_SBOX, dtype=np.uint8)[x]
-    for fn, lvl, ks in ((svc.sub_bytes_array, 2, 255), (svc.sub_bytes_array_bsgs, 1, 32)):
+    for fn, lvl, ks, cj in ((svc.sub_bytes_array, 2, 255, 0), (svc.sub_bytes_array_bsgs_hilo, 1, 32, 0),
+                            (svc.sub_bytes_array_bsgs, 3, 24, 1)):
         ctx.engine.op_counts.clear()
         out = fn(ct)
         assert out.level == lvl and ctx.engine.op_counts["keyswitch_relin"] == ks
+        assert ctx.engine.op_counts.get("keyswitch_galois", 0) == cj
         dec = ctx.decrypt(out)
         assert np.abs(dec - ZetaEncoder.to_zeta(exp, 256)).max() < 1e-3
         assert np.array_equal(ZetaEncoder.from_zeta(dec, 256), exp)
