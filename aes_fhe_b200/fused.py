@@ -13,7 +13,7 @@ relinearisation.  Everything is batched: the ciphertext operands may carry any b
 
 Depth: baby basis + giant basis + 2.  For the reference's degree-255 S-box pair
 (/root/reference/sbox/sbox_service.py:116-138: 254 relinearisations, 10 levels) that is
-4 + 4 + 2 (+1 for hi x lo) = 11 levels and 15 + 14 + 2 + 1 = 32 key switches (25 and 9 levels in the
+4 + 4 + 2 (+1 for hi x lo) = 11 levels and 15 + 14 + 2 + 1 = 32 key switches (23 and 10 levels in the
 folded single-polynomial form of SBoxService.sub_bytes_array_bsgs); for the 4-bit XOR
 (/root/reference/xor_service.py:271-286: 92 key switches, 5 levels) 5 levels and 29 key switches.
 Same slot values within CKKS noise; residues differ from the reference operation order.

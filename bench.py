@@ -10,7 +10,7 @@ sbox_hi / sbox_lo degree-255 LUT polynomials and their product;
 (test/test_sbox_service.py:19), on a batch of B ciphertexts per GPU; one ciphertext packs
 slot_count/16 = 2048 AES blocks.  Both arms evaluate it with the baby-step/giant-step
 Paterson-Stockmeyer schedule of aes_fhe_b200/fused.py on the product polynomial hi * lo folded by
-conjugate symmetry (SBoxService.sub_bytes_array_bsgs: 25 key switches, 9 levels); the reference's
+conjugate symmetry (SBoxService.sub_bytes_array_bsgs: 23 key switches, 10 levels); the reference's
 own operation order (255 key switches) is timed with --reference-order.
 
 A "step" is one pass of that path over one batch.  `value` = AES blocks per second with the
@@ -111,7 +111,7 @@ class ClockSampler(threading.Thread):
 
 # --------------------------------------------------------------------------- CPU arm
 def cpu_arm(threads: int = 0):
-    """One full pass of the same schedule (sub_bytes_array_bsgs, 25 key switches) on ONE
+    """One full pass of the same schedule (sub_bytes_array_bsgs, 23 key switches) on ONE
     ciphertext (2048 blocks) on the CPU oracle, N = 2^16, max_level 22, all host cores."""
     from oracle.refmod import RefBackend, build
     build()
@@ -383,7 +383,7 @@ def main():
                              "note": "FP64-pipe bound: 8 FP64 ops per butterfly, pipe at 70 % (profiles/r01_ncu_chained.md); "
                                      "traffic = ncu dram bytes of the launch"},
                 "ms_per_ciphertext": ms / args.batch,
-                "keyswitches_per_ciphertext": 25}
+                "keyswitches_per_ciphertext": 23}
         if not args.no_full_round and world == 1:
             try:
                 line["full_round"] = full_round_probe(min(args.batch, 4))

@@ -113,7 +113,7 @@ def test_sbox_all_256_bytes_both_schedules(ref_backend_cls):
     ct = ctx.encrypt(ZetaEncoder.to_zeta(x, 256))
     exp = np.array(AES_SBOX, dtype=np.uint8)[x]
     for fn, lvl, ks, cj in ((svc.sub_bytes_array, 2, 255, 0), (svc.sub_bytes_array_bsgs_hilo, 1, 32, 0),
-                            (svc.sub_bytes_array_bsgs, 3, 24, 1)):
+                            (svc.sub_bytes_array_bsgs, 2, 22, 1)):
         ctx.engine.op_counts.clear()
         out = fn(ct)
         assert out.level == lvl and ctx.engine.op_counts["keyswitch_relin"] == ks
