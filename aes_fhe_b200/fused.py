@@ -15,7 +15,8 @@ Depth: baby basis + giant basis + 2.  For the reference's degree-255 S-box pair
 (/root/reference/sbox/sbox_service.py:116-138: 254 relinearisations, 10 levels) that is
 4 + 4 + 2 (+1 for hi x lo) = 11 levels and 15 + 14 + 2 + 1 = 32 key switches (23 and 10 levels in the
 folded single-polynomial form of SBoxService.sub_bytes_array_bsgs); for the 4-bit XOR
-(/root/reference/xor_service.py:271-286: 92 key switches, 5 levels) 5 levels and 29 key switches.
+(/root/reference/xor_service.py:271-286: 92 key switches, 5 levels) 5 levels and 17 key switches (odd powers only: 5 products per operand, 4 conjugations for y, two
+lazily relinearised outer sums and one conjugation).
 Same slot values within CKKS noise; residues differ from the reference operation order.
 """
 from __future__ import annotations
@@ -30,13 +31,31 @@ from .engine import Ciphertext
 _EPS = 1e-13
 
 
-def power_basis_16(eng_wrap, ct) -> Dict[int, Ciphertext]:
-    """{k: ct^k} for k = 1..15 of a unit-modulus (zeta_16) ciphertext: 7 products and 7
-    conjugations (t^(16-k) = conj(t^k)), as /root/reference/xor_service.py:245-254."""
-    pos = eng_wrap.make_power_basis(ct, 8)
-    basis = {k: c for k, c in enumerate(pos, 1)}
-    for k in range(1, 8):
-        basis[16 - k] = eng_wrap.conjugate(pos[k - 1])
+def power_basis_16(eng_wrap, ct, wanted: Optional[Sequence[int]] = None) -> Dict[int, Ciphertext]:
+    """{k: ct^k} of a unit-modulus (zeta_16) ciphertext for the exponents in `wanted` (default: all
+    of 1..15), with t^(16-k) = conj(t^k) as /root/reference/xor_service.py:245-254.  Only the powers
+    that are wanted, or needed to build a wanted one (t^k = t^ceil(k/2) * t^floor(k/2), depth 3), are
+    computed: the XOR polynomial has odd exponents only, which takes 5 products and 4 conjugations
+    instead of 7 and 7."""
+    eng, rlk = eng_wrap.engine, eng_wrap.relin_key
+    wanted = sorted(set(range(1, 16) if wanted is None else wanted))
+    low = sorted({k if k <= 8 else 16 - k for k in wanted})          # positive powers 1..8 behind them
+    need = set()
+
+    def req(k):
+        if k > 1 and k not in need:
+            need.add(k)
+            req((k + 1) // 2)
+            req(k // 2)
+
+    for k in low:
+        req(k)
+    pw: Dict[int, Ciphertext] = {1: ct}
+    for k in sorted(need):
+        pw[k] = eng.multiply(pw[(k + 1) // 2], pw[k // 2], rlk)
+    basis = {}
+    for k in wanted:
+        basis[k] = pw[k] if k <= 8 else eng_wrap.conjugate(pw[16 - k])
     return basis
 
 
@@ -107,12 +126,33 @@ def bivariate_lut(eng_wrap, ct_x, ct_y, coeff_mats: Sequence[np.ndarray],
                   by: Optional[Dict[int, Ciphertext]] = None, cache_key="biv") -> List[Ciphertext]:
     """f_m(x, y) = sum_ij C_m[i][j] x^i y^j for 16x16 coefficient matrices (zeta_16 inputs)."""
     eng = eng_wrap.engine
-    if bx is None:
-        bx = power_basis_16(eng_wrap, ct_x)
-    if by is None:
-        by = power_basis_16(eng_wrap, ct_y)
     used_i = [i for i in range(1, 16) if any(np.any(np.abs(np.asarray(C)[i]) > _EPS) for C in coeff_mats)]
     used_j = [j for j in range(1, 16) if any(np.any(np.abs(np.asarray(C)[:, j]) > _EPS) for C in coeff_mats)]
+    hi_i = [i for i in used_i if i > 8]
+    if bx is None and by is None and 2 * len(coeff_mats) < len(hi_i):
+        # Few outputs: do not build conj(x^k) at all.  With x^i = conj(x^(16-i)) for i > 8,
+        #     f = sum_{i<=8} x^i g_i(y)  +  conj( sum_{i>8} x^(16-i) conj(g_i)(y) ),
+        # and conj(g_i)(y) = sum_j conj(c_ij) y^((16-j) % 16) is again a constant-only sum over the
+        # y basis.  Two outer sums and ONE conjugation per output replace the conjugations of the
+        # x basis (XOR: 17 key switches instead of 19).
+        by = power_basis_16(eng_wrap, ct_y, sorted(set(used_j) | {(16 - j) % 16 for j in used_j if j}))
+        bx = power_basis_16(eng_wrap, ct_x, sorted({i if i <= 8 else 16 - i for i in used_i}))
+        mats = []
+        for C in coeff_mats:
+            C = np.asarray(C, dtype=np.complex128)
+            A = C.copy(); A[9:] = 0.0
+            B = np.zeros_like(C)
+            for i in hi_i:
+                for j in range(16):
+                    B[16 - i, (16 - j) % 16] = np.conj(C[i, j])
+            mats += [A, B]
+        outs = _outer_sum(eng, eng_wrap.relin_key, {i: bx[i] for i in sorted(bx)}, {j: by[j] for j in sorted(by)},
+                          mats, (cache_key, "conj-split", len(coeff_mats)))
+        return [eng.add(outs[2 * m], eng_wrap.conjugate(outs[2 * m + 1])) for m in range(len(coeff_mats))]
+    if bx is None:
+        bx = power_basis_16(eng_wrap, ct_x, used_i)
+    if by is None:
+        by = power_basis_16(eng_wrap, ct_y, used_j)
     outer = {i: bx[i] for i in used_i}
     inner = {j: by[j] for j in used_j}
     return _outer_sum(eng, eng_wrap.relin_key, outer, inner, coeff_mats, (cache_key, len(coeff_mats)))
