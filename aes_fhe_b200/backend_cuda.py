@@ -210,6 +210,19 @@ class CudaBackend:
         self._call("fhe_add", self._ptr(out), self._ptr(out), self._ptr(p), 1, a.shape[1], 1, a.shape[1], nq, 0)
         return out
 
+    def add_poly0_inplace(self, a, p, nq):
+        """as add_poly0 for a temporary `a` the caller owns"""
+        p = self.expand_batch(p, a.shape[1]).contiguous()
+        self._call("fhe_add", self._ptr(a), self._ptr(a), self._ptr(p), 1, a.shape[1], 1, a.shape[1], nq, 0)
+        return a
+
+    def add_into_polys(self, acc, p, nq):
+        """acc[:p.shape[0]] += p in place (p broadcast over the batch if it has batch 1)"""
+        k, bt = p.shape[0], acc.shape[1]
+        p = self.expand_batch(p, bt).contiguous()
+        self._call("fhe_add", self._ptr(acc), self._ptr(acc), self._ptr(p), k, bt, k, bt, nq, 0)
+        return acc
+
     def tensor(self, a, b, nq):
         bt = max(a.shape[1], b.shape[1])
         a = self.expand_batch(a, bt).contiguous()
@@ -355,7 +368,15 @@ class CudaBackend:
         a_list = [x.contiguous() for x in a_list]
         b_batch = b_list[0].shape[1]
         bt = max(b_batch, max(x.shape[1] for x in a_list))
-        bcat = torch.stack([x.contiguous() for x in b_list], dim=0).contiguous()
+        # the inner sums usually are consecutive slices of one fhe_lincomb output: use them in place
+        step = b_list[0].numel() * 8
+        if all(x.is_contiguous() and x.shape == b_list[0].shape and x.data_ptr() == b_list[0].data_ptr() + k * step
+               for k, x in enumerate(b_list)):
+            b_base = b_list[0].data_ptr()
+            keep = b_list                                           # keeps the storage alive during the calls
+        else:
+            keep = torch.stack([x.contiguous() for x in b_list], dim=0).contiguous()
+            b_base = keep.data_ptr()
         accumulate = 1
         if acc is None:
             acc = self._empty(3, bt, nq, self.n)
@@ -366,7 +387,7 @@ class CudaBackend:
             ptrs = (C.c_void_p * g)(*[x.data_ptr() for x in a_list[done:done + g]])
             nqs = (C.c_int * g)(*[x.shape[2] for x in a_list[done:done + g]])
             abs_ = (C.c_int * g)(*[x.shape[1] for x in a_list[done:done + g]])
-            self._call("fhe_tensor_acc", self._ptr(acc), ptrs, nqs, abs_, self._ptr(bcat[done]), b_batch, g, nq, bt,
+            self._call("fhe_tensor_acc", self._ptr(acc), ptrs, nqs, abs_, C.c_void_p(b_base + done * step), b_batch, g, nq, bt,
                        accumulate)
             accumulate = 1
             done += g

@@ -606,7 +606,8 @@ class Engine:
             acc = be.ks_inner(be.automorphism_rows(ext, key.galois), be.select_poly(rot, 1), key.data, nq)
             ks = be.moddown_inplace(acc, nq) if hasattr(be, "moddown_inplace") else be.moddown(acc, nq)
             self._count('keyswitch_galois')
-            outs.append(Ciphertext(self, be.add_poly0(ks, be.select_poly(rot, 0), nq), ct.level))
+            add0 = be.add_poly0_inplace if hasattr(be, "add_poly0_inplace") else be.add_poly0
+            outs.append(Ciphertext(self, add0(ks, be.select_poly(rot, 0), nq), ct.level))
         return outs
 
     def _mul_scalar(self, ct: Ciphertext, value) -> Ciphertext:
@@ -686,7 +687,8 @@ class Engine:
         rot = be.automorphism(ct.polys, key.galois, nq, 0)
         ks = be.keyswitch(be.select_poly(rot, 1), key.data, nq)
         self._count('keyswitch_galois')
-        return Ciphertext(self, be.add_poly0(ks, be.select_poly(rot, 0), nq), ct.level)
+        add0 = be.add_poly0_inplace if hasattr(be, "add_poly0_inplace") else be.add_poly0      # ks is a temporary
+        return Ciphertext(self, add0(ks, be.select_poly(rot, 0), nq), ct.level)
 
     def conjugate(self, ct: Ciphertext, conj_key: ConjugationKey) -> Ciphertext:
         if ct.zero:

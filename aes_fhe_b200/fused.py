@@ -115,7 +115,10 @@ def _outer_sum(eng, relin_key, outer: Dict[int, Ciphertext], inner_basis: Dict[i
         else:
             acc = be.zeros(3, bt, nq, False)
         if zero_term is not None:
-            acc = be.concat([be.add(be.take_polys(acc, 2), be.expand_batch(zero_term, bt), nq, 0), be.select_poly(acc, 2)])
+            if hasattr(be, "add_into_polys"):
+                acc = be.add_into_polys(acc, zero_term, nq)              # in place on polynomials 0 and 1
+            else:
+                acc = be.concat([be.add(be.take_polys(acc, 2), be.expand_batch(zero_term, bt), nq, 0), be.select_poly(acc, 2)])
         ct2 = eng._relin(Ciphertext(eng, acc, lo), relin_key)
         outs.append(eng._rescale(eng._rescale(ct2)))
     return outs
