@@ -296,9 +296,9 @@ void launch_ks_inner(fhe_ctx* c, cudaStream_t s, int nq, int batch, u64* acc, co
                      const u64* ksk, const u64* lift, const ConstF* lift_c) {
     const int beta = c->modup_beta[nq];
     dim3 grid(c->n / 256, nq + c->n_p), block(256);
-    if (beta <= 2) launch(k_ks_inner<2, 4>, grid, block, s, c->T, nq, c->alpha, beta, batch, acc, ext, d, ksk, lift, lift_c);
-    else if (beta <= 4) launch(k_ks_inner<4, 4>, grid, block, s, c->T, nq, c->alpha, beta, batch, acc, ext, d, ksk, lift, lift_c);
-    else launch(k_ks_inner<8, 2>, grid, block, s, c->T, nq, c->alpha, beta, batch, acc, ext, d, ksk, lift, lift_c);
+    if (beta <= 2) launch(k_ks_inner<2, 2>, grid, block, s, c->T, nq, c->alpha, beta, batch, acc, ext, d, ksk, lift, lift_c);
+    else if (beta <= 4) launch(k_ks_inner<4, 2>, grid, block, s, c->T, nq, c->alpha, beta, batch, acc, ext, d, ksk, lift, lift_c);
+    else launch(k_ks_inner<8, 1>, grid, block, s, c->T, nq, c->alpha, beta, batch, acc, ext, d, ksk, lift, lift_c);
 }
 
 #ifndef FHE_EMU

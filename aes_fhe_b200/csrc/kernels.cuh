@@ -393,8 +393,11 @@ __global__ void __launch_bounds__(256, (BMAX <= 4 ? 3 : 2)) k_ks_inner(DevTables
     const u64* dp = d + ((size_t)t << log_n) + idx;                 // + b * nq * N
     const u64* ep = ext + ((size_t)t << log_n) + idx;               // + (b * beta + j) * ne * N
     const u64* lp = has_lift ? lift + ((size_t)t << log_n) + idx : nullptr;
-    for (int b0 = 0; b0 < batch; b0 += UNR) {
-        u64 e[UNR][BMAX], l0[UNR], l1[UNR];
+    // software pipeline: the loads of the next UNR ciphertexts are in flight while the current ones are
+    // multiplied, so the memory system never waits for the FP64 work (and vice versa)
+    u64 e[UNR][BMAX], l0[UNR], l1[UNR];
+    u64 en[UNR][BMAX], l0n[UNR], l1n[UNR];
+    auto fetch = [&](int b0, u64 (&E)[UNR][BMAX], u64 (&L0)[UNR], u64 (&L1)[UNR]) {
 #pragma unroll
         for (int u = 0; u < UNR; ++u) {
             const int b = b0 + u;
@@ -402,14 +405,18 @@ __global__ void __launch_bounds__(256, (BMAX <= 4 ? 3 : 2)) k_ks_inner(DevTables
 #pragma unroll
                 for (int j = 0; j < BMAX; ++j)
                     if (j < beta)
-                        e[u][j] = ld_u64(j == own ? dp + (((size_t)b * nq) << log_n)
+                        E[u][j] = ld_u64(j == own ? dp + (((size_t)b * nq) << log_n)
                                                   : ep + ((((size_t)b * beta + j) * ne) << log_n));
                 if (has_lift) {
-                    l0[u] = ld_u64(lp + (((size_t)b * nq) << log_n));
-                    l1[u] = ld_u64(lp + ps + (((size_t)b * nq) << log_n));
+                    L0[u] = ld_u64(lp + (((size_t)b * nq) << log_n));
+                    L1[u] = ld_u64(lp + ps + (((size_t)b * nq) << log_n));
                 }
             }
         }
+    };
+    fetch(0, e, l0, l1);
+    for (int b0 = 0; b0 < batch; b0 += UNR) {
+        if (b0 + UNR < batch) fetch(b0 + UNR, en, l0n, l1n);
 #pragma unroll
         for (int u = 0; u < UNR; ++u) {
             const int b = b0 + u;
@@ -431,6 +438,12 @@ __global__ void __launch_bounds__(256, (BMAX <= 4 ? 3 : 2)) k_ks_inner(DevTables
                 acc[(((size_t)b * ne + t) << log_n) + idx] = f_to_u64(reduce_canon(a0, q, qi));
                 acc[((((size_t)batch + b) * ne + t) << log_n) + idx] = f_to_u64(reduce_canon(a1, q, qi));
             }
+        }
+#pragma unroll
+        for (int u = 0; u < UNR; ++u) {
+#pragma unroll
+            for (int j = 0; j < BMAX; ++j) e[u][j] = en[u][j];
+            l0[u] = l0n[u]; l1[u] = l1n[u];
         }
     }
 }
