@@ -23,7 +23,12 @@ METRICS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.
 
 
 def full(rep, out):
-    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    """rep: an .ncu-rep file, or the CSV written on the GPU box by `ncu --set full --csv --page raw`"""
+    if str(rep).endswith(".csv"):
+        raw = Path(rep).read_text()
+        raw = raw[raw.index('"ID"'):]
+    else:
+        raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(raw)))
     hdr, units = rows[0], rows[1]
     idx = {h: i for i, h in enumerate(hdr)}
