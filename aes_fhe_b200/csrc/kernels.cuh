@@ -474,4 +474,8 @@ struct StoreSubMul {
         const double x = u64_to_f(in[(size_t)poly * in_poly_stride + lo]);
         out[(size_t)poly * out_poly_stride + lo] = f_to_u64(canon(mulmod_const(d_add(x, -v), c[j], M.qd), M.qd));
     }
+    // the epilogue reads `in`: bring the 128-byte line the 16 lanes of a row cover into L2 early
+    FHE_D void warm(const RowMap& map, RowRef row, int idx) const {
+        prefetch_l2(in + (size_t)row.blk * in_poly_stride + ((size_t)row.j << map.log_n) + idx);
+    }
 };

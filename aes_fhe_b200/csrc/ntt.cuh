@@ -196,6 +196,9 @@ struct StorePlain {
     FHE_D void operator()(const RowMap& map, RowRef row, int idx, double v, int, const Modulus&) const {
         dst[row_off(map, row, poly_stride) + idx] = f_to_u64(v);
     }
+    // a StoreOp may read other operands in its epilogue: warm(idx) is called once per thread at the
+    // start of the last pass with the first of 16 consecutive elements the thread's row will need
+    FHE_D void warm(const RowMap&, RowRef, int) const {}
 };
 struct LoadRaw {            // lazy doubles written by the other pass
     const u64* src; long long poly_stride;
@@ -333,6 +336,7 @@ FHE_D void fwd_pass_b_body(const DevTables& T, const RowMap& map, RowRef rref, i
     double* smS = sm + rr * RS + l16;                         // strided view    [18 * i]
     double* smC = sm + rr * RS + 18 * l16;                    // contiguous view [i]
     double x[16];
+    st.warm(map, rref, (grow << 8) + 16 * l16);               // epilogue operands -> L2 while the butterflies run
 #pragma unroll
     for (int i = 0; i < 16; ++i) x[i] = ld(map, rref, rbase + 16 * i, mid, M);
     const Tw15 t2 = ld_tw15c<LOG_N>(tw, grow * 16 + l16);     // issued early, used in round 2
