@@ -323,7 +323,28 @@ __global__ void __launch_bounds__(256) k_bconv(DevTables T, const BConvTable* ta
         } else { y0[k] = 0.0; y1[k] = 0.0; }
     }
     __syncthreads();
-    for (int t = 0; t < nt; ++t) {
+    // two targets per iteration: four independent accumulation chains per thread
+    int t = 0;
+    for (; t + 1 < nt; t += 2) {
+        const double qa = sq[t], qb = sq[t + 1];
+        double a0 = 0.0, a1 = 0.0, b0 = 0.0, b1 = 0.0;
+#pragma unroll
+        for (int k = 0; k < NS_MAX; ++k)
+            if (k < ns) {
+                const ConstF ca = sf[t * NS_MAX + k], cb = sf[(t + 1) * NS_MAX + k];
+                a0 = d_add(a0, mulmod_const(y0[k], ca, qa));
+                a1 = d_add(a1, mulmod_const(y1[k], ca, qa));
+                b0 = d_add(b0, mulmod_const(y0[k], cb, qb));
+                b1 = d_add(b1, mulmod_const(y1[k], cb, qb));
+            }
+        u64* da = d + ((size_t)sslot[t] << log_n);
+        u64* db = d + ((size_t)sslot[t + 1] << log_n);
+        da[0] = f_to_u64(reduce_canon(a0, qa, sqi[t]));
+        da[half] = f_to_u64(reduce_canon(a1, qa, sqi[t]));
+        db[0] = f_to_u64(reduce_canon(b0, qb, sqi[t + 1]));
+        db[half] = f_to_u64(reduce_canon(b1, qb, sqi[t + 1]));
+    }
+    if (t < nt) {
         const double q = sq[t];
         double a0 = 0.0, a1 = 0.0;
 #pragma unroll
