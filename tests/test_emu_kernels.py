@@ -53,3 +53,16 @@ def test_engine_ops(emu_lib, ref_backend_cls):
 def test_fused_lut_services(emu_lib, ref_backend_cls):
     P = make_params(12, 13)
     kp.check_fused_services(P, _emu(P, emu_lib), ref_backend_cls(P), batch=2)
+
+
+@pytest.mark.parametrize("chunk", [1, 3, 5])
+def test_chained_ntt_many_chunks(chunk, emu_lib, ref_backend_cls, monkeypatch):
+    """The chained single-launch NTT with tiny chunks (FHE_CHAIN_ROWS): several segments, a ragged last
+    chunk, padding CTAs and skipped rows (ModUp layout) all occur at these sizes."""
+    monkeypatch.setenv("FHE_CHAIN_ROWS", str(chunk))
+    P = make_params(12, 6, dnum=4)
+    b = _emu(P, emu_lib, 2)
+    kp.check_primitives(P, b, ref_backend_cls(P))
+    kp.check_keyswitch(P, b, ref_backend_cls(P))
+    kp.check_rescale(P, b, ref_backend_cls(P))
+    assert b.lib.fhe_ntt_fused_status(b.ctx) == 0
