@@ -347,6 +347,16 @@ void fused_calibrate(fhe_ctx* c) {
 
 }  // namespace
 
+// constant tiles above the default 48 KB dynamic shared-memory limit need an opt-in per kernel
+#define FHE_LC_SMEM_LIMIT (160 * 1024)
+template <class K> static void lc_allow_smem(K k, size_t smem) {
+#ifndef FHE_EMU
+    if (smem > 48 * 1024) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, FHE_LC_SMEM_LIMIT);
+#else
+    (void)k; (void)smem;
+#endif
+}
+
 extern "C" {
 
 const char* fhe_last_error(void) { return g_err.c_str(); }
@@ -587,15 +597,17 @@ int fhe_lincomb(fhe_ctx* c, void* stream, uint64_t* out, const uint64_t* const* 
         li.batch_stride[t] = (long long)nt * c->n;
         li.poly_stride[t] = (long long)batch * nt * c->n;
     }
-    dim3 grid(c->n / 512, 2 * batch * nq), block(256);
     cudaStream_t s = (cudaStream_t)stream;
     const ConstF* cf = (const ConstF*)consts;
-    const size_t smem = (size_t)M * T * sizeof(ConstF);
-    if (smem > 48 * 1024) return fail("fhe_lincomb: M * T too large for the shared-memory constant tile");
+    const int kt = (T + 3) / 4;
+    const size_t smem = FHE_LCM_SMEM(M, kt);
+    if (smem > FHE_LC_SMEM_LIMIT) return fail("fhe_lincomb: M * T too large for the shared-memory constant tile");
+    dim3 grid(c->n / FHE_LCM_CHUNK, 2 * batch * nq), block(256);
     g_launches.fetch_add(1, std::memory_order_relaxed);
-    if (T <= 4) fhe_launch(k_lincomb<4>, grid, block, smem, s, c->T, nq, batch, M, T, li, cf, (const u64*)c0, (u64*)out);
-    else if (T <= 8) fhe_launch(k_lincomb<8>, grid, block, smem, s, c->T, nq, batch, M, T, li, cf, (const u64*)c0, (u64*)out);
-    else fhe_launch(k_lincomb<16>, grid, block, smem, s, c->T, nq, batch, M, T, li, cf, (const u64*)c0, (u64*)out);
+#define FHE_LC_CASE(KT) case KT: lc_allow_smem(k_lincomb_mma<KT>, smem); \
+        fhe_launch(k_lincomb_mma<KT>, grid, block, smem, s, c->T, nq, batch, M, T, li, cf, (const u64*)c0, (u64*)out); break;
+    switch (kt) { FHE_LC_CASE(1) FHE_LC_CASE(2) FHE_LC_CASE(3) default: FHE_LC_CASE(4) }
+#undef FHE_LC_CASE
     return check("fhe_lincomb");
 }
 

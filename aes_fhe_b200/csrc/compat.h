@@ -30,6 +30,13 @@ inline void fhe_launch(void (*k)(KArgs...), dim3 g, dim3 b, size_t smem, cudaStr
 
 FHE_D u64 umulhi64(u64 a, u64 b) { return __umul64hi(a, b); }
 FHE_D u32 brev32(u32 x) { return __brev(x); }
+// FP64 tensor-core product of one warp: C[8x8] += A[8x4] B[4x8].  With g = lane >> 2, t = lane & 3 a lane holds
+// a = A[g][t], b = B[t][g], c0 = C[g][2t], c1 = C[g][2t+1].  Same 64 FMA/clk/SM as DFMA (tools/ubench/dmma.cu)
+// but eight FMAs per lane per instruction with both operands in registers.
+FHE_D void dmma884(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
 
 #else
 // ----------------------------------------------------------------------------- emulation
@@ -91,6 +98,20 @@ inline u32 brev32(u32 x) {
     u32 r = 0;
     for (int i = 0; i < 32; ++i) { r = (r << 1) | (x & 1); x >>= 1; }
     return r;
+}
+// warp-collective 8x8x4 product: lanes exchange their fragments through a per-block buffer between two barriers
+// (every thread of the block must execute the same sequence of dmma884 calls, which the kernels guarantee)
+#include <cmath>
+inline void dmma884(double& c0, double& c1, double a, double b) {
+    static thread_local double ea[1024], eb[1024];
+    const int tid = (int)threadIdx.x, wb = tid & ~31, g = (tid & 31) >> 2, t = tid & 3;
+    ea[tid] = a; eb[tid] = b;
+    __syncthreads();
+    for (int k = 0; k < 4; ++k) {
+        c0 = std::fma(ea[wb + g * 4 + k], eb[wb + (2 * t) * 4 + k], c0);
+        c1 = std::fma(ea[wb + g * 4 + k], eb[wb + (2 * t + 1) * 4 + k], c1);
+    }
+    __syncthreads();
 }
 template <typename T> inline T min(T a, T b) { return a < b ? a : b; }
 template <typename T> inline T max(T a, T b) { return a > b ? a : b; }

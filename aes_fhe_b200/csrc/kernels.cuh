@@ -148,50 +148,90 @@ struct LinCombIn {
     long long batch_stride[FHE_LC_MAX_T];
 };
 // consts: [M][T][nq][2] ConstF (first / second half of the spectrum); c0: [M][nq][2] u64 or null
-// grid: (N/512, 2 * batch * nq): a thread owns two coefficients 256 apart (same half of the
-// spectrum), so each constant fetched from shared memory feeds two modular products.
-template <int T_MAX>
-__global__ void __launch_bounds__(256) k_lincomb(DevTables Tb, int nq, int batch, int M, int T, LinCombIn in,
-                                                 const ConstF* consts, const u64* c0, u64* out) {
-    FHE_DYN_SHARED(ConstF, s_c);                                  // [M][T] constants of this (limb, half)
+// The sums are a warp-level matrix product on the FP64 tensor cores: rows = 8 coefficients,
+// K = the T inputs, columns = 8 outputs.  Exact Karatsuba dot products (modarith.cuh, split23 / dot3_finish):
+// inputs and constants are split at 2^23 into (h, l, s = h + l); the three sums  sum h h', sum s s', sum l l'
+// are DMMA accumulations of integers below 2^51, so every FMA inside the tensor core is exact, and each output
+// is reduced once.  Three FMAs per term instead of the seven of mulmod_const + add, no operand fetch per FMA:
+// the constants of an 8-output tile are a B fragment in registers (one conflict-free LDS.64 per 8x8x4 block).
+// The scalar form of this kernel (constants broadcast from shared memory into DFMAs) ran at 53 % of the FP64
+// peak because a broadcast LDS delivers 4 bytes per cycle per SM; DMMA runs at the same 64 FMA/clk/SM as DFMA
+// (tools/ubench/dmma.cu) but needs no operand traffic: 5.70 -> 3.56 ms for the 22 x 11 sums of SubBytes at
+// batch 16 (profiles/r01_kernel_breakdown_*.md).  The same formulation for the base conversion was measured
+// and not kept: k_bconv already runs at 89 % of the FP64 peak and the reduction per target eats the gain.
+//   consts staged per CTA as three shared-memory planes [ceil8(M)][STRIDE];  grid: (N / 512, 2 * batch * nq)
+#define FHE_LCM_CHUNK 512
+#define FHE_LCM_STRIDE(KT) (4 * (KT) + ((KT) % 2 == 0 ? 4 : 0))
+#define FHE_LCM_SMEM(M, KT) ((size_t)3 * (((M) + 7) & ~7) * FHE_LCM_STRIDE(KT) * sizeof(double))
+template <int KT>
+__global__ void __launch_bounds__(256, 2) k_lincomb_mma(DevTables Tb, int nq, int batch, int M, int T, LinCombIn in,
+                                                        const ConstF* consts, const u64* c0, u64* out) {
+    constexpr int TP = 4 * KT, STRIDE = FHE_LCM_STRIDE(KT), MT = 2;
+    FHE_DYN_SHARED(double, s_c);
     const int row = blockIdx.y;
     const int j = row % nq, b = (row / nq) % batch, poly = row / (nq * batch);
     const Modulus Mo = Tb.mod[j];
     const double q = Mo.qd, qi = Mo.qinv;
-    const u32 idx = blockIdx.x * 512 + threadIdx.x;
-    const int half = (blockIdx.x * 512) >> (Tb.log_n - 1);        // uniform over the CTA
-    for (int i = threadIdx.x; i < M * T; i += 256)
-        s_c[i] = consts[((size_t)i * nq + j) * 2 + half];
-    const size_t lo = ((size_t)j << Tb.log_n) + idx;
-    double x0[T_MAX], x1[T_MAX];
+    const int half = (blockIdx.x * FHE_LCM_CHUNK) >> (Tb.log_n - 1);      // uniform over the CTA
+    const int MP = (M + 7) & ~7, plane = MP * STRIDE;
+    for (int i = threadIdx.x; i < MP * TP; i += 256) {
+        const int m = i / TP, t = i % TP;
+        const Split3 c = split23(m < M && t < T ? consts[(((size_t)m * T + t) * nq + j) * 2 + half].w : 0.0);
+        s_c[m * STRIDE + t] = c.h; s_c[plane + m * STRIDE + t] = c.l; s_c[2 * plane + m * STRIDE + t] = c.s;
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, gid = lane >> 2, tig = lane & 3;
+    const u64* p[KT];
 #pragma unroll
-    for (int t = 0; t < T_MAX; ++t) {
-        if (t < T) {
-            const u64* p = in.ptr[t] + (size_t)poly * in.poly_stride[t] + (size_t)b * in.batch_stride[t] + lo;
-            x0[t] = u64_to_f(p[0]); x1[t] = u64_to_f(p[256]);
-        } else { x0[t] = 0.0; x1[t] = 0.0; }
+    for (int kt = 0; kt < KT; ++kt) {
+        const int t = 4 * kt + tig;
+        p[kt] = t < T ? in.ptr[t] + (size_t)poly * in.poly_stride[t] + (size_t)b * in.batch_stride[t] + ((size_t)j << Tb.log_n)
+                      : nullptr;
     }
     __syncthreads();
     const size_t out_ct = (size_t)2 * batch * nq << Tb.log_n;
-    u64* o = out + (((size_t)poly * batch + b) * nq << Tb.log_n) + lo;
-    for (int m = 0; m < M; ++m) {
-        const ConstF* cm = s_c + m * T;
-        double a0 = 0.0, a1 = 0.0;
+    u64* o = out + (((size_t)poly * batch + b) * nq << Tb.log_n) + ((size_t)j << Tb.log_n);
+    const bool add_c0 = c0 != nullptr && poly == 0;
+    const u32 base = blockIdx.x * FHE_LCM_CHUNK + warp * (FHE_LCM_CHUNK / 8);
+    for (int it = 0; it < FHE_LCM_CHUNK / 8 / (8 * MT); ++it) {
+        Split3 a[MT][KT];
+        u32 ci[MT];
 #pragma unroll
-        for (int t = 0; t < T_MAX; ++t)
-            if (t < T) {
-                const ConstF c = cm[t];
-                a0 = d_add(a0, mulmod_const(x0[t], c, q));
-                a1 = d_add(a1, mulmod_const(x1[t], c, q));
-            }
-        double r0 = reduce_canon(a0, q, qi), r1 = reduce_canon(a1, q, qi);
-        if (c0 != nullptr && poly == 0) {
-            const double k = u64_to_f(c0[((size_t)m * nq + j) * 2 + half]);
-            r0 = d_add(r0, k); r0 = r0 >= q ? d_add(r0, -q) : r0;
-            r1 = d_add(r1, k); r1 = r1 >= q ? d_add(r1, -q) : r1;
+        for (int mi = 0; mi < MT; ++mi) {
+            ci[mi] = base + (it * MT + mi) * 8 + gid;
+#pragma unroll
+            for (int kt = 0; kt < KT; ++kt) a[mi][kt] = split23(p[kt] != nullptr ? u64_to_f(p[kt][ci[mi]]) : 0.0);
         }
-        o[(size_t)m * out_ct] = f_to_u64(r0);
-        o[(size_t)m * out_ct + 256] = f_to_u64(r1);
+        for (int n = 0; n < MP / 8; ++n) {
+            const int bo = (8 * n + gid) * STRIDE + tig;
+            double acc[MT][3][2];
+#pragma unroll
+            for (int mi = 0; mi < MT; ++mi)
+#pragma unroll
+                for (int u = 0; u < 3; ++u) acc[mi][u][0] = acc[mi][u][1] = 0.0;
+#pragma unroll
+            for (int kt = 0; kt < KT; ++kt) {
+                const double bh = s_c[bo + 4 * kt], bl = s_c[plane + bo + 4 * kt], bs = s_c[2 * plane + bo + 4 * kt];
+#pragma unroll
+                for (int mi = 0; mi < MT; ++mi) {
+                    dmma884(acc[mi][0][0], acc[mi][0][1], a[mi][kt].h, bh);
+                    dmma884(acc[mi][1][0], acc[mi][1][1], a[mi][kt].s, bs);
+                    dmma884(acc[mi][2][0], acc[mi][2][1], a[mi][kt].l, bl);
+                }
+            }
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int m = 8 * n + 2 * tig + e;
+                if (m < M) {
+                    const double k = add_c0 ? u64_to_f(c0[((size_t)m * nq + j) * 2 + half]) : 0.0;
+#pragma unroll
+                    for (int mi = 0; mi < MT; ++mi) {
+                        double r = dot3_finish(acc[mi][0][e], acc[mi][1][e], acc[mi][2][e], q, qi);
+                        if (add_c0) { r = d_add(r, k); r = r >= q ? d_add(r, -q) : r; }
+                        o[(size_t)m * out_ct + ci[mi]] = f_to_u64(r);
+                    }
+                }
+            }
+        }
     }
 }
 

@@ -85,6 +85,39 @@ FHE_D double reduce_sym(double x, double q, double qinv) { return d_fma(-round_q
 FHE_D double canon(double r, double q) { return r < 0.0 ? d_add(r, q) : r; }
 FHE_D double reduce_canon(double x, double q, double qinv) { return canon(reduce_sym(x, q, qinv), q); }
 
+// ---- exact dot products with constants:  sum_t x_t c_t mod q  in three FP64 operations per term
+// Both factors are split at 2^23 (x = xh 2^23 + xl, c = ch 2^23 + cl, |xl|, |cl| <= 2^22, xh, ch <= 2^22), and
+// the three Karatsuba sums  A = sum xh ch,  B = sum (xh+xl)(ch+cl),  C = sum xl cl  are plain FMA chains whose
+// partial sums stay below 2^51 for up to 16 terms -- every FMA is exact.  The split of x is done once per input
+// and the split of c once per table entry, so a term costs 3 FP64 operations instead of the 7 of
+// mulmod_const + add; the modular reduction happens once per output:
+//     sum = (A 2^23 + (B - A - C)) 2^23 + C       (Horner; a product by 2^23 is exact, so each step is a
+//                                                  quotient estimate and one FMA)
+// Needs |x_t| < 2^45, 0 <= c_t < 2^45, at most 16 terms, q > 2^24.
+#define FHE_TWO23 8388608.0
+#define FHE_INV_TWO23 1.1920928955078125e-07
+struct Split3 { double h, l, s; };     // v = h 2^23 + l,  s = h + l
+FHE_D Split3 split23(double v) {
+    Split3 r;
+    r.h = d_add(d_fma(v, FHE_INV_TWO23, FHE_MAGIC), -FHE_MAGIC);
+    r.l = d_fma(r.h, -FHE_TWO23, v);
+    r.s = d_add(r.h, r.l);
+    return r;
+}
+// x 2^23 mod q, signed, |r| <= q (1/2 + |x| 2^-52): the product by a power of two is exact, so no error term
+FHE_D double mul23_mod(double x, double q, double wq23) {
+    const double qe = round_quot(x, wq23);
+    return d_fma(-qe, q, d_mul(x, FHE_TWO23));
+}
+// canonical residue of A 2^46 + (B - A - C) 2^23 + C
+FHE_D double dot3_finish(double A, double B, double C, double q, double qinv) {
+    const double wq23 = d_mul(FHE_TWO23, qinv);
+    const double mid = d_add(d_add(B, -A), -C);
+    const double t1 = mul23_mod(A, q, wq23);
+    const double t2 = mul23_mod(d_add(t1, mid), q, wq23);
+    return reduce_canon(d_add(t2, C), q, qinv);
+}
+
 // ---- integer helpers (canonical add/sub are pure ALU work; Barrett only on cold paths)
 FHE_HD u64 add_mod(u64 a, u64 b, u64 q) { u64 s = a + b; return s >= q ? s - q : s; }
 FHE_HD u64 sub_mod(u64 a, u64 b, u64 q) { return a >= b ? a - b : a + q - b; }

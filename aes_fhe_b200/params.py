@@ -33,6 +33,9 @@ BASE_BITS = 45
 SPECIAL_BITS = 45
 DEFAULT_SCALE_BITS = 40
 DEFAULT_DNUM = 4
+# log2(P Q) allowed at N = 2^16 for 128-bit security with a sparse ternary secret (the bound the default
+# L = 30 parameter set was sized against)
+LOG_PQ_BUDGET_2_16 = 1770
 
 
 # --------------------------------------------------------------------------- #
@@ -170,9 +173,31 @@ class CKKSParams:
 
 
 @lru_cache(maxsize=None)
+def auto_dnum(log_n: int, max_level: int, scale_bits: int) -> int:
+    """Key-switch digit count when the caller does not give one.
+
+    Fewer, wider digits mean fewer ModUp rows to transform (beta (n + K) - n per key switch), a smaller
+    key stream (2 beta (n + K) limbs) and fewer inner-product terms, at the price of more special primes
+    (P must exceed the widest digit).  On the B200 the trade is a clear win as long as P Q stays inside
+    the security budget: SubBytes at max_level = 22 takes 55.1 ms per 16 ciphertexts with 4 digits,
+    54.0 with 3 and 53.7 with 2 (profiles/r01_dnum_sweep.md).  So at N = 2^16: the smallest digit count
+    in {2, 3, 4} whose log2(P Q) fits LOG_PQ_BUDGET_2_16.  Smaller rings (tests) keep four digits."""
+    if log_n != 16:
+        return DEFAULT_DNUM
+    n_q = max_level + 1
+    for d in (2, 3):
+        alpha = -(-n_q // d)
+        digit_bits = BASE_BITS + (alpha - 1) * scale_bits
+        k = -(-(digit_bits + 1) // (SPECIAL_BITS - 1))          # special primes are just below 2^45
+        if BASE_BITS + max_level * scale_bits + k * SPECIAL_BITS <= LOG_PQ_BUDGET_2_16:
+            return d
+    return DEFAULT_DNUM
+
+
+@lru_cache(maxsize=None)
 def make_params(log_n: int = 16, max_level: int = 30, special_count: int = 0,
-                dnum: int = DEFAULT_DNUM, scale_bits: int = DEFAULT_SCALE_BITS) -> CKKSParams:
-    """Build the deterministic parameter set.
+                dnum: int = 0, scale_bits: int = DEFAULT_SCALE_BITS) -> CKKSParams:
+    """Build the deterministic parameter set.  ``dnum == 0`` means "choose" (auto_dnum).
 
     ``special_count == 0`` means "derive K from the digit size" (enough special
     primes that P exceeds the largest digit product, the hybrid key-switching
@@ -187,6 +212,8 @@ def make_params(log_n: int = 16, max_level: int = 30, special_count: int = 0,
     n = 1 << log_n
     two_n = 2 * n
     n_q = max_level + 1
+    if dnum <= 0:
+        dnum = auto_dnum(log_n, max_level, scale_bits)
 
     q0 = _primes_below(1 << BASE_BITS, two_n, 1)[0]
 

@@ -42,6 +42,12 @@ METRIC = "homomorphic AES blocks/sec (SubBytes stage, 2048 blocks per ciphertext
 UNIT = "blocks/s"
 MAX_LEVEL = 22
 LOG_N = 16
+DNUM = None          # key-switch digit count; None = the parameter set's default (params.make_params)
+
+
+def _params(level=MAX_LEVEL):
+    from aes_fhe_b200.params import make_params
+    return make_params(LOG_N, level) if DNUM is None else make_params(LOG_N, level, dnum=DNUM)
 
 
 def _peak_gbs():
@@ -65,7 +71,7 @@ def _make_service(backend=None, seed=1, device_id=0):
     from aes_fhe_b200.params import make_params
     from aes_fhe_b200.services.engine_context import EngineContext
     from aes_fhe_b200.services.sbox_service import SBoxService
-    kw = dict(_params=make_params(LOG_N, MAX_LEVEL), seed=seed)
+    kw = dict(_params=_params(), seed=seed)
     if backend is not None:
         kw["_backend"] = backend
     ctx = EngineContext(signature=2, max_level=MAX_LEVEL, mode="parallel", device_id=device_id, _engine_kwargs=kw,
@@ -118,7 +124,7 @@ def cpu_arm(threads: int = 0):
     from aes_fhe_b200.params import make_params
     from aes_fhe_b200.services.xor_service import ZetaEncoder
     from aes_fhe_b200.services.sbox_service import AES_SBOX
-    P = make_params(LOG_N, MAX_LEVEL)
+    P = _params()
     be = RefBackend(P, threads=threads)
     ctx, svc = _make_service(backend=be)
     eng = ctx.engine
@@ -220,6 +226,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=16, help="ciphertexts per GPU per step")
+    ap.add_argument("--dnum", type=int, default=None, help="key-switch digit count of the SubBytes parameter set")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-full-round", action="store_true",
                     help="skip the extra measurement of one full AES round (configs[3])")
@@ -228,6 +235,8 @@ def main():
     ap.add_argument("--reference-order", action="store_true",
                     help="also time the reference's own 255-key-switch operation order")
     args = ap.parse_args()
+    global DNUM
+    DNUM = args.dnum
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -44,6 +44,14 @@ def test_keyswitch_phases(log_n, lvl, dnum, fused, emu_lib, ref_backend_cls):
     kp.check_keyswitch(P, _emu(P, emu_lib, fused), ref_backend_cls(P))
 
 
+def test_keyswitch_wide_digits(emu_lib, ref_backend_cls):
+    """Digits of 10 limbs (dnum = 2 at 20 limbs): the base conversion's one-coefficient-per-thread form
+    (more than six source limbs) and its 16-term exact dot product."""
+    P = make_params(12, 19, dnum=2)
+    assert P.alpha == 10
+    kp.check_keyswitch(P, _emu(P, emu_lib, 2), ref_backend_cls(P), levels=[19, 12, 4])
+
+
 def test_engine_ops(emu_lib, ref_backend_cls):
     P = make_params(12, 6)
     eg, er = make_engines(P, ref_backend_cls, _emu(P, emu_lib))
