@@ -292,15 +292,23 @@ void launch_bconv(fhe_ctx* c, cudaStream_t s, int ns_max, int groups, const BCon
 #undef FHE_BCONV_CASE
 }
 
+// ab: `d` / `lift` are the operand ciphertexts a / b of a fused multiply (k_ks_inner, AB)
 void launch_ks_inner(fhe_ctx* c, cudaStream_t s, int nq, int batch, u64* acc, const u64* ext, const u64* d,
-                     const u64* ksk, const u64* lift, const ConstF* lift_c) {
+                     const u64* ksk, const u64* lift, const ConstF* lift_c, bool ab = false) {
     const int beta = c->modup_beta[nq];
     dim3 grid(c->n / 256, nq + c->n_p), block(256);
-    if (beta <= 2) launch(k_ks_inner<2, 2>, grid, block, s, c->T, nq, c->alpha, beta, batch, acc, ext, d, ksk, lift, lift_c);
-    else if (beta <= 4) launch(k_ks_inner<4, 2>, grid, block, s, c->T, nq, c->alpha, beta, batch, acc, ext, d, ksk, lift, lift_c);
-    else launch(k_ks_inner<8, 1>, grid, block, s, c->T, nq, c->alpha, beta, batch, acc, ext, d, ksk, lift, lift_c);
+#define FHE_KS_ARGS grid, block, s, c->T, nq, c->alpha, beta, batch, acc, ext, d, ksk, lift, lift_c
+    if (ab) {
+        if (beta <= 2) launch(k_ks_inner<2, 2, true>, FHE_KS_ARGS);
+        else if (beta <= 4) launch(k_ks_inner<4, 2, true>, FHE_KS_ARGS);
+        else launch(k_ks_inner<8, 1, true>, FHE_KS_ARGS);
+    } else {
+        if (beta <= 2) launch(k_ks_inner<2, 2, false>, FHE_KS_ARGS);
+        else if (beta <= 4) launch(k_ks_inner<4, 2, false>, FHE_KS_ARGS);
+        else launch(k_ks_inner<8, 1, false>, FHE_KS_ARGS);
+    }
+#undef FHE_KS_ARGS
 }
-
 #ifndef FHE_EMU
 // The warp scheduler favours the CTAs that have been resident longest, so the groups of the
 // persistent fused-NTT grid run at different speeds depending on the residency slot their CTAs
@@ -346,6 +354,28 @@ void fused_calibrate(fhe_ctx* c) {
 #endif
 
 }  // namespace
+
+// ModUp of [batch][nq][N] rows produced by `ld` (plain NTT-domain residues, or the product a1 * b1 of a fused multiply)
+template <class LoadOp>
+static int modup_from(fhe_ctx* c, cudaStream_t s, u64* ext, LoadOp ld, int nq, int batch) {
+    const int n = c->n, ne = nq + c->n_p, beta = c->modup_beta[nq];
+    u64* y = arena(c, (size_t)batch * nq * n);
+    if (!y) return fail("fhe_modup: scratch allocation failed");
+    {   // iNTT with the (Q_j/q_i)^-1 factor folded into the final stage
+        RowMap m = make_map(c, nq, 0, nq);
+        StorePlain st; st.dst = y; st.poly_stride = (long long)nq * n;
+        ntt_inv(c, m, batch * nq, ld, y, (long long)nq * n, st, c->modup_scale[nq], s);
+    }
+    launch_bconv(c, s, std::min(c->alpha, nq), batch * beta, c->modup_tables[nq], beta, ext, (long long)ne * n, y,
+                 (long long)nq * n);
+    {   // NTT of every converted row (a digit's own limbs are skipped)
+        RowMap m = make_map(c, ne, 0, nq, c->alpha);
+        LoadPlain l2; l2.src = (const u64*)ext; l2.poly_stride = (long long)ne * n;
+        StorePlain st; st.dst = ext; st.poly_stride = (long long)ne * n;
+        ntt_fwd(c, m, batch * beta * ne, l2, ext, (long long)ne * n, st, s);
+    }
+    return check("fhe_modup");
+}
 
 // constant tiles above the default 48 KB dynamic shared-memory limit need an opt-in per kernel
 #define FHE_LC_SMEM_LIMIT (160 * 1024)
@@ -707,25 +737,8 @@ int fhe_automorphism(fhe_ctx* c, void* stream, uint64_t* out, const uint64_t* in
 
 int fhe_modup(fhe_ctx* c, void* stream, uint64_t* ext, const uint64_t* d, int nq, int batch) {
     if (bad_shape(c, nq, 0) || c->n_p == 0 || batch < 1) return fail("fhe_modup: bad shape");
-    cudaStream_t s = (cudaStream_t)stream;
-    const int n = c->n, ne = nq + c->n_p, beta = c->modup_beta[nq];
-    u64* y = arena(c, (size_t)batch * nq * n);
-    if (!y) return fail("fhe_modup: scratch allocation failed");
-    {   // iNTT with the (Q_j/q_i)^-1 factor folded into the final stage
-        RowMap m = make_map(c, nq, 0, nq);
-        LoadPlain ld; ld.src = (const u64*)d; ld.poly_stride = (long long)nq * n;
-        StorePlain st; st.dst = y; st.poly_stride = (long long)nq * n;
-        ntt_inv(c, m, batch * nq, ld, y, (long long)nq * n, st, c->modup_scale[nq], s);
-    }
-    launch_bconv(c, s, std::min(c->alpha, nq), batch * beta, c->modup_tables[nq], beta, (u64*)ext, (long long)ne * n, y,
-                 (long long)nq * n);
-    {   // NTT of every converted row (a digit's own limbs are skipped)
-        RowMap m = make_map(c, ne, 0, nq, c->alpha);
-        LoadPlain ld; ld.src = (const u64*)ext; ld.poly_stride = (long long)ne * n;
-        StorePlain st; st.dst = (u64*)ext; st.poly_stride = (long long)ne * n;
-        ntt_fwd(c, m, batch * beta * ne, ld, (u64*)ext, (long long)ne * n, st, s);
-    }
-    return check("fhe_modup");
+    LoadPlain ld; ld.src = (const u64*)d; ld.poly_stride = (long long)nq * c->n;
+    return modup_from(c, (cudaStream_t)stream, (u64*)ext, ld, nq, batch);
 }
 
 int fhe_ks_inner(fhe_ctx* c, void* stream, uint64_t* acc, const uint64_t* ext, const uint64_t* d,
@@ -737,22 +750,31 @@ int fhe_ks_inner(fhe_ctx* c, void* stream, uint64_t* acc, const uint64_t* ext, c
     return check("fhe_ks_inner");
 }
 
-int fhe_relin_rescale(fhe_ctx* c, void* stream, uint64_t* out, const uint64_t* d3, const uint64_t* rlk, int nq,
-                      int batch) {
+// d3 != null: the 3-polynomial tensor product; else (a, b): the operands of a fused multiply
+static int relin_rescale_impl(fhe_ctx* c, void* stream, uint64_t* out, const uint64_t* d3, const uint64_t* a,
+                              const uint64_t* b, const uint64_t* rlk, int nq, int batch, const char* who) {
     if (bad_shape(c, nq, 0) || nq < 2 || c->n_p == 0 || batch < 1 || c->modup_beta[nq] > FHE_MAX_BETA)
-        return fail("fhe_relin_rescale: bad shape");
+        return fail((std::string(who) + ": bad shape").c_str());
     cudaStream_t s = (cudaStream_t)stream;
     const int n = c->n, K = c->n_p, ne = nq + K, beta = c->modup_beta[nq], no = nq - 1;
     const size_t words = ((size_t)batch * nq + (size_t)batch * beta * ne + 2 * (size_t)batch * ne) * n;
     u64* base = arena(c, words);
-    if (!base) return fail("fhe_relin_rescale: scratch allocation failed");
+    if (!base) return fail((std::string(who) + ": scratch allocation failed").c_str());
     u64* ext = base + (size_t)batch * nq * n;
     u64* acc = ext + (size_t)batch * beta * ne * n;
-    const u64* d2 = (const u64*)d3 + 2 * (size_t)batch * nq * n;
+    const size_t poly = (size_t)batch * nq * n;
     int rc;
-    if ((rc = fhe_modup(c, stream, (uint64_t*)ext, (const uint64_t*)d2, nq, batch))) return rc;
-    // inner product with the key, plus P * (d0, d1) on the q-limbs
-    launch_ks_inner(c, s, nq, batch, acc, (const u64*)ext, d2, (const u64*)rlk, (const u64*)d3, c->p_mod_q);
+    if (d3) {
+        const u64* d2 = (const u64*)d3 + 2 * poly;
+        if ((rc = fhe_modup(c, stream, (uint64_t*)ext, (const uint64_t*)d2, nq, batch))) return rc;
+        // inner product with the key, plus P * (d0, d1) on the q-limbs
+        launch_ks_inner(c, s, nq, batch, acc, (const u64*)ext, d2, (const u64*)rlk, (const u64*)d3, c->p_mod_q);
+    } else {
+        LoadMul ld; ld.a = (const u64*)a + poly; ld.b = (const u64*)b + poly; ld.poly_stride = (long long)nq * n;
+        if ((rc = modup_from(c, s, ext, ld, nq, batch))) return rc;
+        launch_ks_inner(c, s, nq, batch, acc, (const u64*)ext, (const u64*)a, (const u64*)rlk, (const u64*)b, c->p_mod_q,
+                        true);
+    }
     const int npoly = 2 * batch;
     u64* accs = acc + (size_t)no * n;                       // rows q_{nq-1}, p_0 .. p_{K-1} are contiguous
     {
@@ -769,7 +791,19 @@ int fhe_relin_rescale(fhe_ctx* c, void* stream, uint64_t* out, const uint64_t* d
         st.in = acc; st.in_poly_stride = (long long)ne * n; st.c = c->mdrs_inv[nq];
         ntt_fwd(c, m, npoly * no, ld, (u64*)out, (long long)no * n, st, s);
     }
-    return check("fhe_relin_rescale");
+    return check(who);
+}
+
+int fhe_relin_rescale(fhe_ctx* c, void* stream, uint64_t* out, const uint64_t* d3, const uint64_t* rlk, int nq,
+                      int batch) {
+    if (!d3) return fail("fhe_relin_rescale: null operand");
+    return relin_rescale_impl(c, stream, out, d3, nullptr, nullptr, rlk, nq, batch, "fhe_relin_rescale");
+}
+
+int fhe_mul_relin_rescale(fhe_ctx* c, void* stream, uint64_t* out, const uint64_t* a, const uint64_t* b,
+                          const uint64_t* rlk, int nq, int batch) {
+    if (!a || !b) return fail("fhe_mul_relin_rescale: null operand");
+    return relin_rescale_impl(c, stream, out, nullptr, a, b, rlk, nq, batch, "fhe_mul_relin_rescale");
 }
 
 int fhe_moddown(fhe_ctx* c, void* stream, uint64_t* out, uint64_t* acc, int nq, int npoly) {

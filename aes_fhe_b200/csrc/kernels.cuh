@@ -426,7 +426,10 @@ FHE_D void st2(u64* p, u64 a, u64 b) {
 // words are read once (2 * beta doubles in registers), then the batch is walked UNR ciphertexts at
 // a time with all UNR * (beta + 2) loads issued before the first multiply -- the kernel is
 // HBM-bound and what matters is the number of bytes in flight per SM (Little's law: ~150 KB).
-template <int BMAX, int UNR>
+// AB: fused multiply + relinearise + rescale.  `d` and `lift` then are the two operand ciphertexts a, b
+// ([2][batch][nq][N]) and the tensor product is formed here: the digit's own limb is a1 b1, the lifted part
+// P * (a0 b0, a0 b1 + a1 b0) -- the 3-polynomial product never goes through HBM.
+template <int BMAX, int UNR, bool AB>
 __global__ void __launch_bounds__(256, (BMAX <= 4 ? 3 : 2)) k_ks_inner(DevTables T, int nq, int alpha, int beta, int batch,
                                                   u64* acc, const u64* ext, const u64* d, const u64* ksk,
                                                   const u64* lift, const ConstF* lift_c) {
@@ -456,45 +459,60 @@ __global__ void __launch_bounds__(256, (BMAX <= 4 ? 3 : 2)) k_ks_inner(DevTables
     const u64* lp = has_lift ? lift + ((size_t)t << log_n) + idx : nullptr;
     // software pipeline: the loads of the next UNR ciphertexts are in flight while the current ones are
     // multiplied, so the memory system never waits for the FP64 work (and vice versa)
-    u64 e[UNR][BMAX], l0[UNR], l1[UNR];
-    u64 en[UNR][BMAX], l0n[UNR], l1n[UNR];
-    auto fetch = [&](int b0, u64 (&E)[UNR][BMAX], u64 (&L0)[UNR], u64 (&L1)[UNR]) {
+    // (AB: l0/l1 carry b0/b1 and m0/m1 carry a0/a1 of the q-limbs; the own-digit slot of e is not loaded)
+    u64 e[UNR][BMAX], l0[UNR], l1[UNR], m0[UNR], m1[UNR];
+    u64 en[UNR][BMAX], l0n[UNR], l1n[UNR], m0n[UNR], m1n[UNR];
+    const u64* bp = AB && has_lift ? d + ((size_t)t << log_n) + idx : nullptr;      // operand a (named d), q-limbs only
+    auto fetch = [&](int b0, u64 (&E)[UNR][BMAX], u64 (&L0)[UNR], u64 (&L1)[UNR], u64 (&M0)[UNR], u64 (&M1)[UNR]) {
 #pragma unroll
         for (int u = 0; u < UNR; ++u) {
             const int b = b0 + u;
             if (b < batch) {
 #pragma unroll
                 for (int j = 0; j < BMAX; ++j)
-                    if (j < beta)
-                        E[u][j] = ld_u64(j == own ? dp + (((size_t)b * nq) << log_n)
-                                                  : ep + ((((size_t)b * beta + j) * ne) << log_n));
+                    if (j < beta) {
+                        if (AB) { if (j != own) E[u][j] = ld_u64(ep + ((((size_t)b * beta + j) * ne) << log_n)); }
+                        else E[u][j] = ld_u64(j == own ? dp + (((size_t)b * nq) << log_n)
+                                                       : ep + ((((size_t)b * beta + j) * ne) << log_n));
+                    }
                 if (has_lift) {
                     L0[u] = ld_u64(lp + (((size_t)b * nq) << log_n));
                     L1[u] = ld_u64(lp + ps + (((size_t)b * nq) << log_n));
+                    if (AB) {
+                        M0[u] = ld_u64(bp + (((size_t)b * nq) << log_n));
+                        M1[u] = ld_u64(bp + ps + (((size_t)b * nq) << log_n));
+                    }
                 }
             }
         }
     };
-    fetch(0, e, l0, l1);
+    fetch(0, e, l0, l1, m0, m1);
     for (int b0 = 0; b0 < batch; b0 += UNR) {
-        if (b0 + UNR < batch) fetch(b0 + UNR, en, l0n, l1n);
+        if (b0 + UNR < batch) fetch(b0 + UNR, en, l0n, l1n, m0n, m1n);
 #pragma unroll
         for (int u = 0; u < UNR; ++u) {
             const int b = b0 + u;
             if (b < batch) {
                 double a0 = 0.0, a1 = 0.0;
+                double own_v = 0.0, t0 = 0.0, t1 = 0.0;
+                if (AB && has_lift) {
+                    const double x0 = u64_to_f(m0[u]), x1 = u64_to_f(m1[u]), y0 = u64_to_f(l0[u]), y1 = u64_to_f(l1[u]);
+                    own_v = mulmod_var(x1, y1, q, qi);                                   // d2 on this limb
+                    t0 = mulmod_var(x0, y0, q, qi);                                      // d0
+                    t1 = d_add(mulmod_var(x0, y1, q, qi), mulmod_var(x1, y0, q, qi));    // d1, |.| <= 1.02 q
+                }
 #pragma unroll
                 for (int j = 0; j < BMAX; ++j) {
                     if (j < beta) {
-                        const double ev = u64_to_f(e[u][j]);
+                        const double ev = AB && j == own ? own_v : u64_to_f(e[u][j]);
                         a0 = d_add(a0, mulmod_var(ev, k0[j], q, qi));
                         a1 = d_add(a1, mulmod_var(ev, k1[j], q, qi));
                     }
                 }
                 if (has_lift) {
                     // fused relinearise + rescale: add P * (d0, d1) so the sum can be divided by P q_last at once
-                    a0 = d_add(a0, mulmod_const(u64_to_f(l0[u]), pc, q));
-                    a1 = d_add(a1, mulmod_const(u64_to_f(l1[u]), pc, q));
+                    a0 = d_add(a0, mulmod_const(AB ? t0 : u64_to_f(l0[u]), pc, q));
+                    a1 = d_add(a1, mulmod_const(AB ? t1 : u64_to_f(l1[u]), pc, q));
                 }
                 acc[(((size_t)b * ne + t) << log_n) + idx] = f_to_u64(reduce_canon(a0, q, qi));
                 acc[((((size_t)batch + b) * ne + t) << log_n) + idx] = f_to_u64(reduce_canon(a1, q, qi));
@@ -505,6 +523,7 @@ __global__ void __launch_bounds__(256, (BMAX <= 4 ? 3 : 2)) k_ks_inner(DevTables
 #pragma unroll
             for (int j = 0; j < BMAX; ++j) e[u][j] = en[u][j];
             l0[u] = l0n[u]; l1[u] = l1n[u];
+            if (AB) { m0[u] = m0n[u]; m1[u] = m1n[u]; }
         }
     }
 }
@@ -522,6 +541,18 @@ struct LoadCentered {
     FHE_D void prefetch(const RowMap& map, RowRef row, int idx, int count) const {
         const u64* p = last + ((size_t)row.blk << map.log_n) + idx;
         for (int k = 0; k < count; k += 16) prefetch_l2(p + k);
+    }
+};
+// fused multiply + relinearise: the key switch transforms d2 = a1 * b1 without d2 ever being written
+struct LoadMul {
+    const u64* a; const u64* b; long long poly_stride;      // polynomial 1 of each operand, rows [batch][nq]
+    FHE_D double operator()(const RowMap& map, RowRef row, int idx, int, const Modulus& M) const {
+        const size_t o = row_off(map, row, poly_stride) + idx;
+        return canon(mulmod_var(u64_to_f(a[o]), u64_to_f(b[o]), M.qd, M.qinv), M.qd);
+    }
+    FHE_D void prefetch(const RowMap& map, RowRef row, int idx, int count) const {
+        const size_t o = row_off(map, row, poly_stride) + idx;
+        for (int k = 0; k < count; k += 16) { prefetch_l2(a + o + k); prefetch_l2(b + o + k); }
     }
 };
 // rescale / ModDown epilogue: out = (in - ntt_value) * c[j]

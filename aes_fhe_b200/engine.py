@@ -632,12 +632,16 @@ class Engine:
             return self._zero(a.level - 1, 2 if rlk is not None else 3, max(a.batch, b.batch))
         nq = a.level + 1
         self._count('mul_ct')
-        d = self.backend.tensor(a.polys, b.polys, nq)
         if rlk is not None:
             # relinearise and rescale together: one ModDown by P * q_l instead of ModDown + rescale
             self._count('keyswitch_relin')
             self._count('rescale')
+            if hasattr(self.backend, "mul_relin_rescale"):
+                # ... and the tensor product inside the key switch (never stored)
+                return Ciphertext(self, self.backend.mul_relin_rescale(a.polys, b.polys, rlk.data, nq), a.level - 1)
+            d = self.backend.tensor(a.polys, b.polys, nq)
             return Ciphertext(self, self.backend.relin_rescale(d, rlk.data, nq), a.level - 1)
+        d = self.backend.tensor(a.polys, b.polys, nq)
         return self._rescale(Ciphertext(self, d, a.level))
 
     def square(self, a: Ciphertext, relin_key=None) -> Ciphertext:

@@ -145,6 +145,14 @@ int fhe_moddown(fhe_ctx* ctx, void* stream, uint64_t* out, uint64_t* acc, int nq
 int fhe_relin_rescale(fhe_ctx* ctx, void* stream, uint64_t* out, const uint64_t* d3, const uint64_t* rlk,
                       int nq, int batch);
 
+/* Engine.multiply(ct, ct, rlk) in one call (xor_service.py:71, and every product of make_power_basis,
+ * xor_service.py:86 / sbox/sbox_service.py:93): a, b [2][batch][nq][N] -> out[2][batch][nq-1][N], the same
+ * residues as fhe_tensor followed by fhe_relin_rescale.  The 3-polynomial product is never stored: the
+ * key switch's first inverse NTT forms d2 = a1 b1 on load and the key inner product forms
+ * P (a0 b0, a0 b1 + a1 b0) from the operands. */
+int fhe_mul_relin_rescale(fhe_ctx* ctx, void* stream, uint64_t* out, const uint64_t* a, const uint64_t* b,
+                          const uint64_t* rlk, int nq, int batch);
+
 /* Engine.encode / encrypt residue step (xor_service.py:59-66): signed 64-bit coefficients
  * coeffs[batch][N] (device) -> coefficient-domain residues out[batch][nq + np][N]. */
 int fhe_from_i64(fhe_ctx* ctx, void* stream, uint64_t* out, const int64_t* coeffs, int nq, int np, int batch);

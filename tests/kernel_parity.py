@@ -71,6 +71,19 @@ def check_keyswitch(P, gb, rb, levels=None, seed=3):
         gm, rm = gb.moddown(ga, nq), rb.moddown(ra, nq)
         assert np.array_equal(gb.to_numpy(gm), rm), f"moddown nq={nq}"
         assert np.array_equal(gb.to_numpy(gb.keyswitch(gb.from_numpy(d), gk, nq)), rm), f"keyswitch nq={nq}"
+        if nq >= 2:
+            # ct x ct + relinearise + rescale: the fused call (product formed inside the key switch) against
+            # the oracle's tensor product followed by its relinearise + rescale, incl. a batch-broadcast operand
+            bt = 1 + it % 3
+            a = rand_poly(P, rng, 2, nq, False, batch=bt)
+            b = rand_poly(P, rng, 2, nq, False, batch=1 if it % 2 else bt)
+            want = rb.relin_rescale(rb.tensor(a, b, nq), ksk, nq)
+            got = gb.mul_relin_rescale(gb.from_numpy(a), gb.from_numpy(b), gk, nq)
+            assert np.array_equal(gb.to_numpy(got), want), f"mul_relin_rescale nq={nq}"
+            assert np.array_equal(gb.to_numpy(gb.relin_rescale(gb.tensor(gb.from_numpy(a), gb.from_numpy(b), nq), gk, nq)),
+                                  want), f"relin_rescale nq={nq}"
+            sq = gb.mul_relin_rescale(gb.from_numpy(a), gb.from_numpy(a), gk, nq)
+            assert np.array_equal(gb.to_numpy(sq), rb.relin_rescale(rb.tensor(a, a, nq), ksk, nq)), f"square nq={nq}"
 
 
 def check_engine_ops(eg, er, slot_tol=1e-5):
