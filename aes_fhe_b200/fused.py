@@ -9,7 +9,8 @@ relinearisation.  Everything is batched: the ciphertext operands may carry any b
   power once and writes all inner sums of all outputs; the level / scale alignment of every
   operand is folded into the constants, so nothing is rescaled on its own;
 * the outer products of one output are accumulated as a 3-polynomial ciphertext
-  (``fhe_tensor_acc``) and relinearised ONCE, then rescaled twice.
+  (``fhe_tensor_acc``), relinearised ONCE together with the first rescale (one ModDown by P q_l), then
+  rescaled once more.
 
 Depth: baby basis + giant basis + 2.  For the reference's degree-255 S-box pair
 (/root/reference/sbox/sbox_service.py:116-138: 254 relinearisations, 10 levels) that is
@@ -119,8 +120,11 @@ def _outer_sum(eng, relin_key, outer: Dict[int, Ciphertext], inner_basis: Dict[i
                 acc = be.add_into_polys(acc, zero_term, nq)              # in place on polynomials 0 and 1
             else:
                 acc = be.concat([be.add(be.take_polys(acc, 2), be.expand_batch(zero_term, bt), nq, 0), be.select_poly(acc, 2)])
-        ct2 = eng._relin(Ciphertext(eng, acc, lo), relin_key)
-        outs.append(eng._rescale(eng._rescale(ct2)))
+        # relinearise and do the first of the two rescales in one ModDown by P * q_lo (as Engine.multiply does)
+        eng._count('keyswitch_relin')
+        eng._count('rescale')
+        ct2 = Ciphertext(eng, be.relin_rescale(acc, relin_key.data, nq), lo - 1)
+        outs.append(eng._rescale(ct2))
     return outs
 
 
