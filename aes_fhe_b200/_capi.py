@@ -44,7 +44,7 @@ SIGNATURES = {
     "fhe_ks_inner": [_P, _P, _P, _P, _P, _P, _I, _I],
     "fhe_moddown": [_P, _P, _P, _P, _I, _I],
     "fhe_relin_rescale": [_P, _P, _P, _P, _P, _I, _I],
-    "fhe_mul_relin_rescale": [_P, _P, _P, _P, _P, _P, _I, _I],
+    "fhe_mul_relin_rescale": [_P, _P, _P, _P, _I, _P, _I, _P, _I, _I],
     "fhe_from_i64": [_P, _P, _P, _P, _I, _I, _I],
     "fhe_crt_centered": [_P, _P, _P, _P, _I, _I],
 }

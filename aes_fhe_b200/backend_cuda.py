@@ -287,13 +287,15 @@ class CudaBackend:
         return out
 
     def mul_relin_rescale(self, a, b, ksk, nq):
-        """ct x ct + relinearise + rescale in one call: [2,B,nq,N] x [2,B,nq,N] -> [2,B,nq-1,N]; same residues
-        as tensor() followed by relin_rescale(), without the 3-polynomial product in memory."""
+        """ct x ct + relinearise + rescale in one call: [2,B,>=nq,N] x [2,B,>=nq,N] -> [2,B,nq-1,N]; same residues
+        as tensor() followed by relin_rescale(), without the 3-polynomial product in memory.  An operand with
+        more than nq limbs (a higher level) is read in place, limbs 0..nq-1."""
         bt = max(a.shape[1], b.shape[1])
-        a = self.expand_batch(a, bt)[:, :, :nq].contiguous()
-        b = self.expand_batch(b, bt)[:, :, :nq].contiguous()
+        a = self.expand_batch(a, bt).contiguous()
+        b = self.expand_batch(b, bt).contiguous()
         out = self._empty(2, bt, nq - 1, self.n)
-        self._call("fhe_mul_relin_rescale", self._ptr(out), self._ptr(a), self._ptr(b), self._ptr(ksk), nq, bt)
+        self._call("fhe_mul_relin_rescale", self._ptr(out), self._ptr(a), a.shape[2], self._ptr(b), b.shape[2],
+                   self._ptr(ksk), nq, bt)
         return out
 
     def keyswitch(self, d, ksk, nq):

@@ -294,10 +294,13 @@ void launch_bconv(fhe_ctx* c, cudaStream_t s, int ns_max, int groups, const BCon
 
 // ab: `d` / `lift` are the operand ciphertexts a / b of a fused multiply (k_ks_inner, AB)
 void launch_ks_inner(fhe_ctx* c, cudaStream_t s, int nq, int batch, u64* acc, const u64* ext, const u64* d,
-                     const u64* ksk, const u64* lift, const ConstF* lift_c, bool ab = false) {
+                     const u64* ksk, const u64* lift, const ConstF* lift_c, bool ab = false, int d_nq = 0,
+                     int lift_nq = 0) {
+    if (d_nq == 0) d_nq = nq;
+    if (lift_nq == 0) lift_nq = nq;
     const int beta = c->modup_beta[nq];
     dim3 grid(c->n / 256, nq + c->n_p), block(256);
-#define FHE_KS_ARGS grid, block, s, c->T, nq, c->alpha, beta, batch, acc, ext, d, ksk, lift, lift_c
+#define FHE_KS_ARGS grid, block, s, c->T, nq, c->alpha, beta, batch, acc, ext, d, ksk, lift, lift_c, d_nq, lift_nq
     if (ab) {
         if (beta <= 2) launch(k_ks_inner<2, 2, true>, FHE_KS_ARGS);
         else if (beta <= 4) launch(k_ks_inner<4, 2, true>, FHE_KS_ARGS);
@@ -751,8 +754,8 @@ int fhe_ks_inner(fhe_ctx* c, void* stream, uint64_t* acc, const uint64_t* ext, c
 }
 
 // d3 != null: the 3-polynomial tensor product; else (a, b): the operands of a fused multiply
-static int relin_rescale_impl(fhe_ctx* c, void* stream, uint64_t* out, const uint64_t* d3, const uint64_t* a,
-                              const uint64_t* b, const uint64_t* rlk, int nq, int batch, const char* who) {
+static int relin_rescale_impl(fhe_ctx* c, void* stream, uint64_t* out, const uint64_t* d3, const uint64_t* a, int a_nq,
+                              const uint64_t* b, int b_nq, const uint64_t* rlk, int nq, int batch, const char* who) {
     if (bad_shape(c, nq, 0) || nq < 2 || c->n_p == 0 || batch < 1 || c->modup_beta[nq] > FHE_MAX_BETA)
         return fail((std::string(who) + ": bad shape").c_str());
     cudaStream_t s = (cudaStream_t)stream;
@@ -762,18 +765,21 @@ static int relin_rescale_impl(fhe_ctx* c, void* stream, uint64_t* out, const uin
     if (!base) return fail((std::string(who) + ": scratch allocation failed").c_str());
     u64* ext = base + (size_t)batch * nq * n;
     u64* acc = ext + (size_t)batch * beta * ne * n;
-    const size_t poly = (size_t)batch * nq * n;
     int rc;
     if (d3) {
-        const u64* d2 = (const u64*)d3 + 2 * poly;
+        const u64* d2 = (const u64*)d3 + 2 * (size_t)batch * nq * n;
         if ((rc = fhe_modup(c, stream, (uint64_t*)ext, (const uint64_t*)d2, nq, batch))) return rc;
         // inner product with the key, plus P * (d0, d1) on the q-limbs
         launch_ks_inner(c, s, nq, batch, acc, (const u64*)ext, d2, (const u64*)rlk, (const u64*)d3, c->p_mod_q);
     } else {
-        LoadMul ld; ld.a = (const u64*)a + poly; ld.b = (const u64*)b + poly; ld.poly_stride = (long long)nq * n;
+        if (a_nq < nq || a_nq > c->n_q || b_nq < nq || b_nq > c->n_q)
+            return fail((std::string(who) + ": operand has fewer limbs than the product").c_str());
+        LoadMul ld;
+        ld.a = (const u64*)a + (size_t)batch * a_nq * n; ld.a_stride = (long long)a_nq * n;
+        ld.b = (const u64*)b + (size_t)batch * b_nq * n; ld.b_stride = (long long)b_nq * n;
         if ((rc = modup_from(c, s, ext, ld, nq, batch))) return rc;
         launch_ks_inner(c, s, nq, batch, acc, (const u64*)ext, (const u64*)a, (const u64*)rlk, (const u64*)b, c->p_mod_q,
-                        true);
+                        true, a_nq, b_nq);
     }
     const int npoly = 2 * batch;
     u64* accs = acc + (size_t)no * n;                       // rows q_{nq-1}, p_0 .. p_{K-1} are contiguous
@@ -797,13 +803,13 @@ static int relin_rescale_impl(fhe_ctx* c, void* stream, uint64_t* out, const uin
 int fhe_relin_rescale(fhe_ctx* c, void* stream, uint64_t* out, const uint64_t* d3, const uint64_t* rlk, int nq,
                       int batch) {
     if (!d3) return fail("fhe_relin_rescale: null operand");
-    return relin_rescale_impl(c, stream, out, d3, nullptr, nullptr, rlk, nq, batch, "fhe_relin_rescale");
+    return relin_rescale_impl(c, stream, out, d3, nullptr, 0, nullptr, 0, rlk, nq, batch, "fhe_relin_rescale");
 }
 
-int fhe_mul_relin_rescale(fhe_ctx* c, void* stream, uint64_t* out, const uint64_t* a, const uint64_t* b,
-                          const uint64_t* rlk, int nq, int batch) {
+int fhe_mul_relin_rescale(fhe_ctx* c, void* stream, uint64_t* out, const uint64_t* a, int a_nq, const uint64_t* b,
+                          int b_nq, const uint64_t* rlk, int nq, int batch) {
     if (!a || !b) return fail("fhe_mul_relin_rescale: null operand");
-    return relin_rescale_impl(c, stream, out, nullptr, a, b, rlk, nq, batch, "fhe_mul_relin_rescale");
+    return relin_rescale_impl(c, stream, out, nullptr, a, a_nq, b, b_nq, rlk, nq, batch, "fhe_mul_relin_rescale");
 }
 
 int fhe_moddown(fhe_ctx* c, void* stream, uint64_t* out, uint64_t* acc, int nq, int npoly) {

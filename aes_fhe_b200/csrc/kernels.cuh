@@ -432,7 +432,8 @@ FHE_D void st2(u64* p, u64 a, u64 b) {
 template <int BMAX, int UNR, bool AB>
 __global__ void __launch_bounds__(256, (BMAX <= 4 ? 3 : 2)) k_ks_inner(DevTables T, int nq, int alpha, int beta, int batch,
                                                   u64* acc, const u64* ext, const u64* d, const u64* ksk,
-                                                  const u64* lift, const ConstF* lift_c) {
+                                                  const u64* lift, const ConstF* lift_c, int d_nq, int lift_nq) {
+    // d_nq / lift_nq: limbs per batch element of `d` / `lift` (>= nq; only the AB operands may carry more)
     const int t = blockIdx.y;
     const int ne = nq + T.n_p;
     const int id = t < nq ? t : T.n_q + (t - nq);
@@ -451,7 +452,8 @@ __global__ void __launch_bounds__(256, (BMAX <= 4 ? 3 : 2)) k_ks_inner(DevTables
     }
     const int own = t < nq ? t / alpha : -1;
     const bool has_lift = lift != nullptr && t < nq;
-    const size_t ps = (size_t)batch * nq << log_n;
+    const size_t ps = (size_t)batch * lift_nq << log_n;          // polynomial strides of lift / d
+    const size_t pd = (size_t)batch * d_nq << log_n;
     ConstF pc; pc.w = 0; pc.wq = 0;
     if (has_lift) pc = lift_c[t];
     const u64* dp = d + ((size_t)t << log_n) + idx;                 // + b * nq * N
@@ -472,15 +474,15 @@ __global__ void __launch_bounds__(256, (BMAX <= 4 ? 3 : 2)) k_ks_inner(DevTables
                 for (int j = 0; j < BMAX; ++j)
                     if (j < beta) {
                         if (AB) { if (j != own) E[u][j] = ld_u64(ep + ((((size_t)b * beta + j) * ne) << log_n)); }
-                        else E[u][j] = ld_u64(j == own ? dp + (((size_t)b * nq) << log_n)
+                        else E[u][j] = ld_u64(j == own ? dp + (((size_t)b * d_nq) << log_n)
                                                        : ep + ((((size_t)b * beta + j) * ne) << log_n));
                     }
                 if (has_lift) {
-                    L0[u] = ld_u64(lp + (((size_t)b * nq) << log_n));
-                    L1[u] = ld_u64(lp + ps + (((size_t)b * nq) << log_n));
+                    L0[u] = ld_u64(lp + (((size_t)b * lift_nq) << log_n));
+                    L1[u] = ld_u64(lp + ps + (((size_t)b * lift_nq) << log_n));
                     if (AB) {
-                        M0[u] = ld_u64(bp + (((size_t)b * nq) << log_n));
-                        M1[u] = ld_u64(bp + ps + (((size_t)b * nq) << log_n));
+                        M0[u] = ld_u64(bp + (((size_t)b * d_nq) << log_n));
+                        M1[u] = ld_u64(bp + pd + (((size_t)b * d_nq) << log_n));
                     }
                 }
             }
@@ -545,14 +547,16 @@ struct LoadCentered {
 };
 // fused multiply + relinearise: the key switch transforms d2 = a1 * b1 without d2 ever being written
 struct LoadMul {
-    const u64* a; const u64* b; long long poly_stride;      // polynomial 1 of each operand, rows [batch][nq]
+    const u64* a; const u64* b;                 // polynomial 1 of each operand, rows [batch][>= nq]
+    long long a_stride, b_stride;               // words per batch element (an operand may carry more limbs than nq)
     FHE_D double operator()(const RowMap& map, RowRef row, int idx, int, const Modulus& M) const {
-        const size_t o = row_off(map, row, poly_stride) + idx;
-        return canon(mulmod_var(u64_to_f(a[o]), u64_to_f(b[o]), M.qd, M.qinv), M.qd);
+        return canon(mulmod_var(u64_to_f(a[row_off(map, row, a_stride) + idx]), u64_to_f(b[row_off(map, row, b_stride) + idx]),
+                                M.qd, M.qinv), M.qd);
     }
     FHE_D void prefetch(const RowMap& map, RowRef row, int idx, int count) const {
-        const size_t o = row_off(map, row, poly_stride) + idx;
-        for (int k = 0; k < count; k += 16) { prefetch_l2(a + o + k); prefetch_l2(b + o + k); }
+        const u64* pa = a + row_off(map, row, a_stride) + idx;
+        const u64* pb = b + row_off(map, row, b_stride) + idx;
+        for (int k = 0; k < count; k += 16) { prefetch_l2(pa + k); prefetch_l2(pb + k); }
     }
 };
 // rescale / ModDown epilogue: out = (in - ntt_value) * c[j]

@@ -644,6 +644,34 @@ class Engine:
         d = self.backend.tensor(a.polys, b.polys, nq)
         return self._rescale(Ciphertext(self, d, a.level))
 
+    def _mul_ct_dropped(self, a: Ciphertext, b: Ciphertext, rlk: RelinearizationKey):
+        """a x b + relinearise + rescale where an operand of a higher level is used at the lower level by
+        ignoring its upper limbs -- an exact modulus switch (same message, same scale, no noise, no key
+        switch, no transform) -- instead of ``level_down`` (constant multiply + rescale: 2 n limb transforms).
+        The product then is off the scale table: returns ``(ct, dev)`` with the true scale of ``ct`` equal
+        to ``delta[ct.level] * dev``.  Only the LUT schedules (aes_fhe_b200/fused.py) use this: they fold
+        ``dev`` into their constants, so no ciphertext with an off-table scale leaves them."""
+        if a.npoly != 2 or b.npoly != 2:
+            raise RuntimeError("multiply: operands must have 2 polynomials (relinearize first)")
+        P, be = self.params, self.backend
+        lvl = min(a.level, b.level)
+        if lvl == 0:
+            raise RuntimeError("multiply: no multiplicative depth left")
+        if a.zero or b.zero:
+            return self._zero(lvl - 1, 2, max(a.batch, b.batch)), Fraction(1)
+        dev = (P.delta[a.level] / P.delta[lvl]) * (P.delta[b.level] / P.delta[lvl])
+        nq = lvl + 1
+        self._count('mul_ct')
+        self._count('keyswitch_relin')
+        self._count('rescale')
+        if hasattr(be, "mul_relin_rescale"):
+            out = be.mul_relin_rescale(a.polys, b.polys, rlk.data, nq)
+        else:
+            ap = a.polys if a.level == lvl else be.take_limbs(a.polys, nq, False)
+            bp = b.polys if b.level == lvl else be.take_limbs(b.polys, nq, False)
+            out = be.relin_rescale(be.tensor(ap, bp, nq), rlk.data, nq)
+        return Ciphertext(self, out, lvl - 1), dev
+
     def square(self, a: Ciphertext, relin_key=None) -> Ciphertext:
         return self._mul_ct(a, a, relin_key)
 

@@ -32,12 +32,21 @@ from .engine import Ciphertext
 _EPS = 1e-13
 
 
-def power_basis_16(eng_wrap, ct, wanted: Optional[Sequence[int]] = None) -> Dict[int, Ciphertext]:
+def _lim(x: Fraction) -> Fraction:
+    return x.limit_denominator(1 << 600)
+
+
+def power_basis_16(eng_wrap, ct, wanted: Optional[Sequence[int]] = None, with_dev: bool = False):
     """{k: ct^k} of a unit-modulus (zeta_16) ciphertext for the exponents in `wanted` (default: all
     of 1..15), with t^(16-k) = conj(t^k) as /root/reference/xor_service.py:245-254.  Only the powers
     that are wanted, or needed to build a wanted one (t^k = t^ceil(k/2) * t^floor(k/2), depth 3), are
     computed: the XOR polynomial has odd exponents only, which takes 5 products and 4 conjugations
-    instead of 7 and 7."""
+    instead of 7 and 7.
+
+    ``with_dev``: products of operands at different levels use the higher one in place (upper limbs
+    ignored, Engine._mul_ct_dropped) instead of bringing it down with a constant multiply + rescale;
+    returns ``(basis, dev)`` where ``dev[k]`` is the factor by which the scale of ``basis[k]`` exceeds
+    the table scale of its level (the LUT constants absorb it)."""
     eng, rlk = eng_wrap.engine, eng_wrap.relin_key
     wanted = sorted(set(range(1, 16) if wanted is None else wanted))
     low = sorted({k if k <= 8 else 16 - k for k in wanted})          # positive powers 1..8 behind them
@@ -52,12 +61,33 @@ def power_basis_16(eng_wrap, ct, wanted: Optional[Sequence[int]] = None) -> Dict
     for k in low:
         req(k)
     pw: Dict[int, Ciphertext] = {1: ct}
+    dv: Dict[int, Fraction] = {1: Fraction(1)}
     for k in sorted(need):
-        pw[k] = eng.multiply(pw[(k + 1) // 2], pw[k // 2], rlk)
-    basis = {}
+        hi, lo = (k + 1) // 2, k // 2
+        if with_dev:
+            pw[k], d = eng._mul_ct_dropped(pw[hi], pw[lo], rlk)
+            dv[k] = _lim(d * dv[hi] * dv[lo])
+        else:
+            pw[k] = eng.multiply(pw[hi], pw[lo], rlk)
+            dv[k] = Fraction(1)
+    basis, dev = {}, {}
     for k in wanted:
         basis[k] = pw[k] if k <= 8 else eng_wrap.conjugate(pw[16 - k])
-    return basis
+        dev[k] = dv[k] if k <= 8 else dv[16 - k]
+    return (basis, dev) if with_dev else basis
+
+
+def lazy_power_basis(eng, rlk, ct, degree: int, dev0: Fraction = Fraction(1)):
+    """[ct^1 .. ct^degree] with the recursion of Engine.make_power_basis (ct^k = ct^ceil(k/2) ct^floor(k/2)),
+    mixed-level products done with Engine._mul_ct_dropped.  Returns (powers, devs)."""
+    pw: List[Optional[Ciphertext]] = [None] * (degree + 1)
+    dv: List[Fraction] = [Fraction(1)] * (degree + 1)
+    pw[1], dv[1] = ct, dev0
+    for k in range(2, degree + 1):
+        hi, lo = (k + 1) // 2, k // 2
+        pw[k], d = eng._mul_ct_dropped(pw[hi], pw[lo], rlk)
+        dv[k] = _lim(d * dv[hi] * dv[lo])
+    return pw[1:], dv[1:]
 
 
 def _const_pair(eng, value: complex, scale: Fraction, nq: int):
@@ -67,11 +97,14 @@ def _const_pair(eng, value: complex, scale: Fraction, nq: int):
 
 
 def _outer_sum(eng, relin_key, outer: Dict[int, Ciphertext], inner_basis: Dict[int, Ciphertext],
-               coeff_mats: Sequence[np.ndarray], cache_key) -> List[Ciphertext]:
+               coeff_mats: Sequence[np.ndarray], cache_key, outer_dev: Optional[Dict[int, Fraction]] = None,
+               inner_dev: Optional[Dict[int, Fraction]] = None) -> List[Ciphertext]:
     """sum_i outer[i] * (sum_j C[i][j] inner_basis[j]),  i = 0 meaning the constant 1 (same for
     j = 0).  ``coeff_mats`` is a list of (n_outer+1) x (n_inner+1) complex matrices; all outputs
     share the two bases.  Returns one ciphertext per matrix, two levels below the lowest
-    operand."""
+    operand.  ``outer_dev`` / ``inner_dev``: scale deviations of the basis elements (power_basis_16,
+    lazy_power_basis); the constants of the inner sums are divided by them, so the outputs sit exactly on the
+    scale table."""
     be, P = eng.backend, eng.params
     lo = min([c.level for c in outer.values()] + [c.level for c in inner_basis.values()])
     if lo < 2:
@@ -81,18 +114,22 @@ def _outer_sum(eng, relin_key, outer: Dict[int, Ciphertext], inner_basis: Dict[i
     n_out = len(coeff_mats)
     i_list = sorted(outer)                       # outer powers actually present
     j_list = sorted(inner_basis)
+    odev = {i: Fraction(1) for i in i_list} if outer_dev is None else outer_dev
+    idev = {j: Fraction(1) for j in j_list} if inner_dev is None else inner_dev
     rows = [(m, i) for m in range(n_out) for i in [0] + i_list
             if np.any(np.abs(np.asarray(coeff_mats[m])[i]) > _EPS)]
 
     cache = eng.__dict__.setdefault("_lut_cache", {})
-    key = (cache_key, lo, tuple(outer[i].level for i in i_list), tuple(inner_basis[j].level for j in j_list))
+    key = (cache_key, lo, tuple(outer[i].level for i in i_list), tuple(inner_basis[j].level for j in j_list),
+           tuple(odev[i] for i in i_list), tuple(idev[j] for j in j_list))
     prep = cache.get(key)
     if prep is None:
         const_res, c0_res = [], []
         for (m, i) in rows:
             C = np.asarray(coeff_mats[m], dtype=np.complex128)
-            s_in = target if i == 0 else target / P.delta[outer[i].level]
-            const_res.append([_const_pair(eng, C[i, j], s_in / P.delta[inner_basis[j].level], nq) for j in j_list])
+            s_in = target if i == 0 else target / (P.delta[outer[i].level] * odev[i])
+            const_res.append([_const_pair(eng, C[i, j], s_in / (P.delta[inner_basis[j].level] * idev[j]), nq)
+                              for j in j_list])
             c0_res.append(_const_pair(eng, C[i, 0], s_in, nq))
         prep = be.prepare_lincomb(const_res, c0_res, nq)
         cache[key] = prep
@@ -142,8 +179,8 @@ def bivariate_lut(eng_wrap, ct_x, ct_y, coeff_mats: Sequence[np.ndarray],
         # and conj(g_i)(y) = sum_j conj(c_ij) y^((16-j) % 16) is again a constant-only sum over the
         # y basis.  Two outer sums and ONE conjugation per output replace the conjugations of the
         # x basis (XOR: 17 key switches instead of 19).
-        by = power_basis_16(eng_wrap, ct_y, sorted(set(used_j) | {(16 - j) % 16 for j in used_j if j}))
-        bx = power_basis_16(eng_wrap, ct_x, sorted({i if i <= 8 else 16 - i for i in used_i}))
+        by, dy = power_basis_16(eng_wrap, ct_y, sorted(set(used_j) | {(16 - j) % 16 for j in used_j if j}), with_dev=True)
+        bx, dx = power_basis_16(eng_wrap, ct_x, sorted({i if i <= 8 else 16 - i for i in used_i}), with_dev=True)
         mats = []
         for C in coeff_mats:
             C = np.asarray(C, dtype=np.complex128)
@@ -154,15 +191,16 @@ def bivariate_lut(eng_wrap, ct_x, ct_y, coeff_mats: Sequence[np.ndarray],
                     B[16 - i, (16 - j) % 16] = np.conj(C[i, j])
             mats += [A, B]
         outs = _outer_sum(eng, eng_wrap.relin_key, {i: bx[i] for i in sorted(bx)}, {j: by[j] for j in sorted(by)},
-                          mats, (cache_key, "conj-split", len(coeff_mats)))
+                          mats, (cache_key, "conj-split", len(coeff_mats)), dx, dy)
         return [eng.add(outs[2 * m], eng_wrap.conjugate(outs[2 * m + 1])) for m in range(len(coeff_mats))]
+    dx = dy = None
     if bx is None:
-        bx = power_basis_16(eng_wrap, ct_x, used_i)
+        bx, dx = power_basis_16(eng_wrap, ct_x, used_i, with_dev=True)
     if by is None:
-        by = power_basis_16(eng_wrap, ct_y, used_j)
+        by, dy = power_basis_16(eng_wrap, ct_y, used_j, with_dev=True)
     outer = {i: bx[i] for i in used_i}
     inner = {j: by[j] for j in used_j}
-    return _outer_sum(eng, eng_wrap.relin_key, outer, inner, coeff_mats, (cache_key, len(coeff_mats)))
+    return _outer_sum(eng, eng_wrap.relin_key, outer, inner, coeff_mats, (cache_key, len(coeff_mats)), dx, dy)
 
 
 def poly_eval_bsgs(engine, relin_key, ct, coeff_vecs: Sequence[np.ndarray], baby: int = 16,
@@ -171,12 +209,15 @@ def poly_eval_bsgs(engine, relin_key, ct, coeff_vecs: Sequence[np.ndarray], baby
     ciphertext, sharing the baby basis t^1..t^baby and the giant basis (t^baby)^1..(baby-1)."""
     deg = max(len(c) for c in coeff_vecs) - 1
     n_giant = deg // baby                                     # highest giant power needed
-    pw = engine.make_power_basis(ct, baby, relin_key)         # t^1 .. t^baby
+    pw, dv = lazy_power_basis(engine, relin_key, ct, baby)    # t^1 .. t^baby (+ scale deviations)
     babies = {j: pw[j - 1] for j in range(1, baby)}
+    bdev = {j: dv[j - 1] for j in range(1, baby)}
     giants: Dict[int, Ciphertext] = {}
+    gdev: Dict[int, Fraction] = {}
     if n_giant >= 1:
-        gp = engine.make_power_basis(pw[baby - 1], n_giant, relin_key)
+        gp, gd = lazy_power_basis(engine, relin_key, pw[baby - 1], n_giant, dv[baby - 1])
         giants = {m: gp[m - 1] for m in range(1, n_giant + 1)}
+        gdev = {m: gd[m - 1] for m in range(1, n_giant + 1)}
     mats = []
     for c in coeff_vecs:
         c = np.asarray(c, dtype=np.complex128)
@@ -184,4 +225,4 @@ def poly_eval_bsgs(engine, relin_key, ct, coeff_vecs: Sequence[np.ndarray], baby
         for k, v in enumerate(c):
             M[k // baby, k % baby] = v
         mats.append(M)
-    return _outer_sum(engine, relin_key, giants, babies, mats, (cache_key, len(mats), baby))
+    return _outer_sum(engine, relin_key, giants, babies, mats, (cache_key, len(mats), baby), gdev, bdev)

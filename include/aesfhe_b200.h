@@ -146,12 +146,13 @@ int fhe_relin_rescale(fhe_ctx* ctx, void* stream, uint64_t* out, const uint64_t*
                       int nq, int batch);
 
 /* Engine.multiply(ct, ct, rlk) in one call (xor_service.py:71, and every product of make_power_basis,
- * xor_service.py:86 / sbox/sbox_service.py:93): a, b [2][batch][nq][N] -> out[2][batch][nq-1][N], the same
- * residues as fhe_tensor followed by fhe_relin_rescale.  The 3-polynomial product is never stored: the
- * key switch's first inverse NTT forms d2 = a1 b1 on load and the key inner product forms
- * P (a0 b0, a0 b1 + a1 b0) from the operands. */
-int fhe_mul_relin_rescale(fhe_ctx* ctx, void* stream, uint64_t* out, const uint64_t* a, const uint64_t* b,
-                          const uint64_t* rlk, int nq, int batch);
+ * xor_service.py:86 / sbox/sbox_service.py:93): a[2][batch][a_nq][N], b[2][batch][b_nq][N] with
+ * a_nq, b_nq >= nq (only limbs 0..nq-1 are used: an operand of a higher level is used as it lies)
+ * -> out[2][batch][nq-1][N], the same residues as fhe_tensor followed by fhe_relin_rescale.  The
+ * 3-polynomial product is never stored: the key switch's first inverse NTT forms d2 = a1 b1 on load
+ * and the key inner product forms P (a0 b0, a0 b1 + a1 b0) from the operands. */
+int fhe_mul_relin_rescale(fhe_ctx* ctx, void* stream, uint64_t* out, const uint64_t* a, int a_nq,
+                          const uint64_t* b, int b_nq, const uint64_t* rlk, int nq, int batch);
 
 /* Engine.encode / encrypt residue step (xor_service.py:59-66): signed 64-bit coefficients
  * coeffs[batch][N] (device) -> coefficient-domain residues out[batch][nq + np][N]. */

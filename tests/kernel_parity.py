@@ -82,6 +82,14 @@ def check_keyswitch(P, gb, rb, levels=None, seed=3):
             assert np.array_equal(gb.to_numpy(got), want), f"mul_relin_rescale nq={nq}"
             assert np.array_equal(gb.to_numpy(gb.relin_rescale(gb.tensor(gb.from_numpy(a), gb.from_numpy(b), nq), gk, nq)),
                                   want), f"relin_rescale nq={nq}"
+            if nq < P.n_q:
+                # an operand that still carries the limbs of a higher level is used in place
+                extra = min(2, P.n_q - nq)
+                a_hi = np.concatenate([a, rand_poly(P, rng, 2, nq + extra, False, batch=bt)[:, :, nq:]], axis=2)
+                got = gb.mul_relin_rescale(gb.from_numpy(np.ascontiguousarray(a_hi)), gb.from_numpy(b), gk, nq)
+                assert np.array_equal(gb.to_numpy(got), want), f"mul_relin_rescale with a higher-level operand nq={nq}"
+                got = gb.mul_relin_rescale(gb.from_numpy(b), gb.from_numpy(np.ascontiguousarray(a_hi)), gk, nq)
+                assert np.array_equal(gb.to_numpy(got), rb.relin_rescale(rb.tensor(b, a, nq), ksk, nq)), f"... as b, nq={nq}"
             sq = gb.mul_relin_rescale(gb.from_numpy(a), gb.from_numpy(a), gk, nq)
             assert np.array_equal(gb.to_numpy(sq), rb.relin_rescale(rb.tensor(a, a, nq), ksk, nq)), f"square nq={nq}"
 
