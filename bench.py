@@ -244,6 +244,7 @@ def main():
     config = {"workload": "configs[1]: SubBytes (sbox_hi x sbox_lo degree-255 zeta_256 LUT polynomials, BSGS schedule) on "
                           "2048-block ciphertexts, N=2^16, max_level=22",
               "batch_ciphertexts_per_gpu": args.batch, "blocks_per_ciphertext": (1 << (LOG_N - 1)) // 16,
+              "keyswitch_digits": _params().dnum, "special_primes": _params().n_p,
               "l2": "working set per step (GBs of power-basis ciphertexts) exceeds the 126 MB L2",
               "sharding": "independent ciphertext batches per rank, no data-path collective"}
 
@@ -390,7 +391,8 @@ def main():
                              "achieved": achieved, "peak": peak, "peak_kind": peak_kind, "unit": "GB/s",
                              "frac": achieved / peak, "traffic": traffic,
                              "note": "FP64-pipe bound: 8 FP64 ops per butterfly, pipe at 70 % (profiles/r01_ncu_chained.md); "
-                                     "traffic = ncu dram bytes of the launch"},
+                                     "traffic = ncu dram bytes of the launch; the NTT launches are 47 % of the step "
+                                     "(profiles/r01_kernel_breakdown_final.md)"},
                 "ms_per_ciphertext": ms / args.batch,
                 "keyswitches_per_ciphertext": 23}
         if not args.no_full_round and world == 1:
