@@ -574,4 +574,11 @@ struct StoreSubMul {
     FHE_D void warm(const RowMap& map, RowRef row, int idx) const {
         prefetch_l2(in + (size_t)row.blk * in_poly_stride + ((size_t)row.j << map.log_n) + idx);
     }
+    FHE_D double fetch(const RowMap& map, RowRef row, int idx) const {
+        return u64_to_f(ld_u64(in + (size_t)row.blk * in_poly_stride + ((size_t)row.j << map.log_n) + idx));
+    }
+    FHE_D void put(const RowMap& map, RowRef row, int idx, double v, int, const Modulus& M, double x) const {
+        out[(size_t)row.blk * out_poly_stride + ((size_t)row.j << map.log_n) + idx] =
+            f_to_u64(canon(mulmod_const(d_add(x, -v), c[row.j], M.qd), M.qd));
+    }
 };

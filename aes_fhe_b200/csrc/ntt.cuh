@@ -199,6 +199,13 @@ struct StorePlain {
     // a StoreOp may read other operands in its epilogue: warm(idx) is called once per thread at the
     // start of the last pass with the first of 16 consecutive elements the thread's row will need
     FHE_D void warm(const RowMap&, RowRef, int) const {}
+    // ... and fetch(idx) returns that operand ahead of the store loop (all 16 loads of a thread in flight at
+    // once; inside operator() each load would have to wait for the previous store, the compiler cannot prove
+    // that `out` and `in` do not alias); put() is operator() with the fetched value
+    FHE_D double fetch(const RowMap&, RowRef, int) const { return 0.0; }
+    FHE_D void put(const RowMap& map, RowRef row, int idx, double v, int mid, const Modulus& M, double) const {
+        (*this)(map, row, idx, v, mid, M);
+    }
 };
 struct LoadRaw {            // lazy doubles written by the other pass
     const u64* src; long long poly_stride;
@@ -357,7 +364,11 @@ FHE_D void fwd_pass_b_body(const DevTables& T, const RowMap& map, RowRef rref, i
     sts16(smC, x);
     ntt_sync_warp();
 #pragma unroll
-    for (int i = 0; i < 16; ++i) st(map, rref, rbase + 16 * i, smS[18 * i], mid, M);
+    double ep[16];                                            // epilogue operands (zeros for a plain store)
+#pragma unroll
+    for (int i = 0; i < 16; ++i) ep[i] = st.fetch(map, rref, rbase + 16 * i);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) st.put(map, rref, rbase + 16 * i, smS[18 * i], mid, M, ep[i]);
 }
 template <int LOG_N, class StoreOp>
 __global__ void __launch_bounds__(256, FHE_PASSB_MINB) ntt_fwd_pass_b(DevTables T, RowMap map, LoadRaw ld, StoreOp st) {
