@@ -163,10 +163,15 @@ struct LinCombIn {
 #define FHE_LCM_CHUNK 512
 #define FHE_LCM_STRIDE(KT) (4 * (KT) + ((KT) % 2 == 0 ? 4 : 0))
 #define FHE_LCM_SMEM(M, KT) ((size_t)3 * (((M) + 7) & ~7) * FHE_LCM_STRIDE(KT) * sizeof(double))
+#ifndef FHE_LCM_MT
+#define FHE_LCM_MT 2          // row blocks (of 8 coefficients) per B fragment load
+#define FHE_LCM_MINB 3        // measured on B200 (22 x 11 sums, batch 16): (MT, CTAs/SM) = (2,2) 3.56 ms, (1,3) 3.52,
+                              // (1,4) 3.53, (2,3) 3.33, (4,1) 4.45 -- the kernel is bound by dependent-issue latency
+#endif
 template <int KT>
-__global__ void __launch_bounds__(256, 2) k_lincomb_mma(DevTables Tb, int nq, int batch, int M, int T, LinCombIn in,
+__global__ void __launch_bounds__(256, FHE_LCM_MINB) k_lincomb_mma(DevTables Tb, int nq, int batch, int M, int T, LinCombIn in,
                                                         const ConstF* consts, const u64* c0, u64* out) {
-    constexpr int TP = 4 * KT, STRIDE = FHE_LCM_STRIDE(KT), MT = 2;
+    constexpr int TP = 4 * KT, STRIDE = FHE_LCM_STRIDE(KT), MT = FHE_LCM_MT;
     FHE_DYN_SHARED(double, s_c);
     const int row = blockIdx.y;
     const int j = row % nq, b = (row / nq) % batch, poly = row / (nq * batch);
@@ -501,7 +506,8 @@ __global__ void __launch_bounds__(256, (BMAX <= 4 ? 3 : 2)) k_ks_inner(DevTables
                     const double x0 = u64_to_f(m0[u]), x1 = u64_to_f(m1[u]), y0 = u64_to_f(l0[u]), y1 = u64_to_f(l1[u]);
                     own_v = mulmod_var(x1, y1, q, qi);                                   // d2 on this limb
                     t0 = mulmod_var(x0, y0, q, qi);                                      // d0
-                    t1 = d_add(mulmod_var(x0, y1, q, qi), mulmod_var(x1, y0, q, qi));    // d1, |.| <= 1.02 q
+                    // d1 = a0 b1 + a1 b0 = (a0 + a1)(b0 + b1) - d0 - d2: three products instead of four
+                    t1 = d_add(d_add(mulmod_var(d_add(x0, x1), d_add(y0, y1), q, qi), -t0), -own_v);   // |.| <= 1.6 q
                 }
 #pragma unroll
                 for (int j = 0; j < BMAX; ++j) {

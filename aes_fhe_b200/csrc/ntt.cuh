@@ -362,11 +362,10 @@ FHE_D void fwd_pass_b_body(const DevTables& T, const RowMap& map, RowRef rref, i
 #pragma unroll
     for (int i = 0; i < 16; ++i) x[i] = reduce_canon(x[i], q, qinv);
     sts16(smC, x);
-    ntt_sync_warp();
-#pragma unroll
     double ep[16];                                            // epilogue operands (zeros for a plain store)
 #pragma unroll
     for (int i = 0; i < 16; ++i) ep[i] = st.fetch(map, rref, rbase + 16 * i);
+    ntt_sync_warp();
 #pragma unroll
     for (int i = 0; i < 16; ++i) st.put(map, rref, rbase + 16 * i, smS[18 * i], mid, M, ep[i]);
 }
