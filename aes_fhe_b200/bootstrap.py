@@ -299,11 +299,15 @@ def _linear_transform(engine, ct: Ciphertext, entry) -> Ciphertext:
                 babies[b] = engine.rotate(ct, plan_keys[b])
             cts.append(babies[b])
             pts.append(pt)
-        inner = engine.multiply_plain_sum(cts, pts)
+        # the diagonal sums stay un-rescaled (scale delta * q_level) through the giant-step rotation and the
+        # final sum: ONE rescale per transform instead of one per giant step (a rescale is 2 (n - 1) limb
+        # transforms; the rotation one level higher costs a few per cent more, and its key-switch noise now
+        # lands on the larger scale)
+        inner = engine.multiply_plain_sum(cts, pts, rescale=False)
         if g:
             inner = engine.rotate(inner, plan_keys[g])
         out = inner if out is None else engine.add(out, inner)
-    return out
+    return engine._rescale(out)
 
 
 def bootstrap(engine, ct: Ciphertext, relin_key, conj_key, boot_key: BootstrapKey) -> Ciphertext:

@@ -569,9 +569,11 @@ class Engine:
             return self._rescale(Ciphertext(self, prod, a.level))
         return self._mul_scalar(a, b)
 
-    def multiply_plain_sum(self, cts: Sequence[Ciphertext], pts: Sequence[Plaintext]) -> Ciphertext:
+    def multiply_plain_sum(self, cts: Sequence[Ciphertext], pts: Sequence[Plaintext], rescale: bool = True) -> Ciphertext:
         """sum_i ct_i (.) pt_i with ONE rescale (the rotate-mask-add pattern of
-        /root/reference/shiftrows_service.py:41-50 without a rescale per mask)."""
+        /root/reference/shiftrows_service.py:41-50 without a rescale per mask).
+        ``rescale=False`` returns the sum before that rescale (same level, scale delta * q_level): the
+        caller rotates / adds such sums and rescales once (baby-step/giant-step linear transforms)."""
         lvl = min(c.level for c in cts)
         if lvl == 0:
             raise RuntimeError("multiply: no multiplicative depth left")
@@ -580,13 +582,13 @@ class Engine:
         if hasattr(be, "mul_plain_sum") and not _NO_FUSE and all(c.batch == cts[0].batch and c.npoly == 2 for c in cts):
             # one fused pass (fhe_mul_plain_sum): every operand read once, the sum written once
             acc = be.mul_plain_sum([self.level_down(c, lvl).polys for c in cts], [p.at_level(lvl) for p in pts], lvl + 1)
-            return self._rescale(Ciphertext(self, acc, lvl))
+            return self._rescale(Ciphertext(self, acc, lvl)) if rescale else Ciphertext(self, acc, lvl)
         acc = None
         for ct, pt in zip(cts, pts):
             ct = self.level_down(ct, lvl)
             prod = be.mul(ct.polys, pt.at_level(lvl), lvl + 1, 0)
             acc = prod if acc is None else be.add(acc, prod, lvl + 1, 0)
-        return self._rescale(Ciphertext(self, acc, lvl))
+        return self._rescale(Ciphertext(self, acc, lvl)) if rescale else Ciphertext(self, acc, lvl)
 
     def rotate_hoisted(self, ct: Ciphertext, keys: Sequence[FixedRotationKey]) -> List[Ciphertext]:
         """Several rotations of ONE ciphertext sharing a single ModUp (the base extension commutes

@@ -25,6 +25,8 @@ def main():
     ap.add_argument("--lib", default=None)
     ap.add_argument("--steps", type=int, default=2)
     ap.add_argument("--json", default=None)
+    ap.add_argument("--workload", default="sbox", choices=["sbox", "aes128"],
+                    help="sbox: the bench step (SubBytes, BASELINE configs[1]); aes128: ten rounds with refreshes (configs[4])")
     args = ap.parse_args()
     if args.lib:
         from aes_fhe_b200 import _capi
@@ -32,24 +34,43 @@ def main():
     import bench
     bench.DNUM = args.dnum
     from aes_fhe_b200.services.xor_service import ZetaEncoder
-    ctx, svc = bench._make_service(seed=1)
-    eng = ctx.engine
-    data = bench._inputs(eng.slot_count, args.batch, seed=0)
-    ct = eng.encrypt(ZetaEncoder.to_zeta(data, 256), ctx.public_key)
-    for _ in range(2):
-        svc.sub_bytes_array_bsgs(ct)
+    if args.workload == "sbox":
+        ctx, svc = bench._make_service(seed=1)
+        eng = ctx.engine
+        data = bench._inputs(eng.slot_count, args.batch, seed=0)
+        ct = eng.encrypt(ZetaEncoder.to_zeta(data, 256), ctx.public_key)
+
+        def step():
+            return svc.sub_bytes_array_bsgs(ct)
+        warm = 2
+    else:
+        import numpy as np
+        from aes_fhe_b200.services.aes128 import AES128Service
+        from aes_fhe_b200.services.xor_service import XORService, EngineWrapper, XORConfig, CoefficientCache
+        cfg = XORConfig()
+        w = EngineWrapper(cfg, _engine_kwargs=dict(seed=3), rotation_steps=[])
+        aes = AES128Service(w, XORService(w, CoefficientCache(cfg.coeffs_path)))
+        key = bytes.fromhex("2b7e151628aed2a6abf7158809cf4f3c")
+        rng = np.random.default_rng(9)
+        st = aes.encrypt_state([rng.integers(0, 256, (aes.B, 16), dtype=np.uint8) for _ in range(args.batch)])
+
+        def step():
+            return aes.encrypt_blocks(st, key)
+        warm = 1
+    for _ in range(warm):
+        step()
     torch.cuda.synchronize()
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a.record()
     for _ in range(args.steps):
-        svc.sub_bytes_array_bsgs(ct)
+        step()
     b.record()
     torch.cuda.synchronize()
     step_ms = a.elapsed_time(b) / args.steps
     from torch.profiler import profile, ProfilerActivity
     with profile(activities=[ProfilerActivity.CUDA]) as prof:
         for _ in range(args.steps):
-            svc.sub_bytes_array_bsgs(ct)
+            step()
         torch.cuda.synchronize()
     agg = defaultdict(lambda: [0, 0.0])
     for ev in prof.events():
