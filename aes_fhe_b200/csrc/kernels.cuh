@@ -335,6 +335,7 @@ struct BConvTable {
 // Every thread converts TWO coefficients (idx and idx + N/2): each constant fetched from shared
 // memory feeds two modular products, which halves the non-FP64 instructions per FP64 instruction
 // (the kernel is FP64-pipe bound and was co-limited by issue slots).   grid: (N/512, groups)
+// (forcing 4 CTAs/SM with 64 registers changes nothing: 245.8 against 248.1 us for 12-limb digits)
 template <int NS_MAX>
 __global__ void __launch_bounds__(256) k_bconv(DevTables T, const BConvTable* tables, int n_tables,
                                                u64* dst, long long dst_group_stride,
