@@ -368,6 +368,29 @@ def main():
     except Exception:
         pass
 
+    # second kernel of the key switch, timed the same way: the key inner product (HBM-bound).  Algorithmic bytes per
+    # launch: the key 2 beta (n+K) limbs once per batch + per ciphertext beta (n+K) extended rows in
+    # (own-digit rows come from the n input limbs) and 2 (n+K) accumulator rows out
+    beta, ne = P.digits_at(nq), nq + P.n_p
+    ext = torch.randint(0, 2 ** 39, (args.batch, beta, ne, P.n), dtype=torch.int64, device="cuda")
+    dd = torch.randint(0, 2 ** 39, (1, args.batch, nq, P.n), dtype=torch.int64, device="cuda")
+    acc = torch.empty(2, args.batch, ne, P.n, dtype=torch.int64, device="cuda")
+    ksk = svc.rlk.data
+    kt2 = []
+    for it in range(13):
+        flush.zero_()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); be._call("fhe_ks_inner", be._ptr(acc), be._ptr(ext), be._ptr(dd), be._ptr(ksk), nq, args.batch); b.record()
+        torch.cuda.synchronize()
+        if it >= 3:
+            kt2.append(a.elapsed_time(b))
+    ks_ms = float(np.median(kt2))
+    ks_bytes = (2 * beta * ne + args.batch * (beta * ne + 2 * ne)) * P.n * 8
+    ks_inner = {"kernel": "k_ks_inner", "bound": "hbm", "achieved": ks_bytes / (ks_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                "frac": ks_bytes / (ks_ms * 1e-3) / 1e9 / peak, "us": ks_ms * 1e3,
+                "algorithmic_bytes": int(ks_bytes)}
+    del ext, dd, acc
+
     t = torch.tensor([ms, e2e_ms], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -393,6 +416,7 @@ def main():
                              "note": "FP64-pipe bound: 8 FP64 ops per butterfly, pipe at 70 % (profiles/r01_ncu_chained.md); "
                                      "traffic = ncu dram bytes of the launch; the NTT launches are 47 % of the step "
                                      "(profiles/r01_kernel_breakdown_final.md)"},
+                "roofline_keyswitch_inner": ks_inner,
                 "ms_per_ciphertext": ms / args.batch,
                 "keyswitches_per_ciphertext": 23}
         if not args.no_full_round and world == 1:

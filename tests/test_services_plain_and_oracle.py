@@ -134,3 +134,26 @@ def test_mixrow_operation_sequence_on_plain_engine_matches_reference():
         for k, v in saved.items():
             if v is not None:
                 sys.modules[k] = v
+
+
+def test_lazy_power_basis_scale_deviation(ref_backend_cls):
+    """fused.lazy_power_basis uses the higher operand of a mixed-level product in place (upper limbs ignored)
+    and reports the factor by which each power's scale is off the table: decoded at the table scale, power k
+    must be dev[k] * t^k, and every power sits on the level Engine.make_power_basis puts it on
+    (/root/reference/xor_service.py:86: [k-1] = ct^k, ceil(log2 k) levels down)."""
+    from aes_fhe_b200.fused import lazy_power_basis
+    P = make_params(11, 8)
+    w, _ = _wrap(P, ref_backend_cls(P))
+    eng = w.engine
+    rng = np.random.default_rng(5)
+    x = rng.integers(0, 16, eng.slot_count, dtype=np.uint8)
+    t = ZetaEncoder.to_zeta(x, 16)
+    ct = w.encrypt(t)
+    pw, dev = lazy_power_basis(eng, w.relin_key, ct, 12)
+    ref = eng.make_power_basis(ct, 12, w.relin_key)
+    assert any(d != 1 for d in dev), "no mixed-level product took the in-place path"
+    for k in range(1, 13):
+        assert pw[k - 1].level == ref[k - 1].level
+        got = np.asarray(w.decrypt(pw[k - 1])) / float(dev[k - 1])
+        assert np.max(np.abs(got - t ** k)) < 1e-5, k
+        assert abs(float(dev[k - 1]) - 1.0) < 1e-3          # scales stay within the drift of the prime chain
