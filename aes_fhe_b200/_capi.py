@@ -45,6 +45,8 @@ SIGNATURES = {
     "fhe_moddown": [_P, _P, _P, _P, _I, _I],
     "fhe_relin_rescale": [_P, _P, _P, _P, _P, _I, _I],
     "fhe_mul_relin_rescale": [_P, _P, _P, _P, _I, _P, _I, _P, _I, _I],
+    "fhe_ks_accum": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I],
+    "fhe_moddown_rescale": [_P, _P, _P, _P, _I, _I],
     "fhe_from_i64": [_P, _P, _P, _P, _I, _I, _I],
     "fhe_crt_centered": [_P, _P, _P, _P, _I, _I],
 }

@@ -298,6 +298,27 @@ class CudaBackend:
                    self._ptr(ksk), nq, bt)
         return out
 
+    def ks_accum(self, acc, d, ksk, lift, nq):
+        """acc [2,B,nq+K,N] (or None) += <ModUp(d), ksk> + P * lift in the extended basis (no ModDown).
+        d [1,B,nq,N] or None (lift only); lift [1 or 2,B,nq,N] or None.  Returns acc (updated in place)."""
+        src = d if d is not None else lift
+        bt = src.shape[1]
+        fresh = acc is None
+        if fresh:
+            acc = self._empty(2, bt, nq + self._K, self.n)
+        d = d.contiguous() if d is not None else None
+        lift = lift.contiguous() if lift is not None else None
+        self._call("fhe_ks_accum", self._ptr(acc), self._ptr(d) if d is not None else None,
+                   self._ptr(ksk) if d is not None else None, self._ptr(lift) if lift is not None else None,
+                   lift.shape[0] if lift is not None else 0, nq, bt, 0 if fresh else 1)
+        return acc
+
+    def moddown_rescale(self, acc, nq):
+        """extended accumulator [2,B,nq+K,N] (a temporary: used as scratch) -> [2,B,nq-1,N] = round(acc / (P q_{nq-1}))"""
+        out = self._empty(acc.shape[0], acc.shape[1], nq - 1, self.n)
+        self._call("fhe_moddown_rescale", self._ptr(out), self._ptr(acc), nq, acc.shape[0] * acc.shape[1])
+        return out
+
     def keyswitch(self, d, ksk, nq):
         d = d.contiguous()
         bt = d.shape[1]

@@ -291,7 +291,9 @@ def _linear_transform(engine, ct: Ciphertext, entry) -> Ciphertext:
     need = sorted({b for items in entry["giants"].values() for b, _ in items if b})
     for b, r in zip(need, engine.rotate_hoisted(ct, [plan_keys[b] for b in need])):      # one ModUp for all baby steps
         babies[b] = r
-    out = None
+    be = engine.backend
+    shared = hasattr(be, "ks_accum")          # giant-step key switches accumulate in the extended basis: ONE ModDown
+    out, acc, lvl = None, None, None
     for g, items in entry["giants"].items():
         cts, pts = [], []
         for b, pt in items:
@@ -304,9 +306,26 @@ def _linear_transform(engine, ct: Ciphertext, entry) -> Ciphertext:
         # transforms; the rotation one level higher costs a few per cent more, and its key-switch noise now
         # lands on the larger scale)
         inner = engine.multiply_plain_sum(cts, pts, rescale=False)
+        if shared:
+            # ... and the giant rotations share their ModDown: rot_g(x) = ModDown(<ModUp(sigma x1), key_g> + P sigma x0),
+            # ModDown is linear up to rounding, so the extended accumulators are summed (inside the inner-product
+            # kernel) and divided by P q_level once -- G - 1 ModDowns and the separate rescale disappear
+            lvl = inner.level
+            nq = lvl + 1
+            if g:
+                key = plan_keys[g]
+                rot = be.automorphism(inner.polys, key.galois, nq, 0)
+                acc = be.ks_accum(acc, be.select_poly(rot, 1), key.data, be.select_poly(rot, 0), nq)
+                engine._count('keyswitch_galois')
+            else:
+                acc = be.ks_accum(acc, None, None, inner.polys, nq)
+            continue
         if g:
             inner = engine.rotate(inner, plan_keys[g])
         out = inner if out is None else engine.add(out, inner)
+    if shared:
+        engine._count('rescale')
+        return Ciphertext(engine, be.moddown_rescale(acc, lvl + 1), lvl - 1)
     return engine._rescale(out)
 
 

@@ -293,14 +293,16 @@ void launch_bconv(fhe_ctx* c, cudaStream_t s, int ns_max, int groups, const BCon
 }
 
 // ab: `d` / `lift` are the operand ciphertexts a / b of a fused multiply (k_ks_inner, AB)
+// lift_polys / accum / lift_only: see k_ks_inner (lift_only launches it with beta = 0)
 void launch_ks_inner(fhe_ctx* c, cudaStream_t s, int nq, int batch, u64* acc, const u64* ext, const u64* d,
                      const u64* ksk, const u64* lift, const ConstF* lift_c, bool ab = false, int d_nq = 0,
-                     int lift_nq = 0) {
+                     int lift_nq = 0, int lift_polys = 2, int accum = 0, bool lift_only = false) {
     if (d_nq == 0) d_nq = nq;
     if (lift_nq == 0) lift_nq = nq;
-    const int beta = c->modup_beta[nq];
+    const int beta = lift_only ? 0 : c->modup_beta[nq];
     dim3 grid(c->n / 256, nq + c->n_p), block(256);
-#define FHE_KS_ARGS grid, block, s, c->T, nq, c->alpha, beta, batch, acc, ext, d, ksk, lift, lift_c, d_nq, lift_nq
+#define FHE_KS_ARGS grid, block, s, c->T, nq, c->alpha, beta, batch, acc, ext, d, ksk, lift, lift_c, d_nq, lift_nq, \
+                    lift_polys, accum
     if (ab) {
         if (beta <= 2) launch(k_ks_inner<2, 2, true>, FHE_KS_ARGS);
         else if (beta <= 4) launch(k_ks_inner<4, 2, true>, FHE_KS_ARGS);
@@ -753,6 +755,27 @@ int fhe_ks_inner(fhe_ctx* c, void* stream, uint64_t* acc, const uint64_t* ext, c
     return check("fhe_ks_inner");
 }
 
+// ModDown by P * q_{nq-1} of an extended accumulator acc[npoly][nq + K][N] (used as scratch) -> out[npoly][nq-1][N]
+static int moddown_rescale_tail(fhe_ctx* c, cudaStream_t s, u64* out, u64* acc, int nq, int npoly, const char* who) {
+    const int n = c->n, K = c->n_p, ne = nq + K, no = nq - 1;
+    u64* accs = acc + (size_t)no * n;                       // rows q_{nq-1}, p_0 .. p_{K-1} are contiguous
+    {
+        RowMap m = make_map(c, K + 1, no, nq);
+        LoadPlain ld; ld.src = accs; ld.poly_stride = (long long)ne * n;
+        StorePlain st; st.dst = accs; st.poly_stride = (long long)ne * n;
+        ntt_inv(c, m, npoly * (K + 1), ld, accs, (long long)ne * n, st, c->mdrs_scale[nq], s);
+    }
+    launch_bconv(c, s, K + 1, npoly, c->mdrs_table[nq], 1, out, (long long)no * n, accs, (long long)ne * n);
+    {
+        RowMap m = make_map(c, no, 0, nq);
+        LoadPlain ld; ld.src = (const u64*)out; ld.poly_stride = (long long)no * n;
+        StoreSubMul st; st.out = out; st.out_poly_stride = (long long)no * n;
+        st.in = acc; st.in_poly_stride = (long long)ne * n; st.c = c->mdrs_inv[nq];
+        ntt_fwd(c, m, npoly * no, ld, out, (long long)no * n, st, s);
+    }
+    return check(who);
+}
+
 // d3 != null: the 3-polynomial tensor product; else (a, b): the operands of a fused multiply
 static int relin_rescale_impl(fhe_ctx* c, void* stream, uint64_t* out, const uint64_t* d3, const uint64_t* a, int a_nq,
                               const uint64_t* b, int b_nq, const uint64_t* rlk, int nq, int batch, const char* who) {
@@ -781,23 +804,7 @@ static int relin_rescale_impl(fhe_ctx* c, void* stream, uint64_t* out, const uin
         launch_ks_inner(c, s, nq, batch, acc, (const u64*)ext, (const u64*)a, (const u64*)rlk, (const u64*)b, c->p_mod_q,
                         true, a_nq, b_nq);
     }
-    const int npoly = 2 * batch;
-    u64* accs = acc + (size_t)no * n;                       // rows q_{nq-1}, p_0 .. p_{K-1} are contiguous
-    {
-        RowMap m = make_map(c, K + 1, no, nq);
-        LoadPlain ld; ld.src = accs; ld.poly_stride = (long long)ne * n;
-        StorePlain st; st.dst = accs; st.poly_stride = (long long)ne * n;
-        ntt_inv(c, m, npoly * (K + 1), ld, accs, (long long)ne * n, st, c->mdrs_scale[nq], s);
-    }
-    launch_bconv(c, s, K + 1, npoly, c->mdrs_table[nq], 1, (u64*)out, (long long)no * n, accs, (long long)ne * n);
-    {
-        RowMap m = make_map(c, no, 0, nq);
-        LoadPlain ld; ld.src = (const u64*)out; ld.poly_stride = (long long)no * n;
-        StoreSubMul st; st.out = (u64*)out; st.out_poly_stride = (long long)no * n;
-        st.in = acc; st.in_poly_stride = (long long)ne * n; st.c = c->mdrs_inv[nq];
-        ntt_fwd(c, m, npoly * no, ld, (u64*)out, (long long)no * n, st, s);
-    }
-    return check(who);
+    return moddown_rescale_tail(c, s, (u64*)out, acc, nq, 2 * batch, who);
 }
 
 int fhe_relin_rescale(fhe_ctx* c, void* stream, uint64_t* out, const uint64_t* d3, const uint64_t* rlk, int nq,
@@ -810,6 +817,34 @@ int fhe_mul_relin_rescale(fhe_ctx* c, void* stream, uint64_t* out, const uint64_
                           int b_nq, const uint64_t* rlk, int nq, int batch) {
     if (!a || !b) return fail("fhe_mul_relin_rescale: null operand");
     return relin_rescale_impl(c, stream, out, nullptr, a, a_nq, b, b_nq, rlk, nq, batch, "fhe_mul_relin_rescale");
+}
+
+int fhe_ks_accum(fhe_ctx* c, void* stream, uint64_t* acc, const uint64_t* d, const uint64_t* ksk, const uint64_t* lift,
+                 int lift_polys, int nq, int batch, int accumulate) {
+    if (bad_shape(c, nq, 0) || c->n_p == 0 || batch < 1 || c->modup_beta[nq] > FHE_MAX_BETA || !acc ||
+        (lift && lift_polys != 1 && lift_polys != 2) || (!d && !lift) || (d && !ksk))
+        return fail("fhe_ks_accum: bad arguments");
+    cudaStream_t s = (cudaStream_t)stream;
+    const int n = c->n, ne = nq + c->n_p, beta = c->modup_beta[nq];
+    if (!d) {                                              // no key switch: acc (+)= P * lift
+        launch_ks_inner(c, s, nq, batch, (u64*)acc, nullptr, (const u64*)lift, nullptr, (const u64*)lift, c->p_mod_q, false,
+                        0, 0, lift_polys, accumulate, true);
+        return check("fhe_ks_accum");
+    }
+    u64* base = arena(c, ((size_t)batch * nq + (size_t)batch * beta * ne) * n);
+    if (!base) return fail("fhe_ks_accum: scratch allocation failed");
+    u64* ext = base + (size_t)batch * nq * n;
+    int rc;
+    if ((rc = fhe_modup(c, stream, (uint64_t*)ext, d, nq, batch))) return rc;
+    launch_ks_inner(c, s, nq, batch, (u64*)acc, (const u64*)ext, (const u64*)d, (const u64*)ksk, (const u64*)lift,
+                    c->p_mod_q, false, 0, 0, lift_polys, accumulate);
+    return check("fhe_ks_accum");
+}
+
+int fhe_moddown_rescale(fhe_ctx* c, void* stream, uint64_t* out, uint64_t* acc, int nq, int npoly) {
+    if (bad_shape(c, nq, 0) || nq < 2 || c->n_p == 0 || npoly < 1 || !out || !acc)
+        return fail("fhe_moddown_rescale: bad shape");
+    return moddown_rescale_tail(c, (cudaStream_t)stream, (u64*)out, (u64*)acc, nq, npoly, "fhe_moddown_rescale");
 }
 
 int fhe_moddown(fhe_ctx* c, void* stream, uint64_t* out, uint64_t* acc, int nq, int npoly) {

@@ -438,8 +438,11 @@ FHE_D void st2(u64* p, u64 a, u64 b) {
 template <int BMAX, int UNR, bool AB>
 __global__ void __launch_bounds__(256, (BMAX <= 4 ? 3 : 2)) k_ks_inner(DevTables T, int nq, int alpha, int beta, int batch,
                                                   u64* acc, const u64* ext, const u64* d, const u64* ksk,
-                                                  const u64* lift, const ConstF* lift_c, int d_nq, int lift_nq) {
+                                                  const u64* lift, const ConstF* lift_c, int d_nq, int lift_nq,
+                                                  int lift_polys, int accum) {
     // d_nq / lift_nq: limbs per batch element of `d` / `lift` (>= nq; only the AB operands may carry more)
+    // lift_polys: 2, or 1 when only polynomial 0 is lifted (a rotation: (sigma c0, 0));  accum: acc += instead of acc =
+    // beta == 0: no key-switch part at all (acc (+)= P * lift on the q-limbs, (+)= 0 on the special limbs)
     const int t = blockIdx.y;
     const int ne = nq + T.n_p;
     const int id = t < nq ? t : T.n_q + (t - nq);
@@ -485,7 +488,7 @@ __global__ void __launch_bounds__(256, (BMAX <= 4 ? 3 : 2)) k_ks_inner(DevTables
                     }
                 if (has_lift) {
                     L0[u] = ld_u64(lp + (((size_t)b * lift_nq) << log_n));
-                    L1[u] = ld_u64(lp + ps + (((size_t)b * lift_nq) << log_n));
+                    L1[u] = AB || lift_polys == 2 ? ld_u64(lp + ps + (((size_t)b * lift_nq) << log_n)) : 0;
                     if (AB) {
                         M0[u] = ld_u64(bp + (((size_t)b * d_nq) << log_n));
                         M1[u] = ld_u64(bp + pd + (((size_t)b * d_nq) << log_n));
@@ -523,8 +526,11 @@ __global__ void __launch_bounds__(256, (BMAX <= 4 ? 3 : 2)) k_ks_inner(DevTables
                     a0 = d_add(a0, mulmod_const(AB ? t0 : u64_to_f(l0[u]), pc, q));
                     a1 = d_add(a1, mulmod_const(AB ? t1 : u64_to_f(l1[u]), pc, q));
                 }
-                acc[(((size_t)b * ne + t) << log_n) + idx] = f_to_u64(reduce_canon(a0, q, qi));
-                acc[((((size_t)batch + b) * ne + t) << log_n) + idx] = f_to_u64(reduce_canon(a1, q, qi));
+                u64* o0 = acc + (((size_t)b * ne + t) << log_n) + idx;
+                u64* o1 = acc + ((((size_t)batch + b) * ne + t) << log_n) + idx;
+                if (accum) { a0 = d_add(a0, u64_to_f(*o0)); a1 = d_add(a1, u64_to_f(*o1)); }
+                *o0 = f_to_u64(reduce_canon(a0, q, qi));
+                *o1 = f_to_u64(reduce_canon(a1, q, qi));
             }
         }
 #pragma unroll

@@ -154,6 +154,17 @@ int fhe_relin_rescale(fhe_ctx* ctx, void* stream, uint64_t* out, const uint64_t*
 int fhe_mul_relin_rescale(fhe_ctx* ctx, void* stream, uint64_t* out, const uint64_t* a, int a_nq,
                           const uint64_t* b, int b_nq, const uint64_t* rlk, int nq, int batch);
 
+/* Key switches whose ModDown is shared (the giant steps of a baby-step/giant-step linear transform inside
+ * Engine.bootstrap, xor_service.py:120-129): acc[2][batch][nq + K][N] (+)= <ModUp(d), ksk> + P * lift, all in the
+ * extended basis.  d[1][batch][nq][N] (NTT domain) or NULL for "no key switch, lift only"; lift[lift_polys][batch][nq][N]
+ * or NULL, lift_polys = 1 lifts polynomial 0 only (a rotation: (sigma(c0), 0)); accumulate != 0 adds to acc. */
+int fhe_ks_accum(fhe_ctx* ctx, void* stream, uint64_t* acc, const uint64_t* d, const uint64_t* ksk,
+                 const uint64_t* lift, int lift_polys, int nq, int batch, int accumulate);
+
+/* ... and the shared ModDown, merged with the rescale that follows: acc[npoly][nq + K][N] (overwritten) ->
+ * out[npoly][nq-1][N] = round(acc / (P * q_{nq-1})). */
+int fhe_moddown_rescale(fhe_ctx* ctx, void* stream, uint64_t* out, uint64_t* acc, int nq, int npoly);
+
 /* Engine.encode / encrypt residue step (xor_service.py:59-66): signed 64-bit coefficients
  * coeffs[batch][N] (device) -> coefficient-domain residues out[batch][nq + np][N]. */
 int fhe_from_i64(fhe_ctx* ctx, void* stream, uint64_t* out, const int64_t* coeffs, int nq, int np, int batch);

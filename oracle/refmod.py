@@ -271,6 +271,30 @@ class RefBackend:
     def keyswitch(self, d, ksk, nq):
         return self.moddown(self.ks_inner(self.modup(d, nq), d, ksk, nq), nq)
 
+    def ks_accum(self, acc, d, ksk, lift, nq):
+        """acc (+)= <ModUp(d), ksk> + P * lift in the extended basis (restated with the plain primitives)."""
+        P = self.params
+        src = d if d is not None else lift
+        bt = src.shape[1]
+        if d is not None:
+            part = np.array(self.ks_inner(self.modup(d, nq), d, ksk, nq), copy=True)
+        else:
+            part = np.zeros((2, bt, nq + P.n_p, self.n), dtype=np.uint64)
+        if lift is not None:
+            pprod = 1
+            for p in P.p:
+                pprod *= p
+            l = self.mul_scalar(np.ascontiguousarray(lift), [pprod % P.moduli[j] for j in range(nq)], nq, 0)
+            k = l.shape[0]
+            part[:k, :, :nq] = self.add(np.ascontiguousarray(part[:k, :, :nq]), l, nq, 0)
+        return part if acc is None else self.add(acc, part, nq, P.n_p)
+
+    def moddown_rescale(self, acc, nq):
+        flat = np.ascontiguousarray(acc).reshape(-1, acc.shape[2], self.n)
+        out = np.empty((flat.shape[0], nq - 1, self.n), dtype=np.uint64)
+        self._L.ref_moddown_ex(self._ctx, _p(out), _p(flat), C.c_int(nq), C.c_int(flat.shape[0]), C.c_int(1))
+        return out.reshape(acc.shape[0], acc.shape[1], nq - 1, self.n)
+
     # ---- fused LUT evaluation pieces, restated with the plain primitives
     def prepare_lincomb(self, const_res, c0_res, nq: int):
         return dict(const_res=const_res, c0_res=c0_res, nq=nq, M=len(const_res), T=len(const_res[0]))

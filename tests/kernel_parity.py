@@ -90,6 +90,20 @@ def check_keyswitch(P, gb, rb, levels=None, seed=3):
                 assert np.array_equal(gb.to_numpy(got), want), f"mul_relin_rescale with a higher-level operand nq={nq}"
                 got = gb.mul_relin_rescale(gb.from_numpy(b), gb.from_numpy(np.ascontiguousarray(a_hi)), gk, nq)
                 assert np.array_equal(gb.to_numpy(got), rb.relin_rescale(rb.tensor(b, a, nq), ksk, nq)), f"... as b, nq={nq}"
+            # key switches that share one ModDown: acc = KS_ext(d) + P (l0, 0); acc += KS_ext(d') + P (l0', l1'); acc += P u
+            d2 = rand_poly(P, rng, 1, nq, False, batch=bt)
+            l1 = rand_poly(P, rng, 1, nq, False, batch=bt)
+            l2 = rand_poly(P, rng, 2, nq, False, batch=bt)
+            ga = gb.ks_accum(None, gb.from_numpy(d2), gk, gb.from_numpy(l1), nq)
+            ra = rb.ks_accum(None, d2, ksk, l1, nq)
+            assert np.array_equal(gb.to_numpy(ga), ra), f"ks_accum nq={nq}"
+            ga = gb.ks_accum(ga, gb.from_numpy(a[1:2]), gk, gb.from_numpy(l2), nq)
+            ra = rb.ks_accum(ra, a[1:2], ksk, l2, nq)
+            assert np.array_equal(gb.to_numpy(ga), ra), f"ks_accum accumulate nq={nq}"
+            ga = gb.ks_accum(ga, None, None, gb.from_numpy(l2), nq)
+            ra = rb.ks_accum(ra, None, None, l2, nq)
+            assert np.array_equal(gb.to_numpy(ga), ra), f"ks_accum lift only nq={nq}"
+            assert np.array_equal(gb.to_numpy(gb.moddown_rescale(ga, nq)), rb.moddown_rescale(ra, nq)), f"moddown_rescale nq={nq}"
             sq = gb.mul_relin_rescale(gb.from_numpy(a), gb.from_numpy(a), gk, nq)
             assert np.array_equal(gb.to_numpy(sq), rb.relin_rescale(rb.tensor(a, a, nq), ksk, nq)), f"square nq={nq}"
 
