@@ -598,18 +598,26 @@ class Engine:
         be = self.backend
         if ct.zero or not keys:
             return [ct for _ in keys]
-        if not hasattr(be, "modup_raw") or len(keys) < 2 or _NO_FUSE:
+        if not hasattr(be, "modup_raw") or not hasattr(be, "automorphism_rows") or len(keys) < 2 or _NO_FUSE:
             return [self._apply_galois(ct, k) for k in keys]
         nq = ct.level + 1
-        ext = be.modup_raw(be.select_poly(ct.polys, 1), nq)
+        c1 = be.select_poly(ct.polys, 1)
+        ext = be.modup_raw(c1, nq)
         outs = []
+        two_n = 2 * self.params.n
         for key in keys:
-            rot = be.automorphism(ct.polys, key.galois, nq, 0)
-            acc = be.ks_inner(be.automorphism_rows(ext, key.galois), be.select_poly(rot, 1), key.data, nq)
+            # sigma(<e, sigma^-1(key)>) = <sigma(e), key>: with the key permuted once (cached on the key object) the
+            # shared ModUp output is used as it is, and the automorphism runs once on the 2 n rows of the result
+            # instead of on the beta (n + K) extended rows of every rotation -- bit-identical either way
+            pre = getattr(key, "_pre_permuted", None)
+            if pre is None:
+                pre = key._pre_permuted = be.automorphism_rows(key.data, pow(int(key.galois), -1, two_n))
+            acc = be.ks_inner(ext, c1, pre, nq)
             ks = be.moddown_inplace(acc, nq) if hasattr(be, "moddown_inplace") else be.moddown(acc, nq)
             self._count('keyswitch_galois')
             add0 = be.add_poly0_inplace if hasattr(be, "add_poly0_inplace") else be.add_poly0
-            outs.append(Ciphertext(self, add0(ks, be.select_poly(rot, 0), nq), ct.level))
+            outs.append(Ciphertext(self, be.automorphism(add0(ks, be.select_poly(ct.polys, 0), nq), key.galois, nq, 0),
+                                   ct.level))
         return outs
 
     def _mul_scalar(self, ct: Ciphertext, value) -> Ciphertext:
