@@ -379,6 +379,20 @@ class CudaBackend:
             done += g
         return out
 
+    def mul_plain_multi(self, a_list: List, p_rows: List[List], nq: int):
+        """out_g = sum_t a_t (.) p_rows[g][t] for all g in one pass (None = absent term); a_t [2,B,>=nq,N],
+        plaintexts [1,1,nq,N] -> [G,2,B,nq,N]."""
+        a_list = [x.contiguous() for x in a_list]
+        T, G = len(a_list), len(p_rows)
+        bt = a_list[0].shape[1]
+        keep = [[None if x is None else x.contiguous() for x in row] for row in p_rows]
+        out = self._empty(G, 2, bt, nq, self.n)
+        ap = (C.c_void_p * T)(*[x.data_ptr() for x in a_list])
+        an = (C.c_int * T)(*[x.shape[2] for x in a_list])
+        pp = (C.c_void_p * (G * T))(*[None if x is None else x.data_ptr() for row in keep for x in row])
+        self._call("fhe_mul_plain_multi", self._ptr(out), ap, an, pp, T, G, nq, bt)
+        return out
+
     def automorphism_rows(self, h, g: int):
         """X -> X^g on every row of an arbitrary [.., N] tensor (hoisted rotations act on ModUp output)."""
         h = h.contiguous()

@@ -294,18 +294,20 @@ def _linear_transform(engine, ct: Ciphertext, entry) -> Ciphertext:
     be = engine.backend
     shared = hasattr(be, "ks_accum")          # giant-step key switches accumulate in the extended basis: ONE ModDown
     out, acc, lvl = None, None, None
-    for g, items in entry["giants"].items():
-        cts, pts = [], []
-        for b, pt in items:
+    for items in entry["giants"].values():
+        for b, _ in items:
             if b not in babies:
                 babies[b] = engine.rotate(ct, plan_keys[b])
-            cts.append(babies[b])
-            pts.append(pt)
-        # the diagonal sums stay un-rescaled (scale delta * q_level) through the giant-step rotation and the
-        # final sum: ONE rescale per transform instead of one per giant step (a rescale is 2 (n - 1) limb
-        # transforms; the rotation one level higher costs a few per cent more, and its key-switch noise now
-        # lands on the larger scale)
-        inner = engine.multiply_plain_sum(cts, pts, rescale=False)
+    # all diagonal sums in one pass over the baby rotations (each read once, not once per giant step); they stay
+    # un-rescaled (scale delta * q_level) through the giant-step rotation and the final sum: ONE rescale per
+    # transform instead of one per giant step
+    blist = sorted(babies)
+    rows = []
+    for items in entry["giants"].values():
+        have = dict(items)
+        rows.append([have.get(b) for b in blist])
+    inners = engine.multiply_plain_sums([babies[b] for b in blist], rows)
+    for g, inner in zip(entry["giants"], inners):
         if shared:
             # ... and the giant rotations share their ModDown: rot_g(x) = ModDown(<ModUp(sigma x1), key_g> + P sigma x0),
             # ModDown is linear up to rounding, so the extended accumulators are summed (inside the inner-product

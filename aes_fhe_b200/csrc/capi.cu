@@ -667,6 +667,27 @@ int fhe_mul_plain_sum(fhe_ctx* c, void* stream, uint64_t* out, const uint64_t* c
     return check("fhe_mul_plain_sum");
 }
 
+int fhe_mul_plain_multi(fhe_ctx* c, void* stream, uint64_t* out, const uint64_t* const* a, const int* a_nq,
+                        const uint64_t* const* p, int T, int G, int nq, int batch) {
+    if (bad_shape(c, nq, 0) || batch < 1 || T < 1 || T > FHE_LC_MAX_T || G < 1 || G > FHE_PM_MAX_G || !a || !a_nq || !p)
+        return fail("fhe_mul_plain_multi: bad shape");
+    PlainMultiIn in;
+    for (int t = 0; t < FHE_LC_MAX_T; ++t) {
+        const int nt = t < T ? a_nq[t] : nq;
+        if (t < T && nt < nq) return fail("fhe_mul_plain_multi: operand has fewer limbs than the output");
+        in.a[t] = t < T ? (const u64*)a[t] : nullptr;
+        in.a_batch_stride[t] = (long long)nt * c->n;
+        in.a_poly_stride[t] = (long long)batch * nt * c->n;
+        for (int g = 0; g < FHE_PM_MAX_G; ++g) in.p[g][t] = (g < G && t < T) ? (const u64*)p[(size_t)g * T + t] : nullptr;
+    }
+    dim3 grid(c->n / 256, nq), block(256);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (T <= 4) launch(k_mul_plain_multi<4>, grid, block, s, c->T, nq, batch, T, G, in, (u64*)out);
+    else if (T <= 8) launch(k_mul_plain_multi<8>, grid, block, s, c->T, nq, batch, T, G, in, (u64*)out);
+    else launch(k_mul_plain_multi<16>, grid, block, s, c->T, nq, batch, T, G, in, (u64*)out);
+    return check("fhe_mul_plain_multi");
+}
+
 int fhe_tensor_acc(fhe_ctx* c, void* stream, uint64_t* acc, const uint64_t* const* a, const int* a_nq,
                    const int* a_batch, const uint64_t* b, int b_batch, int G, int nq, int batch, int accumulate) {
     if (bad_shape(c, nq, 0) || batch < 1 || G < 1 || G > FHE_LC_MAX_T || !a || !a_nq || !a_batch || !b ||

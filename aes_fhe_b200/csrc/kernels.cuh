@@ -313,6 +313,57 @@ __global__ void __launch_bounds__(256, 2) k_mul_plain_sum(DevTables Tb, int nq, 
         }
 }
 
+// out_g = sum_t a_t (.) p_{g,t} for g < G in ONE pass over the ciphertexts: all the diagonal sums of a baby-step/
+// giant-step linear transform (one per giant step, same baby rotations a_t) -- every a_t is read once instead of G
+// times (once per sweep of GC = 32 / T_MAX output rows, whose plaintext words a thread keeps in registers).
+// p_{g,t} == nullptr: that diagonal is absent.   out : [G][2][batch][nq][N]      grid: (N/256, nq)
+#define FHE_PM_MAX_G 8
+struct PlainMultiIn {
+    const u64* a[FHE_LC_MAX_T];
+    long long a_poly_stride[FHE_LC_MAX_T];
+    long long a_batch_stride[FHE_LC_MAX_T];
+    const u64* p[FHE_PM_MAX_G][FHE_LC_MAX_T];
+};
+template <int T_MAX>
+__global__ void __launch_bounds__(256, 2) k_mul_plain_multi(DevTables Tb, int nq, int batch, int T, int G, PlainMultiIn in,
+                                                             u64* out) {
+    constexpr int GC = 32 / T_MAX;                              // output rows per sweep: GC * T_MAX plaintext words in registers
+    const int j = blockIdx.y;
+    const Modulus Mo = Tb.mod[j];
+    const double q = Mo.qd, qi = Mo.qinv;
+    const size_t lo = ((size_t)j << Tb.log_n) + blockIdx.x * 256 + threadIdx.x;
+    const size_t ops = (size_t)batch * nq << Tb.log_n, obs = (size_t)nq << Tb.log_n;
+    for (int g0 = 0; g0 < G; g0 += GC) {
+        double p[GC][T_MAX];
+#pragma unroll
+        for (int c = 0; c < GC; ++c)
+#pragma unroll
+            for (int t = 0; t < T_MAX; ++t) {
+                const u64* pp = (g0 + c < G && t < T) ? in.p[g0 + c][t] : nullptr;
+                p[c][t] = pp != nullptr ? u64_to_f(ld_u64(pp + lo)) : 0.0;
+            }
+        for (int poly = 0; poly < 2; ++poly)
+            for (int b = 0; b < batch; ++b) {
+                double a[T_MAX];
+#pragma unroll
+                for (int t = 0; t < T_MAX; ++t)
+                    a[t] = t < T ? u64_to_f(ld_u64(in.a[t] + (size_t)poly * in.a_poly_stride[t] + (size_t)b * in.a_batch_stride[t] + lo))
+                                 : 0.0;
+#pragma unroll
+                for (int c = 0; c < GC; ++c) {
+                    if (g0 + c < G) {
+                        double acc = 0.0;
+#pragma unroll
+                        for (int t = 0; t < T_MAX; ++t)
+                            if (t < T) acc = d_add(acc, mulmod_var(a[t], p[c][t], q, qi));      // absent term: p = 0
+                        out[(size_t)(g0 + c) * 2 * ops + (size_t)poly * ops + (size_t)b * obs + lo] =
+                            f_to_u64(reduce_canon(acc, q, qi));
+                    }
+                }
+            }
+    }
+}
+
 // ---------------------------------------------------------------- base conversion
 // One table per source basis.  Output value for target t:
 //     sum_k yc_k * f[k][t]   (mod m_t),     yc_k = centred representative of y_k mod q_k

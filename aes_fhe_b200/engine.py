@@ -590,6 +590,27 @@ class Engine:
             acc = prod if acc is None else be.add(acc, prod, lvl + 1, 0)
         return self._rescale(Ciphertext(self, acc, lvl)) if rescale else Ciphertext(self, acc, lvl)
 
+    def multiply_plain_sums(self, cts: Sequence[Ciphertext], pt_rows: Sequence[Sequence[Optional[Plaintext]]]) -> List[Ciphertext]:
+        """[sum_t ct_t (.) pt_rows[g][t] for g] BEFORE the rescale (same level, scale delta * q_level), every
+        ciphertext read once for all rows (fhe_mul_plain_multi): the diagonal sums of all giant steps of a
+        baby-step/giant-step linear transform.  ``None`` entries are absent terms."""
+        lvl = min(c.level for c in cts)
+        if lvl == 0:
+            raise RuntimeError("multiply: no multiplicative depth left")
+        be = self.backend
+        G, T = len(pt_rows), len(cts)
+        if (hasattr(be, "mul_plain_multi") and not _NO_FUSE and T <= 16 and G <= 8
+                and all(c.batch == cts[0].batch and c.npoly == 2 and not c.zero for c in cts)):
+            self._count('mul_pt', sum(1 for row in pt_rows for p in row if p is not None))
+            polys = [self.level_down(c, lvl).polys for c in cts]
+            out = be.mul_plain_multi(polys, [[None if p is None else p.at_level(lvl) for p in row] for row in pt_rows], lvl + 1)
+            return [Ciphertext(self, out[g], lvl) for g in range(G)]
+        outs = []
+        for row in pt_rows:
+            sel = [(c, p) for c, p in zip(cts, row) if p is not None]
+            outs.append(self.multiply_plain_sum([c for c, _ in sel], [p for _, p in sel], rescale=False))
+        return outs
+
     def rotate_hoisted(self, ct: Ciphertext, keys: Sequence[FixedRotationKey]) -> List[Ciphertext]:
         """Several rotations of ONE ciphertext sharing a single ModUp (the base extension commutes
         with the Galois automorphism bit for bit: centred digits are odd functions and the

@@ -99,6 +99,12 @@ int fhe_lincomb(fhe_ctx* ctx, void* stream, uint64_t* out, const uint64_t* const
 int fhe_mul_plain_sum(fhe_ctx* ctx, void* stream, uint64_t* out, const uint64_t* const* a, const int* a_nq,
                       const uint64_t* const* p, int T, int nq, int batch, int accumulate);
 
+/* The same pattern for G output sums over ONE set of T ciphertexts (the diagonal sums of all giant steps of a
+ * baby-step/giant-step linear transform in Engine.bootstrap, xor_service.py:120-129): out[G][2][batch][nq][N],
+ * out_g = sum_t a_t (.) p[g * T + t]; a NULL plaintext pointer skips that term.  Every a_t is read once. */
+int fhe_mul_plain_multi(fhe_ctx* ctx, void* stream, uint64_t* out, const uint64_t* const* a, const int* a_nq,
+                        const uint64_t* const* p, int T, int G, int nq, int batch);
+
 /* Lazy-relinearised products: acc[3][batch][nq][N] (+)= sum_g a_g (x) b_g for G <= 16 products;
  * a[g] are ciphertexts [2][a_batch[g]][a_nq[g]][N] (host array of device pointers), b is G
  * contiguous ciphertexts [2][b_batch][nq][N]; a_batch[g] and b_batch are `batch` or 1 (a
