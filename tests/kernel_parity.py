@@ -39,17 +39,21 @@ def check_primitives(P, gb, rb, seed=1):
     assert np.array_equal(gb.to_numpy(gb.add_poly0(up(b), up(c1), nq)), rb.add_poly0(b, c1, nq)), "add_poly0"
     if hasattr(gb, "mul_plain_multi"):
         # diagonal sums of several giant steps in one pass: out_g = sum_t a_t (.) p[g][t], absent terms skipped
-        al = [rand_poly(P, rng, 2, nq, False, batch=2) for _ in range(3)]
-        pl = [[rand_poly(P, rng, 1, nq, False, batch=1) for _ in range(3)] for _ in range(2)]
-        pl[1][1] = None
-        got = gb.to_numpy(gb.mul_plain_multi([up(a_) for a_ in al], [[None if p_ is None else up(p_) for p_ in row] for row in pl], nq))
-        for g_, row in enumerate(pl):
-            want = None
-            for a_, p_ in zip(al, row):
-                if p_ is not None:
-                    term = rb.mul(a_, p_, nq, 0)
-                    want = term if want is None else rb.add(want, term, nq, 0)
-            assert np.array_equal(got[g_], want), f"mul_plain_multi row {g_}"
+        # (T, G) = (3, 2): eight rows per sweep; (6, 5): four per sweep, ragged last sweep; (9, 3): two per sweep
+        for T_, G_ in ((3, 2), (6, 5), (9, 3)):
+            al = [rand_poly(P, rng, 2, nq, False, batch=2) for _ in range(T_)]
+            pl = [[rand_poly(P, rng, 1, nq, False, batch=1) for _ in range(T_)] for _ in range(G_)]
+            pl[1][1] = None
+            pl[G_ - 1][0] = None
+            got = gb.to_numpy(gb.mul_plain_multi([up(a_) for a_ in al],
+                                                 [[None if p_ is None else up(p_) for p_ in row] for row in pl], nq))
+            for g_, row in enumerate(pl):
+                want = None
+                for a_, p_ in zip(al, row):
+                    if p_ is not None:
+                        term = rb.mul(a_, p_, nq, 0)
+                        want = term if want is None else rb.add(want, term, nq, 0)
+                assert np.array_equal(got[g_], want), f"mul_plain_multi T={T_} G={G_} row {g_}"
     x = rand_poly(P, rng, 1, 2, False, batch=3)
     assert np.array_equal(gb.crt_centered(up(x), 2), rb.crt_centered(x, 2)), "crt2"
     x1 = np.ascontiguousarray(x[:, :, :1])
