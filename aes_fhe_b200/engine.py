@@ -475,12 +475,15 @@ class Engine:
         cp, cm = self._const_residues(re, im, nq)
         return Ciphertext(self, self.backend.mul_const(ct.polys, cp, cm, nq), ct.level)
 
-    def level_down(self, ct: Ciphertext, target: int) -> Ciphertext:
-        """Bring ``ct`` to ``target`` (< ct.level) *and* onto that level's scale."""
-        if target == ct.level:
+    def level_down(self, ct: Ciphertext, target: int, factor=None) -> Ciphertext:
+        """Bring ``ct`` to ``target`` (< ct.level) *and* onto that level's scale.  ``factor`` (a real number)
+        multiplies the message on the way: the constant multiply that changes the scale carries it, so
+        ``factor * ct`` at a lower level costs one constant multiply + one rescale on target + 2 limbs."""
+        if target == ct.level and factor is None:
             return ct
-        if target > ct.level:
-            raise RuntimeError("cannot raise the level of a ciphertext without bootstrapping")
+        if target >= ct.level:
+            raise RuntimeError("cannot raise the level of a ciphertext without bootstrapping" if factor is None
+                               else "level_down with a factor needs a lower target level")
         P = self.params
         if ct.zero:
             return self._zero(target, ct.npoly, ct.batch)
@@ -488,6 +491,8 @@ class Engine:
         if ct.level > target + 1:
             polys = self.backend.take_limbs(polys, target + 2, False)
         c = P.delta[target] * P.moduli[target + 1] / P.delta[ct.level]
+        if factor is not None:
+            c = c * Fraction(float(factor))
         tmp = self._mul_int_const(Ciphertext(self, polys, target + 1), int(round(c)), 0)
         self._count('level_adjust')
         return self._rescale(tmp)

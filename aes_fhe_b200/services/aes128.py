@@ -29,7 +29,6 @@ from typing import Dict, List, Optional, Sequence
 
 import numpy as np
 
-from ..bootstrap import lincomb_const
 from ..engine import Ciphertext
 from .aes_round import AESRoundService
 from .key_expansion import expand_key
@@ -53,8 +52,10 @@ class AES128Service(AESRoundService):
         x4 = e.multiply(x2, x2, rlk)
         x8 = e.multiply(x4, x4, rlk)
         x16 = e.multiply(x8, x8, rlk)
-        y = lincomb_const(e, {1: ct}, {1: -1.0 / 16.0})
-        z = lincomb_const(e, {1: ct}, {1: 17.0 / 16.0})
+        # -x/16 straight onto the level of x^16 and 17x/16 onto the level of the product: one constant multiply +
+        # rescale each, on the few limbs those levels have (not a multiply at the top followed by a level adjustment)
+        y = e.level_down(ct, x16.level, factor=-1.0 / 16.0)
+        z = e.level_down(ct, x16.level - 1, factor=17.0 / 16.0)
         return e.add(e.multiply(x16, y, rlk), z)
 
     def refresh(self, cts: Sequence[Ciphertext]) -> List[Ciphertext]:
