@@ -225,7 +225,7 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--batch", type=int, default=16, help="ciphertexts per GPU per step")
+    ap.add_argument("--batch", type=int, default=32, help="ciphertexts per GPU per step (16: 727k blocks/s, 32: 736k)")
     ap.add_argument("--dnum", type=int, default=None, help="key-switch digit count of the SubBytes parameter set")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-full-round", action="store_true",
