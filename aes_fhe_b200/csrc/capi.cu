@@ -634,6 +634,12 @@ int fhe_lincomb(fhe_ctx* c, void* stream, uint64_t* out, const uint64_t* const* 
     }
     cudaStream_t s = (cudaStream_t)stream;
     const ConstF* cf = (const ConstF*)consts;
+    if (M <= 2) {                                            // too few columns for a tensor-core tile
+        dim3 grid(c->n / 512, 2 * batch * nq), block(256);
+        if (T <= 4) launch(k_lincomb_few<4>, grid, block, s, c->T, nq, batch, M, T, li, cf, (const u64*)c0, (u64*)out);
+        else launch(k_lincomb_few<16>, grid, block, s, c->T, nq, batch, M, T, li, cf, (const u64*)c0, (u64*)out);
+        return check("fhe_lincomb");
+    }
     const int kt = (T + 3) / 4;
     const size_t smem = FHE_LCM_SMEM(M, kt);
     if (smem > FHE_LC_SMEM_LIMIT) return fail("fhe_lincomb: M * T too large for the shared-memory constant tile");

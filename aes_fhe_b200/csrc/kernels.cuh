@@ -240,6 +240,54 @@ __global__ void __launch_bounds__(256, FHE_LCM_MINB) k_lincomb_mma(DevTables Tb,
     }
 }
 
+// One or two outputs (M <= 2: the constant-weighted sums of the Chebyshev leaves of EvalMod, level adjustments): the
+// 8-column tensor-core tile would be seven eighths padding, so these run as plain FP64 code -- mulmod_const per term,
+// constants of the (limb, half) in shared memory, two coefficients 256 apart per thread.  HBM-bound.
+//   grid: (N / 512, 2 * batch * nq)
+template <int T_MAX>
+__global__ void __launch_bounds__(256) k_lincomb_few(DevTables Tb, int nq, int batch, int M, int T, LinCombIn in,
+                                                     const ConstF* consts, const u64* c0, u64* out) {
+    FHE_SHARED ConstF s_c[2 * FHE_LC_MAX_T];                       // [M <= 2][T]
+    const int row = blockIdx.y;
+    const int j = row % nq, b = (row / nq) % batch, poly = row / (nq * batch);
+    const Modulus Mo = Tb.mod[j];
+    const double q = Mo.qd, qi = Mo.qinv;
+    const u32 idx = blockIdx.x * 512 + threadIdx.x;
+    const int half = (blockIdx.x * 512) >> (Tb.log_n - 1);        // uniform over the CTA
+    for (int i = threadIdx.x; i < M * T; i += 256) s_c[i] = consts[((size_t)i * nq + j) * 2 + half];
+    const size_t lo = ((size_t)j << Tb.log_n) + idx;
+    double x0[T_MAX], x1[T_MAX];
+#pragma unroll
+    for (int t = 0; t < T_MAX; ++t) {
+        if (t < T) {
+            const u64* p = in.ptr[t] + (size_t)poly * in.poly_stride[t] + (size_t)b * in.batch_stride[t] + lo;
+            x0[t] = u64_to_f(ld_u64(p)); x1[t] = u64_to_f(ld_u64(p + 256));
+        } else { x0[t] = 0.0; x1[t] = 0.0; }
+    }
+    __syncthreads();
+    const size_t out_ct = (size_t)2 * batch * nq << Tb.log_n;
+    u64* o = out + (((size_t)poly * batch + b) * nq << Tb.log_n) + lo;
+    for (int m = 0; m < M; ++m) {
+        const ConstF* cm = s_c + m * T;
+        double a0 = 0.0, a1 = 0.0;
+#pragma unroll
+        for (int t = 0; t < T_MAX; ++t)
+            if (t < T) {
+                const ConstF c = cm[t];
+                a0 = d_add(a0, mulmod_const(x0[t], c, q));
+                a1 = d_add(a1, mulmod_const(x1[t], c, q));
+            }
+        double r0 = reduce_canon(a0, q, qi), r1 = reduce_canon(a1, q, qi);
+        if (c0 != nullptr && poly == 0) {
+            const double k = u64_to_f(c0[((size_t)m * nq + j) * 2 + half]);
+            r0 = d_add(r0, k); r0 = r0 >= q ? d_add(r0, -q) : r0;
+            r1 = d_add(r1, k); r1 = r1 >= q ? d_add(r1, -q) : r1;
+        }
+        o[(size_t)m * out_ct] = f_to_u64(r0);
+        o[(size_t)m * out_ct + 256] = f_to_u64(r1);
+    }
+}
+
 // acc3 (+)= a (x) b  : accumulate the three tensor components of G products in one pass.
 //   a_g : [2][batch][nq_a][N]  (first nq limbs used),  b : G x [2][batch][nq][N] contiguous
 //   acc : [3][batch][nq][N]    grid: (N/256, batch * nq)

@@ -54,6 +54,16 @@ def check_primitives(P, gb, rb, seed=1):
                         term = rb.mul(a_, p_, nq, 0)
                         want = term if want is None else rb.add(want, term, nq, 0)
                 assert np.array_equal(got[g_], want), f"mul_plain_multi T={T_} G={G_} row {g_}"
+    # constant-weighted sums straight through fhe_lincomb: one / two outputs (plain FP64 kernel) and more (tensor cores)
+    for M_, T_ in ((1, 3), (2, 5), (3, 2), (9, 13)):
+        ins = [rand_poly(P, rng, 2, nq, False, batch=2) for _ in range(T_)]
+        rc = lambda: [int(rng.integers(0, P.moduli[l])) for l in range(nq)]
+        cres = [[(rc(), rc()) for _ in range(T_)] for _ in range(M_)]
+        c0 = [(rc(), rc()) for _ in range(M_)] if M_ != 2 else None
+        got = gb.lincomb([up(a_) for a_ in ins], gb.prepare_lincomb(cres, c0, nq))
+        want = rb.lincomb(ins, rb.prepare_lincomb(cres, c0, nq))
+        for m_ in range(M_):
+            assert np.array_equal(gb.to_numpy(got[m_]), want[m_]), f"lincomb M={M_} T={T_} output {m_}"
     x = rand_poly(P, rng, 1, 2, False, batch=3)
     assert np.array_equal(gb.crt_centered(up(x), 2), rb.crt_centered(x, 2)), "crt2"
     x1 = np.ascontiguousarray(x[:, :, :1])
