@@ -762,7 +762,7 @@ int fhe_mod_raise(fhe_ctx* c, void* stream, uint64_t* out, const uint64_t* in, i
 
 int fhe_automorphism(fhe_ctx* c, void* stream, uint64_t* out, const uint64_t* in, uint64_t galois, int nrows) {
     if (!c || nrows < 1 || !(galois & 1)) return fail("fhe_automorphism: bad arguments");
-    launch(k_automorphism, dim3(c->n / 256, nrows), dim3(256), (cudaStream_t)stream, c->log_n, (u64*)out,
+    launch(k_automorphism, dim3(c->n / 1024, nrows), dim3(256), (cudaStream_t)stream, c->log_n, (u64*)out,
            (const u64*)in, (u64)galois);
     return check("fhe_automorphism");
 }

@@ -85,14 +85,21 @@ __global__ void __launch_bounds__(256) k_const(DevTables T, RowMap map, u64* out
 }
 
 // NTT-domain automorphism X -> X^g on bit-reversed spectra: out[p] = in[perm(p)]
+// A thread moves four elements 256 apart (four gathers in flight before the first store): the kernel is pure
+// memory traffic and one 8-byte load per thread left the memory system short of requests.   grid: (N/1024, rows)
 __global__ void __launch_bounds__(256) k_automorphism(int log_n, u64* out, const u64* in, u64 g) {
-    const u32 p = blockIdx.x * 256 + threadIdx.x;
     const size_t ro = (size_t)blockIdx.y << log_n;
-    const u32 k = brev32(p) >> (32 - log_n);
     const u32 mask = (2u << log_n) - 1;
-    const u32 kk = (u32)((g * (u64)(2 * k + 1)) & mask) >> 1;
-    const u32 src = brev32(kk) >> (32 - log_n);
-    out[ro + p] = in[ro + src];
+    const u32 p0 = blockIdx.x * 1024 + threadIdx.x;
+    u64 v[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const u32 k = brev32(p0 + 256 * i) >> (32 - log_n);
+        const u32 kk = (u32)((g * (u64)(2 * k + 1)) & mask) >> 1;
+        v[i] = ld_u64(in + ro + (brev32(kk) >> (32 - log_n)));
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) out[ro + p0 + 256 * i] = v[i];
 }
 
 // signed coefficients [batch][N] -> residues of every row's modulus, rows [batch][limbs]
