@@ -574,7 +574,7 @@ static int binary(int op, fhe_ctx* c, void* stream, uint64_t* out, const uint64_
     so.poly = sa.poly = blk * batch; so.batch = sa.batch = blk;
     sb.batch = b_batch == 1 ? 0 : blk;
     sb.poly = b_npoly == 1 ? 0 : blk * b_batch;
-    dim3 grid(c->n / 256, npoly * batch * rpp), block(256);
+    dim3 grid(c->n / 1024, npoly * batch * rpp), block(256);
     cudaStream_t s = (cudaStream_t)stream;
     if (op == 0) launch(k_binary<0>, grid, block, s, c->T, m, batch, (u64*)out, (const u64*)a, (const u64*)b, so, sa, sb);
     else if (op == 1) launch(k_binary<1>, grid, block, s, c->T, m, batch, (u64*)out, (const u64*)a, (const u64*)b, so, sa, sb);

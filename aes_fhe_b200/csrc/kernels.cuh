@@ -36,17 +36,24 @@ __global__ void __launch_bounds__(256) k_binary(DevTables T, RowMap map, int bat
     const int row = blockIdx.y;
     const int mid = map.mod_id(row);
     const Modulus M = T.mod[mid];
-    const u32 idx = blockIdx.x * 256 + threadIdx.x;
+    // four elements 256 apart per thread, all eight loads issued before the first store (HBM-bound: bytes in flight)
+    const u32 idx = blockIdx.x * 1024 + threadIdx.x;
     const int blk = row / map.rows_per_poly, j = row % map.rows_per_poly;
     const size_t poly = blk / batch, bt = blk % batch;
     const size_t lo = ((size_t)j << map.log_n) + idx;
-    const u64 x = a[poly * sa.poly + bt * sa.batch + lo];
-    const u64 y = b[poly * sb.poly + bt * sb.batch + lo];
-    u64 r;
-    if (OP == 0) r = add_mod(x, y, M.q);
-    else if (OP == 1) r = sub_mod(x, y, M.q);
-    else r = f_to_u64(canon(mulmod_var(u64_to_f(x), u64_to_f(y), M.qd, M.qinv), M.qd));
-    out[poly * so.poly + bt * so.batch + lo] = r;
+    const u64* ap = a + poly * sa.poly + bt * sa.batch + lo;
+    const u64* bp = b + poly * sb.poly + bt * sb.batch + lo;
+    u64 x[4], y[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { x[i] = ld_u64(ap + 256 * i); y[i] = ld_u64(bp + 256 * i); }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        u64 r;
+        if (OP == 0) r = add_mod(x[i], y[i], M.q);
+        else if (OP == 1) r = sub_mod(x[i], y[i], M.q);
+        else r = f_to_u64(canon(mulmod_var(u64_to_f(x[i]), u64_to_f(y[i]), M.qd, M.qinv), M.qd));
+        out[poly * so.poly + bt * so.batch + lo + 256 * i] = r;
+    }
 }
 
 __global__ void __launch_bounds__(256) k_neg(DevTables T, RowMap map, u64* out, const u64* a) {
