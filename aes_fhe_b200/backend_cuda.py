@@ -111,6 +111,18 @@ class CudaBackend:
     def split_batch(self, h, sizes: Sequence[int]):
         return [x.contiguous() for x in torch.split(h, list(sizes), dim=1)]
 
+    def slice_batch(self, h, lo: int, hi: int):
+        return h[:, lo:hi]
+
+    def permute_batch(self, h, idx: Sequence[int]):
+        """batch elements re-ordered / replicated: out[:, i] = h[:, idx[i]] (one device copy)"""
+        key = tuple(idx)
+        cache = self.__dict__.setdefault("_perm_cache", {})
+        t = cache.get(key)
+        if t is None:
+            t = cache[key] = torch.tensor(list(idx), dtype=torch.int64, device=self.device)
+        return h.index_select(1, t)
+
     def mod_raise(self, h, nq_out: int):
         """[p, B, 1, N] at level 0 (NTT) -> [p, B, nq_out, N]: centred lift of the coefficients
         from q_0 to the first nq_out moduli (the overflow polynomial q_0 * I comes with it)."""

@@ -30,6 +30,12 @@ from numpy.polynomial import chebyshev as _cheb
 
 from .engine import BootstrapKey, Ciphertext, FixedRotationKey, Plaintext
 
+# bit bootstrap (bootstrap_bits): the message sits at +-q_0/4, where sin(2 pi x) is flat, so the refresh squares the
+# incoming error and only EvalMod's own error stays.  A double-angle step amplifies an error at the crest of the
+# cosine 4x, so the interpolant has to be accurate to 1e-3 / 4^r: r = 5 with degree 18 (5 levels) is one level
+# cheaper than r = 6 with degree 12..22 (tools/bits_study.py prints the table)
+DOUBLE_ANGLES_BITS = 5
+POLY_DEGREE_BITS = 18
 RHO_TARGET = 32.0         # q_0 / (scaled message): the message is divided by RHO_TARGET * Delta_0 / q_0
 K_NORM = 33               # |I| <= 32 for hamming weight <= 192 (8 sigma)
 DOUBLE_ANGLES = 6
@@ -112,18 +118,19 @@ def _bsgs_split(rots: List[int], n: int):
     return bm, plan
 
 
-def _evalmod_design(rho: float, basis: str = "monomial"):
+def _evalmod_design(rho: float, basis: str = "monomial", r: int = None, degree: int = None):
     """coefficients of alpha_0 cos(2 pi (K_n y - 1/4) / 2^r) on y in [-1, 1] (monomial or
     Chebyshev basis) and the constants alpha_1..alpha_r of the double-angle steps
-    c <- c^2 - alpha."""
-    r = DOUBLE_ANGLES
+    c <- c^2 - alpha.  The final amplitude is rho / 2 pi."""
+    r = DOUBLE_ANGLES if r is None else r
+    degree = POLY_DEGREE if degree is None else degree
     A = 2 * np.pi * K_NORM / 2 ** r
     phi = 2 * np.pi * 0.25 / 2 ** r
     alphas = [rho / (2 * np.pi)]
     for _ in range(r):
         alphas.append(np.sqrt(2 * alphas[-1]))
     alphas = alphas[::-1]                       # alphas[0] scales the base polynomial
-    cheb = _cheb.chebinterpolate(lambda y: alphas[0] * np.cos(A * y - phi), POLY_DEGREE)
+    cheb = _cheb.chebinterpolate(lambda y: alphas[0] * np.cos(A * y - phi), degree)
     return (cheb if basis == "chebyshev" else _cheb.cheb2poly(cheb)), alphas
 
 
@@ -217,6 +224,19 @@ def lincomb_const(engine, cts: Dict[int, Ciphertext], coeffs, const: float = 0.0
     return engine._rescale(Ciphertext(engine, acc, lo))
 
 
+def _ps_depth(degree: int, baby: int = 4) -> int:
+    """levels chebyshev_eval_ps uses for a dense polynomial of this degree (mirrors its recursion: a leaf is one
+    constant-only sum below T_(baby-1), a node is one product with T_n below its quotient)"""
+    def depth(d):
+        if d < baby:
+            return (max(d, 1) - 1).bit_length() + 1 if d >= 1 else 0
+        n = baby
+        while 2 * n <= d:
+            n *= 2
+        return max(max(depth(d - n), (n - 1).bit_length()) + 1, depth(n - 1))
+    return depth(degree)
+
+
 # --------------------------------------------------------------------------- key
 class _Plan:
     pass
@@ -242,8 +262,9 @@ def _materialise(engine, bk: BootstrapKey):
     groups = bk._groups
     groups_stc = getattr(bk, "_groups_stc", groups)
     depth = 1 + groups + 5 + DOUBLE_ANGLES + groups_stc    # extra rescale of the first matrix, EvalMod polynomial (5), the rest
-    if L < depth + 1:
-        raise RuntimeError(f"bootstrapping needs max_level >= {depth + 1}, engine has {L}")
+    depth_bits = 1 + groups + _ps_depth(POLY_DEGREE_BITS) + DOUBLE_ANGLES_BITS
+    if L < min(depth, depth_bits) + 1:
+        raise RuntimeError(f"bootstrapping needs max_level >= {min(depth, depth_bits) + 1}, engine has {L}")
     layers, inv_layers = _fft_layers(n)
     # CoeffToSlot: L_1^-1 ... L_last^-1 with L_last^-1 applied first; fold 1 / (2 K_n)
     cts = _group(list(reversed(inv_layers)), groups, n)
@@ -279,6 +300,10 @@ def _materialise(engine, bk: BootstrapKey):
     plan.shift = max(1.0, RHO_TARGET * float(P.delta[0]) / P.moduli[0])        # message divisor
     plan.rho = plan.shift * float(P.moduli[0] / P.delta[0])
     plan.poly, plan.alphas = _evalmod_design(plan.rho, "chebyshev")
+    # bit bootstrap: message * q_0 / 4 at level 0, unit amplitude out
+    plan.shift_bits = 4.0 * float(P.delta[0]) / P.moduli[0]
+    plan.poly_bits, plan.alphas_bits = _evalmod_design(2.0 * np.pi, "chebyshev", DOUBLE_ANGLES_BITS, POLY_DEGREE_BITS)
+    plan.depth_bits = 1 + groups + _ps_depth(POLY_DEGREE_BITS) + DOUBLE_ANGLES_BITS      # levels above the ModRaise
     bk.plan = plan
     return plan
 
@@ -378,3 +403,61 @@ def bootstrap(engine, ct: Ciphertext, relin_key, conj_key, boot_key: BootstrapKe
     for entry in plan.stc:
         u = _linear_transform(engine, u, entry)
     return u
+
+
+def bootstrap_bits(engine, ct: Ciphertext, relin_key, conj_key, boot_key: BootstrapKey) -> Ciphertext:
+    """Refresh of +-1-valued slots ("bit bootstrap").  ``ct`` [batch B] holds u + i v with u, v real and close to
+    +-1 (two bit planes per ciphertext); the result [batch 2 B: all u, then all v] holds the cleaned values at
+    level  max_level - plan.depth_bits.
+
+    Order of operations (binary-message bootstrapping, Bae-Cheon-Kim-Stehle 2024, with this repo's pieces):
+      0. SlotToCoeff FIRST, at the bottom of the chain (levels groups_stc + 1 -> 1, a few limbs: almost free); the
+         plaintext polynomial then has the coefficients Delta u_k and Delta v_k themselves
+      1. down to level 0 with the message scaled to q_0 / 4, ModRaise: coefficient = q_0 (I + s / 4) + e
+      2. CoeffToSlot, real / imaginary split by one conjugation (stacked on the batch axis)
+      3. EvalMod = sin(2 pi x) with unit amplitude: at x = I +- 1/4 the derivative vanishes, so an input error e
+         comes out as pi^2 e^2 / 8 -- the refresh is also the clean-up -- and the result is already slot-encoded:
+         no SlotToCoeff at the top, no separate clean-up polynomial."""
+    if getattr(boot_key, "small", False) or not hasattr(boot_key, "_sk"):
+        raise RuntimeError("bootstrap needs the key from create_bootstrap_key")
+    if ct.npoly != 2:
+        raise RuntimeError("bootstrap: ciphertext must have 2 polynomials")
+    from fractions import Fraction
+    plan = _materialise(engine, boot_key)
+    for e in plan.cts + plan.stc:
+        e["_keys"] = plan.rot_keys
+    be, P = engine.backend, engine.params
+    L = P.max_level
+    if L < plan.depth_bits + 1:
+        raise RuntimeError(f"bit bootstrapping needs max_level >= {plan.depth_bits + 1}, engine has {L}")
+    engine._count("bootstrap")
+    lvl_in = len(plan.stc) + 1
+    if ct.level < lvl_in:
+        raise RuntimeError(f"bootstrap_bits: {ct.level} levels left, SlotToCoeff and the step to level 0 need {lvl_in}")
+
+    # 0. SlotToCoeff on the lowest limbs.  Dropping limbs is an exact modulus switch: same message, the scale stays
+    # delta[ct.level]; the factor is carried to step 1
+    dev = P.delta[ct.level] / P.delta[lvl_in]
+    u = ct if ct.level == lvl_in else Ciphertext(engine, be.take_limbs(ct.polys, lvl_in + 1, False), lvl_in)
+    for entry in plan.stc:
+        u = _linear_transform(engine, u, entry)                                     # ends at level 1
+
+    # 1. level 0, plaintext coefficient = s * q_0 / 4; ModRaise (declared scale q_0: values I + s / 4)
+    c = P.delta[0] * P.moduli[1] / (P.delta[1] * dev * Fraction(plan.shift_bits))
+    x = engine._rescale(engine._mul_int_const(u, int(round(c)), 0))
+    raised = Ciphertext(engine, be.mod_raise(x.polys, L + 1), L)
+
+    # 2. CoeffToSlot; y = (I + s / 4) / K_n for the first and the second half of the coefficients
+    t = engine._rescale(_linear_transform(engine, raised, plan.cts[0]))
+    for entry in plan.cts[1:]:
+        t = _linear_transform(engine, t, entry)
+    tc = engine.conjugate(t, conj_key)
+    re = engine.add(t, tc)
+    im = engine.multiply_by_i(engine.subtract(t, tc), -1)
+    y = Ciphertext(engine, be.concat_batch([re.polys, im.polys]), t.level)
+
+    # 3. EvalMod with unit amplitude
+    cpoly = chebyshev_eval_ps(engine, relin_key, y, plan.poly_bits)
+    for i in range(DOUBLE_ANGLES_BITS):
+        cpoly = engine.add_plain(engine.multiply(cpoly, cpoly, relin_key), -plan.alphas_bits[i + 1])
+    return cpoly

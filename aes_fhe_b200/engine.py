@@ -807,3 +807,9 @@ class Engine:
         """Refresh the level of a ciphertext (xor_service.py:120-129, :274-277)."""
         from .bootstrap import bootstrap
         return bootstrap(self, ct, relin_key, conj_key, boot_key)
+
+    def bootstrap_bits(self, ct: Ciphertext, relin_key, conj_key, boot_key) -> Ciphertext:
+        """Refresh of a ciphertext whose slots are u + i v with u, v = +-1 (two bit planes): returns the batch
+        [all u, all v] of real ciphertexts, cleaned (aes_fhe_b200/bootstrap.py::bootstrap_bits)."""
+        from .bootstrap import bootstrap_bits
+        return bootstrap_bits(self, ct, relin_key, conj_key, boot_key)

@@ -1,0 +1,349 @@
+"""Bit-sliced homomorphic AES-128 (BASELINE configs 4 and 5): every state bit is a slot value
+s = (-1)^bit, so that
+
+  * XOR is a product (MixColumns + AddRoundKey: three levels, 140 ciphertext products per 32 state bits),
+  * the S-box is eight multilinear polynomials  out_k = sum_{A,B} w_k[A,B] m_A(hi) m_B(lo)  over the 16 x 16
+    monomials of the high / low four input bits (its Walsh-Hadamard spectrum) -- the same bivariate
+    baby-step/giant-step shape as the reference's 16 x 16 zeta_16 XOR table
+    (/root/reference/xor_service.py:271-286), evaluated by the same fused schedule (aes_fhe_b200/fused.py:
+    constant-only inner sums in one pass, lazily relinearised outer sums): 22 + 8 key switches, four levels,
+    first-order error gain <= 8 (every partial derivative of a multilinear +-1 function is in {-1, 0, 1}),
+  * the once-per-round refresh is the *bit bootstrap* of aes_fhe_b200/bootstrap.py (``bootstrap_bits``):
+    SlotToCoeff at the bottom of the chain, ModRaise with the bits at +- q_0 / 4, CoeffToSlot, and
+    EvalMod = sin(2 pi x) whose derivative vanishes exactly there -- the refresh squares the incoming
+    error, so no separate clean-up polynomial is needed, and two real ciphertexts share one bootstrap
+    (real and imaginary part).
+
+This replaces the zeta_16 nibble-pair pipeline of services/aes128.py (116 refreshed ciphertexts per
+2048 blocks, 5-level LUT layers with error gain 18) for the AES-128 throughput path; the reference's
+round functions (new.py:186-227, test_all_process.py:21-48) define *what* is computed -- ARK, SubBytes,
+ShiftRows, MixColumns on 16-byte states in FIPS order -- and FIPS-197 is the ground truth.
+
+Layout.  One *state* is 32 ciphertexts (bit k = 0..7 of the byte in state row r = 0..3), each packing the four
+columns of slot_count / 4 blocks: slot = c * Bs + b for column c of block b (Bs = 8192 at N = 2^16), i.e.
+FIPS byte i = 4 c + r of block b sits in ciphertext (k, r), slot c * Bs + b.  ShiftRows then is a pure
+rotation of ciphertext (k, r) by r columns -- no masks, no level -- and MixColumns a slot-wise product of
+the four row ciphertexts.  G states ride together on the batch axis: batch index = (k * 4 + r) * G + g.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from ..engine import Ciphertext
+from ..fused import _outer_sum
+from . import lut
+from .key_expansion import expand_key
+
+# xtime on bit planes: (2 t)_k = t_(k-1) ^ (t_7 if k in {0, 1, 3, 4}), FIPS-197 section 4.2.1 (0x1b = bits 0, 1, 3, 4)
+_XT_WITH_T7 = (1, 3, 4)
+
+
+# --------------------------------------------------------------------------- plain bit algebra
+def bits_pm(x) -> np.ndarray:
+    """integer array [...] -> float64 [8, ...] with (-1)^(bit k of x)"""
+    x = np.asarray(x).astype(np.int64)
+    return np.stack([1.0 - 2.0 * ((x >> k) & 1) for k in range(8)])
+
+
+def from_pm(s: np.ndarray) -> np.ndarray:
+    """[8, ...] (approximately +-1) -> uint8 [...]"""
+    out = np.zeros(s.shape[1:], dtype=np.uint8)
+    for k in range(8):
+        out |= ((np.real(s[k]) < 0).astype(np.uint8) << k)
+    return out
+
+
+def monomials(s4: np.ndarray) -> np.ndarray:
+    """[4, ...] -> [16, ...]: entry A = prod_{j in A} s4[j] (A a 4-bit subset mask; A = 0 is the constant 1)"""
+    out = [np.ones_like(s4[0])]
+    for a in range(1, 16):
+        j = a.bit_length() - 1
+        out.append(out[a ^ (1 << j)] * s4[j])
+    return np.stack(out)
+
+
+_WALSH = None
+
+
+def sbox_walsh() -> np.ndarray:
+    """W[k, A, B]: (-1)^(bit k of S(x)) = sum_{A,B} W[k,A,B] m_A(bits 4..7 of x) m_B(bits 0..3 of x).
+    The Walsh-Hadamard spectrum of the AES S-box (FIPS-197 5.1.1), derived from the definition."""
+    global _WALSH
+    if _WALSH is None:
+        x = np.arange(256)
+        s = bits_pm(x)
+        chi = np.einsum("ax,bx->abx", monomials(s[4:]), monomials(s[:4]))          # [16,16,256] characters
+        f = bits_pm(lut.AES_SBOX[x])                                                 # [8,256]
+        _WALSH = np.einsum("kx,abx->kab", f, chi) / 256.0
+    return _WALSH
+
+
+class PlainBits:
+    """The schedule on plain float arrays [8, 4, 4 * nb] (bit, row, column-major slots): the model the
+    ciphertext code is tested against (tests/test_aes_bits.py) and the noise study (tools/bits_study.py)."""
+
+    @staticmethod
+    def from_blocks(blocks: np.ndarray) -> np.ndarray:
+        b = np.asarray(blocks, dtype=np.uint8).reshape(-1, 4, 4)            # [nb, c, r]
+        return bits_pm(b.transpose(2, 1, 0).reshape(4, -1))                 # [8, r, c * nb + b]
+
+    @staticmethod
+    def from_key(rk16, nb: int) -> np.ndarray:
+        return PlainBits.from_blocks(np.tile(np.asarray(rk16, dtype=np.uint8).reshape(1, 16), (nb, 1)))
+
+    @staticmethod
+    def to_blocks(st: np.ndarray) -> np.ndarray:
+        by = from_pm(st)                                                    # [4(r), 4 nb]
+        nb = by.shape[1] // 4
+        return by.reshape(4, 4, nb).transpose(2, 1, 0).reshape(nb, 16)
+
+    @staticmethod
+    def xor(a, b):
+        return a * b
+
+    @staticmethod
+    def shift_rows(st):
+        nb = st.shape[2] // 4
+        return np.stack([np.roll(st[:, r], -r * nb, axis=-1) for r in range(4)], axis=1)
+
+    @staticmethod
+    def sub_bytes(st, W=None):
+        W = sbox_walsh() if W is None else W
+        return np.einsum("kab,a...,b...->k...", W, monomials(st[4:]), monomials(st[:4]))
+
+    @staticmethod
+    def mix_ark(a, key, last: bool = False):
+        """MixColumns + AddRoundKey (AddRoundKey only when `last`): products in the order the ciphertext code uses"""
+        if last:
+            return a * key
+        rr = lambda v, j: np.roll(v, -j, axis=1)                            # noqa: E731  row r <- row r + j
+        t = a * rr(a, 1)
+        u = rr(t, 1) * (rr(a, 3) * key)
+        xt = np.empty_like(t)
+        xt[0] = t[7]
+        for k in range(1, 8):
+            xt[k] = t[k - 1] * t[7] if k in _XT_WITH_T7 else t[k - 1]
+        return xt * u
+
+
+# --------------------------------------------------------------------------- ciphertext service
+class AESBitService:
+    SBOX_LEVELS = 4             # monomials (2) + constant inner sums and outer products (2)
+    MIX_LEVELS = 3
+    ARK_LEVELS = 1
+
+    def __init__(self, eng_wrap, boot_groups: Tuple[int, int] = (3, 3), boot_key=None):
+        self.eng = eng_wrap
+        self.engine = eng_wrap.engine
+        self.sc = self.engine.slot_count
+        self.Bs = self.sc // 4                      # blocks per state
+        self.W = sbox_walsh()
+        self._rot_keys: Dict[int, object] = {}
+        self.boot_key = boot_key if boot_key is not None else \
+            self.engine.create_bootstrap_key(eng_wrap.secret_key, boot_groups[0], boot_groups[1])
+        self.boot_in_levels = boot_groups[1] + 1    # SlotToCoeff transforms + the step down to level 0
+        self.refreshes = 0                          # complex ciphertexts bootstrapped (two state bits each)
+        self.stage_ms: Optional[Dict[str, float]] = None      # filled when `timer` is set
+        self.timer = None
+
+    # ------------------------------------------------------------------ batch-axis plumbing
+    def _G(self, ct: Ciphertext) -> int:
+        if ct.batch % 32:
+            raise ValueError("state ciphertexts carry 32 * G batch elements")
+        return ct.batch // 32
+
+    def _take(self, ct: Ciphertext, idx: Sequence[int]) -> Ciphertext:
+        return Ciphertext(self.engine, self.engine.backend.permute_batch(ct.polys, list(idx)), ct.level)
+
+    def _slice(self, ct: Ciphertext, lo: int, hi: int) -> Ciphertext:
+        return Ciphertext(self.engine, self.engine.backend.slice_batch(ct.polys, lo, hi), ct.level)
+
+    def _cat(self, cts: Sequence[Ciphertext]) -> Ciphertext:
+        e = self.engine
+        lvl = min(c.level for c in cts)
+        cts = [e.level_down(c, lvl) for c in cts]
+        return Ciphertext(e, e.backend.concat_batch([c.polys for c in cts]), lvl)
+
+    @staticmethod
+    def _row_roll_index(G: int, j: int, nk: int = 8) -> List[int]:
+        """batch permutation: (k, r, g) <- (k, (r + j) % 4, g)"""
+        return [(k * 4 + (r + j) % 4) * G + g for k in range(nk) for r in range(4) for g in range(G)]
+
+    # ------------------------------------------------------------------ packing (client side)
+    def pack_bits(self, blocks: np.ndarray) -> np.ndarray:
+        """blocks [G * Bs (or fewer), 16] bytes -> uint8 bit planes [32 * G, slot_count], row (k * 4 + r) * G + g,
+        slot c * Bs + b; unused block slots hold zero bytes"""
+        blocks = np.asarray(blocks, dtype=np.uint8).reshape(-1, 16)
+        G = max(1, -(-blocks.shape[0] // self.Bs))
+        full = np.zeros((G * self.Bs, 16), dtype=np.uint8)
+        full[:blocks.shape[0]] = blocks
+        by = full.reshape(G, self.Bs, 4, 4).transpose(3, 0, 2, 1).reshape(4, G, self.sc)     # [r, g, c * Bs + b]
+        planes = np.stack([(by >> k) & 1 for k in range(8)])                                  # [k, r, g, slot]
+        return planes.reshape(32 * G, self.sc)
+
+    def unpack_bits(self, planes: np.ndarray, nb: Optional[int] = None) -> np.ndarray:
+        planes = np.asarray(planes, dtype=np.uint8)
+        G = planes.shape[0] // 32
+        p = planes.reshape(8, 4, G, 4, self.Bs)
+        by = np.zeros((4, G, 4, self.Bs), dtype=np.uint8)
+        for k in range(8):
+            by |= p[k] << k
+        out = by.transpose(1, 3, 2, 0).reshape(G * self.Bs, 16)                               # [g, b, c, r]
+        return out if nb is None else out[:nb]
+
+    def encrypt_state(self, blocks: np.ndarray, level: Optional[int] = None) -> Ciphertext:
+        planes = self.pack_bits(blocks)
+        return self.engine.encrypt_zeta(planes, self.eng.public_key, 2, level=level)
+
+    def encrypt_round_key(self, rk16, G: int = 1, level: Optional[int] = None) -> Ciphertext:
+        """one 16-byte round key replicated over every block slot and over the G states of a batch"""
+        rk = np.tile(np.asarray(rk16, dtype=np.uint8).reshape(1, 16), (self.Bs, 1))
+        ct = self.engine.encrypt_zeta(self.pack_bits(rk), self.eng.public_key, 2, level=level)
+        if G > 1:
+            ct = self._take(ct, [i for i in range(32) for _ in range(G)])
+        return ct
+
+    def decrypt_state(self, ct: Ciphertext, nb: Optional[int] = None) -> np.ndarray:
+        planes = np.atleast_2d(self.engine.decrypt_zeta(ct, self.eng.secret_key, 2))
+        return self.unpack_bits(planes, nb)
+
+    def decrypt_slots(self, ct: Ciphertext) -> np.ndarray:
+        return np.atleast_2d(self.eng.decrypt(ct))
+
+    # ------------------------------------------------------------------ stages
+    def _tick(self, name: str):
+        if self.timer is not None:
+            self.timer(name)
+
+    def add_round_key(self, state: Ciphertext, key: Ciphertext) -> Ciphertext:
+        out = self.engine.multiply(state, key, self.eng.relin_key)
+        self._tick("add_round_key")
+        return out
+
+    def _rot_key(self, r: int):
+        key = self._rot_keys.get(r)
+        if key is None:
+            key = self.engine.create_fixed_rotation_key(self.eng.secret_key, -r * self.Bs)
+            self._rot_keys[r] = key
+        return key
+
+    def shift_rows(self, state: Ciphertext) -> Ciphertext:
+        """row r of every bit plane rotated left by r columns (three batched rotations, no level)"""
+        G = self._G(state)
+        rows = [[(k * 4 + r) * G + g for k in range(8) for g in range(G)] for r in range(4)]
+        parts = [self._take(state, rows[0])]
+        for r in (1, 2, 3):
+            parts.append(self.engine.rotate(self._take(state, rows[r]), self._rot_key(r)))
+        inv = [0] * (32 * G)
+        for r in range(4):
+            for pos, i in enumerate(rows[r]):
+                inv[i] = r * 8 * G + pos
+        out = self._take(self._cat(parts), inv)
+        self._tick("shift_rows")
+        return out
+
+    def _monomial_basis(self, bits: List[Ciphertext]) -> Dict[int, Ciphertext]:
+        """{A: prod_{j in A} bits[j]} for the 15 non-empty subsets A of four +-1 ciphertexts (any batch): the 6 pair
+        products in one batched multiply, then the 4 triples (pair x single) and the quadruple (pair x pair) in
+        another -- 11 key switches per batch element, depth 2."""
+        e, rlk = self.engine, self.eng.relin_key
+        bt = bits[0].batch
+        pairs = [(0, 1), (0, 2), (0, 3), (1, 2), (1, 3), (2, 3)]
+        pp = e.multiply(self._cat([bits[i] for i, _ in pairs]), self._cat([bits[j] for _, j in pairs]), rlk)
+        mono = {1 << j: bits[j] for j in range(4)}
+        for n, (i, j) in enumerate(pairs):
+            mono[(1 << i) | (1 << j)] = self._slice(pp, n * bt, (n + 1) * bt)
+        low = [e.level_down(b, pp.level) for b in bits]
+        second = [(0b0111, mono[0b0011], low[2]), (0b1011, mono[0b0011], low[3]), (0b1101, mono[0b1100], low[0]),
+                  (0b1110, mono[0b1100], low[1]), (0b1111, mono[0b0011], mono[0b1100])]
+        qq = e.multiply(self._cat([a for _, a, _ in second]), self._cat([b for _, _, b in second]), rlk)
+        for n, (m, _, _) in enumerate(second):
+            mono[m] = self._slice(qq, n * bt, (n + 1) * bt)
+        return mono
+
+    def sub_bytes(self, state: Ciphertext) -> Ciphertext:
+        """the S-box on every byte of the state: eight multilinear polynomials over the monomials of the high and
+        the low four bits (22 + 8 key switches per (row, state), four levels)"""
+        G = self._G(state)
+        bits = [self._slice(state, k * 4 * G, (k + 1) * 4 * G) for k in range(8)]
+        lo, hi = self._monomial_basis(bits[:4]), self._monomial_basis(bits[4:])
+        outs = _outer_sum(self.engine, self.eng.relin_key, hi, lo, [self.W[k] for k in range(8)], ("sbox-bits",))
+        out = self._cat(outs)
+        self._tick("sub_bytes")
+        return out
+
+    def mix_columns_ark(self, a: Ciphertext, key: Ciphertext) -> Ciphertext:
+        """MixColumns + AddRoundKey on a state that has been through ShiftRows and SubBytes:
+            out_r = 2 a_r ^ 3 a_(r+1) ^ a_(r+2) ^ a_(r+3) ^ k_r = xtime(t_r) ^ t_(r+1) ^ a_(r+3) ^ k_r,   t_r = a_r ^ a_(r+1)
+        as +-1 products: t (32), a_(r+3) k (32), t_(r+1) (a_(r+3) k) (32), the three xtime bits that take t_7 (12),
+        and the final product (32): 140 key switches per state, three levels."""
+        e, rlk = self.engine, self.eng.relin_key
+        G = self._G(a)
+        key = e.level_down(key, a.level) if key.level > a.level else key
+        a1 = self._take(a, self._row_roll_index(G, 1))
+        a3 = self._take(a, self._row_roll_index(G, 3))
+        both = e.multiply(self._cat([a, a3]), self._cat([a1, key]), rlk)             # t | a_(r+3) k
+        t, ka = self._slice(both, 0, 32 * G), self._slice(both, 32 * G, 64 * G)
+        tk = lambda k: self._slice(t, k * 4 * G, (k + 1) * 4 * G)                    # noqa: E731
+        t7 = tk(7)
+        lhs = self._cat([self._take(t, self._row_roll_index(G, 1))] + [tk(k - 1) for k in _XT_WITH_T7])
+        rhs = self._cat([ka] + [t7] * len(_XT_WITH_T7))
+        second = e.multiply(lhs, rhs, rlk)                                           # u | xtime bits 1, 3, 4
+        u = self._slice(second, 0, 32 * G)
+        xt7 = {k: self._slice(second, (32 + 4 * n) * G, (36 + 4 * n) * G) for n, k in enumerate(_XT_WITH_T7)}
+        plain_bits = [k for k in range(8) if k not in _XT_WITH_T7]                   # xtime bits that are a plain shift
+        src = self._cat([t7 if k == 0 else tk(k - 1) for k in plain_bits])
+        src = e.level_down(src, second.level)
+        parts = []
+        for k in range(8):
+            if k in xt7:
+                parts.append(xt7[k])
+            else:
+                n = plain_bits.index(k)
+                parts.append(self._slice(src, n * 4 * G, (n + 1) * 4 * G))
+        out = e.multiply(self._cat(parts), u, rlk)
+        self._tick("mix_columns_ark")
+        return out
+
+    # ------------------------------------------------------------------ refresh and chained rounds
+    def refresh(self, state: Ciphertext) -> Ciphertext:
+        """bit bootstrap of a whole state: bit planes k and k + 4 travel as real and imaginary part"""
+        e = self.engine
+        G = self._G(state)
+        half = 16 * G
+        re, im = self._slice(state, 0, half), self._slice(state, half, 2 * half)
+        packed = e.add(re, e.multiply_by_i(im, 1))
+        out = e.bootstrap_bits(packed, self.eng.relin_key, self.eng.conj_key, self.boot_key)
+        self.refreshes += half
+        self._tick("refresh")
+        return out
+
+    def round_levels(self, last: bool) -> int:
+        return self.SBOX_LEVELS + (self.ARK_LEVELS if last else self.MIX_LEVELS)
+
+    def encrypt_blocks(self, state: Ciphertext, key16, rounds: int = 10, round_keys: Optional[Sequence[Ciphertext]] = None):
+        """AES-128 (or its first `rounds` rounds) on an encrypted state; the round keys come from the clear
+        FIPS-197 key schedule (key_expansion.py) and are encrypted once each unless `round_keys` holds them.
+        A round is ShiftRows (moved in front of SubBytes: they commute), [refresh], SubBytes,
+        MixColumns + AddRoundKey; the refresh happens only when the levels left would not carry the round and
+        the entry of the next bootstrap."""
+        G = self._G(state)
+        if round_keys is None:
+            rks = expand_key(bytes(key16))
+            round_keys = [self.encrypt_round_key(rks[r], G) for r in range(rounds + 1)]
+        st = self.add_round_key(state, round_keys[0])
+        for r in range(1, rounds + 1):
+            last = (r == 10)
+            need = self.round_levels(last) + (0 if r == rounds else self.boot_in_levels)
+            st = self.shift_rows(st)
+            if st.level < need:
+                if st.level < self.boot_in_levels:
+                    raise RuntimeError(f"round {r}: {st.level} levels left, the bit bootstrap needs {self.boot_in_levels}")
+                st = self.refresh(st)
+                if st.level < need:
+                    raise RuntimeError(f"refresh leaves {st.level} levels, a round needs {need}: raise max_level")
+            st = self.sub_bytes(st)
+            st = self.add_round_key(st, round_keys[r]) if last else self.mix_columns_ark(st, round_keys[r])
+        return st

@@ -109,6 +109,12 @@ class RefBackend:
             o += s
         return out
 
+    def slice_batch(self, h, lo: int, hi: int):
+        return np.ascontiguousarray(h[:, lo:hi])
+
+    def permute_batch(self, h, idx: Sequence[int]):
+        return np.ascontiguousarray(h[:, np.asarray(idx, dtype=np.int64)])
+
     def mod_raise(self, h, nq_out: int):
         coef = self.intt(h, 1, 0)                                   # [p, B, 1, N] coefficients mod q0
         q0 = self.params.moduli[0]

@@ -1,0 +1,147 @@
+"""Bit-sliced AES-128 (aes_fhe_b200/services/aes_bits.py) on the CPU oracle at small rings: every stage
+against the plain +-1 model and plain AES, the bit bootstrap, and chained rounds.  The full-size run
+(N = 2^16, ten rounds) is in test_gpu_aes.py."""
+import numpy as np
+import pytest
+
+from aes_fhe_b200 import bootstrap as B
+from aes_fhe_b200.params import make_params
+from aes_fhe_b200.services import aes_bits as AB
+from aes_fhe_b200.services.key_expansion import expand_key
+from aes_fhe_b200.services.xor_service import EngineWrapper, XORConfig
+from oracle import aes_plain as A
+
+KEY_B = bytes.fromhex("2b7e151628aed2a6abf7158809cf4f3c")
+PT_B = bytes.fromhex("3243f6a8885a308d313198a2e0370734")
+
+
+def make_service(backend, P, seed=2, **kw):
+    w = EngineWrapper(XORConfig(), _engine_kwargs=dict(_params=P, _backend=backend, seed=seed), rotation_steps=[])
+    return w, AB.AESBitService(w, **kw)
+
+
+def test_walsh_form_of_the_sbox_is_exact_and_multilinear():
+    W = AB.sbox_walsh()
+    x = np.arange(256)
+    s = AB.bits_pm(x)
+    out = np.einsum("kab,ax,bx->kx", W, AB.monomials(s[4:]), AB.monomials(s[:4]))
+    assert np.abs(out - AB.bits_pm(A.SBOX[x])).max() < 1e-12
+    assert np.allclose(np.abs(W).sum(axis=(1, 2)), 13.5)           # sum |w| of every output bit
+
+
+def test_plain_bit_model_is_aes128():
+    rng = np.random.default_rng(1)
+    blocks = rng.integers(0, 256, (64, 16), dtype=np.uint8)
+    blocks[0] = np.frombuffer(PT_B, np.uint8)
+    rks = A.key_schedule(KEY_B)
+    st = AB.PlainBits.xor(AB.PlainBits.from_blocks(blocks), AB.PlainBits.from_key(rks[0], 64))
+    for r in range(1, 11):
+        st = AB.PlainBits.sub_bytes(AB.PlainBits.shift_rows(st))
+        st = AB.PlainBits.mix_ark(st, AB.PlainBits.from_key(rks[r], 64), last=(r == 10))
+    got = AB.PlainBits.to_blocks(st)
+    assert np.array_equal(got, A.encrypt_blocks(blocks, KEY_B))
+    assert got[0].tobytes().hex() == "3925841d02dc09fbdc118597196a0b32"          # FIPS-197 Appendix B
+
+
+def test_pack_unpack_round_trip_and_layout():
+    class _E:                                                            # just enough engine for the packing
+        slot_count = 512
+    svc = AB.AESBitService.__new__(AB.AESBitService)
+    svc.sc, svc.Bs = 512, 128
+    rng = np.random.default_rng(0)
+    blocks = rng.integers(0, 256, (2 * 128, 16), dtype=np.uint8)
+    planes = svc.pack_bits(blocks)
+    assert planes.shape == (64, 512)
+    assert np.array_equal(svc.unpack_bits(planes), blocks)
+    # bit k of FIPS byte 4 c + r of block b of state g: row (k * 4 + r) * G + g, slot c * Bs + b
+    k, r, g, c, b = 5, 2, 1, 3, 17
+    assert planes[(k * 4 + r) * 2 + g, c * 128 + b] == (blocks[g * 128 + b, 4 * c + r] >> k) & 1
+    assert np.array_equal(svc.unpack_bits(svc.pack_bits(blocks[:100]), nb=100), blocks[:100])     # ragged
+
+
+def test_round_stages_on_oracle(ref_backend_cls):
+    """ARK_0, ShiftRows, SubBytes, MixColumns + ARK of round 1 on two states, each stage against plain AES and
+    the slot error against the +-1 model; then the last-round form (no MixColumns)."""
+    P = make_params(10, 9, scale_bits=44)
+    w, svc = make_service(ref_backend_cls(P), P, boot_key=object())
+    rng = np.random.default_rng(3)
+    G = 2
+    blocks = rng.integers(0, 256, (G * svc.Bs, 16), dtype=np.uint8)
+    blocks[0] = np.frombuffer(PT_B, np.uint8)
+    rks = expand_key(KEY_B)
+    k0, k1 = svc.encrypt_round_key(rks[0], G), svc.encrypt_round_key(rks[1], G)
+    st = svc.add_round_key(svc.encrypt_state(blocks), k0)
+    assert st.level == 8 and np.array_equal(svc.decrypt_state(st), blocks ^ rks[0])
+    st = svc.shift_rows(st)
+    want = A.shift_rows(blocks ^ rks[0])
+    assert st.level == 8 and np.array_equal(svc.decrypt_state(st), want)
+    st = svc.sub_bytes(st)
+    want = A.sub_bytes(want)
+    assert st.level == 8 - svc.SBOX_LEVELS and np.array_equal(svc.decrypt_state(st), want)
+    assert np.abs(svc.decrypt_slots(st) - (1.0 - 2.0 * svc.pack_bits(want))).max() < 1e-6
+    last = svc.add_round_key(st, k1)
+    assert np.array_equal(svc.decrypt_state(last), want ^ rks[1])
+    st = svc.mix_columns_ark(st, k1)
+    want = A.mix_columns(want) ^ rks[1]
+    assert st.level == 8 - svc.SBOX_LEVELS - svc.MIX_LEVELS and np.array_equal(svc.decrypt_state(st), want)
+    assert svc.decrypt_state(st)[0].tobytes().hex() == "a49c7ff2689f352b6b5bea43026a5049"       # FIPS-197 App. B, round 2 input
+    assert np.abs(svc.decrypt_slots(st) - (1.0 - 2.0 * svc.pack_bits(want))).max() < 1e-5
+    # 1 + 22 + 8 + 140 products per state, 3 batched rotations
+    n = w.engine.op_counts
+    assert n["keyswitch_galois"] == 3 and n["mul_ct"] == 1 + 4 + 1 + 3          # batched calls
+
+
+def test_evalmod_design_for_bits_is_flat_at_the_bits():
+    """sin(2 pi x) by the degree-18 interpolant + 5 double-angle steps: exact at x = I +- 1/4 to 1e-4, and an
+    input error e comes out as pi^2 e^2 / 8"""
+    poly, alphas = B._evalmod_design(2 * np.pi, "monomial", B.DOUBLE_ANGLES_BITS, B.POLY_DEGREE_BITS)
+    rng = np.random.default_rng(0)
+    I = rng.integers(-(B.K_NORM - 1), B.K_NORM, 40000)
+    s = rng.choice([-1.0, 1.0], I.size)
+
+    def f(e):
+        c = np.polynomial.polynomial.polyval((I + (s + e) / 4) / B.K_NORM, poly)
+        for i in range(B.DOUBLE_ANGLES_BITS):
+            c = c * c - alphas[i + 1]
+        return c
+
+    assert np.abs(f(0.0) - s).max() < 1e-4
+    e = rng.normal(0, 0.02, I.size)
+    assert np.abs(f(e) - s * (1 - np.pi ** 2 * e ** 2 / 8)).max() < 2e-4
+
+
+@pytest.mark.parametrize("log_n", [11])
+def test_bit_bootstrap_on_oracle(log_n, ref_backend_cls):
+    P = make_params(log_n, 20, scale_bits=44)
+    w, svc = make_service(ref_backend_cls(P), P)
+    eng = w.engine
+    rng = np.random.default_rng(5)
+    u = rng.choice([-1.0, 1.0], (2, eng.slot_count))
+    v = rng.choice([-1.0, 1.0], (2, eng.slot_count))
+    noise = rng.normal(0, 0.005, (2, 2, eng.slot_count))
+    ct = eng.encrypt((u + noise[0]) + 1j * (v + noise[1]), w.public_key, level=svc.boot_in_levels + 1)
+    out = eng.bootstrap_bits(ct, w.relin_key, w.conj_key, svc.boot_key)
+    plan = svc.boot_key.plan
+    assert out.batch == 4 and out.level == 20 - plan.depth_bits
+    got = eng.decrypt(out, w.secret_key)
+    err = np.abs(got - np.concatenate([u, v])).max()
+    assert err < 1e-3, err                      # input error 5e-3 rms (2e-2 max) came out squared: pi^2 e^2 / 8
+
+
+def test_two_rounds_with_refresh_on_oracle(ref_backend_cls):
+    P = make_params(11, 25, scale_bits=44)          # 14 (bit bootstrap) + 7 (round) + 4 (entry of the next bootstrap)
+    w, svc = make_service(ref_backend_cls(P), P)
+    rng = np.random.default_rng(7)
+    blocks = rng.integers(0, 256, (svc.Bs, 16), dtype=np.uint8)
+    blocks[0] = np.frombuffer(PT_B, np.uint8)
+    rks = expand_key(KEY_B)
+    st = svc.encrypt_state(blocks, level=1 + svc.boot_in_levels)
+    out = svc.encrypt_blocks(st, KEY_B, rounds=2)
+    s = blocks ^ rks[0]
+    for r in (1, 2):
+        s = A.round_fn(s, rks[r])
+    got = svc.decrypt_state(out)
+    assert np.array_equal(got, s)
+    assert got[0].tobytes().hex() == "aa8f5f0361dde3ef82d24ad26832469a"      # FIPS-197 App. B, start of round 3
+    assert w.engine.op_counts["bootstrap"] == 2 and svc.refreshes == 32
+    assert np.abs(svc.decrypt_slots(out) - (1.0 - 2.0 * svc.pack_bits(s))).max() < 1e-3
