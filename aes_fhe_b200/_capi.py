@@ -22,6 +22,7 @@ SIGNATURES = {
     "fhe_ctx_destroy": [_P],
     "fhe_last_error": [],
     "fhe_launch_count": [],
+    "fhe_ntt_row_count": [],
     "fhe_set_ntt_fused": [_P, _I],
     "fhe_ntt_fused_status": [_P],
     "fhe_ntt_fwd": [_P, _P, _P, _I, _I, _I],
@@ -51,7 +52,7 @@ SIGNATURES = {
     "fhe_from_i64": [_P, _P, _P, _P, _I, _I, _I],
     "fhe_crt_centered": [_P, _P, _P, _P, _I, _I],
 }
-_RESTYPES = {"fhe_ctx_destroy": None, "fhe_last_error": C.c_char_p, "fhe_launch_count": _U64}
+_RESTYPES = {"fhe_ctx_destroy": None, "fhe_last_error": C.c_char_p, "fhe_launch_count": _U64, "fhe_ntt_row_count": _U64}
 
 
 class FheError(RuntimeError):

@@ -70,6 +70,9 @@ class CudaBackend:
     def launch_count(self) -> int:
         return int(self.lib.fhe_launch_count())
 
+    def ntt_row_count(self) -> int:
+        return int(self.lib.fhe_ntt_row_count())
+
     # ---- layout helpers
     def npoly(self, h) -> int:
         return h.shape[0]

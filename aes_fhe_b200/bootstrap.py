@@ -256,13 +256,16 @@ def make_bootstrap_key(engine, sk, groups: int = 3, groups_stc: Optional[int] = 
 def _materialise(engine, bk: BootstrapKey):
     if bk.plan is not None:
         return bk.plan
+    if engine.secret_hamming_weight <= 0:
+        raise RuntimeError("bootstrapping needs the sparse secret: construct the engine with use_bootstrap=True "
+                           "(a uniform ternary secret makes the ModRaise overflow |I| ~ sqrt(N), not <= 32)")
     P = engine.params
     n = engine.slot_count
     L = P.max_level
     groups = bk._groups
     groups_stc = getattr(bk, "_groups_stc", groups)
     depth = 1 + groups + 5 + DOUBLE_ANGLES + groups_stc    # extra rescale of the first matrix, EvalMod polynomial (5), the rest
-    depth_bits = 1 + groups + _ps_depth(POLY_DEGREE_BITS) + DOUBLE_ANGLES_BITS
+    depth_bits = groups + _ps_depth(POLY_DEGREE_BITS) + DOUBLE_ANGLES_BITS
     if L < min(depth, depth_bits) + 1:
         raise RuntimeError(f"bootstrapping needs max_level >= {min(depth, depth_bits) + 1}, engine has {L}")
     layers, inv_layers = _fft_layers(n)
@@ -295,6 +298,9 @@ def _materialise(engine, bk: BootstrapKey):
     first_scale = lambda lvl: P.delta[lvl - 2] * P.moduli[lvl] * P.moduli[lvl - 1] / P.moduli[0]      # noqa: E731
     for gi, m in enumerate(cts):
         plan.cts.append(prepare(m, first_scale if gi == 0 else None))
+    # bit bootstrap: everything in front of EvalMod comes out squared, so its first matrix needs no extra precision:
+    # one rescale (plaintext scale Delta q / q_0), one level saved
+    plan.cts_bits0 = prepare(cts[0], lambda lvl: P.delta[lvl - 1] * P.moduli[lvl] / P.moduli[0])
     for m in stc:
         plan.stc.append(prepare(m))
     plan.shift = max(1.0, RHO_TARGET * float(P.delta[0]) / P.moduli[0])        # message divisor
@@ -303,7 +309,7 @@ def _materialise(engine, bk: BootstrapKey):
     # bit bootstrap: message * q_0 / 4 at level 0, unit amplitude out
     plan.shift_bits = 4.0 * float(P.delta[0]) / P.moduli[0]
     plan.poly_bits, plan.alphas_bits = _evalmod_design(2.0 * np.pi, "chebyshev", DOUBLE_ANGLES_BITS, POLY_DEGREE_BITS)
-    plan.depth_bits = 1 + groups + _ps_depth(POLY_DEGREE_BITS) + DOUBLE_ANGLES_BITS      # levels above the ModRaise
+    plan.depth_bits = groups + _ps_depth(POLY_DEGREE_BITS) + DOUBLE_ANGLES_BITS          # levels above the ModRaise
     bk.plan = plan
     return plan
 
@@ -424,7 +430,7 @@ def bootstrap_bits(engine, ct: Ciphertext, relin_key, conj_key, boot_key: Bootst
         raise RuntimeError("bootstrap: ciphertext must have 2 polynomials")
     from fractions import Fraction
     plan = _materialise(engine, boot_key)
-    for e in plan.cts + plan.stc:
+    for e in plan.cts + plan.stc + [plan.cts_bits0]:
         e["_keys"] = plan.rot_keys
     be, P = engine.backend, engine.params
     L = P.max_level
@@ -448,7 +454,7 @@ def bootstrap_bits(engine, ct: Ciphertext, relin_key, conj_key, boot_key: Bootst
     raised = Ciphertext(engine, be.mod_raise(x.polys, L + 1), L)
 
     # 2. CoeffToSlot; y = (I + s / 4) / K_n for the first and the second half of the coefficients
-    t = engine._rescale(_linear_transform(engine, raised, plan.cts[0]))
+    t = _linear_transform(engine, raised, plan.cts_bits0)
     for entry in plan.cts[1:]:
         t = _linear_transform(engine, t, entry)
     tc = engine.conjugate(t, conj_key)

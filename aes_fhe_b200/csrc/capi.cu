@@ -16,6 +16,7 @@ typedef unsigned __int128 u128;
 
 static thread_local std::string g_err;
 static std::atomic<uint64_t> g_launches(0);
+static std::atomic<uint64_t> g_ntt_rows(0);          // length-N transforms (forward + inverse) launched since load
 
 namespace {
 
@@ -117,11 +118,13 @@ inline void launch(void (*k)(KArgs...), dim3 g, dim3 b, cudaStream_t s, Args&&..
 
 template <class LoadOp, class StoreOp>
 inline void ntt_fwd(fhe_ctx* c, const RowMap& m, int rows, LoadOp ld, u64* work, long long ws, StoreOp st, cudaStream_t s) {
+    g_ntt_rows.fetch_add((uint64_t)rows, std::memory_order_relaxed);
     g_launches.fetch_add(ntt_forward_auto(c->T, c->fz, m, rows, ld, work, ws, st, s), std::memory_order_relaxed);
 }
 template <class LoadOp, class StoreOp>
 inline void ntt_inv(fhe_ctx* c, const RowMap& m, int rows, LoadOp ld, u64* work, long long ws, StoreOp st,
                     const ConstF* scale, cudaStream_t s) {
+    g_ntt_rows.fetch_add((uint64_t)rows, std::memory_order_relaxed);
     g_launches.fetch_add(ntt_inverse_auto(c->T, c->fz, m, rows, ld, work, ws, st, scale, s), std::memory_order_relaxed);
 }
 
@@ -396,6 +399,7 @@ extern "C" {
 
 const char* fhe_last_error(void) { return g_err.c_str(); }
 uint64_t fhe_launch_count(void) { return g_launches.load(); }
+uint64_t fhe_ntt_row_count(void) { return g_ntt_rows.load(); }
 
 int fhe_ctx_create(fhe_ctx** out, int log_n, int n_q, int n_p, int alpha, const uint64_t* moduli,
                    const uint64_t* psi, int device) {

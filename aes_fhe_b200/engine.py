@@ -27,13 +27,62 @@ from typing import Any, Dict, List, Optional, Sequence
 import numpy as np
 
 from . import encoding
-from .params import CKKSParams, make_params, sqrt_minus_one
+from .params import CKKSParams, LOG_PQ_BUDGET_DENSE, LOG_PQ_BUDGET_SPARSE, make_params, sqrt_minus_one
 
 _SIGMA = 3.2
 
 
 import os as _os
 _NO_FUSE = _os.environ.get("FHE_NO_HOIST") == "1"      # A/B switch: separate rotations, mul + add per mask
+
+
+class SystemRNG:
+    """The subset of numpy.random.Generator the engine uses, drawn from ``os.urandom`` (the kernel CSPRNG):
+    uniform integers by rejection on 64-bit words (no modulo bias), Gaussians by Box-Muller on 53-bit uniforms,
+    choice without replacement by sorting random keys."""
+
+    @staticmethod
+    def _words(count: int) -> np.ndarray:
+        return np.frombuffer(_os.urandom(8 * count), dtype=np.uint64)
+
+    def integers(self, low, high=None, size=None, dtype=np.int64):
+        if high is None:
+            low, high = 0, low
+        low, span = int(low), int(high) - int(low)
+        if span <= 0:
+            raise ValueError("empty range")
+        shape = () if size is None else (tuple(size) if np.iterable(size) else (int(size),))
+        count = int(np.prod(shape)) if shape else 1
+        limit = (1 << 64) - ((1 << 64) % span)                    # accept words below the largest multiple of span
+        out = np.empty(count, dtype=np.uint64)
+        filled = 0
+        while filled < count:
+            w = self._words(count - filled + 16)
+            if limit < (1 << 64):
+                w = w[w < np.uint64(limit)]
+            take = min(w.size, count - filled)
+            out[filled:filled + take] = w[:take] % np.uint64(span)
+            filled += take
+        res = (out.astype(np.int64) + low) if np.dtype(dtype) != np.uint64 else (out + np.uint64(low))
+        res = res.astype(dtype, copy=False).reshape(shape)
+        return res if shape else res[()]
+
+    def _uniform(self, count: int) -> np.ndarray:
+        return ((self._words(count) >> np.uint64(11)).astype(np.float64) + 0.5) * (1.0 / (1 << 53))      # (0, 1)
+
+    def normal(self, loc=0.0, scale=1.0, size=None):
+        shape = () if size is None else (tuple(size) if np.iterable(size) else (int(size),))
+        count = int(np.prod(shape)) if shape else 1
+        half = (count + 1) // 2
+        r = np.sqrt(-2.0 * np.log(self._uniform(half)))
+        t = 2.0 * np.pi * self._uniform(half)
+        z = np.concatenate([r * np.cos(t), r * np.sin(t)])[:count]
+        return (loc + scale * z).reshape(shape) if shape else float(loc + scale * z[0])
+
+    def choice(self, n: int, size: int, replace: bool = False):
+        if replace:
+            return self.integers(0, n, size=size)
+        return np.argsort(self._words(int(n)), kind="stable")[:int(size)]
 
 
 class Plaintext:
@@ -175,7 +224,7 @@ class Engine:
     def __init__(self, *args, mode: str = 'cpu', use_bootstrap: bool = False,
                  use_multiparty: bool = False, thread_count: int = 0, device_id: int = 0,
                  max_level: Optional[int] = None, log_coeff_count: Optional[int] = None,
-                 special_prime_count: Optional[int] = None, seed: int = 0, device_codec: bool = False,
+                 special_prime_count: Optional[int] = None, seed: Optional[int] = None, device_codec: bool = False,
                  secret_hamming_weight: Optional[int] = None, scale_bits: Optional[int] = None,
                  _backend=None, _params: Optional[CKKSParams] = None):
         args = list(args)
@@ -212,16 +261,20 @@ class Engine:
             lvl = max(1, min(30, (budget - 60 - 60 * max(k, 1)) // 40))
             params = make_params(log_n, lvl, special_count=k)
         else:
-            # a bootstrappable engine works at the largest scale the < 2^45 moduli allow: every
-            # operation is 16x more precise, which is what bootstrapping at N = 2^16 needs
+            # a bootstrappable engine works at the largest scale the < 2^45 moduli allow (every operation is
+            # 16x more precise) and has a sparse secret, so its chain is sized against the sparse-secret bound:
+            # 24 levels = bit bootstrap (13) + one AES round (7) + the entry of the next bootstrap (4),
+            # log2(P Q) = 1551 with three key-switch digits.  Other engines: 30 levels, uniform ternary secret.
             sb = scale_bits if scale_bits is not None else (44 if use_bootstrap else 40)
-            params = make_params(16, int(max_level) if max_level is not None else 30, scale_bits=sb)
+            lvl = int(max_level) if max_level is not None else (24 if use_bootstrap else 30)
+            params = make_params(16, lvl, scale_bits=sb,
+                                 log_pq_budget=LOG_PQ_BUDGET_SPARSE if use_bootstrap else LOG_PQ_BUDGET_DENSE)
         self.params = params
-        # sparse ternary secret (bootstrappable-CKKS practice, e.g. h = 192 at N = 2^16): bounds the
-        # overflow polynomial of ModRaise and shrinks every rounding-noise term from sqrt(2N/3)
-        # to sqrt(h)
+        # Secret distribution.  Bootstrappable engines: sparse ternary, Hamming weight 192 (bounds the overflow
+        # polynomial of ModRaise: |I| <= 32).  All others: uniform ternary -- the distribution the 1770-bit bound is
+        # stated for.  ``secret_hamming_weight`` overrides (0 = uniform ternary).
         if secret_hamming_weight is None:
-            secret_hamming_weight = min(192, params.n // 8)
+            secret_hamming_weight = min(192, params.n // 8) if use_bootstrap else 0
         self.secret_hamming_weight = int(secret_hamming_weight)
         self.slot_count = params.slot_count
         self.max_level = params.max_level
@@ -232,7 +285,11 @@ class Engine:
         elif isinstance(_backend, type):
             _backend = _backend(params)
         self.backend = _backend
-        self._rng = np.random.Generator(np.random.PCG64(seed))
+        # Randomness.  seed=None (the default, and what every reference call site gets: desilofhe.Engine takes no
+        # seed) draws every key, mask and error from the operating system's CSPRNG.  An integer seed makes keys and
+        # ciphertexts reproducible for the parity tests and is NOT secure: anyone can regenerate the secret key.
+        self.seeded = seed is not None
+        self._rng = np.random.Generator(np.random.PCG64(seed)) if self.seeded else SystemRNG()
         # per-limb sqrt(-1) (NTT image of X^(N/2))
         self._imag = [sqrt_minus_one(params, l) for l in range(len(params.moduli))]
         self.op_counts: Dict[str, int] = {}
@@ -267,10 +324,25 @@ class Engine:
     # ------------------------------------------------------------------ keys
     def create_secret_key(self) -> SecretKey:
         n, h = self.params.n, self.secret_hamming_weight
-        s = np.zeros((1, n), dtype=np.int64)
-        pos = self._rng.choice(n, size=h, replace=False)
-        s[0, pos] = self._rng.integers(0, 2, size=h, dtype=np.int64) * 2 - 1
+        if h <= 0:
+            s = self._rng.integers(-1, 2, size=(1, n), dtype=np.int64)          # uniform ternary
+        else:
+            s = np.zeros((1, n), dtype=np.int64)
+            pos = self._rng.choice(n, size=h, replace=False)
+            s[0, pos] = self._rng.integers(0, 2, size=h, dtype=np.int64) * 2 - 1
         return SecretKey(s, self.backend.from_i64(s, self.params.n_q, True))
+
+    @property
+    def security(self) -> Dict[str, Any]:
+        """log2(P Q) against the cited 128-bit bound for this engine's secret distribution (params.py); only
+        meaningful at N = 2^16 -- smaller rings are test rings."""
+        sparse = self.secret_hamming_weight > 0
+        budget = LOG_PQ_BUDGET_SPARSE if sparse else LOG_PQ_BUDGET_DENSE
+        lp = self.params.log_pq
+        return {"log_n": self.params.log_n, "log_pq": round(lp, 1), "budget": budget,
+                "secret": f"sparse ternary h={self.secret_hamming_weight}" if sparse else "uniform ternary",
+                "within_128_bit_budget": bool(self.params.log_n == 16 and lp <= budget),
+                "randomness": "seeded PCG64 (test only, insecure)" if self.seeded else "os.urandom"}
 
     def create_public_key(self, sk: SecretKey) -> PublicKey:
         be, P = self.backend, self.params
@@ -390,7 +462,7 @@ class Engine:
         if g is None:
             import torch
             g = torch.Generator(device=self.backend.device)
-            g.manual_seed(int(self._rng.integers(0, 2 ** 62)))
+            g.manual_seed(int(self._rng.integers(0, 2 ** 62)))            # OS entropy unless the engine is seeded
             self._tgen = g
         return g
 

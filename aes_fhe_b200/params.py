@@ -33,9 +33,16 @@ BASE_BITS = 45
 SPECIAL_BITS = 45
 DEFAULT_SCALE_BITS = 40
 DEFAULT_DNUM = 4
-# log2(P Q) allowed at N = 2^16 for 128-bit security with a sparse ternary secret (the bound the default
-# L = 30 parameter set was sized against)
-LOG_PQ_BUDGET_2_16 = 1770
+# log2(P Q) allowed at N = 2^16 for 128-bit classical security, by secret distribution:
+#  * uniform ternary secret: 1770 -- the HomomorphicEncryption.org standard table (881 bits at N = 2^15) doubled, the
+#    value libraries quote for N = 2^16;
+#  * sparse ternary secret of Hamming weight 192 (what bootstrapping's ModRaise needs): 1553 -- the largest of the
+#    published bootstrappable N = 2^16, h = 192 sets (Bossuat, Mouchet, Troncoso-Pastoriza, Hubaux, EUROCRYPT 2021,
+#    sets I-IV: log QP 1546..1553, estimated at 128 bits with the hybrid dual attack included).
+# No lattice estimator is installed in this image; these are cited bounds, not a fresh estimate.
+LOG_PQ_BUDGET_DENSE = 1770
+LOG_PQ_BUDGET_SPARSE = 1553
+LOG_PQ_BUDGET_2_16 = LOG_PQ_BUDGET_DENSE
 
 
 # --------------------------------------------------------------------------- #
@@ -171,9 +178,15 @@ class CKKSParams:
     def galois_conj(self) -> int:
         return 2 * self.n - 1
 
+    @property
+    def log_pq(self) -> float:
+        """log2 of the full modulus P Q (what the security bound is stated on)"""
+        import math
+        return sum(math.log2(m) for m in self.moduli)
+
 
 @lru_cache(maxsize=None)
-def auto_dnum(log_n: int, max_level: int, scale_bits: int) -> int:
+def auto_dnum(log_n: int, max_level: int, scale_bits: int, budget: int = LOG_PQ_BUDGET_DENSE) -> int:
     """Key-switch digit count when the caller does not give one.
 
     Fewer, wider digits mean fewer ModUp rows to transform (beta (n + K) - n per key switch), a smaller
@@ -181,7 +194,8 @@ def auto_dnum(log_n: int, max_level: int, scale_bits: int) -> int:
     (P must exceed the widest digit).  On the B200 the trade is a clear win as long as P Q stays inside
     the security budget: SubBytes at max_level = 22 takes 55.1 ms per 16 ciphertexts with 4 digits,
     54.0 with 3 and 53.7 with 2 (profiles/r01_dnum_sweep.md).  So at N = 2^16: the smallest digit count
-    in {2, 3, 4} whose log2(P Q) fits LOG_PQ_BUDGET_2_16.  Smaller rings (tests) keep four digits."""
+    in {2, 3, 4} whose log2(P Q) fits the budget of the secret distribution in use.  Smaller rings (tests) keep
+    four digits."""
     if log_n != 16:
         return DEFAULT_DNUM
     n_q = max_level + 1
@@ -189,15 +203,17 @@ def auto_dnum(log_n: int, max_level: int, scale_bits: int) -> int:
         alpha = -(-n_q // d)
         digit_bits = BASE_BITS + (alpha - 1) * scale_bits
         k = -(-(digit_bits + 1) // (SPECIAL_BITS - 1))          # special primes are just below 2^45
-        if BASE_BITS + max_level * scale_bits + k * SPECIAL_BITS <= LOG_PQ_BUDGET_2_16:
+        if BASE_BITS + max_level * scale_bits + k * SPECIAL_BITS <= budget:
             return d
     return DEFAULT_DNUM
 
 
 @lru_cache(maxsize=None)
 def make_params(log_n: int = 16, max_level: int = 30, special_count: int = 0,
-                dnum: int = 0, scale_bits: int = DEFAULT_SCALE_BITS) -> CKKSParams:
-    """Build the deterministic parameter set.  ``dnum == 0`` means "choose" (auto_dnum).
+                dnum: int = 0, scale_bits: int = DEFAULT_SCALE_BITS, log_pq_budget: int = 0) -> CKKSParams:
+    """Build the deterministic parameter set.  ``dnum == 0`` means "choose" (auto_dnum) within
+    ``log_pq_budget`` (0 = the bound for a uniform ternary secret; engines with a sparse secret pass
+    LOG_PQ_BUDGET_SPARSE).
 
     ``special_count == 0`` means "derive K from the digit size" (enough special
     primes that P exceeds the largest digit product, the hybrid key-switching
@@ -213,7 +229,7 @@ def make_params(log_n: int = 16, max_level: int = 30, special_count: int = 0,
     two_n = 2 * n
     n_q = max_level + 1
     if dnum <= 0:
-        dnum = auto_dnum(log_n, max_level, scale_bits)
+        dnum = auto_dnum(log_n, max_level, scale_bits, log_pq_budget or LOG_PQ_BUDGET_DENSE)
 
     q0 = _primes_below(1 << BASE_BITS, two_n, 1)[0]
 

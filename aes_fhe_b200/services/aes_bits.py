@@ -193,20 +193,30 @@ class AESBitService:
         out = by.transpose(1, 3, 2, 0).reshape(G * self.Bs, 16)                               # [g, b, c, r]
         return out if nb is None else out[:nb]
 
+    def _encrypt_planes(self, planes: np.ndarray, level: Optional[int]) -> Ciphertext:
+        """bit planes -> ciphertexts of (-1)^bit.  With the engine's device codec the bytes go to the GPU and
+        encoding, sampling and encryption happen there (Engine.encrypt_zeta, modulus 2); without it the host
+        path keeps the ciphertexts reproducible from the seed (parity tests against the oracle)."""
+        if self.engine.device_codec:
+            return self.engine.encrypt_zeta(planes, self.eng.public_key, 2, level=level)
+        return self.engine.encrypt(1.0 - 2.0 * planes.astype(np.float64), self.eng.public_key, level=level)
+
     def encrypt_state(self, blocks: np.ndarray, level: Optional[int] = None) -> Ciphertext:
-        planes = self.pack_bits(blocks)
-        return self.engine.encrypt_zeta(planes, self.eng.public_key, 2, level=level)
+        return self._encrypt_planes(self.pack_bits(blocks), level)
 
     def encrypt_round_key(self, rk16, G: int = 1, level: Optional[int] = None) -> Ciphertext:
         """one 16-byte round key replicated over every block slot and over the G states of a batch"""
         rk = np.tile(np.asarray(rk16, dtype=np.uint8).reshape(1, 16), (self.Bs, 1))
-        ct = self.engine.encrypt_zeta(self.pack_bits(rk), self.eng.public_key, 2, level=level)
+        ct = self._encrypt_planes(self.pack_bits(rk), level)
         if G > 1:
             ct = self._take(ct, [i for i in range(32) for _ in range(G)])
         return ct
 
     def decrypt_state(self, ct: Ciphertext, nb: Optional[int] = None) -> np.ndarray:
-        planes = np.atleast_2d(self.engine.decrypt_zeta(ct, self.eng.secret_key, 2))
+        if self.engine.device_codec:
+            planes = np.atleast_2d(self.engine.decrypt_zeta(ct, self.eng.secret_key, 2))
+        else:
+            planes = (np.atleast_2d(self.eng.decrypt(ct)).real < 0).astype(np.uint8)
         return self.unpack_bits(planes, nb)
 
     def decrypt_slots(self, ct: Ciphertext) -> np.ndarray:

@@ -39,6 +39,9 @@ void fhe_ctx_destroy(fhe_ctx* ctx);
 const char* fhe_last_error(void);
 /* number of kernels this library has launched since load (bench.py's gpu_launches) */
 uint64_t fhe_launch_count(void);
+/* number of length-N transforms (forward + inverse NTT rows) launched since load: the work unit bench.py uses to
+ * scale the CPU sample of the reference arm to a whole AES-128 (the schedule's row count does not depend on N) */
+uint64_t fhe_ntt_row_count(void);
 
 /* NTT variant used by every entry point below (results are bit-identical):
  *   2 (default)  csrc/ntt_chained.cuh -- both passes in ONE launch, ticket-ordered so that the lazy

@@ -23,6 +23,7 @@
 #include <cstdint>
 #include <cstdlib>
 #include <cstring>
+#include <atomic>
 #include <vector>
 #ifdef _OPENMP
 #include <omp.h>
@@ -84,7 +85,11 @@ struct Ctx {
     int threads;
 };
 
+// length-N transforms done since load (bench.py scales its CPU sample to a whole AES-128 by this unit)
+static std::atomic<unsigned long long> g_ntt_rows(0);
+
 void ntt_one(const Ctx& c, u64* a, int limb) {
+    g_ntt_rows.fetch_add(1, std::memory_order_relaxed);
     const Mod& m = c.mod[limb];
     const u64* w = c.psi_br[limb].data();
     int n = c.n;
@@ -105,6 +110,7 @@ void ntt_one(const Ctx& c, u64* a, int limb) {
 }
 
 void intt_one(const Ctx& c, u64* a, int limb) {
+    g_ntt_rows.fetch_add(1, std::memory_order_relaxed);
     const Mod& m = c.mod[limb];
     const u64* w = c.ipsi_br[limb].data();
     int n = c.n;
@@ -205,6 +211,7 @@ void* ref_ctx_create(int log_n, int n_q, int n_p, int alpha, const u64* moduli, 
 
 void ref_ctx_destroy(void* h) { delete (Ctx*)h; }
 int ref_ctx_threads(void* h) { return ((Ctx*)h)->threads; }
+unsigned long long ref_ntt_rows(void) { return g_ntt_rows.load(); }
 
 // data: [n_ids, N] rows, row r belongs to limb ids[r]
 void ref_ntt(void* h, u64* data, const int* ids, int n_ids) {

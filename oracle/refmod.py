@@ -34,6 +34,8 @@ def lib():
         _LIB.ref_ctx_create.restype = C.c_void_p
         _LIB.ref_ctx_threads.restype = C.c_int
         _LIB.ref_ctx_threads.argtypes = [C.c_void_p]
+        _LIB.ref_ntt_rows.restype = C.c_ulonglong
+        _LIB.ref_ntt_rows.argtypes = []
     return _LIB
 
 
@@ -54,6 +56,10 @@ class RefBackend:
                                                 _p(mod), _p(psi), int(threads)))
         self.threads = L.ref_ctx_threads(self._ctx)
         self._L = L
+
+    def ntt_row_count(self) -> int:
+        """length-N transforms done by the library since load"""
+        return int(self._L.ref_ntt_rows())
 
     def __del__(self):
         try:

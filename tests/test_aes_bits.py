@@ -129,7 +129,7 @@ def test_bit_bootstrap_on_oracle(log_n, ref_backend_cls):
 
 
 def test_two_rounds_with_refresh_on_oracle(ref_backend_cls):
-    P = make_params(11, 25, scale_bits=44)          # 14 (bit bootstrap) + 7 (round) + 4 (entry of the next bootstrap)
+    P = make_params(11, 24, scale_bits=44)          # 13 (bit bootstrap) + 7 (round) + 4 (entry of the next bootstrap)
     w, svc = make_service(ref_backend_cls(P), P)
     rng = np.random.default_rng(7)
     blocks = rng.integers(0, 256, (svc.Bs, 16), dtype=np.uint8)

@@ -47,7 +47,7 @@ def test_evalmod_polynomial_recovers_the_message():
 @pytest.mark.parametrize("log_n,scale_bits,tol", [(11, 40, 3e-3), (12, 44, 5e-4)])
 def test_bootstrap_refreshes_levels_on_oracle(log_n, scale_bits, tol, ref_backend_cls):
     P = make_params(log_n, 22, scale_bits=scale_bits)
-    eng = Engine(_params=P, _backend=ref_backend_cls(P), seed=5)
+    eng = Engine(_params=P, _backend=ref_backend_cls(P), seed=5, use_bootstrap=True)
     sk = eng.create_secret_key()
     pk = eng.create_public_key(sk)
     rlk = eng.create_relinearization_key(sk)
@@ -72,7 +72,7 @@ def test_chebyshev_paterson_stockmeyer_matches_numpy(ref_backend_cls):
     22) against numpy's chebval on the decrypted slots."""
     from numpy.polynomial import chebyshev as C
     P = make_params(11, 8)
-    eng = Engine(_params=P, _backend=ref_backend_cls(P), seed=3)
+    eng = Engine(_params=P, _backend=ref_backend_cls(P), seed=3, use_bootstrap=True)
     sk = eng.create_secret_key(); pk = eng.create_public_key(sk); rlk = eng.create_relinearization_key(sk)
     rng = np.random.default_rng(1)
     yv = rng.uniform(-1, 1, eng.slot_count)

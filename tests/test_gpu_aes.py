@@ -48,7 +48,7 @@ def test_bootstrap_full_size(cuda_lib):
     import time
     from aes_fhe_b200.engine import Engine
     P = make_params(16, 30, scale_bits=44)
-    eng = Engine(_params=P, seed=5)
+    eng = Engine(_params=P, seed=5, use_bootstrap=True)
     sk = eng.create_secret_key(); pk = eng.create_public_key(sk)
     rlk = eng.create_relinearization_key(sk); cj = eng.create_conjugation_key(sk)
     bk = eng.create_bootstrap_key(sk)

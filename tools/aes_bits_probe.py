@@ -1,0 +1,106 @@
+#!/usr/bin/env python
+"""Full-size probe of the bit-sliced AES-128 path on one B200: N = 2^16, G states of 8192 blocks, per-stage
+device time, every decoded block checked against plain AES.
+
+    python tools/aes_bits_probe.py [--states G] [--level L] [--groups 3,3] [--rounds 10]
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import sys
+import time
+from pathlib import Path
+
+import numpy as np
+
+sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
+
+
+class StageTimer:
+    """CUDA events at stage boundaries on the current stream; `ms()` after a synchronize"""
+
+    def __init__(self):
+        import torch
+        self.torch = torch
+        self.marks = []
+        self.reset()
+
+    def reset(self):
+        e = self.torch.cuda.Event(enable_timing=True)
+        e.record()
+        self.marks = [("start", e)]
+
+    def __call__(self, name):
+        e = self.torch.cuda.Event(enable_timing=True)
+        e.record()
+        self.marks.append((name, e))
+
+    def ms(self):
+        self.torch.cuda.synchronize()
+        out = {}
+        for (_, a), (name, b) in zip(self.marks[:-1], self.marks[1:]):
+            out[name] = out.get(name, 0.0) + a.elapsed_time(b)
+        return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--states", type=int, default=1)
+    ap.add_argument("--level", type=int, default=25)
+    ap.add_argument("--scale-bits", type=int, default=44)
+    ap.add_argument("--groups", default="3,3")
+    ap.add_argument("--rounds", type=int, default=10)
+    ap.add_argument("--fresh-level", type=int, default=None)
+    args = ap.parse_args()
+    import torch
+    from aes_fhe_b200.params import make_params
+    from aes_fhe_b200.services.aes_bits import AESBitService
+    from aes_fhe_b200.services.key_expansion import expand_key
+    from aes_fhe_b200.services.xor_service import EngineWrapper, XORConfig
+    from oracle import aes_plain as A
+
+    P = make_params(16, args.level, scale_bits=args.scale_bits)
+    groups = tuple(int(x) for x in args.groups.split(","))
+    t0 = time.time()
+    w = EngineWrapper(XORConfig(), _engine_kwargs=dict(_params=P, seed=3, device_codec=True), rotation_steps=[])
+    svc = AESBitService(w, boot_groups=groups)
+    G = args.states
+    key = bytes.fromhex("2b7e151628aed2a6abf7158809cf4f3c")
+    rng = np.random.default_rng(9)
+    blocks = rng.integers(0, 256, (G * svc.Bs, 16), dtype=np.uint8)
+    blocks[0] = np.frombuffer(bytes.fromhex("3243f6a8885a308d313198a2e0370734"), np.uint8)
+    rks = expand_key(key)
+    fresh = args.fresh_level if args.fresh_level is not None else 1 + svc.boot_in_levels
+    st = svc.encrypt_state(blocks, level=fresh)
+    rkeys = [svc.encrypt_round_key(rks[r], G, level=min(P.max_level, max(12, fresh))) for r in range(args.rounds + 1)]
+    out = svc.encrypt_blocks(st, key, rounds=args.rounds, round_keys=rkeys)            # warm-up: keys, matrices, tables
+    torch.cuda.synchronize()
+    setup = time.time() - t0
+    c0, r0 = dict(w.engine.op_counts), svc.refreshes
+    l0 = w.engine.backend.launch_count()
+    svc.timer = StageTimer()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    out = svc.encrypt_blocks(st, key, rounds=args.rounds, round_keys=rkeys)
+    b.record()
+    stages = svc.timer.ms()
+    svc.timer = None
+    ms = a.elapsed_time(b)
+    got = svc.decrypt_state(out)
+    s = blocks ^ rks[0]
+    for r in range(1, args.rounds + 1):
+        s = A.round_fn(s, rks[r], last=(r == 10))
+    slots = svc.decrypt_slots(out)
+    err = float(np.abs(slots - (1.0 - 2.0 * svc.pack_bits(s))).max())
+    cnt = {k: v - c0.get(k, 0) for k, v in w.engine.op_counts.items()}
+    print(json.dumps({"states": G, "blocks": int(G * svc.Bs), "level": args.level, "groups": groups, "rounds": args.rounds,
+                      "limbs": [P.n_q, P.n_p, P.dnum], "ms": ms, "blocks_per_s": G * svc.Bs / (ms * 1e-3), "stages_ms": stages,
+                      "bytes_equal_plain_aes": bool(np.array_equal(got, s)), "max_slot_err": err,
+                      "bootstrapped_ciphertexts": svc.refreshes - r0, "op_counts": cnt,
+                      "launches": w.engine.backend.launch_count() - l0, "out_level": out.level, "setup_s": setup,
+                      "mem_gb": torch.cuda.max_memory_allocated() / 2 ** 30}))
+
+
+if __name__ == "__main__":
+    main()
