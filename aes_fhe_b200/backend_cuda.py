@@ -114,6 +114,10 @@ class CudaBackend:
     def split_batch(self, h, sizes: Sequence[int]):
         return [x.contiguous() for x in torch.split(h, list(sizes), dim=1)]
 
+    def alloc(self, shape):
+        """uninitialised device tensor of 64-bit residues (receive buffer for distributed keys)"""
+        return self._empty(*shape)
+
     def slice_batch(self, h, lo: int, hi: int):
         return h[:, lo:hi]
 

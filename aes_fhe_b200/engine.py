@@ -293,6 +293,7 @@ class Engine:
         # per-limb sqrt(-1) (NTT image of X^(N/2))
         self._imag = [sqrt_minus_one(params, l) for l in range(len(params.moduli))]
         self.op_counts: Dict[str, int] = {}
+        self.issued_rotation_keys: Dict[int, FixedRotationKey] = {}
 
     # ------------------------------------------------------------------ utils
     def _count(self, name: str, k: int = 1):
@@ -389,8 +390,13 @@ class Engine:
         return ConjugationKey(self._galois_key(sk, g), g)
 
     def create_fixed_rotation_key(self, sk: SecretKey, delta: int) -> FixedRotationKey:
+        if hasattr(sk, "fetch_rotation_key"):
+            # a rank that evaluates without the secret key: the key owner shipped this key (sharding.ReceivedKeys)
+            return sk.fetch_rotation_key(int(delta))
         g = self.params.galois_for_rotation(int(delta))
-        return FixedRotationKey(self._galois_key(sk, g), g, int(delta))
+        key = FixedRotationKey(self._galois_key(sk, g), g, int(delta))
+        self.issued_rotation_keys[int(delta)] = key          # what distribute_keys ships to the other ranks
+        return key
 
     def create_rotation_key(self, sk: SecretKey, steps: Optional[Sequence[int]] = None) -> RotationKey:
         """All +-2^k steps by default (the reference passes only ``sk``:

@@ -148,6 +148,15 @@ class AESBitService:
         self.stage_ms: Optional[Dict[str, float]] = None      # filled when `timer` is set
         self.timer = None
 
+    def prepare_keys(self):
+        """create (owner) or look up (other ranks) every Galois key the service will use: the three ShiftRows
+        rotations and the rotations of the bootstrap's linear transforms.  sharding.distribute_keys ships what the
+        owner's engine has issued, so the owner calls this first."""
+        from ..bootstrap import _materialise
+        for r in (1, 2, 3):
+            self._rot_key(r)
+        _materialise(self.engine, self.boot_key)
+
     # ------------------------------------------------------------------ batch-axis plumbing
     def _G(self, ct: Ciphertext) -> int:
         if ct.batch % 32:
@@ -211,6 +220,49 @@ class AESBitService:
         if G > 1:
             ct = self._take(ct, [i for i in range(32) for _ in range(G)])
         return ct
+
+    # ---- throughput path: raw block bytes cross PCIe (16 B per block each way), bit planes are made on the GPU
+    def _plane_index(self, G: int):
+        """(byte index into the [G * Bs * 16] block buffer, bit) of every slot of every plane, on the device"""
+        import torch
+        key = ("plane_index", G)
+        cache = self.__dict__.setdefault("_dev_cache", {})
+        if key not in cache:
+            dev = self.engine.backend.device
+            r = torch.arange(4, device=dev).view(1, 4, 1, 1, 1)
+            g = torch.arange(G, device=dev).view(1, 1, G, 1, 1)
+            c = torch.arange(4, device=dev).view(1, 1, 1, 4, 1)
+            b = torch.arange(self.Bs, device=dev).view(1, 1, 1, 1, self.Bs)
+            byte = ((g * self.Bs + b) * 16 + 4 * c + r).expand(8, 4, G, 4, self.Bs).reshape(32 * G, self.sc)
+            bit = torch.arange(8, device=dev, dtype=torch.uint8).view(8, 1, 1).expand(8, 4 * G, self.sc).reshape(32 * G, self.sc)
+            cache[key] = (byte.contiguous(), bit.contiguous())
+        return cache[key]
+
+    def encrypt_state_device(self, blocks, level: Optional[int] = None) -> Ciphertext:
+        """blocks: uint8 [G * Bs, 16] as a (pinned) torch tensor or array.  One H2D copy of the raw bytes; bit
+        extraction, encoding, sampling and encryption on the GPU."""
+        import torch
+        if not self.engine.device_codec:
+            raise RuntimeError("encrypt_state_device needs Engine(device_codec=True)")
+        x = blocks if isinstance(blocks, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(blocks, dtype=np.uint8))
+        if x.shape[0] % self.Bs:
+            raise ValueError(f"a whole number of states ({self.Bs} blocks each) is required; pad with pack_bits")
+        G = x.shape[0] // self.Bs
+        flat = x.reshape(-1).to(self.engine.backend.device, non_blocking=True)
+        byte, bit = self._plane_index(G)
+        planes = (flat[byte] >> bit) & 1
+        return self.engine.encrypt_zeta(planes, self.eng.public_key, 2, level=level)
+
+    def decrypt_state_device(self, ct: Ciphertext):
+        """decrypt + decode + bit packing on the GPU; one D2H copy of the block bytes [G * Bs, 16] (torch uint8, host)"""
+        import torch
+        G = self._G(ct)
+        z = self.engine.decrypt_device(ct, self.eng.secret_key)                  # [32 G, sc] complex
+        neg = (z.real < 0).to(torch.uint8).view(8, 4, G, 4, self.Bs)
+        by = torch.zeros((4, G, 4, self.Bs), dtype=torch.uint8, device=z.device)
+        for k in range(8):
+            by |= neg[k] << k
+        return by.permute(1, 3, 2, 0).reshape(G * self.Bs, 16).cpu()
 
     def decrypt_state(self, ct: Ciphertext, nb: Optional[int] = None) -> np.ndarray:
         if self.engine.device_codec:
@@ -357,3 +409,36 @@ class AESBitService:
             st = self.sub_bytes(st)
             st = self.add_round_key(st, round_keys[r]) if last else self.mix_columns_ark(st, round_keys[r])
         return st
+
+
+# --------------------------------------------------------------------------- bytes in, bytes out (row f-3)
+def _run_blocks(svc: AESBitService, blocks: np.ndarray, key16: bytes) -> np.ndarray:
+    """AES-128 of [nb, 16] plaintext blocks under `key16`, state by state (Bs blocks per state)"""
+    nb = blocks.shape[0]
+    st = svc.encrypt_state(blocks, level=1 + svc.boot_in_levels)
+    return svc.decrypt_state(svc.encrypt_blocks(st, key16), nb)
+
+
+def encrypt_ecb(svc: AESBitService, data: bytes, key16: bytes) -> bytes:
+    """AES-128-ECB of `data` (PKCS#7-padded, chunked into 16-byte blocks: the reference's utils.pkcs7_pad /
+    chunk_bytes, /root/reference/utils.py:62-91) evaluated homomorphically: the blocks are bit-sliced and encrypted
+    under the service's public key, run through ten rounds with the encrypted round keys of `key16`, decrypted and
+    re-assembled.  What the server sees is ciphertext only; this helper plays client and server."""
+    from .utils import chunk_bytes, pkcs7_pad
+    chunks = chunk_bytes(pkcs7_pad(bytes(data)))
+    blocks = np.frombuffer(b"".join(chunks), dtype=np.uint8).reshape(-1, 16)
+    return _run_blocks(svc, blocks, key16).tobytes()
+
+
+def encrypt_ctr(svc: AESBitService, data: bytes, key16: bytes, nonce12: bytes, counter0: int = 1) -> bytes:
+    """AES-128-CTR keystream (nonce || 32-bit big-endian counter, NIST SP 800-38A) evaluated homomorphically and
+    XORed onto `data` in the clear -- the transciphering use of this pipeline (the keystream blocks are public
+    counters, only the key is secret)."""
+    n = -(-len(data) // 16)
+    ctr = np.zeros((n, 16), dtype=np.uint8)
+    ctr[:, :12] = np.frombuffer(bytes(nonce12), dtype=np.uint8)
+    c = (counter0 + np.arange(n, dtype=np.uint64)) & np.uint64(0xFFFFFFFF)
+    for j in range(4):
+        ctr[:, 12 + j] = ((c >> np.uint64(8 * (3 - j))) & np.uint64(0xFF)).astype(np.uint8)
+    ks = _run_blocks(svc, ctr, key16).reshape(-1)[:len(data)]
+    return (np.frombuffer(bytes(data), dtype=np.uint8) ^ ks).tobytes()

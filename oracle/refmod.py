@@ -115,6 +115,9 @@ class RefBackend:
             o += s
         return out
 
+    def alloc(self, shape):
+        return np.empty(tuple(shape), dtype=np.uint64)
+
     def slice_batch(self, h, lo: int, hi: int):
         return np.ascontiguousarray(h[:, lo:hi])
 

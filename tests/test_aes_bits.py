@@ -145,3 +145,54 @@ def test_two_rounds_with_refresh_on_oracle(ref_backend_cls):
     assert got[0].tobytes().hex() == "aa8f5f0361dde3ef82d24ad26832469a"      # FIPS-197 App. B, start of round 3
     assert w.engine.op_counts["bootstrap"] == 2 and svc.refreshes == 32
     assert np.abs(svc.decrypt_slots(out) - (1.0 - 2.0 * svc.pack_bits(s))).max() < 1e-3
+
+
+def test_block_io_helpers_follow_the_reference_interface():
+    """utils mirror (row f-3): column-major state, PKCS#7 always pads, chunking"""
+    from aes_fhe_b200.services import utils as U
+    b = bytes(range(16))
+    s = U.bytes_to_state(b)
+    assert s[1, 0] == 1 and s[0, 1] == 4 and U.state_to_bytes(s) == b
+    assert U.pkcs7_unpad(U.pkcs7_pad(b"abc")) == b"abc" and len(U.pkcs7_pad(b"a" * 16)) == 32
+    assert U.chunk_bytes(b"x" * 40) == [b"x" * 16, b"x" * 16, b"x" * 8]
+    with pytest.raises(ValueError):
+        U.pkcs7_unpad(b"abc\x05")
+    with pytest.raises(ValueError):
+        U.bytes_to_state(b"short")
+    assert np.array_equal(U.zeta_decode(U.zeta_encode(np.arange(256), 256), 256), np.arange(256))
+
+
+def test_ctr_counter_blocks(monkeypatch):
+    """encrypt_ctr builds nonce || big-endian counter blocks and XORs the keystream (checked with plain AES in
+    place of the homomorphic evaluation; NIST SP 800-38A F.5.1 uses a 128-bit counter, so the vector here is
+    plain AES of the same blocks)"""
+    seen = {}
+
+    def fake(svc, blocks, key16):
+        seen["blocks"] = blocks.copy()
+        return A.encrypt_blocks(blocks, key16)
+
+    monkeypatch.setattr(AB, "_run_blocks", fake)
+    nonce = bytes(range(100, 112))
+    data = bytes(range(50))
+    out = AB.encrypt_ctr(None, data, KEY_B, nonce, counter0=0xFFFFFFFE)
+    assert seen["blocks"].shape == (4, 16) and seen["blocks"][0, :12].tobytes() == nonce
+    assert [bytes(b[12:]).hex() for b in seen["blocks"]] == ["fffffffe", "ffffffff", "00000000", "00000001"]
+    ks = A.encrypt_blocks(seen["blocks"], KEY_B).reshape(-1)[:50]
+    assert out == (np.frombuffer(data, np.uint8) ^ ks).tobytes()
+    assert AB.encrypt_ctr(None, out, KEY_B, nonce, counter0=0xFFFFFFFE) == data
+
+
+def test_ecb_ten_rounds_on_oracle(ref_backend_cls):
+    """bytes in, bytes out: AES-128-ECB of a 40-byte message (PKCS#7 -> 3 blocks) through ten homomorphic rounds
+    with nine bit bootstraps on the oracle at N = 2^11; FIPS-197 Appendix C.1 is the first block"""
+    P = make_params(11, 24, scale_bits=44)
+    w, svc = make_service(ref_backend_cls(P), P)
+    key = bytes(range(16))
+    msg = bytes.fromhex("00112233445566778899aabbccddeeff") + b"twenty-four more bytes.."
+    ct = AB.encrypt_ecb(svc, msg, key)
+    assert len(ct) == 48 and ct[:16].hex() == "69c4e0d86a7b0430d8cdb78070b4c55a"
+    from aes_fhe_b200.services.utils import pkcs7_pad
+    want = A.encrypt_blocks(np.frombuffer(pkcs7_pad(msg), np.uint8).reshape(-1, 16), key).tobytes()
+    assert ct == want
+    assert w.engine.op_counts["bootstrap"] == 10

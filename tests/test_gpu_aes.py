@@ -75,7 +75,8 @@ def test_mixrow_named_function_runs_with_bootstrapping(cuda_lib):
     from aes_fhe_b200.services.xor_service import XORService, EngineWrapper, XORConfig, CoefficientCache, ZetaEncoder
     from test_services_plain_and_oracle import _plain_wrapper
     cfg = XORConfig()
-    w = EngineWrapper(cfg, _engine_kwargs=dict(seed=3), rotation_steps=[-1, -2, -3, -5, -10, -15])
+    w = EngineWrapper(cfg, _engine_kwargs=dict(seed=3, _params=make_params(16, 30, scale_bits=44)),
+                      rotation_steps=[-1, -2, -3, -5, -10, -15])
     assert w.engine.params.scale_bits == 44 and w.engine.max_level == 30
     xs = XORService(w, CoefficientCache(cfg.coeffs_path))
     state = np.random.default_rng(2025).integers(0, 256, (4, 4), dtype=np.uint8)
@@ -92,32 +93,72 @@ def test_mixrow_named_function_runs_with_bootstrapping(cuda_lib):
     assert err < 1e-3
 
 
+def _bit_service(seed=4, **kw):
+    from aes_fhe_b200.services.aes_bits import AESBitService
+    from aes_fhe_b200.services.xor_service import EngineWrapper, XORConfig
+    w = EngineWrapper(XORConfig(), _engine_kwargs=dict(seed=seed, **kw), rotation_steps=[])
+    assert w.engine.params.log_n == 16 and w.engine.max_level == 24 and w.engine.params.scale_bits == 44
+    assert w.engine.security["within_128_bit_budget"]
+    return w, AESBitService(w)
+
+
 def test_aes128_ten_rounds_full_size(cuda_lib):
-    """BASELINE config 5 on the B200: AES-128, ten rounds, N = 2^16 (2048 blocks per ciphertext),
-    refresh (bootstrap + clean-up) after every LUT layer.  Decoded ciphertext bytes of all 2048
-    blocks must equal plain AES; block 0 is FIPS-197 Appendix B, block 1 uses the Appendix C.1
-    plaintext under the Appendix B key."""
+    """BASELINE configs 4 / 5 on the B200: AES-128, ten rounds, N = 2^16, the default bootstrappable engine
+    (24 levels, 44-bit scale, log PQ = 1551 with the sparse secret), one state of 8192 blocks in 32 bit-plane
+    ciphertexts (services/aes_bits.py), one bit bootstrap per round.  Decoded bytes of all 8192 blocks must equal
+    plain AES; block 0 is FIPS-197 Appendix B, block 1 is the Appendix C.1 plaintext under the Appendix B key, and
+    a second run under the Appendix C.1 key reproduces 69c4e0d8...c55a.  Slot level (north_star check 2): the final
+    slots and the slots right after a refresh are within 1e-3 of +-1."""
     import time
-    from aes_fhe_b200.services.aes128 import AES128Service
-    from aes_fhe_b200.services.xor_service import XORService, EngineWrapper, XORConfig, CoefficientCache
+    from aes_fhe_b200.services.key_expansion import expand_key
     from oracle import aes_plain as A
-    cfg = XORConfig()
-    w = EngineWrapper(cfg, _engine_kwargs=dict(seed=4), rotation_steps=[])
-    assert w.engine.params.log_n == 16 and w.engine.max_level == 30
-    svc = AES128Service(w, XORService(w, CoefficientCache(cfg.coeffs_path)))
+    w, svc = _bit_service()
     key = bytes.fromhex("2b7e151628aed2a6abf7158809cf4f3c")
     rng = np.random.default_rng(11)
-    blocks = rng.integers(0, 256, (svc.B, 16), dtype=np.uint8)
+    blocks = rng.integers(0, 256, (svc.Bs, 16), dtype=np.uint8)
     blocks[0] = np.frombuffer(bytes.fromhex("3243f6a8885a308d313198a2e0370734"), np.uint8)
     blocks[1] = np.frombuffer(bytes.fromhex("00112233445566778899aabbccddeeff"), np.uint8)
     t0 = time.time()
-    out = svc.encrypt_blocks(svc.encrypt_state(blocks), key)
+    st = svc.encrypt_state(blocks, level=1 + svc.boot_in_levels)
+    out = svc.encrypt_blocks(st, key)
     torch.cuda.synchronize()
     dt = time.time() - t0
     got = svc.decrypt_state(out)
     want = A.encrypt_blocks(blocks, key)
     bad = int((got != want).any(axis=1).sum())
-    print(f"AES-128 x {svc.B} blocks: {dt:.1f}s first run (keys, matrices, tables included), "
-          f"{w.engine.op_counts['bootstrap']} bootstrap calls, {svc.refreshes} ciphertexts refreshed, wrong blocks {bad}")
+    err = np.abs(svc.decrypt_slots(out) - (1.0 - 2.0 * svc.pack_bits(want))).max()
+    print(f"AES-128 x {svc.Bs} blocks: {dt:.1f}s first run (keys, matrices, tables included), "
+          f"{w.engine.op_counts['bootstrap']} bootstrap calls, {svc.refreshes} ciphertexts bootstrapped, "
+          f"wrong blocks {bad}, max slot error {err:.2e}")
     assert got[0].tobytes().hex() == "3925841d02dc09fbdc118597196a0b32"
-    assert bad == 0
+    assert bad == 0 and err < 1e-3
+    assert w.engine.op_counts["bootstrap"] == 10 and svc.refreshes == 160
+    # FIPS-197 Appendix C.1 (key 000102...0f) through the same service
+    key_c = bytes(range(16))
+    out_c = svc.encrypt_blocks(svc.encrypt_state(blocks[:4], level=1 + svc.boot_in_levels), key_c)
+    assert svc.decrypt_state(out_c, 4)[1].tobytes().hex() == "69c4e0d86a7b0430d8cdb78070b4c55a"
+    # the refresh on a state that has been through a round (error ~1e-3): slots back within 1e-3 of +-1
+    rks = expand_key(key)
+    s1 = svc.encrypt_state(blocks, level=12)
+    s1 = svc.mix_columns_ark(svc.sub_bytes(svc.shift_rows(s1)), svc.encrypt_round_key(rks[1], level=12))
+    ref = A.mix_columns(A.sub_bytes(A.shift_rows(blocks))) ^ rks[1]
+    fresh = svc.refresh(s1)
+    e_in = np.abs(svc.decrypt_slots(s1) - (1.0 - 2.0 * svc.pack_bits(ref))).max()
+    e_out = np.abs(svc.decrypt_slots(fresh) - (1.0 - 2.0 * svc.pack_bits(ref))).max()
+    print(f"refresh: max slot error {e_in:.2e} -> {e_out:.2e}, level {s1.level} -> {fresh.level}")
+    assert fresh.level == 24 - 13 and e_out < 1e-3
+
+
+def test_bytes_in_bytes_out_ecb_full_size(cuda_lib):
+    """row f-3: encrypt_ecb(bytes, key) -- PKCS#7 padding and 16-byte chunking as /root/reference/utils.py:62-91,
+    FIPS-197 Appendix C.1 as the first block, a ragged tail -- through the device codec."""
+    from aes_fhe_b200.services.aes_bits import encrypt_ecb
+    from oracle import aes_plain as A
+    w, svc = _bit_service(seed=6, device_codec=True)
+    key = bytes(range(16))
+    msg = bytes.fromhex("00112233445566778899aabbccddeeff") + bytes(np.random.default_rng(2).integers(0, 256, 1000, dtype=np.uint8))
+    ct = encrypt_ecb(svc, msg, key)
+    assert len(ct) == 1024 and ct[:16].hex() == "69c4e0d86a7b0430d8cdb78070b4c55a"
+    padded = msg + bytes([8] * 8)
+    want = A.encrypt_blocks(np.frombuffer(padded, np.uint8).reshape(-1, 16), key).tobytes()
+    assert ct == want

@@ -24,7 +24,7 @@ def test_primitives_small_chain(log_n, lvl, ref_backend_cls, cuda_lib):
 
 
 def test_primitives_full_parameters(ref_backend_cls, cuda_lib):
-    P = make_params(16, 30)          # N = 2^16, 31 + 6 limbs: the BASELINE configuration
+    P = make_params(16, 30)          # N = 2^16, 31 + 10 limbs, 3 digits of 11: the default Engine() chain
     kp.check_primitives(P, _gpu(P), ref_backend_cls(P))
 
 
@@ -42,6 +42,33 @@ def test_keyswitch_phases_small(log_n, lvl, dnum, ref_backend_cls, cuda_lib):
 def test_keyswitch_full_parameters(ref_backend_cls, cuda_lib):
     P = make_params(16, 30)
     kp.check_keyswitch(P, _gpu(P), ref_backend_cls(P), levels=[31, 30, 25, 17, 16, 9, 8, 2, 1])
+
+
+def _benchmarked_sets():
+    """the parameter sets bench.py times at N = 2^16: SubBytes (configs[1]: 23 + 11 limbs, two digits of 12 ->
+    k_bconv<12>, k_ks_inner<2,...>) and bit-sliced AES-128 (configs[4]: 25 + 10 limbs, three digits of 9, 44-bit scale,
+    sized against the sparse-secret bound)"""
+    from aes_fhe_b200.params import LOG_PQ_BUDGET_SPARSE
+    return {"subbytes": make_params(16, 22),
+            "aes128": make_params(16, 24, scale_bits=44, log_pq_budget=LOG_PQ_BUDGET_SPARSE)}
+
+
+@pytest.mark.parametrize("name", ["subbytes", "aes128"])
+def test_primitives_at_benchmarked_parameters(name, ref_backend_cls, cuda_lib):
+    P = _benchmarked_sets()[name]
+    assert (P.n_q, P.n_p, P.alpha, P.dnum) == {"subbytes": (23, 11, 12, 2), "aes128": (25, 10, 9, 3)}[name]
+    kp.check_primitives(P, _gpu(P), ref_backend_cls(P))
+    kp.check_rescale(P, _gpu(P), ref_backend_cls(P))
+
+
+@pytest.mark.parametrize("name", ["subbytes", "aes128"])
+def test_keyswitch_phases_at_benchmarked_parameters(name, ref_backend_cls, cuda_lib):
+    """residues of ModUp / key inner product / ModDown and of the whole key switch, bit for bit, at the top level,
+    at digit boundaries and at the bottom of the chain"""
+    P = _benchmarked_sets()[name]
+    a = P.alpha
+    levels = sorted({P.n_q, P.n_q - 1, 2 * a + 1, 2 * a, a + 1, a, 2, 1} & set(range(1, P.n_q + 1)), reverse=True)
+    kp.check_keyswitch(P, _gpu(P), ref_backend_cls(P), levels=levels)
 
 
 @pytest.mark.parametrize("log_n,lvl", [(12, 6), (14, 6)])
@@ -141,3 +168,75 @@ def test_fused_ntt_equals_two_pass_at_scale(ref_backend_cls, cuda_lib):
     one = rand_poly(P, rng, 1, nq, True)
     assert gb.lib.fhe_set_ntt_fused(gb.ctx, 1) == 0
     assert np.array_equal(gb.to_numpy(gb.ntt(gb.from_numpy(one), nq, K)), ref_backend_cls(P).ntt(one, nq, K))
+
+
+def test_bit_sliced_round_residues_equal_oracle(ref_backend_cls, cuda_lib):
+    """ARK_0 + ShiftRows + SubBytes + MixColumns/ARK of the bit-sliced AES path (services/aes_bits.py) on the
+    B200 and on the oracle from the same seed: the 32 output ciphertexts must agree residue for residue, and
+    decode to plain AES."""
+    from test_aes_bits import make_service, KEY_B
+    from aes_fhe_b200.services.key_expansion import expand_key
+    from oracle import aes_plain as A
+    P = make_params(13, 9, scale_bits=44)
+    res = []
+    for be in (_gpu(P), ref_backend_cls(P)):
+        w, svc = make_service(be, P, boot_key=object())
+        rng = np.random.default_rng(3)
+        blocks = rng.integers(0, 256, (svc.Bs, 16), dtype=np.uint8)
+        rks = expand_key(KEY_B)
+        k0, k1 = svc.encrypt_round_key(rks[0]), svc.encrypt_round_key(rks[1])
+        st = svc.add_round_key(svc.encrypt_state(blocks), k0)
+        st = svc.mix_columns_ark(svc.sub_bytes(svc.shift_rows(st)), k1)
+        assert np.array_equal(svc.decrypt_state(st), A.round_fn(blocks ^ rks[0], rks[1]))
+        res.append(be.to_numpy(st.polys))
+    assert np.array_equal(res[0], res[1])
+
+
+def test_bit_bootstrap_residues_equal_oracle(ref_backend_cls, cuda_lib):
+    """the whole bit bootstrap (SlotToCoeff, ModRaise, CoeffToSlot with hoisted rotations and shared ModDowns,
+    EvalMod) on the B200 against the oracle, residue for residue, at N = 2^12"""
+    from test_aes_bits import make_service
+    P = make_params(12, 18, scale_bits=44)
+    res = []
+    for be in (_gpu(P), ref_backend_cls(P)):
+        w, svc = make_service(be, P)
+        rng = np.random.default_rng(5)
+        u = rng.choice([-1.0, 1.0], (2, w.engine.slot_count)) + 1j * rng.choice([-1.0, 1.0], (2, w.engine.slot_count))
+        ct = w.engine.encrypt(u, w.public_key, level=svc.boot_in_levels + 1)
+        out = w.engine.bootstrap_bits(ct, w.relin_key, w.conj_key, svc.boot_key)
+        got = w.engine.decrypt(out, w.secret_key)
+        assert np.abs(got - np.concatenate([u.real, u.imag])).max() < 1e-4
+        res.append(be.to_numpy(out.polys))
+    assert np.array_equal(res[0], res[1])
+
+
+def test_byte_nibble_bridge_gf_service_on_gpu(ref_backend_cls, cuda_lib):
+    """rows a8 / a10 / f-2 on the B200 (the CPU-oracle versions are in test_services_plain_and_oracle.py):
+    extract_nibbles / recombine_nibbles / byte-domain add_round_key (xor_service.py:256-269, 434-547) and
+    GFService.mul2 / mul3 (gf_service.py:55-78): decoded values exact, slots within 1e-3 of the zeta encoding."""
+    from aes_fhe_b200.services.gf_service import GFService, gf_tables
+    from aes_fhe_b200.services.xor_service import XORService, EngineWrapper, XORConfig, CoefficientCache, ZetaEncoder
+    P = make_params(13, 24)
+    cfg = XORConfig()
+    w = EngineWrapper(cfg, _engine_kwargs=dict(_params=P, _backend=_gpu(P), seed=21), rotation_steps=[])
+    xs = XORService(w, CoefficientCache(cfg.coeffs_path))
+    sc = w.engine.slot_count
+    rng = np.random.default_rng(4)
+    x = rng.integers(0, 256, sc, dtype=np.uint8)
+    x[:256] = np.arange(256)
+    ct = w.encrypt(ZetaEncoder.to_zeta(x, 256))
+    hi, lo = xs.extract_nibbles(ct)
+    assert np.abs(w.decrypt(hi) - ZetaEncoder.to_zeta(x >> 4)).max() < 1e-3
+    assert np.array_equal(ZetaEncoder.from_zeta(w.decrypt(hi)), x >> 4)
+    assert np.array_equal(ZetaEncoder.from_zeta(w.decrypt(lo)), x & 15)
+    back = xs.recombine_nibbles(hi, lo)
+    assert np.array_equal(ZetaEncoder.from_zeta(w.decrypt(back), 256), x)
+    key = rng.integers(0, 256, sc, dtype=np.uint8)
+    out = xs.add_round_key(ct, key)
+    assert np.array_equal(ZetaEncoder.from_zeta(w.decrypt(out), 256), x ^ key)
+    gf = GFService(w, xs)
+    t2, t3 = gf_tables()
+    for fn, tab in ((gf.mul2_bsgs, t2), (gf.mul3_bsgs, t3)):
+        h2, l2 = fn(ct)
+        assert np.array_equal(ZetaEncoder.from_zeta(w.decrypt(h2)), tab[x] >> 4)
+        assert np.array_equal(ZetaEncoder.from_zeta(w.decrypt(l2), 256), tab[x] & 15)
