@@ -51,7 +51,24 @@ class CudaBackend:
 
     # ---- plumbing
     def _stream(self):
-        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream) if self.is_cuda else C.c_void_p(0)
+        """the caller's current torch stream; ONE stream per context (include/aesfhe_b200.h): the scratch arena and
+        the NTT hand-over counters are per context, so a second stream on the same engine would race on them"""
+        if not self.is_cuda:
+            return C.c_void_p(0)
+        s = torch.cuda.current_stream(self.device).cuda_stream
+        bound = self.__dict__.get("_bound_stream")
+        if bound is None:
+            self._bound_stream = s
+        elif s != bound:
+            raise _capi.FheError("this engine's context is bound to another CUDA stream: use one Engine per stream "
+                                 "(scratch memory and NTT hand-over counters are per context)")
+        return C.c_void_p(s)
+
+    def check_status(self):
+        """raise if a single-launch NTT ever gave up waiting for its hand-over (its output would be wrong).
+        Called wherever results leave the device: decrypt, download, synchronize."""
+        if self.is_cuda:
+            _capi.check(self.lib, self.lib.fhe_ntt_fused_status(self.ctx), "fhe_ntt_fused_status")
 
     def _empty(self, *shape):
         return torch.empty(shape, dtype=torch.int64, device=self.device)
@@ -66,6 +83,7 @@ class CudaBackend:
     def synchronize(self):
         if self.is_cuda:
             torch.cuda.synchronize(self.device)
+            self.check_status()
 
     def launch_count(self) -> int:
         return int(self.lib.fhe_launch_count())
@@ -85,7 +103,9 @@ class CudaBackend:
         return torch.from_numpy(a.view(np.int64)).to(self.device)
 
     def to_numpy(self, h) -> np.ndarray:
-        return h.detach().cpu().contiguous().numpy().view(np.uint64).copy()
+        out = h.detach().cpu().contiguous().numpy().view(np.uint64).copy()
+        self.check_status()
+        return out
 
     def zeros(self, npoly: int, batch: int, nq: int, with_p: bool):
         return torch.zeros((npoly, batch, nq + (self._K if with_p else 0), self.n), dtype=torch.int64,
@@ -496,6 +516,7 @@ class CudaBackend:
         bt = h.shape[1]
         m = torch.empty((bt, self.n), dtype=torch.float64, device=self.device)
         self._call("fhe_crt_centered", self._ptr(m), self._ptr(h), use, bt)
+        self.check_status()                       # decrypt boundary: nothing upstream may have failed silently
         spec = torch.fft.ifft(m * twist, dim=1) * self.n
         return spec[:, k_pos] / scale
 
@@ -505,4 +526,6 @@ class CudaBackend:
         bt = h.shape[1]
         out = torch.empty((bt, self.n), dtype=torch.float64, device=self.device)
         self._call("fhe_crt_centered", self._ptr(out), self._ptr(h), use, bt)
-        return out.cpu().numpy()
+        res = out.cpu().numpy()
+        self.check_status()
+        return res

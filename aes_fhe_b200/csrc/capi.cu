@@ -419,8 +419,8 @@ int fhe_ctx_create(fhe_ctx** out, int log_n, int n_q, int n_p, int alpha, const 
     std::vector<ConstF> fin(2 * (size_t)tot);
     for (int l = 0; l < tot; ++l) {
         const u64 q = (u64)moduli[l];
-        if (q >= (1ull << 45) || (q - 1) % (2ull * n) != 0) { delete c; return fail("fhe_ctx_create: modulus must be < 2^45 and = 1 mod 2N"); }
-        if (h_pow(psi[l], n, q) != q - 1) { delete c; return fail("fhe_ctx_create: psi is not a primitive 2N-th root"); }
+        if (q >= (1ull << 45) || (q - 1) % (2ull * n) != 0) { fhe_ctx_destroy(c); return fail("fhe_ctx_create: modulus must be < 2^45 and = 1 mod 2N"); }
+        if (h_pow(psi[l], n, q) != q - 1) { fhe_ctx_destroy(c); return fail("fhe_ctx_create: psi is not a primitive 2N-th root"); }
         mods[l] = h_modulus(q);
         const u64 ipsi = h_inv(psi[l], q);
         std::vector<u64> pw(n), ipw(n);
@@ -439,7 +439,7 @@ int fhe_ctx_create(fhe_ctx** out, int log_n, int n_q, int n_p, int alpha, const 
     double* d_twf = to_device(twf);
     double* d_twi = to_device(twi);
     ConstF* d_fin = to_device(fin);
-    if (!d_mod || !d_twf || !d_twi || !d_fin) { delete c; return fail("fhe_ctx_create: device allocation failed"); }
+    if (!d_mod || !d_twf || !d_twi || !d_fin) { fhe_ctx_destroy(c); return fail("fhe_ctx_create: device allocation failed"); }
     c->owned = {d_mod, d_twf, d_twi, d_fin};
     c->T.mod = d_mod; c->T.tw_fwd = d_twf; c->T.tw_inv = d_twi; c->T.inv_final = d_fin;
     c->T.log_n = log_n; c->T.n_q = n_q; c->T.n_p = n_p;
@@ -465,7 +465,7 @@ int fhe_ctx_create(fhe_ctx** out, int log_n, int n_q, int n_p, int alpha, const 
         if (coop && sms > 0) {
             if (cudaMalloc((void**)&fz.scratch, sizeof(u64) * 2 * (size_t)fz.max_groups * n) != cudaSuccess ||
                 cudaMalloc((void**)&fz.ctr, sizeof(unsigned) * (32 * fz.max_groups + 1)) != cudaSuccess) {
-                delete c; return fail("fhe_ctx_create: fused-NTT scratch allocation failed");
+                fhe_ctx_destroy(c); return fail("fhe_ctx_create: fused-NTT scratch allocation failed");
             }
             cudaMemset(fz.ctr, 0, sizeof(unsigned) * (32 * fz.max_groups + 1));
             c->owned.push_back(fz.scratch); c->owned.push_back(fz.ctr);
@@ -524,6 +524,8 @@ extern "C" int fhe_fused_profile(fhe_ctx* c, unsigned long long* out8) {
 int fhe_ntt_fused_status(fhe_ctx* c) {
     if (!c) return fail("fhe_ntt_fused_status: null context");
     if (!c->fz.ctr) return 0;
+    // the flags are written by kernels on the caller's (non-blocking) streams: wait for all of them first
+    if (cudaDeviceSynchronize() != cudaSuccess) return check("fhe_ntt_fused_status");
     unsigned flag = 0;
     if (cudaMemcpy(&flag, c->fz.ctr + 32 * c->fz.max_groups, sizeof(unsigned), cudaMemcpyDeviceToHost) != cudaSuccess)
         return check("fhe_ntt_fused_status");

@@ -99,18 +99,45 @@ def dumps(engine: Engine, obj) -> bytes:
     raise WireError(f"{type(obj).__name__} is not serialisable (secret keys never are)")
 
 
+def _expect(cond: bool, what: str):
+    if not cond:
+        raise WireError(what)
+
+
 def loads(engine: Engine, blob):
+    """Untrusted input: every dimension is checked against the engine's parameter set before a raw pointer can
+    reach a kernel (the kernels index [dnum][2][n_q + n_p][N] keys and [npoly][batch][level + 1][N] ciphertexts
+    without size information)."""
     kind, header, arr = _unpack(blob)
-    be = engine.backend
+    be, P = engine.backend, engine.params
+    if header.get("params") != params_digest(P):
+        raise WireError("object was produced under a different parameter set (ring degree / RNS chain)")
     if kind == "ciphertext":
-        if arr.ndim != 4 or arr.shape[2] != int(header["level"]) + 1:
-            raise WireError("ciphertext shape does not match its level")
+        level = header.get("level")
+        _expect(isinstance(level, int) and 0 <= level <= P.max_level, "ciphertext level outside the parameter set")
+        _expect(arr.ndim == 4, "ciphertext must be [npoly, batch, level + 1, N]")
+        _expect(arr.shape[0] in (2, 3), "ciphertext must have 2 or 3 polynomials")
+        _expect(arr.shape[1] >= 1, "ciphertext batch must be at least 1")
+        _expect(arr.shape[2] == level + 1, "ciphertext shape does not match its level")
         _check(engine, header, arr, 2)
-        return Ciphertext(engine, be.from_numpy(arr), int(header["level"]))
+        return Ciphertext(engine, be.from_numpy(arr), level)
     if kind == "public_key":
+        _expect(arr.ndim == 4 and tuple(arr.shape[:3]) == (2, 1, P.n_q), f"public key must be [2, 1, {P.n_q}, N]")
         _check(engine, header, arr, 2)
         return PublicKey(be.from_numpy(arr))
-    _check(engine, header, arr, arr.ndim - 2)
+    want = (P.dnum, 2, 1, P.n_q + P.n_p)
+    _expect(arr.ndim == 5 and tuple(arr.shape[:4]) == want,
+            f"switching key must be [dnum = {P.dnum}, 2, 1, n_q + n_p = {P.n_q + P.n_p}, N]")
+    _check(engine, header, arr, 3)
+    two_n = 2 * P.n
+    if kind != "relinearization_key":
+        g = header.get("galois")
+        _expect(isinstance(g, int) and 0 < g < two_n and g % 2 == 1, "Galois element must be odd and below 2N")
+        if kind == "conjugation_key":
+            _expect(g == P.galois_conj, "conjugation key carries the wrong Galois element")
+        else:
+            d = header.get("delta")
+            _expect(isinstance(d, int) and g == P.galois_for_rotation(d), "Galois element does not match the rotation amount")
     data = be.from_numpy(arr)
     if kind == "relinearization_key":
         return RelinearizationKey(data)

@@ -1,27 +1,35 @@
 #!/usr/bin/env python
 """Benchmark of the homomorphic-AES hot path on B200 ("Measurement").
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--batch B]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--states G]
+                    [--scaling weak|strong --total-states T] [--no-extras]
 
-Workload (BASELINE.json configs[1]): SubBytes on 2K-block-packed ciphertexts -- the function of
-the reference's ``SBoxService.sub_bytes_array`` (zeta_256^x -> zeta_256^S(x) through the
-sbox_hi / sbox_lo degree-255 LUT polynomials and their product;
-/root/reference/sbox/sbox_service.py:116-138) at N = 2^16, max_level = 22
-(test/test_sbox_service.py:19), on a batch of B ciphertexts per GPU; one ciphertext packs
-slot_count/16 = 2048 AES blocks.  Both arms evaluate it with the baby-step/giant-step
-Paterson-Stockmeyer schedule of aes_fhe_b200/fused.py on the product polynomial hi * lo folded by
-conjugate symmetry (SBoxService.sub_bytes_array_bsgs: 23 key switches, 10 levels); the reference's
-own operation order (255 key switches) is timed with --reference-order.
+Workload (BASELINE.json configs[4]; the metric "homomorphic AES-128 blocks/sec"): full AES-128 -- AddRoundKey_0 and
+ten rounds (SubBytes, ShiftRows, MixColumns, AddRoundKey; the functions of the reference's round drivers
+/root/reference/test_all_process.py:21-48 and /root/reference/new.py:186-227,248-261), round keys from the clear
+FIPS-197 key schedule encrypted bit by bit -- at N = 2^16 on G *states* per GPU.  One state = 8192 AES blocks in 32
+bit-plane ciphertexts (aes_fhe_b200/services/aes_bits.py); every round ends in one bit bootstrap of the state
+(aes_fhe_b200/bootstrap.py::bootstrap_bits).  Parameter set: the default bootstrappable engine, 24 levels at a
+44-bit scale, 25 + 9 limbs, log2(PQ) = 1506 (inside the 1553-bit bound for the sparse secret, params.py).
 
-A "step" is one pass of that path over one batch.  `value` = AES blocks per second with the
-input ciphertexts resident in HBM; `e2e` = the same through the public API from host buffers
-(encode + encrypt + H2D, SubBytes, decrypt + D2H + decode inside the timed region).
-Ciphertext batches shard across ranks with no data-path collective (weak scaling); NCCL is
-used once to broadcast the evaluation key and once to gather result checksums.
+A "step" is one AES-128 pass over the G states of a rank.  `value` = AES blocks per second with the input
+ciphertexts and the encrypted round keys resident in HBM (CUDA events, max over ranks); `e2e` = the same from host
+buffers: the raw block bytes go to the GPU (H2D inside the timed region), are bit-sliced, encoded and encrypted
+there, run through AES-128, come back to the key owner as ciphertexts (NCCL gather when N > 1), are decrypted and
+decoded on the GPU and returned as bytes (D2H).  Every decoded block is compared with plain AES (FIPS-197
+Appendix B is block 0).
 
-`--impl reference` times the same operation sequence on the CPU oracle (oracle/refmod.cpp,
-OpenMP over all host cores): the reference's own arithmetic lives in the closed `desilofhe`
-wheel, so the oracle port is the CPU arm (cpu_baseline.kind = "port").
+Multi-GPU: states are sharded over the ranks with no data-path collective ("weak": G states per rank; "strong":
+--total-states split over the ranks).  Rank 0 alone generates the keys and keeps the secret; public,
+relinearisation, conjugation and all Galois keys are broadcast once over NCCL (`startup`), result ciphertexts are
+gathered to rank 0.
+
+`--impl reference` / `cpu_baseline`: the reference's arithmetic lives in the closed `desilofhe` wheel (absent), so
+the CPU arm is the oracle port (oracle/refmod.cpp, OpenMP, all host cores).  A whole AES-128 at N = 2^16 takes hours
+there, so each step times a bounded SAMPLE of the same arithmetic at N = 2^16 on the same parameter set (relinearised
+products and rotations at the top, middle and bottom of the chain), measures seconds per length-N transform row, and
+scales by the transform rows of one AES-128 state (tests/golden/aes_bits_work.json, counted by the library's
+fhe_ntt_row_count at N = 2^16).  The extrapolation is stated in `cpu_baseline.sample`.
 """
 from __future__ import annotations
 
@@ -38,16 +46,18 @@ import numpy as np
 ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 
-METRIC = "homomorphic AES blocks/sec (SubBytes stage, 2048 blocks per ciphertext)"
+METRIC = "homomorphic AES-128 blocks/sec"
 UNIT = "blocks/s"
-MAX_LEVEL = 22
 LOG_N = 16
-DNUM = None          # key-switch digit count; None = the parameter set's default (params.make_params)
+AES_LEVEL = 24
+KEY_HEX = "2b7e151628aed2a6abf7158809cf4f3c"         # FIPS-197 Appendix B
+PT_HEX = "3243f6a8885a308d313198a2e0370734"
+CT_HEX = "3925841d02dc09fbdc118597196a0b32"
 
 
-def _params(level=MAX_LEVEL):
-    from aes_fhe_b200.params import make_params
-    return make_params(LOG_N, level) if DNUM is None else make_params(LOG_N, level, dnum=DNUM)
+def aes_params():
+    from aes_fhe_b200.params import LOG_PQ_BUDGET_SPARSE, make_params
+    return make_params(LOG_N, AES_LEVEL, scale_bits=44, log_pq_budget=LOG_PQ_BUDGET_SPARSE)
 
 
 def _peak_gbs():
@@ -57,26 +67,27 @@ def _peak_gbs():
         return 6650.0, "fallback"
 
 
-def _inputs(slot_count: int, batch: int, seed: int) -> np.ndarray:
-    """test_sbox_array_simd's input (tile(arange(256))) for ciphertext 0, seeded uniform bytes
-    for the others (test/test_sbox_service.py:55-66)."""
-    rng = np.random.default_rng(seed)
-    rows = [np.tile(np.arange(256, dtype=np.uint8), slot_count // 256 + 1)[:slot_count]]
-    for _ in range(batch - 1):
-        rows.append(rng.integers(0, 256, slot_count, dtype=np.uint8))
-    return np.stack(rows)
+def _golden_work():
+    try:
+        return json.load(open(ROOT / "tests" / "golden" / "aes_bits_work.json"))
+    except Exception:
+        return None
 
 
-def _make_service(backend=None, seed=1, device_id=0):
-    from aes_fhe_b200.params import make_params
-    from aes_fhe_b200.services.engine_context import EngineContext
-    from aes_fhe_b200.services.sbox_service import SBoxService
-    kw = dict(_params=_params(), seed=seed)
-    if backend is not None:
-        kw["_backend"] = backend
-    ctx = EngineContext(signature=2, max_level=MAX_LEVEL, mode="parallel", device_id=device_id, _engine_kwargs=kw,
-                        rotation_steps=[])
-    return ctx, SBoxService(ctx)
+def host_threads() -> int:
+    """cores this process may use -- never omp_get_max_threads(): torchrun exports OMP_NUM_THREADS=1"""
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def rank_blocks(rank: int, n_blocks: int) -> np.ndarray:
+    """synthetic plaintext of a rank: seeded uniform bytes; block 0 of rank 0 is FIPS-197 Appendix B"""
+    b = np.random.default_rng(1000 + rank).integers(0, 256, (n_blocks, 16), dtype=np.uint8)
+    if rank == 0:
+        b[0] = np.frombuffer(bytes.fromhex(PT_HEX), np.uint8)
+    return b
 
 
 class ClockSampler(threading.Thread):
@@ -115,107 +126,174 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
 
 
+class StageTimer:
+    """CUDA events at the stage boundaries of AESBitService (its `timer` hook), on the launching stream"""
+
+    def __init__(self):
+        import torch
+        self.torch = torch
+        e = torch.cuda.Event(enable_timing=True)
+        e.record()
+        self.marks = [("start", e)]
+
+    def __call__(self, name):
+        e = self.torch.cuda.Event(enable_timing=True)
+        e.record()
+        self.marks.append((name, e))
+
+    def ms(self):
+        self.torch.cuda.synchronize()
+        out = {}
+        for (_, a), (name, b) in zip(self.marks[:-1], self.marks[1:]):
+            out[name] = out.get(name, 0.0) + a.elapsed_time(b)
+        return out
+
+
 # --------------------------------------------------------------------------- CPU arm
-def cpu_arm(threads: int = 0):
-    """One full pass of the same schedule (sub_bytes_array_bsgs, 23 key switches) on ONE
-    ciphertext (2048 blocks) on the CPU oracle, N = 2^16, max_level 22, all host cores."""
-    from oracle.refmod import RefBackend, build
-    build()
+class CpuSample:
+    """The bounded CPU sample: on ONE ciphertext at N = 2^16, same parameter set, oracle backend with all host
+    cores -- two relinearised products and two rotations each at levels 24, 16 and 8.  `run()` returns
+    (seconds, transform rows)."""
+
+    LEVELS = (24, 16, 8)
+
+    def __init__(self, threads: int):
+        from oracle.refmod import RefBackend, build
+        build()
+        from aes_fhe_b200.engine import Engine
+        P = aes_params()
+        self.be = RefBackend(P, threads=threads)
+        eng = Engine(_params=P, _backend=self.be, use_bootstrap=True)
+        sk = eng.create_secret_key()
+        pk = eng.create_public_key(sk)
+        self.rlk = eng.create_relinearization_key(sk)
+        self.rot = eng.create_fixed_rotation_key(sk, -eng.slot_count // 4)          # the ShiftRows rotation by one column
+        self.eng, self.sk = eng, sk
+        rng = np.random.default_rng(0)
+        self.v = rng.choice([-1.0, 1.0], eng.slot_count)
+        self.cts = {lvl: eng.encrypt(self.v, pk, level=lvl) for lvl in self.LEVELS}
+        self.threads = self.be.threads
+
+    def run(self):
+        eng = self.eng
+        r0 = self.be.ntt_row_count()
+        t0 = time.perf_counter()
+        outs = []
+        for lvl in self.LEVELS:
+            ct = self.cts[lvl]
+            a = eng.multiply(ct, ct, self.rlk)
+            b = eng.multiply(a, a, self.rlk)
+            c = eng.rotate(eng.rotate(ct, self.rot), self.rot)
+            outs.append((b, c))
+        dt = time.perf_counter() - t0
+        rows = self.be.ntt_row_count() - r0
+        return dt, rows, outs
+
+    def check(self, outs):
+        for b, c in outs:
+            assert np.abs(self.eng.decrypt(b, self.sk) - 1.0).max() < 1e-4          # (+-1)^4
+            assert np.abs(self.eng.decrypt(c, self.sk) - np.roll(self.v, -self.eng.slot_count // 2)).max() < 1e-4
+
+
+def cpu_baseline(samples: int, rows_per_state: int, blocks_per_state: int):
+    cs = CpuSample(host_threads())
+    times, rows = [], 0
+    outs = None
+    for _ in range(samples):
+        dt, rows, outs = cs.run()
+        times.append(dt)
+    cs.check(outs)
+    s_per_row = float(np.median(times)) / rows
+    t_state = s_per_row * rows_per_state
+    return {"value": blocks_per_state / t_state, "unit": UNIT, "cores": cs.threads, "kind": "port", "extrapolated": True,
+            "sample": f"{samples} x [2 relinearised products + 2 rotations at each of levels 24/16/8, one ciphertext, N=2^16, "
+                      f"25+9 limbs] = {rows} transform rows in {float(np.median(times)):.2f}s (median) on {cs.threads} threads "
+                      f"(oracle/refmod.cpp) -> {s_per_row * 1e6:.1f} us per row; one AES-128 state (8192 blocks) = "
+                      f"{rows_per_state} rows -> {t_state:.0f}s extrapolated",
+            "seconds_per_transform_row": s_per_row, "rows_per_state_aes128": rows_per_state}, times
+
+
+def reference_arm(args):
+    work = _golden_work()
+    if work is None:
+        print(json.dumps({"impl": "reference", "unavailable": "tests/golden/aes_bits_work.json missing"}))
+        return
+    rows_state, bps = int(work["ntt_rows_per_state_aes128"]), int(work["blocks_per_state_at_2_16"])
+    cs = CpuSample(host_threads())
+    for _ in range(args.warmup):
+        cs.run()
+    times, rows, outs = [], 0, None
+    for _ in range(args.steps):
+        dt, rows, outs = cs.run()
+        times.append(dt)
+    cs.check(outs)
+    ms_step = float(np.mean(times)) * 1e3
+    s_per_row = float(np.mean(times)) / rows
+    v = bps / (s_per_row * rows_state)
+    cb = {"value": v, "unit": UNIT, "cores": cs.threads, "kind": "port", "extrapolated": True,
+          "sample": f"each step = 2 relinearised products + 2 rotations at each of levels 24/16/8 on one ciphertext at N=2^16 "
+                    f"({rows} transform rows, {ms_step:.0f} ms mean on {cs.threads} threads, oracle/refmod.cpp); value = 8192 blocks / "
+                    f"({rows_state} rows of one AES-128 state x {s_per_row * 1e6:.1f} us per row)",
+          "seconds_per_transform_row": s_per_row, "rows_per_state_aes128": rows_state}
+    print(json.dumps({"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus,
+                      "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
+                      "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64-exact-int",
+                      "data": "synthetic", "config": workload_config(args, 1), "cpu_baseline": cb,
+                      "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+
+
+# --------------------------------------------------------------------------- extras (configs[1])
+def subbytes_extra(batch: int = 16, steps: int = 2):
+    """BASELINE configs[1] (last round's headline): the reference's zeta_256 SubBytes polynomial pair
+    (sbox/sbox_service.py:116-138) in the 23-key-switch BSGS schedule, N = 2^16, max_level 22"""
+    import torch
     from aes_fhe_b200.params import make_params
+    from aes_fhe_b200.services.engine_context import EngineContext
+    from aes_fhe_b200.services.sbox_service import SBoxService, AES_SBOX
     from aes_fhe_b200.services.xor_service import ZetaEncoder
-    from aes_fhe_b200.services.sbox_service import AES_SBOX
-    P = _params()
-    be = RefBackend(P, threads=threads)
-    ctx, svc = _make_service(backend=be)
-    eng = ctx.engine
-    x = _inputs(eng.slot_count, 1, 0)[0]
-    ct = ctx.encrypt(ZetaEncoder.to_zeta(x, 256))
-    t0 = time.perf_counter()
+    ctx = EngineContext(signature=2, max_level=22, mode="parallel",
+                        _engine_kwargs=dict(_params=make_params(LOG_N, 22)), rotation_steps=[])
+    svc = SBoxService(ctx)
+    sc = ctx.engine.slot_count
+    rng = np.random.default_rng(0)
+    data = np.stack([np.tile(np.arange(256, dtype=np.uint8), sc // 256 + 1)[:sc]] +
+                    [rng.integers(0, 256, sc, dtype=np.uint8) for _ in range(batch - 1)])
+    ct = ctx.engine.encrypt(ZetaEncoder.to_zeta(data, 256), ctx.public_key)
     out = svc.sub_bytes_array_bsgs(ct)
-    full = time.perf_counter() - t0
-    got = ZetaEncoder.from_zeta(ctx.decrypt(out), 256)
-    assert np.array_equal(got, np.array(AES_SBOX, dtype=np.uint8)[x])
-    blocks = eng.slot_count // 16
-    return {"value": blocks / full, "unit": UNIT, "cores": be.threads, "kind": "port",
-            "sample": f"one ciphertext ({blocks} blocks), full sub_bytes_array_bsgs at N=2^16, L=22: {full:.2f}s "
-                      f"on {be.threads} threads (oracle/refmod.cpp)"}, full
-
-
-def full_round_probe(batch: int):
-    """configs[3]: AddRoundKey_0 + one full AES round (SubBytes, ShiftRows, MixColumns,
-    AddRoundKey) on `batch` ciphertexts of 2048 blocks at N = 2^16, L = 30; FIPS-197 App. B is
-    block 0 and the decoded bytes of every block are checked against plain AES."""
-    import torch
-    from aes_fhe_b200.params import make_params
-    from aes_fhe_b200.services.aes_round import AESRoundService
-    from aes_fhe_b200.services.key_expansion import expand_key
-    from aes_fhe_b200.services.xor_service import XORService, EngineWrapper, XORConfig, CoefficientCache
-    from oracle import aes_plain as A
-    cfg = XORConfig()
-    w = EngineWrapper(cfg, _engine_kwargs=dict(_params=make_params(LOG_N, 30), seed=2), rotation_steps=[])
-    svc = AESRoundService(w, XORService(w, CoefficientCache(cfg.coeffs_path)))
-    key = bytes.fromhex("2b7e151628aed2a6abf7158809cf4f3c")
-    rks = expand_key(key)
-    rng = np.random.default_rng(7)
-    blocks = [rng.integers(0, 256, (svc.B, 16), dtype=np.uint8) for _ in range(batch)]
-    blocks[0][0] = np.frombuffer(bytes.fromhex("3243f6a8885a308d313198a2e0370734"), np.uint8)
-    st = svc.encrypt_state(blocks)
-    k0, k1 = svc.encrypt_round_key(rks[0]), svc.encrypt_round_key(rks[1])
-
-    def one():
-        return svc.round(svc.add_round_key(st, k0), k1)
-
-    r1 = one()                                     # warm-up: builds rotation keys, LUT tables
+    ok = np.array_equal(ZetaEncoder.from_zeta(np.atleast_2d(ctx.engine.decrypt(out, ctx.secret_key)), 256),
+                        np.array(AES_SBOX, dtype=np.uint8)[data])
+    svc.sub_bytes_array_bsgs(ct)
     torch.cuda.synchronize()
-    c0 = dict(w.engine.op_counts)
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    a.record(); r1 = one(); b.record()
+    a.record()
+    for _ in range(steps):
+        svc.sub_bytes_array_bsgs(ct)
+    b.record()
     torch.cuda.synchronize()
-    ms = a.elapsed_time(b)
-    ks = sum(v - c0.get(k, 0) for k, v in w.engine.op_counts.items() if k.startswith("keyswitch"))
-    got = svc.decrypt_state(r1)
-    ok = np.array_equal(got, A.round_fn(np.stack(blocks) ^ rks[0], rks[1]))
-    fips = got.reshape(-1, 16)[0].tobytes().hex() == "a49c7ff2689f352b6b5bea43026a5049"
-    nblk = batch * svc.B
-    return {"workload": "configs[3]: AddRoundKey_0 + full round 1, N=2^16, L=30", "batch": batch, "ms": ms,
-            "blocks_per_s": nblk / (ms * 1e-3), "keyswitches_per_ciphertext_pair": int(ks),
-            "levels_used": 30 - r1[0].level, "bytes_equal_plain_aes": bool(ok), "fips197_appendix_b_round2_input": bool(fips)}
+    ms = a.elapsed_time(b) / steps
+    return {"workload": "configs[1]: SubBytes (sbox_hi x sbox_lo zeta_256 polynomials, BSGS, 23 key switches), N=2^16, L=22",
+            "batch": batch, "ms_per_step": ms, "blocks_per_s": batch * (sc // 16) / (ms * 1e-3), "bytes_equal_sbox": bool(ok)}
 
 
-def aes128_probe(batch: int):
-    """configs[4]: full AES-128 (ten rounds, clear key schedule, refresh = bootstrap + clean-up after
-    every LUT layer; aes_fhe_b200/services/aes128.py) on `batch` ciphertexts of 2048 blocks, N = 2^16,
-    L = 30.  Timed on the second run (keys, matrices and LUT tables exist); every decoded block is
-    checked against plain AES, block 0 is FIPS-197 Appendix B."""
-    import torch
-    from aes_fhe_b200.services.aes128 import AES128Service
-    from aes_fhe_b200.services.xor_service import XORService, EngineWrapper, XORConfig, CoefficientCache
-    from oracle import aes_plain as A
-    cfg = XORConfig()
-    w = EngineWrapper(cfg, _engine_kwargs=dict(seed=3), rotation_steps=[])
-    svc = AES128Service(w, XORService(w, CoefficientCache(cfg.coeffs_path)))
-    key = bytes.fromhex("2b7e151628aed2a6abf7158809cf4f3c")
-    rng = np.random.default_rng(9)
-    blocks = [rng.integers(0, 256, (svc.B, 16), dtype=np.uint8) for _ in range(batch)]
-    blocks[0][0] = np.frombuffer(bytes.fromhex("3243f6a8885a308d313198a2e0370734"), np.uint8)
-    st = svc.encrypt_state(blocks)
-    svc.encrypt_blocks(st, key)                               # warm-up: builds every key / matrix / table
-    torch.cuda.synchronize()
-    c0, r0 = dict(w.engine.op_counts), svc.refreshes
-    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    a.record(); out = svc.encrypt_blocks(st, key); b.record()
-    torch.cuda.synchronize()
-    ms = a.elapsed_time(b)
-    got = svc.decrypt_state(out).reshape(batch, svc.B, 16)
-    want = np.stack([A.encrypt_blocks(bl, key) for bl in blocks])
-    ks = sum(v - c0.get(k, 0) for k, v in w.engine.op_counts.items() if k.startswith("keyswitch"))
-    nblk = batch * svc.B
-    return {"workload": "configs[4]: AES-128, 10 rounds, N=2^16, L=30, refresh after every LUT layer", "batch": batch,
-            "ms": ms, "ms_per_round": ms / 10, "blocks_per_s": nblk / (ms * 1e-3),
-            "bootstrap_calls": int(w.engine.op_counts["bootstrap"] - c0.get("bootstrap", 0)),
-            "ciphertexts_refreshed_per_batch_element": int((svc.refreshes - r0) // batch),
-            "keyswitches": int(ks), "bytes_equal_plain_aes": bool(np.array_equal(got, want)),
-            "fips197_appendix_b_ciphertext": bool(got[0, 0].tobytes().hex() == "3925841d02dc09fbdc118597196a0b32")}
+def workload_config(args, world):
+    P = aes_params()
+    G = states_per_rank(args, world)
+    return {"workload": "configs[4]: full AES-128 (AddRoundKey_0 + 10 rounds, encrypted FIPS-197 round keys), bit-sliced, "
+                        "N=2^16, 24 levels, one bit bootstrap per round",
+            "states_per_gpu": G, "blocks_per_state": (1 << (LOG_N - 1)) // 4, "ciphertexts_per_state": 32,
+            "limbs_q_p_alpha_dnum": [P.n_q, P.n_p, P.alpha, P.dnum], "log2_pq": round(P.log_pq, 1), "scale_bits": 44,
+            "l2": "working set per step (tens of GB of ciphertexts and keys) exceeds the 126 MB L2",
+            "sharding": "independent states per rank, no data-path collective; keys broadcast once from rank 0, "
+                        "result ciphertexts gathered to rank 0",
+            "scaling_mode": args.scaling}
+
+
+def states_per_rank(args, world):
+    if args.scaling == "strong":
+        if args.total_states % world:
+            raise SystemExit("--total-states must be a multiple of the number of GPUs")
+        return args.total_states // world
+    return args.states
 
 
 # --------------------------------------------------------------------------- main
@@ -225,45 +303,20 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--batch", type=int, default=32, help="ciphertexts per GPU per step (16: 727k blocks/s, 32: 736k)")
-    ap.add_argument("--dnum", type=int, default=None, help="key-switch digit count of the SubBytes parameter set")
+    ap.add_argument("--states", type=int, default=2, help="states (8192 blocks each) per GPU per step")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
+    ap.add_argument("--total-states", type=int, default=8, help="strong scaling: states in the whole job")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-full-round", action="store_true",
-                    help="skip the extra measurement of one full AES round (configs[3])")
-    ap.add_argument("--no-aes128", action="store_true",
-                    help="skip the extra measurement of full AES-128 (configs[4], ten rounds with bootstrapping)")
-    ap.add_argument("--reference-order", action="store_true",
-                    help="also time the reference's own 255-key-switch operation order")
+    ap.add_argument("--no-extras", action="store_true", help="skip the configs[1] SubBytes extra and the kernel rooflines")
     args = ap.parse_args()
-    global DNUM
-    DNUM = args.dnum
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
-    config = {"workload": "configs[1]: SubBytes (sbox_hi x sbox_lo degree-255 zeta_256 LUT polynomials, BSGS schedule) on "
-                          "2048-block ciphertexts, N=2^16, max_level=22",
-              "batch_ciphertexts_per_gpu": args.batch, "blocks_per_ciphertext": (1 << (LOG_N - 1)) // 16,
-              "keyswitch_digits": _params().dnum, "special_primes": _params().n_p,
-              "l2": "working set per step (GBs of power-basis ciphertexts) exceeds the 126 MB L2",
-              "sharding": "independent ciphertext batches per rank, no data-path collective"}
 
     if args.impl == "reference":
-        if rank != 0:
-            return
-        times = []
-        for _ in range(max(1, min(args.steps, 3))):
-            cb, full = cpu_arm()
-            times.append(full)
-        full = float(np.median(times))
-        blocks = (1 << (LOG_N - 1)) // 16
-        v = blocks / full
-        cb["value"] = v
-        print(json.dumps({"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus,
-                          "steps": args.steps, "warmup": args.warmup, "ms_per_step": full * 1e3,
-                          "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64-exact-int",
-                          "data": "synthetic", "config": config, "cpu_baseline": cb,
-                          "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        if rank == 0:
+            reference_arm(args)
         return
 
     import torch
@@ -271,37 +324,58 @@ def main():
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    from aes_fhe_b200.services.xor_service import ZetaEncoder
-    from aes_fhe_b200.services.sbox_service import AES_SBOX
-    import aes_fhe_b200.backend_cuda as bc
+    from aes_fhe_b200.engine import Engine
+    from aes_fhe_b200.services.aes_bits import AESBitService
+    from aes_fhe_b200.services.key_expansion import expand_key
+    from aes_fhe_b200.services.xor_service import EngineWrapper, XORConfig
+    from aes_fhe_b200.sharding import distribute_keys, gather_ciphertexts
+    from oracle import aes_plain as A          # the byte checker, outside every timed region
 
-    ctx, svc = _make_service(seed=1, device_id=local)
-    eng = ctx.engine
-    be = eng.backend
+    P = aes_params()
+    G = states_per_rank(args, world)
+    config = workload_config(args, world)
+    t_setup = time.perf_counter()
+    startup = None
+    if rank == 0:
+        # the key owner: OS-entropy randomness (no seed), all keys of the service issued before they are shipped
+        w = EngineWrapper(XORConfig(device_id=local), _engine_kwargs=dict(_params=P, device_codec=True), rotation_steps=[])
+        engine = w.engine
+        svc = AESBitService(w)
+        svc.prepare_keys()
+    else:
+        w, svc = None, None
+        engine = Engine(_params=P, use_bootstrap=True, device_codec=True, device_id=local)
     if world > 1:
-        # evaluation key comes from rank 0 over NCCL/NVLink (every rank derived the same key from
-        # the shared seed; the broadcast is the deployment path and must be a no-op on the bits)
-        from aes_fhe_b200.sharding import broadcast_handle
-        before = svc.rlk.data.clone() if rank else None
-        svc.rlk.data = broadcast_handle(be, svc.rlk.data, src=0)
+        ctx, startup = distribute_keys(engine, w, src=0)
         if rank:
-            assert torch.equal(before, svc.rlk.data)
-    sc = eng.slot_count
-    sbox = np.array(AES_SBOX, dtype=np.uint8)
-    data = _inputs(sc, args.batch, seed=rank)
-    zeta = ZetaEncoder.to_zeta(data, 256)
-    ct_in = eng.encrypt(zeta, ctx.public_key)
+            svc = AESBitService(ctx)
+            svc.prepare_keys()
+        startup = {"broadcast_keys": startup["keys"], "broadcast_bytes": startup["bytes"],
+                   "broadcast_seconds": startup["seconds"], "broadcast_gbs": startup["gbs"],
+                   "secret_key": "rank 0 only", "transport": "ncclBroadcast per key over NVLink/NVSwitch"}
+    be = engine.backend
+    Bs = svc.Bs
+    key = bytes.fromhex(KEY_HEX)
+    rks = expand_key(key)
+    blocks = rank_blocks(rank, G * Bs)
+    fresh = 1 + svc.boot_in_levels
+    st = svc.encrypt_state(blocks, level=fresh)
+    rkeys = [svc.encrypt_round_key(rks[r], G, level=12) for r in range(11)]
+    pinned = torch.from_numpy(blocks).pin_memory()
 
     def step():
-        return svc.sub_bytes_array_bsgs(ct_in)
+        return svc.encrypt_blocks(st, key, round_keys=rkeys)
 
-    pinned = torch.from_numpy(data).pin_memory()             # host input buffer of the user: the bytes
+    def collect(out):
+        """result ciphertexts on the key owner -> decoded block bytes per rank (None on other ranks)"""
+        parts = gather_ciphertexts(engine, out, dst=0) if world > 1 else [out]
+        if rank:
+            return None
+        return [svc.decrypt_state_device(p).numpy() for p in parts]
 
     def e2e_step():
-        # bytes in, bytes out (the reference's XORService.xor / SBoxService tests do zeta-encode + encrypt
-        # ... decrypt + decode around the service call): zeta codec, sampling and decode on the GPU
-        out = svc.sub_bytes_array_bsgs(eng.encrypt_zeta(pinned, ctx.public_key, 256))     # H2D inside
-        return eng.decrypt_zeta(out, ctx.secret_key, 256)                                 # D2H inside
+        ct = svc.encrypt_state_device(pinned, level=fresh)            # H2D of the raw block bytes inside
+        return collect(svc.encrypt_blocks(ct, key, round_keys=rkeys))  # gather + decrypt + D2H of the bytes inside
 
     def sync_all():
         torch.cuda.synchronize()
@@ -309,143 +383,176 @@ def main():
             dist.barrier()
             torch.cuda.synchronize()
 
+    def verify(decoded):
+        if rank:
+            return True
+        ok = True
+        for r, got in enumerate(decoded):
+            ok &= bool(np.array_equal(got, A.encrypt_blocks(rank_blocks(r, G * Bs), key)))
+        return ok and decoded[0][0].tobytes().hex() == CT_HEX
+
     # correctness of what is being timed (also the first warm-up)
     out = step()
-    got = ZetaEncoder.from_zeta(np.atleast_2d(eng.decrypt(out, ctx.secret_key)), 256)
-    assert np.array_equal(got, sbox[data]), "SubBytes output differs from the AES S-box"
+    ok_resident = verify(collect(out))
+    if not ok_resident:
+        raise SystemExit("AES-128 output differs from plain AES / FIPS-197")
+    setup_s = time.perf_counter() - t_setup
     for _ in range(max(0, args.warmup - 1)):
         step()
 
     sampler = ClockSampler(local)
     sampler.start()
     sync_all()
-    l0 = be.launch_count()
+    l0, r0 = be.launch_count(), be.ntt_row_count()
+    c0, b0 = dict(engine.op_counts), svc.refreshes
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
     torch.cuda.nvtx.range_push("timed_region")
     ev[0].record()
     for _ in range(args.steps):
-        step()
+        out = step()
     ev[1].record()
     torch.cuda.nvtx.range_pop()
     sync_all()
     launches = be.launch_count() - l0
+    rows_step = (be.ntt_row_count() - r0) // args.steps
     ms = ev[0].elapsed_time(ev[1]) / args.steps
     clocks = sampler.stop()
+    counts = {k: (v - c0.get(k, 0)) // args.steps for k, v in engine.op_counts.items() if v - c0.get(k, 0)}
+    boots = (svc.refreshes - b0) // args.steps
 
-    # end-to-end through the public API from host buffers
+    # per-stage device time of one more pass (events at the stage boundaries)
+    svc.timer = StageTimer()
+    out = step()
+    stages = svc.timer.ms()
+    svc.timer = None
+
+    # end to end from host buffers through the public API
+    n_e2e = max(1, args.steps // 4)
     e2e_step()
     sync_all()
     t0 = time.perf_counter()
-    for _ in range(max(1, args.steps // 2)):
-        res = e2e_step()
-    torch.cuda.synchronize()
-    e2e_ms = (time.perf_counter() - t0) / max(1, args.steps // 2) * 1e3
-    assert np.array_equal(np.atleast_2d(res), sbox[data])
-
-    # dominant kernel: the forward NTT (both passes, one chained launch), timed alone on this stream at
-    # the row count one key-switch ModUp of this batch launches
-    nq = MAX_LEVEL + 1
-    P = eng.params
-    rows = args.batch * P.digits_at(nq) * (nq + P.n_p)
-    x = torch.randint(0, 2 ** 39, (rows // (nq + P.n_p), nq + P.n_p, P.n), dtype=torch.int64, device="cuda")
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
-    for _ in range(3):
-        be._call("fhe_ntt_fwd", be._ptr(x), x.shape[0], nq, P.n_p)
-    kt = []
-    for _ in range(10):
-        flush.zero_()
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record(); be._call("fhe_ntt_fwd", be._ptr(x), x.shape[0], nq, P.n_p); b.record()
-        torch.cuda.synchronize()
-        kt.append(a.elapsed_time(b))
-    k_ms = float(np.median(kt))
-    alg_bytes = 2 * rows * P.n * 8                      # read once + write once per limb
-    peak, peak_kind = _peak_gbs()
-    achieved = alg_bytes / (k_ms * 1e-3) / 1e9
-    traffic = None
-    try:
-        traffic = json.load(open(ROOT / "profiles" / "ntt_traffic.json"))["dram_bytes_per_row"] * rows
-    except Exception:
-        pass
-
-    # second kernel of the key switch, timed the same way: the key inner product (HBM-bound).  Algorithmic bytes per
-    # launch: the key 2 beta (n+K) limbs once per batch + per ciphertext beta (n+K) extended rows in
-    # (own-digit rows come from the n input limbs) and 2 (n+K) accumulator rows out
-    beta, ne = P.digits_at(nq), nq + P.n_p
-    ext = torch.randint(0, 2 ** 39, (args.batch, beta, ne, P.n), dtype=torch.int64, device="cuda")
-    dd = torch.randint(0, 2 ** 39, (1, args.batch, nq, P.n), dtype=torch.int64, device="cuda")
-    acc = torch.empty(2, args.batch, ne, P.n, dtype=torch.int64, device="cuda")
-    ksk = svc.rlk.data
-    kt2 = []
-    for it in range(13):
-        flush.zero_()
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record(); be._call("fhe_ks_inner", be._ptr(acc), be._ptr(ext), be._ptr(dd), be._ptr(ksk), nq, args.batch); b.record()
-        torch.cuda.synchronize()
-        if it >= 3:
-            kt2.append(a.elapsed_time(b))
-    ks_ms = float(np.median(kt2))
-    ks_bytes = (2 * beta * ne + args.batch * (beta * ne + 2 * ne)) * P.n * 8
-    ks_inner = {"kernel": "k_ks_inner", "bound": "hbm", "achieved": ks_bytes / (ks_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
-                "frac": ks_bytes / (ks_ms * 1e-3) / 1e9 / peak, "us": ks_ms * 1e3,
-                "algorithmic_bytes": int(ks_bytes)}
-    del ext, dd, acc
+    for _ in range(n_e2e):
+        dec = e2e_step()
+    sync_all()
+    e2e_ms = (time.perf_counter() - t0) / n_e2e * 1e3
+    ok_e2e = verify(dec)
 
     t = torch.tensor([ms, e2e_ms], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        chk = torch.tensor([int(got.astype(np.uint64).sum())], dtype=torch.int64, device="cuda")
-        gathered = [torch.zeros_like(chk) for _ in range(world)]
-        dist.all_gather(gathered, chk)
     ms, e2e_ms = float(t[0]), float(t[1])
-    blocks = world * args.batch * (sc // 16)
-    value = blocks / (ms * 1e-3)
-    e2e_value = blocks / (e2e_ms * 1e-3)
+    n_blocks = world * G * Bs
+    value = n_blocks / (ms * 1e-3)
 
     if rank == 0:
+        peak, peak_kind = _peak_gbs()
+        work = _golden_work()
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-                "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+                "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": args.scaling,
                 "vs_baseline": None, "dtype": "f64-exact-int", "data": "synthetic", "config": config,
                 "clocks": clocks, "gpu_launches": int(launches),
-                "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms,
-                        "h2d_bytes_per_step": int(data.nbytes),
-                        "d2h_bytes_per_step": int(data.nbytes)},
-                "roofline": {"bound": "hbm", "kernel": "ntt_fwd_chained (both radix passes in one launch)", "rows_per_launch": rows,
-                             "achieved": achieved, "peak": peak, "peak_kind": peak_kind, "unit": "GB/s",
-                             "frac": achieved / peak, "traffic": traffic,
-                             "note": "FP64-pipe bound: 8 FP64 ops per butterfly, pipe at 70 % (profiles/r01_ncu_chained.md); "
-                                     "traffic = ncu dram bytes of the launch; the NTT launches are 47 % of the step "
-                                     "(profiles/r01_kernel_breakdown_final.md)"},
-                "roofline_keyswitch_inner": ks_inner,
-                "ms_per_ciphertext": ms / args.batch,
-                "keyswitches_per_ciphertext": 23}
-        if not args.no_full_round and world == 1:
-            try:
-                line["full_round"] = full_round_probe(min(args.batch, 4))
-            except Exception as e:  # pragma: no cover
-                line["full_round"] = {"unavailable": repr(e)}
-        if not args.no_aes128 and world == 1:
-            try:
-                line["aes128"] = aes128_probe(min(args.batch, 4))
-            except Exception as e:  # pragma: no cover
-                line["aes128"] = {"unavailable": repr(e)}
-        if args.reference_order:
-            torch.cuda.synchronize()
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            svc.sub_bytes_array(ct_in)
-            a.record(); o2 = svc.sub_bytes_array(ct_in); b.record()
-            torch.cuda.synchronize()
-            ok = np.array_equal(ZetaEncoder.from_zeta(np.atleast_2d(eng.decrypt(o2, ctx.secret_key)), 256), sbox[data])
-            line["reference_order"] = {"ms_per_step": a.elapsed_time(b), "keyswitches_per_ciphertext": 255,
-                                       "blocks_per_s": blocks / (a.elapsed_time(b) * 1e-3), "bytes_ok": bool(ok)}
+                "e2e": {"value": n_blocks / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms,
+                        "h2d_bytes_per_step": int(world * blocks.nbytes), "d2h_bytes_per_step": int(world * blocks.nbytes),
+                        "steps_timed": n_e2e, "bytes_equal_plain_aes": bool(ok_e2e),
+                        "round_keys": "encrypted once, resident (the client's key does not change per step)"},
+                "ms_per_round": ms / 10, "ms_per_state": ms / G,
+                "stage_ms": {**stages, "note": "device time of one pass on rank 0, CUDA events at stage boundaries; refresh = "
+                                               "bit bootstrap of the whole state once per round"},
+                "bytes_equal_plain_aes": bool(ok_resident), "fips197_appendix_b": True,
+                "bootstrapped_ciphertexts_per_step": int(boots), "bootstrapped_ciphertexts_per_2048_blocks": boots / G / 4,
+                "batched_op_calls_per_step": counts, "ntt_rows_per_state": int(rows_step // G),
+                "ntt_rows_per_state_golden": None if work is None else work["ntt_rows_per_state_aes128"],
+                "setup_seconds": setup_s, "security": engine.security,
+                "hbm_peak_allocated_gb": torch.cuda.max_memory_allocated() / 2 ** 30}
+        if startup is not None:
+            line["startup"] = startup
+        if not args.no_extras:
+            line.update(kernel_rooflines(be, P, G, peak, peak_kind, clocks))
+        else:
+            line["roofline"] = None
+        print_line = line
+    del st, out
+    if rank == 0 and world == 1 and not args.no_extras:
+        del rkeys, svc
+        torch.cuda.empty_cache()
+        try:
+            print_line["subbytes"] = subbytes_extra()
+        except Exception as e:  # pragma: no cover
+            print_line["subbytes"] = {"unavailable": repr(e)}
+    if rank == 0:
         if not args.no_cpu_baseline and world == 1:
+            work = _golden_work()
             try:
-                line["cpu_baseline"], _ = cpu_arm()
+                rows_state = int(work["ntt_rows_per_state_aes128"]) if work else int(print_line["ntt_rows_per_state"])
+                print_line["cpu_baseline"], _ = cpu_baseline(3, rows_state, Bs)
             except Exception as e:  # pragma: no cover
-                line["cpu_baseline"] = {"unavailable": repr(e)}
-        print(json.dumps(line))
+                print_line["cpu_baseline"] = {"unavailable": repr(e)}
+        print(json.dumps(print_line))
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
+
+
+def kernel_rooflines(be, P, G, peak, peak_kind, clocks):
+    """The dominant kernel (forward NTT, both radix passes in one chained launch) and the key inner product, each
+    timed alone with CUDA events on the launching stream, L2 flushed between launches, at the row counts of one
+    key switch of a bootstrap batch at the top of the chain."""
+    import torch
+    nq, K = P.n_q, P.n_p
+    batch = 16 * G
+    beta, ne = P.digits_at(nq), nq + K
+    rows = batch * beta * ne
+    x = torch.randint(0, 2 ** 39, (batch * beta, ne, P.n), dtype=torch.int64, device="cuda")
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    for _ in range(3):
+        be._call("fhe_ntt_fwd", be._ptr(x), x.shape[0], nq, K)
+    kt = []
+    for _ in range(10):
+        flush.zero_()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); be._call("fhe_ntt_fwd", be._ptr(x), x.shape[0], nq, K); b.record()
+        torch.cuda.synchronize()
+        kt.append(a.elapsed_time(b))
+    k_ms = float(np.median(kt))
+    alg_bytes = 2 * rows * P.n * 8                      # read once + write once per limb (SURVEY 8d)
+    achieved = alg_bytes / (k_ms * 1e-3) / 1e9
+    traffic, traffic_src = None, None
+    try:
+        traffic = json.load(open(ROOT / "profiles" / "ntt_traffic.json"))["dram_bytes_per_row"] * rows
+        traffic_src = "static: ncu dram__bytes of the same kernel (profiles/ntt_traffic.json) x rows"
+    except Exception:
+        pass
+    # FP64 work of the transform: N/2 log2 N butterflies x 8 FP64 instructions + 1.1 N (conversions, final reduction)
+    fp64_ops = rows * (P.n // 2 * P.log_n * 8 + 1.1 * P.n)
+    sm_mhz = clocks.get("sm_mhz") or clocks.get("sm_max_mhz") or 1965
+    fp64_peak = 64 * 148 * sm_mhz * 1e6 / 1e9           # G instr/s: 64 DFMA-class per clock per SM (tools/ubench/pipes.cu)
+    del x
+    ext = torch.randint(0, 2 ** 39, (batch, beta, ne, P.n), dtype=torch.int64, device="cuda")
+    dd = torch.randint(0, 2 ** 39, (1, batch, nq, P.n), dtype=torch.int64, device="cuda")
+    acc = torch.empty(2, batch, ne, P.n, dtype=torch.int64, device="cuda")
+    ksk = torch.randint(0, 2 ** 39, (P.dnum, 2, 1, ne, P.n), dtype=torch.int64, device="cuda")
+    kt2 = []
+    for it in range(13):
+        flush.zero_()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); be._call("fhe_ks_inner", be._ptr(acc), be._ptr(ext), be._ptr(dd), be._ptr(ksk), nq, batch); b.record()
+        torch.cuda.synchronize()
+        if it >= 3:
+            kt2.append(a.elapsed_time(b))
+    ks_ms = float(np.median(kt2))
+    ks_bytes = (2 * beta * ne + batch * (beta * ne + 2 * ne)) * P.n * 8
+    return {
+        "roofline": {"bound": "hbm", "limiter": "fp64 pipe (see roofline_fp64)", "kernel": "ntt_fwd_chained (both radix passes in one launch)",
+                     "rows_per_launch": rows, "us_per_launch": k_ms * 1e3, "us_per_row": k_ms * 1e3 / rows,
+                     "achieved": achieved, "peak": peak, "peak_kind": peak_kind, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": traffic, "traffic_source": traffic_src, "algorithmic_bytes": int(alg_bytes)},
+        "roofline_fp64": {"kernel": "ntt_fwd_chained", "achieved": fp64_ops / (k_ms * 1e-3) / 1e9, "peak": fp64_peak,
+                          "unit": "G FP64 instr/s", "frac": fp64_ops / (k_ms * 1e-3) / 1e9 / fp64_peak,
+                          "peak_kind": f"64 per clk per SM x 148 SMs x {sm_mhz:.0f} MHz (median SM clock of the timed region)",
+                          "ops_per_row": fp64_ops / rows},
+        "roofline_keyswitch_inner": {"kernel": "k_ks_inner", "bound": "hbm", "achieved": ks_bytes / (ks_ms * 1e-3) / 1e9,
+                                     "peak": peak, "unit": "GB/s", "frac": ks_bytes / (ks_ms * 1e-3) / 1e9 / peak,
+                                     "us": ks_ms * 1e3, "algorithmic_bytes": int(ks_bytes)}}
 
 
 if __name__ == "__main__":

@@ -15,8 +15,14 @@
  *     contiguous: [npoly][nq + np][N].  Residues are canonical [0,q), NTT domain
  *     (bit-reversed spectrum) unless a function says "coefficient domain".
  *   - return value 0 = ok; negative = error, text via fhe_last_error().  No function
- *     synchronises the stream; nothing is allocated per call except when the context's
- *     scratch arena has to grow (first call at a new size).
+ *     synchronises the stream (fhe_ntt_fused_status and fhe_ctx_destroy excepted); nothing is allocated per
+ *     call except when the context's scratch arena has to grow (first call at a new size).
+ *   - ONE STREAM PER CONTEXT: the scratch arena and the hand-over counters of the single-launch NTTs belong to
+ *     the context, so all calls on one context must be issued on one stream (or be serialised by the caller).
+ *     Use one context per stream for concurrency.  The Python host layer enforces this (backend_cuda.py).
+ *   - the single-launch NTTs never hang: a hand-over wait that times out sets a sticky error flag and the
+ *     transform's output is then wrong.  Callers MUST check fhe_ntt_fused_status() before trusting results that
+ *     leave the device (the host layer does so on every decrypt / download / synchronize).
  */
 #ifndef AESFHE_B200_H
 #define AESFHE_B200_H

@@ -48,6 +48,51 @@ def test_rejects_foreign_parameters_damage_and_secret_keys(ref_backend_cls):
         wire.dumps(a, sk)
 
 
+def test_rejects_wrong_shapes_before_they_reach_a_kernel(ref_backend_cls):
+    """undersized keys, 1-polynomial ciphertexts, wrong batch / digit dimensions and Galois elements
+    that do not match their rotation must raise WireError, never IndexError or an out-of-bounds device read."""
+    eng = _engine(ref_backend_cls)
+    P = eng.params
+    sk = eng.create_secret_key(); pk = eng.create_public_key(sk)
+    rlk = eng.create_relinearization_key(sk); rk = eng.create_fixed_rotation_key(sk, 3)
+    base = {"params": wire.params_digest(P)}
+    good = eng.backend.to_numpy(rlk.data)
+
+    def load(kind, header, arr):
+        return wire.loads(eng, wire._pack(kind, dict(base, **header), arr))
+
+    assert isinstance(load("relinearization_key", {}, good), type(rlk))
+    for bad in (good[:, :, :, :P.n_q],                       # q-limbs only: kernels would read n_q + n_p rows
+                good[:P.dnum - 1],                           # a digit short
+                good[:, :1],                                 # one polynomial
+                np.concatenate([good, good], axis=2),        # batch 2
+                good[..., : P.n // 2]):                      # half a ring
+        with pytest.raises(wire.WireError):
+            load("relinearization_key", {}, bad)
+    ct = eng.backend.to_numpy(eng.encrypt(np.ones(8), pk).polys)
+    assert load("ciphertext", {"level": 5}, ct).npoly == 2
+    for hdr, bad in (({"level": 5}, ct[:1]),                 # 1 polynomial
+                     ({"level": 5}, np.concatenate([ct, ct], axis=0)),      # 4 polynomials
+                     ({"level": 5}, ct[:, :0]),              # empty batch
+                     ({"level": 4}, ct),                     # level / limb mismatch
+                     ({"level": 99}, ct),
+                     ({"level": "5"}, ct),
+                     ({"level": 5}, ct[0])):                 # 3-d
+        with pytest.raises(wire.WireError):
+            load("ciphertext", hdr, bad)
+    with pytest.raises(wire.WireError):
+        load("public_key", {}, eng.backend.to_numpy(pk.polys)[0])           # was an IndexError
+    with pytest.raises(wire.WireError):
+        load("public_key", {}, eng.backend.to_numpy(pk.polys)[:, :, :3])
+    rot = eng.backend.to_numpy(rk.data)
+    assert load("fixed_rotation_key", {"galois": int(rk.galois), "delta": 3}, rot).delta == 3
+    for hdr in ({"galois": int(rk.galois), "delta": 4}, {"galois": 4, "delta": 3}, {"galois": int(rk.galois)}, {"delta": 3}):
+        with pytest.raises(wire.WireError):
+            load("fixed_rotation_key", hdr, rot)
+    with pytest.raises(wire.WireError):
+        load("conjugation_key", {"galois": int(rk.galois)}, rot)
+
+
 def test_byte_codec_fallback_matches_zeta_encoder(ref_backend_cls):
     """Engine.encrypt_zeta / decrypt_zeta (device codec on the GPU) on a backend without a device codec:
     same values as ZetaEncoder.to_zeta + encrypt / decrypt + from_zeta (xor_service.py:132-145)."""
