@@ -36,6 +36,8 @@ from .engine import BootstrapKey, Ciphertext, FixedRotationKey, Plaintext
 # cheaper than r = 6 with degree 12..22 (tools/bits_study.py prints the table)
 DOUBLE_ANGLES_BITS = 5
 POLY_DEGREE_BITS = 18
+import os as _os
+_EAGER_PS = _os.environ.get("FHE_EAGER_PS") == "1"        # A/B switch: EvalMod polynomial with level adjustments
 RHO_TARGET = 32.0         # q_0 / (scaled message): the message is divided by RHO_TARGET * Delta_0 / q_0
 K_NORM = 33               # |I| <= 32 for hamming weight <= 192 (8 sigma)
 DOUBLE_ANGLES = 6
@@ -202,6 +204,141 @@ def chebyshev_eval_ps(engine, relin_key, y: Ciphertext, coeffs, baby: int = 4) -
     out = ev(c)
     if isinstance(out, float):
         raise ValueError("chebyshev_eval_ps: constant polynomial")
+    return out
+
+
+def chebyshev_eval_ps_lazy(engine, relin_key, y: Ciphertext, coeffs, baby: int = 4) -> Ciphertext:
+    """The same polynomial and the same products as chebyshev_eval_ps (Paterson-Stockmeyer in the Chebyshev basis,
+    baby = 4) without a single level adjustment.  Every ciphertext carries its exact scale as a rational factor
+    `dev` on the scale table (true scale = delta[level] * dev):
+
+    * a product of operands at different levels uses the higher one in place (Engine._mul_ct_dropped: upper limbs
+      ignored, an exact modulus switch) -- the product's scale leaves the table by a known factor;
+    * T_2n = 2 T_n^2 - 1 costs no doubling: the product T_n^2 at scale s IS the value 2 T_n^2 at scale s / 2, then
+      the constant -1 is added at that scale;
+    * the leaves use {T_1, T_2, T_1 T_2} (T_3 = 2 T_1 T_2 - T_1 folded into the constants), one constant-only
+      pass each, and a leaf can be produced at ANY scale;
+    * so a node  q T_n + r  first fixes the scale S it must deliver, asks q for S q_l / scale(T_n) and r for S:
+      the sum needs no alignment, and the root is asked for the table scale.
+
+    Same depth (5 levels for degree <= 23) and 9 products for degree 18, but none of the 19 constant-multiply +
+    rescale alignments per evaluation that the eager form spends on mixed-level adds and products."""
+    from fractions import Fraction
+    from .fused import _const_pair
+    be, P = engine.backend, engine.params
+    c = [float(v) for v in coeffs]
+    while len(c) > 1 and abs(c[-1]) < 1e-300:
+        c.pop()
+    deg = len(c) - 1
+    if baby != 4 or deg < baby:
+        return chebyshev_eval_ps(engine, relin_key, y, coeffs, baby)
+
+    def scale_of(ct, dev):
+        return P.delta[ct.level] * dev
+
+    def mul(a, da, b, db):
+        out, d = engine._mul_ct_dropped(a, b, relin_key)
+        return out, (d * da * db).limit_denominator(1 << 600)
+
+    def two_x_minus_one(a, da):
+        """2 a^2 - 1 from a: the square read as twice its value at half the scale"""
+        sq, d = mul(a, da, a, da)
+        d = d / 2
+        return engine.add_plain(sq, -float(d)), d
+
+    one = Fraction(1)
+    T: Dict[int, Tuple[Ciphertext, Fraction]] = {1: (y, one)}
+    T[2] = two_x_minus_one(y, one)
+    p12 = mul(y, one, *T[2])                                   # T_1 T_2 = (T_3 + T_1) / 2
+    T[4] = two_x_minus_one(*T[2])
+    n = 4
+    while 2 * n <= deg:
+        T[2 * n] = two_x_minus_one(*T[n])
+        n *= 2
+    leaf_in = {1: T[1], 2: T[2], 3: p12}                       # 3 = the product T_1 T_2
+
+    def leaf_terms(cc):
+        cc = list(cc) + [0.0] * (4 - len(cc))
+        terms = {1: cc[1] - cc[3], 2: cc[2], 3: 2.0 * cc[3]}
+        return {k: v for k, v in terms.items() if abs(v) > 0.0}, cc[0]
+
+    def leaf_level(cc):
+        terms, _ = leaf_terms(cc)
+        return min(leaf_in[k][0].level for k in terms) - 1 if terms else None
+
+    def plan_level(cc):
+        d = len(cc) - 1
+        if d < baby:
+            return leaf_level(cc)
+        n = baby
+        while 2 * n <= d:
+            n *= 2
+        q, _ = split(cc, n)
+        lq = plan_level(q)
+        return min(lq if lq is not None else T[n][0].level, T[n][0].level) - 1
+
+    def split(cc, n):
+        d = len(cc) - 1
+        q = [0.0] * (d - n + 1)
+        r = list(cc[:n])
+        q[0] = cc[n]
+        for k in range(n + 1, d + 1):
+            q[k - n] += 2.0 * cc[k]
+            r[2 * n - k] -= cc[k]
+        return q, r
+
+    def leaf(cc, S):
+        """the leaf polynomial at true scale S (default: the table scale of its level), or a float"""
+        terms, c0 = leaf_terms(cc)
+        if not terms:
+            return float(c0), None
+        lo = min(leaf_in[k][0].level for k in terms)
+        nq = lo + 1
+        if S is None:
+            S = P.delta[lo - 1]
+        target = S * P.moduli[lo]                               # scale in front of the rescale
+        keys = sorted(terms)
+        res = [[_const_pair(engine, complex(terms[k]), target / scale_of(*leaf_in[k]), nq) for k in keys]]
+        c0r = [_const_pair(engine, complex(c0), target, nq)]
+        out = be.lincomb([leaf_in[k][0].polys for k in keys], be.prepare_lincomb(res, c0r, nq))[0]
+        ct = engine._rescale(Ciphertext(engine, out, lo))
+        return ct, (S / P.delta[ct.level]).limit_denominator(1 << 600)
+
+    def ev(cc, S=None):
+        d = len(cc) - 1
+        if d < baby:
+            return leaf(cc, S)
+        n = baby
+        while 2 * n <= d:
+            n *= 2
+        q, r = split(cc, n)
+        tn, dn = T[n]
+        lq = plan_level(q)
+        if lq is None:
+            # constant quotient: q[0] * T_n as a constant multiple, delivered at scale S one level below T_n
+            lvl = tn.level
+            if S is None:
+                S = P.delta[lvl - 1]
+            k = S * P.moduli[lvl] / scale_of(tn, dn) * Fraction(float(q[0]))
+            src = tn
+            prod = engine._rescale(engine._mul_int_const(src, int(round(k)), 0))
+        else:
+            lvl = min(lq, tn.level)
+            if S is None:
+                S = P.delta[lvl - 1]
+            qv, dq = ev(q, S * P.moduli[lvl] / scale_of(tn, dn))
+            prod, dp = mul(qv, dq, tn, dn)
+            assert prod.level == lvl - 1
+        rv, dr = ev(r, S)
+        if isinstance(rv, float):
+            return engine.add_plain(prod, rv * float(S / P.delta[prod.level])), (S / P.delta[prod.level]).limit_denominator(1 << 600)
+        nq = prod.level + 1
+        rp = rv.polys if rv.level == prod.level else be.take_limbs(rv.polys, nq, False)
+        engine._count('add_ct')
+        return Ciphertext(engine, be.add(prod.polys, rp, nq, 0), prod.level), (S / P.delta[prod.level]).limit_denominator(1 << 600)
+
+    out, dev = ev(c, None)
+    assert dev == 1, dev
     return out
 
 
@@ -411,6 +548,13 @@ def bootstrap(engine, ct: Ciphertext, relin_key, conj_key, boot_key: BootstrapKe
     return u
 
 
+def _phase(engine, name: str):
+    """optional hook for profiling tools (tools/aes_bits_probe.py): engine.phase_timer(name) at phase boundaries"""
+    hook = getattr(engine, "phase_timer", None)
+    if hook is not None:
+        hook(name)
+
+
 def bootstrap_bits(engine, ct: Ciphertext, relin_key, conj_key, boot_key: BootstrapKey) -> Ciphertext:
     """Refresh of +-1-valued slots ("bit bootstrap").  ``ct`` [batch B] holds u + i v with u, v real and close to
     +-1 (two bit planes per ciphertext); the result [batch 2 B: all u, then all v] holds the cleaned values at
@@ -445,25 +589,34 @@ def bootstrap_bits(engine, ct: Ciphertext, relin_key, conj_key, boot_key: Bootst
     # delta[ct.level]; the factor is carried to step 1
     dev = P.delta[ct.level] / P.delta[lvl_in]
     u = ct if ct.level == lvl_in else Ciphertext(engine, be.take_limbs(ct.polys, lvl_in + 1, False), lvl_in)
+    _phase(engine, "boot:entry")
     for entry in plan.stc:
         u = _linear_transform(engine, u, entry)                                     # ends at level 1
+    _phase(engine, "boot:slot_to_coeff")
 
     # 1. level 0, plaintext coefficient = s * q_0 / 4; ModRaise (declared scale q_0: values I + s / 4)
     c = P.delta[0] * P.moduli[1] / (P.delta[1] * dev * Fraction(plan.shift_bits))
     x = engine._rescale(engine._mul_int_const(u, int(round(c)), 0))
     raised = Ciphertext(engine, be.mod_raise(x.polys, L + 1), L)
+    _phase(engine, "boot:mod_raise")
 
     # 2. CoeffToSlot; y = (I + s / 4) / K_n for the first and the second half of the coefficients
     t = _linear_transform(engine, raised, plan.cts_bits0)
     for entry in plan.cts[1:]:
         t = _linear_transform(engine, t, entry)
+    _phase(engine, "boot:coeff_to_slot")
     tc = engine.conjugate(t, conj_key)
     re = engine.add(t, tc)
     im = engine.multiply_by_i(engine.subtract(t, tc), -1)
     y = Ciphertext(engine, be.concat_batch([re.polys, im.polys]), t.level)
 
+    _phase(engine, "boot:conjugate_split")
+
     # 3. EvalMod with unit amplitude
-    cpoly = chebyshev_eval_ps(engine, relin_key, y, plan.poly_bits)
+    cpoly = (chebyshev_eval_ps_lazy if hasattr(engine, "_mul_ct_dropped") and not _EAGER_PS else chebyshev_eval_ps)(
+        engine, relin_key, y, plan.poly_bits)
+    _phase(engine, "boot:evalmod_polynomial")
     for i in range(DOUBLE_ANGLES_BITS):
         cpoly = engine.add_plain(engine.multiply(cpoly, cpoly, relin_key), -plan.alphas_bits[i + 1])
+    _phase(engine, "boot:evalmod_double_angle")
     return cpoly

@@ -110,6 +110,8 @@ def distribute_keys(engine: Engine, owner_ctx=None, src: int = 0):
         return be.alloc(shape)
 
     cuda = isinstance(getattr(be, "device", None), torch.device) and be.device.type == "cuda"
+    # one small broadcast first: the collective's channels are set up on its first use, which is not key traffic
+    broadcast_handle(be, be.alloc([1, 1, 1, 1, engine.params.n]) if rank != src else rlk.data[:1, :1, :, :1], src)
     if cuda:
         torch.cuda.synchronize()
     dist.barrier()

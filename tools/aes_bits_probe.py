@@ -24,6 +24,7 @@ class StageTimer:
         import torch
         self.torch = torch
         self.marks = []
+        self.peaks = {}
         self.reset()
 
     def reset(self):
@@ -35,6 +36,8 @@ class StageTimer:
         e = self.torch.cuda.Event(enable_timing=True)
         e.record()
         self.marks.append((name, e))
+        self.peaks[name] = max(self.peaks.get(name, 0.0), self.torch.cuda.max_memory_allocated() / 2 ** 30)
+        self.torch.cuda.reset_peak_memory_stats()
 
     def ms(self):
         self.torch.cuda.synchronize()
@@ -47,11 +50,12 @@ class StageTimer:
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--states", type=int, default=1)
-    ap.add_argument("--level", type=int, default=25)
+    ap.add_argument("--level", type=int, default=24)
     ap.add_argument("--scale-bits", type=int, default=44)
     ap.add_argument("--groups", default="3,3")
     ap.add_argument("--rounds", type=int, default=10)
     ap.add_argument("--fresh-level", type=int, default=None)
+    ap.add_argument("--dnum", type=int, default=0)
     args = ap.parse_args()
     import torch
     from aes_fhe_b200.params import make_params
@@ -60,7 +64,8 @@ def main():
     from aes_fhe_b200.services.xor_service import EngineWrapper, XORConfig
     from oracle import aes_plain as A
 
-    P = make_params(16, args.level, scale_bits=args.scale_bits)
+    from aes_fhe_b200.params import LOG_PQ_BUDGET_SPARSE
+    P = make_params(16, args.level, scale_bits=args.scale_bits, dnum=args.dnum, log_pq_budget=LOG_PQ_BUDGET_SPARSE)
     groups = tuple(int(x) for x in args.groups.split(","))
     t0 = time.time()
     w = EngineWrapper(XORConfig(), _engine_kwargs=dict(_params=P, seed=3, device_codec=True), rotation_steps=[])
@@ -79,13 +84,19 @@ def main():
     setup = time.time() - t0
     c0, r0 = dict(w.engine.op_counts), svc.refreshes
     l0 = w.engine.backend.launch_count()
+    resident = torch.cuda.memory_allocated() / 2 ** 30
+    peak_all = torch.cuda.max_memory_allocated() / 2 ** 30
+    torch.cuda.reset_peak_memory_stats()
     svc.timer = StageTimer()
+    w.engine.phase_timer = svc.timer
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a.record()
     out = svc.encrypt_blocks(st, key, rounds=args.rounds, round_keys=rkeys)
     b.record()
     stages = svc.timer.ms()
+    peaks = svc.timer.peaks
     svc.timer = None
+    w.engine.phase_timer = None
     ms = a.elapsed_time(b)
     got = svc.decrypt_state(out)
     s = blocks ^ rks[0]
@@ -99,7 +110,8 @@ def main():
                       "bytes_equal_plain_aes": bool(np.array_equal(got, s)), "max_slot_err": err,
                       "bootstrapped_ciphertexts": svc.refreshes - r0, "op_counts": cnt,
                       "launches": w.engine.backend.launch_count() - l0, "out_level": out.level, "setup_s": setup,
-                      "mem_gb": torch.cuda.max_memory_allocated() / 2 ** 30}))
+                      "mem_gb_peak_first_run": peak_all, "mem_gb_resident_after_warmup": resident,
+                      "mem_gb_peak_by_stage": peaks}))
 
 
 if __name__ == "__main__":
