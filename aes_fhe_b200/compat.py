@@ -38,3 +38,23 @@ def mount_reference(path) -> None:
         pkg = types.ModuleType("aes_xor_fhe")
         pkg.__path__ = [path]
         sys.modules["aes_xor_fhe"] = pkg
+
+
+def patch_reference_defects() -> None:
+    """Work around SURVEY defect D4 at THIS layer (the reference tree is never edited): on NumPy 2,
+    ``ZetaEncoder.to_zeta(uint8_array, modulus=256)`` (xor_service.py:134-137) raises OverflowError because 256 does
+    not fit uint8.  After ``mount_reference`` the class is wrapped so the input is widened first; every reference
+    module that imported ZetaEncoder sees the same class object."""
+    import importlib
+    import numpy as np
+    xs = importlib.import_module("aes_xor_fhe.xor_service")
+    enc = xs.ZetaEncoder
+    if getattr(enc, "_b200_patched", False):
+        return
+    inner = enc.to_zeta
+
+    def to_zeta(arr, modulus: int = 16):
+        return inner(np.asarray(arr).astype(np.int64), modulus)
+
+    enc.to_zeta = staticmethod(to_zeta)
+    enc._b200_patched = True

@@ -162,3 +162,15 @@ def test_bytes_in_bytes_out_ecb_full_size(cuda_lib):
     padded = msg + bytes([8] * 8)
     want = A.encrypt_blocks(np.frombuffer(padded, np.uint8).reshape(-1, 16), key).tobytes()
     assert ct == want
+
+
+def test_aes_fhe_transformer_columns_on_gpu(cuda_lib):
+    """row a12 on the B200: the mirror of AESFHETransformer (shiftrow_mixcolumns.py:16-80), steps 1-4 at N = 2^16,
+    slots against the plain-complex evaluation of the same call sequence (see check_transformer_columns)."""
+    from aes_fhe_b200.services.xor_service import XORService, EngineWrapper, XORConfig, CoefficientCache
+    from test_services_plain_and_oracle import check_transformer_columns
+    cfg = XORConfig()
+    w = EngineWrapper(cfg, _engine_kwargs=dict(seed=3, _params=make_params(16, 30, scale_bits=44)),
+                      rotation_steps=[-1, -2, -3, -5, -10, -15])
+    errs = check_transformer_columns(w, XORService(w, CoefficientCache(cfg.coeffs_path)), 32768)
+    print("AESFHETransformer collapsed columns: max slot errors", errs, w.engine.op_counts)

@@ -1,7 +1,7 @@
-"""Device time per kernel of one SubBytes step (the bench workload), taken with CUPTI through
+"""Device time per kernel of one bench step (bit-sliced AES-128, or SubBytes), taken with CUPTI through
 torch.profiler -- concurrent-safe, no replay, so the sum is the real busy time of the step.
 
-    python tools/kernel_breakdown.py [--batch 16] [--dnum D] [--lib path/to/other/libaesfhe_b200.so]
+    python tools/kernel_breakdown.py [--workload aes128|sbox] [--batch B] [--dnum D] [--lib path/to/other/libaesfhe_b200.so]
 
 `--lib` loads another build of the library (A/B runs against aes_fhe_b200/csrc/variants/*.so).
 Prints a markdown table; `--json FILE` also writes {kernel: [launches, total_us]}.
@@ -20,42 +20,51 @@ sys.path.insert(0, str(ROOT))
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--batch", type=int, default=16)
+    ap.add_argument("--batch", type=int, default=None, help="sbox: ciphertexts (default 16); aes128: states of 8192 blocks (default 1)")
     ap.add_argument("--dnum", type=int, default=None)
     ap.add_argument("--lib", default=None)
     ap.add_argument("--steps", type=int, default=2)
     ap.add_argument("--json", default=None)
-    ap.add_argument("--workload", default="sbox", choices=["sbox", "aes128"],
-                    help="sbox: the bench step (SubBytes, BASELINE configs[1]); aes128: ten rounds with refreshes (configs[4])")
+    ap.add_argument("--workload", default="aes128", choices=["sbox", "aes128"],
+                    help="aes128: the bench step (bit-sliced AES-128, BASELINE configs[4]); sbox: SubBytes (configs[1])")
     args = ap.parse_args()
+    if args.batch is None:
+        args.batch = 16 if args.workload == "sbox" else 1
     if args.lib:
         from aes_fhe_b200 import _capi
         _capi.LIB_PATH = Path(args.lib).resolve()
-    import bench
-    bench.DNUM = args.dnum
-    from aes_fhe_b200.services.xor_service import ZetaEncoder
+    import numpy as np
     if args.workload == "sbox":
-        ctx, svc = bench._make_service(seed=1)
+        from aes_fhe_b200.params import make_params
+        from aes_fhe_b200.services.engine_context import EngineContext
+        from aes_fhe_b200.services.sbox_service import SBoxService
+        from aes_fhe_b200.services.xor_service import ZetaEncoder
+        P = make_params(16, 22) if args.dnum is None else make_params(16, 22, dnum=args.dnum)
+        ctx = EngineContext(signature=2, max_level=22, mode="parallel", _engine_kwargs=dict(_params=P, seed=1), rotation_steps=[])
+        svc = SBoxService(ctx)
         eng = ctx.engine
-        data = bench._inputs(eng.slot_count, args.batch, seed=0)
+        data = np.random.default_rng(0).integers(0, 256, (args.batch, eng.slot_count), dtype=np.uint8)
         ct = eng.encrypt(ZetaEncoder.to_zeta(data, 256), ctx.public_key)
 
         def step():
             return svc.sub_bytes_array_bsgs(ct)
         warm = 2
     else:
-        import numpy as np
-        from aes_fhe_b200.services.aes128 import AES128Service
-        from aes_fhe_b200.services.xor_service import XORService, EngineWrapper, XORConfig, CoefficientCache
-        cfg = XORConfig()
-        w = EngineWrapper(cfg, _engine_kwargs=dict(seed=3), rotation_steps=[])
-        aes = AES128Service(w, XORService(w, CoefficientCache(cfg.coeffs_path)))
-        key = bytes.fromhex("2b7e151628aed2a6abf7158809cf4f3c")
-        rng = np.random.default_rng(9)
-        st = aes.encrypt_state([rng.integers(0, 256, (aes.B, 16), dtype=np.uint8) for _ in range(args.batch)])
+        import bench
+        from aes_fhe_b200.services.aes_bits import AESBitService
+        from aes_fhe_b200.services.key_expansion import expand_key
+        from aes_fhe_b200.services.xor_service import EngineWrapper, XORConfig
+        P = bench.aes_params()
+        w = EngineWrapper(XORConfig(), _engine_kwargs=dict(_params=P, seed=3, device_codec=True), rotation_steps=[])
+        aes = AESBitService(w)
+        G = args.batch
+        key = bytes.fromhex(bench.KEY_HEX)
+        rks = expand_key(key)
+        st = aes.encrypt_state(bench.rank_blocks(0, G * aes.Bs), level=1 + aes.boot_in_levels)
+        rkeys = [aes.encrypt_round_key(rks[r], G, level=12) for r in range(11)]
 
         def step():
-            return aes.encrypt_blocks(st, key)
+            return aes.encrypt_blocks(st, key, round_keys=rkeys)
         warm = 1
     for _ in range(warm):
         step()
