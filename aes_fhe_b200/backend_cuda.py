@@ -432,6 +432,21 @@ class CudaBackend:
         self._call("fhe_mul_plain_multi", self._ptr(out), ap, an, pp, T, G, nq, bt)
         return out
 
+    def bsgs_inner(self, ext, ct, keys: List, galois: List[int], pt_rows: List[List], nq: int):
+        """double-hoisted baby steps (fhe_bsgs_inner): ext [B,beta,nq+K,N] = modup_raw(c1 of ct); ct [2,B,>=nq,N];
+        keys[b] = switching-key tensor or None (no rotation); pt_rows[g][b] = extended-basis plaintext [1,1,nq+K,N] or
+        None -> [G, 2, B, nq+K, N]"""
+        ct = ct.contiguous()
+        ext = ext.contiguous()
+        nb, G, bt = len(keys), len(pt_rows), ct.shape[1]
+        keep = [[None if x is None else x.contiguous() for x in row] for row in pt_rows]
+        kp = (C.c_void_p * nb)(*[None if k is None else k.data_ptr() for k in keys])
+        gp = (C.c_uint64 * nb)(*[int(g) for g in galois])
+        pp = (C.c_void_p * (G * nb))(*[None if x is None else x.data_ptr() for row in keep for x in row])
+        out = self._empty(G, 2, bt, nq + self._K, self.n)
+        self._call("fhe_bsgs_inner", self._ptr(out), self._ptr(ext), self._ptr(ct), ct.shape[2], kp, gp, pp, nb, G, nq, bt)
+        return out
+
     def automorphism_rows(self, h, g: int):
         """X -> X^g on every row of an arbitrary [.., N] tensor (hoisted rotations act on ModUp output)."""
         h = h.contiguous()

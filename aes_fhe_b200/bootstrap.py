@@ -38,6 +38,8 @@ DOUBLE_ANGLES_BITS = 5
 POLY_DEGREE_BITS = 18
 import os as _os
 _EAGER_PS = _os.environ.get("FHE_EAGER_PS") == "1"        # A/B switch: EvalMod polynomial with level adjustments
+_NO_DH = _os.environ.get("FHE_NO_DH") == "1"              # A/B switch: single-hoisted linear transforms (square BSGS)
+_NO_DH_FUSE = _os.environ.get("FHE_NO_DH_FUSE") == "1"    # A/B switch: double hoisting from separate primitives
 RHO_TARGET = 32.0         # q_0 / (scaled message): the message is divided by RHO_TARGET * Delta_0 / q_0
 K_NORM = 33               # |I| <= 32 for hamming weight <= 192 (8 sigma)
 DOUBLE_ANGLES = 6
@@ -102,16 +104,23 @@ def _group(mats: List[Dict[int, np.ndarray]], groups: int, n: int) -> List[Dict[
     return out
 
 
-def _bsgs_split(rots: List[int], n: int):
-    """d = g + b with b in [0, bm): returns (bm, {g: [(b, d), ...]})."""
+def _bsgs_split(rots: List[int], n: int, double_hoist: bool = False):
+    """d = g + b with b in [0, bm): returns (bm, {g: [(b, d), ...]}).  Square split (n1 ~ sqrt of the number of
+    diagonals) for the single-hoisted evaluation; with double hoisting the baby steps are cheap (one fused pass,
+    no ModDown) and every giant step costs a ModDown + ModUp, so the split is as lopsided as the fused kernel
+    takes: up to 16 baby steps."""
     nz = [d for d in rots if d]
     stride = n
     for d in nz:
         stride = np.gcd(stride, d)
     stride = int(stride) if nz else 1
     n1 = 1
-    while n1 * n1 < len(rots):
-        n1 *= 2
+    if double_hoist:
+        while n1 < 16 and 2 * n1 < len(rots):
+            n1 *= 2
+    else:
+        while n1 * n1 < len(rots):
+            n1 *= 2
     bm = stride * n1
     plan: Dict[int, List[Tuple[int, int]]] = {}
     for d in rots:
@@ -415,20 +424,10 @@ def _materialise(engine, bk: BootstrapKey):
     plan.rot_keys: Dict[int, FixedRotationKey] = {}
     plan.cts, plan.stc = [], []
 
+    dh = bool(getattr(bk, "_double_hoist", not _NO_DH))
+
     def prepare(mat, scale_fn=None):
-        bm, split = _bsgs_split(sorted(mat), n)
-        entry = dict(bm=bm, giants={})
-        for g, items in split.items():
-            lst = []
-            for b, d in items:
-                # inner sum is rotated by g afterwards, so the diagonal is pre-rotated the other way
-                lst.append((b, Plaintext(engine, np.roll(mat[d], g), scale_fn=scale_fn)))
-                if b and b not in plan.rot_keys:
-                    plan.rot_keys[b] = engine.create_fixed_rotation_key(bk._sk, -b)
-            entry["giants"][g] = lst
-            if g and g not in plan.rot_keys:
-                plan.rot_keys[g] = engine.create_fixed_rotation_key(bk._sk, -g)
-        return entry
+        return prepare_matrix(engine, bk._sk, mat, plan.rot_keys, scale_fn, dh and scale_fn is not first_scale)
 
     # first matrix: two rescales, plaintext scale ~ Delta * q / q_0 * q: rounding of the diagonals
     # must be far below 2^-40 because the raised ciphertext's slots are ~ sqrt(n) * |I| large
@@ -451,9 +450,105 @@ def _materialise(engine, bk: BootstrapKey):
     return plan
 
 
+def prepare_matrix(engine, sk, mat: Dict[int, np.ndarray], rot_keys: Dict[int, FixedRotationKey], scale_fn=None,
+                   double_hoist: bool = False):
+    """A slot-domain matrix in diagonal form ({rotation d: diagonal}, out[p] = sum_d diag_d[p] in[(p + d) % n]) made
+    ready for _linear_transform: baby-step/giant-step split, pre-rotated plaintext diagonals, Galois keys (created
+    with `sk`, or fetched from a ReceivedKeys object, into `rot_keys`)."""
+    n = engine.slot_count
+    bm, split = _bsgs_split(sorted(mat), n, double_hoist)
+    entry = dict(bm=bm, giants={}, dh=bool(double_hoist), _keys=rot_keys)
+    for g, items in split.items():
+        lst = []
+        for b, d in items:
+            # inner sum is rotated by g afterwards, so the diagonal is pre-rotated the other way
+            lst.append((b, Plaintext(engine, np.roll(mat[d], g), scale_fn=scale_fn)))
+            if b and b not in rot_keys:
+                rot_keys[b] = engine.create_fixed_rotation_key(sk, -b)
+        entry["giants"][g] = lst
+        if g and g not in rot_keys:
+            rot_keys[g] = engine.create_fixed_rotation_key(sk, -g)
+    return entry
+
+
 # --------------------------------------------------------------------------- evaluation
+def _linear_transform_dh(engine, ct: Ciphertext, entry) -> Ciphertext:
+    """The same sum with DOUBLE hoisting (Bossuat-Mouchet-Troncoso-Pastoriza-Hubaux 2021): the baby-step rotations
+    share one ModUp AND skip their ModDowns -- the rotated ciphertexts stay in the extended basis Q u P, are
+    multiplied there with extended-basis plaintexts and summed; only the G giant-step sums are brought down (one
+    ModDown each), rotated (one ModUp each) and accumulated, with one final ModDown merged with the rescale.
+    1 + (G-1) ModUps and G ModDowns instead of n1 + n2 each.  On the B200 the baby side is ONE kernel
+    (fhe_bsgs_inner): inner products with all baby keys, the lift of c0, the automorphisms (as gathers) and the
+    plaintext products, without any intermediate in memory."""
+    be, P = engine.backend, engine.params
+    keys = entry["_keys"]
+    lvl = ct.level
+    nq, K = lvl + 1, P.n_p
+    giants = entry["giants"]
+    glist = list(giants)
+    blist = sorted({b for items in giants.values() for b, _ in items})
+    rows = [[dict(items).get(b) for b in blist] for items in giants.values()]
+
+    def pt(p):
+        return None if p is None else p.at_level(lvl, ext=True)
+
+    c0, c1 = be.select_poly(ct.polys, 0), be.select_poly(ct.polys, 1)
+    engine._count('keyswitch_galois', sum(1 for b in blist if b))
+    engine._count('mul_pt', sum(1 for row in rows for p in row if p is not None))
+    if hasattr(be, "bsgs_inner") and not _NO_DH_FUSE and len(blist) <= 16 and P.digits_at(nq) <= 4:
+        ext = be.modup_raw(c1, nq)
+        inners = []
+        for s in range(0, len(glist), 4):
+            chunk = rows[s:s + 4]
+            out = be.bsgs_inner(ext, ct.polys, [None if b == 0 else keys[b].data for b in blist],
+                                [1 if b == 0 else int(keys[b].galois) for b in blist],
+                                [[pt(p) for p in row] for row in chunk], nq)
+            inners += [out[i] for i in range(len(chunk))]
+    else:
+        # the same values from the primitives both backends have (the oracle's path):
+        #   Z_b = sigma_b( <ModUp(c1), sigma_b^-1 key_b> + P (c0, 0) )
+        ext = be.modup(c1, nq)
+        two_n = 2 * P.n
+        Z = {}
+        for b in blist:
+            if b == 0:
+                Z[b] = be.ks_accum(None, None, None, ct.polys, nq)
+                continue
+            key = keys[b]
+            pre = getattr(key, "_pre_permuted", None)
+            if pre is None:
+                kd = key.data
+                flat = be.automorphism(kd.reshape((-1, 1) + tuple(kd.shape[-2:])), pow(int(key.galois), -1, two_n), kd.shape[-2], 0)
+                pre = key._pre_permuted = flat.reshape(kd.shape)
+            acc = be.ks_accum(be.ks_inner(ext, c1, pre, nq), None, None, c0, nq)
+            Z[b] = be.automorphism(acc, key.galois, nq, K)
+        inners = []
+        for row in rows:
+            acc = None
+            for b, p in zip(blist, row):
+                if p is None:
+                    continue
+                term = be.mul(Z[b], pt(p), nq, K)
+                acc = term if acc is None else be.add(acc, term, nq, K)
+            inners.append(acc)
+    acc = None
+    for g, inner in zip(glist, inners):
+        if g == 0:
+            acc = inner if acc is None else be.add(acc, inner, nq, K)
+            continue
+        key = keys[g]
+        low = be.moddown_inplace(inner, nq) if hasattr(be, "moddown_inplace") else be.moddown(inner, nq)
+        rot = be.automorphism(low, key.galois, nq, 0)
+        acc = be.ks_accum(acc, be.select_poly(rot, 1), key.data, be.select_poly(rot, 0), nq)
+        engine._count('keyswitch_galois')
+    engine._count('rescale')
+    return Ciphertext(engine, be.moddown_rescale(acc, nq), lvl - 1)
+
+
 def _linear_transform(engine, ct: Ciphertext, entry) -> Ciphertext:
     """sum_d diag_d (.) roll(x, -d) with baby-step / giant-step rotations; one level."""
+    if entry.get("dh") and hasattr(engine.backend, "ks_accum"):
+        return _linear_transform_dh(engine, ct, entry)
     plan_keys = entry["_keys"]
     babies: Dict[int, Ciphertext] = {0: ct}
     need = sorted({b for items in entry["giants"].values() for b, _ in items if b})

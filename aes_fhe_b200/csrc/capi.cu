@@ -381,6 +381,7 @@ static int modup_from(fhe_ctx* c, cudaStream_t s, u64* ext, LoadOp ld, int nq, i
         LoadPlain l2; l2.src = (const u64*)ext; l2.poly_stride = (long long)ne * n;
         StorePlain st; st.dst = ext; st.poly_stride = (long long)ne * n;
         ntt_fwd(c, m, batch * beta * ne, l2, ext, (long long)ne * n, st, s);
+        g_ntt_rows.fetch_sub((uint64_t)batch * nq, std::memory_order_relaxed);      // the skipped own-digit rows are not transforms
     }
     return check("fhe_modup");
 }
@@ -786,6 +787,29 @@ int fhe_ks_inner(fhe_ctx* c, void* stream, uint64_t* acc, const uint64_t* ext, c
     launch_ks_inner(c, (cudaStream_t)stream, nq, batch, (u64*)acc, (const u64*)ext, (const u64*)d, (const u64*)ksk,
                     nullptr, nullptr);
     return check("fhe_ks_inner");
+}
+
+int fhe_bsgs_inner(fhe_ctx* c, void* stream, uint64_t* out, const uint64_t* ext, const uint64_t* ct, int ct_nq,
+                   const uint64_t* const* keys, const uint64_t* galois, const uint64_t* const* pts, int nb, int G, int nq,
+                   int batch) {
+    if (bad_shape(c, nq, 0) || c->n_p == 0 || batch < 1 || c->modup_beta[nq] > 4 || nb < 1 || nb > FHE_BSGS_MAX_BABY ||
+        G < 1 || G > FHE_BSGS_MAX_G || ct_nq < nq || !out || !ext || !ct || !keys || !galois || !pts)
+        return fail("fhe_bsgs_inner: bad arguments");
+    BsgsIn in;
+    for (int b = 0; b < FHE_BSGS_MAX_BABY; ++b) {
+        in.key[b] = b < nb ? (const u64*)keys[b] : nullptr;
+        in.galois[b] = b < nb ? (u64)galois[b] : 1;
+        for (int g = 0; g < FHE_BSGS_MAX_G; ++g) in.pt[g][b] = (g < G && b < nb) ? (const u64*)pts[(size_t)g * nb + b] : nullptr;
+    }
+    const int beta = c->modup_beta[nq];
+    constexpr int BB = 4;
+    dim3 grid(c->n / 256, nq + c->n_p, (batch + BB - 1) / BB), block(256);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (beta <= 2) launch(k_bsgs_inner<2, BB>, grid, block, s, c->T, nq, c->alpha, beta, batch, nb, G, in, (const u64*)ext,
+                          (const u64*)ct, ct_nq, (const ConstF*)c->p_mod_q, (u64*)out);
+    else launch(k_bsgs_inner<4, BB>, grid, block, s, c->T, nq, c->alpha, beta, batch, nb, G, in, (const u64*)ext,
+                (const u64*)ct, ct_nq, (const ConstF*)c->p_mod_q, (u64*)out);
+    return check("fhe_bsgs_inner");
 }
 
 // ModDown by P * q_{nq-1} of an extended accumulator acc[npoly][nq + K][N] (used as scratch) -> out[npoly][nq-1][N]

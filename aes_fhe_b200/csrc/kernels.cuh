@@ -426,6 +426,138 @@ __global__ void __launch_bounds__(256, 2) k_mul_plain_multi(DevTables Tb, int nq
     }
 }
 
+// ---------------------------------------------------------------- double-hoisted baby steps of a BSGS transform
+// All baby-step rotations of a baby-step/giant-step linear transform, their plaintext products and the sums over
+// the baby steps, in ONE pass and entirely in the extended basis Q u P ("double hoisting": no ModDown per baby
+// rotation, one per giant step):
+//
+//     out_g = sum_bb  pt[g][bb] (.) Z_bb,      Z_bb = < sigma_bb(ModUp(c1)), key_bb >  +  P (sigma_bb(c0), 0)
+//
+// sigma_bb is the Galois automorphism of baby step bb; on the bit-reversed spectrum it is the gather x[perm(p)]
+// (k_automorphism), and it commutes with the base extension bit for bit, so ONE ModUp output `ext` serves every
+// baby step.  The keys are read at p (coalesced), ext / c0 are gathered at perm(p): the automorphism maps every
+// aligned block of 2^k spectrum indices onto an aligned block, so the 32 gathers of a warp cover exactly two
+// 128-byte lines, and all gathers of one limb (batch x beta rows, 24 MB at batch 16) hit in L2 after the first
+// baby step.  Neither the rotated ciphertexts nor the products ever exist in memory: HBM sees ext once, the keys,
+// the plaintexts and the G output sums.
+//   key[bb]  : [dnum][2][n_q + n_p][N] switching key of baby step bb; nullptr = the identity (Z = P (c0, c1))
+//   pt[g][bb]: [nq + n_p][N] plaintext in the extended basis; nullptr = absent diagonal
+//   ext      : [batch][beta][nq + n_p][N] (own-digit rows are read from c1);  ct: [2][batch][ct_nq][N]
+//   out      : [G][2][batch][nq + n_p][N]           grid: (N/256, nq + n_p, ceil(batch / BB))
+#define FHE_BSGS_MAX_BABY 16
+#define FHE_BSGS_MAX_G 4
+struct BsgsIn {
+    const u64* key[FHE_BSGS_MAX_BABY];
+    u64 galois[FHE_BSGS_MAX_BABY];
+    const u64* pt[FHE_BSGS_MAX_G][FHE_BSGS_MAX_BABY];
+};
+template <int BMAX, int BB>
+__global__ void __launch_bounds__(256, 2) k_bsgs_inner(DevTables T, int nq, int alpha, int beta, int batch, int nb, int G,
+                                                       BsgsIn in, const u64* ext, const u64* ct, int ct_nq,
+                                                       const ConstF* p_mod_q, u64* out) {
+    const int t = blockIdx.y;
+    const int ne = nq + T.n_p;
+    const int id = t < nq ? t : T.n_q + (t - nq);
+    const Modulus M = T.mod[id];
+    const double q = M.qd, qi = M.qinv;
+    const int log_n = T.log_n;
+    const u32 p = blockIdx.x * 256 + threadIdx.x;
+    const int b0 = blockIdx.z * BB;
+    const size_t tot = (size_t)(T.n_q + T.n_p);
+    const int own = t < nq ? t / alpha : -1;
+    const bool qlimb = t < nq;
+    ConstF pc; pc.w = 0; pc.wq = 0;
+    if (qlimb) pc = p_mod_q[t];
+    const u32 mask = (2u << log_n) - 1;
+    const u32 kbr = brev32(p) >> (32 - log_n);
+    const size_t c1_off = ((size_t)batch * ct_nq) << log_n;             // polynomial 1 of ct
+    double acc[FHE_BSGS_MAX_G][2][BB];
+#pragma unroll
+    for (int g = 0; g < FHE_BSGS_MAX_G; ++g)
+#pragma unroll
+        for (int u = 0; u < BB; ++u) { acc[g][0][u] = 0.0; acc[g][1][u] = 0.0; }
+    for (int bb = 0; bb < nb; ++bb) {
+        double pv[FHE_BSGS_MAX_G];
+#pragma unroll
+        for (int g = 0; g < FHE_BSGS_MAX_G; ++g) {
+            const u64* pp = g < G ? in.pt[g][bb] : nullptr;
+            pv[g] = pp != nullptr ? u64_to_f(ld_u64(pp + ((size_t)t << log_n) + p)) : 0.0;
+        }
+        const u64* key = in.key[bb];
+        double k0[BMAX], k1[BMAX];
+        u32 pp = p;
+        if (key != nullptr) {
+#pragma unroll
+            for (int j = 0; j < BMAX; ++j) {
+                if (j < beta) {
+                    const u64* kp = key + ((((size_t)j * 2) * tot + id) << log_n) + p;
+                    k0[j] = u64_to_f(ld_u64(kp)); k1[j] = u64_to_f(ld_u64(kp + (tot << log_n)));
+                } else { k0[j] = k1[j] = 0.0; }
+            }
+            const u32 kk = (u32)((in.galois[bb] * (u64)(2 * kbr + 1)) & mask) >> 1;
+            pp = brev32(kk) >> (32 - log_n);
+        }
+        // gathers of the whole chunk first (all in flight), then the arithmetic
+        u64 e[BB][BMAX], l0[BB], l1[BB];
+#pragma unroll
+        for (int u = 0; u < BB; ++u) {
+            const int b = b0 + u;
+            if (b < batch) {
+                const u64* c0p = ct + ((((size_t)b * ct_nq) + t) << log_n) + pp;
+                if (key != nullptr) {
+#pragma unroll
+                    for (int j = 0; j < BMAX; ++j)
+                        if (j < beta)
+                            e[u][j] = ld_u64(j == own ? c0p + c1_off : ext + ((((size_t)b * beta + j) * ne + t) << log_n) + pp);
+                    l0[u] = qlimb ? ld_u64(c0p) : 0; l1[u] = 0;
+                } else {
+                    l0[u] = qlimb ? ld_u64(c0p) : 0; l1[u] = qlimb ? ld_u64(c0p + c1_off) : 0;
+                }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < BB; ++u) {
+            const int b = b0 + u;
+            if (b < batch) {
+                double z0 = 0.0, z1 = 0.0;
+                if (key != nullptr) {
+#pragma unroll
+                    for (int j = 0; j < BMAX; ++j)
+                        if (j < beta) {
+                            const double ev = u64_to_f(e[u][j]);
+                            z0 = d_add(z0, mulmod_var(ev, k0[j], q, qi));
+                            z1 = d_add(z1, mulmod_var(ev, k1[j], q, qi));
+                        }
+                    if (qlimb) z0 = d_add(z0, mulmod_const(u64_to_f(l0[u]), pc, q));
+                } else if (qlimb) {
+                    z0 = mulmod_const(u64_to_f(l0[u]), pc, q);
+                    z1 = mulmod_const(u64_to_f(l1[u]), pc, q);
+                }
+                // |z| <= (beta + 1) 0.51 q < 2^47: a valid mulmod_var operand; the sums over the baby steps stay lazy
+#pragma unroll
+                for (int g = 0; g < FHE_BSGS_MAX_G; ++g)
+                    if (g < G) {
+                        acc[g][0][u] = d_add(acc[g][0][u], mulmod_var(z0, pv[g], q, qi));
+                        acc[g][1][u] = d_add(acc[g][1][u], mulmod_var(z1, pv[g], q, qi));
+                    }
+            }
+        }
+    }
+    const size_t ops = ((size_t)batch * ne) << log_n;
+#pragma unroll
+    for (int g = 0; g < FHE_BSGS_MAX_G; ++g)
+        if (g < G)
+#pragma unroll
+            for (int u = 0; u < BB; ++u) {
+                const int b = b0 + u;
+                if (b < batch) {
+                    u64* o = out + (size_t)g * 2 * ops + ((((size_t)b * ne) + t) << log_n) + p;
+                    o[0] = f_to_u64(reduce_canon(acc[g][0][u], q, qi));
+                    o[ops] = f_to_u64(reduce_canon(acc[g][1][u], q, qi));
+                }
+            }
+}
+
 // ---------------------------------------------------------------- base conversion
 // One table per source basis.  Output value for target t:
 //     sum_k yc_k * f[k][t]   (mod m_t),     yc_k = centred representative of y_k mod q_k

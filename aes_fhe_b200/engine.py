@@ -103,14 +103,18 @@ class Plaintext:
         self.const = encoding.as_constant(self.values) if self.values.size == engine.slot_count else None
         self._cache: Dict[int, Any] = {}
 
-    def at_level(self, level: int):
-        h = self._cache.get(level)
+    def at_level(self, level: int, ext: bool = False):
+        """residues at `level`; ``ext``: in the extended basis Q u P (limbs 0..level followed by the special primes),
+        for products with key-switch accumulators that have not been divided by P yet (double hoisting)"""
+        h = self._cache.get((level, ext))
         if h is None:
             eng = self.engine
             scale = eng.params.scale(level) if self.scale_fn is None else float(self.scale_fn(level))
             if scale < 2.0 ** 58:
                 coeffs = encoding.encode_i64(self.values, scale, eng.params.log_n)
-                h = eng.backend.from_i64(coeffs, level + 1, False)
+                h = eng.backend.from_i64(coeffs, level + 1, ext)
+            elif ext:
+                raise RuntimeError("extended-basis encoding is not available at this scale")
             else:
                 # very high scale (first bootstrapping matrix): coefficient = hi * 2^40 + lo, both
                 # exact in int64, recombined on the residues
@@ -121,7 +125,7 @@ class Plaintext:
                 fac = [(1 << 40) % eng.params.moduli[l] for l in range(nq)]
                 h = be.add(be.mul_scalar(be.from_i64(hi.astype(np.int64), nq, False), fac, nq, 0),
                            be.from_i64(lo.astype(np.int64), nq, False), nq, 0)
-            self._cache[level] = h
+            self._cache[(level, ext)] = h
         return h
 
 

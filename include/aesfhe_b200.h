@@ -108,6 +108,18 @@ int fhe_lincomb(fhe_ctx* ctx, void* stream, uint64_t* out, const uint64_t* const
 int fhe_mul_plain_sum(fhe_ctx* ctx, void* stream, uint64_t* out, const uint64_t* const* a, const int* a_nq,
                       const uint64_t* const* p, int T, int nq, int batch, int accumulate);
 
+/* Double-hoisted baby steps of a baby-step/giant-step linear transform (the CoeffToSlot / SlotToCoeff matrices of
+ * Engine.bootstrap, xor_service.py:120-129): for nb <= 16 baby rotations of ONE ciphertext batch and G <= 4 giant
+ * steps,  out[G][2][batch][nq+K][N],  out_g = sum_b pts[g * nb + b] (.) ( <sigma_b(ext), keys[b]> + P (sigma_b(c0), 0) )
+ * in the extended basis: no rotated ciphertext is stored and no ModDown happens per baby step (one per giant step,
+ * by the caller: fhe_moddown / fhe_ks_accum / fhe_moddown_rescale).  ext = fhe_modup output of c1 of `ct`
+ * ([2][batch][ct_nq >= nq][N]); keys[b] = Galois key of baby step b with Galois element galois[b] (host arrays of
+ * device pointers / values), keys[b] == NULL = no rotation; pts[.] = plaintexts [nq+K][N] in the extended basis,
+ * NULL = absent diagonal. */
+int fhe_bsgs_inner(fhe_ctx* ctx, void* stream, uint64_t* out, const uint64_t* ext, const uint64_t* ct, int ct_nq,
+                   const uint64_t* const* keys, const uint64_t* galois, const uint64_t* const* pts, int nb, int G,
+                   int nq, int batch);
+
 /* The same pattern for G output sums over ONE set of T ciphertexts (the diagonal sums of all giant steps of a
  * baby-step/giant-step linear transform in Engine.bootstrap, xor_service.py:120-129): out[G][2][batch][nq][N],
  * out_g = sum_t a_t (.) p[g * T + t]; a NULL plaintext pointer skips that term.  Every a_t is read once. */

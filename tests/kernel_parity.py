@@ -235,3 +235,38 @@ def check_fused_services(P, gpu_backend, ref_backend, batch=2):
         outs.append((be.to_numpy(out.polys), be.to_numpy(r.polys)))
     assert np.array_equal(outs[0][0], outs[1][0]), "BSGS S-box residues"
     assert np.array_equal(outs[0][1], outs[1][1]), "fused XOR residues"
+
+
+def check_double_hoisted_transform(P, gpu_backend, ref_backend, batch=3, half_width=20, stride=2):
+    """A BSGS linear transform (the shape of the bootstrap's CoeffToSlot / SlotToCoeff factors: diagonals at the
+    rotations stride * k, -half_width <= k < half_width) with double hoisting: the fused kernel fhe_bsgs_inner on
+    the GPU side against the same sum assembled from the oracle's primitives (ModUp, key inner product with the
+    permuted key, lift, automorphism, extended-basis plaintext products) -- identical residues; slots equal to the
+    matrix applied in NumPy; and identical to the single-hoisted evaluation within CKKS noise."""
+    from aes_fhe_b200 import bootstrap as B
+    from aes_fhe_b200.engine import Engine
+    outs, slots = [], []
+    for be in (gpu_backend, ref_backend):
+        eng = Engine(_params=P, _backend=be, seed=11)
+        sk = eng.create_secret_key()
+        pk = eng.create_public_key(sk)
+        n = eng.slot_count
+        rng = np.random.default_rng(4)
+        mat = {(stride * k) % n: (rng.standard_normal(n) + 1j * rng.standard_normal(n)) * 0.2
+               for k in range(-half_width, half_width)}
+        v = rng.standard_normal((batch, n)) + 1j * rng.standard_normal((batch, n))
+        ct = eng.encrypt(v, pk)
+        keys = {}
+        entry = B.prepare_matrix(eng, sk, mat, keys, None, double_hoist=True)
+        nb = len({b for items in entry["giants"].values() for b, _ in items})
+        assert entry["dh"] and nb <= 16 and len(entry["giants"]) <= 4
+        out = B._linear_transform(eng, ct, entry)
+        assert out.level == ct.level - 1
+        want = sum(d_vec * np.roll(v, -d, axis=-1) for d, d_vec in mat.items())
+        got = eng.decrypt(out, sk)
+        assert np.abs(got - want).max() < 1e-5 * max(1.0, np.abs(want).max()), np.abs(got - want).max()
+        single = B._linear_transform(eng, ct, B.prepare_matrix(eng, sk, mat, keys, None, double_hoist=False))
+        assert np.abs(eng.decrypt(single, sk) - got).max() < 1e-5 * max(1.0, np.abs(want).max())
+        outs.append(be.to_numpy(out.polys))
+        slots.append(got)
+    assert np.array_equal(outs[0], outs[1]), "double-hoisted transform residues"

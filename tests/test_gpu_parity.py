@@ -246,3 +246,11 @@ def test_byte_nibble_bridge_gf_service_on_gpu(ref_backend_cls, cuda_lib):
         h2, l2 = fn(ct)
         assert np.array_equal(ZetaEncoder.from_zeta(w.decrypt(h2)), tab[x] >> 4)
         assert np.array_equal(ZetaEncoder.from_zeta(w.decrypt(l2), 256), tab[x] & 15)
+
+
+@pytest.mark.parametrize("log_n,lvl,half_width,batch", [(13, 8, 31, 5), (16, 6, 31, 2)])
+def test_double_hoisted_transform_on_gpu(log_n, lvl, half_width, batch, ref_backend_cls, cuda_lib):
+    """fhe_bsgs_inner on the B200 against the oracle's primitives, residue for residue (62 diagonals: 16 baby x 4
+    giant steps, the shape of a CoeffToSlot factor at N = 2^16)"""
+    P = make_params(log_n, lvl)
+    kp.check_double_hoisted_transform(P, _gpu(P), ref_backend_cls(P), batch=batch, half_width=half_width)
