@@ -802,13 +802,29 @@ int fhe_bsgs_inner(fhe_ctx* c, void* stream, uint64_t* out, const uint64_t* ext,
         for (int g = 0; g < FHE_BSGS_MAX_G; ++g) in.pt[g][b] = (g < G && b < nb) ? (const u64*)pts[(size_t)g * nb + b] : nullptr;
     }
     const int beta = c->modup_beta[nq];
-    constexpr int BB = 4;
-    dim3 grid(c->n / 256, nq + c->n_p, (batch + BB - 1) / BB), block(256);
     cudaStream_t s = (cudaStream_t)stream;
-    if (beta <= 2) launch(k_bsgs_inner<2, BB>, grid, block, s, c->T, nq, c->alpha, beta, batch, nb, G, in, (const u64*)ext,
-                          (const u64*)ct, ct_nq, (const ConstF*)c->p_mod_q, (u64*)out);
-    else launch(k_bsgs_inner<4, BB>, grid, block, s, c->T, nq, c->alpha, beta, batch, nb, G, in, (const u64*)ext,
-                (const u64*)ct, ct_nq, (const ConstF*)c->p_mod_q, (u64*)out);
+    // variant 2 (default): accumulators in shared memory, 3 CTAs per SM: 4.8 ms at the CoeffToSlot shape against 5.5 ms for
+    // variant 0 (accumulators in registers, 2 CTAs per SM); env FHE_BSGS_VARIANT, tools/bsgs_bench.py
+    static const int variant = getenv("FHE_BSGS_VARIANT") ? atoi(getenv("FHE_BSGS_VARIANT")) : 2;
+    constexpr int BB = 4;
+    const dim3 grid((c->n / 256) * ((batch + BB - 1) / BB), nq + c->n_p), block(256);
+#define FHE_BSGS_GO(BE, GN) do { \
+        if (variant == 2) { const size_t smem = (size_t)GN * 2 * BB * 256 * sizeof(double); \
+            lc_allow_smem(k_bsgs_inner<BE, GN, BB, true>, smem); g_launches.fetch_add(1, std::memory_order_relaxed); \
+            fhe_launch(k_bsgs_inner<BE, GN, BB, true>, grid, block, smem, s, c->T, nq, c->alpha, batch, nb, in, (const u64*)ext, \
+                       (const u64*)ct, ct_nq, (const ConstF*)c->p_mod_q, (u64*)out); } \
+        else launch(k_bsgs_inner<BE, GN, BB, false>, grid, block, s, c->T, nq, c->alpha, batch, nb, in, (const u64*)ext, \
+                    (const u64*)ct, ct_nq, (const ConstF*)c->p_mod_q, (u64*)out); } while (0)
+#define FHE_BSGS_G(BE) switch (G) { case 1: FHE_BSGS_GO(BE, 1); break; case 2: FHE_BSGS_GO(BE, 2); break; \
+                                    case 3: FHE_BSGS_GO(BE, 3); break; default: FHE_BSGS_GO(BE, 4); break; }
+    switch (beta) {
+        case 1: FHE_BSGS_G(1); break;
+        case 2: FHE_BSGS_G(2); break;
+        case 3: FHE_BSGS_G(3); break;
+        default: FHE_BSGS_G(4); break;
+    }
+#undef FHE_BSGS_G
+#undef FHE_BSGS_GO
     return check("fhe_bsgs_inner");
 }
 

@@ -443,7 +443,9 @@ __global__ void __launch_bounds__(256, 2) k_mul_plain_multi(DevTables Tb, int nq
 //   key[bb]  : [dnum][2][n_q + n_p][N] switching key of baby step bb; nullptr = the identity (Z = P (c0, c1))
 //   pt[g][bb]: [nq + n_p][N] plaintext in the extended basis; nullptr = absent diagonal
 //   ext      : [batch][beta][nq + n_p][N] (own-digit rows are read from c1);  ct: [2][batch][ct_nq][N]
-//   out      : [G][2][batch][nq + n_p][N]           grid: (N/256, nq + n_p, ceil(batch / BB))
+//   out      : [G][2][batch][nq + n_p][N]
+// grid: (N/256 * chunks, nq + n_p), chunks = ceil(batch / BB): the batch chunks of one (tile, limb) are neighbours in
+// launch order, so the keys and plaintexts they share are read from HBM once and from L2 afterwards
 #define FHE_BSGS_MAX_BABY 16
 #define FHE_BSGS_MAX_G 4
 struct BsgsIn {
@@ -451,18 +453,26 @@ struct BsgsIn {
     u64 galois[FHE_BSGS_MAX_BABY];
     const u64* pt[FHE_BSGS_MAX_G][FHE_BSGS_MAX_BABY];
 };
-template <int BMAX, int BB>
-__global__ void __launch_bounds__(256, 2) k_bsgs_inner(DevTables T, int nq, int alpha, int beta, int batch, int nb, int G,
-                                                       BsgsIn in, const u64* ext, const u64* ct, int ct_nq,
-                                                       const ConstF* p_mod_q, u64* out) {
+// BETA (digits), GN (giant steps) and BB (ciphertexts per thread) are compile-time and the batch tail is handled by
+// clamping, so the body has no data-dependent branch inside a baby step: the 14 + 8 independent modular products of
+// every ciphertext of a chunk are one basic block the scheduler can interleave (a first version with runtime
+// `j < beta` / `g < G` tests compiled to ~7-instruction blocks and ran at 25 % of the FP64 pipe).  All row addresses
+// are formed once per thread; a baby step only adds its gather index.
+// SMACC: the GN x 2 x BB lazy accumulators of a thread live in shared memory ([slot][thread], conflict-free) instead
+// of registers.
+template <int BETA, int GN, int BB, bool SMACC>
+__global__ void __launch_bounds__(256, (SMACC ? 3 : 2)) k_bsgs_inner(DevTables T, int nq, int alpha, int batch, int nb,
+                                                                  BsgsIn in, const u64* ext, const u64* ct, int ct_nq,
+                                                                  const ConstF* p_mod_q, u64* out) {
     const int t = blockIdx.y;
     const int ne = nq + T.n_p;
     const int id = t < nq ? t : T.n_q + (t - nq);
     const Modulus M = T.mod[id];
     const double q = M.qd, qi = M.qinv;
     const int log_n = T.log_n;
-    const u32 p = blockIdx.x * 256 + threadIdx.x;
-    const int b0 = blockIdx.z * BB;
+    const int chunks = (batch + BB - 1) / BB;
+    const u32 p = (blockIdx.x / chunks) * 256 + threadIdx.x;
+    const int b0 = (blockIdx.x % chunks) * BB;
     const size_t tot = (size_t)(T.n_q + T.n_p);
     const int own = t < nq ? t / alpha : -1;
     const bool qlimb = t < nq;
@@ -471,91 +481,91 @@ __global__ void __launch_bounds__(256, 2) k_bsgs_inner(DevTables T, int nq, int 
     const u32 mask = (2u << log_n) - 1;
     const u32 kbr = brev32(p) >> (32 - log_n);
     const size_t c1_off = ((size_t)batch * ct_nq) << log_n;             // polynomial 1 of ct
-    double acc[FHE_BSGS_MAX_G][2][BB];
+    // row bases, fixed for the whole kernel (a clamped tail ciphertext recomputes the last one and is not stored)
+    const u64* erow[BB][BETA];
+    const u64* crow[BB];
 #pragma unroll
-    for (int g = 0; g < FHE_BSGS_MAX_G; ++g)
+    for (int u = 0; u < BB; ++u) {
+        const int b = min(b0 + u, batch - 1);
+        crow[u] = ct + ((((size_t)b * ct_nq) + (qlimb ? t : 0)) << log_n);
 #pragma unroll
-        for (int u = 0; u < BB; ++u) { acc[g][0][u] = 0.0; acc[g][1][u] = 0.0; }
+        for (int j = 0; j < BETA; ++j)
+            erow[u][j] = j == own ? crow[u] + c1_off : ext + ((((size_t)b * BETA + j) * ne + t) << log_n);
+    }
+    const size_t key_row = ((size_t)id << log_n) + p, key_poly = tot << log_n, pt_row = ((size_t)t << log_n) + p;
+    double acc[SMACC ? 1 : GN][2][SMACC ? 1 : BB];
+    FHE_DYN_SHARED(double, sacc);                                       // SMACC: [GN * 2 * BB][256]
+#define FHE_ACC(g, pl, u) (*(SMACC ? &sacc[(((g) * 2 + (pl)) * BB + (u)) * 256 + threadIdx.x] : &acc[SMACC ? 0 : (g)][pl][SMACC ? 0 : (u)]))
+#pragma unroll
+    for (int g = 0; g < GN; ++g)
+#pragma unroll
+        for (int u = 0; u < BB; ++u) { FHE_ACC(g, 0, u) = 0.0; FHE_ACC(g, 1, u) = 0.0; }
     for (int bb = 0; bb < nb; ++bb) {
-        double pv[FHE_BSGS_MAX_G];
+        double pv[GN];
 #pragma unroll
-        for (int g = 0; g < FHE_BSGS_MAX_G; ++g) {
-            const u64* pp = g < G ? in.pt[g][bb] : nullptr;
-            pv[g] = pp != nullptr ? u64_to_f(ld_u64(pp + ((size_t)t << log_n) + p)) : 0.0;
+        for (int g = 0; g < GN; ++g) {
+            const u64* pp = in.pt[g][bb];
+            pv[g] = pp != nullptr ? u64_to_f(ld_u64(pp + pt_row)) : 0.0;
         }
         const u64* key = in.key[bb];
-        double k0[BMAX], k1[BMAX];
-        u32 pp = p;
+        double z0[BB], z1[BB];
         if (key != nullptr) {
+            double k0[BETA], k1[BETA];
 #pragma unroll
-            for (int j = 0; j < BMAX; ++j) {
-                if (j < beta) {
-                    const u64* kp = key + ((((size_t)j * 2) * tot + id) << log_n) + p;
-                    k0[j] = u64_to_f(ld_u64(kp)); k1[j] = u64_to_f(ld_u64(kp + (tot << log_n)));
-                } else { k0[j] = k1[j] = 0.0; }
+            for (int j = 0; j < BETA; ++j) {
+                const u64* kp = key + (size_t)j * 2 * key_poly + key_row;
+                k0[j] = u64_to_f(ld_u64(kp)); k1[j] = u64_to_f(ld_u64(kp + key_poly));
             }
             const u32 kk = (u32)((in.galois[bb] * (u64)(2 * kbr + 1)) & mask) >> 1;
-            pp = brev32(kk) >> (32 - log_n);
-        }
-        // gathers of the whole chunk first (all in flight), then the arithmetic
-        u64 e[BB][BMAX], l0[BB], l1[BB];
+            const u32 pp = brev32(kk) >> (32 - log_n);
+            u64 e[BB][BETA], l0[BB];
 #pragma unroll
-        for (int u = 0; u < BB; ++u) {
-            const int b = b0 + u;
-            if (b < batch) {
-                const u64* c0p = ct + ((((size_t)b * ct_nq) + t) << log_n) + pp;
-                if (key != nullptr) {
+            for (int u = 0; u < BB; ++u) {
 #pragma unroll
-                    for (int j = 0; j < BMAX; ++j)
-                        if (j < beta)
-                            e[u][j] = ld_u64(j == own ? c0p + c1_off : ext + ((((size_t)b * beta + j) * ne + t) << log_n) + pp);
-                    l0[u] = qlimb ? ld_u64(c0p) : 0; l1[u] = 0;
-                } else {
-                    l0[u] = qlimb ? ld_u64(c0p) : 0; l1[u] = qlimb ? ld_u64(c0p + c1_off) : 0;
+                for (int j = 0; j < BETA; ++j) e[u][j] = ld_u64(erow[u][j] + pp);
+                l0[u] = ld_u64(crow[u] + pp);
+            }
+#pragma unroll
+            for (int u = 0; u < BB; ++u) {
+                double a0 = 0.0, a1 = 0.0;
+#pragma unroll
+                for (int j = 0; j < BETA; ++j) {
+                    const double ev = u64_to_f(e[u][j]);
+                    a0 = d_add(a0, mulmod_var(ev, k0[j], q, qi));
+                    a1 = d_add(a1, mulmod_var(ev, k1[j], q, qi));
                 }
+                z0[u] = d_add(a0, mulmod_const(u64_to_f(l0[u]), pc, q));      // pc = 0 on the special limbs
+                z1[u] = a1;
+            }
+        } else {
+#pragma unroll
+            for (int u = 0; u < BB; ++u) {
+                z0[u] = mulmod_const(u64_to_f(ld_u64(crow[u] + p)), pc, q);
+                z1[u] = mulmod_const(u64_to_f(ld_u64(crow[u] + c1_off + p)), pc, q);
             }
         }
+        // |z| <= (BETA + 1) 0.51 q < 2^47: a valid mulmod_var operand; the sums over the baby steps stay lazy
 #pragma unroll
-        for (int u = 0; u < BB; ++u) {
-            const int b = b0 + u;
-            if (b < batch) {
-                double z0 = 0.0, z1 = 0.0;
-                if (key != nullptr) {
+        for (int u = 0; u < BB; ++u)
 #pragma unroll
-                    for (int j = 0; j < BMAX; ++j)
-                        if (j < beta) {
-                            const double ev = u64_to_f(e[u][j]);
-                            z0 = d_add(z0, mulmod_var(ev, k0[j], q, qi));
-                            z1 = d_add(z1, mulmod_var(ev, k1[j], q, qi));
-                        }
-                    if (qlimb) z0 = d_add(z0, mulmod_const(u64_to_f(l0[u]), pc, q));
-                } else if (qlimb) {
-                    z0 = mulmod_const(u64_to_f(l0[u]), pc, q);
-                    z1 = mulmod_const(u64_to_f(l1[u]), pc, q);
-                }
-                // |z| <= (beta + 1) 0.51 q < 2^47: a valid mulmod_var operand; the sums over the baby steps stay lazy
-#pragma unroll
-                for (int g = 0; g < FHE_BSGS_MAX_G; ++g)
-                    if (g < G) {
-                        acc[g][0][u] = d_add(acc[g][0][u], mulmod_var(z0, pv[g], q, qi));
-                        acc[g][1][u] = d_add(acc[g][1][u], mulmod_var(z1, pv[g], q, qi));
-                    }
+            for (int g = 0; g < GN; ++g) {
+                FHE_ACC(g, 0, u) = d_add(FHE_ACC(g, 0, u), mulmod_var(z0[u], pv[g], q, qi));
+                FHE_ACC(g, 1, u) = d_add(FHE_ACC(g, 1, u), mulmod_var(z1[u], pv[g], q, qi));
             }
-        }
     }
     const size_t ops = ((size_t)batch * ne) << log_n;
 #pragma unroll
-    for (int g = 0; g < FHE_BSGS_MAX_G; ++g)
-        if (g < G)
+    for (int g = 0; g < GN; ++g)
 #pragma unroll
-            for (int u = 0; u < BB; ++u) {
-                const int b = b0 + u;
-                if (b < batch) {
-                    u64* o = out + (size_t)g * 2 * ops + ((((size_t)b * ne) + t) << log_n) + p;
-                    o[0] = f_to_u64(reduce_canon(acc[g][0][u], q, qi));
-                    o[ops] = f_to_u64(reduce_canon(acc[g][1][u], q, qi));
-                }
+        for (int u = 0; u < BB; ++u) {
+            const int b = b0 + u;
+            if (b < batch) {
+                u64* o = out + (size_t)g * 2 * ops + ((((size_t)b * ne) + t) << log_n) + p;
+                o[0] = f_to_u64(reduce_canon(FHE_ACC(g, 0, u), q, qi));
+                o[ops] = f_to_u64(reduce_canon(FHE_ACC(g, 1, u), q, qi));
             }
+        }
+#undef FHE_ACC
 }
 
 // ---------------------------------------------------------------- base conversion
