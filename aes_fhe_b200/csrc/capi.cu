@@ -279,20 +279,28 @@ void build_level_tables(fhe_ctx* c) {
 
 template <int NS>
 void launch_bconv_ns(fhe_ctx* c, cudaStream_t s, int groups, const BConvTable* tabs, int n_tabs, u64* dst,
-                     long long dst_stride, const u64* src, long long src_stride) {
-    launch(k_bconv<NS>, dim3(c->n / 512, groups), dim3(256), s, c->T, tabs, n_tabs, dst, dst_stride, src, src_stride);
+                     long long dst_stride, const u64* src, long long src_stride, int g_first, int g_step) {
+    launch(k_bconv<NS>, dim3(c->n / 512, groups), dim3(256), s, c->T, tabs, n_tabs, dst, dst_stride, src, src_stride, g_first,
+           g_step);
 }
-void launch_bconv(fhe_ctx* c, cudaStream_t s, int ns_max, int groups, const BConvTable* tabs, int n_tabs, u64* dst,
-                  long long dst_stride, const u64* src, long long src_stride) {
-#define FHE_BCONV_CASE(NS) case NS: launch_bconv_ns<NS>(c, s, groups, tabs, n_tabs, dst, dst_stride, src, src_stride); break;
-    switch (ns_max) {
+// one launch over groups g = y * g_step + g_first (y < groups) whose tables all have exactly `ns` sources
+void launch_bconv_exact(fhe_ctx* c, cudaStream_t s, int ns, int groups, const BConvTable* tabs, int n_tabs, u64* dst,
+                        long long dst_stride, const u64* src, long long src_stride, int g_first, int g_step) {
+#define FHE_BCONV_CASE(NS) case NS: launch_bconv_ns<NS>(c, s, groups, tabs, n_tabs, dst, dst_stride, src, src_stride, g_first, g_step); break;
+    switch (ns) {
         FHE_BCONV_CASE(1) FHE_BCONV_CASE(2) FHE_BCONV_CASE(3) FHE_BCONV_CASE(4)
         FHE_BCONV_CASE(5) FHE_BCONV_CASE(6) FHE_BCONV_CASE(7) FHE_BCONV_CASE(8)
         FHE_BCONV_CASE(9) FHE_BCONV_CASE(10) FHE_BCONV_CASE(11) FHE_BCONV_CASE(12)
-        FHE_BCONV_CASE(13) FHE_BCONV_CASE(14) FHE_BCONV_CASE(15)
-        default: launch_bconv_ns<16>(c, s, groups, tabs, n_tabs, dst, dst_stride, src, src_stride); break;
+        FHE_BCONV_CASE(13) FHE_BCONV_CASE(14) FHE_BCONV_CASE(15) FHE_BCONV_CASE(16)
+        default: break;                                   // FHE_MAX_SRC = 16, checked at context creation
     }
 #undef FHE_BCONV_CASE
+}
+// `src_counts[j]`: sources of table j (a ModUp launches its digits one by one, each with its exact digit size)
+void launch_bconv(fhe_ctx* c, cudaStream_t s, const int* src_counts, int groups, const BConvTable* tabs, int n_tabs, u64* dst,
+                  long long dst_stride, const u64* src, long long src_stride) {
+    for (int j = 0; j < n_tabs; ++j)
+        launch_bconv_exact(c, s, src_counts[j], groups / n_tabs, tabs, n_tabs, dst, dst_stride, src, src_stride, j, n_tabs);
 }
 
 // ab: `d` / `lift` are the operand ciphertexts a / b of a fused multiply (k_ks_inner, AB)
@@ -304,17 +312,17 @@ void launch_ks_inner(fhe_ctx* c, cudaStream_t s, int nq, int batch, u64* acc, co
     if (lift_nq == 0) lift_nq = nq;
     const int beta = lift_only ? 0 : c->modup_beta[nq];
     dim3 grid(c->n / 256, nq + c->n_p), block(256);
-#define FHE_KS_ARGS grid, block, s, c->T, nq, c->alpha, beta, batch, acc, ext, d, ksk, lift, lift_c, d_nq, lift_nq, \
+#define FHE_KS_ARGS grid, block, s, c->T, nq, c->alpha, batch, acc, ext, d, ksk, lift, lift_c, d_nq, lift_nq, \
                     lift_polys, accum
-    if (ab) {
-        if (beta <= 2) launch(k_ks_inner<2, 2, true>, FHE_KS_ARGS);
-        else if (beta <= 4) launch(k_ks_inner<4, 2, true>, FHE_KS_ARGS);
-        else launch(k_ks_inner<8, 1, true>, FHE_KS_ARGS);
-    } else {
-        if (beta <= 2) launch(k_ks_inner<2, 2, false>, FHE_KS_ARGS);
-        else if (beta <= 4) launch(k_ks_inner<4, 2, false>, FHE_KS_ARGS);
-        else launch(k_ks_inner<8, 1, false>, FHE_KS_ARGS);
+#define FHE_KS_CASE(BE, UN) case BE: if (ab) launch(k_ks_inner<BE, UN, true>, FHE_KS_ARGS); \
+                                     else launch(k_ks_inner<BE, UN, false>, FHE_KS_ARGS); break;
+    switch (beta) {
+        case 0: launch(k_ks_inner<0, 2, false>, FHE_KS_ARGS); break;
+        FHE_KS_CASE(1, 2) FHE_KS_CASE(2, 2) FHE_KS_CASE(3, 2) FHE_KS_CASE(4, 2)
+        FHE_KS_CASE(5, 1) FHE_KS_CASE(6, 1) FHE_KS_CASE(7, 1)
+        default: if (ab) launch(k_ks_inner<8, 1, true>, FHE_KS_ARGS); else launch(k_ks_inner<8, 1, false>, FHE_KS_ARGS); break;
     }
+#undef FHE_KS_CASE
 #undef FHE_KS_ARGS
 }
 #ifndef FHE_EMU
@@ -374,8 +382,9 @@ static int modup_from(fhe_ctx* c, cudaStream_t s, u64* ext, LoadOp ld, int nq, i
         StorePlain st; st.dst = y; st.poly_stride = (long long)nq * n;
         ntt_inv(c, m, batch * nq, ld, y, (long long)nq * n, st, c->modup_scale[nq], s);
     }
-    launch_bconv(c, s, std::min(c->alpha, nq), batch * beta, c->modup_tables[nq], beta, ext, (long long)ne * n, y,
-                 (long long)nq * n);
+    int digit_size[FHE_MAX_BETA];
+    for (int j = 0; j < beta; ++j) digit_size[j] = std::min(c->alpha, nq - j * c->alpha);
+    launch_bconv(c, s, digit_size, batch * beta, c->modup_tables[nq], beta, ext, (long long)ne * n, y, (long long)nq * n);
     {   // NTT of every converted row (a digit's own limbs are skipped)
         RowMap m = make_map(c, ne, 0, nq, c->alpha);
         LoadPlain l2; l2.src = (const u64*)ext; l2.poly_stride = (long long)ne * n;
@@ -838,7 +847,7 @@ static int moddown_rescale_tail(fhe_ctx* c, cudaStream_t s, u64* out, u64* acc, 
         StorePlain st; st.dst = accs; st.poly_stride = (long long)ne * n;
         ntt_inv(c, m, npoly * (K + 1), ld, accs, (long long)ne * n, st, c->mdrs_scale[nq], s);
     }
-    launch_bconv(c, s, K + 1, npoly, c->mdrs_table[nq], 1, out, (long long)no * n, accs, (long long)ne * n);
+    { const int ns = K + 1; launch_bconv(c, s, &ns, npoly, c->mdrs_table[nq], 1, out, (long long)no * n, accs, (long long)ne * n); }
     {
         RowMap m = make_map(c, no, 0, nq);
         LoadPlain ld; ld.src = (const u64*)out; ld.poly_stride = (long long)no * n;
@@ -932,7 +941,7 @@ int fhe_moddown(fhe_ctx* c, void* stream, uint64_t* out, uint64_t* acc, int nq, 
         ntt_inv(c, m, npoly * K, ld, accp, (long long)ne * n, st, c->moddown_scale, s);
     }
     // P -> q_i conversion written straight into `out` (coefficient domain) ...
-    launch_bconv(c, s, K, npoly, c->moddown_table[nq], 1, (u64*)out, (long long)nq * n, accp, (long long)ne * n);
+    { const int ns = K; launch_bconv(c, s, &ns, npoly, c->moddown_table[nq], 1, (u64*)out, (long long)nq * n, accp, (long long)ne * n); }
     {   // ... then NTT it in place and finish: out = (acc - it) * P^-1
         RowMap m = make_map(c, nq, 0, nq);
         LoadPlain ld; ld.src = (const u64*)out; ld.poly_stride = (long long)nq * n;

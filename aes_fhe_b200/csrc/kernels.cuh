@@ -591,16 +591,20 @@ struct BConvTable {
 // memory feeds two modular products, which halves the non-FP64 instructions per FP64 instruction
 // (the kernel is FP64-pipe bound and was co-limited by issue slots).   grid: (N/512, groups)
 // (forcing 4 CTAs/SM with 64 registers changes nothing: 245.8 against 248.1 us for 12-limb digits)
+// Every table of one launch has EXACTLY NS_MAX sources (the host launches the digits of a ModUp one by one: group
+// g = blockIdx.y * g_step + g_first), so the source loops carry no `k < ns` test: with the test the unrolled
+// accumulation compiled into one basic block per term and the FP64 pipe idled between them.
 template <int NS_MAX>
 __global__ void __launch_bounds__(256) k_bconv(DevTables T, const BConvTable* tables, int n_tables,
                                                u64* dst, long long dst_group_stride,
-                                               const u64* src, long long src_block_stride) {
+                                               const u64* src, long long src_block_stride, int g_first, int g_step) {
     FHE_SHARED ConstF sf[FHE_MAX_DST * NS_MAX];
     FHE_SHARED double sq[FHE_MAX_DST], sqi[FHE_MAX_DST];
     FHE_SHARED int sslot[FHE_MAX_DST];
-    const int g = blockIdx.y;
+    const int g = blockIdx.y * g_step + g_first;
     const BConvTable& tb = tables[g % n_tables];
-    const int ns = tb.ns, nt = tb.nt;
+    constexpr int ns = NS_MAX;
+    const int nt = tb.nt;
     for (int i = threadIdx.x; i < nt * NS_MAX; i += 256) sf[i] = tb.f[i / NS_MAX][i % NS_MAX];
     for (int t = threadIdx.x; t < nt; t += 256) {
         const Modulus M = T.mod[tb.dst_mod[t]];
@@ -612,16 +616,18 @@ __global__ void __launch_bounds__(256) k_bconv(DevTables T, const BConvTable* ta
     const u64* s = src + (size_t)(g / n_tables) * src_block_stride + idx;
     u64* d = dst + (size_t)g * dst_group_stride + idx;
     double y0[NS_MAX], y1[NS_MAX];
+    u64 v0[NS_MAX], v1[NS_MAX];
 #pragma unroll
-    for (int k = 0; k < NS_MAX; ++k) {
-        if (k < ns) {
-            const u64* sp = s + ((size_t)tb.src_slot[k] << log_n);
-            const u64 v0 = sp[0], v1 = sp[half];
-            const u64 qk = T.mod[tb.src_mod[k]].q;
-            const double qkd = u64_to_f(qk);
-            y0[k] = v0 > (qk >> 1) ? d_add(u64_to_f(v0), -qkd) : u64_to_f(v0);
-            y1[k] = v1 > (qk >> 1) ? d_add(u64_to_f(v1), -qkd) : u64_to_f(v1);
-        } else { y0[k] = 0.0; y1[k] = 0.0; }
+    for (int k = 0; k < ns; ++k) {                                   // all loads in flight before the first use
+        const u64* sp = s + ((size_t)tb.src_slot[k] << log_n);
+        v0[k] = sp[0]; v1[k] = sp[half];
+    }
+#pragma unroll
+    for (int k = 0; k < ns; ++k) {
+        const u64 qk = T.mod[tb.src_mod[k]].q;
+        const double qkd = u64_to_f(qk);
+        y0[k] = v0[k] > (qk >> 1) ? d_add(u64_to_f(v0[k]), -qkd) : u64_to_f(v0[k]);
+        y1[k] = v1[k] > (qk >> 1) ? d_add(u64_to_f(v1[k]), -qkd) : u64_to_f(v1[k]);
     }
     __syncthreads();
     // two targets per iteration: four independent accumulation chains per thread
@@ -630,14 +636,13 @@ __global__ void __launch_bounds__(256) k_bconv(DevTables T, const BConvTable* ta
         const double qa = sq[t], qb = sq[t + 1];
         double a0 = 0.0, a1 = 0.0, b0 = 0.0, b1 = 0.0;
 #pragma unroll
-        for (int k = 0; k < NS_MAX; ++k)
-            if (k < ns) {
-                const ConstF ca = sf[t * NS_MAX + k], cb = sf[(t + 1) * NS_MAX + k];
-                a0 = d_add(a0, mulmod_const(y0[k], ca, qa));
-                a1 = d_add(a1, mulmod_const(y1[k], ca, qa));
-                b0 = d_add(b0, mulmod_const(y0[k], cb, qb));
-                b1 = d_add(b1, mulmod_const(y1[k], cb, qb));
-            }
+        for (int k = 0; k < ns; ++k) {
+            const ConstF ca = sf[t * NS_MAX + k], cb = sf[(t + 1) * NS_MAX + k];
+            a0 = d_add(a0, mulmod_const(y0[k], ca, qa));
+            a1 = d_add(a1, mulmod_const(y1[k], ca, qa));
+            b0 = d_add(b0, mulmod_const(y0[k], cb, qb));
+            b1 = d_add(b1, mulmod_const(y1[k], cb, qb));
+        }
         u64* da = d + ((size_t)sslot[t] << log_n);
         u64* db = d + ((size_t)sslot[t + 1] << log_n);
         da[0] = f_to_u64(reduce_canon(a0, qa, sqi[t]));
@@ -649,12 +654,11 @@ __global__ void __launch_bounds__(256) k_bconv(DevTables T, const BConvTable* ta
         const double q = sq[t];
         double a0 = 0.0, a1 = 0.0;
 #pragma unroll
-        for (int k = 0; k < NS_MAX; ++k)
-            if (k < ns) {
-                const ConstF c = sf[t * NS_MAX + k];
-                a0 = d_add(a0, mulmod_const(y0[k], c, q));
-                a1 = d_add(a1, mulmod_const(y1[k], c, q));
-            }
+        for (int k = 0; k < ns; ++k) {
+            const ConstF c = sf[t * NS_MAX + k];
+            a0 = d_add(a0, mulmod_const(y0[k], c, q));
+            a1 = d_add(a1, mulmod_const(y1[k], c, q));
+        }
         u64* dp = d + ((size_t)sslot[t] << log_n);
         dp[0] = f_to_u64(reduce_canon(a0, q, sqi[t]));
         dp[half] = f_to_u64(reduce_canon(a1, q, sqi[t]));
@@ -690,14 +694,15 @@ FHE_D void st2(u64* p, u64 a, u64 b) {
 // AB: fused multiply + relinearise + rescale.  `d` and `lift` then are the two operand ciphertexts a, b
 // ([2][batch][nq][N]) and the tensor product is formed here: the digit's own limb is a1 b1, the lifted part
 // P * (a0 b0, a0 b1 + a1 b0) -- the 3-polynomial product never goes through HBM.
-template <int BMAX, int UNR, bool AB>
-__global__ void __launch_bounds__(256, (BMAX <= 4 ? 3 : 2)) k_ks_inner(DevTables T, int nq, int alpha, int beta, int batch,
-                                                  u64* acc, const u64* ext, const u64* d, const u64* ksk,
-                                                  const u64* lift, const ConstF* lift_c, int d_nq, int lift_nq,
-                                                  int lift_polys, int accum) {
-    // d_nq / lift_nq: limbs per batch element of `d` / `lift` (>= nq; only the AB operands may carry more)
-    // lift_polys: 2, or 1 when only polynomial 0 is lifted (a rotation: (sigma c0, 0));  accum: acc += instead of acc =
-    // beta == 0: no key-switch part at all (acc (+)= P * lift on the q-limbs, (+)= 0 on the special limbs)
+// BETA (digits touched at this level) is compile-time and the presence of the lifted term is decided ONCE per CTA
+// (one uniform branch into two specialised bodies), so the per-ciphertext arithmetic is straight-line code: with the
+// runtime `j < beta` / `has_lift` tests of the first version every modular product was its own basic block.
+// BETA == 0: no key-switch part at all (acc (+)= P * lift on the q-limbs, (+)= 0 on the special limbs).
+template <int BETA, int UNR, bool AB, bool LIFT>
+FHE_D void ks_inner_body(const DevTables& T, int nq, int alpha, int batch, u64* acc, const u64* ext, const u64* d,
+                         const u64* ksk, const u64* lift, const ConstF* lift_c, int d_nq, int lift_nq, int lift_polys,
+                         int accum) {
+    constexpr int BE = BETA > 0 ? BETA : 1;
     const int t = blockIdx.y;
     const int ne = nq + T.n_p;
     const int id = t < nq ? t : T.n_q + (t - nq);
@@ -706,48 +711,43 @@ __global__ void __launch_bounds__(256, (BMAX <= 4 ? 3 : 2)) k_ks_inner(DevTables
     const int log_n = T.log_n;
     const int idx = blockIdx.x * 256 + threadIdx.x;
     const size_t tot = (size_t)(T.n_q + T.n_p);
-    double k0[BMAX], k1[BMAX];
+    double k0[BE], k1[BE];
 #pragma unroll
-    for (int j = 0; j < BMAX; ++j) {
-        if (j < beta) {
-            const u64* kp = ksk + ((((size_t)j * 2) * tot + id) << log_n) + idx;
-            k0[j] = u64_to_f(ld_u64(kp)); k1[j] = u64_to_f(ld_u64(kp + (tot << log_n)));
-        } else { k0[j] = k1[j] = 0.0; }
+    for (int j = 0; j < BETA; ++j) {
+        const u64* kp = ksk + ((((size_t)j * 2) * tot + id) << log_n) + idx;
+        k0[j] = u64_to_f(ld_u64(kp)); k1[j] = u64_to_f(ld_u64(kp + (tot << log_n)));
     }
     const int own = t < nq ? t / alpha : -1;
-    const bool has_lift = lift != nullptr && t < nq;
     const size_t ps = (size_t)batch * lift_nq << log_n;          // polynomial strides of lift / d
     const size_t pd = (size_t)batch * d_nq << log_n;
     ConstF pc; pc.w = 0; pc.wq = 0;
-    if (has_lift) pc = lift_c[t];
+    if (LIFT) pc = lift_c[t];
     const u64* dp = d + ((size_t)t << log_n) + idx;                 // + b * nq * N
     const u64* ep = ext + ((size_t)t << log_n) + idx;               // + (b * beta + j) * ne * N
-    const u64* lp = has_lift ? lift + ((size_t)t << log_n) + idx : nullptr;
+    const u64* lp = LIFT ? lift + ((size_t)t << log_n) + idx : nullptr;
+    const bool two = AB || lift_polys == 2;
     // software pipeline: the loads of the next UNR ciphertexts are in flight while the current ones are
     // multiplied, so the memory system never waits for the FP64 work (and vice versa)
     // (AB: l0/l1 carry b0/b1 and m0/m1 carry a0/a1 of the q-limbs; the own-digit slot of e is not loaded)
-    u64 e[UNR][BMAX], l0[UNR], l1[UNR], m0[UNR], m1[UNR];
-    u64 en[UNR][BMAX], l0n[UNR], l1n[UNR], m0n[UNR], m1n[UNR];
-    const u64* bp = AB && has_lift ? d + ((size_t)t << log_n) + idx : nullptr;      // operand a (named d), q-limbs only
-    auto fetch = [&](int b0, u64 (&E)[UNR][BMAX], u64 (&L0)[UNR], u64 (&L1)[UNR], u64 (&M0)[UNR], u64 (&M1)[UNR]) {
+    u64 e[UNR][BE], l0[UNR], l1[UNR], m0[UNR], m1[UNR];
+    u64 en[UNR][BE], l0n[UNR], l1n[UNR], m0n[UNR], m1n[UNR];
+    const u64* bp = AB && LIFT ? d + ((size_t)t << log_n) + idx : nullptr;      // operand a (named d), q-limbs only
+    auto fetch = [&](int b0, u64 (&E)[UNR][BE], u64 (&L0)[UNR], u64 (&L1)[UNR], u64 (&M0)[UNR], u64 (&M1)[UNR]) {
 #pragma unroll
         for (int u = 0; u < UNR; ++u) {
-            const int b = b0 + u;
-            if (b < batch) {
+            const int b = min(b0 + u, batch - 1);                 // a clamped tail element is recomputed, not stored
 #pragma unroll
-                for (int j = 0; j < BMAX; ++j)
-                    if (j < beta) {
-                        if (AB) { if (j != own) E[u][j] = ld_u64(ep + ((((size_t)b * beta + j) * ne) << log_n)); }
-                        else E[u][j] = ld_u64(j == own ? dp + (((size_t)b * d_nq) << log_n)
-                                                       : ep + ((((size_t)b * beta + j) * ne) << log_n));
-                    }
-                if (has_lift) {
-                    L0[u] = ld_u64(lp + (((size_t)b * lift_nq) << log_n));
-                    L1[u] = AB || lift_polys == 2 ? ld_u64(lp + ps + (((size_t)b * lift_nq) << log_n)) : 0;
-                    if (AB) {
-                        M0[u] = ld_u64(bp + (((size_t)b * d_nq) << log_n));
-                        M1[u] = ld_u64(bp + pd + (((size_t)b * d_nq) << log_n));
-                    }
+            for (int j = 0; j < BETA; ++j) {
+                if (AB) { E[u][j] = j != own ? ld_u64(ep + ((((size_t)b * BETA + j) * ne) << log_n)) : 0; }
+                else E[u][j] = ld_u64(j == own ? dp + (((size_t)b * d_nq) << log_n)
+                                               : ep + ((((size_t)b * BETA + j) * ne) << log_n));
+            }
+            if (LIFT) {
+                L0[u] = ld_u64(lp + (((size_t)b * lift_nq) << log_n));
+                L1[u] = two ? ld_u64(lp + ps + (((size_t)b * lift_nq) << log_n)) : 0;
+                if (AB) {
+                    M0[u] = ld_u64(bp + (((size_t)b * d_nq) << log_n));
+                    M1[u] = ld_u64(bp + pd + (((size_t)b * d_nq) << log_n));
                 }
             }
         }
@@ -758,29 +758,27 @@ __global__ void __launch_bounds__(256, (BMAX <= 4 ? 3 : 2)) k_ks_inner(DevTables
 #pragma unroll
         for (int u = 0; u < UNR; ++u) {
             const int b = b0 + u;
-            if (b < batch) {
-                double a0 = 0.0, a1 = 0.0;
-                double own_v = 0.0, t0 = 0.0, t1 = 0.0;
-                if (AB && has_lift) {
-                    const double x0 = u64_to_f(m0[u]), x1 = u64_to_f(m1[u]), y0 = u64_to_f(l0[u]), y1 = u64_to_f(l1[u]);
-                    own_v = mulmod_var(x1, y1, q, qi);                                   // d2 on this limb
-                    t0 = mulmod_var(x0, y0, q, qi);                                      // d0
-                    // d1 = a0 b1 + a1 b0 = (a0 + a1)(b0 + b1) - d0 - d2: three products instead of four
-                    t1 = d_add(d_add(mulmod_var(d_add(x0, x1), d_add(y0, y1), q, qi), -t0), -own_v);   // |.| <= 1.6 q
-                }
+            double a0 = 0.0, a1 = 0.0;
+            double own_v = 0.0, t0 = 0.0, t1 = 0.0;
+            if (AB && LIFT) {
+                const double x0 = u64_to_f(m0[u]), x1 = u64_to_f(m1[u]), y0 = u64_to_f(l0[u]), y1 = u64_to_f(l1[u]);
+                own_v = mulmod_var(x1, y1, q, qi);                                   // d2 on this limb
+                t0 = mulmod_var(x0, y0, q, qi);                                      // d0
+                // d1 = a0 b1 + a1 b0 = (a0 + a1)(b0 + b1) - d0 - d2: three products instead of four
+                t1 = d_add(d_add(mulmod_var(d_add(x0, x1), d_add(y0, y1), q, qi), -t0), -own_v);   // |.| <= 1.6 q
+            }
 #pragma unroll
-                for (int j = 0; j < BMAX; ++j) {
-                    if (j < beta) {
-                        const double ev = AB && j == own ? own_v : u64_to_f(e[u][j]);
-                        a0 = d_add(a0, mulmod_var(ev, k0[j], q, qi));
-                        a1 = d_add(a1, mulmod_var(ev, k1[j], q, qi));
-                    }
-                }
-                if (has_lift) {
-                    // fused relinearise + rescale: add P * (d0, d1) so the sum can be divided by P q_last at once
-                    a0 = d_add(a0, mulmod_const(AB ? t0 : u64_to_f(l0[u]), pc, q));
-                    a1 = d_add(a1, mulmod_const(AB ? t1 : u64_to_f(l1[u]), pc, q));
-                }
+            for (int j = 0; j < BETA; ++j) {
+                const double ev = AB && j == own ? own_v : u64_to_f(e[u][j]);
+                a0 = d_add(a0, mulmod_var(ev, k0[j], q, qi));
+                a1 = d_add(a1, mulmod_var(ev, k1[j], q, qi));
+            }
+            if (LIFT) {
+                // fused relinearise + rescale: add P * (d0, d1) so the sum can be divided by P q_last at once
+                a0 = d_add(a0, mulmod_const(AB ? t0 : u64_to_f(l0[u]), pc, q));
+                a1 = d_add(a1, mulmod_const(AB ? t1 : u64_to_f(l1[u]), pc, q));
+            }
+            if (b < batch) {
                 u64* o0 = acc + (((size_t)b * ne + t) << log_n) + idx;
                 u64* o1 = acc + ((((size_t)batch + b) * ne + t) << log_n) + idx;
                 if (accum) { a0 = d_add(a0, u64_to_f(*o0)); a1 = d_add(a1, u64_to_f(*o1)); }
@@ -791,11 +789,23 @@ __global__ void __launch_bounds__(256, (BMAX <= 4 ? 3 : 2)) k_ks_inner(DevTables
 #pragma unroll
         for (int u = 0; u < UNR; ++u) {
 #pragma unroll
-            for (int j = 0; j < BMAX; ++j) e[u][j] = en[u][j];
+            for (int j = 0; j < BETA; ++j) e[u][j] = en[u][j];
             l0[u] = l0n[u]; l1[u] = l1n[u];
             if (AB) { m0[u] = m0n[u]; m1[u] = m1n[u]; }
         }
     }
+}
+template <int BETA, int UNR, bool AB>
+__global__ void __launch_bounds__(256, (BETA <= 4 ? 3 : 2)) k_ks_inner(DevTables T, int nq, int alpha, int batch,
+                                                  u64* acc, const u64* ext, const u64* d, const u64* ksk,
+                                                  const u64* lift, const ConstF* lift_c, int d_nq, int lift_nq,
+                                                  int lift_polys, int accum) {
+    // d_nq / lift_nq: limbs per batch element of `d` / `lift` (>= nq; only the AB operands may carry more)
+    // lift_polys: 2, or 1 when only polynomial 0 is lifted (a rotation: (sigma c0, 0));  accum: acc += instead of acc =
+    if (lift != nullptr && (int)blockIdx.y < nq)
+        ks_inner_body<BETA, UNR, AB, true>(T, nq, alpha, batch, acc, ext, d, ksk, lift, lift_c, d_nq, lift_nq, lift_polys, accum);
+    else
+        ks_inner_body<BETA, UNR, AB, false>(T, nq, alpha, batch, acc, ext, d, ksk, lift, lift_c, d_nq, lift_nq, lift_polys, accum);
 }
 
 // ---------------------------------------------------------------- fused NTT functors
