@@ -280,7 +280,7 @@ def workload_config(args, world):
     G = states_per_rank(args, world)
     return {"workload": "configs[4]: full AES-128 (AddRoundKey_0 + 10 rounds, encrypted FIPS-197 round keys), bit-sliced, "
                         "N=2^16, 24 levels, one bit bootstrap per round",
-            "states_per_gpu": G, "blocks_per_state": (1 << (LOG_N - 1)) // 4, "ciphertexts_per_state": 32,
+            "states_per_gpu": G, "states_per_call": min(G, args.states_per_call), "blocks_per_state": (1 << (LOG_N - 1)) // 4, "ciphertexts_per_state": 32,
             "limbs_q_p_alpha_dnum": [P.n_q, P.n_p, P.alpha, P.dnum], "log2_pq": round(P.log_pq, 1), "scale_bits": 44,
             "l2": "working set per step (tens of GB of ciphertexts and keys) exceeds the 126 MB L2",
             "sharding": "independent states per rank, no data-path collective; keys broadcast once from rank 0, "
@@ -306,6 +306,9 @@ def main():
     ap.add_argument("--states", type=int, default=2, help="states (8192 blocks each) per GPU per step")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
     ap.add_argument("--total-states", type=int, default=8, help="strong scaling: states in the whole job")
+    ap.add_argument("--states-per-call", type=int, default=2,
+                    help="a rank's states go through the pipeline in calls of at most this many (HBM: ~50 GB of "
+                         "temporaries per two states); the step is the sum of the calls")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the configs[1] SubBytes extra and the kernel rooflines")
     args = ap.parse_args()
@@ -359,23 +362,32 @@ def main():
     rks = expand_key(key)
     blocks = rank_blocks(rank, G * Bs)
     fresh = 1 + svc.boot_in_levels
-    st = svc.encrypt_state(blocks, level=fresh)
-    rkeys = [svc.encrypt_round_key(rks[r], G, level=12) for r in range(11)]
-    pinned = torch.from_numpy(blocks).pin_memory()
+    # a rank's G states go through the pipeline in calls of at most --states-per-call states
+    calls = [(lo, min(G, lo + args.states_per_call)) for lo in range(0, G, args.states_per_call)]
+    sts = [svc.encrypt_state(blocks[lo * Bs:hi * Bs], level=fresh) for lo, hi in calls]
+    rkeys = {n: [svc.encrypt_round_key(rks[r], n, level=12) for r in range(11)] for n in {hi - lo for lo, hi in calls}}
+    pinned = [torch.from_numpy(blocks[lo * Bs:hi * Bs]).pin_memory() for lo, hi in calls]
 
     def step():
-        return svc.encrypt_blocks(st, key, round_keys=rkeys)
+        return [svc.encrypt_blocks(st, key, round_keys=rkeys[hi - lo]) for st, (lo, hi) in zip(sts, calls)]
 
-    def collect(out):
+    def collect(outs):
         """result ciphertexts on the key owner -> decoded block bytes per rank (None on other ranks)"""
-        parts = gather_ciphertexts(engine, out, dst=0) if world > 1 else [out]
+        per_call = []
+        for out in outs:
+            parts = gather_ciphertexts(engine, out, dst=0) if world > 1 else [out]
+            if not rank:
+                per_call.append([svc.decrypt_state_device(p).numpy() for p in parts])
         if rank:
             return None
-        return [svc.decrypt_state_device(p).numpy() for p in parts]
+        return [np.concatenate([c[r] for c in per_call]) for r in range(world)]
 
     def e2e_step():
-        ct = svc.encrypt_state_device(pinned, level=fresh)            # H2D of the raw block bytes inside
-        return collect(svc.encrypt_blocks(ct, key, round_keys=rkeys))  # gather + decrypt + D2H of the bytes inside
+        outs = []
+        for pin, (lo, hi) in zip(pinned, calls):
+            ct = svc.encrypt_state_device(pin, level=fresh)                       # H2D of the raw block bytes inside
+            outs.append(svc.encrypt_blocks(ct, key, round_keys=rkeys[hi - lo]))
+        return collect(outs)                                                      # gather + decrypt + D2H of the bytes inside
 
     def sync_all():
         torch.cuda.synchronize()
@@ -471,7 +483,7 @@ def main():
         else:
             line["roofline"] = None
         print_line = line
-    del st, out
+    del sts, out
     if rank == 0 and world == 1 and not args.no_extras:
         del rkeys, svc
         torch.cuda.empty_cache()
