@@ -139,7 +139,9 @@ class CudaBackend:
         return self._empty(*shape)
 
     def slice_batch(self, h, lo: int, hi: int):
-        return h[:, lo:hi]
+        """batch elements lo..hi-1 as a tensor of their own: ONE copy here instead of one inside every kernel call that
+        would otherwise receive the strided view (a slice of the LUT bases is used by up to nine calls)"""
+        return h[:, lo:hi].contiguous()
 
     def permute_batch(self, h, idx: Sequence[int]):
         """batch elements re-ordered / replicated: out[:, i] = h[:, idx[i]] (one device copy)"""
