@@ -128,6 +128,11 @@ class PlainBits:
         return xt * u
 
 
+def len_groups(boot_key) -> int:
+    """CoeffToSlot factors of a bootstrap key"""
+    return int(getattr(boot_key, "_groups", 3))
+
+
 # --------------------------------------------------------------------------- ciphertext service
 class AESBitService:
     SBOX_LEVELS = 4             # monomials (2) + constant inner sums and outer products (2)
@@ -384,6 +389,43 @@ class AESBitService:
 
     def round_levels(self, last: bool) -> int:
         return self.SBOX_LEVELS + (self.ARK_LEVELS if last else self.MIX_LEVELS)
+
+    def plan_levels(self, fresh_level: int, rounds: int = 10) -> Dict[str, object]:
+        """Walk the level schedule of encrypt_blocks for an input encrypted at `fresh_level`: which rounds start with
+        a refresh and at which level each round key is multiplied in (so the client can encrypt key r at exactly
+        that level).  A refresh leaves max_level - depth_bits levels; a round needs 7 (the last: 5) and, unless it
+        is the final one, must leave boot_in_levels for the next refresh."""
+        from ..bootstrap import DOUBLE_ANGLES_BITS, POLY_DEGREE_BITS, _ps_depth
+        after_boot = self.engine.max_level - (len_groups(self.boot_key) + _ps_depth(POLY_DEGREE_BITS) + DOUBLE_ANGLES_BITS)
+        lvl = fresh_level
+        key_levels, boots = [lvl], []
+        lvl -= self.ARK_LEVELS
+        for r in range(1, rounds + 1):
+            last = (r == 10)
+            need = self.round_levels(last) + (0 if r == rounds else self.boot_in_levels)
+            if lvl < need:
+                if lvl < self.boot_in_levels:
+                    raise RuntimeError(f"round {r}: {lvl} levels left, the bit bootstrap needs {self.boot_in_levels}")
+                boots.append(r)
+                lvl = after_boot
+                if lvl < need:
+                    raise RuntimeError(f"refresh leaves {lvl} levels, a round needs {need}: raise max_level")
+            lvl -= self.SBOX_LEVELS
+            key_levels.append(lvl)
+            lvl -= self.ARK_LEVELS if last else self.MIX_LEVELS
+        return {"key_levels": key_levels, "refresh_before_rounds": boots, "out_level": lvl}
+
+    def best_fresh_level(self, rounds: int = 10) -> int:
+        """the lowest input level with the fewest refreshes (a higher level only makes the first rounds dearer)"""
+        best = None
+        for f in range(1 + self.boot_in_levels, self.engine.max_level + 1):
+            try:
+                n = len(self.plan_levels(f, rounds)["refresh_before_rounds"])
+            except RuntimeError:
+                continue
+            if best is None or n < best[0]:
+                best = (n, f)
+        return best[1]
 
     def encrypt_blocks(self, state: Ciphertext, key16, rounds: int = 10, round_keys: Optional[Sequence[Ciphertext]] = None):
         """AES-128 (or its first `rounds` rounds) on an encrypted state; the round keys come from the clear

@@ -309,6 +309,8 @@ def main():
     ap.add_argument("--states-per-call", type=int, default=2,
                     help="a rank's states go through the pipeline in calls of at most this many (HBM: ~50 GB of "
                          "temporaries per two states); the step is the sum of the calls")
+    ap.add_argument("--fresh-level", type=int, default=None,
+                    help="level the input state is encrypted at (default: the lowest level with the fewest refreshes)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the configs[1] SubBytes extra and the kernel rooflines")
     args = ap.parse_args()
@@ -361,11 +363,17 @@ def main():
     key = bytes.fromhex(KEY_HEX)
     rks = expand_key(key)
     blocks = rank_blocks(rank, G * Bs)
-    fresh = 1 + svc.boot_in_levels
+    # the input is encrypted at the lowest level that gives the fewest refreshes (19 of 24: two rounds run on the fresh
+    # levels, eight bit bootstraps instead of ten), each round key at exactly the level where it is multiplied in
+    fresh = args.fresh_level if args.fresh_level is not None else svc.best_fresh_level()
+    plan = svc.plan_levels(fresh)
+    config["fresh_level"] = fresh
+    config["refresh_before_rounds"] = plan["refresh_before_rounds"]
     # a rank's G states go through the pipeline in calls of at most --states-per-call states
     calls = [(lo, min(G, lo + args.states_per_call)) for lo in range(0, G, args.states_per_call)]
     sts = [svc.encrypt_state(blocks[lo * Bs:hi * Bs], level=fresh) for lo, hi in calls]
-    rkeys = {n: [svc.encrypt_round_key(rks[r], n, level=12) for r in range(11)] for n in {hi - lo for lo, hi in calls}}
+    rkeys = {n: [svc.encrypt_round_key(rks[r], n, level=plan["key_levels"][r]) for r in range(11)]
+             for n in {hi - lo for lo, hi in calls}}
     pinned = [torch.from_numpy(blocks[lo * Bs:hi * Bs]).pin_memory() for lo, hi in calls]
 
     def step():

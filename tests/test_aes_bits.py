@@ -196,3 +196,23 @@ def test_ecb_ten_rounds_on_oracle(ref_backend_cls):
     want = A.encrypt_blocks(np.frombuffer(pkcs7_pad(msg), np.uint8).reshape(-1, 16), key).tobytes()
     assert ct == want
     assert w.engine.op_counts["bootstrap"] == 10
+
+
+def test_level_plan_picks_the_input_level_with_the_fewest_refreshes():
+    """host logic of AESBitService.plan_levels / best_fresh_level on the 24-level chain: a refresh leaves 11 levels,
+    a round takes 7 (the last 5) and must leave 4 for the next refresh"""
+    class _Eng:
+        max_level = 24
+
+    class _Key:
+        _groups = 3
+    svc = AB.AESBitService.__new__(AB.AESBitService)
+    svc.engine, svc.boot_key, svc.boot_in_levels = _Eng(), _Key(), 4
+    low = svc.plan_levels(5)
+    assert low["refresh_before_rounds"] == list(range(1, 11)) and low["key_levels"] == [5] + [7] * 10 and low["out_level"] == 6
+    best = svc.plan_levels(19)
+    assert best["refresh_before_rounds"] == [3, 4, 5, 6, 7, 8, 9, 10] and best["key_levels"][:3] == [19, 14, 7]
+    assert svc.plan_levels(24)["refresh_before_rounds"] == best["refresh_before_rounds"]       # more levels buy nothing
+    assert svc.best_fresh_level() == 19
+    with pytest.raises(RuntimeError):
+        svc.plan_levels(3)

@@ -133,10 +133,20 @@ def test_aes128_ten_rounds_full_size(cuda_lib):
     assert got[0].tobytes().hex() == "3925841d02dc09fbdc118597196a0b32"
     assert bad == 0 and err < 1e-3
     assert w.engine.op_counts["bootstrap"] == 10 and svc.refreshes == 160
-    # FIPS-197 Appendix C.1 (key 000102...0f) through the same service
+    # FIPS-197 Appendix C.1 (key 000102...0f) through the same service, the input encrypted at the level that needs the
+    # fewest refreshes (19: two rounds on the fresh levels, eight bit bootstraps) and every round key at its own level
     key_c = bytes(range(16))
-    out_c = svc.encrypt_blocks(svc.encrypt_state(blocks[:4], level=1 + svc.boot_in_levels), key_c)
-    assert svc.decrypt_state(out_c, 4)[1].tobytes().hex() == "69c4e0d86a7b0430d8cdb78070b4c55a"
+    fresh = svc.best_fresh_level()
+    plan = svc.plan_levels(fresh)
+    assert fresh == 19 and plan["refresh_before_rounds"] == [3, 4, 5, 6, 7, 8, 9, 10]
+    rks_c = expand_key(key_c)
+    rk_cts = [svc.encrypt_round_key(rks_c[r], level=plan["key_levels"][r]) for r in range(11)]
+    n0 = w.engine.op_counts["bootstrap"]
+    out_c = svc.encrypt_blocks(svc.encrypt_state(blocks, level=fresh), key_c, round_keys=rk_cts)
+    got_c = svc.decrypt_state(out_c)
+    assert w.engine.op_counts["bootstrap"] - n0 == 8 and out_c.level == plan["out_level"]
+    assert got_c[1].tobytes().hex() == "69c4e0d86a7b0430d8cdb78070b4c55a"
+    assert np.array_equal(got_c, A.encrypt_blocks(blocks, key_c))
     # the refresh on a state that has been through a round (error ~1e-3): slots back within 1e-3 of +-1
     rks = expand_key(key)
     s1 = svc.encrypt_state(blocks, level=12)

@@ -76,9 +76,10 @@ def main():
     blocks = rng.integers(0, 256, (G * svc.Bs, 16), dtype=np.uint8)
     blocks[0] = np.frombuffer(bytes.fromhex("3243f6a8885a308d313198a2e0370734"), np.uint8)
     rks = expand_key(key)
-    fresh = args.fresh_level if args.fresh_level is not None else 1 + svc.boot_in_levels
+    fresh = args.fresh_level if args.fresh_level is not None else svc.best_fresh_level(args.rounds)
+    plan = svc.plan_levels(fresh, args.rounds)
     st = svc.encrypt_state(blocks, level=fresh)
-    rkeys = [svc.encrypt_round_key(rks[r], G, level=min(P.max_level, max(12, fresh))) for r in range(args.rounds + 1)]
+    rkeys = [svc.encrypt_round_key(rks[r], G, level=plan["key_levels"][r]) for r in range(args.rounds + 1)]
     out = svc.encrypt_blocks(st, key, rounds=args.rounds, round_keys=rkeys)            # warm-up: keys, matrices, tables
     torch.cuda.synchronize()
     setup = time.time() - t0
@@ -109,7 +110,8 @@ def main():
                       "limbs": [P.n_q, P.n_p, P.dnum], "ms": ms, "blocks_per_s": G * svc.Bs / (ms * 1e-3), "stages_ms": stages,
                       "bytes_equal_plain_aes": bool(np.array_equal(got, s)), "max_slot_err": err,
                       "bootstrapped_ciphertexts": svc.refreshes - r0, "op_counts": cnt,
-                      "launches": w.engine.backend.launch_count() - l0, "out_level": out.level, "setup_s": setup,
+                      "launches": w.engine.backend.launch_count() - l0, "out_level": out.level, "fresh_level": fresh,
+                      "refresh_before_rounds": plan["refresh_before_rounds"], "setup_s": setup,
                       "mem_gb_peak_first_run": peak_all, "mem_gb_resident_after_warmup": resident,
                       "mem_gb_peak_by_stage": peaks}))
 

@@ -60,8 +60,10 @@ def main():
         G = args.batch
         key = bytes.fromhex(bench.KEY_HEX)
         rks = expand_key(key)
-        st = aes.encrypt_state(bench.rank_blocks(0, G * aes.Bs), level=1 + aes.boot_in_levels)
-        rkeys = [aes.encrypt_round_key(rks[r], G, level=12) for r in range(11)]
+        fresh = aes.best_fresh_level()
+        plan = aes.plan_levels(fresh)
+        st = aes.encrypt_state(bench.rank_blocks(0, G * aes.Bs), level=fresh)
+        rkeys = [aes.encrypt_round_key(rks[r], G, level=plan["key_levels"][r]) for r in range(11)]
 
         def step():
             return aes.encrypt_blocks(st, key, round_keys=rkeys)
