@@ -267,10 +267,12 @@ class Engine:
         else:
             # a bootstrappable engine works at the largest scale the < 2^45 moduli allow (every operation is
             # 16x more precise) and has a sparse secret, so its chain is sized against the sparse-secret bound:
-            # 24 levels = bit bootstrap (13) + one AES round (7) + the entry of the next bootstrap (4),
-            # log2(P Q) = 1551 with three key-switch digits.  Other engines: 30 levels, uniform ternary secret.
+            # 26 levels: a bit bootstrap (13) leaves 13 = one AES round (7) + the entry of the next bootstrap (4)
+            # + 2 to spare, which lets three rounds run on a fresh input and the last round ride on the ninth's
+            # refresh (six refreshes per AES-128; 24 levels: eight); log2(P Q) = 1504 with four key-switch digits of
+            # seven.  Other engines: 30 levels, uniform ternary secret.
             sb = scale_bits if scale_bits is not None else (44 if use_bootstrap else 40)
-            lvl = int(max_level) if max_level is not None else (24 if use_bootstrap else 30)
+            lvl = int(max_level) if max_level is not None else (26 if use_bootstrap else 30)
             params = make_params(16, lvl, scale_bits=sb,
                                  log_pq_budget=LOG_PQ_BUDGET_SPARSE if use_bootstrap else LOG_PQ_BUDGET_DENSE)
         self.params = params

@@ -9,8 +9,8 @@ ten rounds (SubBytes, ShiftRows, MixColumns, AddRoundKey; the functions of the r
 /root/reference/test_all_process.py:21-48 and /root/reference/new.py:186-227,248-261), round keys from the clear
 FIPS-197 key schedule encrypted bit by bit -- at N = 2^16 on G *states* per GPU.  One state = 8192 AES blocks in 32
 bit-plane ciphertexts (aes_fhe_b200/services/aes_bits.py); every round ends in one bit bootstrap of the state
-(aes_fhe_b200/bootstrap.py::bootstrap_bits).  Parameter set: the default bootstrappable engine, 24 levels at a
-44-bit scale, 25 + 9 limbs, log2(PQ) = 1506 (inside the 1553-bit bound for the sparse secret, params.py).
+(aes_fhe_b200/bootstrap.py::bootstrap_bits).  Parameter set: the default bootstrappable engine, 26 levels at a
+44-bit scale, 27 + 7 limbs, log2(PQ) = 1504 (inside the 1553-bit bound for the sparse secret, params.py).
 
 A "step" is one AES-128 pass over the G states of a rank.  `value` = AES blocks per second with the input
 ciphertexts and the encrypted round keys resident in HBM (CUDA events, max over ranks); `e2e` = the same from host
@@ -49,7 +49,7 @@ sys.path.insert(0, str(ROOT))
 METRIC = "homomorphic AES-128 blocks/sec"
 UNIT = "blocks/s"
 LOG_N = 16
-AES_LEVEL = 24
+AES_LEVEL = 26
 KEY_HEX = "2b7e151628aed2a6abf7158809cf4f3c"         # FIPS-197 Appendix B
 PT_HEX = "3243f6a8885a308d313198a2e0370734"
 CT_HEX = "3925841d02dc09fbdc118597196a0b32"
@@ -152,10 +152,10 @@ class StageTimer:
 # --------------------------------------------------------------------------- CPU arm
 class CpuSample:
     """The bounded CPU sample: on ONE ciphertext at N = 2^16, same parameter set, oracle backend with all host
-    cores -- two relinearised products and two rotations each at levels 24, 16 and 8.  `run()` returns
+    cores -- two relinearised products and two rotations each at levels 26, 17 and 8.  `run()` returns
     (seconds, transform rows)."""
 
-    LEVELS = (24, 16, 8)
+    LEVELS = (26, 17, 8)
 
     def __init__(self, threads: int):
         from oracle.refmod import RefBackend, build
@@ -206,8 +206,8 @@ def cpu_baseline(samples: int, rows_per_state: int, blocks_per_state: int):
     s_per_row = float(np.median(times)) / rows
     t_state = s_per_row * rows_per_state
     return {"value": blocks_per_state / t_state, "unit": UNIT, "cores": cs.threads, "kind": "port", "extrapolated": True,
-            "sample": f"{samples} x [2 relinearised products + 2 rotations at each of levels 24/16/8, one ciphertext, N=2^16, "
-                      f"25+9 limbs] = {rows} transform rows in {float(np.median(times)):.2f}s (median) on {cs.threads} threads "
+            "sample": f"{samples} x [2 relinearised products + 2 rotations at each of levels 26/17/8, one ciphertext, N=2^16, "
+                      f"27+7 limbs] = {rows} transform rows in {float(np.median(times)):.2f}s (median) on {cs.threads} threads "
                       f"(oracle/refmod.cpp) -> {s_per_row * 1e6:.1f} us per row; one AES-128 state (8192 blocks) = "
                       f"{rows_per_state} rows -> {t_state:.0f}s extrapolated",
             "seconds_per_transform_row": s_per_row, "rows_per_state_aes128": rows_per_state}, times
@@ -231,7 +231,7 @@ def reference_arm(args):
     s_per_row = float(np.mean(times)) / rows
     v = bps / (s_per_row * rows_state)
     cb = {"value": v, "unit": UNIT, "cores": cs.threads, "kind": "port", "extrapolated": True,
-          "sample": f"each step = 2 relinearised products + 2 rotations at each of levels 24/16/8 on one ciphertext at N=2^16 "
+          "sample": f"each step = 2 relinearised products + 2 rotations at each of levels 26/17/8 on one ciphertext at N=2^16 "
                     f"({rows} transform rows, {ms_step:.0f} ms mean on {cs.threads} threads, oracle/refmod.cpp); value = 8192 blocks / "
                     f"({rows_state} rows of one AES-128 state x {s_per_row * 1e6:.1f} us per row)",
           "seconds_per_transform_row": s_per_row, "rows_per_state_aes128": rows_state}
@@ -279,7 +279,7 @@ def workload_config(args, world):
     P = aes_params()
     G = states_per_rank(args, world)
     return {"workload": "configs[4]: full AES-128 (AddRoundKey_0 + 10 rounds, encrypted FIPS-197 round keys), bit-sliced, "
-                        "N=2^16, 24 levels, one bit bootstrap per round",
+                        "N=2^16, 26 levels, a bit bootstrap of the state wherever the levels run out (six per AES-128)",
             "states_per_gpu": G, "states_per_call": min(G, args.states_per_call), "blocks_per_state": (1 << (LOG_N - 1)) // 4, "ciphertexts_per_state": 32,
             "limbs_q_p_alpha_dnum": [P.n_q, P.n_p, P.alpha, P.dnum], "log2_pq": round(P.log_pq, 1), "scale_bits": 44,
             "l2": "working set per step (tens of GB of ciphertexts and keys) exceeds the 126 MB L2",
@@ -363,8 +363,8 @@ def main():
     key = bytes.fromhex(KEY_HEX)
     rks = expand_key(key)
     blocks = rank_blocks(rank, G * Bs)
-    # the input is encrypted at the lowest level that gives the fewest refreshes (19 of 24: two rounds run on the fresh
-    # levels, eight bit bootstraps instead of ten), each round key at exactly the level where it is multiplied in
+    # the input is encrypted at the lowest level that gives the fewest refreshes (26 of 26: three rounds run on the fresh
+    # levels, six bit bootstraps instead of ten), each round key at exactly the level where it is multiplied in
     fresh = args.fresh_level if args.fresh_level is not None else svc.best_fresh_level()
     plan = svc.plan_levels(fresh)
     config["fresh_level"] = fresh
@@ -477,7 +477,7 @@ def main():
                         "round_keys": "encrypted once, resident (the client's key does not change per step)"},
                 "ms_per_round": ms / 10, "ms_per_state": ms / G,
                 "stage_ms": {**stages, "note": "device time of one pass on rank 0, CUDA events at stage boundaries; refresh = "
-                                               "bit bootstrap of the whole state once per round"},
+                                               "bit bootstraps of the whole state (config.refresh_before_rounds)"},
                 "bytes_equal_plain_aes": bool(ok_resident), "fips197_appendix_b": True,
                 "bootstrapped_ciphertexts_per_step": int(boots), "bootstrapped_ciphertexts_per_2048_blocks": boots / G / 4,
                 "batched_op_calls_per_step": counts, "ntt_rows_per_state": int(rows_step // G),

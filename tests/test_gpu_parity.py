@@ -46,17 +46,17 @@ def test_keyswitch_full_parameters(ref_backend_cls, cuda_lib):
 
 def _benchmarked_sets():
     """the parameter sets bench.py times at N = 2^16: SubBytes (configs[1]: 23 + 11 limbs, two digits of 12 ->
-    k_bconv<12>, k_ks_inner<2,...>) and bit-sliced AES-128 (configs[4]: 25 + 9 limbs, three digits of 9, 44-bit scale,
+    k_bconv<12>, k_ks_inner<2,...>) and bit-sliced AES-128 (configs[4]: 27 + 7 limbs, four digits of 7, 44-bit scale,
     sized against the sparse-secret bound)"""
     from aes_fhe_b200.params import LOG_PQ_BUDGET_SPARSE
     return {"subbytes": make_params(16, 22),
-            "aes128": make_params(16, 24, scale_bits=44, log_pq_budget=LOG_PQ_BUDGET_SPARSE)}
+            "aes128": make_params(16, 26, scale_bits=44, log_pq_budget=LOG_PQ_BUDGET_SPARSE)}
 
 
 @pytest.mark.parametrize("name", ["subbytes", "aes128"])
 def test_primitives_at_benchmarked_parameters(name, ref_backend_cls, cuda_lib):
     P = _benchmarked_sets()[name]
-    assert (P.n_q, P.n_p, P.alpha, P.dnum) == {"subbytes": (23, 11, 12, 2), "aes128": (25, 9, 9, 3)}[name]
+    assert (P.n_q, P.n_p, P.alpha, P.dnum) == {"subbytes": (23, 11, 12, 2), "aes128": (27, 7, 7, 4)}[name]
     kp.check_primitives(P, _gpu(P), ref_backend_cls(P))
     kp.check_rescale(P, _gpu(P), ref_backend_cls(P))
 

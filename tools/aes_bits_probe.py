@@ -50,7 +50,7 @@ class StageTimer:
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--states", type=int, default=1)
-    ap.add_argument("--level", type=int, default=24)
+    ap.add_argument("--level", type=int, default=26)
     ap.add_argument("--scale-bits", type=int, default=44)
     ap.add_argument("--groups", default="3,3")
     ap.add_argument("--rounds", type=int, default=10)
