@@ -311,32 +311,46 @@ class AESBitService:
         self._tick("shift_rows")
         return out
 
-    def _monomial_basis(self, bits: List[Ciphertext]) -> Dict[int, Ciphertext]:
+    def _monomial_basis(self, bits: List[Ciphertext]):
         """{A: prod_{j in A} bits[j]} for the 15 non-empty subsets A of four +-1 ciphertexts (any batch): the 6 pair
         products in one batched multiply, then the 4 triples (pair x single) and the quadruple (pair x pair) in
-        another -- 11 key switches per batch element, depth 2."""
+        another -- 11 key switches per batch element, depth 2.  In a triple the single is one level above the pair: it
+        is used in place (upper limb ignored, an exact modulus switch) and the product's scale leaves the table by
+        delta[l] / delta[l-1]; returns (monomials, scale factors) for the LUT constants to absorb."""
+        from fractions import Fraction
         e, rlk = self.engine, self.eng.relin_key
+        P = e.params
         bt = bits[0].batch
         pairs = [(0, 1), (0, 2), (0, 3), (1, 2), (1, 3), (2, 3)]
         pp = e.multiply(self._cat([bits[i] for i, _ in pairs]), self._cat([bits[j] for _, j in pairs]), rlk)
         mono = {1 << j: bits[j] for j in range(4)}
+        dev = {m: Fraction(1) for m in range(1, 16)}
         for n, (i, j) in enumerate(pairs):
             mono[(1 << i) | (1 << j)] = self._slice(pp, n * bt, (n + 1) * bt)
-        low = [e.level_down(b, pp.level) for b in bits]
-        second = [(0b0111, mono[0b0011], low[2]), (0b1011, mono[0b0011], low[3]), (0b1101, mono[0b1100], low[0]),
-                  (0b1110, mono[0b1100], low[1]), (0b1111, mono[0b0011], mono[0b1100])]
-        qq = e.multiply(self._cat([a for _, a, _ in second]), self._cat([b for _, _, b in second]), rlk)
-        for n, (m, _, _) in enumerate(second):
-            mono[m] = self._slice(qq, n * bt, (n + 1) * bt)
-        return mono
+        triples = [(0b0111, mono[0b0011], bits[2]), (0b1011, mono[0b0011], bits[3]), (0b1101, mono[0b1100], bits[0]),
+                   (0b1110, mono[0b1100], bits[1])]
+        if hasattr(e, "_mul_ct_dropped") and all(b.level == pp.level + 1 for b in bits):
+            tt, d = e._mul_ct_dropped(self._cat([a for _, a, _ in triples]), self._cat([b for _, _, b in triples]), rlk)
+            qd = e.multiply(mono[0b0011], mono[0b1100], rlk)
+            for n, (m, _, _) in enumerate(triples):
+                mono[m] = self._slice(tt, n * bt, (n + 1) * bt)
+                dev[m] = d
+            mono[0b1111] = qd
+        else:
+            low = [e.level_down(b, pp.level) for b in bits]
+            second = [(m, a, low[[2, 3, 0, 1][n]]) for n, (m, a, _) in enumerate(triples)] + [(0b1111, mono[0b0011], mono[0b1100])]
+            qq = e.multiply(self._cat([a for _, a, _ in second]), self._cat([b for _, _, b in second]), rlk)
+            for n, (m, _, _) in enumerate(second):
+                mono[m] = self._slice(qq, n * bt, (n + 1) * bt)
+        return mono, dev
 
     def sub_bytes(self, state: Ciphertext) -> Ciphertext:
         """the S-box on every byte of the state: eight multilinear polynomials over the monomials of the high and
         the low four bits (22 + 8 key switches per (row, state), four levels)"""
         G = self._G(state)
         bits = [self._slice(state, k * 4 * G, (k + 1) * 4 * G) for k in range(8)]
-        lo, hi = self._monomial_basis(bits[:4]), self._monomial_basis(bits[4:])
-        outs = _outer_sum(self.engine, self.eng.relin_key, hi, lo, [self.W[k] for k in range(8)], ("sbox-bits",))
+        (lo, dlo), (hi, dhi) = self._monomial_basis(bits[:4]), self._monomial_basis(bits[4:])
+        outs = _outer_sum(self.engine, self.eng.relin_key, hi, lo, [self.W[k] for k in range(8)], ("sbox-bits",), dhi, dlo)
         out = self._cat(outs)
         self._tick("sub_bytes")
         return out
