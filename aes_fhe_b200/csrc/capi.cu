@@ -280,8 +280,14 @@ void build_level_tables(fhe_ctx* c) {
 template <int NS>
 void launch_bconv_ns(fhe_ctx* c, cudaStream_t s, int groups, const BConvTable* tabs, int n_tabs, u64* dst,
                      long long dst_stride, const u64* src, long long src_stride, int g_first, int g_step) {
-    launch(k_bconv<NS>, dim3(c->n / 512, groups), dim3(256), s, c->T, tabs, n_tabs, dst, dst_stride, src, src_stride, g_first,
-           g_step);
+    // variant 1: the three-FMA exact dot product (k_bconv_dot3); env FHE_BCONV_VARIANT, default from the measurement in DESIGN.md
+    static const int variant = getenv("FHE_BCONV_VARIANT") ? atoi(getenv("FHE_BCONV_VARIANT")) : 0;
+    if (variant == 1)
+        launch(k_bconv_dot3<NS>, dim3(c->n / 256, groups), dim3(256), s, c->T, tabs, n_tabs, dst, dst_stride, src, src_stride,
+               g_first, g_step);
+    else
+        launch(k_bconv<NS>, dim3(c->n / 512, groups), dim3(256), s, c->T, tabs, n_tabs, dst, dst_stride, src, src_stride, g_first,
+               g_step);
 }
 // one launch over groups g = y * g_step + g_first (y < groups) whose tables all have exactly `ns` sources
 void launch_bconv_exact(fhe_ctx* c, cudaStream_t s, int ns, int groups, const BConvTable* tabs, int n_tabs, u64* dst,

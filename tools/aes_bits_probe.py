@@ -56,6 +56,9 @@ def main():
     ap.add_argument("--rounds", type=int, default=10)
     ap.add_argument("--fresh-level", type=int, default=None)
     ap.add_argument("--dnum", type=int, default=0)
+    ap.add_argument("--nvtx", action="store_true",
+                    help="NVTX ranges between the stage / bootstrap-phase boundaries (range 'after_<boundary>'), for "
+                         "ncu --nvtx --nvtx-include; e.g. after_boot_mod_raise = CoeffToSlot, after_boot_conjugate_split = EvalMod")
     args = ap.parse_args()
     import torch
     from aes_fhe_b200.params import make_params
@@ -90,10 +93,24 @@ def main():
     torch.cuda.reset_peak_memory_stats()
     svc.timer = StageTimer()
     w.engine.phase_timer = svc.timer
+    if args.nvtx:
+        import torch.cuda.nvtx as nvtx
+        timer, opened = svc.timer, [False]
+
+        def hook(name):
+            timer(name)
+            if opened[0]:
+                nvtx.range_pop()
+            nvtx.range_push("after_" + name.replace(":", "_"))
+            opened[0] = True
+        svc.timer = w.engine.phase_timer = hook
+        hook.ms, hook.peaks = timer.ms, timer.peaks
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a.record()
     out = svc.encrypt_blocks(st, key, rounds=args.rounds, round_keys=rkeys)
     b.record()
+    if args.nvtx:
+        nvtx.range_pop()
     stages = svc.timer.ms()
     peaks = svc.timer.peaks
     svc.timer = None
