@@ -85,6 +85,18 @@ def main():
         assert gb.lib.fhe_ntt_fused_status(gb.ctx) == 0, "fused NTT barrier timed out"
         gb.lib.fhe_set_ntt_fused(gb.ctx, int(os.environ.get("FHE_NTT_FUSED", "0")))
 
+    # streaming kernels at the batch the AES-128 step runs them with (32 ciphertexts of 2 polynomials): the 2-polynomial
+    # cases below are launch-latency sized (12-22 us)
+    import ctypes as C
+    for nq in (() if only_ntt else (27, 14)):
+        B = 32
+        x = rnd(2, B, nq, n); y = rnd(2, B, nq, n); o = torch.empty_like(x)
+        m, mn = timeit(lambda: gb._call("fhe_add", gb._ptr(o), gb._ptr(x), gb._ptr(y), 2, B, 2, B, nq, 0), flush=flush)
+        rec("add_ct.batch32", m, mn, 6 * B * nq * limb, nq=nq)
+        m, mn = timeit(lambda: gb._call("fhe_mul", gb._ptr(o), gb._ptr(x), gb._ptr(y), 2, B, 1, 1, nq, 0), flush=flush)
+        rec("mul_plain_broadcast.batch32", m, mn, (4 * B + 1) * nq * limb, nq=nq)
+        m, mn = timeit(lambda: gb._call("fhe_automorphism", gb._ptr(o), gb._ptr(x), C.c_uint64(5), 2 * B * nq), flush=flush)
+        rec("automorphism.batch32", m, mn, 4 * B * nq * limb, nq=nq)
     for nq in (() if only_ntt else (31, 21, 11)):
         x = rnd(2, nq, n); y = rnd(2, nq, n); o = torch.empty_like(x)
         m, mn = timeit(lambda: gb._call("fhe_add", gb._ptr(o), gb._ptr(x), gb._ptr(y), 2, 1, 2, 1, nq, 0), flush=flush)
