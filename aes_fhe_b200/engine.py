@@ -493,21 +493,24 @@ class Engine:
 
     # ---- byte-level codec on the device (the reference's ZetaEncoder.to_zeta / from_zeta around
     #      encrypt / decrypt: xor_service.py:132-145, 318-328), so a step moves bytes, not complex128
-    def encrypt_zeta(self, values, public_key: PublicKey, modulus: int = 16, level: Optional[int] = None) -> Ciphertext:
-        """uint8 values [<= slot_count] or [B, <= slot_count] -> ciphertext(s) of zeta_m^x = exp(-2 pi i x / m);
-        one H2D copy of the bytes, everything else on the device.  Same result as
+    def encrypt_zeta(self, values, public_key: PublicKey, modulus: int = 16, level: Optional[int] = None,
+                     amplitude: float = 1.0) -> Ciphertext:
+        """uint8 values [<= slot_count] or [B, <= slot_count] -> ciphertext(s) of zeta_m^x = exp(-2 pi i x / m)
+        (times `amplitude`); one H2D copy of the bytes, everything else on the device.  Same result as
         ``encrypt(ZetaEncoder.to_zeta(values, modulus), pk)`` up to the encryption randomness."""
         import torch
         be = self.backend
         if not hasattr(be, "encode_device"):
             ang = -2.0 * np.pi * (np.asarray(values).astype(np.int64) % modulus) / modulus
-            return self.encrypt(np.exp(1j * ang), public_key, level)
+            return self.encrypt(amplitude * np.exp(1j * ang), public_key, level)
         x = values if isinstance(values, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(np.asarray(values, dtype=np.uint8)))
         x = x.reshape(1, -1) if x.ndim <= 1 else x
         x = x.to(be.device, non_blocking=True)
         n_in = x.shape[1]
         ang = (x.to(torch.float64) % modulus) * (-2.0 * np.pi / modulus)
         z = torch.complex(torch.cos(ang), torch.sin(ang))
+        if amplitude != 1.0:
+            z = z * float(amplitude)
         if n_in < self.slot_count:
             z = torch.nn.functional.pad(z, (0, self.slot_count - n_in))            # zero-padded, like encrypt()
         return self._encrypt_device(z, public_key, self.params.max_level if level is None else int(level))

@@ -138,6 +138,7 @@ class AESBitService:
     SBOX_LEVELS = 4             # monomials (2) + constant inner sums and outer products (2)
     MIX_LEVELS = 3
     ARK_LEVELS = 1
+    FINAL_LEVELS = 2            # last round: AddRoundKey with the half-amplitude key and the sign polish (final_round_key)
 
     def __init__(self, eng_wrap, boot_groups: Tuple[int, int] = (3, 3), boot_key=None):
         self.eng = eng_wrap
@@ -207,24 +208,33 @@ class AESBitService:
         out = by.transpose(1, 3, 2, 0).reshape(G * self.Bs, 16)                               # [g, b, c, r]
         return out if nb is None else out[:nb]
 
-    def _encrypt_planes(self, planes: np.ndarray, level: Optional[int]) -> Ciphertext:
-        """bit planes -> ciphertexts of (-1)^bit.  With the engine's device codec the bytes go to the GPU and
-        encoding, sampling and encryption happen there (Engine.encrypt_zeta, modulus 2); without it the host
+    def _encrypt_planes(self, planes: np.ndarray, level: Optional[int], amplitude: float = 1.0) -> Ciphertext:
+        """bit planes -> ciphertexts of amplitude * (-1)^bit.  With the engine's device codec the bytes go to the GPU
+        and encoding, sampling and encryption happen there (Engine.encrypt_zeta, modulus 2); without it the host
         path keeps the ciphertexts reproducible from the seed (parity tests against the oracle)."""
         if self.engine.device_codec:
-            return self.engine.encrypt_zeta(planes, self.eng.public_key, 2, level=level)
-        return self.engine.encrypt(1.0 - 2.0 * planes.astype(np.float64), self.eng.public_key, level=level)
+            return self.engine.encrypt_zeta(planes, self.eng.public_key, 2, level=level, amplitude=amplitude)
+        return self.engine.encrypt(amplitude * (1.0 - 2.0 * planes.astype(np.float64)), self.eng.public_key, level=level)
 
     def encrypt_state(self, blocks: np.ndarray, level: Optional[int] = None) -> Ciphertext:
         return self._encrypt_planes(self.pack_bits(blocks), level)
 
-    def encrypt_round_key(self, rk16, G: int = 1, level: Optional[int] = None) -> Ciphertext:
-        """one 16-byte round key replicated over every block slot and over the G states of a batch"""
+    def encrypt_round_key(self, rk16, G: int = 1, level: Optional[int] = None, half: bool = False) -> Ciphertext:
+        """one 16-byte round key replicated over every block slot and over the G states of a batch.  half: bit planes
+        of amplitude 1/2 -- the form the LAST round key takes so that final_round_key can polish the output."""
         rk = np.tile(np.asarray(rk16, dtype=np.uint8).reshape(1, 16), (self.Bs, 1))
-        ct = self._encrypt_planes(self.pack_bits(rk), level)
+        ct = self._encrypt_planes(self.pack_bits(rk), level, 0.5 if half else 1.0)
         if G > 1:
             ct = self._take(ct, [i for i in range(32) for _ in range(G)])
+        ct.amplitude = 0.5 if half else 1.0
         return ct
+
+    def encrypt_round_keys(self, key16, G: int = 1, plan: Optional[Dict[str, object]] = None, rounds: int = 10):
+        """the FIPS-197 key schedule of `key16`, every round key encrypted at the level the plan multiplies it in
+        (plan_levels) and the key of round 10 at half amplitude"""
+        rks = expand_key(bytes(key16))
+        lv = (lambda r: None) if plan is None else (lambda r: plan["key_levels"][r])
+        return [self.encrypt_round_key(rks[r], G, level=lv(r), half=(r == 10)) for r in range(rounds + 1)]
 
     # ---- throughput path: raw block bytes cross PCIe (16 B per block each way), bit planes are made on the GPU
     def _plane_index(self, G: int):
@@ -286,6 +296,25 @@ class AESBitService:
 
     def add_round_key(self, state: Ciphertext, key: Ciphertext) -> Ciphertext:
         out = self.engine.multiply(state, key, self.eng.relin_key)
+        self._tick("add_round_key")
+        return out
+
+    def final_round_key(self, o: Ciphertext, key: Ciphertext) -> Ciphertext:
+        """AddRoundKey of the last round.  With the round key at half amplitude (encrypt_round_key(half=True)) and two
+        levels left the output is polished on the way out: for o = s (1 + e), s = +-1 (the SubBytes output) and
+        k' = k / 2,   (o k') (3 - o^2) = s k (1 - 1.5 e^2 + ...):  the error the last round has accumulated since the
+        previous refresh comes out squared, for two products at the bottom of the chain.  A full-amplitude key (or a
+        single level left) gives the plain product."""
+        e, rlk = self.engine, self.eng.relin_key
+        if getattr(key, "amplitude", 1.0) != 0.5:
+            return self.add_round_key(o, key)
+        if o.level < 2:
+            raise RuntimeError("final_round_key: a half-amplitude key needs two levels (plan_levels provides them)")
+        key = e.level_down(key, o.level) if key.level > o.level else key
+        both = e.multiply(self._cat([o, o]), self._cat([key, o]), rlk)                # o k' | o^2
+        n = o.batch
+        z, sq = self._slice(both, 0, n), self._slice(both, n, 2 * n)
+        out = e.multiply(z, e.add_plain(e.negate(sq), 3.0), rlk)
         self._tick("add_round_key")
         return out
 
@@ -402,7 +431,7 @@ class AESBitService:
         return out
 
     def round_levels(self, last: bool) -> int:
-        return self.SBOX_LEVELS + (self.ARK_LEVELS if last else self.MIX_LEVELS)
+        return self.SBOX_LEVELS + (self.FINAL_LEVELS if last else self.MIX_LEVELS)
 
     def plan_levels(self, fresh_level: int, rounds: int = 10) -> Dict[str, object]:
         """Walk the level schedule of encrypt_blocks for an input encrypted at `fresh_level`: which rounds start with
@@ -426,7 +455,7 @@ class AESBitService:
                     raise RuntimeError(f"refresh leaves {lvl} levels, a round needs {need}: raise max_level")
             lvl -= self.SBOX_LEVELS
             key_levels.append(lvl)
-            lvl -= self.ARK_LEVELS if last else self.MIX_LEVELS
+            lvl -= self.FINAL_LEVELS if last else self.MIX_LEVELS
         return {"key_levels": key_levels, "refresh_before_rounds": boots, "out_level": lvl}
 
     def best_fresh_level(self, rounds: int = 10) -> int:
@@ -449,8 +478,7 @@ class AESBitService:
         the entry of the next bootstrap."""
         G = self._G(state)
         if round_keys is None:
-            rks = expand_key(bytes(key16))
-            round_keys = [self.encrypt_round_key(rks[r], G) for r in range(rounds + 1)]
+            round_keys = self.encrypt_round_keys(key16, G, rounds=rounds)
         st = self.add_round_key(state, round_keys[0])
         for r in range(1, rounds + 1):
             last = (r == 10)
@@ -463,7 +491,7 @@ class AESBitService:
                 if st.level < need:
                     raise RuntimeError(f"refresh leaves {st.level} levels, a round needs {need}: raise max_level")
             st = self.sub_bytes(st)
-            st = self.add_round_key(st, round_keys[r]) if last else self.mix_columns_ark(st, round_keys[r])
+            st = self.final_round_key(st, round_keys[r]) if last else self.mix_columns_ark(st, round_keys[r])
         return st
 
 

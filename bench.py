@@ -372,8 +372,7 @@ def main():
     # a rank's G states go through the pipeline in calls of at most --states-per-call states
     calls = [(lo, min(G, lo + args.states_per_call)) for lo in range(0, G, args.states_per_call)]
     sts = [svc.encrypt_state(blocks[lo * Bs:hi * Bs], level=fresh) for lo, hi in calls]
-    rkeys = {n: [svc.encrypt_round_key(rks[r], n, level=plan["key_levels"][r]) for r in range(11)]
-             for n in {hi - lo for lo, hi in calls}}
+    rkeys = {n: svc.encrypt_round_keys(key, n, plan) for n in {hi - lo for lo, hi in calls}}     # round 10 at half amplitude
     pinned = [torch.from_numpy(blocks[lo * Bs:hi * Bs]).pin_memory() for lo, hi in calls]
 
     def step():
@@ -416,6 +415,11 @@ def main():
     ok_resident = verify(collect(out))
     if not ok_resident:
         raise SystemExit("AES-128 output differs from plain AES / FIPS-197")
+    slot_err = None
+    if rank == 0:                             # north_star check 2: decoded slots against +-1 (rank 0's first call)
+        lo, hi = calls[0]
+        want = A.encrypt_blocks(blocks[lo * Bs:hi * Bs], key)
+        slot_err = float(np.abs(svc.decrypt_slots(out[0]) - (1.0 - 2.0 * svc.pack_bits(want))).max())
     setup_s = time.perf_counter() - t_setup
     for _ in range(max(0, args.warmup - 1)):
         step()
@@ -480,7 +484,7 @@ def main():
                                                "bit bootstraps of the whole state (config.refresh_before_rounds)"},
                 "bytes_equal_plain_aes": bool(ok_resident), "fips197_appendix_b": True,
                 "bootstrapped_ciphertexts_per_step": int(boots), "bootstrapped_ciphertexts_per_2048_blocks": boots / G / 4,
-                "batched_op_calls_per_step": counts, "ntt_rows_per_state": int(rows_step // G),
+                "max_slot_error": slot_err, "batched_op_calls_per_step": counts, "ntt_rows_per_state": int(rows_step // G),
                 "ntt_rows_per_state_golden": None if work is None else work["ntt_rows_per_state_aes128"],
                 "setup_seconds": setup_s, "security": engine.security,
                 "hbm_peak_allocated_gb": torch.cuda.max_memory_allocated() / 2 ** 30}

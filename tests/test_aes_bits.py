@@ -128,6 +128,29 @@ def test_bit_bootstrap_on_oracle(log_n, ref_backend_cls):
     assert err < 1e-3, err                      # input error 5e-3 rms (2e-2 max) came out squared: pi^2 e^2 / 8
 
 
+def test_final_round_key_squares_the_error(ref_backend_cls):
+    """Last AddRoundKey with the half-amplitude key: (o k / 2)(3 - o^2) = s k (1 - 1.5 e^2) for o = s (1 + e); a
+    full-amplitude key gives the plain product (error e kept)."""
+    P = make_params(10, 4, scale_bits=44)
+    w, svc = make_service(ref_backend_cls(P), P, boot_key=object())
+    eng = w.engine
+    rng = np.random.default_rng(13)
+    blocks = rng.integers(0, 256, (svc.Bs, 16), dtype=np.uint8)
+    rk = expand_key(KEY_B)[10]
+    s = 1.0 - 2.0 * svc.pack_bits(blocks)
+    e = rng.normal(0, 0.01, s.shape)
+    o = eng.encrypt(s * (1.0 + e), w.public_key, level=2)
+    want = 1.0 - 2.0 * svc.pack_bits(blocks ^ rk)
+    half = svc.final_round_key(o, svc.encrypt_round_key(rk, level=2, half=True))
+    assert half.level == 0
+    err_half = np.abs(svc.decrypt_slots(half) - want * (1.0 + e) * (3.0 - (1.0 + e) ** 2) / 2.0).max()     # = 1 - 1.5 e^2 - e^3 / 2
+    assert err_half < 1e-6, err_half
+    assert np.abs(svc.decrypt_slots(half) - want).max() < 1.6 * np.abs(e).max() ** 2 + 2e-5
+    full = svc.final_round_key(o, svc.encrypt_round_key(rk, level=2))
+    assert full.level == 1 and np.abs(svc.decrypt_slots(full) - want * (1.0 + e)).max() < 1e-5
+    assert svc.round_levels(True) == 6 and svc.round_levels(False) == 7
+
+
 def test_two_rounds_with_refresh_on_oracle(ref_backend_cls):
     P = make_params(11, 24, scale_bits=44)          # 13 (bit bootstrap) + 7 (round) + 4 (entry of the next bootstrap)
     w, svc = make_service(ref_backend_cls(P), P)
@@ -209,7 +232,7 @@ def test_level_plan_picks_the_input_level_with_the_fewest_refreshes():
     svc = AB.AESBitService.__new__(AB.AESBitService)
     svc.engine, svc.boot_key, svc.boot_in_levels = _Eng(), _Key(), 4
     low = svc.plan_levels(5)
-    assert low["refresh_before_rounds"] == list(range(1, 11)) and low["key_levels"] == [5] + [7] * 10 and low["out_level"] == 6
+    assert low["refresh_before_rounds"] == list(range(1, 11)) and low["key_levels"] == [5] + [7] * 10 and low["out_level"] == 5
     best = svc.plan_levels(19)
     assert best["refresh_before_rounds"] == [3, 4, 5, 6, 7, 8, 9, 10] and best["key_levels"][:3] == [19, 14, 7]
     assert svc.plan_levels(24)["refresh_before_rounds"] == best["refresh_before_rounds"]       # more levels buy nothing

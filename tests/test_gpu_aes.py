@@ -141,7 +141,7 @@ def test_aes128_ten_rounds_full_size(cuda_lib):
     plan = svc.plan_levels(fresh)
     assert fresh == 26 and plan["refresh_before_rounds"] == [4, 5, 6, 7, 8, 9]
     rks_c = expand_key(key_c)
-    rk_cts = [svc.encrypt_round_key(rks_c[r], level=plan["key_levels"][r]) for r in range(11)]
+    rk_cts = svc.encrypt_round_keys(key_c, 1, plan)
     n0 = w.engine.op_counts["bootstrap"]
     out_c = svc.encrypt_blocks(svc.encrypt_state(blocks, level=fresh), key_c, round_keys=rk_cts)
     got_c = svc.decrypt_state(out_c)

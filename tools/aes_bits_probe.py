@@ -82,7 +82,7 @@ def main():
     fresh = args.fresh_level if args.fresh_level is not None else svc.best_fresh_level(args.rounds)
     plan = svc.plan_levels(fresh, args.rounds)
     st = svc.encrypt_state(blocks, level=fresh)
-    rkeys = [svc.encrypt_round_key(rks[r], G, level=plan["key_levels"][r]) for r in range(args.rounds + 1)]
+    rkeys = svc.encrypt_round_keys(key, G, plan, rounds=args.rounds)
     out = svc.encrypt_blocks(st, key, rounds=args.rounds, round_keys=rkeys)            # warm-up: keys, matrices, tables
     torch.cuda.synchronize()
     setup = time.time() - t0

@@ -37,7 +37,7 @@ def measure(log_n: int = 11):
     rks = expand_key(key)
     blocks = np.random.default_rng(1).integers(0, 256, (svc.Bs, 16), dtype=np.uint8)
     st = svc.encrypt_state(blocks, level=1 + svc.boot_in_levels)
-    rkeys = [svc.encrypt_round_key(rks[r], level=12) for r in range(11)]
+    rkeys = [svc.encrypt_round_key(rks[r], level=12, half=(r == 10)) for r in range(11)]
     svc.prepare_keys()
     r0, c0 = be.ntt_row_count(), dict(w.engine.op_counts)
     out = svc.encrypt_blocks(st, key, round_keys=rkeys)

@@ -63,7 +63,7 @@ def main():
         fresh = aes.best_fresh_level()
         plan = aes.plan_levels(fresh)
         st = aes.encrypt_state(bench.rank_blocks(0, G * aes.Bs), level=fresh)
-        rkeys = [aes.encrypt_round_key(rks[r], G, level=plan["key_levels"][r]) for r in range(11)]
+        rkeys = aes.encrypt_round_keys(key, G, plan)
 
         def step():
             return aes.encrypt_blocks(st, key, round_keys=rkeys)
