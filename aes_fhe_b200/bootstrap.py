@@ -663,10 +663,12 @@ def _phase(engine, name: str):
         hook(name)
 
 
-def bootstrap_bits(engine, ct: Ciphertext, relin_key, conj_key, boot_key: BootstrapKey) -> Ciphertext:
+def bootstrap_bits(engine, ct: Ciphertext, relin_key, conj_key, boot_key: BootstrapKey,
+                   top_level: Optional[int] = None) -> Ciphertext:
     """Refresh of +-1-valued slots ("bit bootstrap").  ``ct`` [batch B] holds u + i v with u, v real and close to
     +-1 (two bit planes per ciphertext); the result [batch 2 B: all u, then all v] holds the cleaned values at
-    level  max_level - plan.depth_bits.
+    level  top_level - plan.depth_bits  (top_level = max_level unless the caller needs fewer levels afterwards: the
+    ModRaise then goes to top_level + 1 limbs only and every step of the refresh runs on fewer limbs).
 
     Order of operations (binary-message bootstrapping, Bae-Cheon-Kim-Stehle 2024, with this repo's pieces):
       0. SlotToCoeff FIRST, at the bottom of the chain (levels groups_stc + 1 -> 1, a few limbs: almost free); the
@@ -685,9 +687,11 @@ def bootstrap_bits(engine, ct: Ciphertext, relin_key, conj_key, boot_key: Bootst
     for e in plan.cts + plan.stc + [plan.cts_bits0]:
         e["_keys"] = plan.rot_keys
     be, P = engine.backend, engine.params
-    L = P.max_level
+    L = P.max_level if top_level is None else int(top_level)
+    if L > P.max_level:
+        raise RuntimeError(f"bootstrap_bits: top_level {L} above max_level {P.max_level}")
     if L < plan.depth_bits + 1:
-        raise RuntimeError(f"bit bootstrapping needs max_level >= {plan.depth_bits + 1}, engine has {L}")
+        raise RuntimeError(f"bit bootstrapping needs {plan.depth_bits + 1} levels at the top, got {L}")
     engine._count("bootstrap")
     lvl_in = len(plan.stc) + 1
     if ct.level < lvl_in:

@@ -895,8 +895,9 @@ class Engine:
         from .bootstrap import bootstrap
         return bootstrap(self, ct, relin_key, conj_key, boot_key)
 
-    def bootstrap_bits(self, ct: Ciphertext, relin_key, conj_key, boot_key) -> Ciphertext:
+    def bootstrap_bits(self, ct: Ciphertext, relin_key, conj_key, boot_key, top_level: Optional[int] = None) -> Ciphertext:
         """Refresh of a ciphertext whose slots are u + i v with u, v = +-1 (two bit planes): returns the batch
-        [all u, all v] of real ciphertexts, cleaned (aes_fhe_b200/bootstrap.py::bootstrap_bits)."""
+        [all u, all v] of real ciphertexts, cleaned (aes_fhe_b200/bootstrap.py::bootstrap_bits).  top_level: raise to
+        this level instead of max_level (the result sits at top_level - depth; every step runs on fewer limbs)."""
         from .bootstrap import bootstrap_bits
-        return bootstrap_bits(self, ct, relin_key, conj_key, boot_key)
+        return bootstrap_bits(self, ct, relin_key, conj_key, boot_key, top_level)

@@ -418,14 +418,15 @@ class AESBitService:
         return out
 
     # ------------------------------------------------------------------ refresh and chained rounds
-    def refresh(self, state: Ciphertext) -> Ciphertext:
-        """bit bootstrap of a whole state: bit planes k and k + 4 travel as real and imaginary part"""
+    def refresh(self, state: Ciphertext, top_level: Optional[int] = None) -> Ciphertext:
+        """bit bootstrap of a whole state: bit planes k and k + 4 travel as real and imaginary part.  top_level: the
+        level the refresh is raised to (plan_levels: only as high as the rounds up to the next refresh need)"""
         e = self.engine
         G = self._G(state)
         half = 16 * G
         re, im = self._slice(state, 0, half), self._slice(state, half, 2 * half)
         packed = e.add(re, e.multiply_by_i(im, 1))
-        out = e.bootstrap_bits(packed, self.eng.relin_key, self.eng.conj_key, self.boot_key)
+        out = e.bootstrap_bits(packed, self.eng.relin_key, self.eng.conj_key, self.boot_key, top_level)
         self.refreshes += half
         self._tick("refresh")
         return out
@@ -439,10 +440,11 @@ class AESBitService:
         that level).  A refresh leaves max_level - depth_bits levels; a round needs 7 (the last: 5) and, unless it
         is the final one, must leave boot_in_levels for the next refresh."""
         from ..bootstrap import DOUBLE_ANGLES_BITS, POLY_DEGREE_BITS, _ps_depth
-        after_boot = self.engine.max_level - (len_groups(self.boot_key) + _ps_depth(POLY_DEGREE_BITS) + DOUBLE_ANGLES_BITS)
-        lvl = fresh_level
-        key_levels, boots = [lvl], []
-        lvl -= self.ARK_LEVELS
+        depth = len_groups(self.boot_key) + _ps_depth(POLY_DEGREE_BITS) + DOUBLE_ANGLES_BITS
+        after_boot = self.engine.max_level - depth
+        # pass 1: which rounds start with a refresh (greedy, refreshes at full height)
+        lvl = fresh_level - self.ARK_LEVELS
+        boots = []
         for r in range(1, rounds + 1):
             last = (r == 10)
             need = self.round_levels(last) + (0 if r == rounds else self.boot_in_levels)
@@ -453,10 +455,25 @@ class AESBitService:
                 lvl = after_boot
                 if lvl < need:
                     raise RuntimeError(f"refresh leaves {lvl} levels, a round needs {need}: raise max_level")
+            lvl -= self.round_levels(last)
+        # pass 2: a refresh is raised only as high as the rounds up to the next refresh (and its entry) need -- the
+        # whole bootstrap and those rounds then run on fewer limbs
+        tops = {}
+        for i, r in enumerate(boots):
+            nxt = boots[i + 1] if i + 1 < len(boots) else rounds + 1
+            used = sum(self.round_levels(q == 10) for q in range(r, nxt)) + (self.boot_in_levels if nxt <= rounds else 0)
+            tops[r] = min(self.engine.max_level, depth + used)
+        lvl = fresh_level
+        key_levels = [lvl]
+        lvl -= self.ARK_LEVELS
+        for r in range(1, rounds + 1):
+            last = (r == 10)
+            if r in tops:
+                lvl = tops[r] - depth
             lvl -= self.SBOX_LEVELS
             key_levels.append(lvl)
             lvl -= self.FINAL_LEVELS if last else self.MIX_LEVELS
-        return {"key_levels": key_levels, "refresh_before_rounds": boots, "out_level": lvl}
+        return {"key_levels": key_levels, "refresh_before_rounds": boots, "refresh_top_levels": tops, "out_level": lvl}
 
     def best_fresh_level(self, rounds: int = 10) -> int:
         """the lowest input level with the fewest refreshes (a higher level only makes the first rounds dearer)"""
@@ -477,8 +494,9 @@ class AESBitService:
         MixColumns + AddRoundKey; the refresh happens only when the levels left would not carry the round and
         the entry of the next bootstrap."""
         G = self._G(state)
+        plan = self.plan_levels(state.level, rounds)
         if round_keys is None:
-            round_keys = self.encrypt_round_keys(key16, G, rounds=rounds)
+            round_keys = self.encrypt_round_keys(key16, G, plan, rounds=rounds)
         st = self.add_round_key(state, round_keys[0])
         for r in range(1, rounds + 1):
             last = (r == 10)
@@ -487,7 +505,7 @@ class AESBitService:
             if st.level < need:
                 if st.level < self.boot_in_levels:
                     raise RuntimeError(f"round {r}: {st.level} levels left, the bit bootstrap needs {self.boot_in_levels}")
-                st = self.refresh(st)
+                st = self.refresh(st, plan["refresh_top_levels"].get(r))
                 if st.level < need:
                     raise RuntimeError(f"refresh leaves {st.level} levels, a round needs {need}: raise max_level")
             st = self.sub_bytes(st)

@@ -222,8 +222,9 @@ def test_ecb_ten_rounds_on_oracle(ref_backend_cls):
 
 
 def test_level_plan_picks_the_input_level_with_the_fewest_refreshes():
-    """host logic of AESBitService.plan_levels / best_fresh_level on the 24-level chain: a refresh leaves 11 levels,
-    a round takes 7 (the last 5) and must leave 4 for the next refresh"""
+    """host logic of AESBitService.plan_levels / best_fresh_level on the 24-level chain: a full-height refresh leaves
+    11 levels, a round takes 7 (the last 6, polish included) and must leave 4 for the next refresh; a refresh is
+    raised only as high as the rounds up to the next one need"""
     class _Eng:
         max_level = 24
 
@@ -232,9 +233,15 @@ def test_level_plan_picks_the_input_level_with_the_fewest_refreshes():
     svc = AB.AESBitService.__new__(AB.AESBitService)
     svc.engine, svc.boot_key, svc.boot_in_levels = _Eng(), _Key(), 4
     low = svc.plan_levels(5)
-    assert low["refresh_before_rounds"] == list(range(1, 11)) and low["key_levels"] == [5] + [7] * 10 and low["out_level"] == 5
+    assert low["refresh_before_rounds"] == list(range(1, 11)) and low["key_levels"] == [5] + [7] * 9 + [2] and low["out_level"] == 0
+    assert low["refresh_top_levels"] == {**{r: 24 for r in range(1, 10)}, 10: 19}      # the last one: 13 + 6, not 24
     best = svc.plan_levels(19)
     assert best["refresh_before_rounds"] == [3, 4, 5, 6, 7, 8, 9, 10] and best["key_levels"][:3] == [19, 14, 7]
+    svc.engine.max_level = 26                                                                # the default chain
+    deep = svc.plan_levels(26)
+    assert deep["refresh_before_rounds"] == [4, 5, 6, 7, 8, 9] and deep["out_level"] == 0
+    assert deep["refresh_top_levels"] == {4: 24, 5: 24, 6: 24, 7: 24, 8: 24, 9: 26} and deep["key_levels"][4:] == [7, 7, 7, 7, 7, 9, 2]
+    svc.engine.max_level = 24
     assert svc.plan_levels(24)["refresh_before_rounds"] == best["refresh_before_rounds"]       # more levels buy nothing
     assert svc.best_fresh_level() == 19
     with pytest.raises(RuntimeError):
