@@ -10,7 +10,13 @@
 #include <cstdlib>
 #include <cstdio>
 #include <string>
+#include <unordered_map>
 #include <vector>
+#include <cmath>
+
+#ifndef FHE_BCONV_DEFAULT_VARIANT
+#define FHE_BCONV_DEFAULT_VARIANT 2
+#endif
 
 typedef unsigned __int128 u128;
 
@@ -74,6 +80,9 @@ struct fhe_ctx {
     ConstF* pinv = nullptr;               // [n_q]  P^-1 mod q_i
     u64 q0inv_mod_q1 = 0;
     std::vector<void*> owned;
+    // host mirrors of the base-conversion tables, keyed by their device array: k_bconv_param takes its table by value
+    std::unordered_map<const BConvTable*, std::vector<BConvTable>> bconv_host;
+    std::unordered_map<const BConvTable*, std::vector<std::vector<unsigned char>>> bconv_params;   // BConvParam<ns> per table, built on first use
     // scratch arena
     u64* scratch = nullptr;
     size_t scratch_words = 0;
@@ -201,6 +210,7 @@ void build_level_tables(fhe_ctx* c) {
             tb.nt = nt;
         }
         c->modup_tables[nq] = to_device(tabs);
+        c->bconv_host[c->modup_tables[nq]] = tabs;
         c->modup_scale[nq] = to_device(scale);
         c->owned.push_back(c->modup_tables[nq]); c->owned.push_back(c->modup_scale[nq]);
 
@@ -216,6 +226,7 @@ void build_level_tables(fhe_ctx* c) {
                 for (int k = 0; k < K; ++k) tb.f[i][k] = h_shoup(prod_except(c, pids, k, m), m);
             }
             c->moddown_table[nq] = to_device(td);
+            c->bconv_host[c->moddown_table[nq]] = td;
             c->owned.push_back(c->moddown_table[nq]);
         }
         if (nq >= 2 && K > 0) {
@@ -242,6 +253,7 @@ void build_level_tables(fhe_ctx* c) {
                 inv[i] = h_shoup(h_inv(prod_except(c, sids, -1, m), m), m);
             }
             c->mdrs_table[nq] = to_device(td);
+            c->bconv_host[c->mdrs_table[nq]] = td;
             c->mdrs_scale[nq] = to_device(sc);
             c->mdrs_inv[nq] = to_device(inv);
             c->owned.push_back(c->mdrs_table[nq]); c->owned.push_back(c->mdrs_scale[nq]); c->owned.push_back(c->mdrs_inv[nq]);
@@ -277,11 +289,53 @@ void build_level_tables(fhe_ctx* c) {
     if (n_q >= 2) c->q0inv_mod_q1 = h_inv(c->q[0] % c->q[1], c->q[1]);
 }
 
+// the table of one launch as a kernel parameter (constants split at 2^23 on the host: the same h = rint(c 2^-23),
+// l = c - h 2^23, s = h + l as split23 on the device)
+template <int NS>
+BConvParam<NS> bconv_param(const fhe_ctx* c, const BConvTable& tb) {
+    BConvParam<NS> p;
+    std::memset(&p, 0, sizeof(p));
+    p.nt = tb.nt;
+    for (int k = 0; k < NS; ++k) { p.src_slot[k] = tb.src_slot[k]; p.src_q[k] = c->q[tb.src_mod[k]]; }
+    for (int t = 0; t < tb.nt; ++t) {
+        p.dst_slot[t] = tb.dst_slot[t];
+        const Modulus M = h_modulus(c->q[tb.dst_mod[t]]);
+        p.q[t] = M.qd; p.qi[t] = M.qinv;
+        for (int k = 0; k < NS; ++k) {
+            const double v = tb.f[t][k].w;
+            Split3 sp;
+            sp.h = std::nearbyint(v * FHE_INV_TWO23);
+            sp.l = v - sp.h * FHE_TWO23;
+            sp.s = sp.h + sp.l;
+            p.f[t][k] = sp;
+        }
+    }
+    for (int t = tb.nt; t < FHE_MAX_DST; ++t) { p.q[t] = 3.0; p.qi[t] = 1.0 / 3.0; }     // never stored
+    return p;
+}
 template <int NS>
 void launch_bconv_ns(fhe_ctx* c, cudaStream_t s, int groups, const BConvTable* tabs, int n_tabs, u64* dst,
                      long long dst_stride, const u64* src, long long src_stride, int g_first, int g_step) {
-    // variant 1: the three-FMA exact dot product (k_bconv_dot3); env FHE_BCONV_VARIANT, default from the measurement in DESIGN.md
-    static const int variant = getenv("FHE_BCONV_VARIANT") ? atoi(getenv("FHE_BCONV_VARIANT")) : 0;
+    // variant 0: k_bconv (mulmod per term, table in shared memory); 1: k_bconv_dot3 (three-FMA dot product, split table in
+    // shared memory); 2: k_bconv_param (three-FMA dot product, table as kernel parameter).  env FHE_BCONV_VARIANT
+    static const int variant = getenv("FHE_BCONV_VARIANT") ? atoi(getenv("FHE_BCONV_VARIANT")) : FHE_BCONV_DEFAULT_VARIANT;
+    if constexpr (NS <= 12) if (variant == 2 && g_step == n_tabs) {
+        auto it = c->bconv_host.find(tabs);
+        if (it != c->bconv_host.end()) {
+            auto& vec = c->bconv_params[tabs];
+            if (vec.empty()) vec.resize(it->second.size());
+            std::vector<unsigned char>& blob = vec[g_first % n_tabs];
+            if (blob.empty()) {                            // the table at index g_first has exactly NS sources (launch_bconv)
+                const BConvParam<NS> p = bconv_param<NS>(c, it->second[g_first % n_tabs]);
+                blob.resize(sizeof(p));
+                std::memcpy(blob.data(), &p, sizeof(p));
+            }
+            constexpr int C = NS <= 7 ? 2 : 1;
+            launch(k_bconv_param<NS, C>, dim3(c->n / (256 * C), groups), dim3(256), s, c->log_n,
+                   *reinterpret_cast<const BConvParam<NS>*>(blob.data()), n_tabs, dst, dst_stride, src, src_stride, g_first, g_step);
+            return;
+        }
+    }
     if (variant == 1)
         launch(k_bconv_dot3<NS>, dim3(c->n / 256, groups), dim3(256), s, c->T, tabs, n_tabs, dst, dst_stride, src, src_stride,
                g_first, g_step);

@@ -725,6 +725,93 @@ __global__ void __launch_bounds__(256) k_bconv_dot3(DevTables T, const BConvTabl
     }
 }
 
+// The same three-FMA dot product with the table as a KERNEL PARAMETER: a launch converts with exactly one table (the digits
+// of a ModUp are launched one by one), so the split constants sit in the constant bank and, with the loops over targets
+// and sources fully unrolled, every FMA takes its constant as an immediate constant-bank operand -- no shared-memory
+// load per term, which is what made k_bconv_dot3 load/store bound (3 LDS per 3 FMA).  40 FP64 operations per output
+// with seven sources (21 FMA, ~18 for the reduction, the splits of the sources amortised over the targets) against 54
+// in k_bconv.  C coefficients per thread (idx, idx + N/2): two for digits of up to seven limbs, one above (3 NS C
+// doubles of split sources in registers).  Same canonical residues as k_bconv.     grid: (N / (256 C), groups)
+template <int NS>
+struct BConvParam {
+    int nt;
+    int src_slot[NS];
+    u64 src_q[NS];
+    int dst_slot[FHE_MAX_DST];
+    double q[FHE_MAX_DST], qi[FHE_MAX_DST];
+    Split3 f[FHE_MAX_DST][NS];              // (Q/q_k) mod m_t split at 2^23
+};
+// targets t and t + 1 in one straight-line block (6 C independent FMA chains); the second is stored only if it exists
+// (the table is zero beyond nt: its arithmetic is harmless and never leaves the registers)
+template <int NS, int C>
+FHE_D void bconv_param_pair(const BConvParam<NS>& tb, int t, bool second, const Split3 (&y)[C][NS], u64* d, u32 half, int log_n) {
+    double A[2][C], B[2][C], Cc[2][C];
+#pragma unroll
+    for (int u = 0; u < 2; ++u)
+#pragma unroll
+        for (int c = 0; c < C; ++c) { A[u][c] = 0.0; B[u][c] = 0.0; Cc[u][c] = 0.0; }
+#pragma unroll
+    for (int k = 0; k < NS; ++k)
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const Split3 f = tb.f[t + u][k];
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+                A[u][c] = d_fma(y[c][k].h, f.h, A[u][c]); B[u][c] = d_fma(y[c][k].s, f.s, B[u][c]);
+                Cc[u][c] = d_fma(y[c][k].l, f.l, Cc[u][c]);
+            }
+        }
+    double r[2][C];
+#pragma unroll
+    for (int u = 0; u < 2; ++u)
+#pragma unroll
+        for (int c = 0; c < C; ++c) r[u][c] = dot3_finish(A[u][c], B[u][c], Cc[u][c], tb.q[t + u], tb.qi[t + u]);
+    u64* d0 = d + ((size_t)tb.dst_slot[t] << log_n);
+#pragma unroll
+    for (int c = 0; c < C; ++c) d0[c * half] = f_to_u64(r[0][c]);
+    if (second) {
+        u64* d1 = d + ((size_t)tb.dst_slot[t + 1] << log_n);
+#pragma unroll
+        for (int c = 0; c < C; ++c) d1[c * half] = f_to_u64(r[1][c]);
+    }
+}
+#ifndef FHE_EMU
+#define FHE_GRID_CONSTANT __grid_constant__
+#else
+#define FHE_GRID_CONSTANT
+#endif
+template <int NS, int C>
+__global__ void __launch_bounds__(256, (C == 2 || NS > 9 ? 2 : 3)) k_bconv_param(int log_n, const FHE_GRID_CONSTANT BConvParam<NS> tb, int n_tables,
+                                                                       u64* dst, long long dst_group_stride, const u64* src,
+                                                                       long long src_block_stride, int g_first, int g_step) {
+    const int g = blockIdx.y * g_step + g_first;
+    const u32 idx = blockIdx.x * 256 + threadIdx.x;
+    const u32 half = 1u << (log_n - 1);
+    const u64* s = src + (size_t)(g / n_tables) * src_block_stride + idx;
+    u64* d = dst + (size_t)g * dst_group_stride + idx;
+    u64 v[C][NS];
+#pragma unroll
+    for (int k = 0; k < NS; ++k)
+#pragma unroll
+        for (int c = 0; c < C; ++c) v[c][k] = s[((size_t)tb.src_slot[k] << log_n) + c * half];      // all loads before the first use
+    Split3 y[C][NS];
+#pragma unroll
+    for (int k = 0; k < NS; ++k) {
+        const u64 qk = tb.src_q[k];
+        const double qkd = u64_to_f(qk);
+#pragma unroll
+        for (int c = 0; c < C; ++c)
+            y[c][k] = split23(v[c][k] > (qk >> 1) ? d_add(u64_to_f(v[c][k]), -qkd) : u64_to_f(v[c][k]));
+    }
+    const int nt = tb.nt;
+    // two targets per (uniform) test: the index into the table stays a compile-time constant
+#pragma unroll
+    for (int t = 0; t < FHE_MAX_DST; t += 2) {
+        if (t >= nt) break;
+        bconv_param_pair<NS, C>(tb, t, t + 1 < nt, y, d, half, log_n);
+    }
+}
+
 
 // ---------------------------------------------------------------- key inner product
 // acc[c][b][t] = sum_j e_bj[t] * ksk[j][c][id(t)],  e_bj[t] = d[b][t] if t in digit j else ext[b][j][t]

@@ -183,7 +183,11 @@ FHE_D size_t row_off(const RowMap& map, RowRef row, long long poly_stride) {
 struct LoadPlain {          // canonical residues
     const u64* src; long long poly_stride;
     FHE_D double operator()(const RowMap& map, RowRef row, int idx, int, const Modulus&) const {
+#ifdef FHE_NTT_DIAG_NOMEM      /* measurement variant only (tools/ntt_ab.py): arithmetic and exchanges without global data traffic */
+        return u64_to_f((u64)(idx * 2654435761u + row.j));
+#else
         return u64_to_f(src[row_off(map, row, poly_stride) + idx]);
+#endif
     }
     // hint: `count` consecutive elements starting at idx will be loaded soon (fused NTT, L2 prefetch)
     FHE_D void prefetch(const RowMap& map, RowRef row, int idx, int count) const {
@@ -194,7 +198,11 @@ struct LoadPlain {          // canonical residues
 struct StorePlain {
     u64* dst; long long poly_stride;
     FHE_D void operator()(const RowMap& map, RowRef row, int idx, double v, int, const Modulus&) const {
+#ifdef FHE_NTT_DIAG_NOMEM
+        if (v == -12345.0) dst[row_off(map, row, poly_stride) + idx] = f_to_u64(v);
+#else
         dst[row_off(map, row, poly_stride) + idx] = f_to_u64(v);
+#endif
     }
     // a StoreOp may read other operands in its epilogue: warm(idx) is called once per thread at the
     // start of the last pass with the first of 16 consecutive elements the thread's row will need
@@ -304,6 +312,7 @@ FHE_D void fwd_pass_a_body(const DevTables& T, const RowMap& map, RowRef rref, i
 #pragma unroll
         for (int i = 0; i < 16; ++i) x[i] = ld(map, rref, e0 + i * (G << 8), mid, M);
         ct_radix16<(16 >> (LEV1 > 0 ? LEV1 : 1))>(x, 1, [&](int S, int, int i) { return mk_tw(tw_col_r1<LOG_R>(tw, S, i), qinv); }, q);
+#ifndef FHE_NTT_DIAG_NOSMEM     /* measurement variant only: the forward transform without its exchanges (wrong results) */
         double* smw = sm + g * COLS + cc;
 #pragma unroll
         for (int i = 0; i < 16; ++i) smw[i * (G * COLS)] = x[i];
@@ -311,6 +320,7 @@ FHE_D void fwd_pass_a_body(const DevTables& T, const RowMap& map, RowRef rref, i
         const double* smr = sm + 16 * g * COLS + cc;
 #pragma unroll
         for (int i = 0; i < 16; ++i) x[i] = smr[i * COLS];
+#endif
     } else {
         const int e0 = (g << 12) + c;
 #pragma unroll
@@ -353,21 +363,31 @@ FHE_D void fwd_pass_b_body(const DevTables& T, const RowMap& map, RowRef rref, i
         ct_radix16<1>(x, 1, [&](int s, int, int i) {
             return mk_tw(ld_d(s == 1 ? t1 : s == 2 ? t2p + (i >> 3) : s == 3 ? t3 + (i >> 2) : t4 + (i >> 1)), qinv); }, q);
     }
+#ifndef FHE_NTT_DIAG_NOSMEM
 #pragma unroll
     for (int i = 0; i < 16; ++i) smS[18 * i] = x[i];
     ntt_sync_warp();                                          // a row is owned by 16 lanes of one warp
     lds16(x, smC);
+#endif
     ct_radix16<1>(x, 5, [&](int, int half, int i) { return mk_tw(t2.w[8 / half - 1 + i / (2 * half)], qinv); }, q);
     ntt_sync_warp();
 #pragma unroll
     for (int i = 0; i < 16; ++i) x[i] = reduce_canon(x[i], q, qinv);
+#ifndef FHE_NTT_DIAG_NOSMEM
     sts16(smC, x);
+#endif
     double ep[16];                                            // epilogue operands (zeros for a plain store)
 #pragma unroll
     for (int i = 0; i < 16; ++i) ep[i] = st.fetch(map, rref, rbase + 16 * i);
     ntt_sync_warp();
+#ifndef FHE_NTT_DIAG_NOSMEM
 #pragma unroll
     for (int i = 0; i < 16; ++i) st.put(map, rref, rbase + 16 * i, smS[18 * i], mid, M, ep[i]);
+#else
+#pragma unroll
+    for (int i = 0; i < 16; ++i) st.put(map, rref, rbase + 16 * i, x[i], mid, M, ep[i]);
+    (void)smS; (void)smC;
+#endif
 }
 template <int LOG_N, class StoreOp>
 __global__ void __launch_bounds__(256, FHE_PASSB_MINB) ntt_fwd_pass_b(DevTables T, RowMap map, LoadRaw ld, StoreOp st) {

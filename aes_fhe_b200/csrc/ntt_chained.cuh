@@ -56,13 +56,21 @@ inline void chain_pause() { std::this_thread::yield(); }
 struct LoadRawCG {
     const u64* src; long long poly_stride;
     FHE_D double operator()(const RowMap& map, RowRef row, int idx, int, const Modulus&) const {
+#ifdef FHE_NTT_DIAG_NOMEM
+        return u64_to_f((u64)(idx * 2654435761u + row.j));
+#else
         return bits_to_f(chain_ld_cg(src + row_off(map, row, poly_stride) + idx));
+#endif
     }
 };
 struct StoreRawCG {
     u64* dst; long long poly_stride;
     FHE_D void operator()(const RowMap& map, RowRef row, int idx, double v, int, const Modulus&) const {
+#ifdef FHE_NTT_DIAG_NOMEM
+        if (v == -12345.0) chain_st_cg(dst + row_off(map, row, poly_stride) + idx, f_to_bits(v));
+#else
         chain_st_cg(dst + row_off(map, row, poly_stride) + idx, f_to_bits(v));
+#endif
     }
 };
 
