@@ -238,9 +238,9 @@ class CudaBackend:
                    a.shape[0] * a.shape[1], nq, 0)
         return out
 
-    def add_const(self, a, cp, cm, nq):
-        """constant added to polynomial 0 of every ciphertext of the batch"""
-        out = a.clone()
+    def add_const(self, a, cp, cm, nq, inplace: bool = False):
+        """constant added to polynomial 0 of every ciphertext of the batch (inplace: `a` is a temporary the caller owns)"""
+        out = a if inplace and a.is_contiguous() else a.clone()
         fp, fm = self._consts(cp, cm)
         self._call("fhe_add_const", self._ptr(out), self._ptr(out), fp.ctypes.data, fm.ctypes.data, a.shape[1], nq, 0)
         return out

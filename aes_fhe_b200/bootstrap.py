@@ -265,7 +265,7 @@ def chebyshev_eval_ps_lazy(engine, relin_key, y: Ciphertext, coeffs, baby: int =
         """2 a^2 - 1 from a: the square read as twice its value at half the scale"""
         sq, d = mul(a, da, a, da)
         d = d / 2
-        return engine.add_plain(sq, -float(d)), d
+        return engine.add_plain(sq, -float(d), inplace=True), d
 
     one = Fraction(1)
     T: Dict[int, Tuple[Ciphertext, Fraction]] = {1: two_x_minus_one(y, one) if even else (y, one)}
@@ -728,11 +728,11 @@ def bootstrap_bits(engine, ct: Ciphertext, relin_key, conj_key, boot_key: Bootst
     # w = 2 u^2 - 1 instead of degree 18 in y -- 7 products instead of 9 at the same depth (1 + 4 levels)
     ps = chebyshev_eval_ps_lazy if hasattr(engine, "_mul_ct_dropped") and not _EAGER_PS else chebyshev_eval_ps
     if _EVEN_EVALMOD:
-        cpoly = ps(engine, relin_key, engine.add_plain(y, -0.25 / K_NORM), plan.poly_bits_even, even=True)
+        cpoly = ps(engine, relin_key, engine.add_plain(y, -0.25 / K_NORM, inplace=True), plan.poly_bits_even, even=True)
     else:
         cpoly = ps(engine, relin_key, y, plan.poly_bits)
     _phase(engine, "boot:evalmod_polynomial")
     for i in range(DOUBLE_ANGLES_BITS):
-        cpoly = engine.add_plain(engine.multiply(cpoly, cpoly, relin_key), -plan.alphas_bits[i + 1])
+        cpoly = engine.add_plain(engine.multiply(cpoly, cpoly, relin_key), -plan.alphas_bits[i + 1], inplace=True)
     _phase(engine, "boot:evalmod_double_angle")
     return cpoly

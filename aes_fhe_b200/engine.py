@@ -626,11 +626,15 @@ class Engine:
             b = Ciphertext(self, be.concat([b.polys, be.zeros(a.npoly - b.npoly, b.batch, b.level + 1, False)]), b.level)
         return a, b
 
-    def add_plain(self, ct: Ciphertext, value) -> Ciphertext:
+    def add_plain(self, ct: Ciphertext, value, inplace: bool = False) -> Ciphertext:
+        """ct + constant.  inplace: ``ct`` is a temporary of the caller (a product it has just formed): the constant
+        is added into its storage instead of a copy of it."""
         re, im = encoding.const_i64(complex(value), self.params.delta[ct.level])
         nq = ct.level + 1
         cp, cm = self._const_residues(re, im, nq)
         self._count('add_const')
+        if inplace:
+            return Ciphertext(self, self.backend.add_const(ct.polys, cp, cm, nq, True), ct.level)
         return Ciphertext(self, self.backend.add_const(ct.polys, cp, cm, nq), ct.level)
 
     def subtract(self, a: Ciphertext, b: Ciphertext) -> Ciphertext:

@@ -205,7 +205,7 @@ class RefBackend:
     def mul_const(self, a, cp, cm, nq):
         return self._constop(self._L.ref_mul_const, a, cp, cm, nq, 0)
 
-    def add_const(self, a, cp, cm, nq):
+    def add_const(self, a, cp, cm, nq, inplace: bool = False):
         out = np.array(a, copy=True)
         out[0:1] = self._constop(self._L.ref_add_const, out[0:1], cp, cm, nq, 0)
         return out
