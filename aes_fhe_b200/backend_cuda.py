@@ -434,10 +434,10 @@ class CudaBackend:
         self._call("fhe_mul_plain_multi", self._ptr(out), ap, an, pp, T, G, nq, bt)
         return out
 
-    def bsgs_inner(self, ext, ct, keys: List, galois: List[int], pt_rows: List[List], nq: int):
+    def bsgs_inner(self, ext, ct, keys: List, galois: List[int], pt_rows: List[List], nq: int, acc=None):
         """double-hoisted baby steps (fhe_bsgs_inner): ext [B,beta,nq+K,N] = modup_raw(c1 of ct); ct [2,B,>=nq,N];
         keys[b] = switching-key tensor or None (no rotation); pt_rows[g][b] = extended-basis plaintext [1,1,nq+K,N] or
-        None -> [G, 2, B, nq+K, N]"""
+        None -> [G, 2, B, nq+K, N]; acc: the output of a previous pass (other baby steps) to add the sums to"""
         ct = ct.contiguous()
         ext = ext.contiguous()
         nb, G, bt = len(keys), len(pt_rows), ct.shape[1]
@@ -445,8 +445,9 @@ class CudaBackend:
         kp = (C.c_void_p * nb)(*[None if k is None else k.data_ptr() for k in keys])
         gp = (C.c_uint64 * nb)(*[int(g) for g in galois])
         pp = (C.c_void_p * (G * nb))(*[None if x is None else x.data_ptr() for row in keep for x in row])
-        out = self._empty(G, 2, bt, nq + self._K, self.n)
-        self._call("fhe_bsgs_inner", self._ptr(out), self._ptr(ext), self._ptr(ct), ct.shape[2], kp, gp, pp, nb, G, nq, bt)
+        out = self._empty(G, 2, bt, nq + self._K, self.n) if acc is None else acc
+        self._call("fhe_bsgs_inner", self._ptr(out), self._ptr(ext), self._ptr(ct), ct.shape[2], kp, gp, pp, nb, G, nq, bt,
+                   0 if acc is None else 1)
         return out
 
     def automorphism_rows(self, h, g: int):

@@ -39,6 +39,7 @@ POLY_DEGREE_BITS = 18
 import os as _os
 _EAGER_PS = _os.environ.get("FHE_EAGER_PS") == "1"        # A/B switch: EvalMod polynomial with level adjustments
 _EVEN_EVALMOD = _os.environ.get("FHE_EVEN_EVALMOD", "1") != "0"   # A/B switch: EvalMod polynomial in w = 2 u^2 - 1 (7 products) or in y (9)
+BSGS_MAX_BABY = int(_os.environ.get("FHE_BSGS_BABY", "32"))   # baby steps of a double-hoisted transform (16: 16 x 4, 32: 32 x 2 for 63 diagonals)
 _NO_DH = _os.environ.get("FHE_NO_DH") == "1"              # A/B switch: single-hoisted linear transforms (square BSGS)
 _NO_DH_FUSE = _os.environ.get("FHE_NO_DH_FUSE") == "1"    # A/B switch: double hoisting from separate primitives
 RHO_TARGET = 32.0         # q_0 / (scaled message): the message is divided by RHO_TARGET * Delta_0 / q_0
@@ -109,7 +110,8 @@ def _bsgs_split(rots: List[int], n: int, double_hoist: bool = False):
     """d = g + b with b in [0, bm): returns (bm, {g: [(b, d), ...]}).  Square split (n1 ~ sqrt of the number of
     diagonals) for the single-hoisted evaluation; with double hoisting the baby steps are cheap (one fused pass,
     no ModDown) and every giant step costs a ModDown + ModUp, so the split is as lopsided as the fused kernel
-    takes: up to 16 baby steps."""
+    takes: up to BSGS_MAX_BABY baby steps (32: the 63 diagonals of a radix-32 factor then need ONE key-switched giant
+    step; the fused kernel takes 16 baby steps per pass, so two passes are summed)."""
     nz = [d for d in rots if d]
     stride = n
     for d in nz:
@@ -117,7 +119,7 @@ def _bsgs_split(rots: List[int], n: int, double_hoist: bool = False):
     stride = int(stride) if nz else 1
     n1 = 1
     if double_hoist:
-        while n1 < 16 and 2 * n1 < len(rots):
+        while n1 < BSGS_MAX_BABY and 2 * n1 < len(rots):
             n1 *= 2
     else:
         while n1 * n1 < len(rots):
@@ -508,14 +510,17 @@ def _linear_transform_dh(engine, ct: Ciphertext, entry) -> Ciphertext:
     c0, c1 = be.select_poly(ct.polys, 0), be.select_poly(ct.polys, 1)
     engine._count('keyswitch_galois', sum(1 for b in blist if b))
     engine._count('mul_pt', sum(1 for row in rows for p in row if p is not None))
-    if hasattr(be, "bsgs_inner") and not _NO_DH_FUSE and len(blist) <= 16 and P.digits_at(nq) <= 4:
+    if hasattr(be, "bsgs_inner") and not _NO_DH_FUSE and P.digits_at(nq) <= 4:
         ext = be.modup_raw(c1, nq)
         inners = []
         for s in range(0, len(glist), 4):
             chunk = rows[s:s + 4]
-            out = be.bsgs_inner(ext, ct.polys, [None if b == 0 else keys[b].data for b in blist],
-                                [1 if b == 0 else int(keys[b].galois) for b in blist],
-                                [[pt(p) for p in row] for row in chunk], nq)
+            out = None
+            for b0 in range(0, len(blist), 16):                # the kernel takes 16 baby steps per pass
+                bl = blist[b0:b0 + 16]
+                out = be.bsgs_inner(ext, ct.polys, [None if b == 0 else keys[b].data for b in bl],
+                                    [1 if b == 0 else int(keys[b].galois) for b in bl],
+                                    [[pt(p) for p in row[b0:b0 + 16]] for row in chunk], nq, acc=out)
             inners += [out[i] for i in range(len(chunk))]
     else:
         # the same values from the primitives both backends have (the oracle's path):

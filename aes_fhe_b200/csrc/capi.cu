@@ -860,7 +860,7 @@ int fhe_ks_inner(fhe_ctx* c, void* stream, uint64_t* acc, const uint64_t* ext, c
 
 int fhe_bsgs_inner(fhe_ctx* c, void* stream, uint64_t* out, const uint64_t* ext, const uint64_t* ct, int ct_nq,
                    const uint64_t* const* keys, const uint64_t* galois, const uint64_t* const* pts, int nb, int G, int nq,
-                   int batch) {
+                   int batch, int accumulate) {
     if (bad_shape(c, nq, 0) || c->n_p == 0 || batch < 1 || c->modup_beta[nq] > 4 || nb < 1 || nb > FHE_BSGS_MAX_BABY ||
         G < 1 || G > FHE_BSGS_MAX_G || ct_nq < nq || !out || !ext || !ct || !keys || !galois || !pts)
         return fail("fhe_bsgs_inner: bad arguments");
@@ -881,9 +881,9 @@ int fhe_bsgs_inner(fhe_ctx* c, void* stream, uint64_t* out, const uint64_t* ext,
         if (variant == 2) { const size_t smem = (size_t)GN * 2 * BB * 256 * sizeof(double); \
             lc_allow_smem(k_bsgs_inner<BE, GN, BB, true>, smem); g_launches.fetch_add(1, std::memory_order_relaxed); \
             fhe_launch(k_bsgs_inner<BE, GN, BB, true>, grid, block, smem, s, c->T, nq, c->alpha, batch, nb, in, (const u64*)ext, \
-                       (const u64*)ct, ct_nq, (const ConstF*)c->p_mod_q, (u64*)out); } \
+                       (const u64*)ct, ct_nq, (const ConstF*)c->p_mod_q, (u64*)out, accumulate); } \
         else launch(k_bsgs_inner<BE, GN, BB, false>, grid, block, s, c->T, nq, c->alpha, batch, nb, in, (const u64*)ext, \
-                    (const u64*)ct, ct_nq, (const ConstF*)c->p_mod_q, (u64*)out); } while (0)
+                    (const u64*)ct, ct_nq, (const ConstF*)c->p_mod_q, (u64*)out, accumulate); } while (0)
 #define FHE_BSGS_G(BE) switch (G) { case 1: FHE_BSGS_GO(BE, 1); break; case 2: FHE_BSGS_GO(BE, 2); break; \
                                     case 3: FHE_BSGS_GO(BE, 3); break; default: FHE_BSGS_GO(BE, 4); break; }
     switch (beta) {

@@ -463,7 +463,7 @@ struct BsgsIn {
 template <int BETA, int GN, int BB, bool SMACC>
 __global__ void __launch_bounds__(256, (SMACC ? 3 : 2)) k_bsgs_inner(DevTables T, int nq, int alpha, int batch, int nb,
                                                                   BsgsIn in, const u64* ext, const u64* ct, int ct_nq,
-                                                                  const ConstF* p_mod_q, u64* out) {
+                                                                  const ConstF* p_mod_q, u64* out, int accumulate) {
     const int t = blockIdx.y;
     const int ne = nq + T.n_p;
     const int id = t < nq ? t : T.n_q + (t - nq);
@@ -561,8 +561,10 @@ __global__ void __launch_bounds__(256, (SMACC ? 3 : 2)) k_bsgs_inner(DevTables T
             const int b = b0 + u;
             if (b < batch) {
                 u64* o = out + (size_t)g * 2 * ops + ((((size_t)b * ne) + t) << log_n) + p;
-                o[0] = f_to_u64(reduce_canon(FHE_ACC(g, 0, u), q, qi));
-                o[ops] = f_to_u64(reduce_canon(FHE_ACC(g, 1, u), q, qi));
+                double r0 = FHE_ACC(g, 0, u), r1 = FHE_ACC(g, 1, u);
+                if (accumulate) { r0 = d_add(r0, u64_to_f(o[0])); r1 = d_add(r1, u64_to_f(o[ops])); }    // a second pass of baby steps
+                o[0] = f_to_u64(reduce_canon(r0, q, qi));
+                o[ops] = f_to_u64(reduce_canon(r1, q, qi));
             }
         }
 #undef FHE_ACC

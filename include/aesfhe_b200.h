@@ -115,10 +115,11 @@ int fhe_mul_plain_sum(fhe_ctx* ctx, void* stream, uint64_t* out, const uint64_t*
  * by the caller: fhe_moddown / fhe_ks_accum / fhe_moddown_rescale).  ext = fhe_modup output of c1 of `ct`
  * ([2][batch][ct_nq >= nq][N]); keys[b] = Galois key of baby step b with Galois element galois[b] (host arrays of
  * device pointers / values), keys[b] == NULL = no rotation; pts[.] = plaintexts [nq+K][N] in the extended basis,
- * NULL = absent diagonal. */
+ * NULL = absent diagonal.  accumulate != 0: the sums are added to what `out` holds (a transform with more than 16 baby
+ * steps is evaluated in several passes over the same `ext`). */
 int fhe_bsgs_inner(fhe_ctx* ctx, void* stream, uint64_t* out, const uint64_t* ext, const uint64_t* ct, int ct_nq,
                    const uint64_t* const* keys, const uint64_t* galois, const uint64_t* const* pts, int nb, int G,
-                   int nq, int batch);
+                   int nq, int batch, int accumulate);
 
 /* The same pattern for G output sums over ONE set of T ciphertexts (the diagonal sums of all giant steps of a
  * baby-step/giant-step linear transform in Engine.bootstrap, xor_service.py:120-129): out[G][2][batch][nq][N],

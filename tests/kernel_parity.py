@@ -259,7 +259,7 @@ def check_double_hoisted_transform(P, gpu_backend, ref_backend, batch=3, half_wi
         keys = {}
         entry = B.prepare_matrix(eng, sk, mat, keys, None, double_hoist=True)
         nb = len({b for items in entry["giants"].values() for b, _ in items})
-        assert entry["dh"] and nb <= 16 and len(entry["giants"]) <= 4
+        assert entry["dh"] and nb <= B.BSGS_MAX_BABY and len(entry["giants"]) <= 4
         out = B._linear_transform(eng, ct, entry)
         assert out.level == ct.level - 1
         want = sum(d_vec * np.roll(v, -d, axis=-1) for d, d_vec in mat.items())

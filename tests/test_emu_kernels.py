@@ -76,9 +76,13 @@ def test_chained_ntt_many_chunks(chunk, emu_lib, ref_backend_cls, monkeypatch):
     assert b.lib.fhe_ntt_fused_status(b.ctx) == 0
 
 
-@pytest.mark.parametrize("log_n,lvl,dnum,half_width,batch", [(12, 5, 4, 20, 5), (12, 6, 2, 6, 2), (13, 4, 1, 31, 1)])
-def test_double_hoisted_transform(log_n, lvl, dnum, half_width, batch, emu_lib, ref_backend_cls):
+@pytest.mark.parametrize("log_n,lvl,dnum,half_width,batch,max_baby", [(12, 5, 4, 20, 5, 32), (12, 5, 4, 20, 5, 16), (12, 6, 2, 6, 2, 32),
+                                                                      (13, 4, 1, 31, 1, 32), (13, 4, 1, 31, 1, 16)])
+def test_double_hoisted_transform(log_n, lvl, dnum, half_width, batch, max_baby, emu_lib, ref_backend_cls, monkeypatch):
     """fhe_bsgs_inner (all baby steps of a BSGS transform in one pass, extended basis) against the oracle: 40
-    diagonals -> 16 baby x 3 giant steps with a ragged batch chunk; 12 -> 8 x 2; 62 -> 16 x 4 with one digit"""
+    diagonals -> 32 baby x 2 giant steps (two kernel passes summed) or 16 x 3, with a ragged batch chunk; 12 -> 8 x 2;
+    62 -> 32 x 2 or 16 x 4 with one digit"""
+    from aes_fhe_b200 import bootstrap as B
+    monkeypatch.setattr(B, "BSGS_MAX_BABY", max_baby)
     P = make_params(log_n, lvl, dnum=dnum)
     kp.check_double_hoisted_transform(P, _emu(P, emu_lib), ref_backend_cls(P), batch=batch, half_width=half_width)
