@@ -126,6 +126,14 @@ def test_bit_bootstrap_on_oracle(log_n, ref_backend_cls):
     got = eng.decrypt(out, w.secret_key)
     err = np.abs(got - np.concatenate([u, v])).max()
     assert err < 1e-3, err                      # input error 5e-3 rms (2e-2 max) came out squared: pi^2 e^2 / 8
+    # the same refresh raised only to level 17: three limbs fewer in every step, result at 17 - 13, same cleaning
+    low = eng.bootstrap_bits(ct, w.relin_key, w.conj_key, svc.boot_key, top_level=17)
+    assert low.level == 17 - plan.depth_bits
+    assert np.abs(eng.decrypt(low, w.secret_key) - np.concatenate([u, v])).max() < 1e-3
+    with pytest.raises(RuntimeError):
+        eng.bootstrap_bits(ct, w.relin_key, w.conj_key, svc.boot_key, top_level=21)           # above max_level
+    with pytest.raises(RuntimeError):
+        eng.bootstrap_bits(ct, w.relin_key, w.conj_key, svc.boot_key, top_level=plan.depth_bits)     # no level left for the result
 
 
 def test_final_round_key_squares_the_error(ref_backend_cls):
