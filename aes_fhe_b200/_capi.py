@@ -37,6 +37,7 @@ SIGNATURES = {
     "fhe_lincomb": [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I],
     "fhe_mul_plain_sum": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I],
     "fhe_mul_plain_multi": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I],
+    "fhe_mul_relin_rescale_ptrs": [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I],
     "fhe_bsgs_inner": [_P, _P, _P, _P, _P, _I, _P, _P, _P, _I, _I, _I, _I, _I],
     "fhe_tensor_acc": [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I],
     "fhe_rescale": [_P, _P, _P, _P, _I, _I],

@@ -339,6 +339,39 @@ class CudaBackend:
                    self._ptr(ksk), nq, bt)
         return out
 
+    def mul_relin_rescale_gather(self, parts_a, parts_b, ksk, nq):
+        """the same product with gathered operands (fhe_mul_relin_rescale_ptrs): parts_x = [(tensor [2,Bx,>=nq,N],
+        batch indices), ...]; element i of the product multiplies the i-th listed batch element of side a with the
+        i-th of side b -- slices, permutations, replications and concatenations of tensors without a copy."""
+        es = self.n * 8
+
+        def ptrs(parts):
+            p0, p1, keep = [], [], []
+            for t, idx in parts:
+                t = t.contiguous()
+                keep.append(t)
+                step, base = t.shape[2] * es, t.data_ptr()
+                poly1 = t.shape[1] * step
+                for i in idx:
+                    if not 0 <= i < t.shape[1]:
+                        raise IndexError("mul_relin_rescale_gather: batch index out of range")
+                    p0.append(base + i * step)
+                    p1.append(base + poly1 + i * step)
+            return p0, p1, keep
+        a0, a1, keep_a = ptrs(parts_a)
+        b0, b1, keep_b = ptrs(parts_b)
+        bt = len(a0)
+        if bt != len(b0) or bt == 0:
+            raise ValueError("mul_relin_rescale_gather: the two sides list different numbers of batch elements")
+        outs = []
+        for lo in range(0, bt, 128):
+            hi = min(bt, lo + 128)
+            out = self._empty(2, hi - lo, nq - 1, self.n)
+            arr = [(C.c_void_p * (hi - lo))(*p[lo:hi]) for p in (a0, a1, b0, b1)]
+            self._call("fhe_mul_relin_rescale_ptrs", self._ptr(out), arr[0], arr[1], arr[2], arr[3], self._ptr(ksk), nq, hi - lo)
+            outs.append(out)
+        return outs[0] if len(outs) == 1 else torch.cat(outs, dim=1)
+
     def ks_accum(self, acc, d, ksk, lift, nq):
         """acc [2,B,nq+K,N] (or None) += <ModUp(d), ksk> + P * lift in the extended basis (no ModDown).
         d [1,B,nq,N] or None (lift only); lift [1 or 2,B,nq,N] or None.  Returns acc (updated in place)."""

@@ -961,6 +961,39 @@ int fhe_mul_relin_rescale(fhe_ctx* c, void* stream, uint64_t* out, const uint64_
     return relin_rescale_impl(c, stream, out, nullptr, a, a_nq, b, b_nq, rlk, nq, batch, "fhe_mul_relin_rescale");
 }
 
+int fhe_mul_relin_rescale_ptrs(fhe_ctx* c, void* stream, uint64_t* out, const uint64_t* const* a0, const uint64_t* const* a1,
+                               const uint64_t* const* b0, const uint64_t* const* b1, const uint64_t* rlk, int nq, int batch) {
+    if (bad_shape(c, nq, 0) || nq < 2 || c->n_p == 0 || batch < 1 || batch > FHE_MAX_MULB || c->modup_beta[nq] > 4 ||
+        !out || !a0 || !a1 || !b0 || !b1 || !rlk)
+        return fail("fhe_mul_relin_rescale_ptrs: bad arguments (1 <= batch <= 128, at most four digits)");
+    cudaStream_t s = (cudaStream_t)stream;
+    const int n = c->n, K = c->n_p, ne = nq + K, beta = c->modup_beta[nq];
+    const size_t words = ((size_t)batch * nq + (size_t)batch * beta * ne + 2 * (size_t)batch * ne) * n;
+    u64* base = arena(c, words);
+    if (!base) return fail("fhe_mul_relin_rescale_ptrs: scratch allocation failed");
+    u64* ext = base + (size_t)batch * nq * n;
+    u64* acc = ext + (size_t)batch * beta * ne * n;
+    MulPtrs mp;
+    LoadMulPtr ld;
+    for (int b = 0; b < FHE_MAX_MULB; ++b) {
+        const int i = b < batch ? b : batch - 1;
+        if (!a0[i] || !a1[i] || !b0[i] || !b1[i]) return fail("fhe_mul_relin_rescale_ptrs: null operand pointer");
+        mp.a0[b] = (const u64*)a0[i]; mp.a1[b] = (const u64*)a1[i]; mp.b0[b] = (const u64*)b0[i]; mp.b1[b] = (const u64*)b1[i];
+        ld.a1[b] = mp.a1[b]; ld.b1[b] = mp.b1[b];
+    }
+    int rc;
+    if ((rc = modup_from(c, s, ext, ld, nq, batch))) return rc;
+    {
+        dim3 grid(c->n / 256, nq + K), block(256);
+#define FHE_KSP_CASE(BE) case BE: launch(k_ks_inner_ptr<BE, 2>, grid, block, s, c->T, nq, c->alpha, batch, acc, (const u64*)ext, \
+                                         (const u64*)rlk, (const ConstF*)c->p_mod_q, mp); break;
+        switch (beta) { FHE_KSP_CASE(1) FHE_KSP_CASE(2) FHE_KSP_CASE(3) default: launch(k_ks_inner_ptr<4, 2>, grid, block, s, c->T, nq,
+                        c->alpha, batch, acc, (const u64*)ext, (const u64*)rlk, (const ConstF*)c->p_mod_q, mp); break; }
+#undef FHE_KSP_CASE
+    }
+    return moddown_rescale_tail(c, s, (u64*)out, acc, nq, 2 * batch, "fhe_mul_relin_rescale_ptrs");
+}
+
 int fhe_ks_accum(fhe_ctx* c, void* stream, uint64_t* acc, const uint64_t* d, const uint64_t* ksk, const uint64_t* lift,
                  int lift_polys, int nq, int batch, int accumulate) {
     if (bad_shape(c, nq, 0) || c->n_p == 0 || batch < 1 || c->modup_beta[nq] > FHE_MAX_BETA || !acc ||

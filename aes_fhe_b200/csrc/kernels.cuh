@@ -21,6 +21,12 @@ FHE_D u64 ld_u64(const u64* p) {
 #endif
 }
 
+#ifndef FHE_EMU
+#define FHE_GRID_CONSTANT __grid_constant__
+#else
+#define FHE_GRID_CONSTANT
+#endif
+
 struct LimbConsts {          // per-limb-slot constants passed by value
     u64 a[FHE_MAX_LIMBS];
     u64 b[FHE_MAX_LIMBS];
@@ -777,11 +783,6 @@ FHE_D void bconv_param_pair(const BConvParam<NS>& tb, int t, bool second, const 
         for (int c = 0; c < C; ++c) d1[c * half] = f_to_u64(r[1][c]);
     }
 }
-#ifndef FHE_EMU
-#define FHE_GRID_CONSTANT __grid_constant__
-#else
-#define FHE_GRID_CONSTANT
-#endif
 template <int NS, int C>
 __global__ void __launch_bounds__(256, (C == 2 || NS > 9 ? 2 : 3)) k_bconv_param(int log_n, const FHE_GRID_CONSTANT BConvParam<NS> tb, int n_tables,
                                                                        u64* dst, long long dst_group_stride, const u64* src,
@@ -848,10 +849,19 @@ FHE_D void st2(u64* p, u64 a, u64 b) {
 // (one uniform branch into two specialised bodies), so the per-ciphertext arithmetic is straight-line code: with the
 // runtime `j < beta` / `has_lift` tests of the first version every modular product was its own basic block.
 // BETA == 0: no key-switch part at all (acc (+)= P * lift on the q-limbs, (+)= 0 on the special limbs).
-template <int BETA, int UNR, bool AB, bool LIFT>
+// PTR (with AB): the operands of the fused multiply are gathered -- batch element b of the product is
+// (a0[b], a1[b]) x (b0[b], b1[b]), four device pointers to polynomials of >= nq contiguous limbs each.  The table is a
+// kernel parameter; the AES services multiply slices, permutations and concatenations of their state tensors through
+// it without materialising them (fhe_mul_relin_rescale_ptrs).
+#define FHE_MAX_MULB 128
+struct MulPtrs {
+    const u64* a0[FHE_MAX_MULB]; const u64* a1[FHE_MAX_MULB];
+    const u64* b0[FHE_MAX_MULB]; const u64* b1[FHE_MAX_MULB];
+};
+template <int BETA, int UNR, bool AB, bool LIFT, bool PTR = false>
 FHE_D void ks_inner_body(const DevTables& T, int nq, int alpha, int batch, u64* acc, const u64* ext, const u64* d,
                          const u64* ksk, const u64* lift, const ConstF* lift_c, int d_nq, int lift_nq, int lift_polys,
-                         int accum) {
+                         int accum, const MulPtrs* mp = nullptr) {
     constexpr int BE = BETA > 0 ? BETA : 1;
     const int t = blockIdx.y;
     const int ne = nq + T.n_p;
@@ -893,11 +903,17 @@ FHE_D void ks_inner_body(const DevTables& T, int nq, int alpha, int batch, u64* 
                                                : ep + ((((size_t)b * BETA + j) * ne) << log_n));
             }
             if (LIFT) {
-                L0[u] = ld_u64(lp + (((size_t)b * lift_nq) << log_n));
-                L1[u] = two ? ld_u64(lp + ps + (((size_t)b * lift_nq) << log_n)) : 0;
-                if (AB) {
-                    M0[u] = ld_u64(bp + (((size_t)b * d_nq) << log_n));
-                    M1[u] = ld_u64(bp + pd + (((size_t)b * d_nq) << log_n));
+                if (PTR) {
+                    const size_t off = ((size_t)t << log_n) + idx;
+                    L0[u] = ld_u64(mp->b0[b] + off); L1[u] = ld_u64(mp->b1[b] + off);
+                    M0[u] = ld_u64(mp->a0[b] + off); M1[u] = ld_u64(mp->a1[b] + off);
+                } else {
+                    L0[u] = ld_u64(lp + (((size_t)b * lift_nq) << log_n));
+                    L1[u] = two ? ld_u64(lp + ps + (((size_t)b * lift_nq) << log_n)) : 0;
+                    if (AB) {
+                        M0[u] = ld_u64(bp + (((size_t)b * d_nq) << log_n));
+                        M1[u] = ld_u64(bp + pd + (((size_t)b * d_nq) << log_n));
+                    }
                 }
             }
         }
@@ -957,6 +973,16 @@ __global__ void __launch_bounds__(256, (BETA <= 4 ? 3 : 2)) k_ks_inner(DevTables
     else
         ks_inner_body<BETA, UNR, AB, false>(T, nq, alpha, batch, acc, ext, d, ksk, lift, lift_c, d_nq, lift_nq, lift_polys, accum);
 }
+// fused multiply with gathered operands: acc = <ext, ksk> (d2 = a1 b1 on the digit's own limb) + P (a0 b0, a0 b1 + a1 b0)
+template <int BETA, int UNR>
+__global__ void __launch_bounds__(256, (BETA <= 4 ? 3 : 2)) k_ks_inner_ptr(DevTables T, int nq, int alpha, int batch, u64* acc,
+                                                                          const u64* ext, const u64* ksk, const ConstF* lift_c,
+                                                                          const FHE_GRID_CONSTANT MulPtrs mp) {
+    if ((int)blockIdx.y < nq)
+        ks_inner_body<BETA, UNR, true, true, true>(T, nq, alpha, batch, acc, ext, nullptr, ksk, ext, lift_c, nq, nq, 2, 0, &mp);
+    else
+        ks_inner_body<BETA, UNR, true, false, true>(T, nq, alpha, batch, acc, ext, nullptr, ksk, ext, lift_c, nq, nq, 2, 0, &mp);
+}
 
 // ---------------------------------------------------------------- fused NTT functors
 // rescale: load the centred remainder of the dropped limb.  |r| <= q_last/2 < 2^44 is a valid
@@ -985,6 +1011,17 @@ struct LoadMul {
         const u64* pa = a + row_off(map, row, a_stride) + idx;
         const u64* pb = b + row_off(map, row, b_stride) + idx;
         for (int k = 0; k < count; k += 16) { prefetch_l2(pa + k); prefetch_l2(pb + k); }
+    }
+};
+struct LoadMulPtr {         // the same product with gathered operands: polynomial 1 of batch element row.blk at a1[blk] / b1[blk]
+    const u64* a1[FHE_MAX_MULB]; const u64* b1[FHE_MAX_MULB];
+    FHE_D double operator()(const RowMap& map, RowRef row, int idx, int, const Modulus& M) const {
+        const size_t off = ((size_t)row.j << map.log_n) + idx;
+        return canon(mulmod_var(u64_to_f(a1[row.blk][off]), u64_to_f(b1[row.blk][off]), M.qd, M.qinv), M.qd);
+    }
+    FHE_D void prefetch(const RowMap& map, RowRef row, int idx, int count) const {
+        const size_t off = ((size_t)row.j << map.log_n) + idx;
+        for (int k = 0; k < count; k += 16) { prefetch_l2(a1[row.blk] + off + k); prefetch_l2(b1[row.blk] + off + k); }
     }
 };
 // rescale / ModDown epilogue: out = (in - ntt_value) * c[j]

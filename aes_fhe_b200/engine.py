@@ -799,6 +799,37 @@ class Engine:
             out = be.relin_rescale(be.tensor(ap, bp, nq), rlk.data, nq)
         return Ciphertext(self, out, lvl - 1), dev
 
+    def multiply_gather(self, parts_a, parts_b, rlk: RelinearizationKey):
+        """Batched ct x ct + relinearise + rescale whose operands are GATHERED: parts_x = [(Ciphertext, batch indices),
+        ...] (all ciphertexts of one side at one level); element i of the result is the product of the i-th listed
+        element of side a and the i-th of side b.  On the B200 nothing is copied (fhe_mul_relin_rescale_ptrs); other
+        backends materialise the two sides.  An operand above the product's level is used in place, as in
+        ``_mul_ct_dropped``: returns ``(ct, dev)`` with the true scale ``delta[ct.level] * dev``."""
+        P, be = self.params, self.backend
+        la, lb = {c.level for c, _ in parts_a}, {c.level for c, _ in parts_b}
+        if len(la) != 1 or len(lb) != 1:
+            raise RuntimeError("multiply_gather: the ciphertexts of one side must share a level")
+        la, lb = la.pop(), lb.pop()
+        if any(c.npoly != 2 for c, _ in list(parts_a) + list(parts_b)):
+            raise RuntimeError("multiply: operands must have 2 polynomials (relinearize first)")
+        lvl = min(la, lb)
+        if lvl == 0:
+            raise RuntimeError("multiply: no multiplicative depth left")
+        nq = lvl + 1
+        if hasattr(be, "mul_relin_rescale_gather") and P.digits_at(nq) <= 4:
+            dev = (P.delta[la] / P.delta[lvl]) * (P.delta[lb] / P.delta[lvl])
+            self._count('mul_ct')
+            self._count('keyswitch_relin')
+            self._count('rescale')
+            out = be.mul_relin_rescale_gather([(c.polys, list(i)) for c, i in parts_a], [(c.polys, list(i)) for c, i in parts_b],
+                                              rlk.data, nq)
+            return Ciphertext(self, out, lvl - 1), dev
+
+        def side(parts, level):
+            hs = [be.permute_batch(c.polys, list(i)) for c, i in parts]
+            return Ciphertext(self, hs[0] if len(hs) == 1 else be.concat_batch(hs), level)
+        return self._mul_ct_dropped(side(parts_a, la), side(parts_b, lb), rlk)
+
     def square(self, a: Ciphertext, relin_key=None) -> Ciphertext:
         return self._mul_ct(a, a, relin_key)
 

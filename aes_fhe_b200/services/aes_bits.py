@@ -311,10 +311,11 @@ class AESBitService:
         if o.level < 2:
             raise RuntimeError("final_round_key: a half-amplitude key needs two levels (plan_levels provides them)")
         key = e.level_down(key, o.level) if key.level > o.level else key
-        both = e.multiply(self._cat([o, o]), self._cat([key, o]), rlk)                # o k' | o^2
         n = o.batch
+        ident = list(range(n))
+        both, _ = e.multiply_gather([(o, ident + ident)], [(key, ident), (o, ident)], rlk)      # o k' | o^2
         z, sq = self._slice(both, 0, n), self._slice(both, n, 2 * n)
-        out = e.multiply(z, e.add_plain(e.negate(sq), 3.0), rlk)
+        out = e.multiply(z, e.add_plain(e.negate(sq), 3.0, inplace=True), rlk)
         self._tick("add_round_key")
         return out
 
@@ -340,45 +341,43 @@ class AESBitService:
         self._tick("shift_rows")
         return out
 
-    def _monomial_basis(self, bits: List[Ciphertext]):
-        """{A: prod_{j in A} bits[j]} for the 15 non-empty subsets A of four +-1 ciphertexts (any batch): the 6 pair
-        products in one batched multiply, then the 4 triples (pair x single) and the quadruple (pair x pair) in
-        another -- 11 key switches per batch element, depth 2.  In a triple the single is one level above the pair: it
-        is used in place (upper limb ignored, an exact modulus switch) and the product's scale leaves the table by
-        delta[l] / delta[l-1]; returns (monomials, scale factors) for the LUT constants to absorb."""
+    def _monomial_basis(self, src: Ciphertext, offs: Sequence[int], bt: int):
+        """{A: prod_{j in A} bit_j} for the 15 non-empty subsets A of four +-1 bit planes, bit j = batch elements
+        offs[j] .. offs[j] + bt - 1 of `src`: the 6 pair products in one batched multiply, then the 4 triples
+        (pair x single) in another and the quadruple (pair x pair) -- 11 key switches per batch element, depth 2.  The
+        products gather their operands from `src` and from the pair products (Engine.multiply_gather: no copies of
+        slices or concatenations).  In a triple the single is one level above the pair: it is used in place (upper
+        limb ignored, an exact modulus switch) and the product's scale leaves the table by delta[l] / delta[l-1];
+        returns (monomials, scale factors) for the LUT constants to absorb."""
         from fractions import Fraction
         e, rlk = self.engine, self.eng.relin_key
-        P = e.params
-        bt = bits[0].batch
+        R = lambda j: list(range(offs[j], offs[j] + bt))                             # noqa: E731
+        PR = lambda n: list(range(n * bt, (n + 1) * bt))                             # noqa: E731  pair n inside pp
         pairs = [(0, 1), (0, 2), (0, 3), (1, 2), (1, 3), (2, 3)]
-        pp = e.multiply(self._cat([bits[i] for i, _ in pairs]), self._cat([bits[j] for _, j in pairs]), rlk)
-        mono = {1 << j: bits[j] for j in range(4)}
+        pp, dp = e.multiply_gather([(src, [i for a, _ in pairs for i in R(a)])], [(src, [i for _, b in pairs for i in R(b)])], rlk)
+        assert dp == 1
+        mono = {1 << j: self._slice(src, offs[j], offs[j] + bt) for j in range(4)}
         dev = {m: Fraction(1) for m in range(1, 16)}
         for n, (i, j) in enumerate(pairs):
             mono[(1 << i) | (1 << j)] = self._slice(pp, n * bt, (n + 1) * bt)
-        triples = [(0b0111, mono[0b0011], bits[2]), (0b1011, mono[0b0011], bits[3]), (0b1101, mono[0b1100], bits[0]),
-                   (0b1110, mono[0b1100], bits[1])]
-        if hasattr(e, "_mul_ct_dropped") and all(b.level == pp.level + 1 for b in bits):
-            tt, d = e._mul_ct_dropped(self._cat([a for _, a, _ in triples]), self._cat([b for _, _, b in triples]), rlk)
-            qd = e.multiply(mono[0b0011], mono[0b1100], rlk)
-            for n, (m, _, _) in enumerate(triples):
-                mono[m] = self._slice(tt, n * bt, (n + 1) * bt)
-                dev[m] = d
-            mono[0b1111] = qd
-        else:
-            low = [e.level_down(b, pp.level) for b in bits]
-            second = [(m, a, low[[2, 3, 0, 1][n]]) for n, (m, a, _) in enumerate(triples)] + [(0b1111, mono[0b0011], mono[0b1100])]
-            qq = e.multiply(self._cat([a for _, a, _ in second]), self._cat([b for _, _, b in second]), rlk)
-            for n, (m, _, _) in enumerate(second):
-                mono[m] = self._slice(qq, n * bt, (n + 1) * bt)
+        p01, p23 = pairs.index((0, 1)), pairs.index((2, 3))
+        triples = [(0b0111, p01, 2), (0b1011, p01, 3), (0b1101, p23, 0), (0b1110, p23, 1)]
+        tt, d = e.multiply_gather([(pp, [i for _, n, _ in triples for i in PR(n)])], [(src, [i for _, _, j in triples for i in R(j)])], rlk)
+        qd, dq = e.multiply_gather([(pp, PR(p01))], [(pp, PR(p23))], rlk)
+        assert dq == 1
+        for n, (m, _, _) in enumerate(triples):
+            mono[m] = self._slice(tt, n * bt, (n + 1) * bt)
+            dev[m] = d
+        mono[0b1111] = qd
         return mono, dev
 
     def sub_bytes(self, state: Ciphertext) -> Ciphertext:
         """the S-box on every byte of the state: eight multilinear polynomials over the monomials of the high and
         the low four bits (22 + 8 key switches per (row, state), four levels)"""
         G = self._G(state)
-        bits = [self._slice(state, k * 4 * G, (k + 1) * 4 * G) for k in range(8)]
-        (lo, dlo), (hi, dhi) = self._monomial_basis(bits[:4]), self._monomial_basis(bits[4:])
+        bt = 4 * G
+        (lo, dlo) = self._monomial_basis(state, [k * bt for k in range(4)], bt)
+        (hi, dhi) = self._monomial_basis(state, [k * bt for k in range(4, 8)], bt)
         outs = _outer_sum(self.engine, self.eng.relin_key, hi, lo, [self.W[k] for k in range(8)], ("sbox-bits",), dhi, dlo)
         out = self._cat(outs)
         self._tick("sub_bytes")
@@ -388,32 +387,31 @@ class AESBitService:
         """MixColumns + AddRoundKey on a state that has been through ShiftRows and SubBytes:
             out_r = 2 a_r ^ 3 a_(r+1) ^ a_(r+2) ^ a_(r+3) ^ k_r = xtime(t_r) ^ t_(r+1) ^ a_(r+3) ^ k_r,   t_r = a_r ^ a_(r+1)
         as +-1 products: t (32), a_(r+3) k (32), t_(r+1) (a_(r+3) k) (32), the three xtime bits that take t_7 (12),
-        and the final product (32): 140 key switches per state, three levels."""
+        and the final product (32): 140 key switches per state, three levels.  Every product gathers its operands
+        (row rolls, bit slices, replications) from the tensors that hold them: no copies."""
         e, rlk = self.engine, self.eng.relin_key
         G = self._G(a)
+        S, Q = 32 * G, 4 * G                                                         # a state, one bit plane of it
         key = e.level_down(key, a.level) if key.level > a.level else key
-        a1 = self._take(a, self._row_roll_index(G, 1))
-        a3 = self._take(a, self._row_roll_index(G, 3))
-        both = e.multiply(self._cat([a, a3]), self._cat([a1, key]), rlk)             # t | a_(r+3) k
-        t, ka = self._slice(both, 0, 32 * G), self._slice(both, 32 * G, 64 * G)
-        tk = lambda k: self._slice(t, k * 4 * G, (k + 1) * 4 * G)                    # noqa: E731
-        t7 = tk(7)
-        lhs = self._cat([self._take(t, self._row_roll_index(G, 1))] + [tk(k - 1) for k in _XT_WITH_T7])
-        rhs = self._cat([ka] + [t7] * len(_XT_WITH_T7))
-        second = e.multiply(lhs, rhs, rlk)                                           # u | xtime bits 1, 3, 4
-        u = self._slice(second, 0, 32 * G)
-        xt7 = {k: self._slice(second, (32 + 4 * n) * G, (36 + 4 * n) * G) for n, k in enumerate(_XT_WITH_T7)}
+        ident = list(range(S))
+        r1, r3 = self._row_roll_index(G, 1), self._row_roll_index(G, 3)
+        both, _ = e.multiply_gather([(a, ident + r3)], [(a, r1), (key, ident)], rlk)             # t | a_(r+3) k
+        tk = lambda k: list(range(k * Q, (k + 1) * Q))                               # noqa: E731  bit plane k of t inside `both`
+        nx = len(_XT_WITH_T7)
+        second, _ = e.multiply_gather([(both, r1 + [i for k in _XT_WITH_T7 for i in tk(k - 1)])],
+                                      [(both, [S + i for i in ident] + tk(7) * nx)], rlk)  # u | xtime bits 1, 3, 4
         plain_bits = [k for k in range(8) if k not in _XT_WITH_T7]                   # xtime bits that are a plain shift
-        src = self._cat([t7 if k == 0 else tk(k - 1) for k in plain_bits])
+        src = self._take(both, [i for k in plain_bits for i in (tk(7) if k == 0 else tk(k - 1))])
         src = e.level_down(src, second.level)
         parts = []
         for k in range(8):
-            if k in xt7:
-                parts.append(xt7[k])
+            if k in _XT_WITH_T7:
+                n = _XT_WITH_T7.index(k)
+                parts.append((second, list(range(S + n * Q, S + (n + 1) * Q))))
             else:
                 n = plain_bits.index(k)
-                parts.append(self._slice(src, n * 4 * G, (n + 1) * 4 * G))
-        out = e.multiply(self._cat(parts), u, rlk)
+                parts.append((src, list(range(n * Q, (n + 1) * Q))))
+        out, _ = e.multiply_gather(parts, [(second, ident)], rlk)
         self._tick("mix_columns_ark")
         return out
 

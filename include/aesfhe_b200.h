@@ -182,6 +182,15 @@ int fhe_relin_rescale(fhe_ctx* ctx, void* stream, uint64_t* out, const uint64_t*
 int fhe_mul_relin_rescale(fhe_ctx* ctx, void* stream, uint64_t* out, const uint64_t* a, int a_nq,
                           const uint64_t* b, int b_nq, const uint64_t* rlk, int nq, int batch);
 
+/* The same product with GATHERED operands (the batched products of the AES-128 service multiply slices, permutations
+ * and concatenations of its state tensors -- the reference's drivers loop over single ciphertexts,
+ * test_all_process.py:21-48): batch element i of the product is (a0[i], a1[i]) x (b0[i], b1[i]); a0, a1, b0, b1 are
+ * HOST arrays of `batch` device pointers, each to one polynomial of >= nq contiguous limbs [>= nq][N].
+ * 1 <= batch <= 128, at most four key-switching digits at this level.  out[2][batch][nq-1][N]. */
+int fhe_mul_relin_rescale_ptrs(fhe_ctx* ctx, void* stream, uint64_t* out, const uint64_t* const* a0,
+                               const uint64_t* const* a1, const uint64_t* const* b0, const uint64_t* const* b1,
+                               const uint64_t* rlk, int nq, int batch);
+
 /* Key switches whose ModDown is shared (the giant steps of a baby-step/giant-step linear transform inside
  * Engine.bootstrap, xor_service.py:120-129): acc[2][batch][nq + K][N] (+)= <ModUp(d), ksk> + P * lift, all in the
  * extended basis.  d[1][batch][nq][N] (NTT domain) or NULL for "no key switch, lift only"; lift[lift_polys][batch][nq][N]

@@ -1,6 +1,7 @@
 """The CUDA kernel sources, compiled for the host simulator (csrc/compat.h, -DFHE_EMU), must
 match the CPU oracle bit for bit through the C ABI.  Runs without a GPU; the same checks run
 on the real sm_100a build in test_gpu_parity.py."""
+import numpy as np
 import pytest
 
 import kernel_parity as kp
@@ -61,6 +62,34 @@ def test_engine_ops(emu_lib, ref_backend_cls):
 def test_fused_lut_services(emu_lib, ref_backend_cls):
     P = make_params(12, 13)
     kp.check_fused_services(P, _emu(P, emu_lib), ref_backend_cls(P), batch=2)
+
+
+@pytest.mark.parametrize("log_n,lvl,dnum", [(12, 6, 0), (12, 7, 4)])
+def test_multiply_gather(log_n, lvl, dnum, emu_lib, ref_backend_cls):
+    """fused multiply with gathered operands (pointer table as a kernel parameter) against the oracle"""
+    P = make_params(log_n, lvl, dnum=dnum)
+    kp.check_multiply_gather(P, _emu(P, emu_lib), ref_backend_cls(P))
+
+
+def test_bit_sliced_round_on_emulator(emu_lib, ref_backend_cls):
+    """ARK_0, ShiftRows, SubBytes, MixColumns + ARK of the bit-sliced AES path through the real kernels (gathered
+    products, fused LUT sums) against the oracle at N = 2^12: identical residues, plain AES bytes"""
+    from test_aes_bits import make_service, KEY_B
+    from aes_fhe_b200.services.key_expansion import expand_key
+    from oracle import aes_plain as A
+    P = make_params(12, 9, scale_bits=44)
+    res = []
+    for be in (_emu(P, emu_lib), ref_backend_cls(P)):
+        w, svc = make_service(be, P, boot_key=object())
+        rng = np.random.default_rng(3)
+        blocks = rng.integers(0, 256, (svc.Bs, 16), dtype=np.uint8)
+        rks = expand_key(KEY_B)
+        k0, k1 = svc.encrypt_round_key(rks[0]), svc.encrypt_round_key(rks[1])
+        st = svc.add_round_key(svc.encrypt_state(blocks), k0)
+        st = svc.mix_columns_ark(svc.sub_bytes(svc.shift_rows(st)), k1)
+        assert np.array_equal(svc.decrypt_state(st), A.round_fn(blocks ^ rks[0], rks[1]))
+        res.append(be.to_numpy(st.polys))
+    assert np.array_equal(res[0], res[1])
 
 
 @pytest.mark.parametrize("chunk", [1, 3, 5])

@@ -192,6 +192,12 @@ def test_bit_sliced_round_residues_equal_oracle(ref_backend_cls, cuda_lib):
     assert np.array_equal(res[0], res[1])
 
 
+def test_multiply_gather_on_gpu(ref_backend_cls, cuda_lib):
+    """fhe_mul_relin_rescale_ptrs on the B200 against the oracle, residue for residue, at a small ring and at N = 2^16"""
+    for P in (make_params(13, 7, dnum=4), make_params(16, 5)):
+        kp.check_multiply_gather(P, _gpu(P), ref_backend_cls(P))
+
+
 def test_bit_bootstrap_residues_equal_oracle(ref_backend_cls, cuda_lib):
     """the whole bit bootstrap (SlotToCoeff, ModRaise, CoeffToSlot with hoisted rotations and shared ModDowns,
     EvalMod) on the B200 against the oracle, residue for residue, at N = 2^12"""
