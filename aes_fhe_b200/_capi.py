@@ -34,12 +34,12 @@ SIGNATURES = {
     "fhe_tensor": [_P, _P, _P, _P, _P, _I, _I],
     "fhe_mul_const": [_P, _P, _P, _P, _P, _P, _I, _I, _I],
     "fhe_add_const": [_P, _P, _P, _P, _P, _P, _I, _I, _I],
-    "fhe_lincomb": [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I],
+    "fhe_lincomb": [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P],
     "fhe_mul_plain_sum": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I],
     "fhe_mul_plain_multi": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I],
     "fhe_mul_relin_rescale_ptrs": [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I],
     "fhe_bsgs_inner": [_P, _P, _P, _P, _P, _I, _P, _P, _P, _I, _I, _I, _I, _I],
-    "fhe_tensor_acc": [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I],
+    "fhe_tensor_acc": [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
     "fhe_rescale": [_P, _P, _P, _P, _I, _I],
     "fhe_mod_raise": [_P, _P, _P, _P, _I, _I],
     "fhe_automorphism": [_P, _P, _P, _P, _U64, _I],

@@ -138,6 +138,10 @@ class CudaBackend:
         """uninitialised device tensor of 64-bit residues (receive buffer for distributed keys)"""
         return self._empty(*shape)
 
+    def view_batch(self, h, lo: int, hi: int):
+        """batch elements lo..hi-1 as a VIEW: for the kernels that take a polynomial stride (fhe_lincomb, fhe_tensor_acc)"""
+        return h[:, lo:hi]
+
     def slice_batch(self, h, lo: int, hi: int):
         """batch elements lo..hi-1 as a tensor of their own: ONE copy here instead of one inside every kernel call that
         would otherwise receive the strided view (a slice of the LUT bases is used by up to nine calls)"""
@@ -425,16 +429,27 @@ class CudaBackend:
             c0 = torch.from_numpy(a.view(np.int64)).to(self.device)
         return dict(consts=dev, c0=c0, M=M, T=T, nq=nq)
 
+    def _batch_view(self, x):
+        """a tensor the strided kernels can read in place: contiguous, or a batch slice of a contiguous [2,B,L,N] tensor
+        (every polynomial's part contiguous, the two parts B * L * N words apart); anything else is materialised"""
+        if x.is_contiguous():
+            return x
+        L = x.shape[2]
+        if x.dim() == 4 and x.shape[0] == 2 and x.stride(3) == 1 and x.stride(2) == self.n and x.stride(1) == L * self.n:
+            return x
+        return x.contiguous()
+
     def lincomb(self, inputs: List, prep) -> List:
         M, T, nq = prep["M"], prep["T"], prep["nq"]
         assert len(inputs) == T
-        inputs = [x.contiguous() for x in inputs]
+        inputs = [self._batch_view(x) for x in inputs]
         bt = inputs[0].shape[1]
         ptrs = (C.c_void_p * T)(*[x.data_ptr() for x in inputs])
         nqs = (C.c_int * T)(*[x.shape[2] for x in inputs])
+        pst = (C.c_longlong * T)(*[x.stride(0) for x in inputs])
         out = self._empty(M, 2, bt, nq, self.n)
         self._call("fhe_lincomb", self._ptr(out), ptrs, nqs, self._ptr(prep["consts"]),
-                   self._ptr(prep["c0"]) if prep["c0"] is not None else None, M, T, nq, bt)
+                   self._ptr(prep["c0"]) if prep["c0"] is not None else None, M, T, nq, bt, pst)
         return [out[m] for m in range(M)]
 
     def mul_plain_sum(self, a_list: List, p_list: List, nq: int):
@@ -502,7 +517,7 @@ class CudaBackend:
         """acc [3,B,nq,N] (or None) += sum_g a_g (x) b_g ; a_g may carry more limbs than nq and
         either side may be a single ciphertext broadcast over the batch."""
         G = len(a_list)
-        a_list = [x.contiguous() for x in a_list]
+        a_list = [self._batch_view(x) for x in a_list]
         b_batch = b_list[0].shape[1]
         bt = max(b_batch, max(x.shape[1] for x in a_list))
         # the inner sums usually are consecutive slices of one fhe_lincomb output: use them in place
@@ -524,8 +539,9 @@ class CudaBackend:
             ptrs = (C.c_void_p * g)(*[x.data_ptr() for x in a_list[done:done + g]])
             nqs = (C.c_int * g)(*[x.shape[2] for x in a_list[done:done + g]])
             abs_ = (C.c_int * g)(*[x.shape[1] for x in a_list[done:done + g]])
+            pst = (C.c_longlong * g)(*[x.stride(0) for x in a_list[done:done + g]])
             self._call("fhe_tensor_acc", self._ptr(acc), ptrs, nqs, abs_, C.c_void_p(b_base + done * step), b_batch, g, nq, bt,
-                       accumulate)
+                       accumulate, pst)
             accumulate = 1
             done += g
         return acc

@@ -697,7 +697,7 @@ int fhe_add_const(fhe_ctx* c, void* s, uint64_t* o, const uint64_t* a, const uin
                   int npoly, int nq, int np) { return constop(1, c, s, o, a, c1, c2, npoly, nq, np); }
 
 int fhe_lincomb(fhe_ctx* c, void* stream, uint64_t* out, const uint64_t* const* in, const int* in_nq,
-                const double* consts, const uint64_t* c0, int M, int T, int nq, int batch) {
+                const double* consts, const uint64_t* c0, int M, int T, int nq, int batch, const long long* in_poly_stride) {
     if (bad_shape(c, nq, 0) || batch < 1 || M < 1 || T < 1 || T > FHE_LC_MAX_T || !in || !in_nq || !consts)
         return fail("fhe_lincomb: bad shape");
     LinCombIn li;
@@ -706,7 +706,7 @@ int fhe_lincomb(fhe_ctx* c, void* stream, uint64_t* out, const uint64_t* const* 
         if (t < T && nt < nq) return fail("fhe_lincomb: input has fewer limbs than the output");
         li.ptr[t] = t < T ? (const u64*)in[t] : nullptr;
         li.batch_stride[t] = (long long)nt * c->n;
-        li.poly_stride[t] = (long long)batch * nt * c->n;
+        li.poly_stride[t] = (in_poly_stride && t < T) ? in_poly_stride[t] : (long long)batch * nt * c->n;
     }
     cudaStream_t s = (cudaStream_t)stream;
     const ConstF* cf = (const ConstF*)consts;
@@ -771,7 +771,8 @@ int fhe_mul_plain_multi(fhe_ctx* c, void* stream, uint64_t* out, const uint64_t*
 }
 
 int fhe_tensor_acc(fhe_ctx* c, void* stream, uint64_t* acc, const uint64_t* const* a, const int* a_nq,
-                   const int* a_batch, const uint64_t* b, int b_batch, int G, int nq, int batch, int accumulate) {
+                   const int* a_batch, const uint64_t* b, int b_batch, int G, int nq, int batch, int accumulate,
+                   const long long* a_poly_stride) {
     if (bad_shape(c, nq, 0) || batch < 1 || G < 1 || G > FHE_LC_MAX_T || !a || !a_nq || !a_batch || !b ||
         (b_batch != batch && b_batch != 1))
         return fail("fhe_tensor_acc: bad shape");
@@ -783,7 +784,7 @@ int fhe_tensor_acc(fhe_ctx* c, void* stream, uint64_t* acc, const uint64_t* cons
         if (ab != batch && ab != 1) return fail("fhe_tensor_acc: operand batch must be 1 or the accumulator's");
         ti.a[g] = g < G ? (const u64*)a[g] : nullptr;
         ti.a_batch_stride[g] = ab == 1 ? 0 : (long long)ng * c->n;
-        ti.a_poly_stride[g] = (long long)ab * ng * c->n;
+        ti.a_poly_stride[g] = (a_poly_stride && g < G) ? a_poly_stride[g] : (long long)ab * ng * c->n;
     }
     launch(k_tensor_acc, dim3(c->n / 256, batch * nq), dim3(256), (cudaStream_t)stream, c->T, nq, batch, G, ti,
            (const u64*)b, b_batch, (u64*)acc, accumulate);

@@ -38,6 +38,8 @@ from .key_expansion import expand_key
 
 # xtime on bit planes: (2 t)_k = t_(k-1) ^ (t_7 if k in {0, 1, 3, 4}), FIPS-197 section 4.2.1 (0x1b = bits 0, 1, 3, 4)
 _XT_WITH_T7 = (1, 3, 4)
+import os as _os
+LUT_VIEWS = _os.environ.get("FHE_LUT_VIEWS") == "1"     # A/B switch: LUT inputs as strided views instead of slice copies
 
 
 # --------------------------------------------------------------------------- plain bit algebra
@@ -174,6 +176,18 @@ class AESBitService:
 
     def _slice(self, ct: Ciphertext, lo: int, hi: int) -> Ciphertext:
         return Ciphertext(self.engine, self.engine.backend.slice_batch(ct.polys, lo, hi), ct.level)
+
+    def _view(self, ct: Ciphertext, lo: int, hi: int) -> Ciphertext:
+        """batch elements lo..hi-1 for the LUT kernels (the monomials are only ever read by fhe_lincomb /
+        fhe_tensor_acc, which take a polynomial stride).  Measured on the B200 the strided form LOSES: SubBytes 311 ->
+        406 ms per AES-128 pass of two states although 60 GB of slice copies disappear (not profiled further; the
+        sixteen inputs of a sum then are slices of one tensor exactly 44 MB apart, which looks like partition
+        camping -- compact copies from the allocator do not line up like that).  So the monomials are copied;
+        LUT_VIEWS = True keeps the experiment."""
+        be = self.engine.backend
+        if LUT_VIEWS and hasattr(be, "view_batch"):
+            return Ciphertext(self.engine, be.view_batch(ct.polys, lo, hi), ct.level)
+        return self._slice(ct, lo, hi)
 
     def _cat(self, cts: Sequence[Ciphertext]) -> Ciphertext:
         e = self.engine
@@ -356,17 +370,17 @@ class AESBitService:
         pairs = [(0, 1), (0, 2), (0, 3), (1, 2), (1, 3), (2, 3)]
         pp, dp = e.multiply_gather([(src, [i for a, _ in pairs for i in R(a)])], [(src, [i for _, b in pairs for i in R(b)])], rlk)
         assert dp == 1
-        mono = {1 << j: self._slice(src, offs[j], offs[j] + bt) for j in range(4)}
+        mono = {1 << j: self._view(src, offs[j], offs[j] + bt) for j in range(4)}
         dev = {m: Fraction(1) for m in range(1, 16)}
         for n, (i, j) in enumerate(pairs):
-            mono[(1 << i) | (1 << j)] = self._slice(pp, n * bt, (n + 1) * bt)
+            mono[(1 << i) | (1 << j)] = self._view(pp, n * bt, (n + 1) * bt)
         p01, p23 = pairs.index((0, 1)), pairs.index((2, 3))
         triples = [(0b0111, p01, 2), (0b1011, p01, 3), (0b1101, p23, 0), (0b1110, p23, 1)]
         tt, d = e.multiply_gather([(pp, [i for _, n, _ in triples for i in PR(n)])], [(src, [i for _, _, j in triples for i in R(j)])], rlk)
         qd, dq = e.multiply_gather([(pp, PR(p01))], [(pp, PR(p23))], rlk)
         assert dq == 1
         for n, (m, _, _) in enumerate(triples):
-            mono[m] = self._slice(tt, n * bt, (n + 1) * bt)
+            mono[m] = self._view(tt, n * bt, (n + 1) * bt)
             dev[m] = d
         mono[0b1111] = qd
         return mono, dev

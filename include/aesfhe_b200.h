@@ -99,7 +99,11 @@ int fhe_add_const(fhe_ctx* ctx, void* stream, uint64_t* out, const uint64_t* a,
  *   c0      : device, [M][nq][2] residues added to polynomial 0, or NULL
  *   out     : M ciphertexts [2][batch][nq][N], contiguous.  No rescale is performed. */
 int fhe_lincomb(fhe_ctx* ctx, void* stream, uint64_t* out, const uint64_t* const* in, const int* in_nq,
-                const double* consts, const uint64_t* c0, int M, int T, int nq, int batch);
+                const double* consts, const uint64_t* c0, int M, int T, int nq, int batch,
+                const long long* in_poly_stride);
+/* in_poly_stride (fhe_lincomb) / a_poly_stride (fhe_tensor_acc): NULL, or per input the distance in words between its
+ * two polynomials -- an input may then be a batch slice of a larger tensor [2][B][nq_t][N] (pointer to element
+ * [0][lo], stride B * nq_t * N) and is read in place. */
 
 /* Rotate-mask-add and diagonal-matrix sums (shiftrows_service.py:41-50; the linear transforms of
  * Engine.bootstrap): out[2][batch][nq][N] (+)= sum_t a_t (.) p_t for T <= 16 terms in one pass.
@@ -133,7 +137,8 @@ int fhe_mul_plain_multi(fhe_ctx* ctx, void* stream, uint64_t* out, const uint64_
  * single ciphertext, e.g. an encrypted round key, broadcast over the batch).  One
  * fhe_keyswitch then relinearises the sum. */
 int fhe_tensor_acc(fhe_ctx* ctx, void* stream, uint64_t* acc, const uint64_t* const* a, const int* a_nq,
-                   const int* a_batch, const uint64_t* b, int b_batch, int G, int nq, int batch, int accumulate);
+                   const int* a_batch, const uint64_t* b, int b_batch, int G, int nq, int batch, int accumulate,
+                   const long long* a_poly_stride);
 
 /* Rescale after every multiply: [npoly][nq][N] -> [npoly][nq-1][N], division by q_{nq-1}
  * rounded to nearest. */

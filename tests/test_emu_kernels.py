@@ -71,10 +71,14 @@ def test_multiply_gather(log_n, lvl, dnum, emu_lib, ref_backend_cls):
     kp.check_multiply_gather(P, _emu(P, emu_lib), ref_backend_cls(P))
 
 
-def test_bit_sliced_round_on_emulator(emu_lib, ref_backend_cls):
+@pytest.mark.parametrize("views", [False, True])
+def test_bit_sliced_round_on_emulator(views, emu_lib, ref_backend_cls, monkeypatch):
     """ARK_0, ShiftRows, SubBytes, MixColumns + ARK of the bit-sliced AES path through the real kernels (gathered
-    products, fused LUT sums) against the oracle at N = 2^12: identical residues, plain AES bytes"""
+    products, fused LUT sums; views: the LUT inputs as strided batch slices, in_poly_stride of fhe_lincomb /
+    fhe_tensor_acc) against the oracle at N = 2^12: identical residues, plain AES bytes"""
     from test_aes_bits import make_service, KEY_B
+    from aes_fhe_b200.services import aes_bits
+    monkeypatch.setattr(aes_bits, "LUT_VIEWS", views)
     from aes_fhe_b200.services.key_expansion import expand_key
     from oracle import aes_plain as A
     P = make_params(12, 9, scale_bits=44)
