@@ -39,7 +39,7 @@ from .key_expansion import expand_key
 # xtime on bit planes: (2 t)_k = t_(k-1) ^ (t_7 if k in {0, 1, 3, 4}), FIPS-197 section 4.2.1 (0x1b = bits 0, 1, 3, 4)
 _XT_WITH_T7 = (1, 3, 4)
 import os as _os
-LUT_VIEWS = _os.environ.get("FHE_LUT_VIEWS") == "1"     # A/B switch: LUT inputs as strided views instead of slice copies
+LUT_VIEWS = _os.environ.get("FHE_LUT_VIEWS", "1") != "0"     # A/B switch: LUT inputs as strided views (default) or slice copies
 
 
 # --------------------------------------------------------------------------- plain bit algebra
@@ -178,12 +178,12 @@ class AESBitService:
         return Ciphertext(self.engine, self.engine.backend.slice_batch(ct.polys, lo, hi), ct.level)
 
     def _view(self, ct: Ciphertext, lo: int, hi: int) -> Ciphertext:
-        """batch elements lo..hi-1 for the LUT kernels (the monomials are only ever read by fhe_lincomb /
-        fhe_tensor_acc, which take a polynomial stride).  Measured on the B200 the strided form LOSES: SubBytes 311 ->
-        406 ms per AES-128 pass of two states although 60 GB of slice copies disappear (not profiled further; the
-        sixteen inputs of a sum then are slices of one tensor exactly 44 MB apart, which looks like partition
-        camping -- compact copies from the allocator do not line up like that).  So the monomials are copied;
-        LUT_VIEWS = True keeps the experiment."""
+        """batch elements lo..hi-1 for the LUT kernels WITHOUT a copy (the monomials are only ever read by fhe_lincomb
+        / fhe_tensor_acc, which take a polynomial stride): 60 GB of slice copies less per AES-128 pass of two states,
+        SubBytes 316 -> 304 ms in the steady state of bench.py.  (A single timed pass right after ONE warm-up pass
+        -- tools/aes_bits_probe.py -- showed 406 ms instead: the views keep the product tensors alive longer, the
+        caching allocator was still growing; tools/lut_layout_bench.py shows the kernels themselves do not care how
+        their inputs are laid out.)  LUT_VIEWS = False (FHE_LUT_VIEWS=0) restores the copies."""
         be = self.engine.backend
         if LUT_VIEWS and hasattr(be, "view_batch"):
             return Ciphertext(self.engine, be.view_batch(ct.polys, lo, hi), ct.level)
