@@ -15,6 +15,7 @@ LIB_PATH = CSRC / "libaesfhe_b200.so"
 _P = C.c_void_p
 _I = C.c_int
 _U64 = C.c_uint64
+_LL = C.c_longlong
 
 # name -> argtypes (restype is int unless listed in _RESTYPES)
 SIGNATURES = {
@@ -39,7 +40,7 @@ SIGNATURES = {
     "fhe_mul_plain_multi": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I],
     "fhe_mul_relin_rescale_ptrs": [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I],
     "fhe_bsgs_inner": [_P, _P, _P, _P, _P, _I, _P, _P, _P, _I, _I, _I, _I, _I],
-    "fhe_tensor_acc": [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
+    "fhe_tensor_acc": [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _LL, _P],
     "fhe_rescale": [_P, _P, _P, _P, _I, _I],
     "fhe_mod_raise": [_P, _P, _P, _P, _I, _I],
     "fhe_automorphism": [_P, _P, _P, _P, _U64, _I],

@@ -138,6 +138,8 @@ class CudaBackend:
         """uninitialised device tensor of 64-bit residues (receive buffer for distributed keys)"""
         return self._empty(*shape)
 
+    tensor_acc_into = True      # tensor_acc(out=..., init=...): sums written into a batch slice of a larger accumulator
+
     def view_batch(self, h, lo: int, hi: int):
         """batch elements lo..hi-1 as a VIEW: for the kernels that take a polynomial stride (fhe_lincomb, fhe_tensor_acc)"""
         return h[:, lo:hi]
@@ -513,9 +515,10 @@ class CudaBackend:
         self._call("fhe_modup", self._ptr(ext), self._ptr(d), nq, bt)
         return ext
 
-    def tensor_acc(self, acc, a_list: List, b_list: List, nq: int):
+    def tensor_acc(self, acc, a_list: List, b_list: List, nq: int, out=None, init=None):
         """acc [3,B,nq,N] (or None) += sum_g a_g (x) b_g ; a_g may carry more limbs than nq and
-        either side may be a single ciphertext broadcast over the batch."""
+        either side may be a single ciphertext broadcast over the batch.  out: a batch slice [3, lo:hi] of a larger
+        accumulator that receives the sums (acc must be None); init [2,B,nq,N]: a term the sums start from."""
         G = len(a_list)
         a_list = [self._batch_view(x) for x in a_list]
         b_batch = b_list[0].shape[1]
@@ -531,8 +534,20 @@ class CudaBackend:
             b_base = keep.data_ptr()
         accumulate = 1
         if acc is None:
-            acc = self._empty(3, bt, nq, self.n)
+            acc = self._empty(3, bt, nq, self.n) if out is None else out
             accumulate = 0
+        elif out is not None:
+            raise ValueError("tensor_acc: out and acc exclude each other")
+        if not acc.is_contiguous() and not (acc.stride(3) == 1 and acc.stride(2) == self.n and acc.stride(1) == nq * self.n
+                                            and acc.shape[2] == nq):
+            raise ValueError("tensor_acc: accumulator must be contiguous or a batch slice of a contiguous tensor")
+        acc_ps = acc.stride(0)
+        init_p = None
+        if init is not None:
+            init = self.expand_batch(init, bt).contiguous()
+            if tuple(init.shape) != (2, bt, nq, self.n):
+                raise ValueError("tensor_acc: init must be [2, batch, nq, N]")
+            init_p = self._ptr(init)
         done = 0
         while done < G:
             g = min(16, G - done)
@@ -541,7 +556,7 @@ class CudaBackend:
             abs_ = (C.c_int * g)(*[x.shape[1] for x in a_list[done:done + g]])
             pst = (C.c_longlong * g)(*[x.stride(0) for x in a_list[done:done + g]])
             self._call("fhe_tensor_acc", self._ptr(acc), ptrs, nqs, abs_, C.c_void_p(b_base + done * step), b_batch, g, nq, bt,
-                       accumulate, pst)
+                       accumulate, pst, acc_ps, init_p if done == 0 else None)
             accumulate = 1
             done += g
         return acc

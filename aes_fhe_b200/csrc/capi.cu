@@ -772,7 +772,7 @@ int fhe_mul_plain_multi(fhe_ctx* c, void* stream, uint64_t* out, const uint64_t*
 
 int fhe_tensor_acc(fhe_ctx* c, void* stream, uint64_t* acc, const uint64_t* const* a, const int* a_nq,
                    const int* a_batch, const uint64_t* b, int b_batch, int G, int nq, int batch, int accumulate,
-                   const long long* a_poly_stride) {
+                   const long long* a_poly_stride, long long acc_poly_stride, const uint64_t* init) {
     if (bad_shape(c, nq, 0) || batch < 1 || G < 1 || G > FHE_LC_MAX_T || !a || !a_nq || !a_batch || !b ||
         (b_batch != batch && b_batch != 1))
         return fail("fhe_tensor_acc: bad shape");
@@ -786,8 +786,11 @@ int fhe_tensor_acc(fhe_ctx* c, void* stream, uint64_t* acc, const uint64_t* cons
         ti.a_batch_stride[g] = ab == 1 ? 0 : (long long)ng * c->n;
         ti.a_poly_stride[g] = (a_poly_stride && g < G) ? a_poly_stride[g] : (long long)ab * ng * c->n;
     }
+    if (acc_poly_stride != 0 && acc_poly_stride < (long long)batch * nq * c->n)
+        return fail("fhe_tensor_acc: accumulator polynomial stride shorter than one polynomial");
     launch(k_tensor_acc, dim3(c->n / 256, batch * nq), dim3(256), (cudaStream_t)stream, c->T, nq, batch, G, ti,
-           (const u64*)b, b_batch, (u64*)acc, accumulate);
+           (const u64*)b, b_batch, (u64*)acc, accumulate, acc_poly_stride ? acc_poly_stride : (long long)batch * nq * c->n,
+           (const u64*)init);
     return check("fhe_tensor_acc");
 }
 

@@ -316,20 +316,24 @@ struct TensorAccIn {
     long long a_poly_stride[FHE_LC_MAX_T];
     long long a_batch_stride[FHE_LC_MAX_T];
 };
+// acc_ps: polynomial stride of acc in words (the accumulator may be a batch slice of a larger [3][B][nq][N] tensor);
+// init (optional, [2][batch][nq][N]): a 2-polynomial term the sum starts from (the constant-outer row of a LUT)
 __global__ void __launch_bounds__(256) k_tensor_acc(DevTables Tb, int nq, int batch, int G, TensorAccIn in,
-                                                    const u64* bsrc, int b_batch, u64* acc, int accumulate) {
+                                                    const u64* bsrc, int b_batch, u64* acc, int accumulate,
+                                                    long long acc_ps, const u64* init) {
     const int row = blockIdx.y;
     const int j = row % nq, b = row / nq;
     const Modulus Mo = Tb.mod[j];
     const double q = Mo.qd, qi = Mo.qinv;
     const u32 idx = blockIdx.x * 256 + threadIdx.x;
     const size_t lo = ((size_t)j << Tb.log_n) + idx;
-    const size_t ps = (size_t)batch * nq << Tb.log_n;            // poly stride of acc
+    const size_t ps = (size_t)acc_ps;                            // poly stride of acc
     const size_t bo = ((size_t)b * nq << Tb.log_n) + lo;
     const size_t bps = (size_t)b_batch * nq << Tb.log_n;         // poly stride of b_g (b_batch = batch or 1)
     const size_t bbo = ((size_t)(b % b_batch) * nq << Tb.log_n) + lo;
     double d0 = 0.0, d1 = 0.0, d2 = 0.0;
     if (accumulate) { d0 = u64_to_f(acc[bo]); d1 = u64_to_f(acc[bo + ps]); d2 = u64_to_f(acc[bo + 2 * ps]); }
+    if (init) { d0 = d_add(d0, u64_to_f(init[bo])); d1 = d_add(d1, u64_to_f(init[bo + ((size_t)batch * nq << Tb.log_n)])); }
     for (int g = 0; g < G; ++g) {
         const u64* ap = in.a[g] + (size_t)b * in.a_batch_stride[g] + lo;
         const double a0 = u64_to_f(ap[0]), a1 = u64_to_f(ap[in.a_poly_stride[g]]);

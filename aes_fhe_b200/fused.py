@@ -98,13 +98,15 @@ def _const_pair(eng, value: complex, scale: Fraction, nq: int):
 
 def _outer_sum(eng, relin_key, outer: Dict[int, Ciphertext], inner_basis: Dict[int, Ciphertext],
                coeff_mats: Sequence[np.ndarray], cache_key, outer_dev: Optional[Dict[int, Fraction]] = None,
-               inner_dev: Optional[Dict[int, Fraction]] = None) -> List[Ciphertext]:
+               inner_dev: Optional[Dict[int, Fraction]] = None, batched: bool = False):
     """sum_i outer[i] * (sum_j C[i][j] inner_basis[j]),  i = 0 meaning the constant 1 (same for
     j = 0).  ``coeff_mats`` is a list of (n_outer+1) x (n_inner+1) complex matrices; all outputs
     share the two bases.  Returns one ciphertext per matrix, two levels below the lowest
     operand.  ``outer_dev`` / ``inner_dev``: scale deviations of the basis elements (power_basis_16,
     lazy_power_basis); the constants of the inner sums are divided by them, so the outputs sit exactly on the
-    scale table."""
+    scale table.  ``batched``: return ONE ciphertext whose batch holds the outputs one after the other (what a
+    concatenation of the list would give) -- on the B200 the sums of all outputs then land in one accumulator and are
+    relinearised and rescaled together (one key switch over n_out x batch ciphertexts instead of n_out small ones)."""
     be, P = eng.backend, eng.params
     lo = min([c.level for c in outer.values()] + [c.level for c in inner_basis.values()])
     if lo < 2:
@@ -135,6 +137,18 @@ def _outer_sum(eng, relin_key, outer: Dict[int, Ciphertext], inner_basis: Dict[i
         cache[key] = prep
     inner = be.lincomb([inner_basis[j].polys for j in j_list], prep)      # one pass, all inner sums
 
+    bt = max([inner[0].shape[1]] + [c.batch for c in outer.values()])
+    per_out = [[(i, inner[r]) for r, (mm, i) in enumerate(rows) if mm == m] for m in range(n_out)]
+    if batched and getattr(be, "tensor_acc_into", False) and all(any(i for i, _ in terms) for terms in per_out):
+        acc_all = be.alloc((3, n_out * bt, nq, P.n))
+        for m, terms in enumerate(per_out):
+            zero = [t for i, t in terms if i == 0]
+            be.tensor_acc(None, [outer[i].polys for i, _ in terms if i], [t for i, t in terms if i], nq,
+                          out=acc_all[:, m * bt:(m + 1) * bt], init=zero[0] if zero else None)
+        eng._count('keyswitch_relin')
+        eng._count('rescale')
+        return eng._rescale(Ciphertext(eng, be.relin_rescale(acc_all, relin_key.data, nq), lo - 1))
+
     outs = []
     for m in range(n_out):
         a_list, b_list, acc = [], [], None
@@ -162,6 +176,8 @@ def _outer_sum(eng, relin_key, outer: Dict[int, Ciphertext], inner_basis: Dict[i
         eng._count('rescale')
         ct2 = Ciphertext(eng, be.relin_rescale(acc, relin_key.data, nq), lo - 1)
         outs.append(eng._rescale(ct2))
+    if batched:
+        return Ciphertext(eng, be.concat_batch([c.polys for c in outs]), outs[0].level)
     return outs
 
 

@@ -392,8 +392,8 @@ class AESBitService:
         bt = 4 * G
         (lo, dlo) = self._monomial_basis(state, [k * bt for k in range(4)], bt)
         (hi, dhi) = self._monomial_basis(state, [k * bt for k in range(4, 8)], bt)
-        outs = _outer_sum(self.engine, self.eng.relin_key, hi, lo, [self.W[k] for k in range(8)], ("sbox-bits",), dhi, dlo)
-        out = self._cat(outs)
+        out = _outer_sum(self.engine, self.eng.relin_key, hi, lo, [self.W[k] for k in range(8)], ("sbox-bits",), dhi, dlo,
+                         batched=True)                  # bit planes 0..7 one after the other: the state layout
         self._tick("sub_bytes")
         return out
 

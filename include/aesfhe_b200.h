@@ -138,7 +138,11 @@ int fhe_mul_plain_multi(fhe_ctx* ctx, void* stream, uint64_t* out, const uint64_
  * fhe_keyswitch then relinearises the sum. */
 int fhe_tensor_acc(fhe_ctx* ctx, void* stream, uint64_t* acc, const uint64_t* const* a, const int* a_nq,
                    const int* a_batch, const uint64_t* b, int b_batch, int G, int nq, int batch, int accumulate,
-                   const long long* a_poly_stride);
+                   const long long* a_poly_stride, long long acc_poly_stride, const uint64_t* init);
+/* acc_poly_stride: 0, or the distance in words between the polynomials of acc (acc may be a batch slice of a larger
+ * [3][B][nq][N] tensor, so that the sums of several LUT outputs land in ONE tensor and are relinearised together);
+ * init: NULL, or a 2-polynomial term [2][batch][nq][N] added to polynomials 0 and 1 (the row of a LUT whose outer
+ * factor is the constant 1). */
 
 /* Rescale after every multiply: [npoly][nq][N] -> [npoly][nq-1][N], division by q_{nq-1}
  * rounded to nearest. */
