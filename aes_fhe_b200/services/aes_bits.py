@@ -355,43 +355,50 @@ class AESBitService:
         self._tick("shift_rows")
         return out
 
-    def _monomial_basis(self, src: Ciphertext, offs: Sequence[int], bt: int):
-        """{A: prod_{j in A} bit_j} for the 15 non-empty subsets A of four +-1 bit planes, bit j = batch elements
-        offs[j] .. offs[j] + bt - 1 of `src`: the 6 pair products in one batched multiply, then the 4 triples
-        (pair x single) in another and the quadruple (pair x pair) -- 11 key switches per batch element, depth 2.  The
-        products gather their operands from `src` and from the pair products (Engine.multiply_gather: no copies of
-        slices or concatenations).  In a triple the single is one level above the pair: it is used in place (upper
-        limb ignored, an exact modulus switch) and the product's scale leaves the table by delta[l] / delta[l-1];
-        returns (monomials, scale factors) for the LUT constants to absorb."""
+    def _monomial_bases(self, src: Ciphertext, groups: Sequence[Sequence[int]], bt: int):
+        """For every group of four +-1 bit planes (bit j of a group = batch elements offs[j] .. offs[j] + bt - 1 of
+        `src`): {A: prod_{j in A} bit_j} for the 15 non-empty subsets A.  The 6 pair products of ALL groups in one batched
+        multiply, then the 4 triples (pair x single) of all groups in another and the quadruples (pair x pair) in a
+        third -- 11 key switches per batch element and group, depth 2.  The products gather their operands from `src`
+        and from the pair products (Engine.multiply_gather: no copies of slices or concatenations).  In a triple the
+        single is one level above the pair: it is used in place (upper limb ignored, an exact modulus switch) and the
+        product's scale leaves the table by delta[l] / delta[l-1]; returns [(monomials, scale factors), ...] for the
+        LUT constants to absorb."""
         from fractions import Fraction
         e, rlk = self.engine, self.eng.relin_key
-        R = lambda j: list(range(offs[j], offs[j] + bt))                             # noqa: E731
-        PR = lambda n: list(range(n * bt, (n + 1) * bt))                             # noqa: E731  pair n inside pp
+        ng = len(groups)
+        R = lambda g, j: list(range(groups[g][j], groups[g][j] + bt))                # noqa: E731
         pairs = [(0, 1), (0, 2), (0, 3), (1, 2), (1, 3), (2, 3)]
-        pp, dp = e.multiply_gather([(src, [i for a, _ in pairs for i in R(a)])], [(src, [i for _, b in pairs for i in R(b)])], rlk)
+        PR = lambda g, n: list(range((g * 6 + n) * bt, (g * 6 + n + 1) * bt))        # noqa: E731  pair n of group g inside pp
+        pp, dp = e.multiply_gather([(src, [i for g in range(ng) for a, _ in pairs for i in R(g, a)])],
+                                   [(src, [i for g in range(ng) for _, b in pairs for i in R(g, b)])], rlk)
         assert dp == 1
-        mono = {1 << j: self._view(src, offs[j], offs[j] + bt) for j in range(4)}
-        dev = {m: Fraction(1) for m in range(1, 16)}
-        for n, (i, j) in enumerate(pairs):
-            mono[(1 << i) | (1 << j)] = self._view(pp, n * bt, (n + 1) * bt)
         p01, p23 = pairs.index((0, 1)), pairs.index((2, 3))
         triples = [(0b0111, p01, 2), (0b1011, p01, 3), (0b1101, p23, 0), (0b1110, p23, 1)]
-        tt, d = e.multiply_gather([(pp, [i for _, n, _ in triples for i in PR(n)])], [(src, [i for _, _, j in triples for i in R(j)])], rlk)
-        qd, dq = e.multiply_gather([(pp, PR(p01))], [(pp, PR(p23))], rlk)
+        tt, d = e.multiply_gather([(pp, [i for g in range(ng) for _, n, _ in triples for i in PR(g, n)])],
+                                  [(src, [i for g in range(ng) for _, _, j in triples for i in R(g, j)])], rlk)
+        qd, dq = e.multiply_gather([(pp, [i for g in range(ng) for i in PR(g, p01)])],
+                                   [(pp, [i for g in range(ng) for i in PR(g, p23)])], rlk)
         assert dq == 1
-        for n, (m, _, _) in enumerate(triples):
-            mono[m] = self._view(tt, n * bt, (n + 1) * bt)
-            dev[m] = d
-        mono[0b1111] = qd
-        return mono, dev
+        out = []
+        for g in range(ng):
+            mono = {1 << j: self._view(src, groups[g][j], groups[g][j] + bt) for j in range(4)}
+            dev = {m: Fraction(1) for m in range(1, 16)}
+            for n, (i, j) in enumerate(pairs):
+                mono[(1 << i) | (1 << j)] = self._view(pp, (g * 6 + n) * bt, (g * 6 + n + 1) * bt)
+            for n, (m, _, _) in enumerate(triples):
+                mono[m] = self._view(tt, (g * 4 + n) * bt, (g * 4 + n + 1) * bt)
+                dev[m] = d
+            mono[0b1111] = self._view(qd, g * bt, (g + 1) * bt)
+            out.append((mono, dev))
+        return out
 
     def sub_bytes(self, state: Ciphertext) -> Ciphertext:
         """the S-box on every byte of the state: eight multilinear polynomials over the monomials of the high and
         the low four bits (22 + 8 key switches per (row, state), four levels)"""
         G = self._G(state)
         bt = 4 * G
-        (lo, dlo) = self._monomial_basis(state, [k * bt for k in range(4)], bt)
-        (hi, dhi) = self._monomial_basis(state, [k * bt for k in range(4, 8)], bt)
+        (lo, dlo), (hi, dhi) = self._monomial_bases(state, [[k * bt for k in range(4)], [k * bt for k in range(4, 8)]], bt)
         out = _outer_sum(self.engine, self.eng.relin_key, hi, lo, [self.W[k] for k in range(8)], ("sbox-bits",), dhi, dlo,
                          batched=True)                  # bit planes 0..7 one after the other: the state layout
         self._tick("sub_bytes")

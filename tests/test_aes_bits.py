@@ -88,7 +88,7 @@ def test_round_stages_on_oracle(ref_backend_cls):
     assert np.abs(svc.decrypt_slots(st) - (1.0 - 2.0 * svc.pack_bits(want))).max() < 1e-5
     # 1 + 22 + 8 + 140 products per state, 3 batched rotations
     n = w.engine.op_counts
-    assert n["keyswitch_galois"] == 3 and n["mul_ct"] == 1 + 6 + 1 + 3          # batched calls (pairs, triples, quadruple per nibble)
+    assert n["keyswitch_galois"] == 3 and n["mul_ct"] == 1 + 3 + 1 + 3          # batched calls (pairs, triples, quadruples of both nibbles together)
 
 
 def test_evalmod_design_for_bits_is_flat_at_the_bits():
