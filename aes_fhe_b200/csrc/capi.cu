@@ -316,8 +316,8 @@ BConvParam<NS> bconv_param(const fhe_ctx* c, const BConvTable& tb) {
 template <int NS>
 void launch_bconv_ns(fhe_ctx* c, cudaStream_t s, int groups, const BConvTable* tabs, int n_tabs, u64* dst,
                      long long dst_stride, const u64* src, long long src_stride, int g_first, int g_step) {
-    // variant 0: k_bconv (mulmod per term, table in shared memory); 1: k_bconv_dot3 (three-FMA dot product, split table in
-    // shared memory); 2: k_bconv_param (three-FMA dot product, table as kernel parameter).  env FHE_BCONV_VARIANT
+    // variant 0: k_bconv (mulmod per term, table in shared memory); 2 (default): k_bconv_param (three-FMA dot product, table
+    // as kernel parameter).  env FHE_BCONV_VARIANT
     static const int variant = getenv("FHE_BCONV_VARIANT") ? atoi(getenv("FHE_BCONV_VARIANT")) : FHE_BCONV_DEFAULT_VARIANT;
     if constexpr (NS <= 12) if (variant == 2 && g_step == n_tabs) {
         auto it = c->bconv_host.find(tabs);
@@ -336,11 +336,7 @@ void launch_bconv_ns(fhe_ctx* c, cudaStream_t s, int groups, const BConvTable* t
             return;
         }
     }
-    if (variant == 1)
-        launch(k_bconv_dot3<NS>, dim3(c->n / 256, groups), dim3(256), s, c->T, tabs, n_tabs, dst, dst_stride, src, src_stride,
-               g_first, g_step);
-    else
-        launch(k_bconv<NS>, dim3(c->n / 512, groups), dim3(256), s, c->T, tabs, n_tabs, dst, dst_stride, src, src_stride, g_first,
+    launch(k_bconv<NS>, dim3(c->n / 512, groups), dim3(256), s, c->T, tabs, n_tabs, dst, dst_stride, src, src_stride, g_first,
                g_step);
 }
 // one launch over groups g = y * g_step + g_first (y < groups) whose tables all have exactly `ns` sources

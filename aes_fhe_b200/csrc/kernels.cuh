@@ -677,70 +677,15 @@ __global__ void __launch_bounds__(256) k_bconv(DevTables T, const BConvTable* ta
     }
 }
 
-// Base conversion with the exact three-FMA dot product of modarith.cuh (dot3): the centred digits are split at 2^23 once
-// per source, the table constants once per CTA, and a term costs three FMAs (A += xh ch, B += xs cs, C += xl cl) instead
-// of the seven operations of mulmod_const + add; one reduction (dot3_finish, ~14 operations) per target.  With digits of
-// 7 and 27 targets that is 966 FP64 operations per coefficient against 1404.  One coefficient per thread (the splits of
-// the sources need 3 NS registers), two targets per iteration (six independent accumulation chains).
-// Same table, same grouping and the same canonical residues as k_bconv.            grid: (N/256, groups)
-template <int NS_MAX>
-__global__ void __launch_bounds__(256) k_bconv_dot3(DevTables T, const BConvTable* tables, int n_tables,
-                                                    u64* dst, long long dst_group_stride,
-                                                    const u64* src, long long src_block_stride, int g_first, int g_step) {
-    FHE_SHARED Split3 sf[FHE_MAX_DST * NS_MAX];
-    FHE_SHARED double sq[FHE_MAX_DST], sqi[FHE_MAX_DST];
-    FHE_SHARED int sslot[FHE_MAX_DST];
-    const int g = blockIdx.y * g_step + g_first;
-    const BConvTable& tb = tables[g % n_tables];
-    constexpr int ns = NS_MAX;
-    const int nt = tb.nt;
-    for (int i = threadIdx.x; i < nt * NS_MAX; i += 256) sf[i] = split23(tb.f[i / NS_MAX][i % NS_MAX].w);
-    for (int t = threadIdx.x; t < nt; t += 256) {
-        const Modulus M = T.mod[tb.dst_mod[t]];
-        sq[t] = M.qd; sqi[t] = M.qinv; sslot[t] = tb.dst_slot[t];
-    }
-    const int log_n = T.log_n;
-    const u32 idx = blockIdx.x * 256 + threadIdx.x;
-    const u64* s = src + (size_t)(g / n_tables) * src_block_stride + idx;
-    u64* d = dst + (size_t)g * dst_group_stride + idx;
-    u64 v[NS_MAX];
-#pragma unroll
-    for (int k = 0; k < ns; ++k) v[k] = s[(size_t)tb.src_slot[k] << log_n];
-    Split3 y[NS_MAX];
-#pragma unroll
-    for (int k = 0; k < ns; ++k) {
-        const u64 qk = T.mod[tb.src_mod[k]].q;
-        const double c = v[k] > (qk >> 1) ? d_add(u64_to_f(v[k]), -u64_to_f(qk)) : u64_to_f(v[k]);
-        y[k] = split23(c);
-    }
-    __syncthreads();
-    int t = 0;
-    for (; t + 1 < nt; t += 2) {
-        double A0 = 0.0, B0 = 0.0, C0 = 0.0, A1 = 0.0, B1 = 0.0, C1 = 0.0;
-#pragma unroll
-        for (int k = 0; k < ns; ++k) {
-            const Split3 ca = sf[t * NS_MAX + k], cb = sf[(t + 1) * NS_MAX + k];
-            A0 = d_fma(y[k].h, ca.h, A0); B0 = d_fma(y[k].s, ca.s, B0); C0 = d_fma(y[k].l, ca.l, C0);
-            A1 = d_fma(y[k].h, cb.h, A1); B1 = d_fma(y[k].s, cb.s, B1); C1 = d_fma(y[k].l, cb.l, C1);
-        }
-        d[(size_t)sslot[t] << log_n] = f_to_u64(dot3_finish(A0, B0, C0, sq[t], sqi[t]));
-        d[(size_t)sslot[t + 1] << log_n] = f_to_u64(dot3_finish(A1, B1, C1, sq[t + 1], sqi[t + 1]));
-    }
-    if (t < nt) {
-        double A0 = 0.0, B0 = 0.0, C0 = 0.0;
-#pragma unroll
-        for (int k = 0; k < ns; ++k) {
-            const Split3 ca = sf[t * NS_MAX + k];
-            A0 = d_fma(y[k].h, ca.h, A0); B0 = d_fma(y[k].s, ca.s, B0); C0 = d_fma(y[k].l, ca.l, C0);
-        }
-        d[(size_t)sslot[t] << log_n] = f_to_u64(dot3_finish(A0, B0, C0, sq[t], sqi[t]));
-    }
-}
-
-// The same three-FMA dot product with the table as a KERNEL PARAMETER: a launch converts with exactly one table (the digits
-// of a ModUp are launched one by one), so the split constants sit in the constant bank and, with the loops over targets
-// and sources fully unrolled, every FMA takes its constant as an immediate constant-bank operand -- no shared-memory
-// load per term, which is what made k_bconv_dot3 load/store bound (3 LDS per 3 FMA).  40 FP64 operations per output
+// Base conversion with the exact three-FMA dot product of modarith.cuh (dot3): the centred digits are split at 2^23
+// once per source, the table constants once per table, and a term costs three FMAs (A += xh ch, B += xs cs, C += xl cl)
+// instead of the seven operations of mulmod_const + add; one reduction (dot3_finish, ~18 operations) per target.  A first
+// form kept the split table in shared memory (k_bconv_dot3, round 2): three LDS per three FMAs made it load/store bound
+// and slower than k_bconv (7 155 against 8 084 blocks/s on the AES-128 step); it was replaced by:
+// the table as a KERNEL PARAMETER: a launch converts with exactly one table (the digits of a ModUp are launched one by
+// one), so the split constants sit in the constant bank and, with the loops over targets and sources fully unrolled,
+// every FMA takes its constant through a uniform register loaded from the constant bank -- no shared-memory load per
+// term.  40 FP64 operations per output
 // with seven sources (21 FMA, ~18 for the reduction, the splits of the sources amortised over the targets) against 54
 // in k_bconv.  C coefficients per thread (idx, idx + N/2): two for digits of up to seven limbs, one above (3 NS C
 // doubles of split sources in registers).  Same canonical residues as k_bconv.     grid: (N / (256 C), groups)
