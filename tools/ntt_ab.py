@@ -2,6 +2,11 @@
 the context is created), CUDA events on the launching stream, L2 flushed between timed iterations, outputs hashed so that the
 variants can be checked against each other.
     python tools/ntt_ab.py                      # driver: runs all variants listed in VARIANTS (edit per experiment)
+The measurement-only libraries of the last experiment (profiles/r02_ntt_experiments.md) are built by hand into
+aes_fhe_b200/csrc/variants/ (git-ignored) with the flags of aes_fhe_b200/build.py plus
+    -DFHE_NTT_DIAG_NOMEM                          -> libnomem.so         (no global data traffic)
+    -DFHE_NTT_DIAG_NOMEM -DFHE_NTT_DIAG_NOSMEM    -> libnomem_nosmem.so  (and no shared-memory exchange in the forward transform)
+A variant whose library is missing is reported as FAILED and skipped.
     python tools/ntt_ab.py --one                # worker (FHE_LIB / FHE_CHAIN_PERSIST / ... from the environment)"""
 import json
 import os
