@@ -573,7 +573,11 @@ def kernel_rooflines(be, P, G, peak, peak_kind, clocks):
         "roofline_fp64": {"kernel": "ntt_fwd_chained", "achieved": fp64_ops / (k_ms * 1e-3) / 1e9, "peak": fp64_peak,
                           "unit": "G FP64 instr/s", "frac": fp64_ops / (k_ms * 1e-3) / 1e9 / fp64_peak,
                           "peak_kind": f"64 per clk per SM x 148 SMs x {sm_mhz:.0f} MHz (median SM clock of the timed region)",
-                          "ops_per_row": fp64_ops / rows},
+                          "ops_per_row": fp64_ops / rows,
+                          # static count of the compiled kernel (profiles/r02_sass_histogram.md): 1180 FP64 instructions per
+                          # thread of 16 coefficients, twiddle products and reductions included
+                          "frac_counting_all_fp64_instructions": rows * (1180 / 16) * P.n / (k_ms * 1e-3) / 1e9 / fp64_peak,
+                          "diagnostic_builds": "profiles/r02_ntt_experiments.md: data movement costs 17 % of the kernel"},
         "roofline_keyswitch_inner": {"kernel": "k_ks_inner", "bound": "hbm", "achieved": ks_bytes / (ks_ms * 1e-3) / 1e9,
                                      "peak": peak, "unit": "GB/s", "frac": ks_bytes / (ks_ms * 1e-3) / 1e9 / peak,
                                      "us": ks_ms * 1e3, "algorithmic_bytes": int(ks_bytes)}}
