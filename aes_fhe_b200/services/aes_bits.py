@@ -8,11 +8,15 @@ s = (-1)^bit, so that
     (/root/reference/xor_service.py:271-286), evaluated by the same fused schedule (aes_fhe_b200/fused.py:
     constant-only inner sums in one pass, lazily relinearised outer sums): 22 + 8 key switches, four levels,
     first-order error gain <= 8 (every partial derivative of a multilinear +-1 function is in {-1, 0, 1}),
-  * the once-per-round refresh is the *bit bootstrap* of aes_fhe_b200/bootstrap.py (``bootstrap_bits``):
+  * the refresh -- wherever the levels run out: six times per AES-128 on the default 26-level chain, before rounds
+    4..9 (plan_levels) -- is the *bit bootstrap* of aes_fhe_b200/bootstrap.py (``bootstrap_bits``):
     SlotToCoeff at the bottom of the chain, ModRaise with the bits at +- q_0 / 4, CoeffToSlot, and
     EvalMod = sin(2 pi x) whose derivative vanishes exactly there -- the refresh squares the incoming
     error, so no separate clean-up polynomial is needed, and two real ciphertexts share one bootstrap
-    (real and imaginary part).
+    (real and imaginary part),
+  * every batched product gathers its operands (row rolls, bit-plane slices, replications, concatenations) through
+    a pointer table (Engine.multiply_gather) instead of materialising them, the eight S-box sums of a round are
+    relinearised in one key switch, and the last round is polished on the way out (final_round_key).
 
 This replaces the zeta_16 nibble-pair pipeline of services/aes128.py (116 refreshed ciphertexts per
 2048 blocks, 5-level LUT layers with error gain 18) for the AES-128 throughput path; the reference's

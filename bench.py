@@ -8,8 +8,8 @@ Workload (BASELINE.json configs[4]; the metric "homomorphic AES-128 blocks/sec")
 ten rounds (SubBytes, ShiftRows, MixColumns, AddRoundKey; the functions of the reference's round drivers
 /root/reference/test_all_process.py:21-48 and /root/reference/new.py:186-227,248-261), round keys from the clear
 FIPS-197 key schedule encrypted bit by bit -- at N = 2^16 on G *states* per GPU.  One state = 8192 AES blocks in 32
-bit-plane ciphertexts (aes_fhe_b200/services/aes_bits.py); every round ends in one bit bootstrap of the state
-(aes_fhe_b200/bootstrap.py::bootstrap_bits).  Parameter set: the default bootstrappable engine, 26 levels at a
+bit-plane ciphertexts (aes_fhe_b200/services/aes_bits.py); the state is refreshed by a bit bootstrap wherever the
+levels run out (aes_fhe_b200/bootstrap.py::bootstrap_bits; six times per AES-128: `config.refresh_before_rounds`).  Parameter set: the default bootstrappable engine, 26 levels at a
 44-bit scale, 27 + 7 limbs, log2(PQ) = 1504 (inside the 1553-bit bound for the sparse secret, params.py).
 
 A "step" is one AES-128 pass over the G states of a rank.  `value` = AES blocks per second with the input
