@@ -54,6 +54,7 @@ def main():
     ap.add_argument("--scale-bits", type=int, default=44)
     ap.add_argument("--groups", default="3,3")
     ap.add_argument("--rounds", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=2)
     ap.add_argument("--fresh-level", type=int, default=None)
     ap.add_argument("--dnum", type=int, default=0)
     ap.add_argument("--nvtx", action="store_true",
@@ -83,8 +84,9 @@ def main():
     plan = svc.plan_levels(fresh, args.rounds)
     st = svc.encrypt_state(blocks, level=fresh)
     rkeys = svc.encrypt_round_keys(key, G, plan, rounds=args.rounds)
-    out = svc.encrypt_blocks(st, key, rounds=args.rounds, round_keys=rkeys)            # warm-up: keys, matrices, tables
-    torch.cuda.synchronize()
+    for _ in range(max(1, args.warmup)):                                               # warm-up: keys, matrices, tables, and the
+        out = svc.encrypt_blocks(st, key, rounds=args.rounds, round_keys=rkeys)        # caching allocator's growth (one pass is not
+    torch.cuda.synchronize()                                                           # enough after a change of tensor lifetimes)
     setup = time.time() - t0
     c0, r0 = dict(w.engine.op_counts), svc.refreshes
     l0 = w.engine.backend.launch_count()

@@ -6,7 +6,7 @@
 #   gpurun --timeout 2400 -- 'bash tools/run_ncu_kernels.sh r02'
 tag=${1:-r02}
 mkdir -p gpurun_out
-cmd="python tools/aes_bits_probe.py --states 1 --rounds 4 --nvtx"
+cmd="python tools/aes_bits_probe.py --states 1 --rounds 4 --warmup 1 --nvtx"
 timeout 600 $cmd > gpurun_out/ncu_plain.log 2>&1 || { echo plain run failed; tail -5 gpurun_out/ncu_plain.log; exit 1; }
 timeout 1500 ncu --set full --clock-control none --nvtx --nvtx-include "after_boot_mod_raise/" \
    -k regex:"ntt_fwd_chained|ntt_inv_chained|k_bconv|k_bsgs_inner|k_ks_inner" -c 14 \
